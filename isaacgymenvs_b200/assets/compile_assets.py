@@ -1,0 +1,33 @@
+"""Regenerate compiled/*.json from the reference asset tree (run in the build container):
+    python -m isaacgymenvs_b200.assets.compile_assets [/root/reference/assets]
+AssetOptions per file are the ones the reference tasks pass:
+ant.py:149-152, humanoid.py:152-157, cartpole.py:84-88, anymal_terrain.py:218-231."""
+import os
+import sys
+from ..importer.model import BuildOptions, DRIVE_EFFORT
+from ..importer.mjcf import load_mjcf
+from ..importer.urdf import load_urdf
+
+SPECS = {
+    "ant": ("mjcf/nv_ant.xml", BuildOptions()),
+    "humanoid": ("mjcf/nv_humanoid.xml", BuildOptions(angular_damping=0.01)),
+    "cartpole": ("urdf/cartpole.urdf", BuildOptions(fix_base_link=True)),
+    "anymal": ("urdf/anymal_c/urdf/anymal_minimal.urdf",
+               BuildOptions(collapse_fixed_joints=True, replace_cylinder_with_capsule=True, density=0.001,
+                            default_dof_drive_mode=DRIVE_EFFORT)),
+}
+
+
+def main(root="/root/reference/assets"):
+    out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "compiled")
+    os.makedirs(out, exist_ok=True)
+    for name, (rel, opts) in SPECS.items():
+        path = os.path.join(root, rel)
+        m = load_urdf(path, opts, name=name) if rel.endswith(".urdf") else load_mjcf(path, opts, name=name)
+        with open(os.path.join(out, name + ".json"), "w") as f:
+            f.write(m.to_json())
+        print(f"{name}: links={m.nl} bodies={m.nb} dofs={m.ndof} contact_points={len(m.cp_link)} mass={m.total_mass():.5f}")
+
+
+if __name__ == "__main__":
+    main(*sys.argv[1:])

@@ -1,0 +1,403 @@
+"""Articulation model: the compiled, flat description of one actor asset that the CUDA engine,
+the C oracle and the `gym.get_asset_*` queries all read.
+
+The reference's importer lives inside the closed `isaacgym` binary, so the
+semantics below are restated from the asset files themselves and the call sites that query them
+(`isaacgymenvs/tasks/ant.py:149-212`, `humanoid.py:152-207`, `cartpole.py:84-113`).
+
+Internal convention ("links"): every DOF is its own 1-DOF link (hinge or slide).  A body carrying
+several joints (MJCF compound joints, `nv_humanoid.xml:53-54`) becomes a chain of links of which
+only the last has mass; jointless child bodies are welded into their parent's link but stay
+visible as *bodies* (the reference counts them: Humanoid has 16 rigid bodies, `humanoid.py:158`).
+Link frame i: origin at the joint anchor, axes = the body's axes.  DOF k drives link k+1.
+"""
+from dataclasses import dataclass, field
+import json
+import numpy as np
+
+from . import rot
+
+JOINT_HINGE, JOINT_SLIDE = 0, 1
+GEOM_SPHERE, GEOM_CAPSULE, GEOM_BOX, GEOM_CYLINDER, GEOM_ELLIPSOID = 0, 1, 2, 3, 4
+DRIVE_NONE, DRIVE_POS, DRIVE_VEL, DRIVE_EFFORT = 0, 1, 2, 3  # gymapi.DOF_MODE_* order
+
+
+# --------------------------------------------------------------------------- intermediate tree
+@dataclass
+class IRJoint:
+    name: str
+    jtype: int
+    axis: np.ndarray
+    anchor: np.ndarray            # in the body frame
+    lower: float = 0.0
+    upper: float = 0.0
+    limited: bool = False
+    armature: float = 0.0
+    damping: float = 0.0
+    stiffness: float = 0.0
+    effort: float = 1e30          # URDF <limit effort>
+    velocity: float = 1e30
+    friction: float = 0.0
+
+
+@dataclass
+class IRGeom:
+    name: str
+    gtype: int
+    pos: np.ndarray
+    R: np.ndarray
+    size: np.ndarray              # sphere (r,), capsule/cylinder (r, half_len) along local z, box half-sizes
+    density: float = 1000.0
+    mass: float = -1.0            # explicit geom mass overrides density
+    friction: float = 1.0
+    collide: bool = True
+
+
+@dataclass
+class IRBody:
+    name: str
+    pos: np.ndarray
+    R: np.ndarray
+    joints: list = field(default_factory=list)
+    geoms: list = field(default_factory=list)
+    inertial: tuple = None        # (mass, com(3), I_com 3x3 in body axes) or None -> from geoms
+    children: list = field(default_factory=list)
+    sites: dict = field(default_factory=dict)
+    collapsed: bool = False       # jointless body merged away (URDF collapse_fixed_joints)
+
+
+def geom_mass_inertia(g):
+    """Mass, inertia (3x3 about the geom centre, geom axes) of a primitive of uniform density."""
+    t, s = g.gtype, g.size
+    if t == GEOM_SPHERE:
+        r = s[0]
+        v = 4.0 / 3.0 * np.pi * r ** 3
+        m = g.mass if g.mass >= 0 else g.density * v
+        return m, np.eye(3) * (0.4 * m * r * r)
+    if t == GEOM_CAPSULE:
+        r, l = s[0], s[1]
+        vc, vs = np.pi * r * r * 2 * l, 4.0 / 3.0 * np.pi * r ** 3
+        m = g.mass if g.mass >= 0 else g.density * (vc + vs)
+        mc, ms = m * vc / (vc + vs), m * vs / (vc + vs)
+        izz = mc * r * r / 2 + ms * 0.4 * r * r
+        ixx = mc * (r * r / 4 + l * l / 3) + ms * (0.4 * r * r + l * l + 0.75 * l * r)
+        return m, np.diag([ixx, ixx, izz])
+    if t == GEOM_CYLINDER:
+        r, l = s[0], s[1]
+        m = g.mass if g.mass >= 0 else g.density * np.pi * r * r * 2 * l
+        return m, np.diag([m * (3 * r * r + 4 * l * l) / 12] * 2 + [m * r * r / 2])
+    if t == GEOM_BOX:
+        a, b, c = s
+        m = g.mass if g.mass >= 0 else g.density * 8 * a * b * c
+        return m, np.diag([m * (b * b + c * c) / 3, m * (a * a + c * c) / 3, m * (a * a + b * b) / 3])
+    if t == GEOM_ELLIPSOID:
+        a, b, c = s
+        m = g.mass if g.mass >= 0 else g.density * 4.0 / 3.0 * np.pi * a * b * c
+        return m, np.diag([m * (b * b + c * c) / 5, m * (a * a + c * c) / 5, m * (a * a + b * b) / 5])
+    raise ValueError(f"geom type {t}")
+
+
+def combine_inertia(parts):
+    """parts: list of (m, com(3), I_com(3x3)) in one frame -> (m, com, I_com)."""
+    M = sum(p[0] for p in parts)
+    if M <= 0:
+        return 0.0, np.zeros(3), np.zeros((3, 3))
+    c = sum(p[0] * p[1] for p in parts) / M
+    I = np.zeros((3, 3))
+    for m, pc, Ic in parts:
+        d = pc - c
+        I += Ic + m * ((d @ d) * np.eye(3) - np.outer(d, d))
+    return M, c, I
+
+
+# --------------------------------------------------------------------------- compiled model
+@dataclass
+class Model:
+    name: str = ""
+    root_fixed: bool = False
+    # links
+    parent: np.ndarray = None     # (nl,) int, -1 for the root
+    jtype: np.ndarray = None      # (nl,) int, -1 for the root
+    axis: np.ndarray = None       # (nl,3) unit, link frame
+    lpos: np.ndarray = None       # (nl,3) link origin in the parent link frame at q=0
+    lquat: np.ndarray = None      # (nl,4) xyzw link orientation in the parent link frame at q=0
+    mass: np.ndarray = None
+    com: np.ndarray = None        # (nl,3) link frame
+    inertia: np.ndarray = None    # (nl,6) xx,yy,zz,xy,xz,yz about the COM, link axes
+    # per-DOF (index = link index, entry 0 unused)
+    armature: np.ndarray = None
+    damping: np.ndarray = None
+    stiffness: np.ndarray = None
+    lower: np.ndarray = None
+    upper: np.ndarray = None
+    limited: np.ndarray = None
+    effort: np.ndarray = None
+    velocity: np.ndarray = None
+    kp: np.ndarray = None
+    kd: np.ndarray = None
+    drive_mode: np.ndarray = None
+    limit_k: np.ndarray = None    # joint-limit penalty spring / damper (DESIGN.md "joint limits")
+    limit_d: np.ndarray = None
+    # bodies (public numbering)
+    body_names: list = None
+    body_link: np.ndarray = None  # (nb,)
+    body_pos: np.ndarray = None   # (nb,3) body frame in its link frame
+    body_quat: np.ndarray = None  # (nb,4)
+    dof_names: list = None
+    # collision primitives (for queries / non-plane contact) and plane contact points
+    geom_names: list = None
+    geom_type: np.ndarray = None
+    geom_link: np.ndarray = None
+    geom_body: np.ndarray = None
+    geom_pos: np.ndarray = None   # (ng,3) link frame
+    geom_quat: np.ndarray = None
+    geom_size: np.ndarray = None  # (ng,3)
+    geom_friction: np.ndarray = None
+    cp_link: np.ndarray = None    # (ncp,) contact spheres tested against plane / heightfield
+    cp_pos: np.ndarray = None     # (ncp,3) link frame
+    cp_radius: np.ndarray = None
+    cp_mu: np.ndarray = None
+    cp_body: np.ndarray = None
+    # force sensors (body frame), actuators, tendons
+    sensor_body: np.ndarray = None
+    sensor_pos: np.ndarray = None
+    sensor_quat: np.ndarray = None
+    actuator_names: list = None
+    actuator_joint: list = None   # dof names
+    actuator_gear: np.ndarray = None
+    actuator_kp: np.ndarray = None
+    actuator_forcerange: np.ndarray = None  # (na,2)
+    actuator_kind: list = None    # 'motor' | 'position'
+    tendons: list = None          # [{name, dofs:[..], coefs:[..], range:[lo,hi], limited}]
+    # penalty-contact parameters (see DESIGN.md "contact model")
+    contact_kn: float = 0.0
+    contact_cn: float = 0.0
+    contact_vs: float = 0.02
+    gravity_on: bool = True
+    default_root_pos: np.ndarray = None  # body pose from the file (Ant overrides it at create_actor)
+    default_root_quat: np.ndarray = None
+
+    @property
+    def nl(self):
+        return len(self.parent)
+
+    @property
+    def ndof(self):
+        return self.nl - 1
+
+    @property
+    def nb(self):
+        return len(self.body_names)
+
+    def total_mass(self):
+        return float(np.sum(self.mass))
+
+    def depth(self):
+        d = np.zeros(self.nl, dtype=int)
+        for i in range(1, self.nl):
+            d[i] = d[self.parent[i]] + 1
+        return d
+
+    # ---- (de)serialisation: committed under assets/compiled/*.json so the GPU box, which has no
+    # /root/reference, can build the same model
+    def to_json(self):
+        out = {}
+        for k, v in self.__dict__.items():
+            if isinstance(v, np.ndarray):
+                out[k] = {"__nd__": v.tolist(), "dtype": str(v.dtype)}
+            else:
+                out[k] = v
+        return json.dumps(out, indent=None, separators=(",", ":"))
+
+    @staticmethod
+    def from_json(s):
+        d = json.loads(s)
+        m = Model()
+        for k, v in d.items():
+            if isinstance(v, dict) and "__nd__" in v:
+                v = np.array(v["__nd__"], dtype=v["dtype"])
+                if v.ndim == 1 and v.size == 0:
+                    pass
+            setattr(m, k, v)
+        return m
+
+
+def finalize_limits(m: "Model", pen_rad=0.02, tau_s=0.01):
+    """Joint-limit penalty gains: the strongest torque the DOF can see (actuator gear / URDF effort,
+    at least 1) is met at `pen_rad` of penetration; damping time constant `tau_s`.  The terms are
+    integrated implicitly, so the choice affects stiffness, not stability."""
+    strength = np.ones(m.nl)
+    for k, jn in enumerate(m.actuator_joint or []):
+        li = m.dof_names.index(jn) + 1
+        g = abs(m.actuator_gear[k]) if m.actuator_kind[k] == "motor" else abs(m.actuator_forcerange[k][1])
+        if g < 1e29:
+            strength[li] = max(strength[li], g)
+    eff = np.where(m.effort < 1e29, m.effort, 0.0)
+    strength = np.maximum(strength, eff)
+    scale = np.where(m.jtype == JOINT_SLIDE, 10.0, 1.0)   # slide limits: N/m, stiffer per unit
+    m.limit_k = strength / pen_rad * scale
+    m.limit_d = m.limit_k * tau_s
+    m.limit_k[0] = m.limit_d[0] = 0.0
+
+
+@dataclass
+class BuildOptions:
+    """Subset of gymapi.AssetOptions that changes the compiled model (SURVEY.md §8b 'assets')."""
+    fix_base_link: bool = False
+    collapse_fixed_joints: bool = False
+    replace_cylinder_with_capsule: bool = False
+    armature: float = 0.0             # added to every DOF (AssetOptions.armature)
+    density: float = 1000.0           # used when a body has neither <inertial> nor a geom density
+    angular_damping: float = 0.0
+    linear_damping: float = 0.0
+    disable_gravity: bool = False
+    default_dof_drive_mode: int = DRIVE_NONE
+    contact_kn_per_kg: float = 2000.0  # kn = 2000 s^-2 * actor mass
+    contact_zeta: float = 1.0
+
+
+def build_model(name, root: IRBody, has_free_root: bool, opts: BuildOptions) -> Model:
+    """Flatten an IR body tree (file order DFS = the reference's DOF/body order) into a Model."""
+    L = dict(parent=[], jtype=[], axis=[], lpos=[], lquat=[], parts=[], jref=[])
+    bodies = dict(names=[], link=[], pos=[], quat=[])
+    geoms = []
+    sites = {}
+
+    def new_link(parent, jt, axis, lpos, R, j):
+        L["parent"].append(parent); L["jtype"].append(jt)
+        L["axis"].append(np.zeros(3) if axis is None else np.asarray(axis, float) / np.linalg.norm(axis))
+        L["lpos"].append(np.asarray(lpos, float)); L["lquat"].append(rot.mat_to_quat(R))
+        L["parts"].append([]); L["jref"].append(j)
+        return len(L["parent"]) - 1
+
+    def visit(b: IRBody, link, p_lb, R_lb, is_root, parent_bi=-1):
+        # (p_lb, R_lb): pose of b's *parent body frame* expressed in link `link`
+        if is_root:
+            li = new_link(-1, -1, None, np.zeros(3), np.eye(3), None)
+            p_b, R_b = np.zeros(3), np.eye(3)
+        else:
+            p0 = p_lb + R_lb @ b.pos          # body frame at q=0, in `link`
+            R0 = R_lb @ b.R
+            if b.joints:
+                li, prev_anchor = link, None
+                for k, j in enumerate(b.joints):
+                    if k == 0:
+                        li = new_link(link, j.jtype, j.axis, p0 + R0 @ j.anchor, R0, j)
+                    else:
+                        li = new_link(li, j.jtype, j.axis, j.anchor - prev_anchor, np.eye(3), j)
+                    prev_anchor = j.anchor
+                p_b, R_b = -prev_anchor, np.eye(3)
+            else:
+                li, p_b, R_b = link, p0, R0
+        if b.collapsed and not b.joints and not is_root:
+            bi = parent_bi
+        else:
+            bodies["names"].append(b.name); bodies["link"].append(li)
+            bodies["pos"].append(p_b); bodies["quat"].append(rot.mat_to_quat(R_b))
+            bi = len(bodies["names"]) - 1
+        # inertia of this body, expressed in link li
+        if b.inertial is not None:
+            m, c, I = b.inertial
+            parts = [(m, np.asarray(c, float), np.asarray(I, float))]
+        else:
+            parts = []
+            for g in b.geoms:
+                m, Ig = geom_mass_inertia(g)
+                parts.append((m, g.pos, g.R @ Ig @ g.R.T))
+        for m, c, I in parts:
+            L["parts"][li].append((m, p_b + R_b @ c, R_b @ I @ R_b.T))
+        for g in b.geoms:
+            if g.collide:
+                geoms.append((g, li, bi, p_b + R_b @ g.pos, R_b @ g.R))
+        for sname, spos in b.sites.items():
+            sites[sname] = (bi, spos)
+        for ch in b.children:
+            visit(ch, li, p_b, R_b, False, bi)
+
+    visit(root, -1, np.zeros(3), np.eye(3), True)
+
+    nl = len(L["parent"])
+    m = Model(name=name, root_fixed=(opts.fix_base_link or not has_free_root))
+    m.parent = np.array(L["parent"], dtype=np.int32)
+    m.jtype = np.array(L["jtype"], dtype=np.int32)
+    m.axis = np.array(L["axis"]); m.lpos = np.array(L["lpos"]); m.lquat = np.array(L["lquat"])
+    mass, com, inertia = np.zeros(nl), np.zeros((nl, 3)), np.zeros((nl, 6))
+    for i in range(nl):
+        M, c, I = combine_inertia(L["parts"][i])
+        mass[i], com[i], inertia[i] = M, c, rot.mat_to_sym6(I)
+    m.mass, m.com, m.inertia = mass, com, inertia
+
+    def jattr(f, default=0.0):
+        return np.array([default if j is None else getattr(j, f) for j in L["jref"]], dtype=np.float64)
+    m.armature = jattr("armature") + np.where(m.jtype >= 0, opts.armature, 0.0)
+    m.damping, m.stiffness = jattr("damping"), jattr("stiffness")
+    m.lower, m.upper = jattr("lower"), jattr("upper")
+    m.limited = np.array([0 if j is None else int(j.limited) for j in L["jref"]], dtype=np.int32)
+    m.effort, m.velocity = jattr("effort", 1e30), jattr("velocity", 1e30)
+    m.kp, m.kd = np.zeros(nl), np.zeros(nl)
+    m.drive_mode = np.full(nl, opts.default_dof_drive_mode, dtype=np.int32)
+    m.dof_names = [j.name for j in L["jref"][1:]]
+    m.body_names = bodies["names"]
+    m.body_link = np.array(bodies["link"], dtype=np.int32)
+    m.body_pos, m.body_quat = np.array(bodies["pos"]), np.array(bodies["quat"])
+
+    # collision primitives + plane contact points
+    gt, gl, gb, gp, gq, gs, gf, gn = [], [], [], [], [], [], [], []
+    cps = []
+    for g, li, bi, p, R in geoms:
+        t = g.gtype
+        if t == GEOM_CYLINDER and opts.replace_cylinder_with_capsule:
+            t = GEOM_CAPSULE
+        size = np.zeros(3); size[:len(g.size)] = g.size
+        gt.append(t); gl.append(li); gb.append(bi); gp.append(p); gq.append(rot.mat_to_quat(R))
+        gs.append(size); gf.append(g.friction); gn.append(g.name)
+        z = R[:, 2]
+        if t == GEOM_SPHERE:
+            cps.append((li, bi, p, size[0], g.friction))
+        elif t in (GEOM_CAPSULE, GEOM_CYLINDER):
+            cps.append((li, bi, p - z * size[1], size[0], g.friction))
+            cps.append((li, bi, p + z * size[1], size[0], g.friction))
+        elif t == GEOM_BOX:
+            for sx in (-1, 1):
+                for sy in (-1, 1):
+                    for sz in (-1, 1):
+                        cps.append((li, bi, p + R @ (size * np.array([sx, sy, sz])), 0.0, g.friction))
+        elif t == GEOM_ELLIPSOID:
+            cps.append((li, bi, p, float(np.min(size)), g.friction))
+    # drop contact spheres wholly inside another contact sphere of the same link (e.g. the Ant's
+    # aux-capsule ends at the torso centre, nv_ant.xml:42-45) and exact duplicates
+    keep = []
+    for a, ca in enumerate(cps):
+        inside = False
+        for b_, cb in enumerate(cps):
+            if a == b_ or ca[0] != cb[0]:
+                continue
+            d = np.linalg.norm(ca[2] - cb[2])
+            if d + ca[3] <= cb[3] + 1e-12 and (ca[3] < cb[3] or a > b_):
+                inside = True
+                break
+        if not inside:
+            keep.append(ca)
+    m.geom_names = gn
+    m.geom_type = np.array(gt, dtype=np.int32); m.geom_link = np.array(gl, dtype=np.int32)
+    m.geom_body = np.array(gb, dtype=np.int32)
+    m.geom_pos = np.array(gp).reshape(-1, 3); m.geom_quat = np.array(gq).reshape(-1, 4)
+    m.geom_size = np.array(gs).reshape(-1, 3); m.geom_friction = np.array(gf, dtype=np.float64)
+    m.cp_link = np.array([c[0] for c in keep], dtype=np.int32)
+    m.cp_body = np.array([c[1] for c in keep], dtype=np.int32)
+    m.cp_pos = np.array([c[2] for c in keep]).reshape(-1, 3)
+    m.cp_radius = np.array([c[3] for c in keep], dtype=np.float64)
+    m.cp_mu = np.array([c[4] for c in keep], dtype=np.float64)
+
+    m.sensor_body = np.zeros(0, dtype=np.int32)
+    m.sensor_pos = np.zeros((0, 3)); m.sensor_quat = np.zeros((0, 4))
+    m.actuator_names, m.actuator_joint, m.actuator_kind = [], [], []
+    m.actuator_gear = np.zeros(0); m.actuator_kp = np.zeros(0); m.actuator_forcerange = np.zeros((0, 2))
+    m.tendons = []
+    M = m.total_mass()
+    m.contact_kn = opts.contact_kn_per_kg * M
+    m.contact_cn = 2.0 * opts.contact_zeta * np.sqrt(m.contact_kn * M / 4.0)
+    m.gravity_on = not opts.disable_gravity
+    m.default_root_pos = np.asarray(root.pos, float)
+    m.default_root_quat = rot.mat_to_quat(root.R)
+    return m

@@ -1,0 +1,115 @@
+"""URDF -> IR body tree -> Model (Cartpole `assets/urdf/cartpole.urdf`, ANYmal
+`assets/urdf/anymal_c/urdf/anymal_minimal.urdf`, `assets/urdf/objects/cube_multicolor.urdf`).
+
+URDF semantics (published format): a joint's <origin> places the child link frame in the parent
+link frame; <axis> is expressed in the child frame; `continuous` = unlimited revolute; fixed joints
+weld and, with AssetOptions.collapse_fixed_joints (`anymal_terrain.py:220`), disappear from the
+body list.  A link with a mass but no <inertia> (cartpole.urdf:34-36,55-58) takes the inertia of
+its collision primitives scaled to that mass; a link with no <inertial> takes
+AssetOptions.density over its collision primitives.
+"""
+import xml.etree.ElementTree as ET
+import numpy as np
+
+from . import rot
+from .model import (IRBody, IRGeom, IRJoint, BuildOptions, build_model, combine_inertia, finalize_limits,
+                    geom_mass_inertia, JOINT_HINGE, JOINT_SLIDE, GEOM_SPHERE, GEOM_BOX, GEOM_CYLINDER)
+
+
+def _f(s, n=3):
+    return np.array([float(x) for x in s.split()], dtype=np.float64) if s else np.zeros(n)
+
+
+def _origin(e):
+    o = e.find("origin") if e is not None else None
+    if o is None:
+        return np.zeros(3), np.eye(3)
+    return _f(o.attrib.get("xyz"), 3), rot.rpy_to_mat(_f(o.attrib.get("rpy"), 3))
+
+
+def load_urdf(path, opts: BuildOptions = None, name=None):
+    opts = opts or BuildOptions()
+    root = ET.parse(path).getroot()
+    links = {l.attrib["name"]: l for l in root.findall("link")}
+    joints = root.findall("joint")
+    children = {}
+    child_names = set()
+    for j in joints:
+        children.setdefault(j.find("parent").attrib["link"], []).append(j)
+        child_names.add(j.find("child").attrib["link"])
+    roots = [n for n in links if n not in child_names]
+    if len(roots) != 1:
+        raise ValueError(f"{path}: expected one root link, got {roots}")
+
+    def make_body(lname, pos, R, joint_elem):
+        le = links[lname]
+        b = IRBody(name=lname, pos=pos, R=R)
+        for ce in le.findall("collision"):
+            gpos, gR = _origin(ce)
+            ge = ce.find("geometry")
+            if ge.find("box") is not None:
+                g = IRGeom("", GEOM_BOX, gpos, gR, 0.5 * _f(ge.find("box").attrib["size"]))
+            elif ge.find("sphere") is not None:
+                g = IRGeom("", GEOM_SPHERE, gpos, gR, np.array([float(ge.find("sphere").attrib["radius"])]))
+            elif ge.find("cylinder") is not None:
+                c = ge.find("cylinder").attrib
+                g = IRGeom("", GEOM_CYLINDER, gpos, gR, np.array([float(c["radius"]), 0.5 * float(c["length"])]))
+            else:
+                continue  # mesh collision: not a primitive
+            g.density = opts.density
+            g.name = f"{lname}_col{len(b.geoms)}"
+            b.geoms.append(g)
+        ie = le.find("inertial")
+        if ie is not None and ie.find("mass") is not None:
+            mass = float(ie.find("mass").attrib["value"])
+            ipos, iR = _origin(ie)
+            ine = ie.find("inertia")
+            if ine is not None:
+                a = ine.attrib
+                I = np.array([[float(a["ixx"]), float(a["ixy"]), float(a["ixz"])],
+                              [float(a["ixy"]), float(a["iyy"]), float(a["iyz"])],
+                              [float(a["ixz"]), float(a["iyz"]), float(a["izz"])]])
+                b.inertial = (mass, ipos, iR @ I @ iR.T)
+            else:
+                parts = []
+                for g in b.geoms:
+                    m, Ig = geom_mass_inertia(g)
+                    parts.append((m, g.pos, g.R @ Ig @ g.R.T))
+                M, c, I = combine_inertia(parts)
+                if M > 0:
+                    b.inertial = (mass, ipos, I * (mass / M))
+                else:
+                    b.inertial = (mass, ipos, np.eye(3) * 1e-6 * mass)
+        elif not b.geoms:
+            b.inertial = (0.0, np.zeros(3), np.zeros((3, 3)))
+        if joint_elem is not None:
+            jt = joint_elem.attrib["type"]
+            if jt in ("revolute", "continuous", "prismatic"):
+                lim = joint_elem.find("limit")
+                dyn = joint_elem.find("dynamics")
+                ax = joint_elem.find("axis")
+                la = lim.attrib if lim is not None else {}
+                b.joints.append(IRJoint(
+                    name=joint_elem.attrib["name"],
+                    jtype=JOINT_SLIDE if jt == "prismatic" else JOINT_HINGE,
+                    axis=_f(ax.attrib["xyz"]) if ax is not None else np.array([1.0, 0, 0]),
+                    anchor=np.zeros(3),
+                    lower=float(la.get("lower", 0.0)), upper=float(la.get("upper", 0.0)),
+                    limited=(jt != "continuous" and "lower" in la),
+                    effort=float(la.get("effort", 1e30)), velocity=float(la.get("velocity", 1e30)),
+                    damping=float(dyn.attrib.get("damping", 0.0)) if dyn is not None else 0.0,
+                    friction=float(dyn.attrib.get("friction", 0.0)) if dyn is not None else 0.0))
+            elif jt == "fixed":
+                b.collapsed = opts.collapse_fixed_joints
+            else:
+                raise ValueError(f"URDF joint type {jt} not supported")
+        for j in children.get(lname, []):
+            jpos, jR = _origin(j)
+            b.children.append(make_body(j.find("child").attrib["link"], jpos, jR, j))
+        return b
+
+    irroot = make_body(roots[0], np.zeros(3), np.eye(3), None)
+    model = build_model(name or root.attrib.get("name", "urdf"), irroot,
+                        has_free_root=not opts.fix_base_link, opts=opts)
+    finalize_limits(model)
+    return model

@@ -1,0 +1,105 @@
+"""ctypes front-end of the CPU oracle (oracle/aba_oracle.c).  TEST INFRASTRUCTURE ONLY: imported by
+tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs; never by isaacgymenvs_b200/.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE])
+
+
+def _lib(prec):
+    path = os.path.join(_HERE, f"liboracle_{prec}.so")
+    if not os.path.exists(path):
+        build()
+    return C.CDLL(path)
+
+
+class _CModel(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("nl", "ncp", "nb", "nsens", "root_fixed", "gravity_on", "substeps", "pad0")] + \
+               [(n, C.c_void_p) for n in ("parent", "jtype", "limited", "drive_mode", "cp_link", "cp_body",
+                                          "body_link", "sensor_body",
+                                          "axis", "lpos", "lquat", "mass", "com", "inertia",
+                                          "armature", "damping", "stiffness", "lower", "upper", "effort",
+                                          "kp", "kd", "limit_k", "limit_d",
+                                          "cp_pos", "cp_radius", "cp_mu", "body_pos", "body_quat", "hfield")] + \
+               [("hf_nx", C.c_int), ("hf_ny", C.c_int), ("hf_scale", C.c_double), ("hf_ox", C.c_double),
+                ("hf_oy", C.c_double), ("kn", C.c_double), ("cn", C.c_double), ("vs", C.c_double),
+                ("gravity", C.c_double * 3), ("dt", C.c_double)]
+
+
+class OracleSim:
+    """One articulation model replicated over num_envs independent environments."""
+
+    def __init__(self, model, dt, substeps, gravity=(0.0, 0.0, -9.81), ground_mu=1.0, precision="f64",
+                 hfield=None, hf_scale=1.0, hf_origin=(0.0, 0.0), threads=1):
+        self.model, self.prec = model, precision
+        self.dtype = np.float64 if precision == "f64" else np.float32
+        self.lib = _lib(precision)
+        assert self.lib.oracle_real_size() == np.dtype(self.dtype).itemsize
+        self.lib.oracle_set_threads(int(threads))
+        m = model
+        self._keep = {}
+
+        def arr(name, a, dt_):
+            a = np.ascontiguousarray(a, dtype=dt_)
+            self._keep[name] = a
+            return a.ctypes.data
+        cm = _CModel()
+        cm.nl, cm.ncp, cm.nb, cm.nsens = m.nl, len(m.cp_link), m.nb, len(m.sensor_body)
+        cm.root_fixed, cm.gravity_on, cm.substeps = int(m.root_fixed), int(m.gravity_on), int(substeps)
+        for n in ("parent", "jtype", "limited", "drive_mode", "cp_link", "cp_body", "body_link", "sensor_body"):
+            setattr(cm, n, arr(n, getattr(m, n), np.int32))
+        for n in ("axis", "lpos", "lquat", "mass", "com", "inertia", "armature", "damping", "stiffness", "lower",
+                  "upper", "effort", "kp", "kd", "limit_k", "limit_d", "cp_pos", "cp_radius", "body_pos", "body_quat"):
+            setattr(cm, n, arr(n, getattr(m, n), np.float64))
+        # PhysX default friction combine mode is "average" of the two materials
+        cm.cp_mu = arr("cp_mu", 0.5 * (np.asarray(m.cp_mu) + ground_mu), np.float64)
+        if hfield is not None:
+            cm.hfield = arr("hfield", hfield, np.float64)
+            cm.hf_nx, cm.hf_ny = hfield.shape
+            cm.hf_scale, cm.hf_ox, cm.hf_oy = hf_scale, hf_origin[0], hf_origin[1]
+        else:
+            cm.hfield = None
+        cm.kn, cm.cn, cm.vs = m.contact_kn, m.contact_cn, m.contact_vs
+        cm.gravity = (C.c_double * 3)(*gravity)
+        cm.dt = dt
+        self.cm = cm
+        self.nd, self.nb, self.ns = m.ndof, m.nb, len(m.sensor_body)
+
+    def simulate(self, root, dof, tau=None, target=None):
+        """In-place gym.simulate(): root (N,13), dof (N,nd,2).  Returns dict of derived outputs."""
+        N = root.shape[0]
+        assert root.dtype == self.dtype and dof.dtype == self.dtype and root.flags.c_contiguous and dof.flags.c_contiguous
+        tau = None if tau is None else np.ascontiguousarray(tau, dtype=self.dtype)
+        target = None if target is None else np.ascontiguousarray(target, dtype=self.dtype)
+        out = dict(body_state=np.zeros((N, self.nb, 13), self.dtype), contact_force=np.zeros((N, self.nb, 3), self.dtype),
+                   sensor=np.zeros((N, max(self.ns, 1), 6), self.dtype), dof_force=np.zeros((N, max(self.nd, 1)), self.dtype))
+        p = lambda a: None if a is None else C.c_void_p(a.ctypes.data)
+        self.lib.oracle_simulate(C.byref(self.cm), C.c_int(N), p(root), p(dof), p(tau), p(target),
+                                 p(out["body_state"]), p(out["contact_force"]), p(out["sensor"]), p(out["dof_force"]))
+        out["sensor"] = out["sensor"][:, :self.ns]
+        out["dof_force"] = out["dof_force"][:, :self.nd]
+        return out
+
+    def body_states(self, root, dof):
+        N = root.shape[0]
+        bs = np.zeros((N, self.nb, 13), self.dtype)
+        self.lib.oracle_body_states(C.byref(self.cm), C.c_int(N), C.c_void_p(root.ctypes.data),
+                                    C.c_void_p(dof.ctypes.data), C.c_void_p(bs.ctypes.data))
+        return bs
+
+    def forward_dynamics(self, root, dof, tau):
+        """Single env, one sub-step: returns (qdd, root_after, dof_after)."""
+        root = np.ascontiguousarray(root, self.dtype); dof = np.ascontiguousarray(dof, self.dtype)
+        tau = np.ascontiguousarray(tau, self.dtype)
+        qdd = np.zeros(max(self.nd, 1), self.dtype); ra = np.zeros(13, self.dtype); da = np.zeros_like(dof)
+        self.lib.oracle_forward_dynamics(C.byref(self.cm), C.c_void_p(root.ctypes.data), C.c_void_p(dof.ctypes.data),
+                                         C.c_void_p(tau.ctypes.data), C.c_void_p(qdd.ctypes.data),
+                                         C.c_void_p(ra.ctypes.data), C.c_void_p(da.ctypes.data))
+        return qdd[:self.nd], ra, da

@@ -1,0 +1,128 @@
+"""Pins the CPU oracle's rigid-body dynamics (the reference has no golden vectors for
+gym.simulate -- SURVEY.md 8c): ABA accelerations must satisfy an independent Newton-Euler inverse
+dynamics, conserve momentum in free flight, and reproduce closed-form cases."""
+import numpy as np
+import pytest
+
+from isaacgymenvs_b200.assets import load_compiled
+from oracle.oracle import OracleSim
+from tests import rnea_np
+
+G = (0.0, 0.0, -9.81)
+
+
+def random_state(m, rng, z=2.0):
+    root = np.zeros(13)
+    root[:3] = [rng.normal(), rng.normal(), z]
+    qt = rng.normal(size=4); root[3:7] = qt / np.linalg.norm(qt)
+    root[7:13] = rng.normal(size=6)
+    if m.root_fixed:
+        root[7:13] = 0
+    lo = np.where(m.limited[1:] > 0, m.lower[1:], -1.0); hi = np.where(m.limited[1:] > 0, m.upper[1:], 1.0)
+    q = lo + (hi - lo) * rng.uniform(0.1, 0.9, size=m.ndof)
+    qd = rng.normal(size=m.ndof)
+    dof = np.stack([q, qd], -1)
+    return root, dof
+
+
+@pytest.mark.parametrize("name", ["cartpole", "ant", "humanoid", "anymal"])
+def test_aba_satisfies_inverse_dynamics(name):
+    m = load_compiled(name)
+    dt, sub = 0.0166, 2
+    sim = OracleSim(m, dt, sub, G)
+    h = dt / sub
+    rng = np.random.default_rng(0)
+    for trial in range(5):
+        root, dof = random_state(m, rng)
+        tau_act = rng.normal(size=m.ndof) * 5
+        qdd, ra, da = sim.forward_dynamics(root, dof, tau_act)
+        root_acc = ((ra[7:10] - root[7:10]) / h, (ra[10:13] - root[10:13]) / h)
+        q, qd = dof[:, 0], dof[:, 1]
+        tau_req, (f0, n0) = rnea_np.inverse_dynamics(m, root, q, qd, qdd, root_acc, G)
+        # forces applied under the implicit scheme: linear terms at the end of the sub-step
+        qd1 = qd + h * qdd; q1 = q + h * qd1
+        eff = m.effort[1:]
+        applied = np.clip(tau_act, -eff, eff) - m.damping[1:] * qd1 - m.stiffness[1:] * q1 - m.armature[1:] * qdd
+        scale = max(1.0, np.abs(applied).max())
+        assert np.allclose(tau_req, applied, atol=1e-8 * scale, rtol=1e-8), (name, trial, tau_req - applied)
+        if not m.root_fixed:   # a free root transmits no wrench
+            assert np.abs(f0).max() < 1e-7 * scale and np.abs(n0).max() < 1e-7 * scale
+        # integration consistency: q' = q + h*qd'
+        assert np.allclose(da[:, 1], qd1, atol=1e-12) and np.allclose(da[:, 0], q1, atol=1e-12)
+
+
+def test_free_fall_and_momentum():
+    m = load_compiled("ant")
+    dt, sub = 0.0166, 2
+    rng = np.random.default_rng(1)
+    # gravity off: momentum is conserved by the continuous dynamics; the generalized-coordinate
+    # integrator conserves it to O(h), so the drift must be small and shrink with the step
+    root_i, dof_i = random_state(m, rng, z=5.0)
+    drift = []
+    for scale in (1, 4):
+        sim0 = OracleSim(m, dt / scale, sub, (0, 0, 0))
+        root = root_i[None].copy(); dof = dof_i[None].copy()
+        P0, L0 = rnea_np.momentum(m, root[0], dof[0, :, 0], dof[0, :, 1])
+        for _ in range(20 * scale):
+            sim0.simulate(root, dof, np.zeros((1, m.ndof)))
+        P1, L1 = rnea_np.momentum(m, root[0], dof[0, :, 0], dof[0, :, 1])
+        drift.append((np.abs(P1 - P0).max(), np.abs(L1 - L0).max()))
+    assert drift[0][0] < 1e-2 * np.abs(P0).max() and drift[0][1] < 2e-2 * max(1.0, np.abs(L0).max())
+    assert drift[1][0] < 0.5 * drift[0][0] and drift[1][1] < 0.5 * drift[0][1]
+    # gravity on: COM accelerates at g => total momentum changes by M g t
+    sim = OracleSim(m, dt, sub, G)
+    root, dof = random_state(m, rng, z=50.0)
+    root = root[None].copy(); dof = dof[None].copy()
+    P0, _ = rnea_np.momentum(m, root[0], dof[0, :, 0], dof[0, :, 1])
+    n = 10
+    for _ in range(n):
+        sim.simulate(root, dof, np.zeros((1, m.ndof)))
+    P1, _ = rnea_np.momentum(m, root[0], dof[0, :, 0], dof[0, :, 1])
+    assert np.allclose(P1 - P0, m.total_mass() * np.array(G) * n * dt, atol=2e-2)
+
+
+def test_pendulum_period():
+    """Cartpole with the cart held by a stiff drive is a physical pendulum: small-swing period
+    T = 2 pi sqrt(I_pivot / (m g l)) about the hanging equilibrium."""
+    m = load_compiled("cartpole")
+    import copy
+    m = copy.deepcopy(m)
+    m.mass[1] = 1e6                     # immobile cart
+    dt, sub = 0.001, 1
+    sim = OracleSim(m, dt, sub, G)
+    root = np.zeros((1, 13)); root[0, 6] = 1; root[0, 2] = 2
+    th0 = np.pi - 0.01                  # pole hangs down at q = pi
+    dof = np.array([[[0.0, 0.0], [th0, 0.0]]])
+    I = m.inertia[2][0] + m.mass[2] * m.com[2][2] ** 2 + m.armature[2]
+    T = 2 * np.pi * np.sqrt(I / (m.mass[2] * 9.81 * m.com[2][2]))
+    qs = []
+    for _ in range(int(2.2 * T / dt)):
+        sim.simulate(root, dof, np.zeros((1, 2)))
+        qs.append(dof[0, 1, 0] - np.pi)
+    qs = np.array(qs)
+    zc = np.where((qs[:-1] < 0) & (qs[1:] >= 0))[0]   # upward zero crossings, one per period
+    assert len(zc) >= 2
+    T_meas = (zc[1] - zc[0]) * dt
+    assert abs(T_meas - T) / T < 5e-3
+
+
+def test_contact_rest_and_sensor():
+    """An Ant dropped from just above the ground comes to rest on it: penetration stays small, the
+    net contact force balances the weight, and the settled height is near the geometric one."""
+    m = load_compiled("ant")
+    import copy
+    m = copy.deepcopy(m)
+    m.sensor_body = np.array([2, 4, 6, 8], dtype=np.int32)
+    m.sensor_pos = np.zeros((4, 3)); m.sensor_quat = np.tile([0, 0, 0, 1.0], (4, 1))
+    sim = OracleSim(m, 0.0166, 2, G, ground_mu=1.0)
+    root = np.zeros((1, 13)); root[0, 6] = 1; root[0, 2] = 0.6
+    q0 = np.where(m.lower[1:] > 0, m.lower[1:], np.where(m.upper[1:] < 0, m.upper[1:], 0.0))
+    dof = np.zeros((1, 8, 2)); dof[0, :, 0] = q0
+    for _ in range(240):
+        out = sim.simulate(root, dof, np.zeros((1, 8)))
+    W = m.total_mass() * 9.81
+    Fz = out["contact_force"][0, :, 2].sum()
+    assert abs(Fz - W) / W < 0.02, (Fz, W)
+    assert np.abs(root[0, 7:13]).max() < 0.02 and np.abs(dof[0, :, 1]).max() < 0.05
+    assert 0.05 < root[0, 2] < 0.6
+    assert out["sensor"].shape == (1, 4, 6)
