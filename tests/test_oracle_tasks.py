@@ -1,0 +1,83 @@
+"""The numpy obs/reward restatement (oracle/tasks_np.py) against the golden vectors produced by
+the reference's own jit functions (tests/golden/make_golden.py).  Tolerance: 1e-6 absolute on
+O(1) observation entries (libm-vs-torch transcendental differences are 1-2 ulp); potentials and
+integer outputs must match exactly."""
+import os
+import numpy as np
+import pytest
+from oracle import tasks_np as T
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+f32 = np.float32
+
+
+def _consts(n):
+    return (np.tile(f32([1000, 0, 0]), (n, 1)), np.tile(f32([0, 0, 0, 1]), (n, 1)),
+            np.tile(f32([1, 0, 0]), (n, 1)), np.tile(f32([0, 0, 1]), (n, 1)))
+
+
+def test_quat_ops():
+    g = np.load(os.path.join(G, "quat_ops.npz"))
+    qa, qb, v = g["qa"], g["qb"], g["v"]
+    assert np.allclose(T.quat_mul(qa, qb), g["quat_mul"], atol=1e-6)
+    assert np.allclose(T.quat_rotate(qa, v), g["quat_rotate"], atol=2e-6)
+    assert np.allclose(T.quat_rotate_inverse(qa, v), g["quat_rotate_inverse"], atol=2e-6)
+    assert np.allclose(T.quat_apply(qa, v), g["quat_apply"], atol=2e-6)
+    r, p, y = T.get_euler_xyz(qa)
+    for a, b in ((r, g["roll"]), (p, g["pitch"]), (y, g["yaw"])):
+        d = np.abs(a - b); d = np.minimum(d, 2 * np.pi - d)
+        assert d.max() < 2e-6
+    assert np.allclose(T.normalize_angle(v[:, 0] * 3), g["normalize_angle"], atol=1e-6)
+
+
+def test_ant_obs_reward():
+    g = np.load(os.path.join(G, "ant_obs_reward.npz"))
+    n = g["root"].shape[0]
+    targets, isr, b0, b1 = _consts(n)
+    obs, pot, prev, up, head = T.ant_observations(g["root"], targets, g["potentials_in"], isr, g["dof_pos"], g["dof_vel"],
+                                                  g["lower"], g["upper"], 0.2, g["sensors"], g["actions"], float(g["dt"]), 0.1, b0, b1)
+    assert np.array_equal(pot, g["potentials"]) and np.array_equal(prev, g["prev_potentials"])
+    d = np.abs(obs - g["obs"])
+    for col in (7, 8, 9):   # yaw, roll (mod 2pi) and angle_to_target may wrap
+        d[:, col] = np.minimum(d[:, col], np.abs(2 * np.pi - d[:, col]))
+    assert d.max() < 5e-6, (d.max(), np.unravel_index(d.argmax(), d.shape))
+    assert np.allclose(up, g["up_vec"], atol=2e-6) and np.allclose(head, g["heading_vec"], atol=2e-6)
+    rew, reset = T.ant_reward(g["obs"], np.zeros(n, np.int64), g["progress"], g["actions"], 0.1, 0.5, g["potentials"],
+                              g["prev_potentials"], 0.005, 0.05, 0.1, 0.31, -2.0, 1000.0)
+    assert np.array_equal(reset, g["reset"])
+    assert np.allclose(rew, g["rew"], atol=2e-6 * np.maximum(1, np.abs(g["rew"])).max())
+
+
+def test_humanoid_obs_reward():
+    g = np.load(os.path.join(G, "humanoid_obs_reward.npz"))
+    n = g["root"].shape[0]
+    targets, isr, b0, b1 = _consts(n)
+    obs, pot, prev, up, head = T.humanoid_observations(g["root"], targets, g["potentials_in"], isr, g["dof_pos"], g["dof_vel"],
+                                                       g["dof_force"], g["lower"], g["upper"], 0.1, g["sensors"], g["actions"],
+                                                       float(g["dt"]), 0.01, 0.25, b0, b1)
+    assert np.array_equal(pot, g["potentials"])
+    d = np.abs(obs - g["obs"])
+    for col in (7, 8, 9):
+        d[:, col] = np.minimum(d[:, col], np.abs(2 * np.pi - d[:, col]))
+    assert d.max() < 5e-6, (d.max(), np.unravel_index(d.argmax(), d.shape))
+    rew, reset = T.humanoid_reward(g["obs"], np.zeros(n, np.int64), g["progress"], g["actions"], 0.1, 0.5, g["potentials"],
+                                   g["prev_potentials"], 0.01, 0.05, 0.25, float(g["motor_efforts"].max()), g["motor_efforts"],
+                                   0.8, -1.0, 1000.0)
+    assert np.array_equal(reset, g["reset"])
+    assert np.allclose(rew, g["rew"], atol=1e-5, rtol=1e-5)
+
+
+def test_cartpole_reward():
+    g = np.load(os.path.join(G, "cartpole_reward.npz"))
+    n = g["pole_angle"].shape[0]
+    rew, reset = T.cartpole_reward(g["pole_angle"], g["pole_vel"], g["cart_vel"], g["cart_pos"], 3.0,
+                                   np.zeros(n, np.int64), g["progress"], 500.0)
+    assert np.array_equal(reset, g["reset"]) and np.allclose(rew, g["rew"], atol=1e-6)
+
+
+def test_philox_known_answers():
+    """Random123 known-answer vectors for philox4x32-10."""
+    assert T.philox4x32([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert T.philox4x32([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert T.philox4x32([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
