@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the fused VecTask.step() hot path (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps 200 --warmup 5            # Ant, num_envs=16384 per GPU
+    torchrun --nproc-per-node N ... bench.py --gpus N ...       # weak scaling: 16384 envs per rank
+    python bench.py --impl reference ...                        # CPU port of the path (oracle/), host cores
+
+One "step" = one VecTask.step() over all envs under random actions U(-1,1) (the README rollout
+loop of the reference, README.md:39-51).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {   # name -> (task, num_envs per GPU, algorithmic bytes per env-step: SURVEY.md 8d / DESIGN.md)
+    "ant": ("Ant", 16384, 673),
+    "humanoid": ("Humanoid", 8192, 1161),
+    "cartpole": ("Cartpole", 16384, 89),
+}
+METRIC = "env-steps/s at num_envs=16384 (Ant), 1/2/4/8 B200; %HBM roofline"
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_env(task, n, device, rank):
+    import isaacgymenvs_b200
+    from isaacgymenvs_b200 import config
+    cfg = config.builtin_cfg(task, {"sim_device": device, "rl_device": device})
+    cfg["task"]["env_id_offset"] = rank * n
+    return isaacgymenvs_b200.make(seed=42, task=task, num_envs=n, sim_device=device, rl_device=device,
+                                  headless=True, cfg=cfg)
+
+
+# ------------------------------------------------------------------------------------ CPU legs
+def cpu_pipeline(task, n_envs, steps, threads):
+    """The same control step on host cores: oracle physics (C, float32, pthreads over envs) + the
+    numpy restatement of the reference's obs/reward functions.  Returns env-steps/s."""
+    import copy
+    from isaacgymenvs_b200.assets import load_compiled
+    from oracle.oracle import OracleSim
+    from oracle import tasks_np as T
+    assert task == "Ant"
+    m = copy.deepcopy(load_compiled("ant"))
+    m.sensor_body = np.array([2, 4, 6, 8], dtype=np.int32)
+    m.sensor_pos = np.zeros((4, 3)); m.sensor_quat = np.tile([0, 0, 0, 1.0], (4, 1))
+    sim = OracleSim(m, 0.0166, 2, precision="f32", threads=threads)
+    f32 = np.float32
+    rng = np.random.default_rng(42)
+    lo = np.minimum(m.lower[1:], m.upper[1:]).astype(f32); hi = np.maximum(m.lower[1:], m.upper[1:]).astype(f32)
+    init = np.where(lo > 0, lo, np.where(hi < 0, hi, 0)).astype(f32)
+    root = np.zeros((n_envs, 13), f32); root[:, 2] = 0.44; root[:, 6] = 1
+    dof = np.zeros((n_envs, 8, 2), f32); dof[..., 0] = init
+    pot = np.full(n_envs, -1000.0 / 0.0166, f32)
+    targets = np.tile(f32([1000, 0, 0]), (n_envs, 1)); isr = np.tile(f32([0, 0, 0, 1]), (n_envs, 1))
+    b0 = np.tile(f32([1, 0, 0]), (n_envs, 1)); b1 = np.tile(f32([0, 0, 1]), (n_envs, 1))
+    progress = np.zeros(n_envs, np.int64); reset = np.zeros(n_envs, np.int64)
+
+    def one():
+        nonlocal pot, progress, reset
+        a = np.clip(rng.uniform(-1, 1, size=(n_envs, 8)).astype(f32), -1, 1)
+        out = sim.simulate(root, dof, a * f32(15.0))
+        progress += 1
+        ids = np.nonzero(reset)[0]
+        if len(ids):
+            dof[ids, :, 0] = np.clip(init + rng.uniform(-0.2, 0.2, size=(len(ids), 8)).astype(f32), lo, hi)
+            dof[ids, :, 1] = rng.uniform(-0.1, 0.1, size=(len(ids), 8)).astype(f32)
+            root[ids] = 0; root[ids, 2] = 0.44; root[ids, 6] = 1
+            pot[ids] = T.potentials_from(targets[ids] - root[ids, :3], 0.0166)
+            progress[ids] = 0
+        obs, pot2, prev, _, _ = T.ant_observations(root, targets, pot, isr, dof[..., 0], dof[..., 1], lo, hi, 0.2,
+                                                   out["sensor"].reshape(n_envs, 24), a, 0.0166, 0.1, b0, b1)
+        rew, reset = T.ant_reward(obs, np.zeros(n_envs, np.int64), progress, a, 0.1, 0.5, pot2, prev, 0.005, 0.05,
+                                  0.1, 0.31, -2.0, 1000.0)
+        pot = pot2
+    one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = time.perf_counter() - t0
+    return n_envs * steps / dt, dt
+
+
+def run_reference_arm(args):
+    """`--impl reference`: the reference's CPU pipeline cannot run here (closed Isaac Gym binary,
+    SURVEY.md 8c), so this arm times the CPU PORT of the path (oracle/) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    task, n_full, _ = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    n_sample = min(n_full, 4096)
+    # warm-up + K steps, each step a bounded sample (n_sample envs) of the workload
+    cpu_pipeline(task, n_sample, max(1, args.warmup), cores)
+    v, secs = cpu_pipeline(task, n_sample, args.steps, cores)
+    line = {"metric": METRIC, "impl": "reference", "value": v, "unit": "env-steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{task} num_envs={n_full} random actions U(-1,1)", "sample_envs": n_sample},
+            "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                             "sample": f"{n_sample} envs x {args.steps} control steps (oracle/aba_oracle.c f32 + oracle/tasks_np.py); "
+                                       "the reference's own sim_device=cpu path needs the closed Isaac Gym binary"},
+            "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    device = f"cuda:{local}"
+    task, n, bytes_per = WORKLOADS[args.workload]
+    if args.num_envs:
+        n = args.num_envs
+    env = make_env(task, n, device, rank)
+    A = env.num_actions
+    gen = torch.Generator(device=device).manual_seed(42 + rank)
+    ring = [2 * torch.rand((n, A), device=device, generator=gen) - 1 for _ in range(16)]
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=device)   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput: per-step CUDA events on the launching stream, L2 flushed between steps
+    for k in range(args.warmup):
+        env.sim.task_step(ring[k % 16])
+    barrier()
+    sampler = ClockSampler(local); sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    l0 = env.sim.launch_count()
+    barrier()
+    for k in range(args.steps):
+        flush.zero_()
+        ev[k][0].record()
+        env.sim.task_step(ring[k % 16])
+        ev[k][1].record()
+    barrier()
+    launches = env.sim.launch_count() - l0
+    ms_each = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(sum(ms_each))
+    # ---- back-to-back (no flush) over the same K steps: what a rollout loop with a tiny policy sees
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    s0.record()
+    for k in range(args.steps):
+        env.sim.task_step(ring[k % 16])
+    s1.record()
+    barrier()
+    b2b_ms = s0.elapsed_time(s1)
+    # ---- end to end through the public API with HOST buffers (pinned): H2D actions, step, D2H results
+    O = env.num_obs
+    h_a = [r.cpu().pin_memory() for r in ring]
+    h_obs = torch.zeros(n, O).pin_memory(); h_rew = torch.zeros(n).pin_memory()
+    h_reset = torch.zeros(n, dtype=torch.long).pin_memory(); h_to = torch.zeros(n, dtype=torch.uint8).pin_memory()
+    for k in range(max(3, args.warmup)):
+        env.step_host(h_a[k % 16], h_obs, h_rew, h_reset, h_to)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(args.steps):
+        env.step_host(h_a[k % 16], h_obs, h_rew, h_reset, h_to)
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    # ---- logging collective: per-env returns gathered once per rollout (north_star), off the step path
+    if world > 1:
+        gathered = [torch.empty_like(env.rew_buf) for _ in range(world)]
+        dist.all_gather(gathered, env.rew_buf)
+    # ---- max over ranks
+    t = torch.tensor([total_ms, b2b_ms, e2e_ms], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, b2b_ms, e2e_ms = [float(x) for x in t.cpu()]
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    value = world * n * args.steps / (total_ms * 1e-3)
+    peak, peak_kind = measured_peak()
+    kernel_ms = float(np.mean(ms_each))
+    achieved = n * bytes_per / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            traffic = json.load(f).get(args.workload)
+    except Exception:
+        pass
+    line = {
+        "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{task} num_envs={n} per GPU, random actions U(-1,1), sim dt 0.0166 x 2 substeps",
+                   "num_envs_total": world * n, "timing": "per-step CUDA events, 256 MB write flushes L2 between timed steps",
+                   "lanes_per_env": env.sim_lanes if hasattr(env, "sim_lanes") else None},
+        "back_to_back": {"value": world * n * args.steps / (b2b_ms * 1e-3), "unit": "env-steps/s", "ms_per_step": b2b_ms / args.steps,
+                         "note": "same K steps without the L2 flush (state stays L2-resident)"},
+        "e2e": {"value": world * n * args.steps / (e2e_ms * 1e-3), "unit": "env-steps/s",
+                "h2d_bytes_per_step": n * A * 4, "d2h_bytes_per_step": n * (O * 4 + 4 + 8 + 1), "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_kind": peak_kind, "kernel_ms": kernel_ms,
+                     "algorithmic_bytes_per_env_step": bytes_per},
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        ns, ks = 2048, 40
+        v, secs = cpu_pipeline(task, ns, ks, cores) if task == "Ant" else (None, 0)
+        line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                                "sample": f"{ns} envs x {ks} control steps, {secs:.1f} s (oracle f32 physics + numpy obs/reward)"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="ant", choices=sorted(WORKLOADS))
+    ap.add_argument("--num-envs", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

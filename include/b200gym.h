@@ -1,0 +1,172 @@
+/*
+ * b200gym.h -- C ABI of the B200-native vectorised environment stepper.
+ *
+ * The reference has no C FFI: its boundary for this path is the Python surface of the closed
+ * `isaacgym` module.  Each entry point below names the reference call it stands
+ * behind (file:line under /root/reference/isaacgymenvs).  Conventions, taken from the call sites:
+ *   - single caller thread, one sim per process is the common case (tasks/base/vec_task.py:58-64)
+ *     but several handles may coexist;
+ *   - all work is STREAM-ORDERED on the cudaStream_t passed in (the reference issues on the
+ *     current torch stream);
+ *   - state lives in buffers the CALLER owns (torch tensors on the host side) and binds once with
+ *     b2g_bind(); layouts are exactly the reference's tensor views (`acquire_*_tensor`,
+ *     tasks/ant.py:78-95): env-major, float32, quaternions xyzw;
+ *   - every function returns 0 on success, a negative B2G_E_* code otherwise and never throws;
+ *     b2g_last_error() gives the message.  There is NO CPU fallback: without a CUDA device
+ *     b2g_create fails with B2G_E_CUDA.
+ */
+#ifndef B200GYM_H
+#define B200GYM_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2G_VERSION 1
+#define B2G_MAX_LINKS 32
+#define B2G_MAX_CONTACT_POINTS 64
+#define B2G_MAX_SENSORS 8
+
+enum {
+    B2G_OK = 0,
+    B2G_E_INVALID = -1,     /* bad argument / model too large */
+    B2G_E_CUDA = -2,        /* CUDA runtime error (message has the cudaError string) */
+    B2G_E_UNBOUND = -3,     /* a tensor the call needs was never bound */
+    B2G_E_UNSUPPORTED = -4  /* no compiled kernel for this articulation topology / task */
+};
+
+/* Articulation model, host memory, copied by b2g_create.  Produced by the asset importer
+ * (replaces gym.load_asset + gym.create_actor, tasks/ant.py:149-190).  Link 0 is the root. */
+typedef struct {
+    int32_t nl, ncp, nb, nsens;
+    int32_t root_fixed, gravity_on;
+    const int32_t *parent;       /* nl, -1 for the root; parent[i] < i */
+    const int32_t *jtype;        /* nl: -1 root, 0 hinge, 1 slide */
+    const int32_t *limited;      /* nl */
+    const int32_t *drive_mode;   /* nl: gymapi.DOF_MODE_* (1 = position drive) */
+    const int32_t *cp_link;      /* ncp: contact sphere -> link */
+    const int32_t *cp_body;      /* ncp: contact sphere -> body (public numbering) */
+    const int32_t *body_link;    /* nb */
+    const int32_t *sensor_body;  /* nsens */
+    const float *axis, *lpos, *lquat;          /* nl x 3, 3, 4(xyzw) */
+    const float *mass, *com, *inertia;         /* nl x 1, 3, 6 (xx yy zz xy xz yz about the COM) */
+    const float *armature, *damping, *stiffness, *lower, *upper, *effort, *kp, *kd, *limit_k, *limit_d; /* nl */
+    const float *cp_pos, *cp_radius, *cp_mu;   /* ncp x 3, 1, 1 (mu already combined with the ground's) */
+    const float *body_pos, *body_quat;         /* nb x 3, 4: body frame in its link frame */
+    float contact_kn, contact_cn, contact_vs;
+} b2g_model;
+
+/* gymapi.SimParams subset that changes the physics (tasks/base/vec_task.py:514-562) */
+typedef struct {
+    float dt;
+    int32_t substeps;
+    float gravity[3];
+    /* optional height field replacing the z=0 plane (tasks/anymal_terrain.py:196-209): int16
+     * samples * vertical_scale, row-major [nx][ny], cell size horizontal_scale, sample (0,0) at
+     * world (origin_x, origin_y).  NULL = plane. */
+    const int16_t *hf_samples;
+    int32_t hf_nx, hf_ny;
+    float hf_horizontal_scale, hf_vertical_scale, hf_origin_x, hf_origin_y;
+} b2g_sim_params;
+
+/* Tensor slots for b2g_bind().  Shapes in elements; N = num_envs, D = dofs, B = bodies, S = sensors. */
+enum {
+    B2G_T_ROOT_STATE = 0,      /* f32 (N,13)   acquire_actor_root_state_tensor, ant.py:78 */
+    B2G_T_DOF_STATE = 1,       /* f32 (N,D,2)  acquire_dof_state_tensor, ant.py:79 */
+    B2G_T_DOF_ACTUATION = 2,   /* f32 (N,D)    set_dof_actuation_force_tensor, ant.py:285 */
+    B2G_T_DOF_TARGET = 3,      /* f32 (N,D)    set_dof_position_target_tensor, shadow_hand.py:698 */
+    B2G_T_RIGID_BODY_STATE = 4,/* f32 (N,B,13) acquire_rigid_body_state_tensor, shadow_hand.py:172 */
+    B2G_T_FORCE_SENSOR = 5,    /* f32 (N,S,6)  acquire_force_sensor_tensor, ant.py:80 */
+    B2G_T_DOF_FORCE = 6,       /* f32 (N,D)    acquire_dof_force_tensor, humanoid.py:85 */
+    B2G_T_NET_CONTACT = 7,     /* f32 (N,B,3)  acquire_net_contact_force_tensor, anymal_terrain.py:119 */
+    /* task-level buffers (VecTask.allocate_buffers, vec_task.py:301-324, + per-task state) */
+    B2G_T_ACTIONS = 8,         /* f32 (N,A)   clamped actions kept for the observation */
+    B2G_T_OBS = 9,             /* f32 (N,O) */
+    B2G_T_REW = 10,            /* f32 (N) */
+    B2G_T_RESET = 11,          /* i64 (N) */
+    B2G_T_PROGRESS = 12,       /* i64 (N) */
+    B2G_T_TIMEOUT = 13,        /* u8  (N)  bool, vec_task.py:394 */
+    B2G_T_POTENTIALS = 14,     /* f32 (N) */
+    B2G_T_PREV_POTENTIALS = 15,/* f32 (N) */
+    B2G_T_UP_VEC = 16,         /* f32 (N,3) */
+    B2G_T_HEADING_VEC = 17,    /* f32 (N,3) */
+    B2G_T_INITIAL_ROOT = 18,   /* f32 (N,13) initial_root_states, ant.py:89-90 */
+    B2G_T_RESET_COUNT = 19,    /* i32 (N)  per-env reset counter feeding the Philox stream */
+    B2G_T_OBS_CLIPPED = 20,    /* f32 (N,O) clamp(obs, +-clip_obs), vec_task.py:402 (may alias OBS) */
+    B2G_T_COUNT = 21
+};
+
+/* fused per-task control steps */
+enum { B2G_TASK_NONE = 0, B2G_TASK_CARTPOLE = 1, B2G_TASK_ANT = 2, B2G_TASK_HUMANOID = 3 };
+
+/* Scalars of the locomotion tasks (cfg/task/Ant.yaml:13-29, Humanoid.yaml; ant.py:47-68). */
+typedef struct {
+    int32_t task;                    /* B2G_TASK_* */
+    int32_t num_obs, num_actions;
+    int32_t control_freq_inv;        /* gym.simulate calls per step, vec_task.py:379-382 */
+    float clip_actions, clip_obs;    /* vec_task.py:374,402 */
+    float max_episode_length;
+    float power_scale;
+    float joint_gears[B2G_MAX_LINKS];     /* per-DOF effort = action * gear * power_scale, ant.py:283 */
+    float motor_efforts[B2G_MAX_LINKS];   /* humanoid.py:160-171 (actuator order) */
+    float max_motor_effort;
+    float dof_limits_lower[B2G_MAX_LINKS], dof_limits_upper[B2G_MAX_LINKS]; /* sorted, ant.py:199-207 */
+    float initial_dof_pos[B2G_MAX_LINKS];                                   /* ant.py:96-99 */
+    float dof_vel_scale, contact_force_scale, angular_velocity_scale;
+    float heading_weight, up_weight, actions_cost_scale, energy_cost_scale, joints_at_limit_cost_scale;
+    float death_cost, termination_height, alive_reward;
+    float reset_pos_noise, reset_vel_noise;   /* +-0.2, +-0.1: ant.py:257-258 */
+    float dt;                                 /* cfg sim.dt as the task divides by it, ant.py:112 */
+    float target[3];                          /* ant.py:110 */
+    /* cartpole (cartpole.py:44-47,159-163) */
+    float max_push_effort, reset_dist;
+    uint64_t seed;
+    int32_t env_id_offset;                    /* global id of env 0 on this rank: keys the reset RNG so
+                                                 results do not depend on how envs are sharded */
+    int32_t pad_;
+} b2g_task_params;
+
+typedef struct b2g_sim b2g_sim;
+
+/* gymapi.acquire_gym() + gym.create_sim() + create_env/create_actor x N + gym.prepare_sim()
+ * (vec_task.py:247,262; ant.py:185-190): N identical single-actor environments. */
+int b2g_create(const b2g_model *model, const b2g_sim_params *params, int32_t num_envs, int32_t device,
+               b2g_sim **out);
+int b2g_destroy(b2g_sim *sim);
+
+/* gymtorch.wrap_tensor in reverse: hand the engine the device buffer behind a tensor view. */
+int b2g_bind(b2g_sim *sim, int32_t slot, void *device_ptr, size_t bytes);
+
+/* gym.simulate(sim): `substeps` sub-steps (vec_task.py:382); reads DOF_ACTUATION / DOF_TARGET,
+ * updates ROOT_STATE, DOF_STATE and, if bound, FORCE_SENSOR, DOF_FORCE, NET_CONTACT. */
+int b2g_simulate(b2g_sim *sim, void *stream);
+
+/* gym.refresh_rigid_body_state_tensor(sim) (shadow_hand.py:443): forward kinematics into
+ * RIGID_BODY_STATE. */
+int b2g_refresh_rigid_body_state(b2g_sim *sim, void *stream);
+
+/* One whole VecTask.step() (vec_task.py:360-408) for a fused task: clamp actions, pre_physics_step,
+ * control_freq_inv x simulate, post_physics_step (progress, reset_idx, observations, reward),
+ * timeout flags and the clipped observation copy -- one kernel launch.
+ * `actions` is a DEVICE pointer (N, num_actions). */
+int b2g_set_task(b2g_sim *sim, const b2g_task_params *task);
+int b2g_task_step(b2g_sim *sim, const float *actions, void *stream);
+
+/* Same step with HOST buffers (pinned or pageable): copies actions in, runs the step, copies
+ * obs / rew / reset / timeout out and synchronises the stream: the call an rl_device="cpu" user
+ * makes through VecTask.step (vec_task.py:402,408 `.to(rl_device)`). Any output may be NULL. */
+int b2g_task_step_host(b2g_sim *sim, const float *h_actions, float *h_obs, float *h_rew, int64_t *h_reset,
+                       uint8_t *h_timeout, void *stream);
+
+/* number of kernels this library has launched since creation (bench.py "gpu_launches") */
+int64_t b2g_launch_count(const b2g_sim *sim);
+const char *b2g_last_error(void);
+int b2g_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,35 @@
+"""Builds libb200gym.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "csrc", "b200gym.cu")
+OUT = os.path.join(HERE, "libb200gym.so")
+DEPS = [SRC, os.path.join(HERE, "csrc", "b2g_device.cuh"), os.path.join(HERE, "csrc", "b2g_tasks.cuh"),
+        os.path.join(os.path.dirname(HERE), "include", "b200gym.h")]
+
+
+def needs_build():
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    return any(os.path.getmtime(d) > t for d in DEPS)
+
+
+def build(force=False, verbose=False, extra=()):
+    if not force and not needs_build():
+        return OUT
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+           "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared", "-o", OUT, SRC]
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    cmd += list(extra)
+    subprocess.check_call(cmd)
+    return OUT
+
+
+if __name__ == "__main__":
+    build(force=True, verbose="-v" in sys.argv)
+    print(OUT)

@@ -1,0 +1,207 @@
+"""ctypes binding of libb200gym.so (include/b200gym.h) -- the only way the Python side reaches the
+CUDA engine.  torch is used for device memory and streams only: every tensor handed out by `Sim`
+is a torch tensor whose storage the engine reads/writes in place (the reference's
+`gymtorch.wrap_tensor` contract, tasks/ant.py:78-95).
+
+There is no CPU fallback: if the library is missing or no CUDA device is present, construction
+raises (b2g_create returns B2G_E_CUDA).
+"""
+import ctypes as C
+import os
+import numpy as np
+import torch
+
+from . import build as _build
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+MAXL = 32
+
+# tensor slots (mirror of the enum in include/b200gym.h)
+(T_ROOT_STATE, T_DOF_STATE, T_DOF_ACTUATION, T_DOF_TARGET, T_RIGID_BODY_STATE, T_FORCE_SENSOR, T_DOF_FORCE,
+ T_NET_CONTACT, T_ACTIONS, T_OBS, T_REW, T_RESET, T_PROGRESS, T_TIMEOUT, T_POTENTIALS, T_PREV_POTENTIALS,
+ T_UP_VEC, T_HEADING_VEC, T_INITIAL_ROOT, T_RESET_COUNT, T_OBS_CLIPPED) = range(21)
+TASK_NONE, TASK_CARTPOLE, TASK_ANT, TASK_HUMANOID = 0, 1, 2, 3
+
+
+class CModel(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("nl", "ncp", "nb", "nsens", "root_fixed", "gravity_on")] + \
+               [(n, C.c_void_p) for n in ("parent", "jtype", "limited", "drive_mode", "cp_link", "cp_body", "body_link",
+                                          "sensor_body", "axis", "lpos", "lquat", "mass", "com", "inertia", "armature",
+                                          "damping", "stiffness", "lower", "upper", "effort", "kp", "kd", "limit_k",
+                                          "limit_d", "cp_pos", "cp_radius", "cp_mu", "body_pos", "body_quat")] + \
+               [("contact_kn", C.c_float), ("contact_cn", C.c_float), ("contact_vs", C.c_float)]
+
+
+class CSimParams(C.Structure):
+    _fields_ = [("dt", C.c_float), ("substeps", C.c_int32), ("gravity", C.c_float * 3), ("hf_samples", C.c_void_p),
+                ("hf_nx", C.c_int32), ("hf_ny", C.c_int32), ("hf_horizontal_scale", C.c_float),
+                ("hf_vertical_scale", C.c_float), ("hf_origin_x", C.c_float), ("hf_origin_y", C.c_float)]
+
+
+class CTaskParams(C.Structure):
+    _fields_ = [("task", C.c_int32), ("num_obs", C.c_int32), ("num_actions", C.c_int32), ("control_freq_inv", C.c_int32),
+                ("clip_actions", C.c_float), ("clip_obs", C.c_float), ("max_episode_length", C.c_float),
+                ("power_scale", C.c_float), ("joint_gears", C.c_float * MAXL), ("motor_efforts", C.c_float * MAXL),
+                ("max_motor_effort", C.c_float), ("dof_limits_lower", C.c_float * MAXL),
+                ("dof_limits_upper", C.c_float * MAXL), ("initial_dof_pos", C.c_float * MAXL),
+                ("dof_vel_scale", C.c_float), ("contact_force_scale", C.c_float), ("angular_velocity_scale", C.c_float),
+                ("heading_weight", C.c_float), ("up_weight", C.c_float), ("actions_cost_scale", C.c_float),
+                ("energy_cost_scale", C.c_float), ("joints_at_limit_cost_scale", C.c_float), ("death_cost", C.c_float),
+                ("termination_height", C.c_float), ("alive_reward", C.c_float), ("reset_pos_noise", C.c_float),
+                ("reset_vel_noise", C.c_float), ("dt", C.c_float), ("target", C.c_float * 3),
+                ("max_push_effort", C.c_float), ("reset_dist", C.c_float), ("seed", C.c_uint64),
+                ("env_id_offset", C.c_int32), ("pad_", C.c_int32)]
+
+
+_lib = None
+
+
+def lib():
+    """Load (building if necessary) the CUDA library.  Fails loudly when it cannot be had."""
+    global _lib
+    if _lib is None:
+        path = os.path.join(_HERE, "libb200gym.so")
+        if not os.path.exists(path) or _build.needs_build():
+            _build.build()
+        _lib = C.CDLL(path)
+        _lib.b2g_last_error.restype = C.c_char_p
+        _lib.b2g_launch_count.restype = C.c_int64
+        _lib.b2g_launch_count.argtypes = [C.c_void_p]
+        for fn in ("b2g_create", "b2g_destroy", "b2g_bind", "b2g_simulate", "b2g_refresh_rigid_body_state",
+                   "b2g_set_task", "b2g_task_step", "b2g_task_step_host"):
+            getattr(_lib, fn).restype = C.c_int
+    return _lib
+
+
+EXPORTS = ("b2g_create", "b2g_destroy", "b2g_bind", "b2g_simulate", "b2g_refresh_rigid_body_state", "b2g_set_task",
+           "b2g_task_step", "b2g_task_step_host", "b2g_launch_count", "b2g_last_error", "b2g_version")
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise EngineError(f"{what} failed ({rc}): {lib().b2g_last_error().decode()}")
+
+
+def pack_model(model, ground_mu=1.0):
+    """importer Model -> (b2g_model struct, keep-alive arrays).  Friction: PhysX default combine
+    mode averages the two materials (ground plane params: tasks/ant.py:128-133)."""
+    keep = {}
+
+    def arr(name, a, dt):
+        a = np.ascontiguousarray(a, dtype=dt)
+        keep[name] = a
+        return a.ctypes.data
+    cm = CModel()
+    cm.nl, cm.ncp, cm.nb, cm.nsens = model.nl, len(model.cp_link), model.nb, len(model.sensor_body)
+    cm.root_fixed, cm.gravity_on = int(model.root_fixed), int(model.gravity_on)
+    for n in ("parent", "jtype", "limited", "drive_mode", "cp_link", "cp_body", "body_link", "sensor_body"):
+        setattr(cm, n, arr(n, getattr(model, n), np.int32))
+    for n in ("axis", "lpos", "lquat", "mass", "com", "inertia", "armature", "damping", "stiffness", "lower", "upper",
+              "kp", "kd", "limit_k", "limit_d", "cp_pos", "cp_radius", "body_pos", "body_quat"):
+        setattr(cm, n, arr(n, getattr(model, n), np.float32))
+    cm.effort = arr("effort", np.minimum(model.effort, 3e38), np.float32)
+    cm.cp_mu = arr("cp_mu", 0.5 * (np.asarray(model.cp_mu) + ground_mu), np.float32)
+    cm.contact_kn, cm.contact_cn, cm.contact_vs = model.contact_kn, model.contact_cn, model.contact_vs
+    return cm, keep
+
+
+class Sim:
+    """N identical single-actor environments on one GPU (gym.create_sim .. prepare_sim)."""
+
+    def __init__(self, model, num_envs, dt, substeps, gravity=(0.0, 0.0, -9.81), ground_mu=1.0, device="cuda:0",
+                 hfield=None, hf_horizontal_scale=1.0, hf_vertical_scale=1.0, hf_origin=(0.0, 0.0)):
+        self.model = model
+        self.num_envs = int(num_envs)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise EngineError("the B200 engine has no CPU path: device must be a CUDA device")
+        self.nd, self.nb, self.ns = model.ndof, model.nb, len(model.sensor_body)
+        cm, self._keep = pack_model(model, ground_mu)
+        sp = CSimParams()
+        sp.dt, sp.substeps = dt, int(substeps)
+        sp.gravity = (C.c_float * 3)(*gravity)
+        if hfield is not None:
+            hf = np.ascontiguousarray(hfield, dtype=np.int16)
+            self._keep["hf"] = hf
+            sp.hf_samples = hf.ctypes.data
+            sp.hf_nx, sp.hf_ny = hf.shape
+            sp.hf_horizontal_scale, sp.hf_vertical_scale = hf_horizontal_scale, hf_vertical_scale
+            sp.hf_origin_x, sp.hf_origin_y = hf_origin
+        self._h = C.c_void_p()
+        idx = self.device.index if self.device.index is not None else 0
+        _check(lib().b2g_create(C.byref(cm), C.byref(sp), C.c_int32(self.num_envs), C.c_int32(idx), C.byref(self._h)),
+               "b2g_create")
+        self.tensors = {}
+        N = self.num_envs
+        z = lambda *s, dtype=torch.float32: torch.zeros(*s, dtype=dtype, device=self.device)
+        self.root_state = self._bind(T_ROOT_STATE, z(N, 13))
+        self.root_state[:, 6] = 1.0
+        self.dof_state = self._bind(T_DOF_STATE, z(N * max(self.nd, 1), 2))
+        self.dof_actuation = self._bind(T_DOF_ACTUATION, z(N, max(self.nd, 1)))
+        self.dof_target = self._bind(T_DOF_TARGET, z(N, max(self.nd, 1)))
+        self.task = None
+
+    # ---- tensor plumbing
+    def _bind(self, slot, t):
+        assert t.is_contiguous() and t.device == self.device
+        _check(lib().b2g_bind(self._h, C.c_int32(slot), C.c_void_p(t.data_ptr()), C.c_size_t(t.numel() * t.element_size())),
+               f"b2g_bind({slot})")
+        self.tensors[slot] = t
+        return t
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def acquire(self, slot):
+        """Lazy `gym.acquire_*_tensor`: allocates and binds the optional output tensors."""
+        if slot in self.tensors:
+            return self.tensors[slot]
+        N = self.num_envs
+        shape = {T_RIGID_BODY_STATE: (N * self.nb, 13), T_FORCE_SENSOR: (N * max(self.ns, 1), 6),
+                 T_DOF_FORCE: (N * max(self.nd, 1),), T_NET_CONTACT: (N * self.nb, 3)}[slot]
+        return self._bind(slot, torch.zeros(*shape, dtype=torch.float32, device=self.device))
+
+    # ---- gym.* calls
+    def simulate(self):
+        _check(lib().b2g_simulate(self._h, self._stream()), "b2g_simulate")
+
+    def refresh_rigid_body_state(self):
+        self.acquire(T_RIGID_BODY_STATE)
+        _check(lib().b2g_refresh_rigid_body_state(self._h, self._stream()), "b2g_refresh_rigid_body_state")
+        return self.tensors[T_RIGID_BODY_STATE]
+
+    # ---- fused task step
+    def set_task(self, params: CTaskParams, buffers: dict):
+        """buffers: slot -> torch tensor for the task-level slots."""
+        for slot, t in buffers.items():
+            self._bind(slot, t)
+        self.task = params
+        _check(lib().b2g_set_task(self._h, C.byref(params)), "b2g_set_task")
+
+    def task_step(self, actions: torch.Tensor):
+        assert actions.is_contiguous() and actions.dtype == torch.float32 and actions.device == self.device
+        _check(lib().b2g_task_step(self._h, C.c_void_p(actions.data_ptr()), self._stream()), "b2g_task_step")
+
+    def task_step_host(self, h_actions, h_obs=None, h_rew=None, h_reset=None, h_timeout=None):
+        """Host-buffer step (CPU torch tensors, ideally pinned); synchronises."""
+        p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        _check(lib().b2g_task_step_host(self._h, p(h_actions), p(h_obs), p(h_rew), p(h_reset), p(h_timeout),
+                                        self._stream()), "b2g_task_step_host")
+
+    def launch_count(self):
+        return int(lib().b2g_launch_count(self._h))
+
+    def close(self):
+        if self._h:
+            lib().b2g_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,291 @@
+"""GPU parity tests (run on the B200 box): the CUDA engine, called through the C ABI, against the
+fp64 CPU oracle (physics) and the reference-generated golden vectors (observation / reward).
+
+Tolerances (fp32 engine vs fp64 oracle; stated per SURVEY.md 8c):
+  one control step from identical states : |dq|,|dpos|,|dquat| <= 2e-5, velocities <= 2e-3 relative
+                                           to max(1, |v|) (contact-rich states amplify round-off)
+  obs / reward vs the reference's functions: 1e-6 scaled by max(1,|x|) (potentials bit-exact).
+"""
+import copy
+import os
+import numpy as np
+import pytest
+import torch
+
+from isaacgymenvs_b200.assets import load_compiled
+
+pytestmark = pytest.mark.gpu
+G = (0.0, 0.0, -9.81)
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _model(name):
+    m = copy.deepcopy(load_compiled(name))
+    if name == "ant":
+        m.sensor_body = np.array([2, 4, 6, 8], dtype=np.int32)
+    elif name == "humanoid":
+        m.sensor_body = np.array([m.body_names.index("right_foot"), m.body_names.index("left_foot")], dtype=np.int32)
+    m.sensor_pos = np.zeros((len(m.sensor_body), 3)); m.sensor_quat = np.tile([0, 0, 0, 1.0], (len(m.sensor_body), 1))
+    return m
+
+
+def _random_states(m, n, rng, zlo, zhi):
+    root = np.zeros((n, 13))
+    root[:, 0:2] = rng.normal(size=(n, 2))
+    root[:, 2] = rng.uniform(zlo, zhi, size=n)
+    q = rng.normal(size=(n, 4)) * np.array([0.3, 0.3, 0.3, 0.0]) + np.array([0, 0, 0, 1.0])
+    root[:, 3:7] = q / np.linalg.norm(q, axis=1, keepdims=True)
+    root[:, 7:13] = rng.normal(size=(n, 6)) * 0.5
+    if m.root_fixed:
+        root[:, 7:13] = 0; root[:, 3:7] = [0, 0, 0, 1]
+    lo = np.where(m.limited[1:] > 0, m.lower[1:], -1.0); hi = np.where(m.limited[1:] > 0, m.upper[1:], 1.0)
+    qpos = lo + (hi - lo) * rng.uniform(-0.05, 1.05, size=(n, m.ndof))      # some beyond the limits
+    qvel = rng.normal(size=(n, m.ndof))
+    return root, np.stack([qpos, qvel], -1)
+
+
+CASES = {"cartpole": (0.0166, 2, 1.5, 2.5, 200.0), "ant": (0.0166, 2, 0.15, 0.8, 15.0), "humanoid": (0.0166, 2, 0.6, 1.6, 60.0)}
+
+
+@pytest.mark.parametrize("name", ["cartpole", "ant", "humanoid"])
+def test_simulate_matches_oracle(name):
+    from isaacgymenvs_b200 import engine
+    from oracle.oracle import OracleSim
+    m = _model(name)
+    dt, sub, zlo, zhi, tscale = CASES[name]
+    n = 512
+    rng = np.random.default_rng(7)
+    root, dof = _random_states(m, n, rng, zlo, zhi)
+    tau = rng.uniform(-1, 1, size=(n, m.ndof)) * tscale
+    sim = engine.Sim(m, n, dt, sub, G, ground_mu=1.0)
+    for slot in (engine.T_FORCE_SENSOR, engine.T_DOF_FORCE, engine.T_NET_CONTACT):
+        sim.acquire(slot)
+    orc = OracleSim(m, dt, sub, G, ground_mu=1.0, threads=8)
+    sim.root_state.copy_(torch.tensor(root, dtype=torch.float32))
+    sim.dof_state.copy_(torch.tensor(dof.reshape(-1, 2), dtype=torch.float32))
+    sim.dof_actuation.copy_(torch.tensor(tau, dtype=torch.float32))
+    # start the oracle from the SAME float32-rounded state
+    r64 = sim.root_state.cpu().numpy().astype(np.float64)
+    d64 = sim.dof_state.cpu().numpy().astype(np.float64).reshape(n, m.ndof, 2)
+    t64 = sim.dof_actuation.cpu().numpy().astype(np.float64)
+    sim.simulate(); torch.cuda.synchronize()
+    out = orc.simulate(r64, d64, t64)
+    rg = sim.root_state.cpu().numpy().astype(np.float64)
+    dg = sim.dof_state.cpu().numpy().astype(np.float64).reshape(n, m.ndof, 2)
+    if not m.root_fixed:
+        assert np.abs(rg[:, :7] - r64[:, :7]).max() < 2e-5
+        verr = np.abs(rg[:, 7:] - r64[:, 7:]) / np.maximum(1.0, np.abs(r64[:, 7:]))
+        assert verr.max() < 2e-3, verr.max()
+    assert np.abs(dg[..., 0] - d64[..., 0]).max() < 2e-5
+    qerr = np.abs(dg[..., 1] - d64[..., 1]) / np.maximum(1.0, np.abs(d64[..., 1]))
+    assert qerr.max() < 2e-3, qerr.max()
+    # derived outputs of the last sub-step
+    if len(m.sensor_body):
+        sg = sim.tensors[engine.T_FORCE_SENSOR].cpu().numpy().reshape(n, -1, 6)
+        scale = max(1.0, np.abs(out["sensor"]).max())
+        assert np.abs(sg - out["sensor"]).max() < 2e-3 * scale
+    fg = sim.tensors[engine.T_DOF_FORCE].cpu().numpy().reshape(n, -1)
+    assert np.abs(fg - out["dof_force"]).max() < 2e-3 * max(1.0, np.abs(out["dof_force"]).max())
+    cg = sim.tensors[engine.T_NET_CONTACT].cpu().numpy().reshape(n, m.nb, 3)
+    assert np.abs(cg - out["contact_force"]).max() < 2e-3 * max(1.0, np.abs(out["contact_force"]).max())
+    # forward kinematics of the new state
+    bs = sim.refresh_rigid_body_state(); torch.cuda.synchronize()
+    bo = orc.body_states(r64, d64)
+    bg = bs.cpu().numpy().reshape(n, m.nb, 13)
+    assert np.abs(bg[..., :3] - bo[..., :3]).max() < 3e-5
+    qd = np.minimum(np.abs(bg[..., 3:7] - bo[..., 3:7]).max(-1), np.abs(bg[..., 3:7] + bo[..., 3:7]).max(-1))
+    assert qd.max() < 3e-5
+    assert (np.abs(bg[..., 7:] - bo[..., 7:]) / np.maximum(1.0, np.abs(bo[..., 7:]))).max() < 2e-3
+    sim.close()
+
+
+@pytest.mark.parametrize("name", ["ant", "humanoid"])
+def test_rollout_tracks_oracle(name):
+    """30 control steps from rest on the ground under smooth random torques: the fp32 engine stays
+    within 2e-3 (positions) of the fp64 oracle -- divergence is round-off, not a model difference."""
+    from isaacgymenvs_b200 import engine
+    from oracle.oracle import OracleSim
+    m = _model(name)
+    dt, sub, _, _, tscale = CASES[name]
+    n = 64
+    rng = np.random.default_rng(3)
+    sim = engine.Sim(m, n, dt, sub, G)
+    orc = OracleSim(m, dt, sub, G, threads=8)
+    root = np.zeros((n, 13)); root[:, 6] = 1; root[:, 2] = 0.5 if name == "ant" else 1.34
+    q0 = np.where(m.lower[1:] > 0, m.lower[1:], np.where(m.upper[1:] < 0, m.upper[1:], 0.0))
+    dof = np.zeros((n, m.ndof, 2)); dof[..., 0] = q0
+    sim.root_state.copy_(torch.tensor(root, dtype=torch.float32))
+    sim.dof_state.copy_(torch.tensor(dof.reshape(-1, 2), dtype=torch.float32))
+    r64 = sim.root_state.cpu().numpy().astype(np.float64); d64 = sim.dof_state.cpu().numpy().astype(np.float64).reshape(n, m.ndof, 2)
+    amp = rng.uniform(-1, 1, size=(n, m.ndof)) * tscale * 0.3
+    for k in range(30):
+        tau = amp * np.sin(0.3 * k)
+        sim.dof_actuation.copy_(torch.tensor(tau, dtype=torch.float32))
+        sim.simulate()
+        orc.simulate(r64, d64, sim.dof_actuation.cpu().numpy().astype(np.float64))
+    torch.cuda.synchronize()
+    rg = sim.root_state.cpu().numpy(); dg = sim.dof_state.cpu().numpy().reshape(n, m.ndof, 2)
+    assert np.isfinite(rg).all() and np.isfinite(dg).all()
+    assert np.median(np.abs(rg[:, :3] - r64[:, :3]).max(1)) < 2e-3
+    assert np.median(np.abs(dg[..., 0] - d64[..., 0]).max(1)) < 5e-3
+    sim.close()
+
+
+def _make(task, n, **env_over):
+    import isaacgymenvs_b200
+    from isaacgymenvs_b200 import config
+    cfg = config.builtin_cfg(task, {"sim_device": "cuda:0", "rl_device": "cuda:0"})
+    cfg["task"]["env"].update(env_over)
+    return isaacgymenvs_b200.make(seed=42, task=task, num_envs=n, sim_device="cuda:0", rl_device="cuda:0",
+                                  headless=True, cfg=cfg)
+
+
+@pytest.mark.parametrize("task", ["Ant", "Humanoid"])
+def test_obs_reward_match_reference_golden(task):
+    """control_freq_inv=0 (no simulate): the kernel's observation/reward epilogue on the golden
+    inputs must reproduce what the reference's jit functions returned."""
+    g = np.load(os.path.join(GOLD, f"{task.lower()}_obs_reward.npz"))
+    n = g["root"].shape[0]
+    env = _make(task, n, controlFrequencyInv=0)
+    dev = env.device
+    t = lambda a, dt=torch.float32: torch.tensor(a, dtype=dt, device=dev)
+    env.root_states.copy_(t(g["root"]))
+    env.dof_pos.copy_(t(g["dof_pos"])); env.dof_vel.copy_(t(g["dof_vel"]))
+    env.vec_sensor_tensor.copy_(t(g["sensors"]))
+    if task == "Humanoid":
+        env.dof_force_tensor.copy_(t(g["dof_force"]))
+    env.potentials.copy_(t(g["potentials_in"]))
+    env.progress_buf.copy_(t(g["progress"] - 1, torch.long))
+    env.reset_buf.zero_()
+    obs, rew, reset, extras = env.step(t(g["actions"]))
+    torch.cuda.synchronize()
+    assert np.array_equal(env.potentials.cpu().numpy(), g["potentials"])           # bit-exact
+    assert np.array_equal(env.prev_potentials.cpu().numpy(), g["prev_potentials"])
+    o = obs["obs"].cpu().numpy()
+    d = np.abs(o - g["obs"])
+    for col in (7, 8, 9):
+        d[:, col] = np.minimum(d[:, col], np.abs(2 * np.pi - d[:, col]))
+    d = d / np.maximum(1.0, np.abs(g["obs"]))
+    assert d.max() < 2e-6, (d.max(), np.unravel_index(d.argmax(), d.shape))
+    assert np.array_equal(reset.cpu().numpy(), g["reset"])
+    r = rew.cpu().numpy()
+    assert (np.abs(r - g["rew"]) / np.maximum(1.0, np.abs(g["rew"]))).max() < 5e-6
+    assert np.allclose(env.up_vec.cpu().numpy(), g["up_vec"], atol=2e-6)
+    assert np.allclose(env.heading_vec.cpu().numpy(), g["heading_vec"], atol=2e-6)
+    expect_to = (g["progress"] >= 999) & (g["reset"] != 0)
+    assert np.array_equal(extras["time_outs"].cpu().numpy(), expect_to)
+
+
+def test_cartpole_reward_matches_reference_golden():
+    g = np.load(os.path.join(GOLD, "cartpole_reward.npz"))
+    n = g["pole_angle"].shape[0]
+    env = _make("Cartpole", n, controlFrequencyInv=0)
+    dev = env.device
+    t = lambda a, dt=torch.float32: torch.tensor(a, dtype=dt, device=dev)
+    env.dof_pos[:, 0] = t(g["cart_pos"]); env.dof_vel[:, 0] = t(g["cart_vel"])
+    env.dof_pos[:, 1] = t(g["pole_angle"]); env.dof_vel[:, 1] = t(g["pole_vel"])
+    env.progress_buf.copy_(t(g["progress"] - 1, torch.long)); env.reset_buf.zero_()
+    obs, rew, reset, _ = env.step(torch.zeros(n, 1, device=dev))
+    assert np.array_equal(reset.cpu().numpy(), g["reset"])
+    assert np.allclose(rew.cpu().numpy(), g["rew"], atol=1e-6)
+    o = obs["obs"].cpu().numpy()
+    expect = np.clip(np.stack([g["cart_pos"], g["cart_vel"], g["pole_angle"], g["pole_vel"]], -1), -5, 5)   # clipObservations 5
+    assert np.allclose(o, expect, atol=0)
+
+
+def test_fused_ant_step_equals_oracle_pipeline():
+    """A whole VecTask.step: first step resets every env (reset_buf starts as ones,
+    vec_task.py:316) with the Philox stream the oracle restates; following steps must equal
+    oracle physics + the numpy restatement of the reference's obs/reward."""
+    from oracle.oracle import OracleSim
+    from oracle import tasks_np as T
+    n = 256
+    env = _make("Ant", n)
+    m = env.model
+    orc = OracleSim(m, 0.0166, 2, G, ground_mu=1.0, threads=8)
+    rng = np.random.default_rng(0)
+    lo, hi = env.dof_limits_lower_np, env.dof_limits_upper_np
+    init = np.where(lo > 0, lo, np.where(hi < 0, hi, 0)).astype(np.float32)
+    f32 = np.float32
+    # --- step 0: physics from the spawn pose, then reset of all envs
+    a0 = rng.uniform(-1.5, 1.5, size=(n, 8)).astype(f32)
+    obs, rew, reset, _ = env.step(torch.tensor(a0, device=env.device))
+    torch.cuda.synchronize()
+    q = env.dof_pos.cpu().numpy(); qd = env.dof_vel.cpu().numpy()
+    for e in (0, 1, n - 1):
+        u = T.reset_uniforms(42, e, 0, 16)
+        pos = np.clip(init + (f32(0.4) * u[:8] + f32(-0.2)), lo, hi)
+        vel = f32(0.2) * u[8:] + f32(-0.1)
+        assert np.allclose(q[e], pos, atol=1e-7) and np.allclose(qd[e], vel, atol=1e-7)
+    assert (q >= lo - 1e-6).all() and (q <= hi + 1e-6).all()
+    assert np.allclose(env.root_states.cpu().numpy(), env.initial_root_states.cpu().numpy())
+    assert (env.progress_buf == 0).all() and (env.reset_count == 1).all()
+    assert np.allclose(obs["obs"][:, 52:60].cpu().numpy(), np.clip(a0, -1, 1))
+    # --- steps 1..5 against the oracle pipeline
+    for k in range(5):
+        r64 = env.root_states.cpu().numpy().astype(np.float64)
+        d64 = env.dof_state.cpu().numpy().astype(np.float64).reshape(n, 8, 2)
+        pot_in = env.potentials.cpu().numpy().copy()
+        prog_in = env.progress_buf.cpu().numpy().copy()
+        a = rng.uniform(-1.5, 1.5, size=(n, 8)).astype(f32)
+        ac = np.clip(a, -1, 1)
+        out = orc.simulate(r64, d64, (ac * f32(15.0)).astype(np.float64))
+        obs, rew, reset, _ = env.step(torch.tensor(a, device=env.device))
+        torch.cuda.synchronize()
+        n_ = n
+        targets = np.tile(f32([1000, 0, 0]), (n_, 1)); isr = np.tile(f32([0, 0, 0, 1]), (n_, 1))
+        b0 = np.tile(f32([1, 0, 0]), (n_, 1)); b1 = np.tile(f32([0, 0, 1]), (n_, 1))
+        # evaluate the reference arithmetic on the ENGINE's own state (isolates the epilogue) ...
+        rg = env.root_states.cpu().numpy(); qg = env.dof_pos.cpu().numpy(); vg = env.dof_vel.cpu().numpy()
+        sg = env.vec_sensor_tensor.cpu().numpy()
+        o_np, pot, prev, _, _ = T.ant_observations(rg, targets, pot_in, isr, qg, vg, lo, hi, 0.2, sg, ac, 0.0166, 0.1, b0, b1)
+        og = obs["obs"].cpu().numpy()
+        d = np.abs(og - o_np)
+        for col in (7, 8, 9):
+            d[:, col] = np.minimum(d[:, col], np.abs(2 * np.pi - d[:, col]))
+        assert (d / np.maximum(1, np.abs(o_np))).max() < 2e-6
+        assert np.array_equal(env.potentials.cpu().numpy(), pot)
+        r_np, reset_np = T.ant_reward(og, np.zeros(n, np.int64), prog_in + 1, ac, 0.1, 0.5, pot, prev, 0.005, 0.05, 0.1, 0.31, -2.0, 1000.0)
+        assert np.array_equal(reset.cpu().numpy(), reset_np)
+        assert (np.abs(rew.cpu().numpy() - r_np) / np.maximum(1, np.abs(r_np))).max() < 1e-5
+        # ... and the physics against the fp64 oracle
+        assert np.abs(rg[:, :7] - r64[:, :7]).max() < 5e-5
+        assert np.abs(qg - d64[..., 0]).max() < 5e-5
+        assert np.abs(sg.reshape(n, 4, 6) - out["sensor"]).max() < 5e-3 * max(1.0, np.abs(out["sensor"]).max())
+        if reset_np.any():
+            break
+
+
+def test_single_lane_and_four_lane_ant_agree():
+    """The 4-lanes-per-env kernel and the one-thread-per-env kernel are the same arithmetic in a
+    different order: results agree to fp32 round-off."""
+    from isaacgymenvs_b200 import engine
+    m = _model("ant")
+    n = 256
+    rng = np.random.default_rng(5)
+    root, dof = _random_states(m, n, rng, 0.15, 0.8)
+    tau = rng.uniform(-15, 15, size=(n, 8))
+    res = []
+    for single in ("0", "1"):
+        os.environ["B2G_SINGLE_LANE"] = single
+        sim = engine.Sim(m, n, 0.0166, 2, G)
+        sim.root_state.copy_(torch.tensor(root, dtype=torch.float32)); sim.dof_state.copy_(torch.tensor(dof.reshape(-1, 2), dtype=torch.float32))
+        sim.dof_actuation.copy_(torch.tensor(tau, dtype=torch.float32))
+        sim.simulate(); torch.cuda.synchronize()
+        res.append((sim.root_state.cpu().numpy(), sim.dof_state.cpu().numpy()))
+        sim.close()
+    os.environ.pop("B2G_SINGLE_LANE")
+    assert np.abs(res[0][0] - res[1][0]).max() < 2e-4 and np.abs(res[0][1] - res[1][1]).max() < 2e-3
+
+
+def test_host_buffer_step_and_launch_count():
+    n = 128
+    env = _make("Ant", n)
+    h_a = torch.rand(n, 8).pin_memory() * 2 - 1
+    h_obs = torch.zeros(n, 60).pin_memory(); h_rew = torch.zeros(n).pin_memory()
+    h_reset = torch.zeros(n, dtype=torch.long).pin_memory()
+    c0 = env.sim.launch_count()
+    env.step_host(h_a, h_obs, h_rew, h_reset)
+    assert env.sim.launch_count() == c0 + 1
+    assert torch.equal(h_obs, env.obs_buf.cpu()) and torch.equal(h_rew, env.rew_buf.cpu())
+    assert torch.equal(h_reset, env.reset_buf.cpu())

@@ -1,0 +1,94 @@
+"""CPU-side checks that need no GPU: the C-ABI library builds, loads and exports every symbol
+include/b200gym.h declares; the config loaders agree with the reference's YAML; importer
+known-answers; the engine refuses to run without a CUDA device (no CPU fallback)."""
+import ctypes
+import os
+import re
+import numpy as np
+import pytest
+
+from tests.conftest import needs_reference, REFERENCE, ROOT
+
+
+def test_library_builds_and_exports_the_declared_abi():
+    from isaacgymenvs_b200 import build, engine
+    path = build.build()
+    lib = ctypes.CDLL(path)
+    header = open(os.path.join(ROOT, "include", "b200gym.h")).read()
+    declared = set(re.findall(r"\b(b2g_[a-z_]+)\s*\(", header))
+    assert declared == set(engine.EXPORTS), declared ^ set(engine.EXPORTS)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert lib.b2g_version() == 1
+
+
+def test_struct_layouts_match_header_sizes():
+    """ctypes mirrors must have the size the C compiler gives the header's structs."""
+    import subprocess, tempfile
+    from isaacgymenvs_b200 import engine
+    src = '#include "b200gym.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu\\n", sizeof(b2g_model), sizeof(b2g_sim_params), sizeof(b2g_task_params));return 0;}\n'
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "t"), os.path.join(d, "t.c")])
+        sizes = [int(x) for x in subprocess.check_output([os.path.join(d, "t")]).split()]
+    assert sizes == [ctypes.sizeof(engine.CModel), ctypes.sizeof(engine.CSimParams), ctypes.sizeof(engine.CTaskParams)]
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from isaacgymenvs_b200 import engine
+    from isaacgymenvs_b200.assets import load_compiled
+    with pytest.raises(engine.EngineError):
+        engine.Sim(load_compiled("ant"), 4, 0.0166, 2, device="cuda:0")
+    with pytest.raises(engine.EngineError):
+        engine.Sim(load_compiled("ant"), 4, 0.0166, 2, device="cpu")
+
+
+@needs_reference
+@pytest.mark.parametrize("task", ["Cartpole", "Ant", "Humanoid"])
+def test_reference_yaml_loads_unmodified_and_matches_builtin(task):
+    from isaacgymenvs_b200 import config
+    ref = config.load_reference_cfg(os.path.join(REFERENCE, "isaacgymenvs", "cfg"), task, {"num_envs": 64})
+    own = config.builtin_cfg(task, {"num_envs": 64})
+
+    def cmp(a, b, path=""):
+        for k in b:
+            assert k in a, path + k
+            if isinstance(b[k], dict):
+                cmp(a[k], b[k], path + k + ".")
+            else:
+                assert a[k] == b[k], (path + k, a[k], b[k])
+    cmp(ref["task"], own["task"])
+    assert ref["task"]["env"]["numEnvs"] == 64 and ref["task"]["sim"]["use_gpu_pipeline"] is True
+    assert ref["task"]["sim"]["physx"]["num_threads"] == 4
+
+
+@needs_reference
+def test_importer_known_answers_and_compiled_blobs_are_current():
+    """SURVEY.md 8c importer known-answers (analytic, from the XML) + committed blobs == fresh import."""
+    from isaacgymenvs_b200.importer.mjcf import load_mjcf
+    from isaacgymenvs_b200.importer.urdf import load_urdf
+    from isaacgymenvs_b200.importer.model import BuildOptions
+    from isaacgymenvs_b200.assets import load_compiled
+    from isaacgymenvs_b200.assets.compile_assets import SPECS
+    ant = load_mjcf(os.path.join(REFERENCE, "assets/mjcf/nv_ant.xml"))
+    assert abs(ant.mass[0] - 0.48388) < 1e-5 and abs(ant.mass[1] - 0.039158) < 1e-6 and abs(ant.mass[2] - 0.067592) < 1e-6
+    assert abs(ant.total_mass() - 0.91088) < 1e-5
+    assert ant.dof_names == ["hip_1", "ankle_1", "hip_2", "ankle_2", "hip_3", "ankle_3", "hip_4", "ankle_4"]
+    assert np.allclose(np.degrees(ant.lower[1:3]), [-40, 30]) and np.allclose(ant.armature[1:], 0.01) and np.allclose(ant.damping[1:], 0.1)
+    hum = load_mjcf(os.path.join(REFERENCE, "assets/mjcf/nv_humanoid.xml"))
+    assert hum.nb == 16 and hum.ndof == 21 and hum.dof_names[:3] == ["abdomen_z", "abdomen_y", "abdomen_x"]
+    assert hum.actuator_joint[:2] == ["abdomen_y", "abdomen_z"]
+    cp = load_urdf(os.path.join(REFERENCE, "assets/urdf/cartpole.urdf"), BuildOptions(fix_base_link=True))
+    assert cp.ndof == 2 and cp.jtype[1] == 1 and cp.jtype[2] == 0 and cp.limited[2] == 0 and abs(cp.lpos[2][0] - 0.12) < 1e-12
+    any_ = load_urdf(os.path.join(REFERENCE, "assets/urdf/anymal_c/urdf/anymal_minimal.urdf"),
+                     BuildOptions(collapse_fixed_joints=True, replace_cylinder_with_capsule=True))
+    assert any_.nb == 13 and any_.ndof == 12 and len(any_.geom_type) == 9      # base + 4 x (knee, shank) ... feet
+    for name, (rel, opts) in SPECS.items():
+        path = os.path.join(REFERENCE, "assets", rel)
+        fresh = load_urdf(path, opts, name=name) if rel.endswith(".urdf") else load_mjcf(path, opts, name=name)
+        blob = load_compiled(name)
+        for f in ("parent", "jtype", "axis", "lpos", "mass", "com", "inertia", "lower", "upper", "cp_pos", "cp_radius", "limit_k"):
+            assert np.allclose(getattr(fresh, f), getattr(blob, f)), (name, f)
