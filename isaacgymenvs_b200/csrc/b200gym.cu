@@ -22,6 +22,9 @@ struct Buffers {
 };
 
 constexpr int BLOCK = 128;
+#ifndef B2G_MINBLOCKS
+#define B2G_MINBLOCKS 1
+#endif
 
 // shared-memory copy of the model: only the words this model uses are moved
 __device__ __forceinline__ void load_model(DevModel *sm, const DevModel *__restrict__ gm) {
@@ -141,7 +144,7 @@ __global__ void __launch_bounds__(BLOCK) simulate_kernel(const DevModel *__restr
 // -------------------------------------------------------------------------------------------
 // One whole VecTask.step() of Ant / Humanoid (vec_task.py:360-408 + ant.py:281-297 / humanoid.py)
 template <class Topo, bool HUM>
-__global__ void __launch_bounds__(BLOCK) loco_step_kernel(const DevModel *__restrict__ gm, const int16_t *__restrict__ hf,
+__global__ void __launch_bounds__(BLOCK, B2G_MINBLOCKS) loco_step_kernel(const DevModel *__restrict__ gm, const int16_t *__restrict__ hf,
                                                           Buffers B, const __grid_constant__ b2g_task_params P,
                                                           const float *__restrict__ actions_in, int N) {
     __shared__ DevModel sm;

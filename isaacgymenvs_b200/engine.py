@@ -60,9 +60,11 @@ def lib():
     """Load (building if necessary) the CUDA library.  Fails loudly when it cannot be had."""
     global _lib
     if _lib is None:
-        path = os.path.join(_HERE, "libb200gym.so")
-        if not os.path.exists(path) or _build.needs_build():
-            _build.build()
+        path = os.environ.get("B2G_LIB", "")          # experiment hook: an alternative build of the same ABI
+        if not path:
+            path = os.path.join(_HERE, "libb200gym.so")
+            if not os.path.exists(path) or _build.needs_build():
+                _build.build()
         _lib = C.CDLL(path)
         _lib.b2g_last_error.restype = C.c_char_p
         _lib.b2g_launch_count.restype = C.c_int64

@@ -426,17 +426,20 @@ static void *simulate_range(void *arg) {
     for (int e = j->e0; e < j->e1; e++) {
         real cf[3 * MAXL], ct[3 * MAXL], df[MAXL], bs[13 * MAXL];
         real *r = j->root + 13 * e, *d = j->dof + 2 * nd * e;
+        real Rw[9 * MAXL], pw[3 * MAXL], vl[6 * MAXL];
         for (int s = 0; s < m->substeps; s++)
-            substep(m, h, r, d, j->tau_act ? j->tau_act + nd * e : 0, j->target ? j->target + nd * e : 0, cf, ct, df, 0, 0, 0);
+            substep(m, h, r, d, j->tau_act ? j->tau_act + nd * e : 0, j->target ? j->target + nd * e : 0, cf, ct, df, Rw, pw, vl);
         if (j->dof_force) memcpy(j->dof_force + nd * e, df, sizeof(real) * nd);
         if (j->contact_force) memcpy(j->contact_force + 3 * m->nb * e, cf, sizeof(real) * 3 * m->nb);
-        if (j->body_state || j->sensor) body_states(m, r, d, bs);
-        if (j->body_state) memcpy(j->body_state + 13 * m->nb * e, bs, sizeof(real) * 13 * m->nb);
+        if (j->body_state) { body_states(m, r, d, bs); memcpy(j->body_state + 13 * m->nb * e, bs, sizeof(real) * 13 * m->nb); }
+        /* sensors: the contact wrench of the last sub-step in the body frame AS IT WAS when the
+         * forces were evaluated (start of that sub-step) */
         if (j->sensor) for (int s = 0; s < m->nsens; s++) {
-            int b = m->sensor_body[s]; real Rb[9];
-            quat_to_mat(bs + 13 * b + 3, Rb);
-            mat3T_vec(Rb, cf + 3 * b, j->sensor + 6 * (m->nsens * e + s));
-            mat3T_vec(Rb, ct + 3 * b, j->sensor + 6 * (m->nsens * e + s) + 3);
+            int b = m->sensor_body[s], li = m->body_link[b]; real Rb[9], Rwb[9];
+            real bq[4] = {(real)m->body_quat[4 * b], (real)m->body_quat[4 * b + 1], (real)m->body_quat[4 * b + 2], (real)m->body_quat[4 * b + 3]};
+            quat_to_mat(bq, Rb); mat3_mul(Rw + 9 * li, Rb, Rwb);
+            mat3T_vec(Rwb, cf + 3 * b, j->sensor + 6 * (m->nsens * e + s));
+            mat3T_vec(Rwb, ct + 3 * b, j->sensor + 6 * (m->nsens * e + s) + 3);
         }
     }
     return 0;
