@@ -21,185 +21,178 @@ struct Buffers {
     void *p[B2G_T_COUNT];
 };
 
-constexpr int BLOCK = 128;
-#ifndef B2G_MINBLOCKS
-#define B2G_MINBLOCKS 1
-#endif
-
-// shared-memory copy of the model: only the words this model uses are moved
-__device__ __forceinline__ void load_model(DevModel *sm, const DevModel *__restrict__ gm) {
-    const int nl = gm->nl, ncp = gm->ncp;
-    const uint32_t *src = reinterpret_cast<const uint32_t *>(gm);
-    uint32_t *dst = reinterpret_cast<uint32_t *>(sm);
-    const int head = (int)(offsetof(DevModel, links) / 4);
-    for (int i = threadIdx.x; i < head; i += blockDim.x) dst[i] = src[i];
-    const int nlw = nl * (int)(sizeof(LinkC) / 4);
-    for (int i = threadIdx.x; i < nlw; i += blockDim.x) dst[head + i] = src[head + i];
-    const int cph = (int)(offsetof(DevModel, cps) / 4), ncw = ncp * (int)(sizeof(CpC) / 4);
-    for (int i = threadIdx.x; i < ncw; i += blockDim.x) dst[cph + i] = src[cph + i];
+// whole-struct copy (forward-kinematics kernel, which also reads the cold tables)
+__device__ __forceinline__ void load_model_full(DevModel *sm, const DevModel *__restrict__ gm) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(gm);
+    uint4 *dst = reinterpret_cast<uint4 *>(sm);
+    for (int i = threadIdx.x; i < (int)(sizeof(DevModel) / 16); i += blockDim.x) dst[i] = src[i];
     __syncthreads();
 }
 
-template <class Topo>
-__device__ __forceinline__ void load_env(const DevModel &sm, const Buffers &B, int e, int lane, EnvState<Topo> &st) {
-    const float *r = (const float *)B.p[B2G_T_ROOT_STATE] + 13 * (size_t)e;
-    st.rp[0] = r[0]; st.rp[1] = r[1]; st.rp[2] = r[2];
-    st.rq[0] = r[3]; st.rq[1] = r[4]; st.rq[2] = r[5]; st.rq[3] = r[6];
-    st.rv[0] = r[7]; st.rv[1] = r[8]; st.rv[2] = r[9];
-    st.rw[0] = r[10]; st.rw[1] = r[11]; st.rw[2] = r[12];
-    const int nd = sm.nl - 1;
-    const float2 *d = (const float2 *)B.p[B2G_T_DOF_STATE] + (size_t)e * nd;
-#pragma unroll
-    for (int s = 0; s < Topo::NS; s++) {
-        const float2 v = d[sm.slot_link[s][lane] - 1];
-        st.q[s] = v.x; st.qd[s] = v.y;
+// Step-kernel prologue: ONE mbarrier transaction brings the hot part of the model (header, links,
+// contact spheres) and, when the block owns whole 16-byte-aligned tiles, this block's slice of
+// root_state / dof_state / actions into shared memory with bulk-async (TMA) copies.
+struct Tiles {
+    const float *root;     // [envs_per_block][13]   (shared memory, or global when !on)
+    const float2 *dof;     // [envs_per_block][nd]
+    const float *act;      // [envs_per_block][na]
+    bool on;
+};
+__device__ __forceinline__ uint32_t round16(uint32_t b) { return (b + 15u) & ~15u; }
+
+__device__ __forceinline__ Tiles prologue(DevModel *sm, uint64_t *mbar, const DevModel *__restrict__ gm, float4 *tile_smem,
+                                          bool tiles_on, int env0, int epb, const float *g_root, const float *g_dof,
+                                          const float *g_act, int nd_hint, int na_hint) {
+    Tiles t;
+    if (threadIdx.x == 0) mbar_init(mbar, 1);
+    __syncthreads();
+    const uint32_t rb = (uint32_t)epb * 13u * 4u, db = (uint32_t)epb * (uint32_t)nd_hint * 8u, ab = (uint32_t)epb * (uint32_t)na_hint * 4u;
+    float *s_root = reinterpret_cast<float *>(tile_smem);
+    float *s_dof = s_root + rb / 4;
+    float *s_act = s_dof + db / 4;
+    if (threadIdx.x == 0) {
+        const int nl = gm->nl, ncp = gm->ncp;          // two scalar loads; everything else arrives by bulk copy
+        const uint32_t hb = (uint32_t)offsetof(DevModel, links);
+        const uint32_t lb = round16((uint32_t)nl * (uint32_t)sizeof(LinkC)), cb = round16((uint32_t)ncp * (uint32_t)sizeof(CpC));
+        uint32_t total = hb + lb + cb;
+        if (tiles_on) total += rb + db + (g_act ? ab : 0u);
+        mbar_expect_tx(mbar, total);
+        bulk_g2s(sm, gm, hb, mbar);
+        bulk_g2s(sm->links, gm->links, lb, mbar);
+        if (cb) bulk_g2s(sm->cps, gm->cps, cb, mbar);
+        if (tiles_on) {
+            bulk_g2s(s_root, g_root + (size_t)env0 * 13, rb, mbar);
+            bulk_g2s(s_dof, g_dof + (size_t)env0 * nd_hint * 2, db, mbar);
+            if (g_act) bulk_g2s(s_act, g_act + (size_t)env0 * na_hint, ab, mbar);
+        }
     }
+    mbar_wait(mbar, 0);
+    t.on = tiles_on;
+    t.root = tiles_on ? s_root : g_root + (size_t)env0 * 13;
+    t.dof = reinterpret_cast<const float2 *>(tiles_on ? s_dof : g_dof + (size_t)env0 * nd_hint * 2);
+    t.act = g_act ? (tiles_on ? s_act : g_act + (size_t)env0 * na_hint) : nullptr;
+    return t;
 }
 
-template <class Topo>
-__device__ __forceinline__ void store_env(const DevModel &sm, const Buffers &B, int e, int lane, const EnvState<Topo> &st) {
-    const int nd = sm.nl - 1;
-    float2 *d = (float2 *)B.p[B2G_T_DOF_STATE] + (size_t)e * nd;
-#pragma unroll
-    for (int s = 0; s < Topo::NS; s++) d[sm.slot_link[s][lane] - 1] = make_float2(st.q[s], st.qd[s]);
-    if (lane == 0 && !sm.root_fixed) {
-        float *r = (float *)B.p[B2G_T_ROOT_STATE] + 13 * (size_t)e;
-        r[0] = st.rp[0]; r[1] = st.rp[1]; r[2] = st.rp[2];
-        r[3] = st.rq[0]; r[4] = st.rq[1]; r[5] = st.rq[2]; r[6] = st.rq[3];
-        r[7] = st.rv[0]; r[8] = st.rv[1]; r[9] = st.rv[2];
-        r[10] = st.rw[0]; r[11] = st.rw[1]; r[12] = st.rw[2];
-    }
+extern __shared__ float4 b2g_dyn_smem[];
+
+template <int L, bool HF, int BLOCK>
+__device__ __forceinline__ Stepper<L, HF, BLOCK> make_stepper(const DevModel *sm, const int16_t *hf, int lane) {
+    Stepper<L, HF, BLOCK> st;
+    st.m = sm; st.gr = Ground{sm, hf};
+    st.ss = b2g_dyn_smem + threadIdx.x;
+    st.acc = b2g_dyn_smem + (sm->ns + 1) * SLOT_F4 * BLOCK + threadIdx.x;
+    st.lane = lane;
+    return st;
 }
 
-// force sensors / joint forces / net contact forces of the last sub-step -> bound output tensors.
-// sens[s][6] receives the sensor reading of slot s (body frame) for the observation.
-template <class Topo>
-__device__ __forceinline__ void store_outputs(const DevModel &sm, const Buffers &B, int e, int lane, bool valid,
-                                              const StepOut<Topo> &out, float sens[][6]) {
-    constexpr int NS = Topo::NS;
+__device__ __forceinline__ void load_root(const float *r, RootState &rs) {
+    rs.rp[0] = r[0]; rs.rp[1] = r[1]; rs.rp[2] = r[2];
+    rs.rq[0] = r[3]; rs.rq[1] = r[4]; rs.rq[2] = r[5]; rs.rq[3] = r[6];
+    rs.rv[0] = r[7]; rs.rv[1] = r[8]; rs.rv[2] = r[9];
+    rs.rw[0] = r[10]; rs.rw[1] = r[11]; rs.rw[2] = r[12];
+}
+__device__ __forceinline__ void store_root(const Buffers &B, int e, const RootState &rs) {
+    float *r = (float *)B.p[B2G_T_ROOT_STATE] + 13 * (size_t)e;
+    r[0] = rs.rp[0]; r[1] = rs.rp[1]; r[2] = rs.rp[2];
+    r[3] = rs.rq[0]; r[4] = rs.rq[1]; r[5] = rs.rq[2]; r[6] = rs.rq[3];
+    r[7] = rs.rv[0]; r[8] = rs.rv[1]; r[9] = rs.rv[2];
+    r[10] = rs.rw[0]; r[11] = rs.rw[1]; r[12] = rs.rw[2];
+}
+
+template <class ST>
+__device__ __forceinline__ typename ST::Outputs make_outputs(const DevModel &sm, const Buffers &B, int e, bool valid) {
+    typename ST::Outputs o;
     const int nd = sm.nl - 1;
-    float *fs = (float *)B.p[B2G_T_FORCE_SENSOR];
-    float *df = (float *)B.p[B2G_T_DOF_FORCE];
-    float *nc = (float *)B.p[B2G_T_NET_CONTACT];
-#pragma unroll
-    for (int s = -1; s < NS; s++) {
-        const int i = (s < 0) ? NS : s;
-        if (s < 0 && lane != 0) continue;
-        const int link = (s < 0) ? 0 : sm.slot_link[s][lane];
-        const LinkC &lk = sm.links[link];
-        if (lk.sensor >= 0) {
-            // body frame = link frame axes for every sensor body of the five assets (sensor pose
-            // identity, ant.py:176-178); torque is taken about the body origin = link origin + R*body_pos
-            float Fb[3], Tb[3], T[3] = {out.cfT[i][0], out.cfT[i][1], out.cfT[i][2]};
-            const int b = sm.sensor_body[lk.sensor];
-            float bp[3] = {sm.body_pos[b][0], sm.body_pos[b][1], sm.body_pos[b][2]}, wb[3], bxF[3];
-            matvec(out.R[i], bp, wb); cross(wb, out.cfF[i], bxF);
-            T[0] -= bxF[0]; T[1] -= bxF[1]; T[2] -= bxF[2];
-            matTvec(out.R[i], out.cfF[i], Fb); matTvec(out.R[i], T, Tb);
-            if (s >= 0) { sens[s][0] = Fb[0]; sens[s][1] = Fb[1]; sens[s][2] = Fb[2]; sens[s][3] = Tb[0]; sens[s][4] = Tb[1]; sens[s][5] = Tb[2]; }
-            if (fs && valid) {
-                float *o = fs + ((size_t)e * sm.nsens + lk.sensor) * 6;
-                o[0] = Fb[0]; o[1] = Fb[1]; o[2] = Fb[2]; o[3] = Tb[0]; o[4] = Tb[1]; o[5] = Tb[2];
-            }
-        }
-        if (nc && valid && sm.link_body[link] >= 0) {
-            float *o = nc + ((size_t)e * sm.nb + sm.link_body[link]) * 3;
-            o[0] = out.cfF[i][0]; o[1] = out.cfF[i][1]; o[2] = out.cfF[i][2];
-        }
-        if (s >= 0 && df && valid) df[(size_t)e * nd + link - 1] = out.dof_force[s];
-    }
+    float *fs = (float *)B.p[B2G_T_FORCE_SENSOR], *df = (float *)B.p[B2G_T_DOF_FORCE], *nc = (float *)B.p[B2G_T_NET_CONTACT];
+    o.sensor = fs ? fs + (size_t)e * sm.nsens * 6 : nullptr;
+    o.dof_force = df ? df + (size_t)e * nd : nullptr;
+    o.net_contact = nc ? nc + (size_t)e * sm.nb * 3 : nullptr;
+    o.write = valid;
+    return o;
 }
 
 // -------------------------------------------------------------------------------------------
 // gym.simulate(): physics only
-template <class Topo>
+template <int L, bool HF, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) simulate_kernel(const DevModel *__restrict__ gm, const int16_t *__restrict__ hf,
                                                          Buffers B, int N) {
     __shared__ DevModel sm;
-    load_model(&sm, gm);
-    constexpr int L = Topo::L, NS = Topo::NS;
-    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ alignas(8) uint64_t mbar;
+    prologue(&sm, &mbar, gm, nullptr, false, 0, 0, nullptr, nullptr, nullptr, 0, 0);
+    using ST = Stepper<L, HF, BLOCK>;
+    const int gt = blockIdx.x * BLOCK + threadIdx.x;
     const int env = gt / L, lane = gt % L;
     const bool valid = env < N;
     const int e = valid ? env : N - 1;
-    const int nd = sm.nl - 1;
-    EnvState<Topo> st;
-    load_env<Topo>(sm, B, e, lane, st);
+    const int nd = sm.nl - 1, NS = sm.ns;
+    ST st = make_stepper<L, HF, BLOCK>(&sm, hf, lane);
+    RootState rs; load_root((const float *)B.p[B2G_T_ROOT_STATE] + 13 * (size_t)e, rs);
+    const float2 *d = (const float2 *)B.p[B2G_T_DOF_STATE] + (size_t)e * nd;
     const float *act = (const float *)B.p[B2G_T_DOF_ACTUATION];
     const float *tgt = (const float *)B.p[B2G_T_DOF_TARGET];
-#pragma unroll
+#pragma unroll 1
     for (int s = 0; s < NS; s++) {
         const int link = sm.slot_link[s][lane];
-        const float *src = (sm.links[link].drive_mode == 1) ? tgt : act;
-        st.act[s] = src ? src[(size_t)e * nd + link - 1] : 0.f;
+        const float2 v = d[link - 1];
+        const float *src = (sm.links[link].flags & LF_POSDRIVE) ? tgt : act;
+        st.set_joint(s, v.x, v.y, src ? src[(size_t)e * nd + link - 1] : 0.f);
     }
-    Ground gr{&sm, hf};
-    StepOut<Topo> out;
-    for (int k = 0; k < sm.substeps; k++) substep<Topo>(&sm, gr, lane, st, out, k == sm.substeps - 1);
-    float sens[NS][6];
-    store_outputs<Topo>(sm, B, e, lane, valid, out, sens);
-    if (valid) store_env<Topo>(sm, B, e, lane, st);
+    const typename ST::Outputs o = make_outputs<ST>(sm, B, e, valid);
+    for (int k = 0; k < sm.substeps; k++) st.substep(rs, k == sm.substeps - 1, o);
+    if (!valid) return;
+    float2 *dw = (float2 *)B.p[B2G_T_DOF_STATE] + (size_t)e * nd;
+#pragma unroll 1
+    for (int s = 0; s < NS; s++) dw[sm.slot_link[s][lane] - 1] = st.get_q(s);
+    if (lane == 0 && !sm.root_fixed) store_root(B, e, rs);
 }
 
 // -------------------------------------------------------------------------------------------
 // One whole VecTask.step() of Ant / Humanoid (vec_task.py:360-408 + ant.py:281-297 / humanoid.py)
-template <class Topo, bool HUM>
-__global__ void __launch_bounds__(BLOCK, B2G_MINBLOCKS) loco_step_kernel(const DevModel *__restrict__ gm, const int16_t *__restrict__ hf,
+#ifndef B2G_MINBLOCKS
+#define B2G_MINBLOCKS 4
+#endif
+template <int L, bool HF, bool HUM, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? B2G_MINBLOCKS : 1)) loco_step_kernel(const DevModel *__restrict__ gm, const int16_t *__restrict__ hf,
                                                           Buffers B, const __grid_constant__ b2g_task_params P,
-                                                          const float *__restrict__ actions_in, int N) {
+                                                          const float *__restrict__ actions_in, int N, int tiles_on) {
     __shared__ DevModel sm;
-    load_model(&sm, gm);
-    constexpr int L = Topo::L, NS = Topo::NS;
-    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ alignas(8) uint64_t mbar;
+    constexpr int EPB = BLOCK / L;
+    const int nd = P.num_actions;                       // == dofs for the locomotion tasks (checked by b2g_set_task)
+    const int env0 = blockIdx.x * EPB;
+    float4 *tile_smem = b2g_dyn_smem + (size_t)(tiles_on >> 8) * BLOCK;      // host passes the float4-per-thread offset in the high bits
+    const Tiles tl = prologue(&sm, &mbar, gm, tile_smem, (tiles_on & 1) != 0, env0, EPB, (const float *)B.p[B2G_T_ROOT_STATE],
+                              (const float *)B.p[B2G_T_DOF_STATE], actions_in, nd, nd);
+    using ST = Stepper<L, HF, BLOCK>;
+    const int gt = blockIdx.x * BLOCK + threadIdx.x;
     const int env = gt / L, lane = gt % L;
     const bool valid = env < N;
     const int e = valid ? env : N - 1;
-    const int nd = sm.nl - 1;
-
-    EnvState<Topo> st;
-    load_env<Topo>(sm, B, e, lane, st);
+    const int el = e - env0;                             // env index inside this block's tiles
+    const int NS = sm.ns;
+    ST st = make_stepper<L, HF, BLOCK>(&sm, hf, lane);
+    RootState rs; load_root(tl.root + 13 * el, rs);
 
     // ---- VecTask.step :374 clamp ; pre_physics_step (ant.py:281-285 / humanoid.py:281-285)
-    float a[NS];
-    int dof[NS];
+    const float2 *dofs = tl.dof + (size_t)el * nd;
+    const float *acts = tl.act + (size_t)el * nd;
     float *act_out = (float *)B.p[B2G_T_ACTIONS];
-#pragma unroll
+#pragma unroll 1
     for (int s = 0; s < NS; s++) {
-        dof[s] = sm.slot_link[s][lane] - 1;
-        const float v = actions_in[(size_t)e * nd + dof[s]];
-        a[s] = fminf(fmaxf(v, -P.clip_actions), P.clip_actions);
-        if (valid && act_out) act_out[(size_t)e * nd + dof[s]] = a[s];
-        st.act[s] = HUM ? (a[s] * P.motor_efforts[dof[s]] * P.power_scale) : (a[s] * P.joint_gears[dof[s]] * P.power_scale);
+        const int d = sm.slot_link[s][lane] - 1;
+        const float2 v = dofs[d];
+        const float a = fminf(fmaxf(acts[d], -P.clip_actions), P.clip_actions);
+        if (valid && act_out) act_out[(size_t)e * nd + d] = a;
+        st.set_joint(s, v.x, v.y, a * (HUM ? P.motor_efforts[d] : P.joint_gears[d]) * P.power_scale);
     }
 
-    // ---- control_freq_inv x gym.simulate (vec_task.py:379-382)
-    Ground gr{&sm, hf};
-    StepOut<Topo> out;
+    // ---- control_freq_inv x gym.simulate (vec_task.py:379-382).  control_freq_inv == 0: no simulate --
+    // the observation then reads the sensor / joint-force tensors as they stand (what refresh_*_tensor
+    // would return); used to pin the observation/reward arithmetic against the reference's golden vectors
+    const typename ST::Outputs o = make_outputs<ST>(sm, B, e, valid);
     const int total = P.control_freq_inv * sm.substeps;
-    for (int k = 0; k < total; k++) substep<Topo>(&sm, gr, lane, st, out, k == total - 1);
-
-    float sens[NS][6];
-#pragma unroll
-    for (int s = 0; s < NS; s++)
-#pragma unroll
-        for (int c = 0; c < 6; c++) sens[s][c] = 0.f;
-    if (total > 0) {
-        store_outputs<Topo>(sm, B, e, lane, valid, out, sens);
-    } else {
-        // control_freq_inv == 0: no gym.simulate this step -- the observation reads the sensor / joint
-        // force tensors as they stand (what refresh_*_tensor would return); used to pin the
-        // observation/reward arithmetic against the reference's golden vectors
-        const float *fs = (const float *)B.p[B2G_T_FORCE_SENSOR];
-        const float *df = (const float *)B.p[B2G_T_DOF_FORCE];
-#pragma unroll
-        for (int s = 0; s < NS; s++) {
-            const int link = sm.slot_link[s][lane], sk = sm.links[link].sensor;
-            if (sk >= 0 && fs)
-#pragma unroll
-                for (int c = 0; c < 6; c++) sens[s][c] = fs[((size_t)e * sm.nsens + sk) * 6 + c];
-            out.dof_force[s] = df ? df[(size_t)e * nd + link - 1] : 0.f;
-        }
-    }
+    for (int k = 0; k < total; k++) st.substep(rs, k == total - 1, o);
 
     // ---- post_physics_step (ant.py:287-297): progress, reset_idx, observations, reward
     long long *progress_b = (long long *)B.p[B2G_T_PROGRESS];
@@ -212,29 +205,29 @@ __global__ void __launch_bounds__(BLOCK, B2G_MINBLOCKS) loco_step_kernel(const D
         int *rc = (int *)B.p[B2G_T_RESET_COUNT];
         const uint32_t count = (uint32_t)rc[e];
         const uint32_t gid = (uint32_t)(e + P.env_id_offset);
-#pragma unroll
+#pragma unroll 1
         for (int s = 0; s < NS; s++) {
-            const float up = reset_uniform(P.seed, gid, count, dof[s]);
-            const float uv = reset_uniform(P.seed, gid, count, nd + dof[s]);
+            const int d = sm.slot_link[s][lane] - 1;
+            const float up = reset_uniform(P.seed, gid, count, d);
+            const float uv = reset_uniform(P.seed, gid, count, nd + d);
             const float pos = (P.reset_pos_noise - (-P.reset_pos_noise)) * up + (-P.reset_pos_noise);
             const float vel = (P.reset_vel_noise - (-P.reset_vel_noise)) * uv + (-P.reset_vel_noise);
-            st.q[s] = fmaxf(fminf(P.initial_dof_pos[dof[s]] + pos, P.dof_limits_upper[dof[s]]), P.dof_limits_lower[dof[s]]);
-            st.qd[s] = vel;
+            st.set_q(s, fmaxf(fminf(P.initial_dof_pos[d] + pos, P.dof_limits_upper[d]), P.dof_limits_lower[d]), vel);
         }
         const float *ir = (const float *)B.p[B2G_T_INITIAL_ROOT] + 13 * (size_t)e;
-        st.rp[0] = ir[0]; st.rp[1] = ir[1]; st.rp[2] = ir[2];
-        st.rq[0] = ir[3]; st.rq[1] = ir[4]; st.rq[2] = ir[5]; st.rq[3] = ir[6];
-        st.rv[0] = ir[7]; st.rv[1] = ir[8]; st.rv[2] = ir[9];
-        st.rw[0] = ir[10]; st.rw[1] = ir[11]; st.rw[2] = ir[12];
-        potentials = t_potential(P.target[0] - st.rp[0], P.target[1] - st.rp[1], P.dt);
+        rs.rp[0] = ir[0]; rs.rp[1] = ir[1]; rs.rp[2] = ir[2];
+        rs.rq[0] = ir[3]; rs.rq[1] = ir[4]; rs.rq[2] = ir[5]; rs.rq[3] = ir[6];
+        rs.rv[0] = ir[7]; rs.rv[1] = ir[8]; rs.rv[2] = ir[9];
+        rs.rw[0] = ir[10]; rs.rw[1] = ir[11]; rs.rw[2] = ir[12];
+        potentials = t_potential(P.target[0] - rs.rp[0], P.target[1] - rs.rp[1], P.dt);
         progress = 0;
         if (valid && lane == 0) rc[e] = (int)(count + 1);
     }
-    if (valid) store_env<Topo>(sm, B, e, lane, st);
+    if (valid && lane == 0 && !sm.root_fixed) store_root(B, e, rs);
 
     // compute_observations
     LocoRootObs ro;
-    loco_root_obs(P, st.rp, st.rq, st.rv, st.rw, HUM, ro);
+    loco_root_obs(P, rs.rp, rs.rq, rs.rv, rs.rw, HUM, ro);
     const float prev_potentials = potentials;     // prev_potentials_new = potentials.clone(), ant.py:390
     potentials = ro.potentials;
     float *obs = (float *)B.p[B2G_T_OBS] + (size_t)e * P.num_obs;
@@ -256,29 +249,38 @@ __global__ void __launch_bounds__(BLOCK, B2G_MINBLOCKS) loco_step_kernel(const D
     const int o_sens = HUM ? 12 + 3 * nd : 12 + 2 * nd;
     const int o_act = o_sens + 6 * sm.nsens;
     float actions_cost = 0.f, electricity = 0.f, at_limit = 0.f;
-#pragma unroll
+    float2 *dw = (float2 *)B.p[B2G_T_DOF_STATE] + (size_t)e * nd;
+#pragma unroll 1
     for (int s = 0; s < NS; s++) {
-        const int d = dof[s];
-        const float ps = t_unscale(st.q[s], P.dof_limits_lower[d], P.dof_limits_upper[d]);
-        const float vs = st.qd[s] * P.dof_vel_scale;
-        put(o_pos + d, ps); put(o_vel + d, vs); put(o_act + d, a[s]);
-        if (HUM) put(o_frc + d, out.dof_force[s] * P.contact_force_scale);
-        const int sk = sm.links[sm.slot_link[s][lane]].sensor;
-        if (sk >= 0) {
+        const int link = sm.slot_link[s][lane], d = link - 1;
+        const float2 qv = st.get_q(s);
+        if (valid) dw[d] = qv;
+        const float a = fminf(fmaxf(acts[d], -P.clip_actions), P.clip_actions);
+        const float ps = t_unscale(qv.x, P.dof_limits_lower[d], P.dof_limits_upper[d]);
+        const float vs = qv.y * P.dof_vel_scale;
+        put(o_pos + d, ps); put(o_vel + d, vs); put(o_act + d, a);
+        if (HUM) put(o_frc + d, (o.dof_force ? o.dof_force[d] : 0.f) * P.contact_force_scale);
+        const int sk = sm.links[link].sensor;
+        if (sk >= 0 && o.sensor) {
 #pragma unroll
-            for (int c = 0; c < 6; c++) put(o_sens + 6 * sk + c, sens[s][c] * P.contact_force_scale);
+            for (int c = 0; c < 6; c++) put(o_sens + 6 * sk + c, o.sensor[6 * sk + c] * P.contact_force_scale);
         }
         // compute_ant_reward (ant.py:353-355) / compute_humanoid_reward (humanoid.py:352-359)
-        actions_cost += a[s] * a[s];
+        actions_cost += a * a;
         if (HUM) {
             const float ratio = P.motor_efforts[d] / P.max_motor_effort;
             const float scaled = P.joints_at_limit_cost_scale * (fabsf(ps) - 0.98f) / 0.02f;
             at_limit += (fabsf(ps) > 0.98f) ? scaled * ratio : 0.f;
-            electricity += fabsf(a[s] * vs) * ratio;
+            electricity += fabsf(a * vs) * ratio;
         } else {
             at_limit += (ps > 0.99f) ? 1.f : 0.f;
-            electricity += fabsf(a[s] * vs);
+            electricity += fabsf(a * vs);
         }
+    }
+    if (lane == 0 && sm.links[0].sensor >= 0 && o.sensor) {
+        const int sk = sm.links[0].sensor;
+#pragma unroll
+        for (int c = 0; c < 6; c++) put(o_sens + 6 * sk + c, o.sensor[6 * sk + c] * P.contact_force_scale);
     }
     actions_cost = lane_sum<L>(actions_cost);
     electricity = lane_sum<L>(electricity);
@@ -289,12 +291,12 @@ __global__ void __launch_bounds__(BLOCK, B2G_MINBLOCKS) loco_step_kernel(const D
         const float heading_reward = (heading_proj > 0.8f) ? P.heading_weight : P.heading_weight * heading_proj / 0.8f;
         const float up_reward = (up_proj > 0.93f) ? P.up_weight : 0.f;
         const float progress_reward = potentials - prev_potentials;
-        float total = progress_reward + P.alive_reward + up_reward + heading_reward - P.actions_cost_scale * actions_cost -
-                      P.energy_cost_scale * electricity - (HUM ? at_limit : at_limit * P.joints_at_limit_cost_scale);
+        float total_r = progress_reward + P.alive_reward + up_reward + heading_reward - P.actions_cost_scale * actions_cost -
+                        P.energy_cost_scale * electricity - (HUM ? at_limit : at_limit * P.joints_at_limit_cost_scale);
         long long reset = 0;                       // reset_buf was cleared by reset_idx or was already 0
-        if (height < P.termination_height) { total = P.death_cost; reset = 1; }
+        if (height < P.termination_height) { total_r = P.death_cost; reset = 1; }
         if ((float)progress >= P.max_episode_length - 1.f) reset = 1;
-        ((float *)B.p[B2G_T_REW])[e] = total;
+        ((float *)B.p[B2G_T_REW])[e] = total_r;
         reset_b[e] = reset;
         progress_b[e] = progress;
         pot_b[e] = potentials; ppot_b[e] = prev_potentials;
@@ -309,24 +311,26 @@ __global__ void __launch_bounds__(BLOCK, B2G_MINBLOCKS) loco_step_kernel(const D
 
 // -------------------------------------------------------------------------------------------
 // One whole VecTask.step() of Cartpole (cartpole.py:131-163)
+template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) cartpole_step_kernel(const DevModel *__restrict__ gm, Buffers B,
                                                               const __grid_constant__ b2g_task_params P,
                                                               const float *__restrict__ actions_in, int N) {
-    using Topo = TopoChain2x1;
     __shared__ DevModel sm;
-    load_model(&sm, gm);
-    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ alignas(8) uint64_t mbar;
+    prologue(&sm, &mbar, gm, nullptr, false, 0, 0, nullptr, nullptr, nullptr, 0, 0);
+    using ST = Stepper<1, false, BLOCK>;
+    const int env = blockIdx.x * BLOCK + threadIdx.x;
     const bool valid = env < N;
     const int e = valid ? env : N - 1;
-    EnvState<Topo> st;
-    load_env<Topo>(sm, B, e, 0, st);
+    ST st = make_stepper<1, false, BLOCK>(&sm, nullptr, 0);
+    RootState rs; load_root((const float *)B.p[B2G_T_ROOT_STATE] + 13 * (size_t)e, rs);
+    const float2 *dofs = (const float2 *)B.p[B2G_T_DOF_STATE] + (size_t)e * 2;
     const float a = fminf(fmaxf(actions_in[e], -P.clip_actions), P.clip_actions);
-    st.act[0] = a * P.max_push_effort;   // cartpole.py:159-163: effort on DOF 0 only
-    st.act[1] = 0.f;
-    Ground gr{&sm, nullptr};
-    StepOut<Topo> out;
+    st.set_joint(0, dofs[0].x, dofs[0].y, a * P.max_push_effort);   // cartpole.py:159-163: effort on DOF 0 only
+    st.set_joint(1, dofs[1].x, dofs[1].y, 0.f);
+    typename ST::Outputs o; o.sensor = nullptr; o.dof_force = nullptr; o.net_contact = nullptr; o.write = false;
     const int total = P.control_freq_inv * sm.substeps;
-    for (int k = 0; k < total; k++) substep<Topo>(&sm, gr, 0, st, out, false);
+    for (int k = 0; k < total; k++) st.substep(rs, false, o);
     long long *progress_b = (long long *)B.p[B2G_T_PROGRESS];
     long long *reset_b = (long long *)B.p[B2G_T_RESET];
     long long progress = progress_b[e] + 1;
@@ -334,26 +338,26 @@ __global__ void __launch_bounds__(BLOCK) cartpole_step_kernel(const DevModel *__
         int *rc = (int *)B.p[B2G_T_RESET_COUNT];
         const uint32_t count = (uint32_t)rc[e], gid = (uint32_t)(e + P.env_id_offset);
 #pragma unroll
-        for (int s = 0; s < 2; s++) {
-            st.q[s] = 0.2f * (reset_uniform(P.seed, gid, count, s) - 0.5f);
-            st.qd[s] = 0.5f * (reset_uniform(P.seed, gid, count, 2 + s) - 0.5f);
-        }
+        for (int s = 0; s < 2; s++)
+            st.set_q(s, 0.2f * (reset_uniform(P.seed, gid, count, s) - 0.5f), 0.5f * (reset_uniform(P.seed, gid, count, 2 + s) - 0.5f));
         progress = 0;
         if (valid) rc[e] = (int)(count + 1);
     }
     if (!valid) return;
-    store_env<Topo>(sm, B, e, 0, st);
+    const float2 q0 = st.get_q(0), q1 = st.get_q(1);
+    float2 *dw = (float2 *)B.p[B2G_T_DOF_STATE] + (size_t)e * 2;
+    dw[0] = q0; dw[1] = q1;
     float *act_out = (float *)B.p[B2G_T_ACTIONS];
     if (act_out) act_out[e] = a;
     // compute_observations, cartpole.py:131-142
-    const float o[4] = {st.q[0], st.qd[0], st.q[1], st.qd[1]};
+    const float ob[4] = {q0.x, q0.y, q1.x, q1.y};
     float *obs = (float *)B.p[B2G_T_OBS] + 4 * (size_t)e;
     float *obsc = (float *)B.p[B2G_T_OBS_CLIPPED];
     obsc = (obsc && obsc != (float *)B.p[B2G_T_OBS]) ? obsc + 4 * (size_t)e : nullptr;
 #pragma unroll
-    for (int c = 0; c < 4; c++) { obs[c] = o[c]; if (obsc) obsc[c] = fminf(fmaxf(o[c], -P.clip_obs), P.clip_obs); }
+    for (int c = 0; c < 4; c++) { obs[c] = ob[c]; if (obsc) obsc[c] = fminf(fmaxf(ob[c], -P.clip_obs), P.clip_obs); }
     float rew; long long reset = 0;
-    cartpole_reward(st.q[1], st.qd[1], st.qd[0], st.q[0], P.reset_dist, progress, P.max_episode_length, rew, reset);
+    cartpole_reward(q1.x, q1.y, q0.y, q0.x, P.reset_dist, progress, P.max_episode_length, rew, reset);
     ((float *)B.p[B2G_T_REW])[e] = rew;
     reset_b[e] = reset; progress_b[e] = progress;
     uint8_t *to = (uint8_t *)B.p[B2G_T_TIMEOUT];
@@ -362,9 +366,9 @@ __global__ void __launch_bounds__(BLOCK) cartpole_step_kernel(const DevModel *__
 
 // -------------------------------------------------------------------------------------------
 // gym.refresh_rigid_body_state_tensor(): forward kinematics, one thread per env, any topology
-__global__ void __launch_bounds__(BLOCK) body_state_kernel(const DevModel *__restrict__ gm, Buffers B, int N) {
+__global__ void __launch_bounds__(128) body_state_kernel(const DevModel *__restrict__ gm, Buffers B, int N) {
     __shared__ DevModel sm;
-    load_model(&sm, gm);
+    load_model_full(&sm, gm);
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= N) return;
     const int nl = sm.nl, nd = nl - 1;
@@ -380,7 +384,7 @@ __global__ void __launch_bounds__(BLOCK) body_state_kernel(const DevModel *__res
         const float2 qv = d[i - 1];
         float Rt[9], ax[3] = {lk.axis[0], lk.axis[1], lk.axis[2]}, w[3], lp[3] = {lk.lpos[0], lk.lpos[1], lk.lpos[2]}, dd[3], wxd[3];
         matmul(R[p], lk.R0, Rt); matvec(Rt, ax, w);
-        if (lk.jtype == 0) {
+        if (!(lk.flags & LF_SLIDE)) {
             float sn, cs; sincosf(qv.x, &sn, &cs);
             const float oc = 1.f - cs;
             for (int j = 0; j < 3; j++) {
@@ -400,8 +404,8 @@ __global__ void __launch_bounds__(BLOCK) body_state_kernel(const DevModel *__res
         cross(wv[p], dd, wxd);
         for (int c = 0; c < 3; c++) {
             x[i][c] = x[p][c] + dd[c];
-            lv[i][c] = lv[p][c] + wxd[c] + (lk.jtype == 1 ? w[c] * qv.y : 0.f);
-            wv[i][c] = wv[p][c] + (lk.jtype == 0 ? w[c] * qv.y : 0.f);
+            lv[i][c] = lv[p][c] + wxd[c] + ((lk.flags & LF_SLIDE) ? w[c] * qv.y : 0.f);
+            wv[i][c] = wv[p][c] + ((lk.flags & LF_SLIDE) ? 0.f : w[c] * qv.y);
         }
     }
     float *bs = (float *)B.p[B2G_T_RIGID_BODY_STATE] + 13 * (size_t)e * sm.nb;
@@ -419,13 +423,12 @@ __global__ void __launch_bounds__(BLOCK) body_state_kernel(const DevModel *__res
 // ============================================================================================
 // host side
 // ============================================================================================
-enum TopoKind { TK_NONE = 0, TK_CHAIN2x1, TK_CHAIN2x4, TK_CHAIN3x4, TK_ANT1, TK_HUM1 };
-
 struct b2g_sim {
     int device = 0;
     int num_envs = 0;
-    TopoKind topo = TK_NONE;
     int lanes = 1;
+    int block = 128;             // threads per CTA, chosen so the slot state fits in shared memory
+    size_t dyn_smem = 0;
     DevModel hm;                 // host copy
     DevModel *dm = nullptr;      // device copy
     int16_t *d_hf = nullptr;
@@ -445,36 +448,47 @@ extern "C" const char *b2g_last_error(void) { return g_err.c_str(); }
 extern "C" int b2g_version(void) { return B2G_VERSION; }
 extern "C" int64_t b2g_launch_count(const b2g_sim *sim) { return sim ? sim->launches : 0; }
 
-// does the subtree pattern under the root match `L` identical chains of `ns` links?
-static bool match_chains(const b2g_model *m, int L, int ns, int slot_link[MAX_SLOTS][MAX_LANES]) {
-    if (m->nl != 1 + L * ns) return false;
-    std::vector<int> heads;
-    for (int i = 1; i < m->nl; i++) if (m->parent[i] == 0) heads.push_back(i);
-    if ((int)heads.size() != L) return false;
-    for (int l = 0; l < L; l++) {
-        int cur = heads[l];
-        for (int s = 0; s < ns; s++) {
-            slot_link[s][l] = cur;
-            if (s + 1 < ns) {
-                int next = -1, cnt = 0;
-                for (int i = 1; i < m->nl; i++) if (m->parent[i] == cur) { next = i; cnt++; }
-                if (cnt != 1) return false;
-                cur = next;
-            } else {
-                for (int i = 1; i < m->nl; i++) if (m->parent[i] == cur) return false;
-            }
-        }
-    }
-    return true;
+// Decompose the tree into L lanes x NS slots: the sub-trees hanging off the root are dealt to the
+// lanes; L > 1 needs L sub-trees of identical shape (the SIMT lanes run the same slot program).
+static void subtree_dfs(const b2g_model *m, int i, std::vector<int> &out) {
+    out.push_back(i);
+    for (int c = i + 1; c < m->nl; c++) if (m->parent[c] == i) subtree_dfs(m, c, out);
 }
-template <class Topo>
-static bool match_single_lane(const b2g_model *m, int slot_link[MAX_SLOTS][MAX_LANES]) {
-    if (m->nl != Topo::NS + 1) return false;
-    for (int s = 0; s < Topo::NS; s++) {
-        slot_link[s][0] = s + 1;
-        if (m->parent[s + 1] != Topo::ps(s) + 1) return false;
+static int decompose(const b2g_model *m, bool single, DevModel &h) {
+    std::vector<std::vector<int>> subs;
+    for (int i = 1; i < m->nl; i++) if (m->parent[i] == 0) { subs.emplace_back(); subtree_dfs(m, i, subs.back()); }
+    int L = 1;
+    auto shape = [&](const std::vector<int> &v) {
+        std::vector<int> sh;
+        for (int k = 0; k < (int)v.size(); k++) {
+            int p = m->parent[v[k]], ps = -1;
+            for (int j = 0; j < k; j++) if (v[j] == p) ps = j;
+            sh.push_back(ps);
+        }
+        return sh;
+    };
+    if (!single && (subs.size() == 4 || subs.size() == 2)) {
+        bool same = true;
+        for (size_t l = 1; l < subs.size(); l++) same = same && shape(subs[l]) == shape(subs[0]);
+        if (same) L = (int)subs.size();
     }
-    return true;
+    std::vector<std::vector<int>> lanes(L);
+    if (L > 1) lanes = subs; else for (auto &v : subs) lanes[0].insert(lanes[0].end(), v.begin(), v.end());
+    const int ns = (int)lanes[0].size();
+    if (ns > MAX_SLOTS) return -1;
+    h.ns = ns; h.lanes = L;
+    for (int l = 0; l < L; l++) for (int s = 0; s < ns; s++) h.slot_link[s][l] = lanes[l][s];
+    for (int s = 0; s < ns; s++) {
+        int p = m->parent[lanes[0][s]], ps = -1;
+        for (int j = 0; j < s; j++) if (lanes[0][j] == p) ps = j;
+        h.slot_parent[s] = ps; h.slot_acc[s] = -1;
+    }
+    h.nacc = 0;
+    for (int s = 0; s < ns; s++) {
+        const int ps = h.slot_parent[s];
+        if (ps >= 0 && ps != s - 1 && h.slot_acc[ps] < 0) h.slot_acc[ps] = h.nacc++;
+    }
+    return 0;
 }
 
 extern "C" int b2g_create(const b2g_model *m, const b2g_sim_params *sp, int32_t num_envs, int32_t device, b2g_sim **out) {
@@ -498,13 +512,15 @@ extern "C" int b2g_create(const b2g_model *m, const b2g_sim_params *sp, int32_t 
     h.kn = m->contact_kn; h.cn = m->contact_cn; h.vs2 = m->contact_vs * m->contact_vs;
     // topology
     const char *force1 = getenv("B2G_SINGLE_LANE");
-    bool single = force1 && force1[0] == '1';
-    if (!single && match_chains(m, 4, 2, h.slot_link)) { s->topo = TK_CHAIN2x4; s->lanes = 4; }
-    else if (!single && match_chains(m, 4, 3, h.slot_link)) { s->topo = TK_CHAIN3x4; s->lanes = 4; }
-    else if (match_chains(m, 1, 2, h.slot_link)) { s->topo = TK_CHAIN2x1; s->lanes = 1; }
-    else if (match_single_lane<TopoAnt1>(m, h.slot_link)) { s->topo = TK_ANT1; s->lanes = 1; }
-    else if (match_single_lane<TopoHumanoid1>(m, h.slot_link)) { s->topo = TK_HUM1; s->lanes = 1; }
-    else { delete s; return fail(B2G_E_UNSUPPORTED, "b2g_create: no compiled kernel for this articulation topology"); }
+    if (decompose(m, force1 && force1[0] == '1', h) != 0) { delete s; return fail(B2G_E_INVALID, "b2g_create: too many links per lane"); }
+    s->lanes = h.lanes;
+    {   // CTA size: the per-thread slot state must fit in shared memory, preferably several CTAs per SM
+        const size_t per_thread = ((size_t)(h.ns + 1) * SLOT_F4 + (size_t)(h.nacc + 1) * ACC_F4) * sizeof(float4);
+        int blk = 128;
+        while (blk > 32 && per_thread * blk > 96 * 1024) blk >>= 1;
+        if (per_thread * blk > 200 * 1024) { delete s; return fail(B2G_E_INVALID, "b2g_create: articulation too large for shared-memory slot state"); }
+        s->block = blk; s->dyn_smem = per_thread * blk;
+    }
     // links
     std::vector<int> order(m->ncp);
     for (int i = 0; i < m->ncp; i++) order[i] = i;
@@ -516,7 +532,10 @@ extern "C" int b2g_create(const b2g_model *m, const b2g_sim_params *sp, int32_t 
         for (int c = 0; c < 4; c++) h.body_quat[b][c] = m->body_quat[4 * b + c];
     }
     for (int i = 0; i < m->nl; i++) h.link_parent[i] = m->parent[i];
-    for (int k = 0; k < m->nsens; k++) h.sensor_body[k] = m->sensor_body[k];
+    for (int k = 0; k < m->nsens; k++) {
+        h.sensor_body[k] = m->sensor_body[k];
+        for (int c = 0; c < 3; c++) h.sensor_bpos[k][c] = m->body_pos[3 * m->sensor_body[k] + c];
+    }
     for (int i = 0; i < m->nl; i++) {
         LinkC &l = h.links[i];
         const float *q = m->lquat + 4 * i;
@@ -532,7 +551,10 @@ extern "C" int b2g_create(const b2g_model *m, const b2g_sim_params *sp, int32_t 
         l.armature = m->armature[i]; l.damping = m->damping[i]; l.stiffness = m->stiffness[i];
         l.lower = m->lower[i]; l.upper = m->upper[i]; l.effort = m->effort[i];
         l.kp = m->kp[i]; l.kd = m->kd[i]; l.limit_k = m->limit_k[i]; l.limit_d = m->limit_d[i];
-        l.jtype = m->jtype[i]; l.limited = m->limited[i]; l.drive_mode = m->drive_mode[i];
+        {
+            const bool ident = fabsf(R[0] - 1.f) < 1e-7f && fabsf(R[4] - 1.f) < 1e-7f && fabsf(R[8] - 1.f) < 1e-7f;
+            l.flags = (m->jtype[i] == 1 ? LF_SLIDE : 0) | (m->limited[i] ? LF_LIMITED : 0) | (m->drive_mode[i] == 1 ? LF_POSDRIVE : 0) | (ident ? LF_R0_IDENTITY : 0);
+        }
         l.sensor = -1;
         l.cp_begin = l.cp_end = 0;
     }
@@ -598,20 +620,36 @@ static int require(const b2g_sim *s, std::initializer_list<int> slots, const cha
     return B2G_OK;
 }
 
+template <typename K>
+static int set_smem(K kernel, size_t bytes) {
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return B2G_OK;
+}
+#define B2G_LAUNCH(KERNEL, ...)                                                                  \
+    do {                                                                                          \
+        int rc_ = set_smem(KERNEL, s->dyn_smem); if (rc_) return rc_;                             \
+        KERNEL<<<grid, blk, s->dyn_smem, st>>>(__VA_ARGS__);                                      \
+    } while (0)
+// dispatch on (lanes, height field, CTA size)
+#define B2G_DISPATCH_LHB(NAME, ...)                                                                                   \
+    do {                                                                                                               \
+        const bool hf_ = s->d_hf != nullptr;                                                                           \
+        if (s->lanes == 4 && !hf_ && blk == 128) B2G_LAUNCH((NAME<4, false, 128>), __VA_ARGS__);                       \
+        else if (s->lanes == 4 && hf_ && blk == 128) B2G_LAUNCH((NAME<4, true, 128>), __VA_ARGS__);                    \
+        else if (s->lanes == 2 && !hf_ && blk == 128) B2G_LAUNCH((NAME<2, false, 128>), __VA_ARGS__);                  \
+        else if (s->lanes == 1 && !hf_ && blk == 128) B2G_LAUNCH((NAME<1, false, 128>), __VA_ARGS__);                  \
+        else if (s->lanes == 1 && !hf_ && blk == 64) B2G_LAUNCH((NAME<1, false, 64>), __VA_ARGS__);                    \
+        else if (s->lanes == 1 && !hf_ && blk == 32) B2G_LAUNCH((NAME<1, false, 32>), __VA_ARGS__);                    \
+        else return fail(B2G_E_UNSUPPORTED, "no kernel instantiated for this (lanes, terrain, CTA size) combination"); \
+    } while (0)
+
 extern "C" int b2g_simulate(b2g_sim *s, void *stream) {
     if (!s) return fail(B2G_E_INVALID, "b2g_simulate: null sim");
     int rc = require(s, {B2G_T_ROOT_STATE, B2G_T_DOF_STATE}, "b2g_simulate"); if (rc) return rc;
     CUDA_TRY(cudaSetDevice(s->device));
     cudaStream_t st = (cudaStream_t)stream;
-    const int N = s->num_envs, grid = (N * s->lanes + BLOCK - 1) / BLOCK;
-    switch (s->topo) {
-        case TK_CHAIN2x1: simulate_kernel<TopoChain2x1><<<grid, BLOCK, 0, st>>>(s->dm, s->d_hf, s->buf, N); break;
-        case TK_CHAIN2x4: simulate_kernel<TopoChain2x4><<<grid, BLOCK, 0, st>>>(s->dm, s->d_hf, s->buf, N); break;
-        case TK_CHAIN3x4: simulate_kernel<TopoChain3x4><<<grid, BLOCK, 0, st>>>(s->dm, s->d_hf, s->buf, N); break;
-        case TK_ANT1: simulate_kernel<TopoAnt1><<<grid, BLOCK, 0, st>>>(s->dm, s->d_hf, s->buf, N); break;
-        case TK_HUM1: simulate_kernel<TopoHumanoid1><<<grid, BLOCK, 0, st>>>(s->dm, s->d_hf, s->buf, N); break;
-        default: return fail(B2G_E_UNSUPPORTED, "b2g_simulate: unsupported topology");
-    }
+    const int N = s->num_envs, blk = s->block, grid = (N * s->lanes + blk - 1) / blk;
+    B2G_DISPATCH_LHB(simulate_kernel, s->dm, s->d_hf, s->buf, N);
     s->launches++;
     CUDA_TRY(cudaGetLastError());
     return B2G_OK;
@@ -622,7 +660,7 @@ extern "C" int b2g_refresh_rigid_body_state(b2g_sim *s, void *stream) {
     int rc = require(s, {B2G_T_ROOT_STATE, B2G_T_DOF_STATE, B2G_T_RIGID_BODY_STATE}, "b2g_refresh_rigid_body_state"); if (rc) return rc;
     CUDA_TRY(cudaSetDevice(s->device));
     const int N = s->num_envs;
-    body_state_kernel<<<(N + BLOCK - 1) / BLOCK, BLOCK, 0, (cudaStream_t)stream>>>(s->dm, s->buf, N);
+    body_state_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(s->dm, s->buf, N);
     s->launches++;
     CUDA_TRY(cudaGetLastError());
     return B2G_OK;
@@ -632,13 +670,11 @@ extern "C" int b2g_set_task(b2g_sim *s, const b2g_task_params *t) {
     if (!s || !t) return fail(B2G_E_INVALID, "b2g_set_task: null argument");
     const int nd = s->hm.nl - 1;
     if (t->task == B2G_TASK_CARTPOLE) {
-        if (s->topo != TK_CHAIN2x1 || t->num_obs != 4 || t->num_actions != 1) return fail(B2G_E_UNSUPPORTED, "cartpole task needs the 2-DOF fixed-base chain, 4 obs, 1 action");
+        if (s->hm.nl != 3 || !s->hm.root_fixed || t->num_obs != 4 || t->num_actions != 1) return fail(B2G_E_UNSUPPORTED, "cartpole task needs the 2-DOF fixed-base chain, 4 obs, 1 action");
     } else if (t->task == B2G_TASK_ANT) {
-        if ((s->topo != TK_CHAIN2x4 && s->topo != TK_ANT1) || t->num_actions != nd || t->num_obs != 12 + 3 * nd + 6 * s->hm.nsens)
-            return fail(B2G_E_UNSUPPORTED, "ant task: topology / observation size mismatch");
+        if (t->num_actions != nd || t->num_obs != 12 + 3 * nd + 6 * s->hm.nsens) return fail(B2G_E_UNSUPPORTED, "ant task: observation size does not match the articulation");
     } else if (t->task == B2G_TASK_HUMANOID) {
-        if (s->topo != TK_HUM1 || t->num_actions != nd || t->num_obs != 12 + 4 * nd + 6 * s->hm.nsens)
-            return fail(B2G_E_UNSUPPORTED, "humanoid task: topology / observation size mismatch");
+        if (t->num_actions != nd || t->num_obs != 12 + 4 * nd + 6 * s->hm.nsens) return fail(B2G_E_UNSUPPORTED, "humanoid task: observation size does not match the articulation");
     } else return fail(B2G_E_UNSUPPORTED, "b2g_set_task: unknown task id");
     if (t->control_freq_inv < 0) return fail(B2G_E_INVALID, "control_freq_inv < 0");
     s->task = *t; s->has_task = true;
@@ -656,14 +692,33 @@ extern "C" int b2g_task_step(b2g_sim *s, const float *actions, void *stream) {
     if (s->buf.p[B2G_T_ACTIONS] && s->buf_bytes[B2G_T_ACTIONS] < N * P.num_actions * 4) return fail(B2G_E_INVALID, "ACTIONS buffer too small");
     CUDA_TRY(cudaSetDevice(s->device));
     cudaStream_t st = (cudaStream_t)stream;
-    const int grid = ((int)N * s->lanes + BLOCK - 1) / BLOCK;
+    const int blk = s->block, grid = ((int)N * s->lanes + blk - 1) / blk;
     if (P.task == B2G_TASK_CARTPOLE) {
-        cartpole_step_kernel<<<grid, BLOCK, 0, st>>>(s->dm, s->buf, P, actions, (int)N);
+        if (blk != 128) return fail(B2G_E_UNSUPPORTED, "cartpole: unexpected CTA size");
+        B2G_LAUNCH((cartpole_step_kernel<128>), s->dm, s->buf, P, actions, (int)N);
     } else {
         rc = require(s, {B2G_T_POTENTIALS, B2G_T_PREV_POTENTIALS, B2G_T_INITIAL_ROOT}, "b2g_task_step"); if (rc) return rc;
-        if (P.task == B2G_TASK_ANT && s->topo == TK_CHAIN2x4) loco_step_kernel<TopoChain2x4, false><<<grid, BLOCK, 0, st>>>(s->dm, s->d_hf, s->buf, P, actions, (int)N);
-        else if (P.task == B2G_TASK_ANT) loco_step_kernel<TopoAnt1, false><<<grid, BLOCK, 0, st>>>(s->dm, s->d_hf, s->buf, P, actions, (int)N);
-        else loco_step_kernel<TopoHumanoid1, true><<<grid, BLOCK, 0, st>>>(s->dm, s->d_hf, s->buf, P, actions, (int)N);
+        const bool hum = P.task == B2G_TASK_HUMANOID;
+        // state tiles by bulk copy: whole blocks only, every tile a multiple of 16 bytes
+        const int epb = blk / s->lanes, ndof = s->hm.nl - 1;
+        const bool tiles = (N % epb == 0) && ((epb * 52) % 16 == 0) && ((epb * ndof * 8) % 16 == 0) && ((epb * ndof * 4) % 16 == 0);
+        const size_t state_f4 = (size_t)(s->hm.ns + 1) * SLOT_F4 + (size_t)(s->hm.nacc + 1) * ACC_F4;   // float4 per thread
+        const size_t tile_bytes = tiles ? (size_t)epb * (52 + ndof * 12) : 0;
+        const size_t dyn = s->dyn_smem + ((tile_bytes + 15) & ~(size_t)15);
+        const int tiles_arg = (int)(state_f4 << 8) | (tiles ? 1 : 0);
+#define LOCO(LN, HM, BK)                                                                                              \
+    do {                                                                                                               \
+        int rc_ = set_smem(loco_step_kernel<LN, false, HM, BK>, dyn); if (rc_) return rc_;                            \
+        loco_step_kernel<LN, false, HM, BK><<<grid, blk, dyn, st>>>(s->dm, s->d_hf, s->buf, P, actions, (int)N, tiles_arg); \
+    } while (0)
+        if (s->d_hf) return fail(B2G_E_UNSUPPORTED, "locomotion tasks run on the ground plane");
+        if (!hum && s->lanes == 4 && blk == 128) LOCO(4, false, 128);
+        else if (!hum && s->lanes == 1 && blk == 128) LOCO(1, false, 128);
+        else if (hum && s->lanes == 1 && blk == 128) LOCO(1, true, 128);
+        else if (hum && s->lanes == 1 && blk == 64) LOCO(1, true, 64);
+        else if (hum && s->lanes == 1 && blk == 32) LOCO(1, true, 32);
+        else return fail(B2G_E_UNSUPPORTED, "no locomotion kernel instantiated for this (lanes, CTA size) combination");
+#undef LOCO
     }
     s->launches++;
     CUDA_TRY(cudaGetLastError());

@@ -13,13 +13,18 @@
 //     contact spring-damper-friction are integrated implicitly by augmenting the joint-space
 //     diagonal and the link inertia (DESIGN.md "time stepping").
 //
-// Work decomposition: an environment is owned by L lanes of a warp (L = 1, 2 or 4).  Each lane
-// owns whole sub-trees hanging off the root as a fixed sequence of NS "slots" whose parent slot is
-// compile-time (Topo::ps), so all per-slot state lives in registers; the root is replicated on
-// the L lanes and the lanes' sub-tree contributions meet in an xor-butterfly (warp shuffles).
+// Work decomposition: an environment is owned by L lanes of a warp (L = 1, 2 or 4).  Each lane owns
+// whole sub-trees hanging off the root as a sequence of "slots" (one 1-DOF link each, parents
+// before children); the root is replicated on the L lanes and the lanes' sub-tree contributions
+// meet in an xor-butterfly (warp shuffles).  The three ABA sweeps are ROLLED loops over the slots:
+// per-slot state (48 floats) lives in shared memory laid out [slot][float4][thread] (conflict-free
+// 128-bit accesses), the articulated inertia being swept travels in registers along chains.  This
+// keeps the kernel ~1/5 the code size and ~1/2 the registers of the fully unrolled first version
+// (profiles/r1_v1_*: 88 KB of SASS, 255 registers, 24 % of issue stalls "no instruction").
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stddef.h>
 
 #ifndef B2G_FAST_TRIG
 #define B2G_FAST_TRIG 1
@@ -36,6 +41,7 @@ constexpr int MAX_LANES = 4;
 // ---------------------------------------------------------------------------------------------
 // model constants (global memory -> shared memory at kernel start; strides are odd so that the
 // L lanes of an env, which read different links at the same time, hit different banks)
+enum : int { LF_SLIDE = 1, LF_LIMITED = 2, LF_POSDRIVE = 4, LF_R0_IDENTITY = 8 };
 struct LinkC {
     float R0[9];          // link frame in the parent link frame at q = 0, row-major
     float lpos[3];
@@ -44,11 +50,11 @@ struct LinkC {
     float Ic[6];          // xx yy zz xy xz yz about the COM, link axes
     float mass;
     float armature, damping, stiffness, lower, upper, effort, kp, kd, limit_k, limit_d;
-    int jtype, limited, drive_mode;
+    int flags;            // LF_*
     int cp_begin, cp_end; // contact spheres of this link: [begin, end) in the link-sorted cp array
     int sensor;           // force sensor attached to this link's body (-1 none)
-};                        // 41 words
-static_assert(sizeof(LinkC) == 41 * 4, "LinkC stride");
+};                        // 39 words (odd: the L lanes of an env read different links -> different banks)
+static_assert(sizeof(LinkC) == 39 * 4, "LinkC stride");
 
 struct CpC {
     float pos[3];
@@ -58,7 +64,10 @@ struct CpC {
 };                        // 7 words
 static_assert(sizeof(CpC) == 7 * 4, "CpC stride");
 
-struct DevModel {
+// Hot part first (what the step kernels read), 16-byte aligned regions so that the model reaches
+// shared memory as three bulk-async copies (header, links[0..nl), cps[0..ncp)); the cold tail is
+// only read by the forward-kinematics kernel.
+struct alignas(16) DevModel {
     int nl, ncp, nb, nsens;
     int root_fixed, gravity_on, substeps, has_hf;
     float h;              // sub-step length dt / substeps
@@ -66,42 +75,53 @@ struct DevModel {
     float kn, cn, vs2;    // contact stiffness, damping, (slip regularisation speed)^2
     int hf_nx, hf_ny;
     float hf_inv_scale, hf_scale, hf_vscale, hf_ox, hf_oy;
+    int ns, lanes, nacc;  // slots per lane, lanes per env, shared-memory accumulators per thread (excl. the root's)
+    int pad0[3];
     int slot_link[MAX_SLOTS][MAX_LANES];   // (slot, lane) -> link index
+    int slot_parent[MAX_SLOTS];            // parent slot (-1 = root), the same for every lane
+    int slot_acc[MAX_SLOTS];               // accumulator index of a slot with non-adjacent children, else -1
     int sensor_body[MAX_SENS];
-    int body_link[MAX_LINKS];
+    float sensor_bpos[MAX_SENS][3];        // body-frame origin of the sensor's body in its link frame
     int link_body[MAX_LINKS];              // first body riding on the link (-1: massless virtual link)
+    alignas(16) LinkC links[MAX_LINKS];
+    alignas(16) CpC cps[MAX_CP];
+    // ---- cold
+    alignas(16) int body_link[MAX_LINKS];
     int link_parent[MAX_LINKS];
     float body_pos[MAX_LINKS][3];
     float body_quat[MAX_LINKS][4];
-    LinkC links[MAX_LINKS];
-    CpC cps[MAX_CP];
 };
+static_assert(offsetof(DevModel, links) % 16 == 0 && offsetof(DevModel, cps) % 16 == 0, "bulk-copy alignment");
 
 // ---------------------------------------------------------------------------------------------
-// compile-time topologies: L lanes per env, NS slots per lane, ps(s) = parent slot (-1 = root)
-struct TopoChain2x4 {   // Ant: 4 legs x (hip, ankle)                         nv_ant.xml:47-78
-    static constexpr int L = 4, NS = 2;
-    __host__ __device__ static constexpr int ps(int s) { return s - 1; }
-};
-struct TopoChain3x4 {   // ANYmal: 4 legs x (HAA, HFE, KFE)                   anymal_minimal.urdf
-    static constexpr int L = 4, NS = 3;
-    __host__ __device__ static constexpr int ps(int s) { return s - 1; }
-};
-struct TopoChain2x1 {   // Cartpole: slider -> cart -> pole                   cartpole.urdf:61-75
-    static constexpr int L = 1, NS = 2;
-    __host__ __device__ static constexpr int ps(int s) { return s - 1; }
-};
-struct TopoAnt1 {       // Ant on one lane (comparison / fallback)
-    static constexpr int L = 1, NS = 8;
-    __host__ __device__ static constexpr int ps(int s) { return (s & 1) ? s - 1 : -1; }
-};
-struct TopoHumanoid1 {  // Humanoid, 21 1-DOF links on one lane                nv_humanoid.xml:36-136
-    static constexpr int L = 1, NS = 21;
-    __host__ __device__ static constexpr int ps(int s) {
-        constexpr int p[21] = {-1, 0, 1, 2, 3, 4, 5, 6, 7, 2, 9, 10, 11, 12, 13, -1, 15, 16, -1, 18, 19};
-        return p[s];
-    }
-};
+// bulk-async (TMA) copies + mbarrier, sm_90+ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_wait() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------
 // small vector helpers (all fully inlined, arrays are register-resident after unrolling)
@@ -218,27 +238,6 @@ __device__ __forceinline__ void sym6_solve(const float IA[21], const float ba[3]
     xa[0] = x[0]; xa[1] = x[1]; xa[2] = x[2]; xl[0] = x[3]; xl[1] = x[4]; xl[2] = x[5];
 }
 
-// ---------------------------------------------------------------------------------------------
-// per-env dynamic state held in registers across the sub-steps of one control step
-template <class Topo>
-struct EnvState {
-    float rp[3];      // root position (world)
-    float rq[4];      // root quaternion xyzw
-    float rv[3];      // root linear velocity (world, of the root origin)
-    float rw[3];      // root angular velocity (world)
-    float q[Topo::NS], qd[Topo::NS];
-    float act[Topo::NS];   // actuation force (effort mode) or position target (position drive)
-};
-
-// outputs of the last sub-step that the tasks read
-template <class Topo>
-struct StepOut {
-    float cfF[Topo::NS + 1][3];   // net contact force on slot's link (index NS = root), world axes
-    float cfT[Topo::NS + 1][3];   // net contact torque about the LINK origin, world axes
-    float dof_force[Topo::NS];
-    float R[Topo::NS + 1][9];     // link orientation at the start of the last sub-step
-};
-
 struct Ground {
     const DevModel *m;
     const int16_t *hf;
@@ -261,61 +260,6 @@ struct Ground {
     }
 };
 
-// contact spheres of one link against the ground.  Pass A (ACCUM): adds the explicit force to the
-// bias (pa, pl) and the implicit term h*J^T G J to IA.  Pass B (!ACCUM, after the accelerations
-// are known): accumulates the force actually applied over the sub-step, F = F0 - h*G*(J a).
-template <bool ACCUM>
-__device__ __forceinline__ void link_contacts(const DevModel *m, const Ground &gr, const LinkC &lk, const float rp[3],
-                                              const float R[9], const float x[3], const float vw[3], const float vl[3],
-                                              float IA[21], float pa[3], float pl[3],
-                                              const float aw[3], const float al[3], float F[3], float T[3],
-                                              int cp_first, int cp_step) {
-    const float h = m->h;
-    for (int k = lk.cp_begin + cp_first; k < lk.cp_end; k += cp_step) {
-        const CpC &cp = m->cps[k];
-        float pc[3], lp[3] = {cp.pos[0], cp.pos[1], cp.pos[2]};
-        matvec(R, lp, pc);
-        pc[0] += x[0]; pc[1] += x[1]; pc[2] += x[2];          // sphere centre relative to O
-        float hg, n[3];
-        gr.sample(rp[0] + pc[0], rp[1] + pc[1], hg, n);
-        float d = cp.radius - (rp[2] + pc[2] - hg) * n[2];
-        if (d <= 0.f) continue;
-        float r[3] = {pc[0] - cp.radius * n[0], pc[1] - cp.radius * n[1], pc[2] - cp.radius * n[2]};
-        float wxr[3]; cross(vw, r, wxr);
-        float u[3] = {vl[0] + wxr[0], vl[1] + wxr[1], vl[2] + wxr[2]};
-        float gn = m->cn + h * m->kn;
-        float un = dot3(u, n);
-        float Fn = m->kn * d - gn * un;
-        if (Fn <= 0.f) continue;
-        float ut[3] = {u[0] - un * n[0], u[1] - un * n[1], u[2] - un * n[2]};
-        float gam = cp.mu * Fn * rsqrtf(dot3(ut, ut) + m->vs2);
-        float F0[3] = {Fn * n[0] - gam * ut[0], Fn * n[1] - gam * ut[1], Fn * n[2] - gam * ut[2]};
-        if (ACCUM) {
-            float rxF[3]; cross(r, F0, rxF);
-            pa[0] -= rxF[0]; pa[1] -= rxF[1]; pa[2] -= rxF[2];
-            pl[0] -= F0[0]; pl[1] -= F0[1]; pl[2] -= F0[2];
-            // J^T G J with G = gam*1 + (gn-gam) n n^T ; rows of J: j_k = (r x e_k ; e_k)
-            float hg_ = h * gam;
-            const float jx[3] = {0.f, r[2], -r[1]}, jy[3] = {-r[2], 0.f, r[0]}, jz[3] = {r[1], -r[0], 0.f};
-            const float ex[3] = {1.f, 0.f, 0.f}, ey[3] = {0.f, 1.f, 0.f}, ez[3] = {0.f, 0.f, 1.f};
-            sym6_rank1(IA, hg_, jx, ex); sym6_rank1(IA, hg_, jy, ey); sym6_rank1(IA, hg_, jz, ez);
-            float rxn[3]; cross(r, n, rxn);
-            sym6_rank1(IA, h * (gn - gam), rxn, n);
-        } else {
-            float axr[3]; cross(aw, r, axr);
-            float Ja[3] = {al[0] + axr[0], al[1] + axr[1], al[2] + axr[2]};
-            float Jan = dot3(Ja, n);
-            float Fk[3];
-#pragma unroll
-            for (int c = 0; c < 3; c++) Fk[c] = F0[c] - h * (gam * Ja[c] + (gn - gam) * Jan * n[c]);
-            float rl[3] = {r[0] - x[0], r[1] - x[1], r[2] - x[2]}, t[3];
-            cross(rl, Fk, t);
-#pragma unroll
-            for (int c = 0; c < 3; c++) { F[c] += Fk[c]; T[c] += t[c]; }
-        }
-    }
-}
-
 // xor-butterfly sum over the L lanes of an env
 template <int L>
 __device__ __forceinline__ float lane_sum(float v) {
@@ -325,121 +269,444 @@ __device__ __forceinline__ float lane_sum(float v) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// one sub-step for the env this lane (co-)owns.  `lane` = lane index within the env (0..L-1).
-// LAST selects whether the outputs of StepOut are produced (only the last sub-step's are read).
-template <class Topo>
-__device__ __forceinline__ void substep(const DevModel *__restrict__ m, const Ground &gr, int lane,
-                                        EnvState<Topo> &st, StepOut<Topo> &out, const bool LAST) {
-    constexpr int NS = Topo::NS, L = Topo::L;
+// contact spheres of one link against the ground.  ACCUM: add the explicit force to the bias
+// (pa, pl) and the implicit term h*J^T G J to IA.  !ACCUM (after the accelerations are known):
+// accumulate the force actually applied over the sub-step, F = F0 - h*G*(J a), and its torque
+// about the link origin.  HF=false folds the z=0 plane in (n = e_z): G = diag(gam, gam, gn).
+template <bool ACCUM, bool HF>
+__device__ __forceinline__ void link_contacts(const DevModel *m, const Ground &gr, const LinkC &lk, const float rp[3],
+                                              const float R[9], const float x[3], const float vw[3], const float vl[3],
+                                              float IA[21], float pa[3], float pl[3],
+                                              const float aw[3], const float al[3], float F[3], float T[3],
+                                              int cp_first, int cp_step) {
     const float h = m->h;
-    const LinkC &rootc = m->links[0];
-    float g[3] = {m->g[0], m->g[1], m->g[2]};
-
-    float R[NS + 1][9], x[NS + 1][3], vw[NS + 1][3], vl[NS + 1][3];
-    float w[NS][3], sl[NS][3], cwv[NS][3], clv[NS][3];
-    float IA[NS + 1][21], pa[NS + 1][3], pl[NS + 1][3];
-    float U[NS][6], Dinv[NS], uu[NS], tau[NS], diag[NS];
-    constexpr int RT = NS;   // index of the root in the per-link arrays
-
-    // ---- root kinematics
-    quat_to_mat(st.rq, R[RT]);
-    x[RT][0] = x[RT][1] = x[RT][2] = 0.f;
-    if (m->root_fixed) {
+    const float gn = m->cn + h * m->kn;
+#pragma unroll 1
+    for (int k = lk.cp_begin + cp_first; k < lk.cp_end; k += cp_step) {
+        const CpC &cp = m->cps[k];
+        float pc[3], lp[3] = {cp.pos[0], cp.pos[1], cp.pos[2]};
+        matvec(R, lp, pc);
+        pc[0] += x[0]; pc[1] += x[1]; pc[2] += x[2];          // sphere centre relative to O
+        float hg = 0.f, n[3] = {0.f, 0.f, 1.f};
+        if (HF) gr.sample(rp[0] + pc[0], rp[1] + pc[1], hg, n);
+        const float d = HF ? cp.radius - (rp[2] + pc[2] - hg) * n[2] : cp.radius - (rp[2] + pc[2]);
+        if (d <= 0.f) continue;
+        float r[3];
+        if (HF) { r[0] = pc[0] - cp.radius * n[0]; r[1] = pc[1] - cp.radius * n[1]; r[2] = pc[2] - cp.radius * n[2]; }
+        else { r[0] = pc[0]; r[1] = pc[1]; r[2] = pc[2] - cp.radius; }
+        float wxr[3]; cross(vw, r, wxr);
+        const float u[3] = {vl[0] + wxr[0], vl[1] + wxr[1], vl[2] + wxr[2]};
+        const float un = HF ? dot3(u, n) : u[2];
+        const float Fn = m->kn * d - gn * un;
+        if (Fn <= 0.f) continue;
+        float ut[3];
+        if (HF) { ut[0] = u[0] - un * n[0]; ut[1] = u[1] - un * n[1]; ut[2] = u[2] - un * n[2]; }
+        else { ut[0] = u[0]; ut[1] = u[1]; ut[2] = 0.f; }
+        const float gam = cp.mu * Fn * rsqrtf(dot3(ut, ut) + m->vs2);
+        float F0[3];
+        if (HF) { F0[0] = Fn * n[0] - gam * ut[0]; F0[1] = Fn * n[1] - gam * ut[1]; F0[2] = Fn * n[2] - gam * ut[2]; }
+        else { F0[0] = -gam * ut[0]; F0[1] = -gam * ut[1]; F0[2] = Fn; }
+        if (ACCUM) {
+            float rxF[3]; cross(r, F0, rxF);
+            pa[0] -= rxF[0]; pa[1] -= rxF[1]; pa[2] -= rxF[2];
+            pl[0] -= F0[0]; pl[1] -= F0[1]; pl[2] -= F0[2];
+            const float hgam = h * gam;
+            if (HF) {
+                // J^T G J with G = gam*1 + (gn-gam) n n^T ; rows of J: j_k = (r x e_k ; e_k)
+                const float jx[3] = {0.f, r[2], -r[1]}, jy[3] = {-r[2], 0.f, r[0]}, jz[3] = {r[1], -r[0], 0.f};
+                const float ex[3] = {1.f, 0.f, 0.f}, ey[3] = {0.f, 1.f, 0.f}, ez[3] = {0.f, 0.f, 1.f};
+                sym6_rank1(IA, hgam, jx, ex); sym6_rank1(IA, hgam, jy, ey); sym6_rank1(IA, hgam, jz, ez);
+                float rxn[3]; cross(r, n, rxn);
+                sym6_rank1(IA, h * (gn - gam), rxn, n);
+            } else {
+                // the same three rank-1 terms with G = diag(gam, gam, gn), zeros folded away
+                const float hgn = h * gn, rx = r[0], ry = r[1], rz = r[2];
+                IA[0] += hgam * rz * rz + hgn * ry * ry;
+                IA[1] += hgam * rz * rz + hgn * rx * rx;
+                IA[2] += hgam * (rx * rx + ry * ry);
+                IA[3] -= hgn * rx * ry; IA[4] -= hgam * rx * rz; IA[5] -= hgam * ry * rz;
+                IA[7] -= hgam * rz; IA[8] += hgn * ry;
+                IA[9] += hgam * rz; IA[11] -= hgn * rx;
+                IA[12] -= hgam * ry; IA[13] += hgam * rx;
+                IA[15] += hgam; IA[16] += hgam; IA[17] += hgn;
+            }
+        } else {
+            float axr[3]; cross(aw, r, axr);
+            const float Ja[3] = {al[0] + axr[0], al[1] + axr[1], al[2] + axr[2]};
+            float Fk[3];
+            if (HF) {
+                const float Jan = dot3(Ja, n);
 #pragma unroll
-        for (int c = 0; c < 3; c++) { vw[RT][c] = 0.f; vl[RT][c] = 0.f; }
-    } else {
+                for (int c = 0; c < 3; c++) Fk[c] = F0[c] - h * (gam * Ja[c] + (gn - gam) * Jan * n[c]);
+            } else {
+                Fk[0] = F0[0] - h * gam * Ja[0]; Fk[1] = F0[1] - h * gam * Ja[1]; Fk[2] = F0[2] - h * gn * Ja[2];
+            }
+            const float rl[3] = {r[0] - x[0], r[1] - x[1], r[2] - x[2]};
+            float t[3]; cross(rl, Fk, t);
 #pragma unroll
-        for (int c = 0; c < 3; c++) { vw[RT][c] = st.rw[c]; vl[RT][c] = st.rv[c]; }
+            for (int c = 0; c < 3; c++) { F[c] += Fk[c]; T[c] += t[c]; }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-slot state in shared memory: 12 float4 per slot per thread, [slot][k][thread]
+//  k0: R0..R3   k1: R4..R7   k2: R8 x0 x1 x2   k3: vw0 vw1 vw2 vl0   k4: vl1 vl2 w0 w1   k5: w2 sl0 sl1 sl2
+//  k6: cw0 cw1 cw2 cl0   k7: cl1 cl2 tau diag   k8: U0..U3   k9: U4 U5 Dinv act
+//  k10: (u | aw0) aw1 aw2 al0   k11: al1 al2 q qd
+constexpr int SLOT_F4 = 12;
+constexpr int ACC_F4 = 7;     // a parked articulated inertia + bias: 27 floats
+
+struct RootState {            // replicated on the L lanes of the env
+    float rp[3], rq[4], rv[3], rw[3];
+};
+
+template <int L, bool HF, int BLOCK>
+struct Stepper {
+    const DevModel *m;
+    Ground gr;
+    float4 *ss;               // this thread's column of the slot-state array
+    float4 *acc;              // this thread's column of the accumulator pool
+    int lane;
+
+    __device__ __forceinline__ float4 &S4(int s, int k) const { return ss[(s * SLOT_F4 + k) * BLOCK]; }
+    __device__ __forceinline__ float4 &A4(int a, int k) const { return acc[(a * ACC_F4 + k) * BLOCK]; }
+    __device__ __forceinline__ const LinkC &link(int s) const { return m->links[m->slot_link[s][lane]]; }
+
+    // q, qd of a slot (k11.z, k11.w) and its actuation / target (k9.w)
+    __device__ __forceinline__ void set_joint(int s, float q, float qd, float act) const {
+        float4 v = S4(s, 11); v.z = q; v.w = qd; S4(s, 11) = v;
+        float4 u = S4(s, 9); u.w = act; S4(s, 9) = u;
+    }
+    __device__ __forceinline__ void set_q(int s, float q, float qd) const { float4 v = S4(s, 11); v.z = q; v.w = qd; S4(s, 11) = v; }
+    __device__ __forceinline__ float2 get_q(int s) const { const float4 v = S4(s, 11); return make_float2(v.z, v.w); }
+
+    __device__ __forceinline__ void load_pose(int s, float R[9], float x[3], float vw[3], float vl[3]) const {
+        const float4 a = S4(s, 0), b = S4(s, 1), c = S4(s, 2), d = S4(s, 3), e = S4(s, 4);
+        R[0] = a.x; R[1] = a.y; R[2] = a.z; R[3] = a.w; R[4] = b.x; R[5] = b.y; R[6] = b.z; R[7] = b.w; R[8] = c.x;
+        x[0] = c.y; x[1] = c.z; x[2] = c.w; vw[0] = d.x; vw[1] = d.y; vw[2] = d.z; vl[0] = d.w; vl[1] = e.x; vl[2] = e.y;
+    }
+    __device__ __forceinline__ void load_axis(int s, float w[3], float sl[3]) const {
+        const float4 e = S4(s, 4), f = S4(s, 5);
+        w[0] = e.z; w[1] = e.w; w[2] = f.x; sl[0] = f.y; sl[1] = f.z; sl[2] = f.w;
     }
 
-    // ---- pass 1 (root + slots, parents before children)
+    // ---- one sub-step.  LAST: also produce contact wrench / joint force outputs (see Outputs)
+    struct Outputs {
+        float *sensor;      // (nsens, 6) of this env or null
+        float *dof_force;   // (nd) of this env or null
+        float *net_contact; // (nb, 3) of this env or null
+        bool write;         // env index valid
+    };
+
+    __device__ __forceinline__ void substep(RootState &rs, const bool LAST, const Outputs &o) const {
+        const float h = m->h;
+        const int NS = m->ns;
+        const float g[3] = {m->g[0], m->g[1], m->g[2]};
+        const bool fixed = m->root_fixed != 0;
+        {   // the root's pose and twist live in slot NS
+            float Rr[9];
+            quat_to_mat(rs.rq, Rr);
+            S4(NS, 0) = make_float4(Rr[0], Rr[1], Rr[2], Rr[3]);
+            S4(NS, 1) = make_float4(Rr[4], Rr[5], Rr[6], Rr[7]);
+            S4(NS, 2) = make_float4(Rr[8], 0.f, 0.f, 0.f);
+            S4(NS, 3) = fixed ? make_float4(0.f, 0.f, 0.f, 0.f) : make_float4(rs.rw[0], rs.rw[1], rs.rw[2], rs.rv[0]);
+            S4(NS, 4) = fixed ? make_float4(0.f, 0.f, 0.f, 0.f) : make_float4(rs.rv[1], rs.rv[2], 0.f, 0.f);
+        }
+
+        // ================= pass 1: kinematics, velocities, joint forces (root -> leaves)
+        {
+            float Rc[9], xc[3], vwc[3], vlc[3];      // the slot just finished (parent of a chain successor)
+#pragma unroll 1
+            for (int s = 0; s < NS; s++) {
+                const LinkC &lk = link(s);
+                const int ps = m->slot_parent[s];
+                float Rp[9], xp[3], vwp[3], vlp[3];
+                if (ps >= 0 && ps == s - 1) {
 #pragma unroll
-    for (int s = -1; s < NS; s++) {
-        const int i = (s < 0) ? RT : s;
-        const LinkC &lk = (s < 0) ? rootc : m->links[m->slot_link[s][lane]];
-        if (s >= 0) {
-            const int p = (Topo::ps(s) < 0) ? RT : Topo::ps(s);
-            float Rt[9], ax[3] = {lk.axis[0], lk.axis[1], lk.axis[2]};
-            matmul(R[p], lk.R0, Rt);
-            matvec(Rt, ax, w[s]);
-            float lp[3] = {lk.lpos[0], lk.lpos[1], lk.lpos[2]}, d[3];
-            const float q = st.q[s], qd = st.qd[s];
-            if (lk.jtype == 0) {
-                float sn, cs; b2g_sincos(q, &sn, &cs);
-                const float oc = 1.f - cs;
+                    for (int c = 0; c < 9; c++) Rp[c] = Rc[c];
 #pragma unroll
-                for (int j = 0; j < 3; j++) {   // rotate column j of Rt about the world axis w by q
-                    float col[3] = {Rt[j], Rt[3 + j], Rt[6 + j]}, wxc[3];
-                    cross(w[s], col, wxc);
-                    float wd = dot3(w[s], col) * oc;
-                    R[i][j] = col[0] * cs + wxc[0] * sn + w[s][0] * wd;
-                    R[i][3 + j] = col[1] * cs + wxc[1] * sn + w[s][1] * wd;
-                    R[i][6 + j] = col[2] * cs + wxc[2] * sn + w[s][2] * wd;
+                    for (int c = 0; c < 3; c++) { xp[c] = xc[c]; vwp[c] = vwc[c]; vlp[c] = vlc[c]; }
+                } else {
+                    load_pose(ps < 0 ? NS : ps, Rp, xp, vwp, vlp);
                 }
-                matvec(R[p], lp, d);
+                const float4 jq = S4(s, 11);
+                const float q = jq.z, qd = jq.w;
+                const float act = S4(s, 9).w;
+                float Rt[9], w[3], sl[3], cw[3], cl[3];
+                if (lk.flags & LF_R0_IDENTITY) {
 #pragma unroll
-                for (int c = 0; c < 3; c++) x[i][c] = x[p][c] + d[c];
-                cross(x[i], w[s], sl[s]);                        // S = (w ; x x w)
+                    for (int c = 0; c < 9; c++) Rt[c] = Rp[c];
+                } else {
+                    matmul(Rp, lk.R0, Rt);
+                }
+                const float ax[3] = {lk.axis[0], lk.axis[1], lk.axis[2]};
+                matvec(Rt, ax, w);
+                const float lp[3] = {lk.lpos[0], lk.lpos[1], lk.lpos[2]};
+                float d[3]; matvec(Rp, lp, d);
+                if (!(lk.flags & LF_SLIDE)) {
+                    float sn, cs; b2g_sincos(q, &sn, &cs);
+                    const float oc = 1.f - cs;
 #pragma unroll
-                for (int c = 0; c < 3; c++) { vw[i][c] = vw[p][c] + w[s][c] * qd; vl[i][c] = vl[p][c] + sl[s][c] * qd; }
-                // c = crm(v) (S qd):  ang = vw x w qd ; lin = vw x sl qd + vl x w qd
-                float a1[3], a2[3], a3[3];
-                cross(vw[i], w[s], a1); cross(vw[i], sl[s], a2); cross(vl[i], w[s], a3);
+                    for (int j = 0; j < 3; j++) {   // rotate column j of Rt about the world axis w by q
+                        const float col[3] = {Rt[j], Rt[3 + j], Rt[6 + j]};
+                        float wxc[3]; cross(w, col, wxc);
+                        const float wd = dot3(w, col) * oc;
+                        Rc[j] = col[0] * cs + wxc[0] * sn + w[0] * wd;
+                        Rc[3 + j] = col[1] * cs + wxc[1] * sn + w[1] * wd;
+                        Rc[6 + j] = col[2] * cs + wxc[2] * sn + w[2] * wd;
+                    }
 #pragma unroll
-                for (int c = 0; c < 3; c++) { cwv[s][c] = a1[c] * qd; clv[s][c] = (a2[c] + a3[c]) * qd; }
-            } else {
+                    for (int c = 0; c < 3; c++) xc[c] = xp[c] + d[c];
+                    cross(xc, w, sl);                                 // S = (w ; x x w)
 #pragma unroll
-                for (int c = 0; c < 9; c++) R[i][c] = Rt[c];
-                matvec(R[p], lp, d);
+                    for (int c = 0; c < 3; c++) { vwc[c] = vwp[c] + w[c] * qd; vlc[c] = vlp[c] + sl[c] * qd; }
+                    float a1[3], a2[3], a3[3];                        // c = crm(v)(S qd)
+                    cross(vwc, w, a1); cross(vwc, sl, a2); cross(vlc, w, a3);
 #pragma unroll
-                for (int c = 0; c < 3; c++) { x[i][c] = x[p][c] + d[c] + w[s][c] * q; sl[s][c] = w[s][c]; }
+                    for (int c = 0; c < 3; c++) { cw[c] = a1[c] * qd; cl[c] = (a2[c] + a3[c]) * qd; }
+                } else {
 #pragma unroll
-                for (int c = 0; c < 3; c++) { vw[i][c] = vw[p][c]; vl[i][c] = vl[p][c] + w[s][c] * qd; }
-                float a2[3]; cross(vw[i], w[s], a2);             // S = (0 ; w): c = (0 ; vw x w qd)
+                    for (int c = 0; c < 9; c++) Rc[c] = Rt[c];
 #pragma unroll
-                for (int c = 0; c < 3; c++) { cwv[s][c] = 0.f; clv[s][c] = a2[c] * qd; w[s][c] = 0.f; }
+                    for (int c = 0; c < 3; c++) { xc[c] = xp[c] + d[c] + w[c] * q; sl[c] = w[c]; vwc[c] = vwp[c]; vlc[c] = vlp[c] + w[c] * qd; }
+                    float a2[3]; cross(vwc, w, a2);                   // S = (0 ; w): c = (0 ; vw x w qd)
+#pragma unroll
+                    for (int c = 0; c < 3; c++) { cw[c] = 0.f; cl[c] = a2[c] * qd; w[c] = 0.f; }
+                }
+                // joint force: explicit part + implicit diagonal (linear terms at the end of the sub-step)
+                const float qp = q + h * qd;
+                float f = -lk.damping * qd - lk.stiffness * qp;
+                float dg = lk.armature + h * lk.damping + h * h * lk.stiffness;
+                if (lk.flags & LF_POSDRIVE) {
+                    float pd = lk.kp * (act - qp) - lk.kd * qd;
+                    pd = fminf(fmaxf(pd, -lk.effort), lk.effort);
+                    f += pd; dg += h * lk.kd + h * h * lk.kp;
+                } else {
+                    f += fminf(fmaxf(act, -lk.effort), lk.effort);
+                }
+                if (lk.flags & LF_LIMITED) {
+                    if (q < lk.lower) { f += lk.limit_k * (lk.lower - qp) - lk.limit_d * qd; dg += h * lk.limit_d + h * h * lk.limit_k; }
+                    else if (q > lk.upper) { f += lk.limit_k * (lk.upper - qp) - lk.limit_d * qd; dg += h * lk.limit_d + h * h * lk.limit_k; }
+                }
+                S4(s, 0) = make_float4(Rc[0], Rc[1], Rc[2], Rc[3]);
+                S4(s, 1) = make_float4(Rc[4], Rc[5], Rc[6], Rc[7]);
+                S4(s, 2) = make_float4(Rc[8], xc[0], xc[1], xc[2]);
+                S4(s, 3) = make_float4(vwc[0], vwc[1], vwc[2], vlc[0]);
+                S4(s, 4) = make_float4(vlc[1], vlc[2], w[0], w[1]);
+                S4(s, 5) = make_float4(w[2], sl[0], sl[1], sl[2]);
+                S4(s, 6) = make_float4(cw[0], cw[1], cw[2], cl[0]);
+                S4(s, 7) = make_float4(cl[1], cl[2], f, dg);
             }
-            // joint force: explicit part + implicit diagonal (linear terms at the end of the sub-step)
-            const float qp = q + h * qd;
-            float f = -lk.damping * qd - lk.stiffness * qp;
-            float dg = lk.armature + h * lk.damping + h * h * lk.stiffness;
-            if (lk.drive_mode == 1) {
-                float pd = lk.kp * (st.act[s] - qp) - lk.kd * qd;
-                pd = fminf(fmaxf(pd, -lk.effort), lk.effort);
-                f += pd; dg += h * lk.kd + h * h * lk.kp;
-            } else {
-                f += fminf(fmaxf(st.act[s], -lk.effort), lk.effort);
-            }
-            if (lk.limited) {
-                if (q < lk.lower) { f += lk.limit_k * (lk.lower - qp) - lk.limit_d * qd; dg += h * lk.limit_d + h * h * lk.limit_k; }
-                else if (q > lk.upper) { f += lk.limit_k * (lk.upper - qp) - lk.limit_d * qd; dg += h * lk.limit_d + h * h * lk.limit_k; }
-            }
-            tau[s] = f; diag[s] = dg;
         }
-        // spatial inertia about O, world axes, and bias force p = v x* (I v) - gravity
-        // (the root's share is computed on lane 0 only; the butterfly below spreads it)
-        const bool mine = (s >= 0) || (lane == 0);
-        const float mass = mine ? lk.mass : 0.f;
-        float cl_[3] = {lk.com[0], lk.com[1], lk.com[2]}, cw_[3];
-        matvec(R[i], cl_, cw_);
+
+        // ================= pass 2: articulated inertias (leaves -> root)
+        // accumulator m->nacc collects what reaches the root from this lane's sub-trees
+        for (int a = 0; a <= m->nacc; a++)
 #pragma unroll
-        for (int c = 0; c < 3; c++) cw_[c] += x[i][c];
-        float T_[9], Icw[6];
-        {   // Icw = R Ic R^T
-            const float *I6 = lk.Ic;
-            const float Im[9] = {I6[0], I6[3], I6[4], I6[3], I6[1], I6[5], I6[4], I6[5], I6[2]};
-            matmul(R[i], Im, T_);
-            Icw[0] = T_[0] * R[i][0] + T_[1] * R[i][1] + T_[2] * R[i][2];
-            Icw[1] = T_[3] * R[i][3] + T_[4] * R[i][4] + T_[5] * R[i][5];
-            Icw[2] = T_[6] * R[i][6] + T_[7] * R[i][7] + T_[8] * R[i][8];
-            Icw[3] = T_[0] * R[i][3] + T_[1] * R[i][4] + T_[2] * R[i][5];
-            Icw[4] = T_[0] * R[i][6] + T_[1] * R[i][7] + T_[2] * R[i][8];
-            Icw[5] = T_[3] * R[i][6] + T_[4] * R[i][7] + T_[5] * R[i][8];
+            for (int k = 0; k < ACC_F4; k++) A4(a, k) = make_float4(0.f, 0.f, 0.f, 0.f);
+        {
+            float IA[21], pa[3], pl[3];     // travels along chains: child's projected inertia -> parent
+            bool carry = false;
+#pragma unroll 1
+            for (int s = NS - 1; s >= 0; s--) {
+                const LinkC &lk = link(s);
+                float R[9], x[3], vw[3], vl[3], w[3], sl[3];
+                load_pose(s, R, x, vw, vl);
+                load_axis(s, w, sl);
+                float I[21], qa[3], ql[3];
+                link_inertia(lk, lk.mass, 1.f, R, x, vw, vl, g, I, qa, ql);
+                float dummy[3];
+                link_contacts<true, HF>(m, gr, lk, rs.rp, R, x, vw, vl, I, qa, ql, dummy, dummy, dummy, dummy, 0, 1);
+                if (carry) {
+#pragma unroll
+                    for (int c = 0; c < 21; c++) I[c] += IA[c];
+#pragma unroll
+                    for (int c = 0; c < 3; c++) { qa[c] += pa[c]; ql[c] += pl[c]; }
+                }
+                const int ai = m->slot_acc[s];
+                if (ai >= 0) {
+                    float t[28];
+#pragma unroll
+                    for (int k = 0; k < ACC_F4; k++) { const float4 v = A4(ai, k); t[4 * k] = v.x; t[4 * k + 1] = v.y; t[4 * k + 2] = v.z; t[4 * k + 3] = v.w; }
+#pragma unroll
+                    for (int c = 0; c < 21; c++) I[c] += t[c];
+#pragma unroll
+                    for (int c = 0; c < 3; c++) { qa[c] += t[21 + c]; ql[c] += t[24 + c]; }
+                }
+                const float4 k6 = S4(s, 6), k7 = S4(s, 7);
+                const float cw[3] = {k6.x, k6.y, k6.z}, cl[3] = {k6.w, k7.x, k7.y};
+                const float tau = k7.z, dg = k7.w;
+                float Ua[3], Ul[3];
+                sym6_mul(I, w, sl, Ua, Ul);
+                const float D = dot3(w, Ua) + dot3(sl, Ul) + dg;
+                const float di = 1.f / D;
+                const float u_ = tau - (dot3(w, qa) + dot3(sl, ql));
+                S4(s, 8) = make_float4(Ua[0], Ua[1], Ua[2], Ul[0]);
+                { float4 v = S4(s, 9); v.x = Ul[1]; v.y = Ul[2]; v.z = di; S4(s, 9) = v; }
+                { float4 v = S4(s, 10); v.x = u_; S4(s, 10) = v; }
+                sym6_rank1(I, -di, Ua, Ul);                           // Ia = IA - U U^T / D
+                float ya[3], yl[3];
+                sym6_mul(I, cw, cl, ya, yl);
+                const float ud = u_ * di;
+#pragma unroll
+                for (int c = 0; c < 3; c++) { qa[c] += ya[c] + Ua[c] * ud; ql[c] += yl[c] + Ul[c] * ud; }
+                const int ps = m->slot_parent[s];
+                carry = false;
+                if (ps >= 0 && ps == s - 1) {
+#pragma unroll
+                    for (int c = 0; c < 21; c++) IA[c] = I[c];
+#pragma unroll
+                    for (int c = 0; c < 3; c++) { pa[c] = qa[c]; pl[c] = ql[c]; }
+                    carry = true;
+                } else {
+                    const int pi = ps < 0 ? m->nacc : m->slot_acc[ps];
+                    float t[28];
+#pragma unroll
+                    for (int c = 0; c < 21; c++) t[c] = I[c];
+#pragma unroll
+                    for (int c = 0; c < 3; c++) { t[21 + c] = qa[c]; t[24 + c] = ql[c]; }
+                    t[27] = 0.f;
+#pragma unroll
+                    for (int k = 0; k < ACC_F4; k++) {
+                        float4 v = A4(pi, k);
+                        v.x += t[4 * k]; v.y += t[4 * k + 1]; v.z += t[4 * k + 2]; v.w += t[4 * k + 3];
+                        A4(pi, k) = v;
+                    }
+                }
+            }
         }
-        const float sc = mine ? 1.f : 0.f;
+        // ---- root: own inertia (lane 0), its contact spheres (dealt round-robin to the lanes), butterfly, solve
+        {
+            float awr[3], alr[3];
+            const LinkC &lk = m->links[0];
+            const bool mine = (lane == 0);
+            float I[21], qa[3], ql[3], dummy[3], Rr[9], xr[3], vwr[3], vlr[3], IAr[21], par[3], plr[3];
+            load_pose(NS, Rr, xr, vwr, vlr);
+            link_inertia(lk, mine ? lk.mass : 0.f, mine ? 1.f : 0.f, Rr, xr, vwr, vlr, g, I, qa, ql);
+            link_contacts<true, HF>(m, gr, lk, rs.rp, Rr, xr, vwr, vlr, I, qa, ql, dummy, dummy, dummy, dummy, lane, L);
+            {
+                float t[28];
+#pragma unroll
+                for (int k = 0; k < ACC_F4; k++) { const float4 v = A4(m->nacc, k); t[4 * k] = v.x; t[4 * k + 1] = v.y; t[4 * k + 2] = v.z; t[4 * k + 3] = v.w; }
+#pragma unroll
+                for (int c = 0; c < 21; c++) IAr[c] = lane_sum<L>(t[c] + I[c]);
+#pragma unroll
+                for (int c = 0; c < 3; c++) { par[c] = lane_sum<L>(t[21 + c] + qa[c]); plr[c] = lane_sum<L>(t[24 + c] + ql[c]); }
+            }
+            if (fixed) {
+#pragma unroll
+                for (int c = 0; c < 3; c++) { awr[c] = 0.f; alr[c] = 0.f; }
+            } else {
+                const float ba[3] = {-par[0], -par[1], -par[2]}, bl[3] = {-plr[0], -plr[1], -plr[2]};
+                sym6_solve(IAr, ba, bl, awr, alr);
+            }
+            if (LAST) {
+                float F[3] = {0.f, 0.f, 0.f}, T[3] = {0.f, 0.f, 0.f};
+                link_contacts<false, HF>(m, gr, lk, rs.rp, Rr, xr, vwr, vlr, I, qa, ql, awr, alr, F, T, lane, L);
+#pragma unroll
+                for (int c = 0; c < 3; c++) { F[c] = lane_sum<L>(F[c]); T[c] = lane_sum<L>(T[c]); }
+                if (lane == 0) emit_wrench(0, lk, Rr, F, T, o);
+            }
+            S4(NS, 10) = make_float4(awr[0], awr[1], awr[2], alr[0]);
+            S4(NS, 11) = make_float4(alr[1], alr[2], 0.f, 0.f);
+        }
+
+        // ================= pass 3: accelerations (root -> leaves), joint integration, outputs
+        {
+            float awc[3], alc[3];
+#pragma unroll 1
+            for (int s = 0; s < NS; s++) {
+                const int ps = m->slot_parent[s];
+                float ap_w[3], ap_l[3];
+                if (ps >= 0 && ps == s - 1) {
+#pragma unroll
+                    for (int c = 0; c < 3; c++) { ap_w[c] = awc[c]; ap_l[c] = alc[c]; }
+                } else {
+                    const int pp = ps < 0 ? NS : ps;
+                    const float4 a = S4(pp, 10), b = S4(pp, 11);
+                    ap_w[0] = a.x; ap_w[1] = a.y; ap_w[2] = a.z; ap_l[0] = a.w; ap_l[1] = b.x; ap_l[2] = b.y;
+                }
+                float w[3], sl[3];
+                load_axis(s, w, sl);
+                const float4 k6 = S4(s, 6), k7 = S4(s, 7), k8 = S4(s, 8), k9 = S4(s, 9), k10 = S4(s, 10), k11 = S4(s, 11);
+                float a_w[3] = {ap_w[0] + k6.x, ap_w[1] + k6.y, ap_w[2] + k6.z};
+                float a_l[3] = {ap_l[0] + k6.w, ap_l[1] + k7.x, ap_l[2] + k7.y};
+                const float Ua_ = k8.x * a_w[0] + k8.y * a_w[1] + k8.z * a_w[2] + k8.w * a_l[0] + k9.x * a_l[1] + k9.y * a_l[2];
+                const float qdd = (k10.x - Ua_) * k9.z;
+#pragma unroll
+                for (int c = 0; c < 3; c++) { awc[c] = a_w[c] + w[c] * qdd; alc[c] = a_l[c] + sl[c] * qdd; }
+                const float qd = k11.w + h * qdd;
+                const float q = k11.z + h * qd;
+                S4(s, 10) = make_float4(awc[0], awc[1], awc[2], alc[0]);
+                S4(s, 11) = make_float4(alc[1], alc[2], q, qd);
+                if (LAST) {
+                    const LinkC &lk = link(s);
+                    const int li = m->slot_link[s][lane];
+                    if (o.dof_force && o.write) o.dof_force[li - 1] = k7.z - (k7.w - lk.armature) * qdd;
+                    if (lk.cp_end > lk.cp_begin && (lk.sensor >= 0 || o.net_contact)) {
+                        float R[9], x[3], vw[3], vl[3], F[3] = {0.f, 0.f, 0.f}, T[3] = {0.f, 0.f, 0.f}, dI[1], d3[3];
+                        load_pose(s, R, x, vw, vl);
+                        link_contacts<false, HF>(m, gr, lk, rs.rp, R, x, vw, vl, dI, d3, d3, awc, alc, F, T, 0, 1);
+                        emit_wrench(li, lk, R, F, T, o);
+                    } else if (lk.sensor >= 0 || (o.net_contact && m->link_body[li] >= 0)) {
+                        float R[9], x[3], vw[3], vl[3]; const float z[3] = {0.f, 0.f, 0.f};
+                        load_pose(s, R, x, vw, vl);
+                        emit_wrench(li, lk, R, z, z, o);
+                    }
+                }
+            }
+        }
+
+        // ================= root integration (classical acceleration of the origin = spatial + w x v)
+        if (!fixed) {
+            const float4 ra = S4(NS, 10), rb = S4(NS, 11);
+            const float awr[3] = {ra.x, ra.y, ra.z}, alr[3] = {ra.w, rb.x, rb.y};
+            float wxv[3]; cross(rs.rw, rs.rv, wxv);
+#pragma unroll
+            for (int c = 0; c < 3; c++) { rs.rw[c] += h * awr[c]; rs.rv[c] += h * (alr[c] + wxv[c]); }
+#pragma unroll
+            for (int c = 0; c < 3; c++) rs.rp[c] += h * rs.rv[c];
+            const float wn2 = dot3(rs.rw, rs.rw);
+            float dq[4];
+            if (wn2 > 1e-24f) {
+                const float wn = sqrtf(wn2);
+                float sn, cs; b2g_sincos(0.5f * wn * h, &sn, &cs);
+                const float k = sn / wn;
+                dq[0] = rs.rw[0] * k; dq[1] = rs.rw[1] * k; dq[2] = rs.rw[2] * k; dq[3] = cs;
+            } else { dq[0] = 0.5f * h * rs.rw[0]; dq[1] = 0.5f * h * rs.rw[1]; dq[2] = 0.5f * h * rs.rw[2]; dq[3] = 1.f; }
+            const float qx = rs.rq[0], qy = rs.rq[1], qz = rs.rq[2], qw = rs.rq[3];
+            const float nq[4] = {dq[3] * qx + dq[0] * qw + dq[1] * qz - dq[2] * qy,
+                                 dq[3] * qy - dq[0] * qz + dq[1] * qw + dq[2] * qx,
+                                 dq[3] * qz + dq[0] * qy - dq[1] * qx + dq[2] * qw,
+                                 dq[3] * qw - dq[0] * qx - dq[1] * qy - dq[2] * qz};
+            const float inv = rsqrtf(nq[0] * nq[0] + nq[1] * nq[1] + nq[2] * nq[2] + nq[3] * nq[3]);
+#pragma unroll
+            for (int c = 0; c < 4; c++) rs.rq[c] = nq[c] * inv;
+        }
+    }
+
+    // spatial inertia about O in world axes (scaled by `sc`, mass given) and the bias force
+    // p = v x* (I v) - gravity wrench
+    __device__ __forceinline__ static void link_inertia(const LinkC &lk, float mass, float sc, const float R[9], const float x[3],
+                                                         const float vw[3], const float vl[3], const float g[3],
+                                                         float I[21], float pa[3], float pl[3]) {
+        const float cl_[3] = {lk.com[0], lk.com[1], lk.com[2]};
+        float cw_[3]; matvec(R, cl_, cw_);
+#pragma unroll
+        for (int c = 0; c < 3; c++) cw_[c] += x[c];
+        const float *I6 = lk.Ic;
+        const float Im[9] = {I6[0], I6[3], I6[4], I6[3], I6[1], I6[5], I6[4], I6[5], I6[2]};
+        float T_[9]; matmul(R, Im, T_);
+        float Icw[6];
+        Icw[0] = T_[0] * R[0] + T_[1] * R[1] + T_[2] * R[2];
+        Icw[1] = T_[3] * R[3] + T_[4] * R[4] + T_[5] * R[5];
+        Icw[2] = T_[6] * R[6] + T_[7] * R[7] + T_[8] * R[8];
+        Icw[3] = T_[0] * R[3] + T_[1] * R[4] + T_[2] * R[5];
+        Icw[4] = T_[0] * R[6] + T_[1] * R[7] + T_[2] * R[8];
+        Icw[5] = T_[3] * R[6] + T_[4] * R[7] + T_[5] * R[8];
         const float hm[3] = {mass * cw_[0], mass * cw_[1], mass * cw_[2]};
         const float c2 = dot3(cw_, cw_);
-        float *I = IA[i];
         I[0] = sc * Icw[0] + mass * (c2 - cw_[0] * cw_[0]);
         I[1] = sc * Icw[1] + mass * (c2 - cw_[1] * cw_[1]);
         I[2] = sc * Icw[2] + mass * (c2 - cw_[2] * cw_[2]);
@@ -451,115 +718,32 @@ __device__ __forceinline__ void substep(const DevModel *__restrict__ m, const Gr
         I[12] = -hm[1]; I[13] = hm[0]; I[14] = 0.f;
         I[15] = mass; I[16] = mass; I[17] = mass; I[18] = 0.f; I[19] = 0.f; I[20] = 0.f;
         float na[3], nf[3];
-        sym6_mul(I, vw[i], vl[i], na, nf);
-        float t1[3], t2[3], t3[3];
-        cross(vw[i], na, t1); cross(vl[i], nf, t2); cross(vw[i], nf, t3);
-        float hxg[3]; cross(hm, g, hxg);
+        sym6_mul(I, vw, vl, na, nf);
+        float t1[3], t2[3], t3[3], hxg[3];
+        cross(vw, na, t1); cross(vl, nf, t2); cross(vw, nf, t3); cross(hm, g, hxg);
 #pragma unroll
-        for (int c = 0; c < 3; c++) { pa[i][c] = t1[c] + t2[c] - hxg[c]; pl[i][c] = t3[c] - mass * g[c]; }
-        // contacts (root contact spheres are dealt round-robin to the L lanes)
-        float dummy[3];
-        link_contacts<true>(m, gr, lk, st.rp, R[i], x[i], vw[i], vl[i], I, pa[i], pl[i], dummy, dummy, dummy, dummy,
-                            (s < 0) ? lane : 0, (s < 0) ? L : 1);
+        for (int c = 0; c < 3; c++) { pa[c] = t1[c] + t2[c] - hxg[c]; pl[c] = t3[c] - mass * g[c]; }
     }
 
-    // ---- pass 2: leaf -> root
-#pragma unroll
-    for (int s = NS - 1; s >= 0; s--) {
-        const int p = (Topo::ps(s) < 0) ? RT : Topo::ps(s);
-        float Ua[3], Ul[3];
-        sym6_mul(IA[s], w[s], sl[s], Ua, Ul);
-        const float D = dot3(w[s], Ua) + dot3(sl[s], Ul) + diag[s];
-        const float di = 1.f / D;
-        const float u_ = tau[s] - (dot3(w[s], pa[s]) + dot3(sl[s], pl[s]));
-        Dinv[s] = di; uu[s] = u_;
-        U[s][0] = Ua[0]; U[s][1] = Ua[1]; U[s][2] = Ua[2]; U[s][3] = Ul[0]; U[s][4] = Ul[1]; U[s][5] = Ul[2];
-        sym6_rank1(IA[s], -di, Ua, Ul);                          // Ia = IA - U U^T / D
-        float ya[3], yl[3];
-        sym6_mul(IA[s], cwv[s], clv[s], ya, yl);
-        const float ud = u_ * di;
-#pragma unroll
-        for (int c = 0; c < 3; c++) { pa[p][c] += pa[s][c] + ya[c] + Ua[c] * ud; pl[p][c] += pl[s][c] + yl[c] + Ul[c] * ud; }
-#pragma unroll
-        for (int c = 0; c < 21; c++) IA[p][c] += IA[s][c];
-    }
-
-    // ---- root: gather the lanes' contributions, solve the floating base
-    float aw[NS + 1][3], al[NS + 1][3];
-    if (L > 1) {
-#pragma unroll
-        for (int c = 0; c < 21; c++) IA[RT][c] = lane_sum<L>(IA[RT][c]);
-#pragma unroll
-        for (int c = 0; c < 3; c++) { pa[RT][c] = lane_sum<L>(pa[RT][c]); pl[RT][c] = lane_sum<L>(pl[RT][c]); }
-    }
-    if (m->root_fixed) {
-#pragma unroll
-        for (int c = 0; c < 3; c++) { aw[RT][c] = 0.f; al[RT][c] = 0.f; }
-    } else {
-        float ba[3] = {-pa[RT][0], -pa[RT][1], -pa[RT][2]}, bl[3] = {-pl[RT][0], -pl[RT][1], -pl[RT][2]};
-        sym6_solve(IA[RT], ba, bl, aw[RT], al[RT]);
-    }
-
-    // ---- pass 3: root -> leaves, integrate the joints
-#pragma unroll
-    for (int s = 0; s < NS; s++) {
-        const int p = (Topo::ps(s) < 0) ? RT : Topo::ps(s);
-        float a_w[3], a_l[3];
-#pragma unroll
-        for (int c = 0; c < 3; c++) { a_w[c] = aw[p][c] + cwv[s][c]; a_l[c] = al[p][c] + clv[s][c]; }
-        const float Ua_ = U[s][0] * a_w[0] + U[s][1] * a_w[1] + U[s][2] * a_w[2] + U[s][3] * a_l[0] + U[s][4] * a_l[1] + U[s][5] * a_l[2];
-        const float qdd = (uu[s] - Ua_) * Dinv[s];
-#pragma unroll
-        for (int c = 0; c < 3; c++) { aw[s][c] = a_w[c] + w[s][c] * qdd; al[s][c] = a_l[c] + sl[s][c] * qdd; }
-        if (LAST) out.dof_force[s] = tau[s] - (diag[s] - m->links[m->slot_link[s][lane]].armature) * qdd;
-        st.qd[s] += h * qdd;
-        st.q[s] += h * st.qd[s];
-    }
-
-    // ---- forces actually applied by the contacts over this sub-step (sensors, net contact force)
-    if (LAST) {
-#pragma unroll
-        for (int s = -1; s < NS; s++) {
-            const int i = (s < 0) ? RT : s;
-            const LinkC &lk = (s < 0) ? rootc : m->links[m->slot_link[s][lane]];
-            float F[3] = {0.f, 0.f, 0.f}, T[3] = {0.f, 0.f, 0.f};
-            link_contacts<false>(m, gr, lk, st.rp, R[i], x[i], vw[i], vl[i], IA[i], pa[i], pl[i], aw[i], al[i], F, T,
-                                 (s < 0) ? lane : 0, (s < 0) ? L : 1);
-#pragma unroll
-            for (int c = 0; c < 3; c++) { out.cfF[i][c] = F[c]; out.cfT[i][c] = T[c]; }
-#pragma unroll
-            for (int c = 0; c < 9; c++) out.R[i][c] = R[i][c];
+    // contact wrench of a link (world axes, torque about the link origin) -> force sensor (body
+    // frame, torque about the body origin) and net contact force tensors
+    __device__ __forceinline__ void emit_wrench(int li, const LinkC &lk, const float R[9], const float F[3], const float T[3],
+                                                const Outputs &o) const {
+        if (!o.write) return;
+        if (lk.sensor >= 0 && o.sensor) {
+            const float bp[3] = {m->sensor_bpos[lk.sensor][0], m->sensor_bpos[lk.sensor][1], m->sensor_bpos[lk.sensor][2]};
+            float wb[3], bxF[3], Tb_[3], Fb[3], Tb[3];
+            matvec(R, bp, wb); cross(wb, F, bxF);
+            Tb_[0] = T[0] - bxF[0]; Tb_[1] = T[1] - bxF[1]; Tb_[2] = T[2] - bxF[2];
+            matTvec(R, F, Fb); matTvec(R, Tb_, Tb);
+            float *d = o.sensor + 6 * lk.sensor;
+            d[0] = Fb[0]; d[1] = Fb[1]; d[2] = Fb[2]; d[3] = Tb[0]; d[4] = Tb[1]; d[5] = Tb[2];
         }
-        if (L > 1) {
-#pragma unroll
-            for (int c = 0; c < 3; c++) { out.cfF[RT][c] = lane_sum<L>(out.cfF[RT][c]); out.cfT[RT][c] = lane_sum<L>(out.cfT[RT][c]); }
+        if (o.net_contact && m->link_body[li] >= 0) {
+            float *d = o.net_contact + 3 * m->link_body[li];
+            d[0] = F[0]; d[1] = F[1]; d[2] = F[2];
         }
     }
-
-    // ---- root integration (classical acceleration of the origin = spatial + w x v)
-    if (!m->root_fixed) {
-        float wxv[3]; cross(st.rw, st.rv, wxv);
-#pragma unroll
-        for (int c = 0; c < 3; c++) { st.rw[c] += h * aw[RT][c]; st.rv[c] += h * (al[RT][c] + wxv[c]); }
-#pragma unroll
-        for (int c = 0; c < 3; c++) st.rp[c] += h * st.rv[c];
-        const float wn2 = dot3(st.rw, st.rw);
-        float dq[4];
-        if (wn2 > 1e-24f) {
-            const float wn = sqrtf(wn2);
-            float sn, cs; b2g_sincos(0.5f * wn * h, &sn, &cs);
-            const float k = sn / wn;
-            dq[0] = st.rw[0] * k; dq[1] = st.rw[1] * k; dq[2] = st.rw[2] * k; dq[3] = cs;
-        } else { dq[0] = 0.5f * h * st.rw[0]; dq[1] = 0.5f * h * st.rw[1]; dq[2] = 0.5f * h * st.rw[2]; dq[3] = 1.f; }
-        const float qx = st.rq[0], qy = st.rq[1], qz = st.rq[2], qw = st.rq[3];
-        float nq[4] = {dq[3] * qx + dq[0] * qw + dq[1] * qz - dq[2] * qy,
-                       dq[3] * qy - dq[0] * qz + dq[1] * qw + dq[2] * qx,
-                       dq[3] * qz + dq[0] * qy - dq[1] * qx + dq[2] * qw,
-                       dq[3] * qw - dq[0] * qx - dq[1] * qy - dq[2] * qz};
-        const float inv = rsqrtf(nq[0] * nq[0] + nq[1] * nq[1] + nq[2] * nq[2] + nq[3] * nq[3]);
-#pragma unroll
-        for (int c = 0; c < 4; c++) st.rq[c] = nq[c] * inv;
-    }
-}
+};
 
 }  // namespace b2g
