@@ -79,9 +79,9 @@ extern __shared__ float4 b2g_dyn_smem[];
 template <int L, bool HF, int BLOCK>
 __device__ __forceinline__ Stepper<L, HF, BLOCK> make_stepper(const DevModel *sm, const int16_t *hf, int lane) {
     Stepper<L, HF, BLOCK> st;
-    st.m = sm; st.gr = Ground{sm, hf};
+    st.m = sm; st.gr = Ground{sm, hf, sm->cps};
     st.ss = b2g_dyn_smem + threadIdx.x;
-    st.acc = b2g_dyn_smem + (sm->ns + 1) * SLOT_F4 * BLOCK + threadIdx.x;
+    st.acc = b2g_dyn_smem + sm->ns * SLOT_F4 * BLOCK + threadIdx.x;
     st.lane = lane;
     return st;
 }
@@ -92,8 +92,7 @@ __device__ __forceinline__ void load_root(const float *r, RootState &rs) {
     rs.rv[0] = r[7]; rs.rv[1] = r[8]; rs.rv[2] = r[9];
     rs.rw[0] = r[10]; rs.rw[1] = r[11]; rs.rw[2] = r[12];
 }
-__device__ __forceinline__ void store_root(const Buffers &B, int e, const RootState &rs) {
-    float *r = (float *)B.p[B2G_T_ROOT_STATE] + 13 * (size_t)e;
+__device__ __forceinline__ void store_root(float *r, const RootState &rs) {
     r[0] = rs.rp[0]; r[1] = rs.rp[1]; r[2] = rs.rp[2];
     r[3] = rs.rq[0]; r[4] = rs.rq[1]; r[5] = rs.rq[2]; r[6] = rs.rq[3];
     r[7] = rs.rv[0]; r[8] = rs.rv[1]; r[9] = rs.rv[2];
@@ -144,26 +143,66 @@ __global__ void __launch_bounds__(BLOCK) simulate_kernel(const DevModel *__restr
     float2 *dw = (float2 *)B.p[B2G_T_DOF_STATE] + (size_t)e * nd;
 #pragma unroll 1
     for (int s = 0; s < NS; s++) dw[sm.slot_link[s][lane] - 1] = st.get_q(s);
-    if (lane == 0 && !sm.root_fixed) store_root(B, e, rs);
+    if (lane == 0 && !sm.root_fixed) store_root((float *)B.p[B2G_T_ROOT_STATE] + 13 * (size_t)e, rs);
 }
 
 // -------------------------------------------------------------------------------------------
 // One whole VecTask.step() of Ant / Humanoid (vec_task.py:360-408 + ant.py:281-297 / humanoid.py)
+//
+// Data movement: with whole 16-byte-aligned tiles per block (tiles_on) every tensor of the step
+// moves as ONE bulk-async copy per block: in  -- model, root_state, dof_state, actions;
+// out -- root_state, dof_state, clamped actions, force sensors, dof forces, obs (+ clipped obs),
+// rew, reset, progress, potentials, prev_potentials, up_vec, heading_vec, time-outs.  The output
+// tiles are staged in the shared memory that held the slot state during the physics.
 #ifndef B2G_MINBLOCKS
 #define B2G_MINBLOCKS 4
 #endif
+struct TileArgs {
+    int on;          // whole tiles + bulk copies
+    int io_f4;       // float4 offset (per block) of the in/out tile region inside dynamic smem
+    int model_f4;    // float4 offset of the packed model
+};
+
 template <int L, bool HF, bool HUM, int BLOCK>
-__global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? B2G_MINBLOCKS : 1)) loco_step_kernel(const DevModel *__restrict__ gm, const int16_t *__restrict__ hf,
-                                                          Buffers B, const __grid_constant__ b2g_task_params P,
-                                                          const float *__restrict__ actions_in, int N, int tiles_on) {
-    __shared__ DevModel sm;
+__global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? B2G_MINBLOCKS : 1)) loco_step_kernel(
+    const DevModel *__restrict__ gm, const int16_t *__restrict__ hf, Buffers B, const __grid_constant__ b2g_task_params P,
+    const float *__restrict__ actions_in, int N, TileArgs ta) {
     __shared__ alignas(8) uint64_t mbar;
+    // the model's hot part, packed: header | links[0..nl) | cps[0..ncp)
+    DevModel &sm = *reinterpret_cast<DevModel *>(b2g_dyn_smem + ta.model_f4);
     constexpr int EPB = BLOCK / L;
     const int nd = P.num_actions;                       // == dofs for the locomotion tasks (checked by b2g_set_task)
+    const int O = P.num_obs;
     const int env0 = blockIdx.x * EPB;
-    float4 *tile_smem = b2g_dyn_smem + (size_t)(tiles_on >> 8) * BLOCK;      // host passes the float4-per-thread offset in the high bits
-    const Tiles tl = prologue(&sm, &mbar, gm, tile_smem, (tiles_on & 1) != 0, env0, EPB, (const float *)B.p[B2G_T_ROOT_STATE],
-                              (const float *)B.p[B2G_T_DOF_STATE], actions_in, nd, nd);
+    const bool tiles = ta.on != 0;
+    float *const io = reinterpret_cast<float *>(b2g_dyn_smem + ta.io_f4);
+    // ---- in/out tile region: root | dof | act | sensors | dof_force
+    const int nsens6 = 6 * ((P.num_obs - 12 - (HUM ? 4 : 3) * nd) / 6);          // 6 * nsens, from the obs layout
+    float *const s_root = io;
+    float *const s_dof = s_root + EPB * 13;
+    float *const s_act = s_dof + EPB * nd * 2;
+    float *const s_sens = s_act + EPB * nd;
+    float *const s_dfrc = s_sens + EPB * nsens6;
+    {
+        if (threadIdx.x == 0) mbar_init(&mbar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int nl = gm->nl, ncp = gm->ncp;      // two scalar loads; everything else arrives by bulk copy
+            const uint32_t hb = (uint32_t)offsetof(DevModel, links);
+            const uint32_t lb = round16((uint32_t)nl * (uint32_t)sizeof(LinkC)), cb = round16((uint32_t)ncp * (uint32_t)sizeof(CpC));
+            const uint32_t rb = EPB * 13 * 4, db = (uint32_t)(EPB * nd * 8), ab = (uint32_t)(EPB * nd * 4);
+            mbar_expect_tx(&mbar, hb + lb + cb + (tiles ? rb + db + ab : 0u));
+            bulk_g2s(&sm, gm, hb, &mbar);
+            bulk_g2s(sm.links, gm->links, lb, &mbar);
+            if (cb) bulk_g2s(reinterpret_cast<char *>(sm.links) + lb, gm->cps, cb, &mbar);
+            if (tiles) {
+                bulk_g2s(s_root, (const float *)B.p[B2G_T_ROOT_STATE] + (size_t)env0 * 13, rb, &mbar);
+                bulk_g2s(s_dof, (const float *)B.p[B2G_T_DOF_STATE] + (size_t)env0 * nd * 2, db, &mbar);
+                bulk_g2s(s_act, actions_in + (size_t)env0 * nd, ab, &mbar);
+            }
+        }
+        mbar_wait(&mbar, 0);
+    }
     using ST = Stepper<L, HF, BLOCK>;
     const int gt = blockIdx.x * BLOCK + threadIdx.x;
     const int env = gt / L, lane = gt % L;
@@ -172,26 +211,38 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? B2G_MINBLOCKS : 1)) loc
     const int el = e - env0;                             // env index inside this block's tiles
     const int NS = sm.ns;
     ST st = make_stepper<L, HF, BLOCK>(&sm, hf, lane);
-    RootState rs; load_root(tl.root + 13 * el, rs);
+    st.gr.cps = reinterpret_cast<const CpC *>(reinterpret_cast<const char *>(sm.links) + round16((uint32_t)sm.nl * (uint32_t)sizeof(LinkC)));
+
+    // this env's rows: shared-memory tiles, or the tensors themselves
+    float *const row_root = tiles ? s_root + 13 * el : (float *)B.p[B2G_T_ROOT_STATE] + 13 * (size_t)e;
+    float2 *const row_dof = reinterpret_cast<float2 *>(tiles ? s_dof + 2 * nd * el : (float *)B.p[B2G_T_DOF_STATE] + 2 * (size_t)nd * e);
+    const float *const row_act_in = tiles ? s_act + nd * el : actions_in + (size_t)nd * e;
+    float *const g_act_out = (float *)B.p[B2G_T_ACTIONS];
+    float *const row_act_out = tiles ? s_act + nd * el : (g_act_out ? g_act_out + (size_t)nd * e : nullptr);
+    float *const g_sens = (float *)B.p[B2G_T_FORCE_SENSOR], *const g_dfrc = (float *)B.p[B2G_T_DOF_FORCE];
+
+    RootState rs; load_root(row_root, rs);
 
     // ---- VecTask.step :374 clamp ; pre_physics_step (ant.py:281-285 / humanoid.py:281-285)
-    const float2 *dofs = tl.dof + (size_t)el * nd;
-    const float *acts = tl.act + (size_t)el * nd;
-    float *act_out = (float *)B.p[B2G_T_ACTIONS];
 #pragma unroll 1
     for (int s = 0; s < NS; s++) {
         const int d = sm.slot_link[s][lane] - 1;
-        const float2 v = dofs[d];
-        const float a = fminf(fmaxf(acts[d], -P.clip_actions), P.clip_actions);
-        if (valid && act_out) act_out[(size_t)e * nd + d] = a;
+        const float2 v = row_dof[d];
+        const float a = fminf(fmaxf(row_act_in[d], -P.clip_actions), P.clip_actions);
+        if (valid && row_act_out) row_act_out[d] = a;   // in tile mode this overwrites the raw action in place
         st.set_joint(s, v.x, v.y, a * (HUM ? P.motor_efforts[d] : P.joint_gears[d]) * P.power_scale);
     }
 
     // ---- control_freq_inv x gym.simulate (vec_task.py:379-382).  control_freq_inv == 0: no simulate --
     // the observation then reads the sensor / joint-force tensors as they stand (what refresh_*_tensor
     // would return); used to pin the observation/reward arithmetic against the reference's golden vectors
-    const typename ST::Outputs o = make_outputs<ST>(sm, B, e, valid);
     const int total = P.control_freq_inv * sm.substeps;
+    typename ST::Outputs o;
+    o.write = valid;
+    o.net_contact = B.p[B2G_T_NET_CONTACT] ? (float *)B.p[B2G_T_NET_CONTACT] + (size_t)e * sm.nb * 3 : nullptr;
+    const bool stage_out = tiles && total > 0;           // sensor / dof-force tiles are produced by the physics
+    o.sensor = stage_out ? s_sens + nsens6 * el : (g_sens ? g_sens + (size_t)e * nsens6 : nullptr);
+    o.dof_force = (stage_out && HUM) ? s_dfrc + nd * el : (g_dfrc ? g_dfrc + (size_t)e * nd : nullptr);
     for (int k = 0; k < total; k++) st.substep(rs, k == total - 1, o);
 
     // ---- post_physics_step (ant.py:287-297): progress, reset_idx, observations, reward
@@ -200,20 +251,26 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? B2G_MINBLOCKS : 1)) loc
     float *pot_b = (float *)B.p[B2G_T_POTENTIALS], *ppot_b = (float *)B.p[B2G_T_PREV_POTENTIALS];
     long long progress = progress_b[e] + 1;
     float potentials = pot_b[e];
-    if (reset_b[e] != 0) {
-        // reset_idx (ant.py:252-279 / humanoid.py:253-279)
-        int *rc = (int *)B.p[B2G_T_RESET_COUNT];
-        const uint32_t count = (uint32_t)rc[e];
-        const uint32_t gid = (uint32_t)(e + P.env_id_offset);
+    const bool do_reset = reset_b[e] != 0;
+    // final joint state -> dof rows (reset_idx, ant.py:252-279 / humanoid.py:253-279, overrides it)
+    uint32_t count = 0;
+    int *rc = (int *)B.p[B2G_T_RESET_COUNT];
+    if (do_reset) count = (uint32_t)rc[e];
+    const uint32_t gid = (uint32_t)(e + P.env_id_offset);
 #pragma unroll 1
-        for (int s = 0; s < NS; s++) {
-            const int d = sm.slot_link[s][lane] - 1;
+    for (int s = 0; s < NS; s++) {
+        const int d = sm.slot_link[s][lane] - 1;
+        float2 qv = st.get_q(s);
+        if (do_reset) {
             const float up = reset_uniform(P.seed, gid, count, d);
             const float uv = reset_uniform(P.seed, gid, count, nd + d);
             const float pos = (P.reset_pos_noise - (-P.reset_pos_noise)) * up + (-P.reset_pos_noise);
-            const float vel = (P.reset_vel_noise - (-P.reset_vel_noise)) * uv + (-P.reset_vel_noise);
-            st.set_q(s, fmaxf(fminf(P.initial_dof_pos[d] + pos, P.dof_limits_upper[d]), P.dof_limits_lower[d]), vel);
+            qv.x = fmaxf(fminf(P.initial_dof_pos[d] + pos, P.dof_limits_upper[d]), P.dof_limits_lower[d]);
+            qv.y = (P.reset_vel_noise - (-P.reset_vel_noise)) * uv + (-P.reset_vel_noise);
         }
+        if (valid) row_dof[d] = qv;
+    }
+    if (do_reset) {
         const float *ir = (const float *)B.p[B2G_T_INITIAL_ROOT] + 13 * (size_t)e;
         rs.rp[0] = ir[0]; rs.rp[1] = ir[1]; rs.rp[2] = ir[2];
         rs.rq[0] = ir[3]; rs.rq[1] = ir[4]; rs.rq[2] = ir[5]; rs.rq[3] = ir[6];
@@ -223,16 +280,29 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? B2G_MINBLOCKS : 1)) loc
         progress = 0;
         if (valid && lane == 0) rc[e] = (int)(count + 1);
     }
-    if (valid && lane == 0 && !sm.root_fixed) store_root(B, e, rs);
+    if (valid && lane == 0 && !sm.root_fixed) store_root(row_root, rs);
+
+    // the slot state is dead from here on: its shared memory becomes the output staging area
+    // layout (floats unless noted): obs | obs_clipped? | rew | pot | ppot | up(3) | head(3) | reset(i64) | progress(i64) | timeout(u8)
+    __syncthreads();
+    float *const g_obs = (float *)B.p[B2G_T_OBS];
+    float *g_obsc = (float *)B.p[B2G_T_OBS_CLIPPED];
+    if (g_obsc == g_obs) g_obsc = nullptr;
+    float *const so = reinterpret_cast<float *>(b2g_dyn_smem);
+    float *const t_obs = so;
+    float *const t_obsc = t_obs + EPB * O;
+    float *const t_rew = t_obsc + (g_obsc ? EPB * O : 0);
+    float *const t_pot = t_rew + EPB, *const t_ppot = t_pot + EPB, *const t_up = t_ppot + EPB, *const t_head = t_up + 3 * EPB;
+    long long *const t_reset = reinterpret_cast<long long *>(t_head + 3 * EPB), *const t_prog = t_reset + EPB;
+    uint8_t *const t_to = reinterpret_cast<uint8_t *>(t_prog + EPB);
+    float *const obs = tiles ? t_obs + (size_t)el * O : g_obs + (size_t)e * O;
+    float *const obsc = g_obsc ? (tiles ? t_obsc + (size_t)el * O : g_obsc + (size_t)e * O) : nullptr;
 
     // compute_observations
     LocoRootObs ro;
     loco_root_obs(P, rs.rp, rs.rq, rs.rv, rs.rw, HUM, ro);
     const float prev_potentials = potentials;     // prev_potentials_new = potentials.clone(), ant.py:390
     potentials = ro.potentials;
-    float *obs = (float *)B.p[B2G_T_OBS] + (size_t)e * P.num_obs;
-    float *obsc = (float *)B.p[B2G_T_OBS_CLIPPED];
-    obsc = (obsc && obsc != (float *)B.p[B2G_T_OBS]) ? obsc + (size_t)e * P.num_obs : nullptr;
     const float clipo = P.clip_obs;
     auto put = [&](int idx, float v) {
         if (!valid) return;
@@ -247,15 +317,13 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? B2G_MINBLOCKS : 1)) loc
     //    humanoid.py:407-411  [12 | nd pos | nd vel | nd dof_force | 12 sensors | nd actions]
     const int o_pos = 12, o_vel = 12 + nd, o_frc = 12 + 2 * nd;
     const int o_sens = HUM ? 12 + 3 * nd : 12 + 2 * nd;
-    const int o_act = o_sens + 6 * sm.nsens;
+    const int o_act = o_sens + nsens6;
     float actions_cost = 0.f, electricity = 0.f, at_limit = 0.f;
-    float2 *dw = (float2 *)B.p[B2G_T_DOF_STATE] + (size_t)e * nd;
 #pragma unroll 1
     for (int s = 0; s < NS; s++) {
         const int link = sm.slot_link[s][lane], d = link - 1;
-        const float2 qv = st.get_q(s);
-        if (valid) dw[d] = qv;
-        const float a = fminf(fmaxf(acts[d], -P.clip_actions), P.clip_actions);
+        const float2 qv = row_dof[d];
+        const float a = tiles ? row_act_out[d] : fminf(fmaxf(row_act_in[d], -P.clip_actions), P.clip_actions);
         const float ps = t_unscale(qv.x, P.dof_limits_lower[d], P.dof_limits_upper[d]);
         const float vs = qv.y * P.dof_vel_scale;
         put(o_pos + d, ps); put(o_vel + d, vs); put(o_act + d, a);
@@ -296,16 +364,45 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? B2G_MINBLOCKS : 1)) loc
         long long reset = 0;                       // reset_buf was cleared by reset_idx or was already 0
         if (height < P.termination_height) { total_r = P.death_cost; reset = 1; }
         if ((float)progress >= P.max_episode_length - 1.f) reset = 1;
-        ((float *)B.p[B2G_T_REW])[e] = total_r;
-        reset_b[e] = reset;
-        progress_b[e] = progress;
-        pot_b[e] = potentials; ppot_b[e] = prev_potentials;
+        const uint8_t tout = (uint8_t)(((float)progress >= P.max_episode_length - 1.f) && reset != 0);   // vec_task.py:394
         float *uv = (float *)B.p[B2G_T_UP_VEC], *hv = (float *)B.p[B2G_T_HEADING_VEC];
-        if (uv) { uv[3 * e] = ro.up_vec[0]; uv[3 * e + 1] = ro.up_vec[1]; uv[3 * e + 2] = ro.up_vec[2]; }
-        if (hv) { hv[3 * e] = ro.heading_vec[0]; hv[3 * e + 1] = ro.heading_vec[1]; hv[3 * e + 2] = ro.heading_vec[2]; }
-        // vec_task.py:394
         uint8_t *to = (uint8_t *)B.p[B2G_T_TIMEOUT];
-        if (to) to[e] = (uint8_t)(((float)progress >= P.max_episode_length - 1.f) && reset != 0);
+        if (tiles) {
+            t_rew[el] = total_r; t_reset[el] = reset; t_prog[el] = progress; t_pot[el] = potentials; t_ppot[el] = prev_potentials;
+            t_up[3 * el] = ro.up_vec[0]; t_up[3 * el + 1] = ro.up_vec[1]; t_up[3 * el + 2] = ro.up_vec[2];
+            t_head[3 * el] = ro.heading_vec[0]; t_head[3 * el + 1] = ro.heading_vec[1]; t_head[3 * el + 2] = ro.heading_vec[2];
+            t_to[el] = tout;
+        } else {
+            ((float *)B.p[B2G_T_REW])[e] = total_r;
+            reset_b[e] = reset; progress_b[e] = progress;
+            pot_b[e] = potentials; ppot_b[e] = prev_potentials;
+            if (uv) { uv[3 * e] = ro.up_vec[0]; uv[3 * e + 1] = ro.up_vec[1]; uv[3 * e + 2] = ro.up_vec[2]; }
+            if (hv) { hv[3 * e] = ro.heading_vec[0]; hv[3 * e + 1] = ro.heading_vec[1]; hv[3 * e + 2] = ro.heading_vec[2]; }
+            if (to) to[e] = tout;
+        }
+    }
+    if (tiles) {
+        fence_async_smem();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const size_t e0 = (size_t)env0;
+            if (!sm.root_fixed) bulk_s2g((float *)B.p[B2G_T_ROOT_STATE] + e0 * 13, s_root, EPB * 13 * 4);
+            bulk_s2g((float *)B.p[B2G_T_DOF_STATE] + e0 * nd * 2, s_dof, (uint32_t)(EPB * nd * 8));
+            if (g_act_out) bulk_s2g(g_act_out + e0 * nd, s_act, (uint32_t)(EPB * nd * 4));
+            if (stage_out && g_sens && nsens6) bulk_s2g(g_sens + e0 * nsens6, s_sens, (uint32_t)(EPB * nsens6 * 4));
+            if (stage_out && HUM && g_dfrc) bulk_s2g(g_dfrc + e0 * nd, s_dfrc, (uint32_t)(EPB * nd * 4));
+            bulk_s2g(g_obs + e0 * O, t_obs, (uint32_t)(EPB * O * 4));
+            if (g_obsc) bulk_s2g(g_obsc + e0 * O, t_obsc, (uint32_t)(EPB * O * 4));
+            bulk_s2g((float *)B.p[B2G_T_REW] + e0, t_rew, EPB * 4);
+            bulk_s2g(pot_b + e0, t_pot, EPB * 4);
+            bulk_s2g(ppot_b + e0, t_ppot, EPB * 4);
+            if (B.p[B2G_T_UP_VEC]) bulk_s2g((float *)B.p[B2G_T_UP_VEC] + 3 * e0, t_up, EPB * 12);
+            if (B.p[B2G_T_HEADING_VEC]) bulk_s2g((float *)B.p[B2G_T_HEADING_VEC] + 3 * e0, t_head, EPB * 12);
+            bulk_s2g(reset_b + e0, t_reset, EPB * 8);
+            bulk_s2g(progress_b + e0, t_prog, EPB * 8);
+            if (B.p[B2G_T_TIMEOUT]) bulk_s2g((uint8_t *)B.p[B2G_T_TIMEOUT] + e0, t_to, EPB);
+            bulk_commit_wait();
+        }
     }
 }
 
@@ -483,10 +580,11 @@ static int decompose(const b2g_model *m, bool single, DevModel &h) {
         for (int j = 0; j < s; j++) if (lanes[0][j] == p) ps = j;
         h.slot_parent[s] = ps; h.slot_acc[s] = -1;
     }
-    h.nacc = 0;
+    h.nacc = 0; h.root_acc = 0;
     for (int s = 0; s < ns; s++) {
         const int ps = h.slot_parent[s];
         if (ps >= 0 && ps != s - 1 && h.slot_acc[ps] < 0) h.slot_acc[ps] = h.nacc++;
+        if (ps < 0 && s > 0) h.root_acc = 1;
     }
     return 0;
 }
@@ -515,7 +613,7 @@ extern "C" int b2g_create(const b2g_model *m, const b2g_sim_params *sp, int32_t 
     if (decompose(m, force1 && force1[0] == '1', h) != 0) { delete s; return fail(B2G_E_INVALID, "b2g_create: too many links per lane"); }
     s->lanes = h.lanes;
     {   // CTA size: the per-thread slot state must fit in shared memory, preferably several CTAs per SM
-        const size_t per_thread = ((size_t)(h.ns + 1) * SLOT_F4 + (size_t)(h.nacc + 1) * ACC_F4) * sizeof(float4);
+        const size_t per_thread = ((size_t)h.ns * SLOT_F4 + (size_t)(h.nacc + h.root_acc) * ACC_F4) * sizeof(float4);
         int blk = 128;
         while (blk > 32 && per_thread * blk > 96 * 1024) blk >>= 1;
         if (per_thread * blk > 200 * 1024) { delete s; return fail(B2G_E_INVALID, "b2g_create: articulation too large for shared-memory slot state"); }
@@ -699,17 +797,23 @@ extern "C" int b2g_task_step(b2g_sim *s, const float *actions, void *stream) {
     } else {
         rc = require(s, {B2G_T_POTENTIALS, B2G_T_PREV_POTENTIALS, B2G_T_INITIAL_ROOT}, "b2g_task_step"); if (rc) return rc;
         const bool hum = P.task == B2G_TASK_HUMANOID;
-        // state tiles by bulk copy: whole blocks only, every tile a multiple of 16 bytes
-        const int epb = blk / s->lanes, ndof = s->hm.nl - 1;
-        const bool tiles = (N % epb == 0) && ((epb * 52) % 16 == 0) && ((epb * ndof * 8) % 16 == 0) && ((epb * ndof * 4) % 16 == 0);
-        const size_t state_f4 = (size_t)(s->hm.ns + 1) * SLOT_F4 + (size_t)(s->hm.nacc + 1) * ACC_F4;   // float4 per thread
-        const size_t tile_bytes = tiles ? (size_t)epb * (52 + ndof * 12) : 0;
-        const size_t dyn = s->dyn_smem + ((tile_bytes + 15) & ~(size_t)15);
-        const int tiles_arg = (int)(state_f4 << 8) | (tiles ? 1 : 0);
+        // tiles by bulk copy: whole blocks only, every tile a multiple of 16 bytes at a 16-byte-aligned address
+        const int epb = blk / s->lanes, ndof = s->hm.nl - 1, O = P.num_obs, ns6 = 6 * s->hm.nsens;
+        const bool clip_sep = s->buf.p[B2G_T_OBS_CLIPPED] && s->buf.p[B2G_T_OBS_CLIPPED] != s->buf.p[B2G_T_OBS];
+        const size_t state_bytes = s->dyn_smem;                                   // slot state + accumulators
+        const size_t io_bytes = ((size_t)epb * (13 + 3 * ndof + ns6 + (hum ? ndof : 0)) * 4 + 15) & ~(size_t)15;
+        const size_t out_bytes = (size_t)epb * ((clip_sep ? 2 : 1) * O * 4 + 4 * 3 + 12 * 2 + 8 * 2 + 1);
+        const bool tiles = (N % epb == 0) && (epb % 16 == 0) && ((epb * ndof * 4) % 16 == 0) && ((epb * ns6 * 4) % 16 == 0) &&
+                           ((epb * O * 4) % 16 == 0) && out_bytes <= state_bytes && s->buf.p[B2G_T_ACTIONS];
+        const size_t model_bytes = offsetof(DevModel, links) + (((size_t)s->hm.nl * sizeof(LinkC) + 15) & ~(size_t)15) +
+                                   (((size_t)s->hm.ncp * sizeof(CpC) + 15) & ~(size_t)15);
+        const size_t io_used = tiles ? io_bytes : 16;
+        const size_t dyn = state_bytes + io_used + model_bytes;
+        TileArgs ta; ta.on = tiles ? 1 : 0; ta.io_f4 = (int)(state_bytes / 16); ta.model_f4 = (int)((state_bytes + io_used) / 16);
 #define LOCO(LN, HM, BK)                                                                                              \
     do {                                                                                                               \
         int rc_ = set_smem(loco_step_kernel<LN, false, HM, BK>, dyn); if (rc_) return rc_;                            \
-        loco_step_kernel<LN, false, HM, BK><<<grid, blk, dyn, st>>>(s->dm, s->d_hf, s->buf, P, actions, (int)N, tiles_arg); \
+        loco_step_kernel<LN, false, HM, BK><<<grid, blk, dyn, st>>>(s->dm, s->d_hf, s->buf, P, actions, (int)N, ta);  \
     } while (0)
         if (s->d_hf) return fail(B2G_E_UNSUPPORTED, "locomotion tasks run on the ground plane");
         if (!hum && s->lanes == 4 && blk == 128) LOCO(4, false, 128);

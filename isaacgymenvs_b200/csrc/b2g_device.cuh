@@ -76,7 +76,8 @@ struct alignas(16) DevModel {
     int hf_nx, hf_ny;
     float hf_inv_scale, hf_scale, hf_vscale, hf_ox, hf_oy;
     int ns, lanes, nacc;  // slots per lane, lanes per env, shared-memory accumulators per thread (excl. the root's)
-    int pad0[3];
+    int root_acc;         // 1 if a lane owns several root children: accumulator index nacc collects them
+    int pad0[2];
     int slot_link[MAX_SLOTS][MAX_LANES];   // (slot, lane) -> link index
     int slot_parent[MAX_SLOTS];            // parent slot (-1 = root), the same for every lane
     int slot_acc[MAX_SLOTS];               // accumulator index of a slot with non-adjacent children, else -1
@@ -241,6 +242,7 @@ __device__ __forceinline__ void sym6_solve(const float IA[21], const float ba[3]
 struct Ground {
     const DevModel *m;
     const int16_t *hf;
+    const CpC *cps;       // contact spheres (shared memory; packed right behind the used links)
     // height and unit normal at world (x, y)
     __device__ __forceinline__ void sample(float x, float y, float &h, float n[3]) const {
         if (!m->has_hf) { h = 0.f; n[0] = 0.f; n[1] = 0.f; n[2] = 1.f; return; }
@@ -283,7 +285,7 @@ __device__ __forceinline__ void link_contacts(const DevModel *m, const Ground &g
     const float gn = m->cn + h * m->kn;
 #pragma unroll 1
     for (int k = lk.cp_begin + cp_first; k < lk.cp_end; k += cp_step) {
-        const CpC &cp = m->cps[k];
+        const CpC &cp = gr.cps[k];
         float pc[3], lp[3] = {cp.pos[0], cp.pos[1], cp.pos[2]};
         matvec(R, lp, pc);
         pc[0] += x[0]; pc[1] += x[1]; pc[2] += x[2];          // sphere centre relative to O
@@ -350,11 +352,11 @@ __device__ __forceinline__ void link_contacts(const DevModel *m, const Ground &g
 }
 
 // ---------------------------------------------------------------------------------------------
-// per-slot state in shared memory: 12 float4 per slot per thread, [slot][k][thread]
+// per-slot state in shared memory: 10 float4 per slot per thread, [slot][k][thread]
 //  k0: R0..R3   k1: R4..R7   k2: R8 x0 x1 x2   k3: vw0 vw1 vw2 vl0   k4: vl1 vl2 w0 w1   k5: w2 sl0 sl1 sl2
-//  k6: cw0 cw1 cw2 cl0   k7: cl1 cl2 tau diag   k8: U0..U3   k9: U4 U5 Dinv act
-//  k10: (u | aw0) aw1 aw2 al0   k11: al1 al2 q qd
-constexpr int SLOT_F4 = 12;
+//  k6: tau diag q qd   k7: act Dinv u -   k8: U0..U3   k9: U4 U5 - -
+//  after pass 3 the link acceleration (aw, al) overlays k0 / k1.xy for slots with non-adjacent children
+constexpr int SLOT_F4 = 10;
 constexpr int ACC_F4 = 7;     // a parked articulated inertia + bias: 27 floats
 
 struct RootState {            // replicated on the L lanes of the env
@@ -373,13 +375,12 @@ struct Stepper {
     __device__ __forceinline__ float4 &A4(int a, int k) const { return acc[(a * ACC_F4 + k) * BLOCK]; }
     __device__ __forceinline__ const LinkC &link(int s) const { return m->links[m->slot_link[s][lane]]; }
 
-    // q, qd of a slot (k11.z, k11.w) and its actuation / target (k9.w)
     __device__ __forceinline__ void set_joint(int s, float q, float qd, float act) const {
-        float4 v = S4(s, 11); v.z = q; v.w = qd; S4(s, 11) = v;
-        float4 u = S4(s, 9); u.w = act; S4(s, 9) = u;
+        float4 v = S4(s, 6); v.z = q; v.w = qd; S4(s, 6) = v;
+        float4 u = S4(s, 7); u.x = act; S4(s, 7) = u;
     }
-    __device__ __forceinline__ void set_q(int s, float q, float qd) const { float4 v = S4(s, 11); v.z = q; v.w = qd; S4(s, 11) = v; }
-    __device__ __forceinline__ float2 get_q(int s) const { const float4 v = S4(s, 11); return make_float2(v.z, v.w); }
+    __device__ __forceinline__ void set_q(int s, float q, float qd) const { float4 v = S4(s, 6); v.z = q; v.w = qd; S4(s, 6) = v; }
+    __device__ __forceinline__ float2 get_q(int s) const { const float4 v = S4(s, 6); return make_float2(v.z, v.w); }
 
     __device__ __forceinline__ void load_pose(int s, float R[9], float x[3], float vw[3], float vl[3]) const {
         const float4 a = S4(s, 0), b = S4(s, 1), c = S4(s, 2), d = S4(s, 3), e = S4(s, 4);
@@ -389,6 +390,20 @@ struct Stepper {
     __device__ __forceinline__ void load_axis(int s, float w[3], float sl[3]) const {
         const float4 e = S4(s, 4), f = S4(s, 5);
         w[0] = e.z; w[1] = e.w; w[2] = f.x; sl[0] = f.y; sl[1] = f.z; sl[2] = f.w;
+    }
+    // velocity-product acceleration c = crm(v)(S qd) of a slot, from its twist and joint axis
+    __device__ __forceinline__ static void bias_accel(const float vw[3], const float vl[3], const float w[3], const float sl[3],
+                                                      float qd, float cw[3], float cl[3]) {
+        float a1[3], a2[3], a3[3];
+        cross(vw, w, a1); cross(vw, sl, a2); cross(vl, w, a3);
+#pragma unroll
+        for (int c = 0; c < 3; c++) { cw[c] = a1[c] * qd; cl[c] = (a2[c] + a3[c]) * qd; }
+    }
+    __device__ __forceinline__ void root_pose(const RootState &rs, float R[9], float vw[3], float vl[3]) const {
+        quat_to_mat(rs.rq, R);
+        const bool fixed = m->root_fixed != 0;
+#pragma unroll
+        for (int c = 0; c < 3; c++) { vw[c] = fixed ? 0.f : rs.rw[c]; vl[c] = fixed ? 0.f : rs.rv[c]; }
     }
 
     // ---- one sub-step.  LAST: also produce contact wrench / joint force outputs (see Outputs)
@@ -404,36 +419,32 @@ struct Stepper {
         const int NS = m->ns;
         const float g[3] = {m->g[0], m->g[1], m->g[2]};
         const bool fixed = m->root_fixed != 0;
-        {   // the root's pose and twist live in slot NS
-            float Rr[9];
-            quat_to_mat(rs.rq, Rr);
-            S4(NS, 0) = make_float4(Rr[0], Rr[1], Rr[2], Rr[3]);
-            S4(NS, 1) = make_float4(Rr[4], Rr[5], Rr[6], Rr[7]);
-            S4(NS, 2) = make_float4(Rr[8], 0.f, 0.f, 0.f);
-            S4(NS, 3) = fixed ? make_float4(0.f, 0.f, 0.f, 0.f) : make_float4(rs.rw[0], rs.rw[1], rs.rw[2], rs.rv[0]);
-            S4(NS, 4) = fixed ? make_float4(0.f, 0.f, 0.f, 0.f) : make_float4(rs.rv[1], rs.rv[2], 0.f, 0.f);
-        }
 
         // ================= pass 1: kinematics, velocities, joint forces (root -> leaves)
         {
-            float Rc[9], xc[3], vwc[3], vlc[3];      // the slot just finished (parent of a chain successor)
+            float Rc[9], xc[3], vwc[3], vlc[3];      // the slot just finished; starts as the root (parent of slot 0)
+            root_pose(rs, Rc, vwc, vlc);
+            xc[0] = xc[1] = xc[2] = 0.f;
 #pragma unroll 1
             for (int s = 0; s < NS; s++) {
                 const LinkC &lk = link(s);
                 const int ps = m->slot_parent[s];
                 float Rp[9], xp[3], vwp[3], vlp[3];
-                if (ps >= 0 && ps == s - 1) {
+                if (ps == s - 1) {
 #pragma unroll
                     for (int c = 0; c < 9; c++) Rp[c] = Rc[c];
 #pragma unroll
                     for (int c = 0; c < 3; c++) { xp[c] = xc[c]; vwp[c] = vwc[c]; vlp[c] = vlc[c]; }
+                } else if (ps < 0) {
+                    root_pose(rs, Rp, vwp, vlp);
+                    xp[0] = xp[1] = xp[2] = 0.f;
                 } else {
-                    load_pose(ps < 0 ? NS : ps, Rp, xp, vwp, vlp);
+                    load_pose(ps, Rp, xp, vwp, vlp);
                 }
-                const float4 jq = S4(s, 11);
+                const float4 jq = S4(s, 6);
                 const float q = jq.z, qd = jq.w;
-                const float act = S4(s, 9).w;
-                float Rt[9], w[3], sl[3], cw[3], cl[3];
+                const float act = S4(s, 7).x;
+                float Rt[9], w[3], sl[3];
                 if (lk.flags & LF_R0_IDENTITY) {
 #pragma unroll
                     for (int c = 0; c < 9; c++) Rt[c] = Rp[c];
@@ -461,18 +472,11 @@ struct Stepper {
                     cross(xc, w, sl);                                 // S = (w ; x x w)
 #pragma unroll
                     for (int c = 0; c < 3; c++) { vwc[c] = vwp[c] + w[c] * qd; vlc[c] = vlp[c] + sl[c] * qd; }
-                    float a1[3], a2[3], a3[3];                        // c = crm(v)(S qd)
-                    cross(vwc, w, a1); cross(vwc, sl, a2); cross(vlc, w, a3);
-#pragma unroll
-                    for (int c = 0; c < 3; c++) { cw[c] = a1[c] * qd; cl[c] = (a2[c] + a3[c]) * qd; }
                 } else {
 #pragma unroll
                     for (int c = 0; c < 9; c++) Rc[c] = Rt[c];
 #pragma unroll
-                    for (int c = 0; c < 3; c++) { xc[c] = xp[c] + d[c] + w[c] * q; sl[c] = w[c]; vwc[c] = vwp[c]; vlc[c] = vlp[c] + w[c] * qd; }
-                    float a2[3]; cross(vwc, w, a2);                   // S = (0 ; w): c = (0 ; vw x w qd)
-#pragma unroll
-                    for (int c = 0; c < 3; c++) { cw[c] = 0.f; cl[c] = a2[c] * qd; w[c] = 0.f; }
+                    for (int c = 0; c < 3; c++) { xc[c] = xp[c] + d[c] + w[c] * q; sl[c] = w[c]; vwc[c] = vwp[c]; vlc[c] = vlp[c] + w[c] * qd; w[c] = 0.f; }
                 }
                 // joint force: explicit part + implicit diagonal (linear terms at the end of the sub-step)
                 const float qp = q + h * qd;
@@ -495,18 +499,23 @@ struct Stepper {
                 S4(s, 3) = make_float4(vwc[0], vwc[1], vwc[2], vlc[0]);
                 S4(s, 4) = make_float4(vlc[1], vlc[2], w[0], w[1]);
                 S4(s, 5) = make_float4(w[2], sl[0], sl[1], sl[2]);
-                S4(s, 6) = make_float4(cw[0], cw[1], cw[2], cl[0]);
-                S4(s, 7) = make_float4(cl[1], cl[2], f, dg);
+                S4(s, 6) = make_float4(f, dg, q, qd);
             }
         }
 
         // ================= pass 2: articulated inertias (leaves -> root)
-        // accumulator m->nacc collects what reaches the root from this lane's sub-trees
-        for (int a = 0; a <= m->nacc; a++)
+        // accumulator m->nacc (present when the lane has several root children) collects what reaches
+        // the root from sub-trees other than slot 0's, whose contribution arrives in registers
+        const int nacc_all = m->nacc + m->root_acc;
+        for (int a = 0; a < nacc_all; a++)
 #pragma unroll
             for (int k = 0; k < ACC_F4; k++) A4(a, k) = make_float4(0.f, 0.f, 0.f, 0.f);
+        float IA[21], pa[3], pl[3];     // travels along chains: child's projected inertia -> parent (finally the root)
+#pragma unroll
+        for (int c = 0; c < 21; c++) IA[c] = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; c++) { pa[c] = 0.f; pl[c] = 0.f; }
         {
-            float IA[21], pa[3], pl[3];     // travels along chains: child's projected inertia -> parent
             bool carry = false;
 #pragma unroll 1
             for (int s = NS - 1; s >= 0; s--) {
@@ -534,17 +543,18 @@ struct Stepper {
 #pragma unroll
                     for (int c = 0; c < 3; c++) { qa[c] += t[21 + c]; ql[c] += t[24 + c]; }
                 }
-                const float4 k6 = S4(s, 6), k7 = S4(s, 7);
-                const float cw[3] = {k6.x, k6.y, k6.z}, cl[3] = {k6.w, k7.x, k7.y};
-                const float tau = k7.z, dg = k7.w;
+                const float4 k6 = S4(s, 6);
+                const float tau = k6.x, dg = k6.y;
+                float cw[3], cl[3];
+                bias_accel(vw, vl, w, sl, k6.w, cw, cl);
                 float Ua[3], Ul[3];
                 sym6_mul(I, w, sl, Ua, Ul);
                 const float D = dot3(w, Ua) + dot3(sl, Ul) + dg;
                 const float di = 1.f / D;
                 const float u_ = tau - (dot3(w, qa) + dot3(sl, ql));
                 S4(s, 8) = make_float4(Ua[0], Ua[1], Ua[2], Ul[0]);
-                { float4 v = S4(s, 9); v.x = Ul[1]; v.y = Ul[2]; v.z = di; S4(s, 9) = v; }
-                { float4 v = S4(s, 10); v.x = u_; S4(s, 10) = v; }
+                S4(s, 9) = make_float4(Ul[1], Ul[2], 0.f, 0.f);
+                { float4 v = S4(s, 7); v.y = di; v.z = u_; S4(s, 7) = v; }
                 sym6_rank1(I, -di, Ua, Ul);                           // Ia = IA - U U^T / D
                 float ya[3], yl[3];
                 sym6_mul(I, cw, cl, ya, yl);
@@ -552,13 +562,12 @@ struct Stepper {
 #pragma unroll
                 for (int c = 0; c < 3; c++) { qa[c] += ya[c] + Ua[c] * ud; ql[c] += yl[c] + Ul[c] * ud; }
                 const int ps = m->slot_parent[s];
-                carry = false;
-                if (ps >= 0 && ps == s - 1) {
+                carry = (ps == s - 1);                                // includes slot 0 -> root
+                if (carry) {
 #pragma unroll
                     for (int c = 0; c < 21; c++) IA[c] = I[c];
 #pragma unroll
                     for (int c = 0; c < 3; c++) { pa[c] = qa[c]; pl[c] = ql[c]; }
-                    carry = true;
                 } else {
                     const int pi = ps < 0 ? m->nacc : m->slot_acc[ps];
                     float t[28];
@@ -577,29 +586,38 @@ struct Stepper {
             }
         }
         // ---- root: own inertia (lane 0), its contact spheres (dealt round-robin to the lanes), butterfly, solve
+        float awr[3], alr[3];
         {
-            float awr[3], alr[3];
             const LinkC &lk = m->links[0];
             const bool mine = (lane == 0);
-            float I[21], qa[3], ql[3], dummy[3], Rr[9], xr[3], vwr[3], vlr[3], IAr[21], par[3], plr[3];
-            load_pose(NS, Rr, xr, vwr, vlr);
+            float I[21], qa[3], ql[3], dummy[3], Rr[9], vwr[3], vlr[3];
+            const float xr[3] = {0.f, 0.f, 0.f};
+            root_pose(rs, Rr, vwr, vlr);
             link_inertia(lk, mine ? lk.mass : 0.f, mine ? 1.f : 0.f, Rr, xr, vwr, vlr, g, I, qa, ql);
             link_contacts<true, HF>(m, gr, lk, rs.rp, Rr, xr, vwr, vlr, I, qa, ql, dummy, dummy, dummy, dummy, lane, L);
-            {
+#pragma unroll
+            for (int c = 0; c < 21; c++) IA[c] += I[c];               // IA holds slot 0's contribution (or zeros)
+#pragma unroll
+            for (int c = 0; c < 3; c++) { pa[c] += qa[c]; pl[c] += ql[c]; }
+            if (nacc_all > m->nacc) {
                 float t[28];
 #pragma unroll
                 for (int k = 0; k < ACC_F4; k++) { const float4 v = A4(m->nacc, k); t[4 * k] = v.x; t[4 * k + 1] = v.y; t[4 * k + 2] = v.z; t[4 * k + 3] = v.w; }
 #pragma unroll
-                for (int c = 0; c < 21; c++) IAr[c] = lane_sum<L>(t[c] + I[c]);
+                for (int c = 0; c < 21; c++) IA[c] += t[c];
 #pragma unroll
-                for (int c = 0; c < 3; c++) { par[c] = lane_sum<L>(t[21 + c] + qa[c]); plr[c] = lane_sum<L>(t[24 + c] + ql[c]); }
+                for (int c = 0; c < 3; c++) { pa[c] += t[21 + c]; pl[c] += t[24 + c]; }
             }
+#pragma unroll
+            for (int c = 0; c < 21; c++) IA[c] = lane_sum<L>(IA[c]);
+#pragma unroll
+            for (int c = 0; c < 3; c++) { pa[c] = lane_sum<L>(pa[c]); pl[c] = lane_sum<L>(pl[c]); }
             if (fixed) {
 #pragma unroll
                 for (int c = 0; c < 3; c++) { awr[c] = 0.f; alr[c] = 0.f; }
             } else {
-                const float ba[3] = {-par[0], -par[1], -par[2]}, bl[3] = {-plr[0], -plr[1], -plr[2]};
-                sym6_solve(IAr, ba, bl, awr, alr);
+                const float ba[3] = {-pa[0], -pa[1], -pa[2]}, bl[3] = {-pl[0], -pl[1], -pl[2]};
+                sym6_solve(IA, ba, bl, awr, alr);
             }
             if (LAST) {
                 float F[3] = {0.f, 0.f, 0.f}, T[3] = {0.f, 0.f, 0.f};
@@ -608,60 +626,62 @@ struct Stepper {
                 for (int c = 0; c < 3; c++) { F[c] = lane_sum<L>(F[c]); T[c] = lane_sum<L>(T[c]); }
                 if (lane == 0) emit_wrench(0, lk, Rr, F, T, o);
             }
-            S4(NS, 10) = make_float4(awr[0], awr[1], awr[2], alr[0]);
-            S4(NS, 11) = make_float4(alr[1], alr[2], 0.f, 0.f);
         }
 
         // ================= pass 3: accelerations (root -> leaves), joint integration, outputs
         {
-            float awc[3], alc[3];
+            float awc[3] = {awr[0], awr[1], awr[2]}, alc[3] = {alr[0], alr[1], alr[2]};
 #pragma unroll 1
             for (int s = 0; s < NS; s++) {
                 const int ps = m->slot_parent[s];
                 float ap_w[3], ap_l[3];
-                if (ps >= 0 && ps == s - 1) {
+                if (ps == s - 1) {
 #pragma unroll
                     for (int c = 0; c < 3; c++) { ap_w[c] = awc[c]; ap_l[c] = alc[c]; }
+                } else if (ps < 0) {
+#pragma unroll
+                    for (int c = 0; c < 3; c++) { ap_w[c] = awr[c]; ap_l[c] = alr[c]; }
                 } else {
-                    const int pp = ps < 0 ? NS : ps;
-                    const float4 a = S4(pp, 10), b = S4(pp, 11);
+                    const float4 a = S4(ps, 0), b = S4(ps, 1);     // parent's acceleration overlays its R
                     ap_w[0] = a.x; ap_w[1] = a.y; ap_w[2] = a.z; ap_l[0] = a.w; ap_l[1] = b.x; ap_l[2] = b.y;
                 }
-                float w[3], sl[3];
+                float w[3], sl[3], R[9], x[3], vw[3], vl[3];
                 load_axis(s, w, sl);
-                const float4 k6 = S4(s, 6), k7 = S4(s, 7), k8 = S4(s, 8), k9 = S4(s, 9), k10 = S4(s, 10), k11 = S4(s, 11);
-                float a_w[3] = {ap_w[0] + k6.x, ap_w[1] + k6.y, ap_w[2] + k6.z};
-                float a_l[3] = {ap_l[0] + k6.w, ap_l[1] + k7.x, ap_l[2] + k7.y};
+                load_pose(s, R, x, vw, vl);
+                const float4 k6 = S4(s, 6), k7 = S4(s, 7), k8 = S4(s, 8), k9 = S4(s, 9);
+                float cw[3], cl[3];
+                bias_accel(vw, vl, w, sl, k6.w, cw, cl);
+                const float a_w[3] = {ap_w[0] + cw[0], ap_w[1] + cw[1], ap_w[2] + cw[2]};
+                const float a_l[3] = {ap_l[0] + cl[0], ap_l[1] + cl[1], ap_l[2] + cl[2]};
                 const float Ua_ = k8.x * a_w[0] + k8.y * a_w[1] + k8.z * a_w[2] + k8.w * a_l[0] + k9.x * a_l[1] + k9.y * a_l[2];
-                const float qdd = (k10.x - Ua_) * k9.z;
+                const float qdd = (k7.z - Ua_) * k7.y;
 #pragma unroll
                 for (int c = 0; c < 3; c++) { awc[c] = a_w[c] + w[c] * qdd; alc[c] = a_l[c] + sl[c] * qdd; }
-                const float qd = k11.w + h * qdd;
-                const float q = k11.z + h * qd;
-                S4(s, 10) = make_float4(awc[0], awc[1], awc[2], alc[0]);
-                S4(s, 11) = make_float4(alc[1], alc[2], q, qd);
+                const float qd = k6.w + h * qdd;
+                const float q = k6.z + h * qd;
+                S4(s, 6) = make_float4(k6.x, k6.y, q, qd);
                 if (LAST) {
                     const LinkC &lk = link(s);
                     const int li = m->slot_link[s][lane];
-                    if (o.dof_force && o.write) o.dof_force[li - 1] = k7.z - (k7.w - lk.armature) * qdd;
+                    if (o.dof_force && o.write) o.dof_force[li - 1] = k6.x - (k6.y - lk.armature) * qdd;
                     if (lk.cp_end > lk.cp_begin && (lk.sensor >= 0 || o.net_contact)) {
-                        float R[9], x[3], vw[3], vl[3], F[3] = {0.f, 0.f, 0.f}, T[3] = {0.f, 0.f, 0.f}, dI[1], d3[3];
-                        load_pose(s, R, x, vw, vl);
+                        float F[3] = {0.f, 0.f, 0.f}, T[3] = {0.f, 0.f, 0.f}, dI[1], d3[3];
                         link_contacts<false, HF>(m, gr, lk, rs.rp, R, x, vw, vl, dI, d3, d3, awc, alc, F, T, 0, 1);
                         emit_wrench(li, lk, R, F, T, o);
                     } else if (lk.sensor >= 0 || (o.net_contact && m->link_body[li] >= 0)) {
-                        float R[9], x[3], vw[3], vl[3]; const float z[3] = {0.f, 0.f, 0.f};
-                        load_pose(s, R, x, vw, vl);
+                        const float z[3] = {0.f, 0.f, 0.f};
                         emit_wrench(li, lk, R, z, z, o);
                     }
+                }
+                if (m->slot_acc[s] >= 0) {                           // some child is not the next slot: park a
+                    S4(s, 0) = make_float4(awc[0], awc[1], awc[2], alc[0]);
+                    float4 v = S4(s, 1); v.x = alc[1]; v.y = alc[2]; S4(s, 1) = v;
                 }
             }
         }
 
         // ================= root integration (classical acceleration of the origin = spatial + w x v)
         if (!fixed) {
-            const float4 ra = S4(NS, 10), rb = S4(NS, 11);
-            const float awr[3] = {ra.x, ra.y, ra.z}, alr[3] = {ra.w, rb.x, rb.y};
             float wxv[3]; cross(rs.rw, rs.rv, wxv);
 #pragma unroll
             for (int c = 0; c < 3; c++) { rs.rw[c] += h * awr[c]; rs.rv[c] += h * (alr[c] + wxv[c]); }
