@@ -163,11 +163,10 @@ def run_reference_arm(args):
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    from isaacgymenvs_b200 import distributed as D
+    rank, local, world = D.rank_info()
     torch.cuda.set_device(local)
+    D.init("nccl")
     device = f"cuda:{local}"
     task, n, bytes_per = WORKLOADS[args.workload]
     if args.num_envs:
@@ -179,8 +178,7 @@ def run_gpu_arm(args):
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=device)   # > 126 MB L2
 
     def barrier():
-        if world > 1:
-            dist.barrier()
+        D.barrier()
         torch.cuda.synchronize()
 
     # ---- device-resident throughput: per-step CUDA events on the launching stream, L2 flushed between steps
@@ -226,14 +224,10 @@ def run_gpu_arm(args):
     e2e_ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
     # ---- logging collective: per-env returns gathered once per rollout (north_star), off the step path
-    if world > 1:
-        gathered = [torch.empty_like(env.rew_buf) for _ in range(world)]
-        dist.all_gather(gathered, env.rew_buf)
+    all_returns = D.gather_returns(env.rew_buf)           # (world*n,) in global env order
+    assert all_returns.numel() == world * n
     # ---- max over ranks
-    t = torch.tensor([total_ms, b2b_ms, e2e_ms], device=device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, b2b_ms, e2e_ms = [float(x) for x in t.cpu()]
+    total_ms, b2b_ms, e2e_ms = D.max_over_ranks([total_ms, b2b_ms, e2e_ms], device=device)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -254,7 +248,7 @@ def run_gpu_arm(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{task} num_envs={n} per GPU, random actions U(-1,1), sim dt 0.0166 x 2 substeps",
                    "num_envs_total": world * n, "timing": "per-step CUDA events, 256 MB write flushes L2 between timed steps",
-                   "lanes_per_env": env.sim_lanes if hasattr(env, "sim_lanes") else None},
+                   "collective": "none on the step path; one NCCL all_gather of per-env returns per rollout (logging)"},
         "back_to_back": {"value": world * n * args.steps / (b2b_ms * 1e-3), "unit": "env-steps/s", "ms_per_step": b2b_ms / args.steps,
                          "note": "same K steps without the L2 flush (state stays L2-resident)"},
         "e2e": {"value": world * n * args.steps / (e2e_ms * 1e-3), "unit": "env-steps/s",
@@ -267,7 +261,8 @@ def run_gpu_arm(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        ns, ks = 2048, 40
+        ns = n                                            # the workload's own env count ...
+        ks = max(5, min(200, int(15000 * cores / ns)))    # ... for a bounded number of control steps (a few seconds of wall time)
         v, secs = cpu_pipeline(task, ns, ks, cores) if task == "Ant" else (None, 0)
         line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
                                 "sample": f"{ns} envs x {ks} control steps, {secs:.1f} s (oracle f32 physics + numpy obs/reward)"}

@@ -163,7 +163,7 @@ struct TileArgs {
     int model_f4;    // float4 offset of the packed model
 };
 
-template <int L, bool HF, bool HUM, int BLOCK>
+template <int L, bool HF, bool HUM, int BLOCK, bool TILES>
 __global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? B2G_MINBLOCKS : 1)) loco_step_kernel(
     const DevModel *__restrict__ gm, const int16_t *__restrict__ hf, Buffers B, const __grid_constant__ b2g_task_params P,
     const float *__restrict__ actions_in, int N, TileArgs ta) {
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? B2G_MINBLOCKS : 1)) loc
     const int nd = P.num_actions;                       // == dofs for the locomotion tasks (checked by b2g_set_task)
     const int O = P.num_obs;
     const int env0 = blockIdx.x * EPB;
-    const bool tiles = ta.on != 0;
+    constexpr bool tiles = TILES;
     float *const io = reinterpret_cast<float *>(b2g_dyn_smem + ta.io_f4);
     // ---- in/out tile region: root | dof | act | sensors | dof_force
     const int nsens6 = 6 * ((P.num_obs - 12 - (HUM ? 4 : 3) * nd) / 6);          // 6 * nsens, from the obs layout
@@ -183,6 +183,14 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? B2G_MINBLOCKS : 1)) loc
     float *const s_act = s_dof + EPB * nd * 2;
     float *const s_sens = s_act + EPB * nd;
     float *const s_dfrc = s_sens + EPB * nsens6;
+    // per-env scalars of post_physics_step: issued now, consumed after the physics
+    long long *const progress_b = (long long *)B.p[B2G_T_PROGRESS];
+    long long *const reset_b = (long long *)B.p[B2G_T_RESET];
+    float *const pot_b = (float *)B.p[B2G_T_POTENTIALS], *const ppot_b = (float *)B.p[B2G_T_PREV_POTENTIALS];
+    const int e_pre = min((int)((blockIdx.x * BLOCK + threadIdx.x) / L), N - 1);
+    const long long progress_in = progress_b[e_pre];
+    const long long reset_in = reset_b[e_pre];
+    const float potentials_in = pot_b[e_pre];
     {
         if (threadIdx.x == 0) mbar_init(&mbar, 1);
         __syncthreads();
@@ -246,12 +254,9 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? B2G_MINBLOCKS : 1)) loc
     for (int k = 0; k < total; k++) st.substep(rs, k == total - 1, o);
 
     // ---- post_physics_step (ant.py:287-297): progress, reset_idx, observations, reward
-    long long *progress_b = (long long *)B.p[B2G_T_PROGRESS];
-    long long *reset_b = (long long *)B.p[B2G_T_RESET];
-    float *pot_b = (float *)B.p[B2G_T_POTENTIALS], *ppot_b = (float *)B.p[B2G_T_PREV_POTENTIALS];
-    long long progress = progress_b[e] + 1;
-    float potentials = pot_b[e];
-    const bool do_reset = reset_b[e] != 0;
+    long long progress = progress_in + 1;
+    float potentials = potentials_in;
+    const bool do_reset = reset_in != 0;
     // final joint state -> dof rows (reset_idx, ant.py:252-279 / humanoid.py:253-279, overrides it)
     uint32_t count = 0;
     int *rc = (int *)B.p[B2G_T_RESET_COUNT];
@@ -810,11 +815,12 @@ extern "C" int b2g_task_step(b2g_sim *s, const float *actions, void *stream) {
         const size_t io_used = tiles ? io_bytes : 16;
         const size_t dyn = state_bytes + io_used + model_bytes;
         TileArgs ta; ta.on = tiles ? 1 : 0; ta.io_f4 = (int)(state_bytes / 16); ta.model_f4 = (int)((state_bytes + io_used) / 16);
-#define LOCO(LN, HM, BK)                                                                                              \
-    do {                                                                                                               \
-        int rc_ = set_smem(loco_step_kernel<LN, false, HM, BK>, dyn); if (rc_) return rc_;                            \
-        loco_step_kernel<LN, false, HM, BK><<<grid, blk, dyn, st>>>(s->dm, s->d_hf, s->buf, P, actions, (int)N, ta);  \
+#define LOCO_T(LN, HM, BK, TL)                                                                                            \
+    do {                                                                                                                   \
+        int rc_ = set_smem(loco_step_kernel<LN, false, HM, BK, TL>, dyn); if (rc_) return rc_;                            \
+        loco_step_kernel<LN, false, HM, BK, TL><<<grid, blk, dyn, st>>>(s->dm, s->d_hf, s->buf, P, actions, (int)N, ta);  \
     } while (0)
+#define LOCO(LN, HM, BK) do { if (tiles) LOCO_T(LN, HM, BK, true); else LOCO_T(LN, HM, BK, false); } while (0)
         if (s->d_hf) return fail(B2G_E_UNSUPPORTED, "locomotion tasks run on the ground plane");
         if (!hum && s->lanes == 4 && blk == 128) LOCO(4, false, 128);
         else if (!hum && s->lanes == 1 && blk == 128) LOCO(1, false, 128);
@@ -823,6 +829,7 @@ extern "C" int b2g_task_step(b2g_sim *s, const float *actions, void *stream) {
         else if (hum && s->lanes == 1 && blk == 32) LOCO(1, true, 32);
         else return fail(B2G_E_UNSUPPORTED, "no locomotion kernel instantiated for this (lanes, CTA size) combination");
 #undef LOCO
+#undef LOCO_T
     }
     s->launches++;
     CUDA_TRY(cudaGetLastError());
