@@ -51,8 +51,8 @@ __device__ __forceinline__ Tiles prologue(DevModel *sm, uint64_t *mbar, const De
     float *s_dof = s_root + rb / 4;
     float *s_act = s_dof + db / 4;
     if (threadIdx.x == 0) {
-        const int nl = gm->nl, ncp = gm->ncp;          // two scalar loads; everything else arrives by bulk copy
-        const uint32_t hb = (uint32_t)offsetof(DevModel, links);
+        const int nl = gm->nl, ncp = gm->ncp, ns = gm->ns;   // three scalar loads; everything else arrives by bulk copy
+        const uint32_t hb = (uint32_t)offsetof(DevModel, slots) + (uint32_t)ns * MAX_LANES * (uint32_t)sizeof(SlotRec);
         const uint32_t lb = round16((uint32_t)nl * (uint32_t)sizeof(LinkC)), cb = round16((uint32_t)ncp * (uint32_t)sizeof(CpC));
         uint32_t total = hb + lb + cb;
         if (tiles_on) total += rb + db + (g_act ? ab : 0u);
@@ -80,6 +80,7 @@ template <int L, bool HF, int BLOCK>
 __device__ __forceinline__ Stepper<L, HF, BLOCK> make_stepper(const DevModel *sm, const int16_t *hf, int lane) {
     Stepper<L, HF, BLOCK> st;
     st.m = sm; st.gr = Ground{sm, hf, sm->cps};
+    st.slots = &sm->slots[0][0]; st.links = sm->links;
     st.ss = b2g_dyn_smem + threadIdx.x;
     st.acc = b2g_dyn_smem + sm->ns * SLOT_F4 * BLOCK + threadIdx.x;
     st.lane = lane;
@@ -132,7 +133,8 @@ __global__ void __launch_bounds__(BLOCK) simulate_kernel(const DevModel *__restr
     const float *tgt = (const float *)B.p[B2G_T_DOF_TARGET];
 #pragma unroll 1
     for (int s = 0; s < NS; s++) {
-        const int link = sm.slot_link[s][lane];
+        const int link = st.link_of(s);
+        if (link < 0) continue;
         const float2 v = d[link - 1];
         const float *src = (sm.links[link].flags & LF_POSDRIVE) ? tgt : act;
         st.set_joint(s, v.x, v.y, src ? src[(size_t)e * nd + link - 1] : 0.f);
@@ -142,7 +144,7 @@ __global__ void __launch_bounds__(BLOCK) simulate_kernel(const DevModel *__restr
     if (!valid) return;
     float2 *dw = (float2 *)B.p[B2G_T_DOF_STATE] + (size_t)e * nd;
 #pragma unroll 1
-    for (int s = 0; s < NS; s++) dw[sm.slot_link[s][lane] - 1] = st.get_q(s);
+    for (int s = 0; s < NS; s++) { const int link = st.link_of(s); if (link >= 0) dw[link - 1] = st.get_q(s); }
     if (lane == 0 && !sm.root_fixed) store_root((float *)B.p[B2G_T_ROOT_STATE] + 13 * (size_t)e, rs);
 }
 
@@ -195,14 +197,15 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? B2G_MINBLOCKS : 1)) loc
         if (threadIdx.x == 0) mbar_init(&mbar, 1);
         __syncthreads();
         if (threadIdx.x == 0) {
-            const int nl = gm->nl, ncp = gm->ncp;      // two scalar loads; everything else arrives by bulk copy
-            const uint32_t hb = (uint32_t)offsetof(DevModel, links);
+            const int nl = gm->nl, ncp = gm->ncp, ns = gm->ns;   // three scalar loads; everything else arrives by bulk copy
+            const uint32_t hb = (uint32_t)offsetof(DevModel, slots) + (uint32_t)ns * MAX_LANES * (uint32_t)sizeof(SlotRec);
             const uint32_t lb = round16((uint32_t)nl * (uint32_t)sizeof(LinkC)), cb = round16((uint32_t)ncp * (uint32_t)sizeof(CpC));
             const uint32_t rb = EPB * 13 * 4, db = (uint32_t)(EPB * nd * 8), ab = (uint32_t)(EPB * nd * 4);
             mbar_expect_tx(&mbar, hb + lb + cb + (tiles ? rb + db + ab : 0u));
-            bulk_g2s(&sm, gm, hb, &mbar);
-            bulk_g2s(sm.links, gm->links, lb, &mbar);
-            if (cb) bulk_g2s(reinterpret_cast<char *>(sm.links) + lb, gm->cps, cb, &mbar);
+            bulk_g2s(&sm, gm, hb, &mbar);                                      // header | slots[0..ns)
+            char *const pk = reinterpret_cast<char *>(&sm) + hb;               // links and cps packed right behind
+            bulk_g2s(pk, gm->links, lb, &mbar);
+            if (cb) bulk_g2s(pk + lb, gm->cps, cb, &mbar);
             if (tiles) {
                 bulk_g2s(s_root, (const float *)B.p[B2G_T_ROOT_STATE] + (size_t)env0 * 13, rb, &mbar);
                 bulk_g2s(s_dof, (const float *)B.p[B2G_T_DOF_STATE] + (size_t)env0 * nd * 2, db, &mbar);
@@ -219,7 +222,11 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? B2G_MINBLOCKS : 1)) loc
     const int el = e - env0;                             // env index inside this block's tiles
     const int NS = sm.ns;
     ST st = make_stepper<L, HF, BLOCK>(&sm, hf, lane);
-    st.gr.cps = reinterpret_cast<const CpC *>(reinterpret_cast<const char *>(sm.links) + round16((uint32_t)sm.nl * (uint32_t)sizeof(LinkC)));
+    {
+        const char *pk = reinterpret_cast<const char *>(&sm) + offsetof(DevModel, slots) + (size_t)sm.ns * MAX_LANES * sizeof(SlotRec);
+        st.links = reinterpret_cast<const LinkC *>(pk);
+        st.gr.cps = reinterpret_cast<const CpC *>(pk + round16((uint32_t)sm.nl * (uint32_t)sizeof(LinkC)));
+    }
 
     // this env's rows: shared-memory tiles, or the tensors themselves
     float *const row_root = tiles ? s_root + 13 * el : (float *)B.p[B2G_T_ROOT_STATE] + 13 * (size_t)e;
@@ -234,7 +241,8 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? B2G_MINBLOCKS : 1)) loc
     // ---- VecTask.step :374 clamp ; pre_physics_step (ant.py:281-285 / humanoid.py:281-285)
 #pragma unroll 1
     for (int s = 0; s < NS; s++) {
-        const int d = sm.slot_link[s][lane] - 1;
+        const int d = st.link_of(s) - 1;
+        if (d < 0) continue;
         const float2 v = row_dof[d];
         const float a = fminf(fmaxf(row_act_in[d], -P.clip_actions), P.clip_actions);
         if (valid && row_act_out) row_act_out[d] = a;   // in tile mode this overwrites the raw action in place
@@ -264,7 +272,8 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? B2G_MINBLOCKS : 1)) loc
     const uint32_t gid = (uint32_t)(e + P.env_id_offset);
 #pragma unroll 1
     for (int s = 0; s < NS; s++) {
-        const int d = sm.slot_link[s][lane] - 1;
+        const int d = st.link_of(s) - 1;
+        if (d < 0) continue;
         float2 qv = st.get_q(s);
         if (do_reset) {
             const float up = reset_uniform(P.seed, gid, count, d);
@@ -326,14 +335,15 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? B2G_MINBLOCKS : 1)) loc
     float actions_cost = 0.f, electricity = 0.f, at_limit = 0.f;
 #pragma unroll 1
     for (int s = 0; s < NS; s++) {
-        const int link = sm.slot_link[s][lane], d = link - 1;
+        const int link = st.link_of(s), d = link - 1;
+        if (link < 0) continue;
         const float2 qv = row_dof[d];
         const float a = tiles ? row_act_out[d] : fminf(fmaxf(row_act_in[d], -P.clip_actions), P.clip_actions);
         const float ps = t_unscale(qv.x, P.dof_limits_lower[d], P.dof_limits_upper[d]);
         const float vs = qv.y * P.dof_vel_scale;
         put(o_pos + d, ps); put(o_vel + d, vs); put(o_act + d, a);
         if (HUM) put(o_frc + d, (o.dof_force ? o.dof_force[d] : 0.f) * P.contact_force_scale);
-        const int sk = sm.links[link].sensor;
+        const int sk = st.links[link].sensor;
         if (sk >= 0 && o.sensor) {
 #pragma unroll
             for (int c = 0; c < 6; c++) put(o_sens + 6 * sk + c, o.sensor[6 * sk + c] * P.contact_force_scale);
@@ -350,8 +360,8 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? B2G_MINBLOCKS : 1)) loc
             electricity += fabsf(a * vs);
         }
     }
-    if (lane == 0 && sm.links[0].sensor >= 0 && o.sensor) {
-        const int sk = sm.links[0].sensor;
+    if (lane == 0 && st.links[0].sensor >= 0 && o.sensor) {
+        const int sk = st.links[0].sensor;
 #pragma unroll
         for (int c = 0; c < 6; c++) put(o_sens + 6 * sk + c, o.sensor[6 * sk + c] * P.contact_force_scale);
     }
@@ -550,48 +560,84 @@ extern "C" const char *b2g_last_error(void) { return g_err.c_str(); }
 extern "C" int b2g_version(void) { return B2G_VERSION; }
 extern "C" int64_t b2g_launch_count(const b2g_sim *sim) { return sim ? sim->launches : 0; }
 
-// Decompose the tree into L lanes x NS slots: the sub-trees hanging off the root are dealt to the
-// lanes; L > 1 needs L sub-trees of identical shape (the SIMT lanes run the same slot program).
-static void subtree_dfs(const b2g_model *m, int i, std::vector<int> &out) {
-    out.push_back(i);
-    for (int c = i + 1; c < m->nl; c++) if (m->parent[c] == i) subtree_dfs(m, c, out);
-}
-static int decompose(const b2g_model *m, bool single, DevModel &h) {
-    std::vector<std::vector<int>> subs;
-    for (int i = 1; i < m->nl; i++) if (m->parent[i] == 0) { subs.emplace_back(); subtree_dfs(m, i, subs.back()); }
-    int L = 1;
-    auto shape = [&](const std::vector<int> &v) {
-        std::vector<int> sh;
-        for (int k = 0; k < (int)v.size(); k++) {
-            int p = m->parent[v[k]], ps = -1;
-            for (int j = 0; j < k; j++) if (v[j] == p) ps = j;
-            sh.push_back(ps);
+// Build the lanes' slot programs: list-schedule the links over `L` lanes, critical path first; a lane
+// keeps following a chain (parent at step s-1 in the same lane -> state travels in registers), any
+// other parent/child relation goes through shared memory (parked inertia / pose / acceleration).
+static int schedule(const b2g_model *m, int L, DevModel &h) {
+    const int nl = m->nl;
+    std::vector<int> height(nl, 1);
+    for (int i = nl - 1; i >= 1; i--) height[m->parent[i]] = std::max(height[m->parent[i]], height[i] + 1);
+    std::vector<int> t_of(nl, -1), lane_of(nl, -1);
+    t_of[0] = -1;
+    std::vector<int> lane_last(L, -1);
+    int remaining = nl - 1, t = 0;
+    for (int s = 0; s < MAX_SLOTS; s++) for (int l = 0; l < MAX_LANES; l++) {
+        SlotRec &r = h.slots[s][l]; r.link = -1; r.parent = 0; r.out = -1; r.flags = 0;
+        for (int c = 0; c < MAX_CHILD_REFS; c++) r.child[c] = -1;
+    }
+    while (remaining > 0) {
+        if (t >= MAX_SLOTS) return -1;
+        std::vector<int> ready;
+        for (int i = 1; i < nl; i++) if (t_of[i] < 0 && (m->parent[i] == 0 || (t_of[m->parent[i]] >= 0 && t_of[m->parent[i]] < t))) ready.push_back(i);
+        std::stable_sort(ready.begin(), ready.end(), [&](int a, int b) { return height[a] > height[b]; });
+        std::vector<int> pick(L, -1);
+        std::vector<char> used(nl, 0);
+        for (int l = 0; l < L; l++) {                                   // continue chains first
+            if (lane_last[l] < 0) continue;
+            for (int i : ready) if (!used[i] && m->parent[i] == lane_last[l]) { pick[l] = i; used[i] = 1; break; }
         }
-        return sh;
-    };
-    if (!single && (subs.size() == 4 || subs.size() == 2)) {
-        bool same = true;
-        for (size_t l = 1; l < subs.size(); l++) same = same && shape(subs[l]) == shape(subs[0]);
-        if (same) L = (int)subs.size();
+        for (int i : ready) {                                            // then the most critical remaining links
+            if (used[i]) continue;
+            int l = 0; while (l < L && pick[l] >= 0) l++;
+            if (l == L) break;
+            pick[l] = i; used[i] = 1;
+        }
+        for (int l = 0; l < L; l++) {
+            lane_last[l] = pick[l];
+            if (pick[l] >= 0) { t_of[pick[l]] = t; lane_of[pick[l]] = l; h.slots[t][l].link = pick[l]; remaining--; }
+        }
+        t++;
     }
-    std::vector<std::vector<int>> lanes(L);
-    if (L > 1) lanes = subs; else for (auto &v : subs) lanes[0].insert(lanes[0].end(), v.begin(), v.end());
-    const int ns = (int)lanes[0].size();
-    if (ns > MAX_SLOTS) return -1;
-    h.ns = ns; h.lanes = L;
-    for (int l = 0; l < L; l++) for (int s = 0; s < ns; s++) h.slot_link[s][l] = lanes[l][s];
-    for (int s = 0; s < ns; s++) {
-        int p = m->parent[lanes[0][s]], ps = -1;
-        for (int j = 0; j < s; j++) if (lanes[0][j] == p) ps = j;
-        h.slot_parent[s] = ps; h.slot_acc[s] = -1;
+    h.ns = t; h.lanes = L; h.cross_lane = 0; h.root_acc = -1;
+    std::vector<int> nacc(L, 0);
+    bool need_root_acc = false;
+    for (int i = 1; i < nl; i++) if (m->parent[i] == 0 && t_of[i] > 0) need_root_acc = true;
+    if (need_root_acc) { h.root_acc = 0; for (int l = 0; l < L; l++) nacc[l] = 1; }
+    for (int i = 1; i < nl; i++) {
+        const int l = lane_of[i], s = t_of[i], p = m->parent[i];
+        SlotRec &r = h.slots[s][l];
+        if (p == 0) {
+            r.parent = 0;
+            r.out = (s == 0) ? -1 : h.root_acc;
+        } else {
+            const int lp = lane_of[p], sp = t_of[p];
+            r.parent = (lp << 8) | (sp + 1);
+            if (lp != l) h.cross_lane = 1;
+            if (lp == l && sp == s - 1) r.out = -1;
+            else {
+                r.out = nacc[l]++;
+                SlotRec &pr = h.slots[sp][lp];
+                int c = 0; while (c < MAX_CHILD_REFS && pr.child[c] >= 0) c++;
+                if (c == MAX_CHILD_REFS) return -2;
+                pr.child[c] = (l << 8) | r.out;
+                pr.flags |= 1;
+            }
+        }
     }
-    h.nacc = 0; h.root_acc = 0;
-    for (int s = 0; s < ns; s++) {
-        const int ps = h.slot_parent[s];
-        if (ps >= 0 && ps != s - 1 && h.slot_acc[ps] < 0) h.slot_acc[ps] = h.nacc++;
-        if (ps < 0 && s > 0) h.root_acc = 1;
-    }
+    h.nacc = 0;
+    for (int l = 0; l < L; l++) h.nacc = std::max(h.nacc, nacc[l]);
     return 0;
+}
+static int pick_lanes(const b2g_model *m, bool single) {
+    if (single) return 1;
+    int root_children = 0;
+    for (int i = 1; i < m->nl; i++) if (m->parent[i] == 0) root_children++;
+    const char *env = getenv("B2G_LANES");
+    if (env && (env[0] == '1' || env[0] == '2' || env[0] == '4') && env[1] == 0) return env[0] - '0';
+    if (m->nl - 1 >= 16) return 4;                 // long trees (Humanoid, hands): chains run in parallel lanes
+    if (root_children >= 4) return 4;              // quadrupeds
+    if (root_children >= 2) return 2;
+    return 1;
 }
 
 extern "C" int b2g_create(const b2g_model *m, const b2g_sim_params *sp, int32_t num_envs, int32_t device, b2g_sim **out) {
@@ -615,12 +661,12 @@ extern "C" int b2g_create(const b2g_model *m, const b2g_sim_params *sp, int32_t 
     h.kn = m->contact_kn; h.cn = m->contact_cn; h.vs2 = m->contact_vs * m->contact_vs;
     // topology
     const char *force1 = getenv("B2G_SINGLE_LANE");
-    if (decompose(m, force1 && force1[0] == '1', h) != 0) { delete s; return fail(B2G_E_INVALID, "b2g_create: too many links per lane"); }
+    if (schedule(m, pick_lanes(m, force1 && force1[0] == '1'), h) != 0) { delete s; return fail(B2G_E_INVALID, "b2g_create: the articulation does not fit the slot program limits"); }
     s->lanes = h.lanes;
     {   // CTA size: the per-thread slot state must fit in shared memory, preferably several CTAs per SM
-        const size_t per_thread = ((size_t)h.ns * SLOT_F4 + (size_t)(h.nacc + h.root_acc) * ACC_F4) * sizeof(float4);
+        const size_t per_thread = ((size_t)h.ns * SLOT_F4 + (size_t)h.nacc * ACC_F4) * sizeof(float4);
         int blk = 128;
-        while (blk > 32 && per_thread * blk > 96 * 1024) blk >>= 1;
+        while (blk > 32 && per_thread * blk > 104 * 1024) blk >>= 1;
         if (per_thread * blk > 200 * 1024) { delete s; return fail(B2G_E_INVALID, "b2g_create: articulation too large for shared-memory slot state"); }
         s->block = blk; s->dyn_smem = per_thread * blk;
     }
@@ -739,7 +785,11 @@ static int set_smem(K kernel, size_t bytes) {
         const bool hf_ = s->d_hf != nullptr;                                                                           \
         if (s->lanes == 4 && !hf_ && blk == 128) B2G_LAUNCH((NAME<4, false, 128>), __VA_ARGS__);                       \
         else if (s->lanes == 4 && hf_ && blk == 128) B2G_LAUNCH((NAME<4, true, 128>), __VA_ARGS__);                    \
+        else if (s->lanes == 4 && !hf_ && blk == 64) B2G_LAUNCH((NAME<4, false, 64>), __VA_ARGS__);                    \
+        else if (s->lanes == 4 && !hf_ && blk == 32) B2G_LAUNCH((NAME<4, false, 32>), __VA_ARGS__);                    \
         else if (s->lanes == 2 && !hf_ && blk == 128) B2G_LAUNCH((NAME<2, false, 128>), __VA_ARGS__);                  \
+        else if (s->lanes == 2 && !hf_ && blk == 64) B2G_LAUNCH((NAME<2, false, 64>), __VA_ARGS__);                    \
+        else if (s->lanes == 2 && !hf_ && blk == 32) B2G_LAUNCH((NAME<2, false, 32>), __VA_ARGS__);                    \
         else if (s->lanes == 1 && !hf_ && blk == 128) B2G_LAUNCH((NAME<1, false, 128>), __VA_ARGS__);                  \
         else if (s->lanes == 1 && !hf_ && blk == 64) B2G_LAUNCH((NAME<1, false, 64>), __VA_ARGS__);                    \
         else if (s->lanes == 1 && !hf_ && blk == 32) B2G_LAUNCH((NAME<1, false, 32>), __VA_ARGS__);                    \
@@ -810,7 +860,7 @@ extern "C" int b2g_task_step(b2g_sim *s, const float *actions, void *stream) {
         const size_t out_bytes = (size_t)epb * ((clip_sep ? 2 : 1) * O * 4 + 4 * 3 + 12 * 2 + 8 * 2 + 1);
         const bool tiles = (N % epb == 0) && (epb % 16 == 0) && ((epb * ndof * 4) % 16 == 0) && ((epb * ns6 * 4) % 16 == 0) &&
                            ((epb * O * 4) % 16 == 0) && out_bytes <= state_bytes && s->buf.p[B2G_T_ACTIONS];
-        const size_t model_bytes = offsetof(DevModel, links) + (((size_t)s->hm.nl * sizeof(LinkC) + 15) & ~(size_t)15) +
+        const size_t model_bytes = offsetof(DevModel, slots) + (size_t)s->hm.ns * MAX_LANES * sizeof(SlotRec) + (((size_t)s->hm.nl * sizeof(LinkC) + 15) & ~(size_t)15) +
                                    (((size_t)s->hm.ncp * sizeof(CpC) + 15) & ~(size_t)15);
         const size_t io_used = tiles ? io_bytes : 16;
         const size_t dyn = state_bytes + io_used + model_bytes;
@@ -824,7 +874,11 @@ extern "C" int b2g_task_step(b2g_sim *s, const float *actions, void *stream) {
         if (s->d_hf) return fail(B2G_E_UNSUPPORTED, "locomotion tasks run on the ground plane");
         if (!hum && s->lanes == 4 && blk == 128) LOCO(4, false, 128);
         else if (!hum && s->lanes == 1 && blk == 128) LOCO(1, false, 128);
-        else if (hum && s->lanes == 1 && blk == 128) LOCO(1, true, 128);
+        else if (hum && s->lanes == 4 && blk == 128) LOCO(4, true, 128);
+        else if (hum && s->lanes == 4 && blk == 64) LOCO(4, true, 64);
+        else if (hum && s->lanes == 4 && blk == 32) LOCO(4, true, 32);
+        else if (hum && s->lanes == 2 && blk == 64) LOCO(2, true, 64);
+        else if (hum && s->lanes == 2 && blk == 32) LOCO(2, true, 32);
         else if (hum && s->lanes == 1 && blk == 64) LOCO(1, true, 64);
         else if (hum && s->lanes == 1 && blk == 32) LOCO(1, true, 32);
         else return fail(B2G_E_UNSUPPORTED, "no locomotion kernel instantiated for this (lanes, CTA size) combination");

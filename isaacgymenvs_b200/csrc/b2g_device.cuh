@@ -64,9 +64,23 @@ struct CpC {
 };                        // 7 words
 static_assert(sizeof(CpC) == 7 * 4, "CpC stride");
 
-// Hot part first (what the step kernels read), 16-byte aligned regions so that the model reaches
-// shared memory as three bulk-async copies (header, links[0..nl), cps[0..ncp)); the cold tail is
-// only read by the forward-kinematics kernel.
+// One entry of a lane's slot program: which link the lane processes at sweep step s, where its
+// parent lives, where its projected articulated inertia goes and which parked contributions it
+// collects.  A lane may idle at a step (link < 0) while it waits for another lane's chain.
+constexpr int MAX_CHILD_REFS = 4;
+struct SlotRec {
+    int link;                       // link index, -1 = idle
+    int parent;                     // 0 = root, else ((lane << 8) | (slot + 1)) of the parent's slot
+    int out;                        // -1: carried in registers to the next-lower slot of this lane (or to the root after slot 0);
+                                    // else index of the accumulator (own thread column) the projected inertia is parked in
+    int flags;                      // bit 0: park the acceleration after pass 3 (a child is not the next slot of this lane)
+    int child[MAX_CHILD_REFS];      // parked contributions to add: ((lane << 8) | accumulator), -1 = none
+};
+static_assert(sizeof(SlotRec) == 32, "SlotRec");
+
+// Hot part first (what the step kernels read) in 16-byte-aligned regions, so the model reaches shared
+// memory as bulk-async copies of exactly the used bytes: header | slots[0..ns) | links[0..nl) |
+// cps[0..ncp).  The cold tail is only read by the forward-kinematics kernel.
 struct alignas(16) DevModel {
     int nl, ncp, nb, nsens;
     int root_fixed, gravity_on, substeps, has_hf;
@@ -75,15 +89,14 @@ struct alignas(16) DevModel {
     float kn, cn, vs2;    // contact stiffness, damping, (slip regularisation speed)^2
     int hf_nx, hf_ny;
     float hf_inv_scale, hf_scale, hf_vscale, hf_ox, hf_oy;
-    int ns, lanes, nacc;  // slots per lane, lanes per env, shared-memory accumulators per thread (excl. the root's)
-    int root_acc;         // 1 if a lane owns several root children: accumulator index nacc collects them
-    int pad0[2];
-    int slot_link[MAX_SLOTS][MAX_LANES];   // (slot, lane) -> link index
-    int slot_parent[MAX_SLOTS];            // parent slot (-1 = root), the same for every lane
-    int slot_acc[MAX_SLOTS];               // accumulator index of a slot with non-adjacent children, else -1
+    int ns, lanes, nacc;  // sweep steps per lane, lanes per env, accumulators per thread
+    int root_acc;         // accumulator index collecting this lane's root children other than slot 0's (-1: none)
+    int cross_lane;       // some slot's parent lives in another lane (needs the shared-memory handoff + __syncwarp)
+    int pad0;
     int sensor_body[MAX_SENS];
     float sensor_bpos[MAX_SENS][3];        // body-frame origin of the sensor's body in its link frame
     int link_body[MAX_LINKS];              // first body riding on the link (-1: massless virtual link)
+    alignas(16) SlotRec slots[MAX_SLOTS][MAX_LANES];
     alignas(16) LinkC links[MAX_LINKS];
     alignas(16) CpC cps[MAX_CP];
     // ---- cold
@@ -92,7 +105,7 @@ struct alignas(16) DevModel {
     float body_pos[MAX_LINKS][3];
     float body_quat[MAX_LINKS][4];
 };
-static_assert(offsetof(DevModel, links) % 16 == 0 && offsetof(DevModel, cps) % 16 == 0, "bulk-copy alignment");
+static_assert(offsetof(DevModel, slots) % 16 == 0 && offsetof(DevModel, links) % 16 == 0 && offsetof(DevModel, cps) % 16 == 0, "bulk-copy alignment");
 
 // ---------------------------------------------------------------------------------------------
 // bulk-async (TMA) copies + mbarrier, sm_90+ PTX
@@ -365,27 +378,39 @@ struct RootState {            // replicated on the L lanes of the env
 
 template <int L, bool HF, int BLOCK>
 struct Stepper {
-    const DevModel *m;
+    const DevModel *m;        // header (scalars, sensor tables)
+    const SlotRec *slots;     // [ns][MAX_LANES]
+    const LinkC *links;
     Ground gr;
     float4 *ss;               // this thread's column of the slot-state array
     float4 *acc;              // this thread's column of the accumulator pool
     int lane;
 
     __device__ __forceinline__ float4 &S4(int s, int k) const { return ss[(s * SLOT_F4 + k) * BLOCK]; }
+    // slot state of another lane of the same env (cross-lane parents): thread column offset by (ln - lane)
+    __device__ __forceinline__ const float4 &S4x(int ln, int s, int k) const { return ss[(s * SLOT_F4 + k) * BLOCK + (ln - lane)]; }
     __device__ __forceinline__ float4 &A4(int a, int k) const { return acc[(a * ACC_F4 + k) * BLOCK]; }
-    __device__ __forceinline__ const LinkC &link(int s) const { return m->links[m->slot_link[s][lane]]; }
+    __device__ __forceinline__ const float4 &A4x(int ln, int a, int k) const { return acc[(a * ACC_F4 + k) * BLOCK + (ln - lane)]; }
+    __device__ __forceinline__ const SlotRec &rec(int s) const { return slots[s * MAX_LANES + lane]; }
+    __device__ __forceinline__ int link_of(int s) const { return slots[s * MAX_LANES + lane].link; }
 
     __device__ __forceinline__ void set_joint(int s, float q, float qd, float act) const {
         float4 v = S4(s, 6); v.z = q; v.w = qd; S4(s, 6) = v;
         float4 u = S4(s, 7); u.x = act; S4(s, 7) = u;
     }
+    __device__ __forceinline__ void set_act(int s, float act) const { float4 u = S4(s, 7); u.x = act; S4(s, 7) = u; }
     __device__ __forceinline__ void set_q(int s, float q, float qd) const { float4 v = S4(s, 6); v.z = q; v.w = qd; S4(s, 6) = v; }
     __device__ __forceinline__ float2 get_q(int s) const { const float4 v = S4(s, 6); return make_float2(v.z, v.w); }
 
-    __device__ __forceinline__ void load_pose(int s, float R[9], float x[3], float vw[3], float vl[3]) const {
-        const float4 a = S4(s, 0), b = S4(s, 1), c = S4(s, 2), d = S4(s, 3), e = S4(s, 4);
+    __device__ __forceinline__ void load_pose_x(int ln, int s, float R[9], float x[3], float vw[3], float vl[3]) const {
+        const float4 a = S4x(ln, s, 0), b = S4x(ln, s, 1), c = S4x(ln, s, 2), d = S4x(ln, s, 3), e = S4x(ln, s, 4);
         R[0] = a.x; R[1] = a.y; R[2] = a.z; R[3] = a.w; R[4] = b.x; R[5] = b.y; R[6] = b.z; R[7] = b.w; R[8] = c.x;
         x[0] = c.y; x[1] = c.z; x[2] = c.w; vw[0] = d.x; vw[1] = d.y; vw[2] = d.z; vl[0] = d.w; vl[1] = e.x; vl[2] = e.y;
+    }
+    __device__ __forceinline__ void load_pose(int s, float R[9], float x[3], float vw[3], float vl[3]) const { load_pose_x(lane, s, R, x, vw, vl); }
+    __device__ __forceinline__ void load_twist(int s, float vw[3], float vl[3]) const {
+        const float4 d = S4(s, 3), e = S4(s, 4);
+        vw[0] = d.x; vw[1] = d.y; vw[2] = d.z; vl[0] = d.w; vl[1] = e.x; vl[2] = e.y;
     }
     __device__ __forceinline__ void load_axis(int s, float w[3], float sl[3]) const {
         const float4 e = S4(s, 4), f = S4(s, 5);
@@ -405,6 +430,8 @@ struct Stepper {
 #pragma unroll
         for (int c = 0; c < 3; c++) { vw[c] = fixed ? 0.f : rs.rw[c]; vl[c] = fixed ? 0.f : rs.rv[c]; }
     }
+    // lanes of an env exchange slot state through shared memory: order the accesses
+    __device__ __forceinline__ void lane_sync() const { if (L > 1 && m->cross_lane) __syncwarp(); }
 
     // ---- one sub-step.  LAST: also produce contact wrench / joint force outputs (see Outputs)
     struct Outputs {
@@ -427,90 +454,95 @@ struct Stepper {
             xc[0] = xc[1] = xc[2] = 0.f;
 #pragma unroll 1
             for (int s = 0; s < NS; s++) {
-                const LinkC &lk = link(s);
-                const int ps = m->slot_parent[s];
-                float Rp[9], xp[3], vwp[3], vlp[3];
-                if (ps == s - 1) {
+                const SlotRec &sr = rec(s);
+                if (sr.link >= 0) {
+                    const LinkC &lk = links[sr.link];
+                    const int pl_ = sr.parent >> 8, ps = (sr.parent & 255) - 1;   // parent lane / slot (ps = -1: root)
+                    float Rp[9], xp[3], vwp[3], vlp[3];
+                    if (ps == s - 1 && (ps < 0 || pl_ == lane)) {                 // previous slot of this lane (or root before slot 0)
 #pragma unroll
-                    for (int c = 0; c < 9; c++) Rp[c] = Rc[c];
+                        for (int c = 0; c < 9; c++) Rp[c] = Rc[c];
 #pragma unroll
-                    for (int c = 0; c < 3; c++) { xp[c] = xc[c]; vwp[c] = vwc[c]; vlp[c] = vlc[c]; }
-                } else if (ps < 0) {
-                    root_pose(rs, Rp, vwp, vlp);
-                    xp[0] = xp[1] = xp[2] = 0.f;
-                } else {
-                    load_pose(ps, Rp, xp, vwp, vlp);
-                }
-                const float4 jq = S4(s, 6);
-                const float q = jq.z, qd = jq.w;
-                const float act = S4(s, 7).x;
-                float Rt[9], w[3], sl[3];
-                if (lk.flags & LF_R0_IDENTITY) {
-#pragma unroll
-                    for (int c = 0; c < 9; c++) Rt[c] = Rp[c];
-                } else {
-                    matmul(Rp, lk.R0, Rt);
-                }
-                const float ax[3] = {lk.axis[0], lk.axis[1], lk.axis[2]};
-                matvec(Rt, ax, w);
-                const float lp[3] = {lk.lpos[0], lk.lpos[1], lk.lpos[2]};
-                float d[3]; matvec(Rp, lp, d);
-                if (!(lk.flags & LF_SLIDE)) {
-                    float sn, cs; b2g_sincos(q, &sn, &cs);
-                    const float oc = 1.f - cs;
-#pragma unroll
-                    for (int j = 0; j < 3; j++) {   // rotate column j of Rt about the world axis w by q
-                        const float col[3] = {Rt[j], Rt[3 + j], Rt[6 + j]};
-                        float wxc[3]; cross(w, col, wxc);
-                        const float wd = dot3(w, col) * oc;
-                        Rc[j] = col[0] * cs + wxc[0] * sn + w[0] * wd;
-                        Rc[3 + j] = col[1] * cs + wxc[1] * sn + w[1] * wd;
-                        Rc[6 + j] = col[2] * cs + wxc[2] * sn + w[2] * wd;
+                        for (int c = 0; c < 3; c++) { xp[c] = xc[c]; vwp[c] = vwc[c]; vlp[c] = vlc[c]; }
+                    } else if (ps < 0) {
+                        root_pose(rs, Rp, vwp, vlp);
+                        xp[0] = xp[1] = xp[2] = 0.f;
+                    } else {
+                        load_pose_x(pl_, ps, Rp, xp, vwp, vlp);
                     }
+                    const float4 jq = S4(s, 6);
+                    const float q = jq.z, qd = jq.w;
+                    const float act = S4(s, 7).x;
+                    float Rt[9], w[3], sl[3];
+                    if (lk.flags & LF_R0_IDENTITY) {
 #pragma unroll
-                    for (int c = 0; c < 3; c++) xc[c] = xp[c] + d[c];
-                    cross(xc, w, sl);                                 // S = (w ; x x w)
+                        for (int c = 0; c < 9; c++) Rt[c] = Rp[c];
+                    } else {
+                        matmul(Rp, lk.R0, Rt);
+                    }
+                    const float ax[3] = {lk.axis[0], lk.axis[1], lk.axis[2]};
+                    matvec(Rt, ax, w);
+                    const float lp[3] = {lk.lpos[0], lk.lpos[1], lk.lpos[2]};
+                    float d[3]; matvec(Rp, lp, d);
+                    if (!(lk.flags & LF_SLIDE)) {
+                        float sn, cs; b2g_sincos(q, &sn, &cs);
+                        const float oc = 1.f - cs;
 #pragma unroll
-                    for (int c = 0; c < 3; c++) { vwc[c] = vwp[c] + w[c] * qd; vlc[c] = vlp[c] + sl[c] * qd; }
-                } else {
+                        for (int j = 0; j < 3; j++) {   // rotate column j of Rt about the world axis w by q
+                            const float col[3] = {Rt[j], Rt[3 + j], Rt[6 + j]};
+                            float wxc[3]; cross(w, col, wxc);
+                            const float wd = dot3(w, col) * oc;
+                            Rc[j] = col[0] * cs + wxc[0] * sn + w[0] * wd;
+                            Rc[3 + j] = col[1] * cs + wxc[1] * sn + w[1] * wd;
+                            Rc[6 + j] = col[2] * cs + wxc[2] * sn + w[2] * wd;
+                        }
 #pragma unroll
-                    for (int c = 0; c < 9; c++) Rc[c] = Rt[c];
+                        for (int c = 0; c < 3; c++) xc[c] = xp[c] + d[c];
+                        cross(xc, w, sl);                                 // S = (w ; x x w)
 #pragma unroll
-                    for (int c = 0; c < 3; c++) { xc[c] = xp[c] + d[c] + w[c] * q; sl[c] = w[c]; vwc[c] = vwp[c]; vlc[c] = vlp[c] + w[c] * qd; w[c] = 0.f; }
+                        for (int c = 0; c < 3; c++) { vwc[c] = vwp[c] + w[c] * qd; vlc[c] = vlp[c] + sl[c] * qd; }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 9; c++) Rc[c] = Rt[c];
+#pragma unroll
+                        for (int c = 0; c < 3; c++) { xc[c] = xp[c] + d[c] + w[c] * q; sl[c] = w[c]; vwc[c] = vwp[c]; vlc[c] = vlp[c] + w[c] * qd; w[c] = 0.f; }
+                    }
+                    // joint force: explicit part + implicit diagonal (linear terms at the end of the sub-step)
+                    const float qp = q + h * qd;
+                    float f = -lk.damping * qd - lk.stiffness * qp;
+                    float dg = lk.armature + h * lk.damping + h * h * lk.stiffness;
+                    if (lk.flags & LF_POSDRIVE) {
+                        float pd = lk.kp * (act - qp) - lk.kd * qd;
+                        pd = fminf(fmaxf(pd, -lk.effort), lk.effort);
+                        f += pd; dg += h * lk.kd + h * h * lk.kp;
+                    } else {
+                        f += fminf(fmaxf(act, -lk.effort), lk.effort);
+                    }
+                    if (lk.flags & LF_LIMITED) {
+                        if (q < lk.lower) { f += lk.limit_k * (lk.lower - qp) - lk.limit_d * qd; dg += h * lk.limit_d + h * h * lk.limit_k; }
+                        else if (q > lk.upper) { f += lk.limit_k * (lk.upper - qp) - lk.limit_d * qd; dg += h * lk.limit_d + h * h * lk.limit_k; }
+                    }
+                    S4(s, 0) = make_float4(Rc[0], Rc[1], Rc[2], Rc[3]);
+                    S4(s, 1) = make_float4(Rc[4], Rc[5], Rc[6], Rc[7]);
+                    S4(s, 2) = make_float4(Rc[8], xc[0], xc[1], xc[2]);
+                    S4(s, 3) = make_float4(vwc[0], vwc[1], vwc[2], vlc[0]);
+                    S4(s, 4) = make_float4(vlc[1], vlc[2], w[0], w[1]);
+                    S4(s, 5) = make_float4(w[2], sl[0], sl[1], sl[2]);
+                    S4(s, 6) = make_float4(f, dg, q, qd);
                 }
-                // joint force: explicit part + implicit diagonal (linear terms at the end of the sub-step)
-                const float qp = q + h * qd;
-                float f = -lk.damping * qd - lk.stiffness * qp;
-                float dg = lk.armature + h * lk.damping + h * h * lk.stiffness;
-                if (lk.flags & LF_POSDRIVE) {
-                    float pd = lk.kp * (act - qp) - lk.kd * qd;
-                    pd = fminf(fmaxf(pd, -lk.effort), lk.effort);
-                    f += pd; dg += h * lk.kd + h * h * lk.kp;
-                } else {
-                    f += fminf(fmaxf(act, -lk.effort), lk.effort);
-                }
-                if (lk.flags & LF_LIMITED) {
-                    if (q < lk.lower) { f += lk.limit_k * (lk.lower - qp) - lk.limit_d * qd; dg += h * lk.limit_d + h * h * lk.limit_k; }
-                    else if (q > lk.upper) { f += lk.limit_k * (lk.upper - qp) - lk.limit_d * qd; dg += h * lk.limit_d + h * h * lk.limit_k; }
-                }
-                S4(s, 0) = make_float4(Rc[0], Rc[1], Rc[2], Rc[3]);
-                S4(s, 1) = make_float4(Rc[4], Rc[5], Rc[6], Rc[7]);
-                S4(s, 2) = make_float4(Rc[8], xc[0], xc[1], xc[2]);
-                S4(s, 3) = make_float4(vwc[0], vwc[1], vwc[2], vlc[0]);
-                S4(s, 4) = make_float4(vlc[1], vlc[2], w[0], w[1]);
-                S4(s, 5) = make_float4(w[2], sl[0], sl[1], sl[2]);
-                S4(s, 6) = make_float4(f, dg, q, qd);
+                lane_sync();
             }
         }
 
         // ================= pass 2: articulated inertias (leaves -> root)
-        // accumulator m->nacc (present when the lane has several root children) collects what reaches
-        // the root from sub-trees other than slot 0's, whose contribution arrives in registers
-        const int nacc_all = m->nacc + m->root_acc;
-        for (int a = 0; a < nacc_all; a++)
+        // A slot's projected inertia either travels in registers to the next-lower slot of the lane
+        // (chains; finally from slot 0 to the root) or is parked in one of this thread's accumulators,
+        // from where its parent -- possibly in another lane -- collects it (SlotRec::child).
+        if (m->root_acc >= 0) {
 #pragma unroll
-            for (int k = 0; k < ACC_F4; k++) A4(a, k) = make_float4(0.f, 0.f, 0.f, 0.f);
-        float IA[21], pa[3], pl[3];     // travels along chains: child's projected inertia -> parent (finally the root)
+            for (int k = 0; k < ACC_F4; k++) A4(m->root_acc, k) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float IA[21], pa[3], pl[3];
 #pragma unroll
         for (int c = 0; c < 21; c++) IA[c] = 0.f;
 #pragma unroll
@@ -519,76 +551,93 @@ struct Stepper {
             bool carry = false;
 #pragma unroll 1
             for (int s = NS - 1; s >= 0; s--) {
-                const LinkC &lk = link(s);
-                float R[9], x[3], vw[3], vl[3], w[3], sl[3];
-                load_pose(s, R, x, vw, vl);
-                load_axis(s, w, sl);
-                float I[21], qa[3], ql[3];
-                link_inertia(lk, lk.mass, 1.f, R, x, vw, vl, g, I, qa, ql);
-                float dummy[3];
-                link_contacts<true, HF>(m, gr, lk, rs.rp, R, x, vw, vl, I, qa, ql, dummy, dummy, dummy, dummy, 0, 1);
-                if (carry) {
+                const SlotRec &sr = rec(s);
+                if (sr.link >= 0) {
+                    const LinkC &lk = links[sr.link];
+                    float R[9], x[3], vw[3], vl[3], w[3], sl[3];
+                    load_pose(s, R, x, vw, vl);
+                    load_axis(s, w, sl);
+                    float I[21], qa[3], ql[3];
+                    link_inertia(lk, lk.mass, 1.f, R, x, vw, vl, g, I, qa, ql);
+                    float dummy[3];
+                    link_contacts<true, HF>(m, gr, lk, rs.rp, R, x, vw, vl, I, qa, ql, dummy, dummy, dummy, dummy, 0, 1);
+                    if (carry) {
 #pragma unroll
-                    for (int c = 0; c < 21; c++) I[c] += IA[c];
+                        for (int c = 0; c < 21; c++) I[c] += IA[c];
 #pragma unroll
-                    for (int c = 0; c < 3; c++) { qa[c] += pa[c]; ql[c] += pl[c]; }
-                }
-                const int ai = m->slot_acc[s];
-                if (ai >= 0) {
-                    float t[28];
-#pragma unroll
-                    for (int k = 0; k < ACC_F4; k++) { const float4 v = A4(ai, k); t[4 * k] = v.x; t[4 * k + 1] = v.y; t[4 * k + 2] = v.z; t[4 * k + 3] = v.w; }
-#pragma unroll
-                    for (int c = 0; c < 21; c++) I[c] += t[c];
-#pragma unroll
-                    for (int c = 0; c < 3; c++) { qa[c] += t[21 + c]; ql[c] += t[24 + c]; }
-                }
-                const float4 k6 = S4(s, 6);
-                const float tau = k6.x, dg = k6.y;
-                float cw[3], cl[3];
-                bias_accel(vw, vl, w, sl, k6.w, cw, cl);
-                float Ua[3], Ul[3];
-                sym6_mul(I, w, sl, Ua, Ul);
-                const float D = dot3(w, Ua) + dot3(sl, Ul) + dg;
-                const float di = 1.f / D;
-                const float u_ = tau - (dot3(w, qa) + dot3(sl, ql));
-                S4(s, 8) = make_float4(Ua[0], Ua[1], Ua[2], Ul[0]);
-                S4(s, 9) = make_float4(Ul[1], Ul[2], 0.f, 0.f);
-                { float4 v = S4(s, 7); v.y = di; v.z = u_; S4(s, 7) = v; }
-                sym6_rank1(I, -di, Ua, Ul);                           // Ia = IA - U U^T / D
-                float ya[3], yl[3];
-                sym6_mul(I, cw, cl, ya, yl);
-                const float ud = u_ * di;
-#pragma unroll
-                for (int c = 0; c < 3; c++) { qa[c] += ya[c] + Ua[c] * ud; ql[c] += yl[c] + Ul[c] * ud; }
-                const int ps = m->slot_parent[s];
-                carry = (ps == s - 1);                                // includes slot 0 -> root
-                if (carry) {
-#pragma unroll
-                    for (int c = 0; c < 21; c++) IA[c] = I[c];
-#pragma unroll
-                    for (int c = 0; c < 3; c++) { pa[c] = qa[c]; pl[c] = ql[c]; }
-                } else {
-                    const int pi = ps < 0 ? m->nacc : m->slot_acc[ps];
-                    float t[28];
-#pragma unroll
-                    for (int c = 0; c < 21; c++) t[c] = I[c];
-#pragma unroll
-                    for (int c = 0; c < 3; c++) { t[21 + c] = qa[c]; t[24 + c] = ql[c]; }
-                    t[27] = 0.f;
-#pragma unroll
-                    for (int k = 0; k < ACC_F4; k++) {
-                        float4 v = A4(pi, k);
-                        v.x += t[4 * k]; v.y += t[4 * k + 1]; v.z += t[4 * k + 2]; v.w += t[4 * k + 3];
-                        A4(pi, k) = v;
+                        for (int c = 0; c < 3; c++) { qa[c] += pa[c]; ql[c] += pl[c]; }
                     }
+#pragma unroll 1
+                    for (int ci = 0; ci < MAX_CHILD_REFS; ci++) {
+                        const int cr = sr.child[ci];
+                        if (cr < 0) break;
+                        float t[28];
+#pragma unroll
+                        for (int k = 0; k < ACC_F4; k++) { const float4 v = A4x(cr >> 8, cr & 255, k); t[4 * k] = v.x; t[4 * k + 1] = v.y; t[4 * k + 2] = v.z; t[4 * k + 3] = v.w; }
+#pragma unroll
+                        for (int c = 0; c < 21; c++) I[c] += t[c];
+#pragma unroll
+                        for (int c = 0; c < 3; c++) { qa[c] += t[21 + c]; ql[c] += t[24 + c]; }
+                    }
+                    const float4 k6 = S4(s, 6);
+                    const float tau = k6.x, dg = k6.y;
+                    float cw[3], cl[3];
+                    bias_accel(vw, vl, w, sl, k6.w, cw, cl);
+                    float Ua[3], Ul[3];
+                    sym6_mul(I, w, sl, Ua, Ul);
+                    const float D = dot3(w, Ua) + dot3(sl, Ul) + dg;
+                    const float di = 1.f / D;
+                    const float u_ = tau - (dot3(w, qa) + dot3(sl, ql));
+                    S4(s, 8) = make_float4(Ua[0], Ua[1], Ua[2], Ul[0]);
+                    S4(s, 9) = make_float4(Ul[1], Ul[2], 0.f, 0.f);
+                    { float4 v = S4(s, 7); v.y = di; v.z = u_; S4(s, 7) = v; }
+                    sym6_rank1(I, -di, Ua, Ul);                           // Ia = IA - U U^T / D
+                    float ya[3], yl[3];
+                    sym6_mul(I, cw, cl, ya, yl);
+                    const float ud = u_ * di;
+#pragma unroll
+                    for (int c = 0; c < 3; c++) { qa[c] += ya[c] + Ua[c] * ud; ql[c] += yl[c] + Ul[c] * ud; }
+                    carry = (sr.out < 0);
+                    if (carry) {
+#pragma unroll
+                        for (int c = 0; c < 21; c++) IA[c] = I[c];
+#pragma unroll
+                        for (int c = 0; c < 3; c++) { pa[c] = qa[c]; pl[c] = ql[c]; }
+                    } else {
+                        float t[28];
+#pragma unroll
+                        for (int c = 0; c < 21; c++) t[c] = I[c];
+#pragma unroll
+                        for (int c = 0; c < 3; c++) { t[21 + c] = qa[c]; t[24 + c] = ql[c]; }
+                        t[27] = 0.f;
+                        if (sr.out == m->root_acc) {                      // several root children share the root accumulator
+#pragma unroll
+                            for (int k = 0; k < ACC_F4; k++) {
+                                float4 v = A4(sr.out, k);
+                                v.x += t[4 * k]; v.y += t[4 * k + 1]; v.z += t[4 * k + 2]; v.w += t[4 * k + 3];
+                                A4(sr.out, k) = v;
+                            }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < ACC_F4; k++) A4(sr.out, k) = make_float4(t[4 * k], t[4 * k + 1], t[4 * k + 2], t[4 * k + 3]);
+                        }
+                    }
+                } else {
+                    carry = false;
                 }
+                lane_sync();
+            }
+            if (!carry) {
+#pragma unroll
+                for (int c = 0; c < 21; c++) IA[c] = 0.f;
+#pragma unroll
+                for (int c = 0; c < 3; c++) { pa[c] = 0.f; pl[c] = 0.f; }
             }
         }
         // ---- root: own inertia (lane 0), its contact spheres (dealt round-robin to the lanes), butterfly, solve
         float awr[3], alr[3];
         {
-            const LinkC &lk = m->links[0];
+            const LinkC &lk = links[0];
             const bool mine = (lane == 0);
             float I[21], qa[3], ql[3], dummy[3], Rr[9], vwr[3], vlr[3];
             const float xr[3] = {0.f, 0.f, 0.f};
@@ -599,10 +648,10 @@ struct Stepper {
             for (int c = 0; c < 21; c++) IA[c] += I[c];               // IA holds slot 0's contribution (or zeros)
 #pragma unroll
             for (int c = 0; c < 3; c++) { pa[c] += qa[c]; pl[c] += ql[c]; }
-            if (nacc_all > m->nacc) {
+            if (m->root_acc >= 0) {
                 float t[28];
 #pragma unroll
-                for (int k = 0; k < ACC_F4; k++) { const float4 v = A4(m->nacc, k); t[4 * k] = v.x; t[4 * k + 1] = v.y; t[4 * k + 2] = v.z; t[4 * k + 3] = v.w; }
+                for (int k = 0; k < ACC_F4; k++) { const float4 v = A4(m->root_acc, k); t[4 * k] = v.x; t[4 * k + 1] = v.y; t[4 * k + 2] = v.z; t[4 * k + 3] = v.w; }
 #pragma unroll
                 for (int c = 0; c < 21; c++) IA[c] += t[c];
 #pragma unroll
@@ -633,50 +682,56 @@ struct Stepper {
             float awc[3] = {awr[0], awr[1], awr[2]}, alc[3] = {alr[0], alr[1], alr[2]};
 #pragma unroll 1
             for (int s = 0; s < NS; s++) {
-                const int ps = m->slot_parent[s];
-                float ap_w[3], ap_l[3];
-                if (ps == s - 1) {
+                const SlotRec &sr = rec(s);
+                if (sr.link >= 0) {
+                    const int pl_ = sr.parent >> 8, ps = (sr.parent & 255) - 1;
+                    float ap_w[3], ap_l[3];
+                    if (ps == s - 1 && (ps < 0 || pl_ == lane)) {
 #pragma unroll
-                    for (int c = 0; c < 3; c++) { ap_w[c] = awc[c]; ap_l[c] = alc[c]; }
-                } else if (ps < 0) {
+                        for (int c = 0; c < 3; c++) { ap_w[c] = awc[c]; ap_l[c] = alc[c]; }
+                    } else if (ps < 0) {
 #pragma unroll
-                    for (int c = 0; c < 3; c++) { ap_w[c] = awr[c]; ap_l[c] = alr[c]; }
-                } else {
-                    const float4 a = S4(ps, 0), b = S4(ps, 1);     // parent's acceleration overlays its R
-                    ap_w[0] = a.x; ap_w[1] = a.y; ap_w[2] = a.z; ap_l[0] = a.w; ap_l[1] = b.x; ap_l[2] = b.y;
-                }
-                float w[3], sl[3], R[9], x[3], vw[3], vl[3];
-                load_axis(s, w, sl);
-                load_pose(s, R, x, vw, vl);
-                const float4 k6 = S4(s, 6), k7 = S4(s, 7), k8 = S4(s, 8), k9 = S4(s, 9);
-                float cw[3], cl[3];
-                bias_accel(vw, vl, w, sl, k6.w, cw, cl);
-                const float a_w[3] = {ap_w[0] + cw[0], ap_w[1] + cw[1], ap_w[2] + cw[2]};
-                const float a_l[3] = {ap_l[0] + cl[0], ap_l[1] + cl[1], ap_l[2] + cl[2]};
-                const float Ua_ = k8.x * a_w[0] + k8.y * a_w[1] + k8.z * a_w[2] + k8.w * a_l[0] + k9.x * a_l[1] + k9.y * a_l[2];
-                const float qdd = (k7.z - Ua_) * k7.y;
+                        for (int c = 0; c < 3; c++) { ap_w[c] = awr[c]; ap_l[c] = alr[c]; }
+                    } else {
+                        const float4 a = S4x(pl_, ps, 8), b = S4x(pl_, ps, 9);   // parent's parked acceleration (overlays its U)
+                        ap_w[0] = a.x; ap_w[1] = a.y; ap_w[2] = a.z; ap_l[0] = a.w; ap_l[1] = b.x; ap_l[2] = b.y;
+                    }
+                    float w[3], sl[3], vw[3], vl[3];
+                    load_axis(s, w, sl);
+                    load_twist(s, vw, vl);
+                    const float4 k6 = S4(s, 6), k7 = S4(s, 7), k8 = S4(s, 8), k9 = S4(s, 9);
+                    float cw[3], cl[3];
+                    bias_accel(vw, vl, w, sl, k6.w, cw, cl);
+                    const float a_w[3] = {ap_w[0] + cw[0], ap_w[1] + cw[1], ap_w[2] + cw[2]};
+                    const float a_l[3] = {ap_l[0] + cl[0], ap_l[1] + cl[1], ap_l[2] + cl[2]};
+                    const float Ua_ = k8.x * a_w[0] + k8.y * a_w[1] + k8.z * a_w[2] + k8.w * a_l[0] + k9.x * a_l[1] + k9.y * a_l[2];
+                    const float qdd = (k7.z - Ua_) * k7.y;
 #pragma unroll
-                for (int c = 0; c < 3; c++) { awc[c] = a_w[c] + w[c] * qdd; alc[c] = a_l[c] + sl[c] * qdd; }
-                const float qd = k6.w + h * qdd;
-                const float q = k6.z + h * qd;
-                S4(s, 6) = make_float4(k6.x, k6.y, q, qd);
-                if (LAST) {
-                    const LinkC &lk = link(s);
-                    const int li = m->slot_link[s][lane];
-                    if (o.dof_force && o.write) o.dof_force[li - 1] = k6.x - (k6.y - lk.armature) * qdd;
-                    if (lk.cp_end > lk.cp_begin && (lk.sensor >= 0 || o.net_contact)) {
-                        float F[3] = {0.f, 0.f, 0.f}, T[3] = {0.f, 0.f, 0.f}, dI[1], d3[3];
-                        link_contacts<false, HF>(m, gr, lk, rs.rp, R, x, vw, vl, dI, d3, d3, awc, alc, F, T, 0, 1);
-                        emit_wrench(li, lk, R, F, T, o);
-                    } else if (lk.sensor >= 0 || (o.net_contact && m->link_body[li] >= 0)) {
-                        const float z[3] = {0.f, 0.f, 0.f};
-                        emit_wrench(li, lk, R, z, z, o);
+                    for (int c = 0; c < 3; c++) { awc[c] = a_w[c] + w[c] * qdd; alc[c] = a_l[c] + sl[c] * qdd; }
+                    const float qd = k6.w + h * qdd;
+                    const float q = k6.z + h * qd;
+                    S4(s, 6) = make_float4(k6.x, k6.y, q, qd);
+                    if (LAST) {
+                        const LinkC &lk = links[sr.link];
+                        const int li = sr.link;
+                        if (o.dof_force && o.write) o.dof_force[li - 1] = k6.x - (k6.y - lk.armature) * qdd;
+                        if (lk.cp_end > lk.cp_begin && (lk.sensor >= 0 || o.net_contact)) {
+                            float R[9], x[3], F[3] = {0.f, 0.f, 0.f}, T[3] = {0.f, 0.f, 0.f}, dI[1], d3[3];
+                            load_pose(s, R, x, vw, vl);
+                            link_contacts<false, HF>(m, gr, lk, rs.rp, R, x, vw, vl, dI, d3, d3, awc, alc, F, T, 0, 1);
+                            emit_wrench(li, lk, R, F, T, o);
+                        } else if (lk.sensor >= 0 || (o.net_contact && m->link_body[li] >= 0)) {
+                            float R[9], x[3]; const float z[3] = {0.f, 0.f, 0.f};
+                            load_pose(s, R, x, vw, vl);
+                            emit_wrench(li, lk, R, z, z, o);
+                        }
+                    }
+                    if (sr.flags & 1) {                                // a child is not the next slot of this lane: park a over U
+                        S4(s, 8) = make_float4(awc[0], awc[1], awc[2], alc[0]);
+                        S4(s, 9) = make_float4(alc[1], alc[2], 0.f, 0.f);
                     }
                 }
-                if (m->slot_acc[s] >= 0) {                           // some child is not the next slot: park a
-                    S4(s, 0) = make_float4(awc[0], awc[1], awc[2], alc[0]);
-                    float4 v = S4(s, 1); v.x = alc[1]; v.y = alc[2]; S4(s, 1) = v;
-                }
+                lane_sync();
             }
         }
 
