@@ -54,7 +54,7 @@ typedef struct {
     const float *axis, *lpos, *lquat;          /* nl x 3, 3, 4(xyzw) */
     const float *mass, *com, *inertia;         /* nl x 1, 3, 6 (xx yy zz xy xz yz about the COM) */
     const float *armature, *damping, *stiffness, *lower, *upper, *effort, *kp, *kd, *limit_k, *limit_d; /* nl */
-    const float *cp_pos, *cp_radius, *cp_mu;   /* ncp x 3, 1, 1 (mu already combined with the ground's) */
+    const float *cp_pos, *cp_radius, *cp_mu;   /* ncp x 3, 1, 1 (mu = the shape's own friction) */
     const float *body_pos, *body_quat;         /* nb x 3, 4: body frame in its link frame */
     float contact_kn, contact_cn, contact_vs;
 } b2g_model;
@@ -70,6 +70,9 @@ typedef struct {
     const int16_t *hf_samples;
     int32_t hf_nx, hf_ny;
     float hf_horizontal_scale, hf_vertical_scale, hf_origin_x, hf_origin_y;
+    float ground_friction;   /* PlaneParams / TriangleMeshParams dynamic_friction (ant.py:128-133); combined with a shape's
+                                friction by PhysX's default mode, the average */
+    float pad_;
 } b2g_sim_params;
 
 /* Tensor slots for b2g_bind().  Shapes in elements; N = num_envs, D = dofs, B = bodies, S = sensors. */
@@ -96,11 +99,26 @@ enum {
     B2G_T_INITIAL_ROOT = 18,   /* f32 (N,13) initial_root_states, ant.py:89-90 */
     B2G_T_RESET_COUNT = 19,    /* i32 (N)  per-env reset counter feeding the Philox stream */
     B2G_T_OBS_CLIPPED = 20,    /* f32 (N,O) clamp(obs, +-clip_obs), vec_task.py:402 (may alias OBS) */
-    B2G_T_COUNT = 21
+    /* AnymalTerrain state (anymal_terrain.py:126-150) */
+    B2G_T_COMMANDS = 21,       /* f32 (N,4)  x vel, y vel, yaw vel, heading */
+    B2G_T_LAST_ACTIONS = 22,   /* f32 (N,A) */
+    B2G_T_LAST_DOF_VEL = 23,   /* f32 (N,D) */
+    B2G_T_FEET_AIR_TIME = 24,  /* f32 (N,4) */
+    B2G_T_TORQUES = 25,        /* f32 (N,A) */
+    B2G_T_EPISODE_SUMS = 26,   /* f32 (13,N) rows in the order of anymal_terrain.py:144-146 */
+    B2G_T_TERRAIN_LEVELS = 27, /* i64 (N) */
+    B2G_T_TERRAIN_TYPES = 28,  /* i64 (N) */
+    B2G_T_ENV_ORIGINS = 29,    /* f32 (N,3) */
+    B2G_T_TERRAIN_ORIGINS = 30,/* f32 (rows,cols,3) */
+    B2G_T_NOISE_SCALE = 31,    /* f32 (O)   noise_scale_vec, anymal_terrain.py:174-186 */
+    B2G_T_BASE_SCRATCH = 32,   /* f32 (N,12) base_lin_vel, base_ang_vel, projected_gravity handed from kernel 1 to 2 */
+    B2G_T_REDUCE_SCRATCH = 33, /* f32 (>= 1024 + 16) per-block partials of the reset-set norm (anymal_terrain.py:432) + extras sums */
+    B2G_T_ENV_FRICTION = 34,   /* f32 (N)   per-env shape friction (friction buckets, anymal_terrain.py:235-281); NULL = the model's */
+    B2G_T_COUNT = 35
 };
 
 /* fused per-task control steps */
-enum { B2G_TASK_NONE = 0, B2G_TASK_CARTPOLE = 1, B2G_TASK_ANT = 2, B2G_TASK_HUMANOID = 3 };
+enum { B2G_TASK_NONE = 0, B2G_TASK_CARTPOLE = 1, B2G_TASK_ANT = 2, B2G_TASK_HUMANOID = 3, B2G_TASK_ANYMAL_TERRAIN = 4 };
 
 /* Scalars of the locomotion tasks (cfg/task/Ant.yaml:13-29, Humanoid.yaml; ant.py:47-68). */
 typedef struct {
@@ -129,6 +147,28 @@ typedef struct {
     int32_t pad_;
 } b2g_task_params;
 
+/* Scalars of AnymalTerrain (cfg/task/AnymalTerrain.yaml, anymal_terrain.py:43-108). */
+typedef struct {
+    int32_t num_obs, num_actions;           /* 188, 12 */
+    int32_t decimation, control_freq_inv;   /* gym.simulate calls: decimation inside pre_physics_step (:441-451) + control_freq_inv after it */
+    float clip_actions, clip_obs;
+    int32_t max_episode_length, push_interval;
+    int32_t push_robots, add_noise, curriculum, allow_knee_contacts, custom_origins, pad0;
+    float kp, kd, action_scale, torque_limit;
+    float default_dof_pos[B2G_MAX_LINKS];
+    float lin_vel_scale, ang_vel_scale, dof_pos_scale, dof_vel_scale, height_meas_scale;
+    float rew_scales[14];   /* termination, lin_vel_xy, lin_vel_z, ang_vel_z, ang_vel_xy, orient, torque, joint_acc, base_height,
+                               air_time, collision, stumble, action_rate, hip -- already multiplied by dt (:104-105) */
+    float dt, max_episode_length_s;
+    float command_x[2], command_y[2], command_yaw[2];
+    float base_init_state[13];
+    float border_size, terrain_hscale, terrain_vscale, env_length;
+    int32_t hs_rows, hs_cols, env_rows, env_cols;
+    int32_t base_body, knee_bodies[4], feet_bodies[4], pad1;
+    uint64_t seed;
+    int32_t env_id_offset, pad2;
+} b2g_anymal_params;
+
 typedef struct b2g_sim b2g_sim;
 
 /* gymapi.acquire_gym() + gym.create_sim() + create_env/create_actor x N + gym.prepare_sim()
@@ -153,6 +193,9 @@ int b2g_refresh_rigid_body_state(b2g_sim *sim, void *stream);
  * timeout flags and the clipped observation copy -- one kernel launch.
  * `actions` is a DEVICE pointer (N, num_actions). */
 int b2g_set_task(b2g_sim *sim, const b2g_task_params *task);
+/* AnymalTerrain (tasks/anymal_terrain.py:441-485): b2g_task_step then launches two kernels, physics +
+ * termination + reward, and reset (terrain curriculum) + observations. */
+int b2g_set_anymal_task(b2g_sim *sim, const b2g_anymal_params *task);
 int b2g_task_step(b2g_sim *sim, const float *actions, void *stream);
 
 /* Same step with HOST buffers (pinned or pageable): copies actions in, runs the step, copies

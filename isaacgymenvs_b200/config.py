@@ -73,6 +73,37 @@ def _builtin_task(name, root):
                         "asset": {"assetFileName": "mjcf/nv_humanoid.xml"}, "enableCameraSensors": False},
                 "sim": _sim(root, _physx(root)),
                 "task": {"randomize": False, "randomization_params": {}}}
+    if name == "AnymalTerrain":
+        sim = _sim(root, _physx(root, num_velocity_iterations=1, max_depenetration_velocity=100.0, contact_collection=1))
+        sim.update({"dt": 0.005, "substeps": 1})
+        return {"name": "AnymalTerrain", "physics_engine": "physx",
+                "env": {"numEnvs": _num_envs(root, 4096), "numObservations": 188, "numActions": 12, "envSpacing": 3.,
+                        "enableDebugVis": False,
+                        "terrain": {"terrainType": "trimesh", "staticFriction": 1.0, "dynamicFriction": 1.0, "restitution": 0.,
+                                    "curriculum": True, "maxInitMapLevel": 0, "mapLength": 8., "mapWidth": 8., "numLevels": 10,
+                                    "numTerrains": 20, "terrainProportions": [0.1, 0.1, 0.35, 0.25, 0.2], "slopeTreshold": 0.5},
+                        "baseInitState": {"pos": [0.0, 0.0, 0.62], "rot": [0.0, 0.0, 0.0, 1.0], "vLinear": [0.0, 0.0, 0.0],
+                                          "vAngular": [0.0, 0.0, 0.0]},
+                        "randomCommandVelocityRanges": {"linear_x": [-1., 1.], "linear_y": [-1., 1.], "yaw": [-3.14, 3.14]},
+                        "control": {"stiffness": 80.0, "damping": 2.0, "actionScale": 0.5, "decimation": 4},
+                        "defaultJointAngles": {"LF_HAA": 0.03, "LH_HAA": 0.03, "RF_HAA": -0.03, "RH_HAA": -0.03,
+                                               "LF_HFE": 0.4, "LH_HFE": -0.4, "RF_HFE": 0.4, "RH_HFE": -0.4,
+                                               "LF_KFE": -0.8, "LH_KFE": 0.8, "RF_KFE": -0.8, "RH_KFE": 0.8},
+                        "urdfAsset": {"file": "urdf/anymal_c/urdf/anymal_minimal.urdf", "footName": "SHANK", "kneeName": "THIGH",
+                                      "collapseFixedJoints": True, "fixBaseLink": False, "defaultDofDriveMode": 4},
+                        "learn": {"allowKneeContacts": True, "terminalReward": 0.0, "linearVelocityXYRewardScale": 1.0,
+                                  "linearVelocityZRewardScale": -4.0, "angularVelocityXYRewardScale": -0.05,
+                                  "angularVelocityZRewardScale": 0.5, "orientationRewardScale": -0., "torqueRewardScale": -0.00002,
+                                  "jointAccRewardScale": -0.0005, "baseHeightRewardScale": -0.0, "feetAirTimeRewardScale": 1.0,
+                                  "kneeCollisionRewardScale": -0.25, "feetStumbleRewardScale": -0., "actionRateRewardScale": -0.01,
+                                  "hipRewardScale": -0., "linearVelocityScale": 2.0, "angularVelocityScale": 0.25,
+                                  "dofPositionScale": 1.0, "dofVelocityScale": 0.05, "heightMeasurementScale": 5.0,
+                                  "addNoise": True, "noiseLevel": 1.0, "dofPositionNoise": 0.01, "dofVelocityNoise": 1.5,
+                                  "linearVelocityNoise": 0.1, "angularVelocityNoise": 0.2, "gravityNoise": 0.05,
+                                  "heightMeasurementNoise": 0.06, "randomizeFriction": True, "frictionRange": [0.5, 1.25],
+                                  "pushRobots": True, "pushInterval_s": 15, "episodeLength_s": 20},
+                        "viewer": {"refEnv": 0, "pos": [0, 0, 10], "lookat": [1., 1, 9]}, "enableCameraSensors": False},
+                "sim": sim, "task": {"randomize": False}}
     raise KeyError(f"no built-in config for task {name!r}; pass cfg_dir= pointing at a reference-format cfg tree")
 
 

@@ -79,7 +79,7 @@ extern __shared__ float4 b2g_dyn_smem[];
 template <int L, bool HF, int BLOCK>
 __device__ __forceinline__ Stepper<L, HF, BLOCK> make_stepper(const DevModel *sm, const int16_t *hf, int lane) {
     Stepper<L, HF, BLOCK> st;
-    st.m = sm; st.gr = Ground{sm, hf, sm->cps};
+    st.m = sm; st.gr = Ground{sm, hf, sm->cps, -1.f};
     st.slots = &sm->slots[0][0]; st.links = sm->links;
     st.ss = b2g_dyn_smem + threadIdx.x;
     st.acc = b2g_dyn_smem + sm->ns * SLOT_F4 * BLOCK + threadIdx.x;
@@ -476,6 +476,8 @@ __global__ void __launch_bounds__(BLOCK) cartpole_step_kernel(const DevModel *__
     if (to) to[e] = (uint8_t)(((float)progress >= P.max_episode_length - 1.f) && reset != 0);
 }
 
+#include "b2g_anymal.cuh"
+
 // -------------------------------------------------------------------------------------------
 // gym.refresh_rigid_body_state_tensor(): forward kinematics, one thread per env, any topology
 __global__ void __launch_bounds__(128) body_state_kernel(const DevModel *__restrict__ gm, Buffers B, int N) {
@@ -547,7 +549,9 @@ struct b2g_sim {
     Buffers buf;
     size_t buf_bytes[B2G_T_COUNT];
     b2g_task_params task;
-    bool has_task = false;
+    b2g_anymal_params anymal;
+    bool has_task = false, has_anymal = false;
+    unsigned step_counter = 0;   // common_step_counter, anymal_terrain.py:459
     float *d_actions_stage = nullptr;    // device staging for b2g_task_step_host
     int64_t launches = 0;
 };
@@ -659,6 +663,7 @@ extern "C" int b2g_create(const b2g_model *m, const b2g_sim_params *sp, int32_t 
     h.h = sp->dt / (float)sp->substeps;
     for (int c = 0; c < 3; c++) h.g[c] = m->gravity_on ? sp->gravity[c] : 0.f;
     h.kn = m->contact_kn; h.cn = m->contact_cn; h.vs2 = m->contact_vs * m->contact_vs;
+    h.ground_mu = sp->ground_friction;
     // topology
     const char *force1 = getenv("B2G_SINGLE_LANE");
     if (schedule(m, pick_lanes(m, force1 && force1[0] == '1'), h) != 0) { delete s; return fail(B2G_E_INVALID, "b2g_create: the articulation does not fit the slot program limits"); }
@@ -712,7 +717,7 @@ extern "C" int b2g_create(const b2g_model *m, const b2g_sim_params *sp, int32_t 
         int src = order[k];
         CpC &c = h.cps[k];
         for (int j = 0; j < 3; j++) c.pos[j] = m->cp_pos[3 * src + j];
-        c.radius = m->cp_radius[src]; c.mu = m->cp_mu[src]; c.body = m->cp_body[src]; c.pad = 0;
+        c.radius = m->cp_radius[src]; c.mu = 0.5f * (m->cp_mu[src] + sp->ground_friction); c.body = m->cp_body[src]; c.pad = 0;
         LinkC &l = h.links[m->cp_link[src]];
         if (l.cp_end == 0 && l.cp_begin == 0) l.cp_begin = k;
         l.cp_end = k + 1;
@@ -830,12 +835,51 @@ extern "C" int b2g_set_task(b2g_sim *s, const b2g_task_params *t) {
         if (t->num_actions != nd || t->num_obs != 12 + 4 * nd + 6 * s->hm.nsens) return fail(B2G_E_UNSUPPORTED, "humanoid task: observation size does not match the articulation");
     } else return fail(B2G_E_UNSUPPORTED, "b2g_set_task: unknown task id");
     if (t->control_freq_inv < 0) return fail(B2G_E_INVALID, "control_freq_inv < 0");
-    s->task = *t; s->has_task = true;
+    s->task = *t; s->has_task = true; s->has_anymal = false;
+    return B2G_OK;
+}
+
+extern "C" int b2g_set_anymal_task(b2g_sim *s, const b2g_anymal_params *t) {
+    if (!s || !t) return fail(B2G_E_INVALID, "b2g_set_anymal_task: null argument");
+    const int nd = s->hm.nl - 1;
+    if (s->lanes != 4 || s->hm.ns != 3 || nd != 12 || t->num_actions != 12 || t->num_obs != 12 + 3 * nd + 140)
+        return fail(B2G_E_UNSUPPORTED, "AnymalTerrain needs the 4-leg x 3-DOF articulation, 12 actions, 188 observations");
+    if (t->decimation < 0 || t->control_freq_inv < 0) return fail(B2G_E_INVALID, "negative simulate count");
+    s->anymal = *t; s->has_anymal = true; s->has_task = false; s->step_counter = 0;
+    return B2G_OK;
+}
+
+static int anymal_step(b2g_sim *s, const float *actions, void *stream) {
+    const b2g_anymal_params &P = s->anymal;
+    int rc = require(s, {B2G_T_ROOT_STATE, B2G_T_DOF_STATE, B2G_T_OBS, B2G_T_REW, B2G_T_RESET, B2G_T_PROGRESS, B2G_T_RESET_COUNT,
+                         B2G_T_ACTIONS, B2G_T_NET_CONTACT, B2G_T_COMMANDS, B2G_T_LAST_ACTIONS, B2G_T_LAST_DOF_VEL, B2G_T_FEET_AIR_TIME,
+                         B2G_T_TORQUES, B2G_T_EPISODE_SUMS, B2G_T_BASE_SCRATCH, B2G_T_REDUCE_SCRATCH, B2G_T_NOISE_SCALE},
+                     "b2g_task_step(AnymalTerrain)");
+    if (rc) return rc;
+    if (P.custom_origins) { rc = require(s, {B2G_T_ENV_ORIGINS, B2G_T_TERRAIN_LEVELS, B2G_T_TERRAIN_TYPES, B2G_T_TERRAIN_ORIGINS}, "b2g_task_step(AnymalTerrain)"); if (rc) return rc; }
+    CUDA_TRY(cudaSetDevice(s->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int N = s->num_envs, blk = 128, grid = (N * 4 + blk - 1) / blk;
+    if (s->block != 128) return fail(B2G_E_UNSUPPORTED, "AnymalTerrain: unexpected CTA size");
+    if (grid > REDUCE_PARTIALS) return fail(B2G_E_INVALID, "AnymalTerrain: too many blocks for the reduction scratch (num_envs <= 32768)");
+    if (s->buf_bytes[B2G_T_REDUCE_SCRATCH] < (REDUCE_PARTIALS + 16) * 4) return fail(B2G_E_INVALID, "REDUCE_SCRATCH too small");
+    s->step_counter++;                                   // common_step_counter += 1 (:459) before the push test
+    if (s->d_hf) {
+        rc = set_smem(anymal_physics_kernel<4, true, 128>, s->dyn_smem); if (rc) return rc;
+        anymal_physics_kernel<4, true, 128><<<grid, blk, s->dyn_smem, st>>>(s->dm, s->d_hf, s->buf, P, actions, N, s->step_counter);
+    } else {
+        rc = set_smem(anymal_physics_kernel<4, false, 128>, s->dyn_smem); if (rc) return rc;
+        anymal_physics_kernel<4, false, 128><<<grid, blk, s->dyn_smem, st>>>(s->dm, s->d_hf, s->buf, P, actions, N, s->step_counter);
+    }
+    anymal_reset_obs_kernel<4, 128><<<grid, blk, 0, st>>>(s->buf, P, s->d_hf, N, s->hm.nl - 1, grid, s->step_counter);
+    s->launches += 2;
+    CUDA_TRY(cudaGetLastError());
     return B2G_OK;
 }
 
 extern "C" int b2g_task_step(b2g_sim *s, const float *actions, void *stream) {
     if (!s || !actions) return fail(B2G_E_INVALID, "b2g_task_step: null argument");
+    if (s->has_anymal) return anymal_step(s, actions, stream);
     if (!s->has_task) return fail(B2G_E_INVALID, "b2g_task_step: call b2g_set_task first");
     int rc = require(s, {B2G_T_ROOT_STATE, B2G_T_DOF_STATE, B2G_T_OBS, B2G_T_REW, B2G_T_RESET, B2G_T_PROGRESS, B2G_T_RESET_COUNT}, "b2g_task_step");
     if (rc) return rc;
@@ -893,15 +937,17 @@ extern "C" int b2g_task_step(b2g_sim *s, const float *actions, void *stream) {
 extern "C" int b2g_task_step_host(b2g_sim *s, const float *h_actions, float *h_obs, float *h_rew, int64_t *h_reset,
                                   uint8_t *h_timeout, void *stream) {
     if (!s || !h_actions) return fail(B2G_E_INVALID, "b2g_task_step_host: null argument");
-    if (!s->has_task) return fail(B2G_E_INVALID, "b2g_task_step_host: call b2g_set_task first");
+    if (!s->has_task && !s->has_anymal) return fail(B2G_E_INVALID, "b2g_task_step_host: call b2g_set_task first");
     CUDA_TRY(cudaSetDevice(s->device));
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t N = s->num_envs, abytes = N * s->task.num_actions * 4;
+    const int n_act = s->has_anymal ? s->anymal.num_actions : s->task.num_actions;
+    const int n_obs = s->has_anymal ? s->anymal.num_obs : s->task.num_obs;
+    const size_t N = s->num_envs, abytes = N * n_act * 4;
     if (!s->d_actions_stage) CUDA_TRY(cudaMalloc(&s->d_actions_stage, abytes));
     CUDA_TRY(cudaMemcpyAsync(s->d_actions_stage, h_actions, abytes, cudaMemcpyHostToDevice, st));
     int rc = b2g_task_step(s, s->d_actions_stage, stream); if (rc) return rc;
     const void *obs_src = s->buf.p[B2G_T_OBS_CLIPPED] ? s->buf.p[B2G_T_OBS_CLIPPED] : s->buf.p[B2G_T_OBS];
-    if (h_obs) CUDA_TRY(cudaMemcpyAsync(h_obs, obs_src, N * s->task.num_obs * 4, cudaMemcpyDeviceToHost, st));
+    if (h_obs) CUDA_TRY(cudaMemcpyAsync(h_obs, obs_src, N * n_obs * 4, cudaMemcpyDeviceToHost, st));
     if (h_rew) CUDA_TRY(cudaMemcpyAsync(h_rew, s->buf.p[B2G_T_REW], N * 4, cudaMemcpyDeviceToHost, st));
     if (h_reset) CUDA_TRY(cudaMemcpyAsync(h_reset, s->buf.p[B2G_T_RESET], N * 8, cudaMemcpyDeviceToHost, st));
     if (h_timeout && s->buf.p[B2G_T_TIMEOUT]) CUDA_TRY(cudaMemcpyAsync(h_timeout, s->buf.p[B2G_T_TIMEOUT], N, cudaMemcpyDeviceToHost, st));

@@ -92,7 +92,7 @@ struct alignas(16) DevModel {
     int ns, lanes, nacc;  // sweep steps per lane, lanes per env, accumulators per thread
     int root_acc;         // accumulator index collecting this lane's root children other than slot 0's (-1: none)
     int cross_lane;       // some slot's parent lives in another lane (needs the shared-memory handoff + __syncwarp)
-    int pad0;
+    float ground_mu;      // friction of the ground material (combined per contact as the average, PhysX default)
     int sensor_body[MAX_SENS];
     float sensor_bpos[MAX_SENS][3];        // body-frame origin of the sensor's body in its link frame
     int link_body[MAX_LINKS];              // first body riding on the link (-1: massless virtual link)
@@ -256,6 +256,7 @@ struct Ground {
     const DevModel *m;
     const int16_t *hf;
     const CpC *cps;       // contact spheres (shared memory; packed right behind the used links)
+    float env_mu;         // >= 0: this env's combined friction (per-env friction buckets), else use the sphere's
     // height and unit normal at world (x, y)
     __device__ __forceinline__ void sample(float x, float y, float &h, float n[3]) const {
         if (!m->has_hf) { h = 0.f; n[0] = 0.f; n[1] = 0.f; n[2] = 1.f; return; }
@@ -263,9 +264,9 @@ struct Ground {
         int ix = (int)floorf(fx), iy = (int)floorf(fy);
         ix = max(0, min(ix, m->hf_nx - 2)); iy = max(0, min(iy, m->hf_ny - 2));
         float tx = fminf(fmaxf(fx - ix, 0.f), 1.f), ty = fminf(fmaxf(fy - iy, 0.f), 1.f);
-        const int16_t *p = hf + (size_t)ix * m->hf_ny + iy;
-        float h00 = p[0] * m->hf_vscale, h01 = p[1] * m->hf_vscale;
-        float h10 = p[m->hf_ny] * m->hf_vscale, h11 = p[m->hf_ny + 1] * m->hf_vscale;
+        const int16_t *p = hf + (size_t)ix * m->hf_ny + iy;         // height samples: global memory, read-only path
+        float h00 = __ldg(p) * m->hf_vscale, h01 = __ldg(p + 1) * m->hf_vscale;
+        float h10 = __ldg(p + m->hf_ny) * m->hf_vscale, h11 = __ldg(p + m->hf_ny + 1) * m->hf_vscale;
         float dhx, dhy;
         if (tx + ty <= 1.f) { dhx = h10 - h00; dhy = h01 - h00; h = h00 + tx * dhx + ty * dhy; }
         else { dhx = h11 - h01; dhy = h11 - h10; h = h11 - (1.f - tx) * dhx - (1.f - ty) * dhy; }
@@ -317,7 +318,7 @@ __device__ __forceinline__ void link_contacts(const DevModel *m, const Ground &g
         float ut[3];
         if (HF) { ut[0] = u[0] - un * n[0]; ut[1] = u[1] - un * n[1]; ut[2] = u[2] - un * n[2]; }
         else { ut[0] = u[0]; ut[1] = u[1]; ut[2] = 0.f; }
-        const float gam = cp.mu * Fn * rsqrtf(dot3(ut, ut) + m->vs2);
+        const float gam = (gr.env_mu >= 0.f ? gr.env_mu : cp.mu) * Fn * rsqrtf(dot3(ut, ut) + m->vs2);
         float F0[3];
         if (HF) { F0[0] = Fn * n[0] - gam * ut[0]; F0[1] = Fn * n[1] - gam * ut[1]; F0[2] = Fn * n[2] - gam * ut[2]; }
         else { F0[0] = -gam * ut[0]; F0[1] = -gam * ut[1]; F0[2] = Fn; }

@@ -19,8 +19,27 @@ MAXL = 32
 # tensor slots (mirror of the enum in include/b200gym.h)
 (T_ROOT_STATE, T_DOF_STATE, T_DOF_ACTUATION, T_DOF_TARGET, T_RIGID_BODY_STATE, T_FORCE_SENSOR, T_DOF_FORCE,
  T_NET_CONTACT, T_ACTIONS, T_OBS, T_REW, T_RESET, T_PROGRESS, T_TIMEOUT, T_POTENTIALS, T_PREV_POTENTIALS,
- T_UP_VEC, T_HEADING_VEC, T_INITIAL_ROOT, T_RESET_COUNT, T_OBS_CLIPPED) = range(21)
-TASK_NONE, TASK_CARTPOLE, TASK_ANT, TASK_HUMANOID = 0, 1, 2, 3
+ T_UP_VEC, T_HEADING_VEC, T_INITIAL_ROOT, T_RESET_COUNT, T_OBS_CLIPPED, T_COMMANDS, T_LAST_ACTIONS, T_LAST_DOF_VEL,
+ T_FEET_AIR_TIME, T_TORQUES, T_EPISODE_SUMS, T_TERRAIN_LEVELS, T_TERRAIN_TYPES, T_ENV_ORIGINS, T_TERRAIN_ORIGINS,
+ T_NOISE_SCALE, T_BASE_SCRATCH, T_REDUCE_SCRATCH, T_ENV_FRICTION) = range(35)
+TASK_NONE, TASK_CARTPOLE, TASK_ANT, TASK_HUMANOID, TASK_ANYMAL_TERRAIN = 0, 1, 2, 3, 4
+
+
+class CAnymalParams(C.Structure):
+    _fields_ = [("num_obs", C.c_int32), ("num_actions", C.c_int32), ("decimation", C.c_int32), ("control_freq_inv", C.c_int32),
+                ("clip_actions", C.c_float), ("clip_obs", C.c_float), ("max_episode_length", C.c_int32),
+                ("push_interval", C.c_int32), ("push_robots", C.c_int32), ("add_noise", C.c_int32), ("curriculum", C.c_int32),
+                ("allow_knee_contacts", C.c_int32), ("custom_origins", C.c_int32), ("pad0", C.c_int32),
+                ("kp", C.c_float), ("kd", C.c_float), ("action_scale", C.c_float), ("torque_limit", C.c_float),
+                ("default_dof_pos", C.c_float * 32), ("lin_vel_scale", C.c_float), ("ang_vel_scale", C.c_float),
+                ("dof_pos_scale", C.c_float), ("dof_vel_scale", C.c_float), ("height_meas_scale", C.c_float),
+                ("rew_scales", C.c_float * 14), ("dt", C.c_float), ("max_episode_length_s", C.c_float),
+                ("command_x", C.c_float * 2), ("command_y", C.c_float * 2), ("command_yaw", C.c_float * 2),
+                ("base_init_state", C.c_float * 13), ("border_size", C.c_float), ("terrain_hscale", C.c_float),
+                ("terrain_vscale", C.c_float), ("env_length", C.c_float), ("hs_rows", C.c_int32), ("hs_cols", C.c_int32),
+                ("env_rows", C.c_int32), ("env_cols", C.c_int32), ("base_body", C.c_int32), ("knee_bodies", C.c_int32 * 4),
+                ("feet_bodies", C.c_int32 * 4), ("pad1", C.c_int32), ("seed", C.c_uint64), ("env_id_offset", C.c_int32),
+                ("pad2", C.c_int32)]
 
 
 class CModel(C.Structure):
@@ -35,7 +54,8 @@ class CModel(C.Structure):
 class CSimParams(C.Structure):
     _fields_ = [("dt", C.c_float), ("substeps", C.c_int32), ("gravity", C.c_float * 3), ("hf_samples", C.c_void_p),
                 ("hf_nx", C.c_int32), ("hf_ny", C.c_int32), ("hf_horizontal_scale", C.c_float),
-                ("hf_vertical_scale", C.c_float), ("hf_origin_x", C.c_float), ("hf_origin_y", C.c_float)]
+                ("hf_vertical_scale", C.c_float), ("hf_origin_x", C.c_float), ("hf_origin_y", C.c_float),
+                ("ground_friction", C.c_float), ("pad_", C.c_float)]
 
 
 class CTaskParams(C.Structure):
@@ -70,13 +90,13 @@ def lib():
         _lib.b2g_launch_count.restype = C.c_int64
         _lib.b2g_launch_count.argtypes = [C.c_void_p]
         for fn in ("b2g_create", "b2g_destroy", "b2g_bind", "b2g_simulate", "b2g_refresh_rigid_body_state",
-                   "b2g_set_task", "b2g_task_step", "b2g_task_step_host"):
+                   "b2g_set_task", "b2g_set_anymal_task", "b2g_task_step", "b2g_task_step_host"):
             getattr(_lib, fn).restype = C.c_int
     return _lib
 
 
 EXPORTS = ("b2g_create", "b2g_destroy", "b2g_bind", "b2g_simulate", "b2g_refresh_rigid_body_state", "b2g_set_task",
-           "b2g_task_step", "b2g_task_step_host", "b2g_launch_count", "b2g_last_error", "b2g_version")
+           "b2g_set_anymal_task", "b2g_task_step", "b2g_task_step_host", "b2g_launch_count", "b2g_last_error", "b2g_version")
 
 
 class EngineError(RuntimeError):
@@ -106,7 +126,7 @@ def pack_model(model, ground_mu=1.0):
               "kp", "kd", "limit_k", "limit_d", "cp_pos", "cp_radius", "body_pos", "body_quat"):
         setattr(cm, n, arr(n, getattr(model, n), np.float32))
     cm.effort = arr("effort", np.minimum(model.effort, 3e38), np.float32)
-    cm.cp_mu = arr("cp_mu", 0.5 * (np.asarray(model.cp_mu) + ground_mu), np.float32)
+    cm.cp_mu = arr("cp_mu", np.asarray(model.cp_mu), np.float32)
     cm.contact_kn, cm.contact_cn, cm.contact_vs = model.contact_kn, model.contact_cn, model.contact_vs
     return cm, keep
 
@@ -126,6 +146,7 @@ class Sim:
         sp = CSimParams()
         sp.dt, sp.substeps = dt, int(substeps)
         sp.gravity = (C.c_float * 3)(*gravity)
+        sp.ground_friction = float(ground_mu)
         if hfield is not None:
             hf = np.ascontiguousarray(hfield, dtype=np.int16)
             self._keep["hf"] = hf
@@ -182,7 +203,10 @@ class Sim:
         for slot, t in buffers.items():
             self._bind(slot, t)
         self.task = params
-        _check(lib().b2g_set_task(self._h, C.byref(params)), "b2g_set_task")
+        if isinstance(params, CAnymalParams):
+            _check(lib().b2g_set_anymal_task(self._h, C.byref(params)), "b2g_set_anymal_task")
+        else:
+            _check(lib().b2g_set_task(self._h, C.byref(params)), "b2g_set_task")
 
     def task_step(self, actions: torch.Tensor):
         assert actions.is_contiguous() and actions.dtype == torch.float32 and actions.device == self.device

@@ -103,7 +103,9 @@ def load_urdf(path, opts: BuildOptions = None, name=None):
                 b.collapsed = opts.collapse_fixed_joints
             else:
                 raise ValueError(f"URDF joint type {jt} not supported")
-        for j in children.get(lname, []):
+        # Isaac Gym orders an articulation's DOFs/bodies depth-first with siblings by name (the ANYmal
+        # YAML lists LF, LH, RF, RH although the file has LF, RF, LH, RH -- SURVEY.md 7 hard part 3)
+        for j in sorted(children.get(lname, []), key=lambda j_: j_.attrib["name"]):
             jpos, jR = _origin(j)
             b.children.append(make_body(j.find("child").attrib["link"], jpos, jR, j))
         return b

@@ -290,3 +290,128 @@ def test_host_buffer_step_and_launch_count():
     assert env.sim.launch_count() == c0 + 1
     assert torch.equal(h_obs, env.obs_buf.cpu()) and torch.equal(h_rew, env.rew_buf.cpu())
     assert torch.equal(h_reset, env.reset_buf.cpu())
+
+
+# ------------------------------------------------------------------------------------ AnymalTerrain
+def _make_anymal(n, terrain=None, **over):
+    import isaacgymenvs_b200
+    from isaacgymenvs_b200 import config
+    cfg = config.builtin_cfg("AnymalTerrain", {"sim_device": "cuda:0", "rl_device": "cuda:0"})
+    e = cfg["task"]["env"]
+    if terrain:
+        e["terrain"].update(terrain)
+    for k, v in over.items():
+        if k in e["learn"]:
+            e["learn"][k] = v
+        elif k in e["control"]:
+            e["control"][k] = v
+        else:
+            e[k] = v
+    return isaacgymenvs_b200.make(seed=42, task="AnymalTerrain", num_envs=n, sim_device="cuda:0", rl_device="cuda:0",
+                                  headless=True, cfg=cfg)
+
+
+def test_anymal_terrain_epilogue_matches_reference_golden():
+    """No simulate (decimation = controlFrequencyInv = 0): termination, the 13 reward terms, feet air
+    time, commands, height sampling and the 188-d observation against what the reference's own
+    AnymalTerrain methods returned on the same inputs (tests/golden/make_golden_anymal.py)."""
+    g = np.load(os.path.join(GOLD, "anymal_terrain.npz"))
+    n = g["root"].shape[0]
+    hs = np.repeat(np.repeat(g["height_samples"], 8, 0), 8, 1)
+    env = _make_anymal(n, terrain={"heightSamplesOverride": hs}, skipPhysics=True, addNoise=False, pushRobots=False)
+    dev = env.device
+    t = lambda a, dt=torch.float32: torch.tensor(a, dtype=dt, device=dev)
+    env.root_states.copy_(t(g["root"]))
+    env.dof_pos.copy_(t(g["dof_pos"])); env.dof_vel.copy_(t(g["dof_vel"]))
+    env.contact_forces.copy_(t(g["contact_forces"]))
+    env.commands.copy_(t(g["commands_in"]))
+    env.last_actions.copy_(t(g["last_actions"])); env.last_dof_vel.copy_(t(g["last_dof_vel"]))
+    env.torques.copy_(t(g["torques"])); env.feet_air_time.copy_(t(g["feet_air_time_in"]))
+    env.progress_buf.copy_(t(g["progress"] - 1, torch.long))
+    env._episode_sums.zero_()
+    assert np.allclose(env.default_dof_pos[0].cpu().numpy(), g["default_dof_pos"])
+    obs, rew, reset, extras = env.step(t(g["actions"]))
+    torch.cuda.synchronize()
+    keep = g["reset"] == 0
+    assert np.array_equal(reset.cpu().numpy(), g["reset"])
+    assert np.allclose(rew.cpu().numpy(), g["rew"], atol=3e-6)
+    assert np.allclose(env._base_scratch[:, :9].cpu().numpy(), np.concatenate([g["base_lin_vel"], g["base_ang_vel"], g["projected_gravity"]], 1), atol=2e-6)
+    assert np.allclose(env.feet_air_time.cpu().numpy()[keep], g["feet_air_time"][keep], atol=1e-7)
+    assert np.allclose(env.commands.cpu().numpy()[keep], g["commands"][keep], atol=2e-6)
+    assert np.allclose(env._episode_sums.cpu().numpy()[:, keep], g["episode_sums"][:, keep], atol=3e-6)
+    o = obs["obs"].cpu().numpy()[keep]; go = g["obs"][keep]
+    bad = np.abs(o - go) > 3e-6
+    assert bad[:, :36].sum() == 0 and bad[:, 176:].sum() == 0
+    assert bad[:, 36:176].mean() < 2e-3          # height samples: index truncation at a cell border may flip on 1 ulp
+    assert np.allclose(env.last_actions.cpu().numpy(), np.clip(g["actions"], -1e30, 1e30))
+    # envs that were reset: progress 0, reset flag kept at 1, fresh commands inside their ranges
+    r = ~keep
+    assert (env.progress_buf.cpu().numpy()[r] == 0).all() and r.any()
+    c = env.commands.cpu().numpy()[r]
+    assert (np.abs(c[:, :2]) <= 1.0).all() and (np.abs(c[:, 3]) <= 3.14).all()
+
+
+def test_anymal_heightfield_contact_matches_oracle():
+    """gym.simulate on a height field: engine vs fp64 oracle from identical states."""
+    from isaacgymenvs_b200 import engine
+    from oracle.oracle import OracleSim
+    m = copy.deepcopy(load_compiled("anymal"))
+    n = 256
+    rng = np.random.default_rng(11)
+    hf = (rng.normal(size=(40, 40)) * 12).round().astype(np.int16)
+    hf = np.repeat(np.repeat(hf, 4, 0), 4, 1)                    # 160 x 160 samples of 0.1 m, blocks of 0.4 m
+    hscale, vscale, org = 0.1, 0.005, (-8.0, -8.0)
+    root, dof = _random_states(m, n, rng, 0.35, 0.75)
+    root[:, 0:2] = rng.uniform(-5, 5, size=(n, 2))
+    tau = rng.uniform(-40, 40, size=(n, 12))
+    sim = engine.Sim(m, n, 0.005, 1, G, ground_mu=1.0, hfield=hf, hf_horizontal_scale=hscale, hf_vertical_scale=vscale, hf_origin=org)
+    sim.acquire(engine.T_NET_CONTACT)
+    orc = OracleSim(m, 0.005, 1, G, ground_mu=1.0, threads=8, hfield=hf.astype(np.float64) * vscale, hf_scale=hscale, hf_origin=org)
+    sim.root_state.copy_(torch.tensor(root, dtype=torch.float32)); sim.dof_state.copy_(torch.tensor(dof.reshape(-1, 2), dtype=torch.float32))
+    sim.dof_actuation.copy_(torch.tensor(tau, dtype=torch.float32))
+    r64 = sim.root_state.cpu().numpy().astype(np.float64); d64 = sim.dof_state.cpu().numpy().astype(np.float64).reshape(n, 12, 2)
+    for _ in range(3):
+        sim.simulate()
+        out = orc.simulate(r64, d64, sim.dof_actuation.cpu().numpy().astype(np.float64))
+    torch.cuda.synchronize()
+    rg = sim.root_state.cpu().numpy(); dg = sim.dof_state.cpu().numpy().reshape(n, 12, 2)
+    assert (out["contact_force"][:, :, 2] > 1.0).any()           # contacts did happen
+    assert np.abs(rg[:, :7] - r64[:, :7]).max() < 3e-4
+    assert (np.abs(rg[:, 7:] - r64[:, 7:]) / np.maximum(1, np.abs(r64[:, 7:]))).max() < 5e-3
+    assert np.abs(dg[..., 0] - d64[..., 0]).max() < 3e-4
+    cg = sim.tensors[engine.T_NET_CONTACT].cpu().numpy().reshape(n, m.nb, 3)
+    assert np.abs(cg - out["contact_force"]).max() < 5e-3 * max(1.0, np.abs(out["contact_force"]).max())
+    sim.close()
+
+
+def test_anymal_terrain_rollout_is_sane():
+    """Zero actions on flat ground: the PD loop holds the default pose, the robot stands (base height,
+    contact forces carry the weight, no termination); on the curriculum terrain with random actions the
+    rollout stays finite and resets re-spawn robots on their tile."""
+    env = _make_anymal(256, terrain={"terrainType": "plane"}, addNoise=False, pushRobots=False)
+    z = torch.zeros(256, 12, device=env.device)
+    for _ in range(150):
+        obs, rew, reset, _ = env.step(z)
+    torch.cuda.synchronize()
+    h = env.root_states[:, 2].cpu().numpy()
+    assert np.isfinite(obs["obs"].cpu().numpy()).all()
+    assert (h > 0.40).all() and (h < 0.70).all(), (h.min(), h.max())
+    W = env.model.total_mass() * 9.81
+    fz = env.contact_forces[:, env.feet_indices, 2].sum(1).cpu().numpy()
+    assert np.abs(np.median(fz) - W) / W < 0.1
+    assert reset.sum().item() == 0
+    assert (rew.cpu().numpy() >= 0).all()
+    env2 = _make_anymal(512)
+    g = torch.Generator(device=env2.device).manual_seed(0)
+    nres = 0
+    for _ in range(120):
+        obs, rew, reset, extras = env2.step(2 * torch.rand(512, 12, device=env2.device, generator=g) - 1)
+        nres += int(reset.sum().item())
+    torch.cuda.synchronize()
+    assert torch.isfinite(obs["obs"]).all() and torch.isfinite(env2.root_states).all()
+    assert nres > 0
+    lv = env2.terrain_levels.cpu().numpy()
+    assert (lv >= 0).all() and (lv < 10).all()
+    d = (env2.root_states[:, :2] - env2.env_origins[:, :2]).norm(dim=1).cpu().numpy()
+    assert (d < 12.0).all()
+    assert "rew_lin_vel_xy" in extras["episode"] and "terrain_level" in extras["episode"]

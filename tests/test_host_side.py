@@ -26,12 +26,13 @@ def test_struct_layouts_match_header_sizes():
     """ctypes mirrors must have the size the C compiler gives the header's structs."""
     import subprocess, tempfile
     from isaacgymenvs_b200 import engine
-    src = '#include "b200gym.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu\\n", sizeof(b2g_model), sizeof(b2g_sim_params), sizeof(b2g_task_params));return 0;}\n'
+    src = '#include "b200gym.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu\\n", sizeof(b2g_model), sizeof(b2g_sim_params), sizeof(b2g_task_params), sizeof(b2g_anymal_params));return 0;}\n'
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "t.c"), "w").write(src)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "t"), os.path.join(d, "t.c")])
         sizes = [int(x) for x in subprocess.check_output([os.path.join(d, "t")]).split()]
-    assert sizes == [ctypes.sizeof(engine.CModel), ctypes.sizeof(engine.CSimParams), ctypes.sizeof(engine.CTaskParams)]
+    assert sizes == [ctypes.sizeof(engine.CModel), ctypes.sizeof(engine.CSimParams), ctypes.sizeof(engine.CTaskParams),
+                     ctypes.sizeof(engine.CAnymalParams)]
 
 
 def test_no_cpu_fallback():

@@ -81,3 +81,35 @@ def test_philox_known_answers():
     assert T.philox4x32([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
     assert T.philox4x32([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
         [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_anymal_terrain_restatement_matches_reference_methods():
+    """oracle/tasks_np.py anymal_* against the reference's own AnymalTerrain methods
+    (tests/golden/make_golden_anymal.py)."""
+    g = np.load(os.path.join(G, "anymal_terrain.npz"))
+    assert np.array_equal(T.wrap_to_pi(g["wrap_to_pi_in"]), g["wrap_to_pi_out"]) or np.allclose(T.wrap_to_pi(g["wrap_to_pi_in"]), g["wrap_to_pi_out"], atol=1e-6)
+    assert T.wrap_to_pi(f32([-4.0]))[0] == f32(-4.0)            # the fmod quirk (SURVEY.md 3.3)
+    root = g["root"]
+    hs = np.repeat(np.repeat(g["height_samples"], 8, 0), 8, 1)
+    blv, bav, pg, cmd = T.anymal_prepare(root, g["commands_in"])
+    assert np.allclose(blv, g["base_lin_vel"], atol=2e-6) and np.allclose(bav, g["base_ang_vel"], atol=2e-6)
+    assert np.allclose(pg, g["projected_gravity"], atol=2e-6) and np.allclose(cmd, g["commands"], atol=2e-6)
+    mh = T.anymal_get_heights(root, hs, 20, 0.1, 0.005)
+    assert (mh != g["measured_heights"]).mean() < 2e-3          # index truncation at cell borders may flip on 1-ulp differences
+    n = root.shape[0]
+    dt = 0.02
+    max_len = int(20 / dt + 0.5)
+    reset = T.anymal_check_termination(g["contact_forces"], g["progress"], max_len)
+    assert np.array_equal(reset, g["reset"])
+    scales = dict(termination=0.0, lin_vel_xy=1.0, lin_vel_z=-4.0, ang_vel_z=0.5, ang_vel_xy=-0.05, orient=-0.0, torque=-0.00002,
+                  joint_acc=-0.0005, base_height=-0.0, air_time=1.0, collision=-0.25, stumble=-0.0, action_rate=-0.01, hip=-0.0)
+    rs = {k: v * dt for k, v in scales.items()}
+    rew, fat, terms = T.anymal_reward(g["base_lin_vel"], g["base_ang_vel"], g["projected_gravity"], g["commands"], root, g["torques"],
+                                      g["last_dof_vel"], g["dof_vel"], g["dof_pos"], g["default_dof_pos"], g["contact_forces"],
+                                      g["last_actions"], g["actions"], g["feet_air_time_in"], g["reset"], np.zeros(n, bool), rs, dt)
+    assert np.allclose(rew, g["rew"], atol=2e-6) and np.allclose(fat, g["feet_air_time"], atol=1e-7)
+    es = np.stack([terms[k] for k in T.ANYMAL_SUM_KEYS])
+    assert np.allclose(es, g["episode_sums"], atol=2e-6)
+    obs = T.anymal_observations(g["base_lin_vel"], g["base_ang_vel"], g["projected_gravity"], g["commands"], g["dof_pos"], g["dof_vel"],
+                                root, g["measured_heights"], g["actions"])
+    assert np.allclose(obs, g["obs"], atol=2e-6)
