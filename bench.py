@@ -25,6 +25,7 @@ WORKLOADS = {   # name -> (task, num_envs per GPU, algorithmic bytes per env-ste
     "ant": ("Ant", 16384, 673),
     "humanoid": ("Humanoid", 8192, 1161),
     "cartpole": ("Cartpole", 16384, 89),
+    "anymal": ("AnymalTerrain", 4096, 2250),
 }
 METRIC = "env-steps/s at num_envs=16384 (Ant), 1/2/4/8 B200; %HBM roofline"
 
@@ -246,7 +247,7 @@ def run_gpu_arm(args):
         "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{task} num_envs={n} per GPU, random actions U(-1,1), sim dt 0.0166 x 2 substeps",
+        "config": {"workload": f"{task} num_envs={n} per GPU, random actions U(-1,1), sim dt {env.cfg['sim']['dt']} x {env.cfg['sim']['substeps']} substeps",
                    "num_envs_total": world * n, "timing": "per-step CUDA events, 256 MB write flushes L2 between timed steps",
                    "collective": "none on the step path; one NCCL all_gather of per-env returns per rollout (logging)"},
         "back_to_back": {"value": world * n * args.steps / (b2b_ms * 1e-3), "unit": "env-steps/s", "ms_per_step": b2b_ms / args.steps,
@@ -274,7 +275,7 @@ def run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="ant", choices=sorted(WORKLOADS))

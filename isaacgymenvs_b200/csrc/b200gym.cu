@@ -185,35 +185,42 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? B2G_MINBLOCKS : 1)) loc
     float *const s_act = s_dof + EPB * nd * 2;
     float *const s_sens = s_act + EPB * nd;
     float *const s_dfrc = s_sens + EPB * nsens6;
-    // per-env scalars of post_physics_step: issued now, consumed after the physics
+    // ---- prologue.  Programmatic dependent launch: this grid may start while the previous kernel in the
+    // stream (the previous control step) is still draining.  Everything that does not depend on it --
+    // barrier set-up and the bulk copy of the (constant) model -- happens before griddepcontrol.wait;
+    // the state tiles and per-env scalars are fetched after it.
+    __shared__ alignas(8) uint64_t mbar2;
     long long *const progress_b = (long long *)B.p[B2G_T_PROGRESS];
     long long *const reset_b = (long long *)B.p[B2G_T_RESET];
     float *const pot_b = (float *)B.p[B2G_T_POTENTIALS], *const ppot_b = (float *)B.p[B2G_T_PREV_POTENTIALS];
     const int e_pre = min((int)((blockIdx.x * BLOCK + threadIdx.x) / L), N - 1);
+    if (threadIdx.x == 0) { mbar_init(&mbar, 1); mbar_init(&mbar2, 1); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int nl = gm->nl, ncp = gm->ncp, ns = gm->ns;   // three scalar loads; everything else arrives by bulk copy
+        const uint32_t hb = (uint32_t)offsetof(DevModel, slots) + (uint32_t)ns * MAX_LANES * (uint32_t)sizeof(SlotRec);
+        const uint32_t lb = round16((uint32_t)nl * (uint32_t)sizeof(LinkC)), cb = round16((uint32_t)ncp * (uint32_t)sizeof(CpC));
+        mbar_expect_tx(&mbar, hb + lb + cb);
+        bulk_g2s(&sm, gm, hb, &mbar);                                      // header | slots[0..ns)
+        char *const pk = reinterpret_cast<char *>(&sm) + hb;               // links and cps packed right behind
+        bulk_g2s(pk, gm->links, lb, &mbar);
+        if (cb) bulk_g2s(pk + lb, gm->cps, cb, &mbar);
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");                     // previous step's writes are now visible
+    if (tiles && threadIdx.x == 0) {
+        const uint32_t rb = EPB * 13 * 4, db = (uint32_t)(EPB * nd * 8), ab = (uint32_t)(EPB * nd * 4);
+        mbar_expect_tx(&mbar2, rb + db + ab);
+        bulk_g2s(s_root, (const float *)B.p[B2G_T_ROOT_STATE] + (size_t)env0 * 13, rb, &mbar2);
+        bulk_g2s(s_dof, (const float *)B.p[B2G_T_DOF_STATE] + (size_t)env0 * nd * 2, db, &mbar2);
+        bulk_g2s(s_act, actions_in + (size_t)env0 * nd, ab, &mbar2);
+    }
+    // per-env scalars of post_physics_step: issued now, consumed after the physics
     const long long progress_in = progress_b[e_pre];
     const long long reset_in = reset_b[e_pre];
     const float potentials_in = pot_b[e_pre];
-    {
-        if (threadIdx.x == 0) mbar_init(&mbar, 1);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const int nl = gm->nl, ncp = gm->ncp, ns = gm->ns;   // three scalar loads; everything else arrives by bulk copy
-            const uint32_t hb = (uint32_t)offsetof(DevModel, slots) + (uint32_t)ns * MAX_LANES * (uint32_t)sizeof(SlotRec);
-            const uint32_t lb = round16((uint32_t)nl * (uint32_t)sizeof(LinkC)), cb = round16((uint32_t)ncp * (uint32_t)sizeof(CpC));
-            const uint32_t rb = EPB * 13 * 4, db = (uint32_t)(EPB * nd * 8), ab = (uint32_t)(EPB * nd * 4);
-            mbar_expect_tx(&mbar, hb + lb + cb + (tiles ? rb + db + ab : 0u));
-            bulk_g2s(&sm, gm, hb, &mbar);                                      // header | slots[0..ns)
-            char *const pk = reinterpret_cast<char *>(&sm) + hb;               // links and cps packed right behind
-            bulk_g2s(pk, gm->links, lb, &mbar);
-            if (cb) bulk_g2s(pk + lb, gm->cps, cb, &mbar);
-            if (tiles) {
-                bulk_g2s(s_root, (const float *)B.p[B2G_T_ROOT_STATE] + (size_t)env0 * 13, rb, &mbar);
-                bulk_g2s(s_dof, (const float *)B.p[B2G_T_DOF_STATE] + (size_t)env0 * nd * 2, db, &mbar);
-                bulk_g2s(s_act, actions_in + (size_t)env0 * nd, ab, &mbar);
-            }
-        }
-        mbar_wait(&mbar, 0);
-    }
+    mbar_wait(&mbar, 0);
+    if (tiles) mbar_wait(&mbar2, 0);
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");       // the next step's grid may begin its own prologue
     using ST = Stepper<L, HF, BLOCK>;
     const int gt = blockIdx.x * BLOCK + threadIdx.x;
     const int env = gt / L, lane = gt % L;
@@ -912,7 +919,14 @@ extern "C" int b2g_task_step(b2g_sim *s, const float *actions, void *stream) {
 #define LOCO_T(LN, HM, BK, TL)                                                                                            \
     do {                                                                                                                   \
         int rc_ = set_smem(loco_step_kernel<LN, false, HM, BK, TL>, dyn); if (rc_) return rc_;                            \
-        loco_step_kernel<LN, false, HM, BK, TL><<<grid, blk, dyn, st>>>(s->dm, s->d_hf, s->buf, P, actions, (int)N, ta);  \
+        cudaLaunchConfig_t lc = {};                                                                                        \
+        lc.gridDim = dim3(grid); lc.blockDim = dim3(blk); lc.dynamicSmemBytes = dyn; lc.stream = st;                       \
+        cudaLaunchAttribute at[1];                                                                                         \
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                                     \
+        at[0].val.programmaticStreamSerializationAllowed = 1;                                                              \
+        lc.attrs = at; lc.numAttrs = 1;                                                                                    \
+        CUDA_TRY(cudaLaunchKernelEx(&lc, loco_step_kernel<LN, false, HM, BK, TL>, (const DevModel *)s->dm,                 \
+                                    (const int16_t *)s->d_hf, s->buf, P, actions, (int)N, ta));                            \
     } while (0)
 #define LOCO(LN, HM, BK) do { if (tiles) LOCO_T(LN, HM, BK, true); else LOCO_T(LN, HM, BK, false); } while (0)
         if (s->d_hf) return fail(B2G_E_UNSUPPORTED, "locomotion tasks run on the ground plane");

@@ -378,6 +378,21 @@ def build_model(name, root: IRBody, has_free_root: bool, opts: BuildOptions) -> 
                 break
         if not inside:
             keep.append(ca)
+    # a child's sphere centred on its own hinge anchor coincides -- in every configuration -- with a
+    # parent sphere of the same radius at that anchor (capsule chains: nv_ant.xml:42-52): keep the parent's
+    parent_of = L["parent"]
+    dedup = []
+    for ca in keep:
+        li = ca[0]
+        drop = False
+        if li > 0 and L["jtype"][li] == JOINT_HINGE and np.linalg.norm(ca[2]) < 1e-9:
+            for cb in keep:
+                if cb[0] == parent_of[li] and abs(cb[3] - ca[3]) < 1e-12 and np.linalg.norm(cb[2] - L["lpos"][li]) < 1e-9:
+                    drop = True
+                    break
+        if not drop:
+            dedup.append(ca)
+    keep = dedup
     m.geom_names = gn
     m.geom_type = np.array(gt, dtype=np.int32); m.geom_link = np.array(gl, dtype=np.int32)
     m.geom_body = np.array(gb, dtype=np.int32)
