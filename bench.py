@@ -190,8 +190,10 @@ def run_gpu_arm(args):
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     l0 = env.sim.launch_count()
     barrier()
+    sink = torch.zeros(1, device=device)
     for k in range(args.steps):
-        flush.zero_()
+        flush.zero_()                      # write 256 MB (> 126 MB L2): evicts the previous step's tensors ...
+        sink += flush.sum()                # ... then read it back: the dirty lines are written out, L2 is left clean and cold
         ev[k][0].record()
         env.sim.task_step(ring[k % 16])
         ev[k][1].record()
@@ -248,7 +250,7 @@ def run_gpu_arm(args):
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{task} num_envs={n} per GPU, random actions U(-1,1), sim dt {env.cfg['sim']['dt']} x {env.cfg['sim']['substeps']} substeps",
-                   "num_envs_total": world * n, "timing": "per-step CUDA events, 256 MB write flushes L2 between timed steps",
+                   "num_envs_total": world * n, "timing": "per-step CUDA events on the launching stream; between timed steps L2 is flushed by writing a 256 MB buffer and reading it back (inputs come from HBM, no dirty lines left to evict)",
                    "collective": "none on the step path; one NCCL all_gather of per-env returns per rollout (logging)"},
         "back_to_back": {"value": world * n * args.steps / (b2b_ms * 1e-3), "unit": "env-steps/s", "ms_per_step": b2b_ms / args.steps,
                          "note": "same K steps without the L2 flush (state stays L2-resident)"},

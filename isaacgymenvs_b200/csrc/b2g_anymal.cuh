@@ -294,8 +294,18 @@ __global__ void __launch_bounds__(BLOCK) anymal_reset_obs_kernel(Buffers B, cons
     float *obsc = (float *)B.p[B2G_T_OBS_CLIPPED];
     obsc = (obsc && obsc != (float *)B.p[B2G_T_OBS]) ? obsc + (size_t)e * P.num_obs : nullptr;
     const float *nsv = (const float *)B.p[B2G_T_NOISE_SCALE];
+    // observation noise (:481-482): uniform number idx of stream (env, step); one Philox block serves 4 neighbours,
+    // and every lane writes contiguous index ranges, so the block is cached
+    uint32_t nz[4]; int nz_blk = -1;
     auto put = [&](int idx, float v) {
-        if (P.add_noise) v += (2.f * anymal_uniform(P.seed, gid, step_counter, TAG_NOISE, idx) - 1.f) * nsv[idx];
+        if (P.add_noise) {
+            if ((idx >> 2) != nz_blk) {
+                nz_blk = idx >> 2;
+                philox4x32_10((uint32_t)nz_blk, step_counter, gid, TAG_NOISE, (uint32_t)P.seed, (uint32_t)(P.seed >> 32), nz);
+            }
+            const float u = (float)(nz[idx & 3] >> 8) * (1.0f / 16777216.0f);
+            v += (2.f * u - 1.f) * nsv[idx];
+        }
         obs[idx] = v;
         if (obsc) obsc[idx] = fminf(fmaxf(v, -P.clip_obs), P.clip_obs);
     };
@@ -323,7 +333,8 @@ __global__ void __launch_bounds__(BLOCK) anymal_reset_obs_kernel(Buffers B, cons
         const float nq = fmaxf(sqrtf(qy[2] * qy[2] + qy[3] * qy[3]), 1e-9f);
         qy[2] /= nq; qy[3] /= nq;
         const float bz = root[2];
-        for (int p = lane; p < 140; p += L) {
+        constexpr int PER = (140 + L - 1) / L;
+        for (int p = lane * PER; p < min(140, (lane + 1) * PER); p++) {
             const int ix = p / 10, iy = p % 10;
             const int xi = (ix < 7) ? ix - 8 : ix - 5;            // -8..-2, 2..8
             const int yi = (iy < 5) ? iy - 5 : iy - 4;            // -5..-1, 1..5
