@@ -1,0 +1,374 @@
+"""`isaacgym.gymapi` look-alike backed by the B200 engine (SURVEY.md 8b "required exports").
+
+Only what `tasks/base/vec_task.py` and the single-actor-per-env tasks of the reference touch is
+provided; every method cites a representative call site.  Actors, assets and envs are RECORDED
+here (create_actor is called num_envs times in a Python loop, `ant.py:185-197`, so it must cost
+microseconds); the engine is created once, in `prepare_sim`.
+"""
+import copy
+import os
+import types
+
+import numpy as np
+import torch
+
+from .. import engine
+from ..assets import load_asset_file
+from ..importer.model import BuildOptions
+
+SIM_PHYSX, SIM_FLEX = 0, 1
+UP_AXIS_Y, UP_AXIS_Z = 0, 1
+DOF_MODE_NONE, DOF_MODE_POS, DOF_MODE_VEL, DOF_MODE_EFFORT = 0, 1, 2, 3
+DOMAIN_ENV, DOMAIN_SIM, DOMAIN_ACTOR = 0, 1, 2
+MESH_VISUAL, MESH_COLLISION, MESH_VISUAL_AND_COLLISION = 0, 1, 2
+ENV_SPACE, LOCAL_SPACE, GLOBAL_SPACE = 0, 1, 2
+CC_NEVER, CC_LAST_SUBSTEP, CC_ALL_SUBSTEPS = 0, 1, 2
+
+
+def ContactCollection(v):
+    return int(v)
+
+
+class Vec3:
+    __slots__ = ("x", "y", "z")
+
+    def __init__(self, x=0.0, y=0.0, z=0.0):
+        self.x, self.y, self.z = float(x), float(y), float(z)
+
+    def __add__(self, o):
+        return Vec3(self.x + o.x, self.y + o.y, self.z + o.z)
+
+    def __sub__(self, o):
+        return Vec3(self.x - o.x, self.y - o.y, self.z - o.z)
+
+    def __iter__(self):
+        return iter((self.x, self.y, self.z))
+
+    def __repr__(self):
+        return f"Vec3({self.x}, {self.y}, {self.z})"
+
+
+class Quat:
+    __slots__ = ("x", "y", "z", "w")
+
+    def __init__(self, x=0.0, y=0.0, z=0.0, w=1.0):
+        self.x, self.y, self.z, self.w = float(x), float(y), float(z), float(w)
+
+
+class Transform:
+    def __init__(self, p=None, r=None):
+        self.p = p if p is not None else Vec3()
+        self.r = r if r is not None else Quat()
+
+
+class _Bag:
+    """Attribute bag: unknown keys are accepted, as `setattr(sim_params.physx, opt, ...)` relies on
+    (vec_task.py:532-554)."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+class PlaneParams(_Bag):
+    def __init__(self):
+        super().__init__(normal=Vec3(0, 0, 1), distance=0.0, static_friction=1.0, dynamic_friction=1.0, restitution=0.0)
+
+
+class TriangleMeshParams(_Bag):
+    def __init__(self):
+        super().__init__(nb_vertices=0, nb_triangles=0, transform=Transform(), static_friction=1.0, dynamic_friction=1.0,
+                         restitution=0.0)
+
+
+class AssetOptions(_Bag):
+    def __init__(self):
+        super().__init__(fix_base_link=False, default_dof_drive_mode=DOF_MODE_NONE, angular_damping=0.5, linear_damping=0.0,
+                         max_angular_velocity=64.0, collapse_fixed_joints=False, replace_cylinder_with_capsule=False,
+                         flip_visual_attachments=False, density=1000.0, armature=0.0, thickness=0.02, disable_gravity=False,
+                         use_physx_armature=True)
+
+
+class SimParams(_Bag):
+    def __init__(self):
+        super().__init__(dt=1.0 / 60.0, substeps=2, up_axis=UP_AXIS_Y, gravity=Vec3(0.0, -9.81, 0.0), use_gpu_pipeline=False,
+                         num_client_threads=0, physx=_Bag(num_threads=0, solver_type=1, use_gpu=False), flex=_Bag())
+
+
+class CameraProperties(_Bag):
+    pass
+
+
+class _Asset:
+    def __init__(self, model, options):
+        self.model = model
+        self.options = options
+        self.sensors = []           # (body index, Transform)
+        self.shape_props = [types.SimpleNamespace(friction=float(f), restitution=0.0) for f in model.geom_friction]
+
+
+class _Env:
+    def __init__(self, index):
+        self.index = index
+        self.actors = []
+
+
+class _Sim:
+    def __init__(self, compute_device, params):
+        self.compute_device = compute_device
+        self.params = params
+        self.ground = None
+        self.envs = []
+        self.asset = None           # one asset, one actor per env (the BASELINE locomotion tasks)
+        self.start_poses = []
+        self.engine = None
+        self.frame = 0
+
+
+class _Tensor:
+    """What acquire_*_tensor returns; gymtorch.wrap_tensor unwraps it to the torch tensor."""
+
+    def __init__(self, t):
+        self.tensor = t
+
+
+class Gym:
+    # ---- lifecycle (vec_task.py:63,247,262,382,386)
+    def create_sim(self, compute_device, graphics_device, sim_type, params):
+        return _Sim(compute_device, params)
+
+    def add_ground(self, sim, plane_params):
+        sim.ground = plane_params
+
+    def prepare_sim(self, sim):
+        if sim.engine is not None:
+            return True
+        if sim.asset is None or not sim.envs:
+            raise RuntimeError("prepare_sim: no actors were created")
+        a, p = sim.asset, sim.params
+        model = copy.deepcopy(a.model)
+        model.sensor_body = np.array([b for b, _ in a.sensors], dtype=np.int32)
+        model.sensor_pos = np.zeros((len(a.sensors), 3)); model.sensor_quat = np.tile([0, 0, 0, 1.0], (len(a.sensors), 1))
+        mu = sim.ground.dynamic_friction if sim.ground is not None else 1.0
+        g = p.gravity
+        sim.engine = engine.Sim(model, len(sim.envs), dt=p.dt, substeps=p.substeps, gravity=(g.x, g.y, g.z), ground_mu=mu,
+                                device=f"cuda:{sim.compute_device}")
+        rs = sim.engine.root_state
+        for i, pose in enumerate(sim.start_poses):
+            rs[i, 0:3] = torch.tensor([pose.p.x, pose.p.y, pose.p.z])
+            rs[i, 3:7] = torch.tensor([pose.r.x, pose.r.y, pose.r.z, pose.r.w])
+        return True
+
+    def simulate(self, sim):
+        sim.engine.simulate()
+        sim.frame += 1
+
+    def fetch_results(self, sim, wait):
+        pass
+
+    def get_frame_count(self, sim):
+        return sim.frame
+
+    def get_sim_params(self, sim):
+        return sim.params
+
+    def set_sim_params(self, sim, params):
+        sim.params = params
+
+    # ---- assets (ant.py:149-178, humanoid.py:152-171, cartpole.py:84-113)
+    def load_asset(self, sim, root, file, options=None):
+        o = options or AssetOptions()
+        opts = BuildOptions(fix_base_link=o.fix_base_link, collapse_fixed_joints=o.collapse_fixed_joints,
+                            replace_cylinder_with_capsule=o.replace_cylinder_with_capsule, armature=o.armature,
+                            density=o.density, angular_damping=o.angular_damping, linear_damping=o.linear_damping,
+                            disable_gravity=o.disable_gravity, default_dof_drive_mode=o.default_dof_drive_mode)
+        return _Asset(load_asset_file(root, file, opts), o)
+
+    def get_asset_dof_count(self, asset):
+        return asset.model.ndof
+
+    def get_asset_rigid_body_count(self, asset):
+        return asset.model.nb
+
+    def get_asset_joint_count(self, asset):
+        return asset.model.ndof
+
+    def get_asset_rigid_shape_count(self, asset):
+        return len(asset.model.geom_type)
+
+    def get_asset_rigid_body_name(self, asset, i):
+        return asset.model.body_names[i]
+
+    def get_asset_rigid_body_names(self, asset):
+        return list(asset.model.body_names)
+
+    def get_asset_dof_names(self, asset):
+        return list(asset.model.dof_names)
+
+    def find_asset_dof_index(self, asset, name):
+        return asset.model.dof_names.index(name)
+
+    def find_asset_rigid_body_index(self, asset, name):
+        return asset.model.body_names.index(name)
+
+    def get_asset_actuator_count(self, asset):
+        return len(asset.model.actuator_names)
+
+    def get_asset_actuator_joint_name(self, asset, i):
+        return asset.model.actuator_joint[i]
+
+    def get_asset_actuator_properties(self, asset):
+        m = asset.model
+        return [types.SimpleNamespace(motor_effort=float(g), kp=float(k), lower_force_limit=float(fr[0]), upper_force_limit=float(fr[1]))
+                for g, k, fr in zip(m.actuator_gear, m.actuator_kp, m.actuator_forcerange)]
+
+    def get_asset_dof_properties(self, asset):
+        m = asset.model
+        dt = np.dtype([("hasLimits", "?"), ("lower", "f4"), ("upper", "f4"), ("driveMode", "i4"), ("velocity", "f4"),
+                       ("effort", "f4"), ("stiffness", "f4"), ("damping", "f4"), ("friction", "f4"), ("armature", "f4")])
+        p = np.zeros(m.ndof, dtype=dt)
+        p["hasLimits"] = m.limited[1:] > 0
+        p["lower"], p["upper"] = m.lower[1:], m.upper[1:]
+        p["driveMode"] = m.drive_mode[1:]
+        p["velocity"] = np.minimum(m.velocity[1:], 3e38); p["effort"] = np.minimum(m.effort[1:], 3e38)
+        p["stiffness"], p["damping"], p["armature"] = m.kp[1:], m.kd[1:], m.armature[1:]
+        return p
+
+    def get_asset_rigid_shape_properties(self, asset):
+        return asset.shape_props
+
+    def set_asset_rigid_shape_properties(self, asset, props):
+        asset.shape_props = props
+
+    def create_asset_force_sensor(self, asset, body_idx, local_pose, props=None):
+        asset.sensors.append((int(body_idx), local_pose))
+        return len(asset.sensors) - 1
+
+    # ---- envs / actors (ant.py:185-212)
+    def create_env(self, sim, lower, upper, num_per_row):
+        e = _Env(len(sim.envs))
+        e.sim = sim
+        sim.envs.append(e)
+        return e
+
+    def create_actor(self, env, asset, pose, name, group, filter, seg_id=0):
+        sim = env.sim
+        if sim.asset is None:
+            sim.asset = asset
+        elif sim.asset is not asset or env.actors:
+            raise NotImplementedError("the B200 engine steps one actor of one asset per env (SURVEY.md 8f for the rest)")
+        env.actors.append(name)
+        sim.start_poses.append(Transform(Vec3(pose.p.x, pose.p.y, pose.p.z), Quat(pose.r.x, pose.r.y, pose.r.z, pose.r.w)))
+        return 0
+
+    def begin_aggregate(self, *a):
+        pass
+
+    def end_aggregate(self, *a):
+        pass
+
+    def set_rigid_body_color(self, *a):
+        pass
+
+    def get_actor_dof_properties(self, env, actor):
+        return self.get_asset_dof_properties(env.sim.asset)
+
+    def set_actor_dof_properties(self, env, actor, props):
+        m = env.sim.asset.model
+        m.kp[1:] = props["stiffness"]; m.kd[1:] = props["damping"]
+        m.drive_mode[1:] = props["driveMode"]
+        return True
+
+    def enable_actor_dof_force_sensors(self, env, actor):
+        return True
+
+    def find_actor_rigid_body_handle(self, env, actor, name):
+        return env.sim.asset.model.body_names.index(name)
+
+    def get_actor_index(self, env, actor, domain):
+        return env.index
+
+    def get_actor_rigid_body_properties(self, env, actor):
+        m = env.sim.asset.model
+        return [types.SimpleNamespace(mass=float(m.mass[m.body_link[b]])) for b in range(m.nb)]
+
+    def get_sim_dof_count(self, sim):
+        return sim.asset.model.ndof * len(sim.envs)
+
+    def get_env_origin(self, env):
+        return Vec3()
+
+    # ---- state views (ant.py:78-95, humanoid.py:85-86, anymal_terrain.py:119)
+    def acquire_actor_root_state_tensor(self, sim):
+        return _Tensor(sim.engine.root_state)
+
+    def acquire_dof_state_tensor(self, sim):
+        return _Tensor(sim.engine.dof_state)
+
+    def acquire_force_sensor_tensor(self, sim):
+        return _Tensor(sim.engine.acquire(engine.T_FORCE_SENSOR))
+
+    def acquire_dof_force_tensor(self, sim):
+        return _Tensor(sim.engine.acquire(engine.T_DOF_FORCE))
+
+    def acquire_rigid_body_state_tensor(self, sim):
+        return _Tensor(sim.engine.acquire(engine.T_RIGID_BODY_STATE))
+
+    def acquire_net_contact_force_tensor(self, sim):
+        return _Tensor(sim.engine.acquire(engine.T_NET_CONTACT))
+
+    def refresh_actor_root_state_tensor(self, sim):      # written in place by simulate
+        return True
+
+    refresh_dof_state_tensor = refresh_force_sensor_tensor = refresh_dof_force_tensor = refresh_actor_root_state_tensor
+    refresh_net_contact_force_tensor = refresh_actor_root_state_tensor
+
+    def refresh_rigid_body_state_tensor(self, sim):
+        sim.engine.refresh_rigid_body_state()
+        return True
+
+    # ---- writes (ant.py:265-285)
+    def set_dof_actuation_force_tensor(self, sim, t):
+        sim.engine.dof_actuation.view(-1).copy_(t.view(-1))
+        return True
+
+    def set_dof_position_target_tensor(self, sim, t):
+        sim.engine.dof_target.view(-1).copy_(t.view(-1))
+        return True
+
+    def set_actor_root_state_tensor(self, sim, t):
+        if t.data_ptr() != sim.engine.root_state.data_ptr():
+            sim.engine.root_state.copy_(t.view_as(sim.engine.root_state))
+        return True
+
+    def set_actor_root_state_tensor_indexed(self, sim, t, idx, n):
+        if t.data_ptr() != sim.engine.root_state.data_ptr():
+            i = idx[:n].long()
+            sim.engine.root_state[i] = t.view_as(sim.engine.root_state)[i]
+        return True
+
+    def set_dof_state_tensor(self, sim, t):
+        if t.data_ptr() != sim.engine.dof_state.data_ptr():
+            sim.engine.dof_state.copy_(t.view_as(sim.engine.dof_state))
+        return True
+
+    def set_dof_state_tensor_indexed(self, sim, t, idx, n):
+        if t.data_ptr() != sim.engine.dof_state.data_ptr():
+            nd = sim.asset.model.ndof
+            i = idx[:n].long()
+            sim.engine.dof_state.view(-1, nd, 2)[i] = t.view(-1, nd, 2)[i]
+        return True
+
+    # ---- viewer (headless only)
+    def create_viewer(self, sim, props):
+        return None
+
+    def viewer_camera_look_at(self, *a):
+        pass
+
+
+_GYM = Gym()
+
+
+def acquire_gym():
+    """Process-wide singleton (vec_task.py:247)."""
+    return _GYM
