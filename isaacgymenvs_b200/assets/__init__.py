@@ -16,6 +16,8 @@ KNOWN = {
     "mjcf/nv_humanoid.xml": "humanoid",
     "urdf/cartpole.urdf": "cartpole",
     "urdf/anymal_c/urdf/anymal_minimal.urdf": "anymal",
+    "mjcf/open_ai_assets/hand/shadow_hand.xml": "shadow_hand",
+    "urdf/objects/cube_multicolor.urdf": "cube",
 }
 
 

@@ -12,6 +12,10 @@ SPECS = {
     "ant": ("mjcf/nv_ant.xml", BuildOptions()),
     "humanoid": ("mjcf/nv_humanoid.xml", BuildOptions(angular_damping=0.01)),
     "cartpole": ("urdf/cartpole.urdf", BuildOptions(fix_base_link=True)),
+    "shadow_hand": ("mjcf/open_ai_assets/hand/shadow_hand.xml",
+                    BuildOptions(fix_base_link=True, collapse_fixed_joints=True, disable_gravity=True, angular_damping=0.01,
+                                 capsule_mid_spheres=1)),
+    "cube": ("urdf/objects/cube_multicolor.urdf", BuildOptions()),
     "anymal": ("urdf/anymal_c/urdf/anymal_minimal.urdf",
                BuildOptions(collapse_fixed_joints=True, replace_cylinder_with_capsule=True, density=0.001,
                             default_dof_drive_mode=DRIVE_EFFORT)),

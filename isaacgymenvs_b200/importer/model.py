@@ -158,6 +158,12 @@ class Model:
     cp_radius: np.ndarray = None
     cp_mu: np.ndarray = None
     cp_body: np.ndarray = None
+    # box primitives kept as boxes (another body's corner points are tested against them: hand-object contact)
+    box_link: np.ndarray = None   # (nbx,)
+    box_body: np.ndarray = None
+    box_pos: np.ndarray = None    # (nbx,3) link frame
+    box_quat: np.ndarray = None   # (nbx,4)
+    box_half: np.ndarray = None   # (nbx,3)
     # force sensors (body frame), actuators, tendons
     sensor_body: np.ndarray = None
     sensor_pos: np.ndarray = None
@@ -252,6 +258,7 @@ class BuildOptions:
     linear_damping: float = 0.0
     disable_gravity: bool = False
     default_dof_drive_mode: int = DRIVE_NONE
+    capsule_mid_spheres: int = 0       # extra contact spheres along a capsule's axis (hands: the cylinder part must touch objects too)
     contact_kn_per_kg: float = 2000.0  # kn = 2000 s^-2 * actor mass
     contact_zeta: float = 1.0
 
@@ -344,6 +351,7 @@ def build_model(name, root: IRBody, has_free_root: bool, opts: BuildOptions) -> 
     # collision primitives + plane contact points
     gt, gl, gb, gp, gq, gs, gf, gn = [], [], [], [], [], [], [], []
     cps = []
+    boxes = []
     for g, li, bi, p, R in geoms:
         t = g.gtype
         if t == GEOM_CYLINDER and opts.replace_cylinder_with_capsule:
@@ -357,7 +365,12 @@ def build_model(name, root: IRBody, has_free_root: bool, opts: BuildOptions) -> 
         elif t in (GEOM_CAPSULE, GEOM_CYLINDER):
             cps.append((li, bi, p - z * size[1], size[0], g.friction))
             cps.append((li, bi, p + z * size[1], size[0], g.friction))
+            for k in range(opts.capsule_mid_spheres):
+                f = (k + 1) / (opts.capsule_mid_spheres + 1) * 2 - 1
+                cps.append((li, bi, p + z * size[1] * f, size[0], g.friction))
         elif t == GEOM_BOX:
+            if np.min(size) > 2e-3:
+                boxes.append((li, bi, p, rot.mat_to_quat(R), size.copy()))
             for sx in (-1, 1):
                 for sy in (-1, 1):
                     for sz in (-1, 1):
@@ -404,6 +417,9 @@ def build_model(name, root: IRBody, has_free_root: bool, opts: BuildOptions) -> 
     m.cp_radius = np.array([c[3] for c in keep], dtype=np.float64)
     m.cp_mu = np.array([c[4] for c in keep], dtype=np.float64)
 
+    m.box_link = np.array([b[0] for b in boxes], dtype=np.int32); m.box_body = np.array([b[1] for b in boxes], dtype=np.int32)
+    m.box_pos = np.array([b[2] for b in boxes]).reshape(-1, 3); m.box_quat = np.array([b[3] for b in boxes]).reshape(-1, 4)
+    m.box_half = np.array([b[4] for b in boxes]).reshape(-1, 3)
     m.sensor_body = np.zeros(0, dtype=np.int32)
     m.sensor_pos = np.zeros((0, 3)); m.sensor_quat = np.zeros((0, 4))
     m.actuator_names, m.actuator_joint, m.actuator_kind = [], [], []

@@ -60,6 +60,11 @@ def load_urdf(path, opts: BuildOptions = None, name=None):
             g.name = f"{lname}_col{len(b.geoms)}"
             b.geoms.append(g)
         ie = le.find("inertial")
+        if ie is not None and ie.find("mass") is None and ie.find("density") is not None:
+            # Isaac Gym extension (cube_multicolor.urdf:17-19): uniform density over the collision primitives
+            for g in b.geoms:
+                g.density = float(ie.find("density").attrib["value"])
+            ie = None
         if ie is not None and ie.find("mass") is not None:
             mass = float(ie.find("mass").attrib["value"])
             ipos, iR = _origin(ie)

@@ -76,6 +76,17 @@ typedef struct {
     double kn, cn, vs;
     double gravity[3];
     double dt;
+    /* optional second body per env: a free box (ShadowHand's cube, shadow_hand.py:372) in contact with the
+     * articulation's contact spheres, with its box primitives and with the ground */
+    int obj_on, obj_gravity_on, nbx, pad1;
+    double obj_mass, obj_inertia[3], obj_half[3], obj_kn, obj_cn, obj_mu;
+    const int *box_link;                    /* nbx */
+    const double *box_pos, *box_quat, *box_half;   /* nbx x 3,4,3 (link frame) */
+    /* fixed tendons (shared.xml:54-69): length = c0 q[d0] + c1 q[d1], penalty outside [lo, hi] */
+    int nten, pad2;
+    const int *ten_dof;                     /* nten x 2 (dof indices) */
+    const double *ten_coef, *ten_range;     /* nten x 2 */
+    double ten_k, ten_d;
 } OracleModel;
 
 /* ---------------------------------------------------------------- small linear algebra */
@@ -189,11 +200,32 @@ static void ground(const OracleModel *m, real x, real y, real *h, real n[3]) {
     n[0] = -gx * inv; n[1] = -gy * inv; n[2] = inv;
 }
 
+/* sphere (centre c, radius r; world) against a box (centre xb, rotation Rb, half sizes hb): penetration and
+ * the unit normal pointing from the box towards the sphere.  Returns 0 when apart. */
+static int sphere_box(const real c[3], real r, const real xb[3], const real Rb[9], const real hb[3], real *pen, real n[3]) {
+    real d[3] = {c[0] - xb[0], c[1] - xb[1], c[2] - xb[2]}, p[3], q[3], e[3];
+    mat3T_vec(Rb, d, p);
+    int inside = 1;
+    for (int k = 0; k < 3; k++) { q[k] = p[k] < -hb[k] ? -hb[k] : (p[k] > hb[k] ? hb[k] : p[k]); if (q[k] != p[k]) inside = 0; e[k] = p[k] - q[k]; }
+    real nl[3] = {0, 0, 0};
+    if (!inside) {
+        real dist = SQRT(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+        if (dist >= r) return 0;
+        *pen = r - dist; nl[0] = e[0] / dist; nl[1] = e[1] / dist; nl[2] = e[2] / dist;
+    } else {
+        int ax = 0; real best = hb[0] - FABS(p[0]);
+        for (int k = 1; k < 3; k++) { real m_ = hb[k] - FABS(p[k]); if (m_ < best) { best = m_; ax = k; } }
+        *pen = r + best; nl[ax] = p[ax] >= 0 ? 1 : -1;
+    }
+    mat3_vec(Rb, nl, n);
+    return 1;
+}
+
 /* One sub-step for one environment.  root: pos3 quat4(xyzw) linvel3 angvel3 (world); dof: (q,qd)
  * interleaved.  cf_body (nb x 3, world) and dof_force (nd) receive the forces of THIS sub-step. */
 static void substep(const OracleModel *m, real h, real *root, real *dof, const real *tau_act,
                     const real *target, real *cf_body, real *cf_torque_body, real *dof_force,
-                    real *Rw_out, real *pw_out, real *vlink_out) {
+                    real *Rw_out, real *pw_out, real *vlink_out, real *obj) {
     const int nl = m->nl;
     static __thread real Xup[MAXL][36], S[MAXL][6], v[MAXL][6], c[MAXL][6], IA[MAXL][36], pA[MAXL][6];
     static __thread real U[MAXL][6], Dd[MAXL], u[MAXL], a[MAXL][6], Rw[MAXL][9], pw[MAXL][3], tau[MAXL], diag[MAXL];
@@ -225,6 +257,16 @@ static void substep(const OracleModel *m, real h, real *root, real *dof, const r
             else if (q > (real)m->upper[i]) { f += lk * ((real)m->upper[i] - qp) - ld * qd; dg += h * ld + h * h * lk; }
         }
         tau[i] = f; diag[i] = dg;
+    }
+    /* fixed tendons: explicit spring/damper on the tendon length outside its range */
+    for (int t = 0; t < m->nten; t++) {
+        int d0 = m->ten_dof[2 * t], d1 = m->ten_dof[2 * t + 1];
+        real c0 = (real)m->ten_coef[2 * t], c1 = (real)m->ten_coef[2 * t + 1];
+        real len = c0 * dof[2 * d0] + c1 * dof[2 * d1], rate = c0 * dof[2 * d0 + 1] + c1 * dof[2 * d1 + 1];
+        real lo = (real)m->ten_range[2 * t], hi = (real)m->ten_range[2 * t + 1], f = 0;
+        if (len > hi) f = -(real)m->ten_k * (len - hi) - (real)m->ten_d * rate;
+        else if (len < lo) f = -(real)m->ten_k * (len - lo) - (real)m->ten_d * rate;
+        tau[d0 + 1] += c0 * f; tau[d1 + 1] += c1 * f;
     }
 
     /* ---- pass 1: kinematics, velocities, bias forces */
@@ -295,6 +337,103 @@ static void substep(const OracleModel *m, real h, real *root, real *dof, const r
         for (int a_ = 0; a_ < 6; a_++) { real s = 0; for (int k = 0; k < 3; k++) s += J[6 * k + a_] * cF0[n][k]; pA[i][a_] -= s; }
     }
 
+    /* ---- the free object: contacts with the articulation (block-Jacobi implicit: each body sees its own
+     * acceleration implicitly, the other's velocity explicitly), with the ground, then its own 6x6 solve */
+    static __thread real oF0[MAXCP + 64][3], oG[MAXCP + 64][9], oJ[MAXCP + 64][18]; static __thread int olink[MAXCP + 64], obody[MAXCP + 64], ocp[MAXCP + 64];
+    int noc = 0;
+    real Ao[36], bo[6], Ro[9];
+    if (m->obj_on && obj) {
+        quat_to_mat(obj + 3, Ro);
+        real Iw[9], T[9], Id[9] = {(real)m->obj_inertia[0], 0, 0, 0, (real)m->obj_inertia[1], 0, 0, 0, (real)m->obj_inertia[2]};
+        mat3_mul(Ro, Id, T);
+        for (int a_ = 0; a_ < 3; a_++) for (int b_ = 0; b_ < 3; b_++) { real s_ = 0; for (int k = 0; k < 3; k++) s_ += T[3 * a_ + k] * Ro[3 * b_ + k]; Iw[3 * a_ + b_] = s_; }
+        memset(Ao, 0, sizeof(Ao));
+        for (int a_ = 0; a_ < 3; a_++) { for (int b_ = 0; b_ < 3; b_++) Ao[6 * a_ + b_] = Iw[3 * a_ + b_]; Ao[6 * (a_ + 3) + a_ + 3] = (real)m->obj_mass; }
+        real Iww[3], gyro[3]; mat3_vec(Iw, obj + 10, Iww); cross3(obj + 10, Iww, gyro);
+        for (int k = 0; k < 3; k++) { bo[k] = -gyro[k]; bo[3 + k] = m->obj_gravity_on ? (real)m->obj_mass * (real)m->gravity[k] : 0; }
+        real okn = (real)m->obj_kn, ocn = (real)m->obj_cn, ogn = ocn + h * okn, hb[3] = {(real)m->obj_half[0], (real)m->obj_half[1], (real)m->obj_half[2]};
+        /* helper macro: one contact at world point pc with normal nrm (direction of the force on the LINK), penetration pen */
+#define OBJ_CONTACT(LI, BI, CPI, PC, NRM, PEN, MU) do {                                                                       \
+            real rcw_[3] = {(PC)[0] - pw[LI][0], (PC)[1] - pw[LI][1], (PC)[2] - pw[LI][2]}, rc_[3], wxr_[3], ul_[3], uw_[3];       \
+            mat3T_vec(Rw[LI], rcw_, rc_); cross3(v[LI], rc_, wxr_);                                                              \
+            for (int k = 0; k < 3; k++) ul_[k] = v[LI][3 + k] + wxr_[k];                                                         \
+            mat3_vec(Rw[LI], ul_, uw_);                                                                                          \
+            real ro_[3] = {(PC)[0] - obj[0], (PC)[1] - obj[1], (PC)[2] - obj[2]}, wo_[3]; cross3(obj + 10, ro_, wo_);            \
+            real rel_[3] = {uw_[0] - obj[7] - wo_[0], uw_[1] - obj[8] - wo_[1], uw_[2] - obj[9] - wo_[2]};                        \
+            real un_ = rel_[0] * (NRM)[0] + rel_[1] * (NRM)[1] + rel_[2] * (NRM)[2];                                             \
+            real Fn_ = okn * (PEN) - ogn * un_;                                                                                  \
+            if (Fn_ > 0 && noc < MAXCP + 64) {                                                                                   \
+                real ut_[3] = {rel_[0] - un_ * (NRM)[0], rel_[1] - un_ * (NRM)[1], rel_[2] - un_ * (NRM)[2]};                    \
+                real gam_ = (MU) * Fn_ / SQRT(ut_[0] * ut_[0] + ut_[1] * ut_[1] + ut_[2] * ut_[2] + (real)(m->vs * m->vs));     \
+                real F0_[3], Gw_[9];                                                                                             \
+                for (int k = 0; k < 3; k++) F0_[k] = Fn_ * (NRM)[k] - gam_ * ut_[k];                                             \
+                for (int a_ = 0; a_ < 3; a_++) for (int b_ = 0; b_ < 3; b_++) Gw_[3 * a_ + b_] = (a_ == b_ ? gam_ : 0) + (ogn - gam_) * (NRM)[a_] * (NRM)[b_]; \
+                real B_[18], rx_[9], J_[18], GJ_[18]; skew(rc_, rx_);                                                            \
+                for (int a_ = 0; a_ < 3; a_++) for (int b_ = 0; b_ < 3; b_++) { B_[6 * a_ + b_] = -rx_[3 * a_ + b_]; B_[6 * a_ + 3 + b_] = (a_ == b_); } \
+                for (int a_ = 0; a_ < 3; a_++) for (int b_ = 0; b_ < 6; b_++) { real s_ = 0; for (int k = 0; k < 3; k++) s_ += Rw[LI][3 * a_ + k] * B_[6 * k + b_]; J_[6 * a_ + b_] = s_; } \
+                for (int a_ = 0; a_ < 3; a_++) for (int b_ = 0; b_ < 6; b_++) { real s_ = 0; for (int k = 0; k < 3; k++) s_ += Gw_[3 * a_ + k] * J_[6 * k + b_]; GJ_[6 * a_ + b_] = s_; } \
+                for (int a_ = 0; a_ < 6; a_++) for (int b_ = 0; b_ < 6; b_++) { real s_ = 0; for (int k = 0; k < 3; k++) s_ += J_[6 * k + a_] * GJ_[6 * k + b_]; IA[LI][6 * a_ + b_] += h * s_; } \
+                for (int a_ = 0; a_ < 6; a_++) { real s_ = 0; for (int k = 0; k < 3; k++) s_ += J_[6 * k + a_] * F0_[k]; pA[LI][a_] -= s_; } \
+                /* object side: Jo = [ -ro^x  1 ] about its COM, world axes */                                                    \
+                real Jo_[18], rox_[9], GJo_[18]; skew(ro_, rox_);                                                                \
+                for (int a_ = 0; a_ < 3; a_++) for (int b_ = 0; b_ < 3; b_++) { Jo_[6 * a_ + b_] = -rox_[3 * a_ + b_]; Jo_[6 * a_ + 3 + b_] = (a_ == b_); } \
+                for (int a_ = 0; a_ < 3; a_++) for (int b_ = 0; b_ < 6; b_++) { real s_ = 0; for (int k = 0; k < 3; k++) s_ += Gw_[3 * a_ + k] * Jo_[6 * k + b_]; GJo_[6 * a_ + b_] = s_; } \
+                for (int a_ = 0; a_ < 6; a_++) for (int b_ = 0; b_ < 6; b_++) { real s_ = 0; for (int k = 0; k < 3; k++) s_ += Jo_[6 * k + a_] * GJo_[6 * k + b_]; Ao[6 * a_ + b_] += h * s_; } \
+                for (int a_ = 0; a_ < 6; a_++) { real s_ = 0; for (int k = 0; k < 3; k++) s_ += Jo_[6 * k + a_] * F0_[k]; bo[a_] -= s_; } \
+                memcpy(oF0[noc], F0_, sizeof(F0_)); memcpy(oG[noc], Gw_, sizeof(Gw_)); memcpy(oJ[noc], J_, sizeof(J_));          \
+                olink[noc] = LI; obody[noc] = BI; ocp[noc] = CPI; noc++;                                                          \
+            }                                                                                                                    \
+        } while (0)
+        /* S1: the articulation's contact spheres against the object's box */
+        for (int n = 0; n < m->ncp; n++) {
+            int i = m->cp_link[n];
+            real lp[3] = {(real)m->cp_pos[3 * n], (real)m->cp_pos[3 * n + 1], (real)m->cp_pos[3 * n + 2]}, wc[3], pen, nrm[3];
+            mat3_vec(Rw[i], lp, wc); for (int k = 0; k < 3; k++) wc[k] += pw[i][k];
+            real rad = (real)m->cp_radius[n];
+            if (!sphere_box(wc, rad, obj, Ro, hb, &pen, nrm)) continue;
+            real pc[3] = {wc[0] - rad * nrm[0], wc[1] - rad * nrm[1], wc[2] - rad * nrm[2]};
+            OBJ_CONTACT(i, m->cp_body[n], n, pc, nrm, pen, (real)m->obj_mu);
+        }
+        /* S2: the object's corners against the articulation's box primitives */
+        for (int b = 0; b < m->nbx; b++) {
+            int i = m->box_link[b];
+            real bq[4] = {(real)m->box_quat[4 * b], (real)m->box_quat[4 * b + 1], (real)m->box_quat[4 * b + 2], (real)m->box_quat[4 * b + 3]}, Rb[9], Rwb[9];
+            real bp[3] = {(real)m->box_pos[3 * b], (real)m->box_pos[3 * b + 1], (real)m->box_pos[3 * b + 2]}, xb[3];
+            real bh[3] = {(real)m->box_half[3 * b], (real)m->box_half[3 * b + 1], (real)m->box_half[3 * b + 2]};
+            quat_to_mat(bq, Rb); mat3_mul(Rw[i], Rb, Rwb); mat3_vec(Rw[i], bp, xb); for (int k = 0; k < 3; k++) xb[k] += pw[i][k];
+            for (int c = 0; c < 8; c++) {
+                real lc[3] = {(c & 1 ? hb[0] : -hb[0]), (c & 2 ? hb[1] : -hb[1]), (c & 4 ? hb[2] : -hb[2])}, pc[3], pen, nout[3];
+                mat3_vec(Ro, lc, pc); for (int k = 0; k < 3; k++) pc[k] += obj[k];
+                if (!sphere_box(pc, 0, xb, Rwb, bh, &pen, nout)) continue;       /* corner inside the link's box */
+                real nrm[3] = {-nout[0], -nout[1], -nout[2]};                  /* force on the LINK pushes it away from the corner */
+                OBJ_CONTACT(i, -1, -1, pc, nrm, pen, (real)m->obj_mu);
+            }
+        }
+#undef OBJ_CONTACT
+        /* S3: the object's corners against the ground */
+        for (int c = 0; c < 8; c++) {
+            real lc[3] = {(c & 1 ? hb[0] : -hb[0]), (c & 2 ? hb[1] : -hb[1]), (c & 4 ? hb[2] : -hb[2])}, ro_[3], pc[3], hgt, nrm[3];
+            mat3_vec(Ro, lc, ro_); for (int k = 0; k < 3; k++) pc[k] = ro_[k] + obj[k];
+            ground(m, pc[0], pc[1], &hgt, nrm);
+            real d = -(pc[2] - hgt) * nrm[2];
+            if (d <= 0) continue;
+            real wo_[3]; cross3(obj + 10, ro_, wo_);
+            real u_[3] = {obj[7] + wo_[0], obj[8] + wo_[1], obj[9] + wo_[2]};
+            real un_ = u_[0] * nrm[0] + u_[1] * nrm[1] + u_[2] * nrm[2], Fn_ = okn * d - ogn * un_;
+            if (Fn_ <= 0) continue;
+            real ut_[3] = {u_[0] - un_ * nrm[0], u_[1] - un_ * nrm[1], u_[2] - un_ * nrm[2]};
+            real gam_ = (real)m->obj_mu * Fn_ / SQRT(ut_[0] * ut_[0] + ut_[1] * ut_[1] + ut_[2] * ut_[2] + (real)(m->vs * m->vs));
+            real F_[3], Gw_[9], Jo_[18], rox_[9], GJo_[18];
+            for (int k = 0; k < 3; k++) F_[k] = Fn_ * nrm[k] - gam_ * ut_[k];
+            for (int a_ = 0; a_ < 3; a_++) for (int b_ = 0; b_ < 3; b_++) Gw_[3 * a_ + b_] = (a_ == b_ ? gam_ : 0) + (ogn - gam_) * nrm[a_] * nrm[b_];
+            skew(ro_, rox_);
+            for (int a_ = 0; a_ < 3; a_++) for (int b_ = 0; b_ < 3; b_++) { Jo_[6 * a_ + b_] = -rox_[3 * a_ + b_]; Jo_[6 * a_ + 3 + b_] = (a_ == b_); }
+            for (int a_ = 0; a_ < 3; a_++) for (int b_ = 0; b_ < 6; b_++) { real s_ = 0; for (int k = 0; k < 3; k++) s_ += Gw_[3 * a_ + k] * Jo_[6 * k + b_]; GJo_[6 * a_ + b_] = s_; }
+            for (int a_ = 0; a_ < 6; a_++) for (int b_ = 0; b_ < 6; b_++) { real s_ = 0; for (int k = 0; k < 3; k++) s_ += Jo_[6 * k + a_] * GJo_[6 * k + b_]; Ao[6 * a_ + b_] += h * s_; }
+            for (int a_ = 0; a_ < 6; a_++) { real s_ = 0; for (int k = 0; k < 3; k++) s_ += Jo_[6 * k + a_] * F_[k]; bo[a_] += s_; }
+        }
+    }
+
     /* ---- pass 2: articulated inertias, leaf -> root */
     for (int i = nl - 1; i >= 1; i--) {
         int p = m->parent[i];
@@ -344,6 +483,41 @@ static void substep(const OracleModel *m, real h, real *root, real *dof, const r
         for (int k = 0; k < 3; k++) arm[k] = (wc[k] - (real)m->cp_radius[n] * nrm[k]) - (pw[i][k] + wb[k]);
         cross3(arm, F, tq);
         for (int k = 0; k < 3; k++) { cf_body[3 * b + k] += F[k]; cf_torque_body[3 * b + k] += tq[k]; }
+    }
+
+    /* ---- hand-object contacts: forces applied to the articulation's bodies (sensors), then the object itself */
+    if (m->obj_on && obj) {
+        for (int n = 0; n < noc && cf_body; n++) {
+            int i = olink[n], b = obody[n];
+            if (b < 0) continue;
+            real Ja[3], F[3];
+            for (int a_ = 0; a_ < 3; a_++) { real s_ = 0; for (int k = 0; k < 6; k++) s_ += oJ[n][6 * a_ + k] * a[i][k]; Ja[a_] = s_; }
+            for (int a_ = 0; a_ < 3; a_++) { real s_ = 0; for (int k = 0; k < 3; k++) s_ += oG[n][3 * a_ + k] * Ja[k]; F[a_] = oF0[n][a_] - h * s_; }
+            /* contact point in world: recover from J (J = Rw [-rc^x 1]) is awkward -> recompute from the sphere */
+            int cpi = ocp[n];
+            real lp[3] = {(real)m->cp_pos[3 * cpi], (real)m->cp_pos[3 * cpi + 1], (real)m->cp_pos[3 * cpi + 2]}, wc[3], pen, nrm[3];
+            real hb[3] = {(real)m->obj_half[0], (real)m->obj_half[1], (real)m->obj_half[2]};
+            mat3_vec(Rw[i], lp, wc); for (int k = 0; k < 3; k++) wc[k] += pw[i][k];
+            sphere_box(wc, (real)m->cp_radius[cpi], obj, Ro, hb, &pen, nrm);
+            real bp[3] = {(real)m->body_pos[3 * b], (real)m->body_pos[3 * b + 1], (real)m->body_pos[3 * b + 2]}, wb[3], arm[3], tq[3];
+            mat3_vec(Rw[i], bp, wb);
+            for (int k = 0; k < 3; k++) arm[k] = (wc[k] - (real)m->cp_radius[cpi] * nrm[k]) - (pw[i][k] + wb[k]);
+            cross3(arm, F, tq);
+            for (int k = 0; k < 3; k++) { cf_body[3 * b + k] += F[k]; cf_torque_body[3 * b + k] += tq[k]; }
+        }
+        real ao[6];
+        spd6_solve(Ao, bo, ao);
+        for (int k = 0; k < 3; k++) { obj[10 + k] += h * ao[k]; obj[7 + k] += h * ao[3 + k]; }
+        for (int k = 0; k < 3; k++) obj[k] += h * obj[7 + k];
+        real w[3] = {obj[10], obj[11], obj[12]};
+        real wn = SQRT(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]), th = wn * h, dq[4];
+        if (wn > 1e-12) { real s_ = SIN(th / 2) / wn; dq[0] = w[0] * s_; dq[1] = w[1] * s_; dq[2] = w[2] * s_; dq[3] = COS(th / 2); }
+        else { dq[0] = w[0] * h / 2; dq[1] = w[1] * h / 2; dq[2] = w[2] * h / 2; dq[3] = 1; }
+        real *q = obj + 3, x = q[0], y = q[1], z = q[2], ww = q[3];
+        real nq[4] = { dq[3] * x + dq[0] * ww + dq[1] * z - dq[2] * y, dq[3] * y - dq[0] * z + dq[1] * ww + dq[2] * x,
+                       dq[3] * z + dq[0] * y - dq[1] * x + dq[2] * ww, dq[3] * ww - dq[0] * x - dq[1] * y - dq[2] * z };
+        real nn = SQRT(nq[0] * nq[0] + nq[1] * nq[1] + nq[2] * nq[2] + nq[3] * nq[3]);
+        for (int k = 0; k < 4; k++) q[k] = nq[k] / nn;
     }
 
     /* ---- root integration (world-frame twist of the root origin) */
@@ -416,7 +590,7 @@ int oracle_real_size(void) { return (int)sizeof(real); }
  * torque about the body origin, from the LAST sub-step. */
 typedef struct {
     const OracleModel *m; int e0, e1; real *root, *dof; const real *tau_act, *target;
-    real *body_state, *contact_force, *sensor, *dof_force;
+    real *body_state, *contact_force, *sensor, *dof_force, *obj;
 } SimJob;
 
 static void *simulate_range(void *arg) {
@@ -428,7 +602,7 @@ static void *simulate_range(void *arg) {
         real *r = j->root + 13 * e, *d = j->dof + 2 * nd * e;
         real Rw[9 * MAXL], pw[3 * MAXL], vl[6 * MAXL];
         for (int s = 0; s < m->substeps; s++)
-            substep(m, h, r, d, j->tau_act ? j->tau_act + nd * e : 0, j->target ? j->target + nd * e : 0, cf, ct, df, Rw, pw, vl);
+            substep(m, h, r, d, j->tau_act ? j->tau_act + nd * e : 0, j->target ? j->target + nd * e : 0, cf, ct, df, Rw, pw, vl, j->obj ? j->obj + 13 * e : 0);
         if (j->dof_force) memcpy(j->dof_force + nd * e, df, sizeof(real) * nd);
         if (j->contact_force) memcpy(j->contact_force + 3 * m->nb * e, cf, sizeof(real) * 3 * m->nb);
         if (j->body_state) { body_states(m, r, d, bs); memcpy(j->body_state + 13 * m->nb * e, bs, sizeof(real) * 13 * m->nb); }
@@ -448,14 +622,23 @@ static void *simulate_range(void *arg) {
 static int g_threads = 1;
 void oracle_set_threads(int n) { g_threads = n < 1 ? 1 : (n > 256 ? 256 : n); }
 
+void oracle_simulate_obj(const OracleModel *m, int nenv, real *root, real *dof, const real *tau_act,
+                          const real *target, real *body_state, real *contact_force, real *sensor,
+                          real *dof_force, real *obj);
 void oracle_simulate(const OracleModel *m, int nenv, real *root, real *dof, const real *tau_act,
                      const real *target, real *body_state, real *contact_force, real *sensor,
                      real *dof_force) {
+    oracle_simulate_obj(m, nenv, root, dof, tau_act, target, body_state, contact_force, sensor, dof_force, 0);
+}
+/* same, with the optional free object per env: obj (nenv,13) pos quat linvel angvel, updated in place */
+void oracle_simulate_obj(const OracleModel *m, int nenv, real *root, real *dof, const real *tau_act,
+                          const real *target, real *body_state, real *contact_force, real *sensor,
+                          real *dof_force, real *obj) {
     int nt = g_threads; if (nt > nenv) nt = nenv > 0 ? nenv : 1;
     SimJob jobs[256]; pthread_t th[256];
     for (int t = 0; t < nt; t++) {
         SimJob j = {m, (int)((long long)nenv * t / nt), (int)((long long)nenv * (t + 1) / nt), root, dof,
-                    tau_act, target, body_state, contact_force, sensor, dof_force};
+                    tau_act, target, body_state, contact_force, sensor, dof_force, obj};
         jobs[t] = j;
     }
     if (nt == 1) { simulate_range(&jobs[0]); return; }
@@ -476,7 +659,7 @@ void oracle_forward_dynamics(const OracleModel *m, const real *root_in, const re
     const int nd = m->nl - 1;
     real r[13], d[2 * MAXL], h = (real)(m->dt / m->substeps);
     memcpy(r, root_in, sizeof(r)); memcpy(d, dof_in, sizeof(real) * 2 * nd);
-    substep(m, h, r, d, tau_act, 0, 0, 0, 0, 0, 0, 0);
+    substep(m, h, r, d, tau_act, 0, 0, 0, 0, 0, 0, 0, 0);
     for (int i = 0; i < nd; i++) qdd[i] = (d[2 * i + 1] - dof_in[2 * i + 1]) / h;
     memcpy(root_after, r, sizeof(r)); memcpy(dof_after, d, sizeof(real) * 2 * nd);
 }

@@ -30,14 +30,28 @@ class _CModel(C.Structure):
                                           "cp_pos", "cp_radius", "cp_mu", "body_pos", "body_quat", "hfield")] + \
                [("hf_nx", C.c_int), ("hf_ny", C.c_int), ("hf_scale", C.c_double), ("hf_ox", C.c_double),
                 ("hf_oy", C.c_double), ("kn", C.c_double), ("cn", C.c_double), ("vs", C.c_double),
-                ("gravity", C.c_double * 3), ("dt", C.c_double)]
+                ("gravity", C.c_double * 3), ("dt", C.c_double),
+                ("obj_on", C.c_int), ("obj_gravity_on", C.c_int), ("nbx", C.c_int), ("pad1", C.c_int),
+                ("obj_mass", C.c_double), ("obj_inertia", C.c_double * 3), ("obj_half", C.c_double * 3),
+                ("obj_kn", C.c_double), ("obj_cn", C.c_double), ("obj_mu", C.c_double),
+                ("box_link", C.c_void_p), ("box_pos", C.c_void_p), ("box_quat", C.c_void_p), ("box_half", C.c_void_p),
+                ("nten", C.c_int), ("pad2", C.c_int), ("ten_dof", C.c_void_p), ("ten_coef", C.c_void_p),
+                ("ten_range", C.c_void_p), ("ten_k", C.c_double), ("ten_d", C.c_double)]
+
+
+def object_contact_gains(mass):
+    """Penalty gains of the hand-object and object-ground contacts (the object is light, so the
+    gains scale with ITS mass; critically damped for the two-body reduced mass)."""
+    kn = 10000.0 * mass
+    return kn, 2.0 * np.sqrt(kn * mass / 4.0)
 
 
 class OracleSim:
     """One articulation model replicated over num_envs independent environments."""
 
     def __init__(self, model, dt, substeps, gravity=(0.0, 0.0, -9.81), ground_mu=1.0, precision="f64",
-                 hfield=None, hf_scale=1.0, hf_origin=(0.0, 0.0), threads=1):
+                 hfield=None, hf_scale=1.0, hf_origin=(0.0, 0.0), threads=1, obj=None, tendons=None,
+                 tendon_k=0.0, tendon_d=0.0):
         self.model, self.prec = model, precision
         self.dtype = np.float64 if precision == "f64" else np.float32
         self.lib = _lib(precision)
@@ -69,10 +83,32 @@ class OracleSim:
         cm.kn, cm.cn, cm.vs = m.contact_kn, m.contact_cn, m.contact_vs
         cm.gravity = (C.c_double * 3)(*gravity)
         cm.dt = dt
+        # free object (ShadowHand's cube): obj = dict(mass, inertia(3), half(3), mu, gravity_on)
+        cm.obj_on = 0
+        if obj is not None:
+            cm.obj_on, cm.obj_gravity_on = 1, int(obj.get("gravity_on", 1))
+            cm.obj_mass = float(obj["mass"])
+            cm.obj_inertia = (C.c_double * 3)(*obj["inertia"]); cm.obj_half = (C.c_double * 3)(*obj["half"])
+            kn, cn = object_contact_gains(cm.obj_mass)
+            cm.obj_kn, cm.obj_cn, cm.obj_mu = kn, cn, float(obj.get("mu", 1.0))
+            bl = getattr(m, "box_link", None)
+            cm.nbx = 0 if bl is None else len(bl)
+            if cm.nbx:
+                cm.box_link = arr("box_link", m.box_link, np.int32)
+                for n in ("box_pos", "box_quat", "box_half"):
+                    setattr(cm, n, arr(n, getattr(m, n), np.float64))
+        cm.nten = 0
+        if tendons:
+            dn = list(m.dof_names)
+            cm.nten = len(tendons)
+            cm.ten_dof = arr("ten_dof", [[dn.index(t["dofs"][0]), dn.index(t["dofs"][1])] for t in tendons], np.int32)
+            cm.ten_coef = arr("ten_coef", [t["coefs"] for t in tendons], np.float64)
+            cm.ten_range = arr("ten_range", [t["range"] for t in tendons], np.float64)
+            cm.ten_k, cm.ten_d = tendon_k, tendon_d
         self.cm = cm
         self.nd, self.nb, self.ns = m.ndof, m.nb, len(m.sensor_body)
 
-    def simulate(self, root, dof, tau=None, target=None):
+    def simulate(self, root, dof, tau=None, target=None, obj=None):
         """In-place gym.simulate(): root (N,13), dof (N,nd,2).  Returns dict of derived outputs."""
         N = root.shape[0]
         assert root.dtype == self.dtype and dof.dtype == self.dtype and root.flags.c_contiguous and dof.flags.c_contiguous
@@ -81,8 +117,11 @@ class OracleSim:
         out = dict(body_state=np.zeros((N, self.nb, 13), self.dtype), contact_force=np.zeros((N, self.nb, 3), self.dtype),
                    sensor=np.zeros((N, max(self.ns, 1), 6), self.dtype), dof_force=np.zeros((N, max(self.nd, 1)), self.dtype))
         p = lambda a: None if a is None else C.c_void_p(a.ctypes.data)
-        self.lib.oracle_simulate(C.byref(self.cm), C.c_int(N), p(root), p(dof), p(tau), p(target),
-                                 p(out["body_state"]), p(out["contact_force"]), p(out["sensor"]), p(out["dof_force"]))
+        if obj is not None:
+            assert obj.dtype == self.dtype and obj.flags.c_contiguous and obj.shape == (N, 13) and self.cm.obj_on
+        self.lib.oracle_simulate_obj(C.byref(self.cm), C.c_int(N), p(root), p(dof), p(tau), p(target),
+                                     p(out["body_state"]), p(out["contact_force"]), p(out["sensor"]),
+                                     p(out["dof_force"]), p(obj))
         out["sensor"] = out["sensor"][:, :self.ns]
         out["dof_force"] = out["dof_force"][:, :self.nd]
         return out
