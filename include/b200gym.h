@@ -27,7 +27,9 @@ extern "C" {
 
 #define B2G_VERSION 1
 #define B2G_MAX_LINKS 32
-#define B2G_MAX_CONTACT_POINTS 64
+#define B2G_MAX_CONTACT_POINTS 96
+#define B2G_MAX_BOXES 4
+#define B2G_MAX_TENDONS 4
 #define B2G_MAX_SENSORS 8
 
 enum {
@@ -59,6 +61,29 @@ typedef struct {
     float contact_kn, contact_cn, contact_vs;
 } b2g_model;
 
+/* Optional extras of an environment with more than one actor (tasks/shadow_hand.py:338-383: hand, object, goal
+ * object).  The articulation stays actor 0; actor `obj_actor` is a free rigid box simulated in contact with the
+ * articulation's contact spheres, its box primitives and the ground; further actors (the goal marker, created with
+ * gravity disabled in its own collision group, shadow_hand.py:281-282,380) are rows of the root-state tensor the
+ * engine never moves.  ROOT_STATE / INITIAL_ROOT then are (N * actors_per_env, 13), env-major like the reference's
+ * actor_root_state tensor (shadow_hand.py:183). */
+typedef struct {
+    int32_t actors_per_env;      /* >= 1 */
+    int32_t obj_actor;           /* row of the free object inside an env's actors, or -1: none */
+    int32_t obj_gravity_on, pad0;
+    float obj_mass, obj_inertia[3], obj_half[3];   /* box, principal inertia about the COM */
+    float obj_kn, obj_cn, obj_mu;                  /* penalty contact gains / friction of every object contact */
+    int32_t nbox;                                  /* box primitives of the articulation (link frame) */
+    int32_t box_link[B2G_MAX_BOXES];
+    float box_pos[B2G_MAX_BOXES][3], box_quat[B2G_MAX_BOXES][4], box_half[B2G_MAX_BOXES][3];
+    /* fixed two-joint tendons with a length limit (open_ai_assets/hand/shared.xml:54-69; stiffness / damping set at
+     * shadow_hand.py:255-266): length = c0 q[d0] + c1 q[d1], spring-damper outside [lo, hi] */
+    int32_t nten;
+    int32_t ten_dof[B2G_MAX_TENDONS][2];
+    float ten_coef[B2G_MAX_TENDONS][2], ten_range[B2G_MAX_TENDONS][2];
+    float ten_k, ten_d;
+} b2g_model_ext;
+
 /* gymapi.SimParams subset that changes the physics (tasks/base/vec_task.py:514-562) */
 typedef struct {
     float dt;
@@ -77,7 +102,7 @@ typedef struct {
 
 /* Tensor slots for b2g_bind().  Shapes in elements; N = num_envs, D = dofs, B = bodies, S = sensors. */
 enum {
-    B2G_T_ROOT_STATE = 0,      /* f32 (N,13)   acquire_actor_root_state_tensor, ant.py:78 */
+    B2G_T_ROOT_STATE = 0,      /* f32 (N*actors_per_env,13)   acquire_actor_root_state_tensor, ant.py:78 */
     B2G_T_DOF_STATE = 1,       /* f32 (N,D,2)  acquire_dof_state_tensor, ant.py:79 */
     B2G_T_DOF_ACTUATION = 2,   /* f32 (N,D)    set_dof_actuation_force_tensor, ant.py:285 */
     B2G_T_DOF_TARGET = 3,      /* f32 (N,D)    set_dof_position_target_tensor, shadow_hand.py:698 */
@@ -175,6 +200,9 @@ typedef struct b2g_sim b2g_sim;
  * (vec_task.py:247,262; ant.py:185-190): N identical single-actor environments. */
 int b2g_create(const b2g_model *model, const b2g_sim_params *params, int32_t num_envs, int32_t device,
                b2g_sim **out);
+/* same with the multi-actor extras (ext may be NULL) */
+int b2g_create_ext(const b2g_model *model, const b2g_model_ext *ext, const b2g_sim_params *params, int32_t num_envs,
+                   int32_t device, b2g_sim **out);
 int b2g_destroy(b2g_sim *sim);
 
 /* gymtorch.wrap_tensor in reverse: hand the engine the device buffer behind a tensor view. */

@@ -76,9 +76,9 @@ __device__ __forceinline__ Tiles prologue(DevModel *sm, uint64_t *mbar, const De
 
 extern __shared__ float4 b2g_dyn_smem[];
 
-template <int L, bool HF, int BLOCK>
-__device__ __forceinline__ Stepper<L, HF, BLOCK> make_stepper(const DevModel *sm, const int16_t *hf, int lane) {
-    Stepper<L, HF, BLOCK> st;
+template <int L, bool HF, int BLOCK, bool OBJ = false>
+__device__ __forceinline__ Stepper<L, HF, BLOCK, OBJ> make_stepper(const DevModel *sm, const int16_t *hf, int lane) {
+    Stepper<L, HF, BLOCK, OBJ> st;
     st.m = sm; st.gr = Ground{sm, hf, sm->cps, -1.f};
     st.slots = &sm->slots[0][0]; st.links = sm->links;
     st.ss = b2g_dyn_smem + threadIdx.x;
@@ -92,6 +92,18 @@ __device__ __forceinline__ void load_root(const float *r, RootState &rs) {
     rs.rq[0] = r[3]; rs.rq[1] = r[4]; rs.rq[2] = r[5]; rs.rq[3] = r[6];
     rs.rv[0] = r[7]; rs.rv[1] = r[8]; rs.rv[2] = r[9];
     rs.rw[0] = r[10]; rs.rw[1] = r[11]; rs.rw[2] = r[12];
+}
+__device__ __forceinline__ void load_obj(const float *r, ObjState &ob) {
+    ob.p[0] = r[0]; ob.p[1] = r[1]; ob.p[2] = r[2];
+    ob.q[0] = r[3]; ob.q[1] = r[4]; ob.q[2] = r[5]; ob.q[3] = r[6];
+    ob.v[0] = r[7]; ob.v[1] = r[8]; ob.v[2] = r[9];
+    ob.w[0] = r[10]; ob.w[1] = r[11]; ob.w[2] = r[12];
+}
+__device__ __forceinline__ void store_obj(float *r, const ObjState &ob) {
+    r[0] = ob.p[0]; r[1] = ob.p[1]; r[2] = ob.p[2];
+    r[3] = ob.q[0]; r[4] = ob.q[1]; r[5] = ob.q[2]; r[6] = ob.q[3];
+    r[7] = ob.v[0]; r[8] = ob.v[1]; r[9] = ob.v[2];
+    r[10] = ob.w[0]; r[11] = ob.w[1]; r[12] = ob.w[2];
 }
 __device__ __forceinline__ void store_root(float *r, const RootState &rs) {
     r[0] = rs.rp[0]; r[1] = rs.rp[1]; r[2] = rs.rp[2];
@@ -114,20 +126,23 @@ __device__ __forceinline__ typename ST::Outputs make_outputs(const DevModel &sm,
 
 // -------------------------------------------------------------------------------------------
 // gym.simulate(): physics only
-template <int L, bool HF, int BLOCK>
+template <int L, bool HF, int BLOCK, bool OBJ = false>
 __global__ void __launch_bounds__(BLOCK) simulate_kernel(const DevModel *__restrict__ gm, const int16_t *__restrict__ hf,
                                                          Buffers B, int N) {
     __shared__ DevModel sm;
     __shared__ alignas(8) uint64_t mbar;
     prologue(&sm, &mbar, gm, nullptr, false, 0, 0, nullptr, nullptr, nullptr, 0, 0);
-    using ST = Stepper<L, HF, BLOCK>;
+    using ST = Stepper<L, HF, BLOCK, OBJ>;
     const int gt = blockIdx.x * BLOCK + threadIdx.x;
     const int env = gt / L, lane = gt % L;
     const bool valid = env < N;
     const int e = valid ? env : N - 1;
     const int nd = sm.nl - 1, NS = sm.ns;
-    ST st = make_stepper<L, HF, BLOCK>(&sm, hf, lane);
-    RootState rs; load_root((const float *)B.p[B2G_T_ROOT_STATE] + 13 * (size_t)e, rs);
+    ST st = make_stepper<L, HF, BLOCK, OBJ>(&sm, hf, lane);
+    float *const root_row = (float *)B.p[B2G_T_ROOT_STATE] + 13 * (size_t)e * sm.root_stride;
+    RootState rs; load_root(root_row, rs);
+    ObjState ob;
+    if (OBJ) load_obj(root_row + 13 * sm.obj_row, ob);
     const float2 *d = (const float2 *)B.p[B2G_T_DOF_STATE] + (size_t)e * nd;
     const float *act = (const float *)B.p[B2G_T_DOF_ACTUATION];
     const float *tgt = (const float *)B.p[B2G_T_DOF_TARGET];
@@ -140,12 +155,13 @@ __global__ void __launch_bounds__(BLOCK) simulate_kernel(const DevModel *__restr
         st.set_joint(s, v.x, v.y, src ? src[(size_t)e * nd + link - 1] : 0.f);
     }
     const typename ST::Outputs o = make_outputs<ST>(sm, B, e, valid);
-    for (int k = 0; k < sm.substeps; k++) st.substep(rs, k == sm.substeps - 1, o);
+    for (int k = 0; k < sm.substeps; k++) st.substep(rs, k == sm.substeps - 1, o, &ob);
     if (!valid) return;
     float2 *dw = (float2 *)B.p[B2G_T_DOF_STATE] + (size_t)e * nd;
 #pragma unroll 1
     for (int s = 0; s < NS; s++) { const int link = st.link_of(s); if (link >= 0) dw[link - 1] = st.get_q(s); }
-    if (lane == 0 && !sm.root_fixed) store_root((float *)B.p[B2G_T_ROOT_STATE] + 13 * (size_t)e, rs);
+    if (lane == 0 && !sm.root_fixed) store_root(root_row, rs);
+    if (OBJ && lane == 0) store_obj(root_row + 13 * sm.obj_row, ob);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -494,7 +510,7 @@ __global__ void __launch_bounds__(128) body_state_kernel(const DevModel *__restr
     if (e >= N) return;
     const int nl = sm.nl, nd = nl - 1;
     float R[MAX_LINKS][9], x[MAX_LINKS][3], wv[MAX_LINKS][3], lv[MAX_LINKS][3];
-    const float *r = (const float *)B.p[B2G_T_ROOT_STATE] + 13 * (size_t)e;
+    const float *r = (const float *)B.p[B2G_T_ROOT_STATE] + 13 * (size_t)e * sm.root_stride;
     const float q0[4] = {r[3], r[4], r[5], r[6]};
     quat_to_mat(q0, R[0]);
     for (int c = 0; c < 3; c++) { x[0][c] = r[c]; lv[0][c] = sm.root_fixed ? 0.f : r[7 + c]; wv[0][c] = sm.root_fixed ? 0.f : r[10 + c]; }
@@ -529,7 +545,11 @@ __global__ void __launch_bounds__(128) body_state_kernel(const DevModel *__restr
             wv[i][c] = wv[p][c] + ((lk.flags & LF_SLIDE) ? 0.f : w[c] * qv.y);
         }
     }
-    float *bs = (float *)B.p[B2G_T_RIGID_BODY_STATE] + 13 * (size_t)e * sm.nb;
+    // bodies of an env: the articulation's, then one per further actor (single rigid bodies: their root rows)
+    const int nb_env = sm.nb + sm.root_stride - 1;
+    float *bs = (float *)B.p[B2G_T_RIGID_BODY_STATE] + 13 * (size_t)e * nb_env;
+    for (int a = 1; a < sm.root_stride; a++)
+        for (int c = 0; c < 13; c++) bs[13 * (sm.nb + a - 1) + c] = r[13 * a + c];
     for (int b = 0; b < sm.nb; b++) {
         const int i = sm.body_link[b];
         float bp[3] = {sm.body_pos[b][0], sm.body_pos[b][1], sm.body_pos[b][2]}, wb[3], wxb[3], Rb[9], Rwb[9], q[4];
@@ -652,7 +672,16 @@ static int pick_lanes(const b2g_model *m, bool single) {
 }
 
 extern "C" int b2g_create(const b2g_model *m, const b2g_sim_params *sp, int32_t num_envs, int32_t device, b2g_sim **out) {
+    return b2g_create_ext(m, nullptr, sp, num_envs, device, out);
+}
+
+extern "C" int b2g_create_ext(const b2g_model *m, const b2g_model_ext *ext, const b2g_sim_params *sp, int32_t num_envs, int32_t device,
+                              b2g_sim **out) {
     if (!m || !sp || !out || num_envs <= 0) return fail(B2G_E_INVALID, "b2g_create: null argument or num_envs <= 0");
+    if (ext && (ext->actors_per_env < 1 || ext->obj_actor >= ext->actors_per_env || ext->obj_actor == 0 || ext->nbox < 0 ||
+                ext->nbox > MAX_BOX || ext->nten < 0 || ext->nten > MAX_TEN))
+        return fail(B2G_E_INVALID, "b2g_create_ext: bad actor / box / tendon counts");
+    if (ext && ext->obj_actor > 0 && sp->hf_samples) return fail(B2G_E_UNSUPPORTED, "b2g_create_ext: the free object needs the ground plane");
     if (m->nl < 1 || m->nl > MAX_LINKS || m->nl - 1 > MAX_SLOTS || m->ncp > MAX_CP || m->nsens > MAX_SENS || m->nb > MAX_LINKS)
         return fail(B2G_E_INVALID, "b2g_create: model exceeds compiled limits (links/contact points/sensors)");
     int ndev = 0;
@@ -675,6 +704,39 @@ extern "C" int b2g_create(const b2g_model *m, const b2g_sim_params *sp, int32_t 
     const char *force1 = getenv("B2G_SINGLE_LANE");
     if (schedule(m, pick_lanes(m, force1 && force1[0] == '1'), h) != 0) { delete s; return fail(B2G_E_INVALID, "b2g_create: the articulation does not fit the slot program limits"); }
     s->lanes = h.lanes;
+    h.root_stride = ext ? ext->actors_per_env : 1;
+    h.obj_on = 0; h.obj_acc = h.obj_pose_acc = -1;
+    if (ext) {
+        if (ext->obj_actor > 0) {
+            h.obj_on = 1; h.obj_row = ext->obj_actor; h.obj_gravity_on = ext->obj_gravity_on;
+            h.obj_mass = ext->obj_mass; h.obj_kn = ext->obj_kn; h.obj_cn = ext->obj_cn; h.obj_mu = ext->obj_mu;
+            for (int c = 0; c < 3; c++) { h.obj_I[c] = ext->obj_inertia[c]; h.obj_half[c] = ext->obj_half[c]; }
+            h.obj_acc = h.nacc; h.obj_pose_acc = h.nacc + 1; h.nacc += 2;
+            // the object's gravity does not follow the articulation's disable_gravity flag (shadow_hand.py:239,279-282)
+            for (int c = 0; c < 3; c++) h.obj_g[c] = ext->obj_gravity_on ? sp->gravity[c] : 0.f;
+        }
+        h.nbox = ext->nbox;
+        for (int b = 0; b < ext->nbox; b++) {
+            h.box_link[b] = ext->box_link[b];
+            const float *q = ext->box_quat[b];
+            float x = q[0], y = q[1], z = q[2], w = q[3], n = sqrtf(x * x + y * y + z * z + w * w);
+            x /= n; y /= n; z /= n; w /= n;
+            const float R[9] = {1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
+                                2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
+                                2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)};
+            memcpy(h.box_R[b], R, sizeof(R));
+            for (int c = 0; c < 3; c++) { h.box_pos[b][c] = ext->box_pos[b][c]; h.box_half[b][c] = ext->box_half[b][c]; }
+        }
+        h.nten = ext->nten; h.ten_k = ext->ten_k; h.ten_d = ext->ten_d;
+        for (int t = 0; t < ext->nten; t++) for (int k = 0; k < 2; k++) {
+            const int link = ext->ten_dof[t][k] + 1;
+            int ref = -1;
+            for (int sl = 0; sl < h.ns && ref < 0; sl++) for (int l = 0; l < h.lanes; l++) if (h.slots[sl][l].link == link) { ref = (l << 8) | sl; break; }
+            if (ref < 0) { delete s; return fail(B2G_E_INVALID, "b2g_create_ext: tendon joint index out of range"); }
+            h.ten_ref[t][k] = ref; h.ten_coef[t][k] = ext->ten_coef[t][k]; h.ten_range[t][k] = ext->ten_range[t][k];
+        }
+        if (h.nten > 0 && !h.obj_on) { delete s; return fail(B2G_E_UNSUPPORTED, "b2g_create_ext: tendons are only compiled into the object-enabled kernels"); }
+    }
     {   // CTA size: the per-thread slot state must fit in shared memory, preferably several CTAs per SM
         const size_t per_thread = ((size_t)h.ns * SLOT_F4 + (size_t)h.nacc * ACC_F4) * sizeof(float4);
         int blk = 128;
@@ -759,10 +821,10 @@ extern "C" int b2g_bind(b2g_sim *s, int32_t slot, void *ptr, size_t bytes) {
     const int N = s->num_envs, nd = s->hm.nl - 1, nb = s->hm.nb, ns = s->hm.nsens;
     size_t need = 0;
     switch (slot) {
-        case B2G_T_ROOT_STATE: case B2G_T_INITIAL_ROOT: need = (size_t)N * 13 * 4; break;
+        case B2G_T_ROOT_STATE: case B2G_T_INITIAL_ROOT: need = (size_t)N * s->hm.root_stride * 13 * 4; break;
         case B2G_T_DOF_STATE: need = (size_t)N * nd * 8; break;
         case B2G_T_DOF_ACTUATION: case B2G_T_DOF_TARGET: case B2G_T_DOF_FORCE: need = (size_t)N * nd * 4; break;
-        case B2G_T_RIGID_BODY_STATE: need = (size_t)N * nb * 13 * 4; break;
+        case B2G_T_RIGID_BODY_STATE: need = (size_t)N * (nb + s->hm.root_stride - 1) * 13 * 4; break;
         case B2G_T_FORCE_SENSOR: need = (size_t)N * ns * 6 * 4; break;
         case B2G_T_NET_CONTACT: need = (size_t)N * nb * 3 * 4; break;
         case B2G_T_REW: case B2G_T_POTENTIALS: case B2G_T_PREV_POTENTIALS: case B2G_T_RESET_COUNT: need = (size_t)N * 4; break;
@@ -814,7 +876,14 @@ extern "C" int b2g_simulate(b2g_sim *s, void *stream) {
     CUDA_TRY(cudaSetDevice(s->device));
     cudaStream_t st = (cudaStream_t)stream;
     const int N = s->num_envs, blk = s->block, grid = (N * s->lanes + blk - 1) / blk;
-    B2G_DISPATCH_LHB(simulate_kernel, s->dm, s->d_hf, s->buf, N);
+    if (s->hm.obj_on) {
+        if (s->lanes == 4 && blk == 128) B2G_LAUNCH((simulate_kernel<4, false, 128, true>), s->dm, s->d_hf, s->buf, N);
+        else if (s->lanes == 4 && blk == 64) B2G_LAUNCH((simulate_kernel<4, false, 64, true>), s->dm, s->d_hf, s->buf, N);
+        else if (s->lanes == 4 && blk == 32) B2G_LAUNCH((simulate_kernel<4, false, 32, true>), s->dm, s->d_hf, s->buf, N);
+        else if (s->lanes == 1 && blk == 32) B2G_LAUNCH((simulate_kernel<1, false, 32, true>), s->dm, s->d_hf, s->buf, N);
+        else return fail(B2G_E_UNSUPPORTED, "no object-enabled kernel instantiated for this (lanes, CTA size) combination");
+    } else
+        B2G_DISPATCH_LHB(simulate_kernel, s->dm, s->d_hf, s->buf, N);
     s->launches++;
     CUDA_TRY(cudaGetLastError());
     return B2G_OK;
@@ -842,6 +911,7 @@ extern "C" int b2g_set_task(b2g_sim *s, const b2g_task_params *t) {
         if (t->num_actions != nd || t->num_obs != 12 + 4 * nd + 6 * s->hm.nsens) return fail(B2G_E_UNSUPPORTED, "humanoid task: observation size does not match the articulation");
     } else return fail(B2G_E_UNSUPPORTED, "b2g_set_task: unknown task id");
     if (t->control_freq_inv < 0) return fail(B2G_E_INVALID, "control_freq_inv < 0");
+    if (s->hm.root_stride != 1) return fail(B2G_E_UNSUPPORTED, "b2g_set_task: single-actor environments only");
     s->task = *t; s->has_task = true; s->has_anymal = false;
     return B2G_OK;
 }
@@ -852,6 +922,7 @@ extern "C" int b2g_set_anymal_task(b2g_sim *s, const b2g_anymal_params *t) {
     if (s->lanes != 4 || s->hm.ns != 3 || nd != 12 || t->num_actions != 12 || t->num_obs != 12 + 3 * nd + 140)
         return fail(B2G_E_UNSUPPORTED, "AnymalTerrain needs the 4-leg x 3-DOF articulation, 12 actions, 188 observations");
     if (t->decimation < 0 || t->control_freq_inv < 0) return fail(B2G_E_INVALID, "negative simulate count");
+    if (s->hm.root_stride != 1) return fail(B2G_E_UNSUPPORTED, "b2g_set_anymal_task: single-actor environments only");
     s->anymal = *t; s->has_anymal = true; s->has_task = false; s->step_counter = 0;
     return B2G_OK;
 }

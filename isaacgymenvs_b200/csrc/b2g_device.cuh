@@ -33,7 +33,9 @@
 namespace b2g {
 
 constexpr int MAX_LINKS = 32;
-constexpr int MAX_CP = 64;
+constexpr int MAX_CP = 96;
+constexpr int MAX_BOX = 4;      // box primitives of the articulation the free object's corners are tested against
+constexpr int MAX_TEN = 4;      // fixed two-joint tendons
 constexpr int MAX_SENS = 8;
 constexpr int MAX_SLOTS = 24;
 constexpr int MAX_LANES = 4;
@@ -93,6 +95,17 @@ struct alignas(16) DevModel {
     int root_acc;         // accumulator index collecting this lane's root children other than slot 0's (-1: none)
     int cross_lane;       // some slot's parent lives in another lane (needs the shared-memory handoff + __syncwarp)
     float ground_mu;      // friction of the ground material (combined per contact as the average, PhysX default)
+    // ---- optional second actor per env: a free box (ShadowHand's cube, shadow_hand.py:372-378) + fixed tendons
+    int obj_on, obj_gravity_on, nbox, nten;
+    int root_stride;      // actors per env in the root-state tensor (row of the articulation = env * root_stride)
+    int obj_row;          // the object's row inside an env's actors
+    int obj_acc, obj_pose_acc;             // accumulator indices: object inertia/bias sum, object pose of the sub-step
+    float obj_mass, obj_I[3], obj_half[3], obj_kn, obj_cn, obj_mu, obj_g[3];
+    float ten_k, ten_d;
+    int box_link[MAX_BOX];
+    float box_pos[MAX_BOX][3], box_R[MAX_BOX][9], box_half[MAX_BOX][3];   // link frame
+    int ten_ref[MAX_TEN][2];               // ((lane << 8) | slot) of the tendon's two joints
+    float ten_coef[MAX_TEN][2], ten_range[MAX_TEN][2];
     int sensor_body[MAX_SENS];
     float sensor_bpos[MAX_SENS][3];        // body-frame origin of the sensor's body in its link frame
     int link_body[MAX_LINKS];              // first body riding on the link (-1: massless virtual link)
@@ -252,6 +265,43 @@ __device__ __forceinline__ void sym6_solve(const float IA[21], const float ba[3]
     xa[0] = x[0]; xa[1] = x[1]; xa[2] = x[2]; xl[0] = x[3]; xl[1] = x[4]; xl[2] = x[5];
 }
 
+// sphere (centre cen, radius rad) against a box (centre xb, axes Rb, half sizes hb), all in one frame:
+// penetration and the unit normal from the box towards the sphere.  rad = 0 tests a point (a box corner).
+__device__ __forceinline__ bool sphere_box(const float cen[3], float rad, const float xb[3], const float Rb[9], const float hb[3],
+                                           float &pen, float n[3]) {
+    const float d[3] = {cen[0] - xb[0], cen[1] - xb[1], cen[2] - xb[2]};
+    float p[3]; matTvec(Rb, d, p);
+    if (fabsf(p[0]) > hb[0] + rad || fabsf(p[1]) > hb[1] + rad || fabsf(p[2]) > hb[2] + rad) return false;
+    float e[3], nl[3] = {0.f, 0.f, 0.f};
+    bool inside = true;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { const float q = fminf(fmaxf(p[k], -hb[k]), hb[k]); inside = inside && (q == p[k]); e[k] = p[k] - q; }
+    if (!inside) {
+        const float d2 = dot3(e, e);
+        if (d2 >= rad * rad) return false;
+        const float inv = rsqrtf(d2);
+        pen = rad - d2 * inv; nl[0] = e[0] * inv; nl[1] = e[1] * inv; nl[2] = e[2] * inv;
+    } else {
+        int ax = 0; float best = hb[0] - fabsf(p[0]);
+#pragma unroll
+        for (int k = 1; k < 3; k++) { const float m_ = hb[k] - fabsf(p[k]); if (m_ < best) { best = m_; ax = k; } }
+        pen = rad + best;
+        const float sg = p[ax] >= 0.f ? 1.f : -1.f;
+        nl[0] = ax == 0 ? sg : 0.f; nl[1] = ax == 1 ? sg : 0.f; nl[2] = ax == 2 ? sg : 0.f;
+    }
+    matvec(Rb, nl, n);
+    return true;
+}
+// h * J^T G J of a point contact at r (about O) with G = gam*1 + (gn-gam) n n^T, added to a packed 6x6
+__device__ __forceinline__ void contact_inertia(float IA[21], float h, float gam, float gn, const float r[3], const float n[3]) {
+    const float hgam = h * gam;
+    const float jx[3] = {0.f, r[2], -r[1]}, jy[3] = {-r[2], 0.f, r[0]}, jz[3] = {r[1], -r[0], 0.f};
+    const float ex[3] = {1.f, 0.f, 0.f}, ey[3] = {0.f, 1.f, 0.f}, ez[3] = {0.f, 0.f, 1.f};
+    sym6_rank1(IA, hgam, jx, ex); sym6_rank1(IA, hgam, jy, ey); sym6_rank1(IA, hgam, jz, ez);
+    float rxn[3]; cross(r, n, rxn);
+    sym6_rank1(IA, h * (gn - gam), rxn, n);
+}
+
 struct Ground {
     const DevModel *m;
     const int16_t *hf;
@@ -376,8 +426,14 @@ constexpr int ACC_F4 = 7;     // a parked articulated inertia + bias: 27 floats
 struct RootState {            // replicated on the L lanes of the env
     float rp[3], rq[4], rv[3], rw[3];
 };
+struct ObjState {             // the free object (world frame, at its COM), replicated on the L lanes
+    float p[3], q[4], v[3], w[3];
+};
+struct ObjPose {              // the object at the start of the sub-step, as the contacts see it: about O, world axes
+    float Ro[9], c[3], w[3], vO[3];
+};
 
-template <int L, bool HF, int BLOCK>
+template <int L, bool HF, int BLOCK, bool OBJ = false>
 struct Stepper {
     const DevModel *m;        // header (scalars, sensor tables)
     const SlotRec *slots;     // [ns][MAX_LANES]
@@ -397,7 +453,7 @@ struct Stepper {
 
     __device__ __forceinline__ void set_joint(int s, float q, float qd, float act) const {
         float4 v = S4(s, 6); v.z = q; v.w = qd; S4(s, 6) = v;
-        float4 u = S4(s, 7); u.x = act; S4(s, 7) = u;
+        S4(s, 7) = make_float4(act, 0.f, 0.f, 0.f);     // .w: extra explicit joint force (tendons), zero unless set per sub-step
     }
     __device__ __forceinline__ void set_act(int s, float act) const { float4 u = S4(s, 7); u.x = act; S4(s, 7) = u; }
     __device__ __forceinline__ void set_q(int s, float q, float qd) const { float4 v = S4(s, 6); v.z = q; v.w = qd; S4(s, 6) = v; }
@@ -442,13 +498,29 @@ struct Stepper {
         bool write;         // env index valid
     };
 
-    __device__ __forceinline__ void substep(RootState &rs, const bool LAST, const Outputs &o) const {
+    // ================= pass 1: kinematics, velocities, joint forces (root -> leaves).  Also run on its own after
+    // the last sub-step by tasks that read link poses (fingertip states, shadow_hand.py:456-457)
+    __device__ __forceinline__ void pass1(const RootState &rs) const {
         const float h = m->h;
         const int NS = m->ns;
-        const float g[3] = {m->g[0], m->g[1], m->g[2]};
-        const bool fixed = m->root_fixed != 0;
-
-        // ================= pass 1: kinematics, velocities, joint forces (root -> leaves)
+        if (OBJ && m->nten > 0) {
+            // fixed tendons (shared.xml:54-69): penalty spring-damper on the tendon length outside its range,
+            // explicit; each end's lane computes the force of its own joint
+            lane_sync();
+#pragma unroll 1
+            for (int t = 0; t < m->nten; t++) {
+                const int r0 = m->ten_ref[t][0], r1 = m->ten_ref[t][1];
+                if ((r0 >> 8) != lane && (r1 >> 8) != lane) continue;
+                const float4 a = S4x(r0 >> 8, r0 & 255, 6), b = S4x(r1 >> 8, r1 & 255, 6);
+                const float c0 = m->ten_coef[t][0], c1 = m->ten_coef[t][1];
+                const float len = c0 * a.z + c1 * b.z, rate = c0 * a.w + c1 * b.w;
+                float f = 0.f;
+                if (len > m->ten_range[t][1]) f = -m->ten_k * (len - m->ten_range[t][1]) - m->ten_d * rate;
+                else if (len < m->ten_range[t][0]) f = -m->ten_k * (len - m->ten_range[t][0]) - m->ten_d * rate;
+                if ((r0 >> 8) == lane) { float4 u = S4(r0 & 255, 7); u.w = c0 * f; S4(r0 & 255, 7) = u; }
+                if ((r1 >> 8) == lane) { float4 u = S4(r1 & 255, 7); u.w = c1 * f; S4(r1 & 255, 7) = u; }
+            }
+        }
         {
             float Rc[9], xc[3], vwc[3], vlc[3];      // the slot just finished; starts as the root (parent of slot 0)
             root_pose(rs, Rc, vwc, vlc);
@@ -473,7 +545,8 @@ struct Stepper {
                     }
                     const float4 jq = S4(s, 6);
                     const float q = jq.z, qd = jq.w;
-                    const float act = S4(s, 7).x;
+                    const float4 k7in = S4(s, 7);
+                    const float act = k7in.x;
                     float Rt[9], w[3], sl[3];
                     if (lk.flags & LF_R0_IDENTITY) {
 #pragma unroll
@@ -519,6 +592,7 @@ struct Stepper {
                     } else {
                         f += fminf(fmaxf(act, -lk.effort), lk.effort);
                     }
+                    if (OBJ) f += k7in.w;
                     if (lk.flags & LF_LIMITED) {
                         if (q < lk.lower) { f += lk.limit_k * (lk.lower - qp) - lk.limit_d * qd; dg += h * lk.limit_d + h * h * lk.limit_k; }
                         else if (q > lk.upper) { f += lk.limit_k * (lk.upper - qp) - lk.limit_d * qd; dg += h * lk.limit_d + h * h * lk.limit_k; }
@@ -533,6 +607,217 @@ struct Stepper {
                 }
                 lane_sync();
             }
+        }
+    }
+
+    // ---- the free object as the sub-step's contacts see it (kept in this thread's accumulator column)
+    __device__ __forceinline__ void obj_store_pose(const RootState &rs, const ObjState &ob) const {
+        float Ro[9]; quat_to_mat(ob.q, Ro);
+        const float c[3] = {ob.p[0] - rs.rp[0], ob.p[1] - rs.rp[1], ob.p[2] - rs.rp[2]};
+        float wxc[3]; cross(ob.w, c, wxc);
+        const int a = m->obj_pose_acc;
+        A4(a, 0) = make_float4(Ro[0], Ro[1], Ro[2], Ro[3]);
+        A4(a, 1) = make_float4(Ro[4], Ro[5], Ro[6], Ro[7]);
+        A4(a, 2) = make_float4(Ro[8], c[0], c[1], c[2]);
+        A4(a, 3) = make_float4(ob.w[0], ob.w[1], ob.w[2], ob.v[0] - wxc[0]);
+        A4(a, 4) = make_float4(ob.v[1] - wxc[1], ob.v[2] - wxc[2], 0.f, 0.f);
+    }
+    __device__ __forceinline__ void obj_load_pose(ObjPose &P) const {
+        const int ai = m->obj_pose_acc;
+        const float4 a = A4(ai, 0), b = A4(ai, 1), c = A4(ai, 2), d = A4(ai, 3), e = A4(ai, 4);
+        P.Ro[0] = a.x; P.Ro[1] = a.y; P.Ro[2] = a.z; P.Ro[3] = a.w; P.Ro[4] = b.x; P.Ro[5] = b.y; P.Ro[6] = b.z; P.Ro[7] = b.w; P.Ro[8] = c.x;
+        P.c[0] = c.y; P.c[1] = c.z; P.c[2] = c.w; P.w[0] = d.x; P.w[1] = d.y; P.w[2] = d.z; P.vO[0] = d.w; P.vO[1] = e.x; P.vO[2] = e.y;
+    }
+    // one hand-object contact at r (about O), n = unit normal of the force on the LINK, pen = penetration.
+    // ACCUM: the link gets h J^T G J and -J^T F0 (IA, pa, pl); the object, whose J about O is the same, gets the same
+    // inertia term and the opposite force in its accumulator (block-Jacobi: each body implicit in its own acceleration).
+    // !ACCUM: the force applied to the link over the sub-step, F0 - h G (J a_link), and its torque about the link origin.
+    template <bool ACCUM>
+    __device__ __forceinline__ void obj_contact_point(const ObjPose &P, const float r[3], const float n[3], float pen,
+                                                      const float x[3], const float vw[3], const float vl[3],
+                                                      float IA[21], float pa[3], float pl[3],
+                                                      const float aw[3], const float al[3], float F[3], float T[3]) const {
+        const float h = m->h, gn = m->obj_cn + h * m->obj_kn;
+        float wxr[3], oxr[3]; cross(vw, r, wxr); cross(P.w, r, oxr);
+        const float rel[3] = {vl[0] + wxr[0] - P.vO[0] - oxr[0], vl[1] + wxr[1] - P.vO[1] - oxr[1], vl[2] + wxr[2] - P.vO[2] - oxr[2]};
+        const float un = dot3(rel, n);
+        const float Fn = m->obj_kn * pen - gn * un;
+        if (Fn <= 0.f) return;
+        const float ut[3] = {rel[0] - un * n[0], rel[1] - un * n[1], rel[2] - un * n[2]};
+        const float gam = m->obj_mu * Fn * rsqrtf(dot3(ut, ut) + m->vs2);
+        const float F0[3] = {Fn * n[0] - gam * ut[0], Fn * n[1] - gam * ut[1], Fn * n[2] - gam * ut[2]};
+        if (ACCUM) {
+            float dM[21];
+#pragma unroll
+            for (int c = 0; c < 21; c++) dM[c] = 0.f;
+            contact_inertia(dM, h, gam, gn, r, n);
+            float rxF[3]; cross(r, F0, rxF);
+#pragma unroll
+            for (int c = 0; c < 21; c++) IA[c] += dM[c];
+#pragma unroll
+            for (int c = 0; c < 3; c++) { pa[c] -= rxF[c]; pl[c] -= F0[c]; }
+            const int ai = m->obj_acc;
+            float t[28];
+#pragma unroll
+            for (int c = 0; c < 21; c++) t[c] = dM[c];
+            t[21] = rxF[0]; t[22] = rxF[1]; t[23] = rxF[2]; t[24] = F0[0]; t[25] = F0[1]; t[26] = F0[2]; t[27] = 0.f;
+#pragma unroll
+            for (int k = 0; k < ACC_F4; k++) {
+                float4 v = A4(ai, k);
+                v.x += t[4 * k]; v.y += t[4 * k + 1]; v.z += t[4 * k + 2]; v.w += t[4 * k + 3];
+                A4(ai, k) = v;
+            }
+        } else {
+            float axr[3]; cross(aw, r, axr);
+            const float Ja[3] = {al[0] + axr[0], al[1] + axr[1], al[2] + axr[2]};
+            const float Jan = dot3(Ja, n);
+            float Fk[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) Fk[c] = F0[c] - h * (gam * Ja[c] + (gn - gam) * Jan * n[c]);
+            const float rl[3] = {r[0] - x[0], r[1] - x[1], r[2] - x[2]};
+            float tq[3]; cross(rl, Fk, tq);
+#pragma unroll
+            for (int c = 0; c < 3; c++) { F[c] += Fk[c]; T[c] += tq[c]; }
+        }
+    }
+    // all contacts between one link and the object: the link's spheres against the object's box, the object's
+    // corners against the link's box primitives
+    template <bool ACCUM>
+    __device__ __forceinline__ void obj_link_contacts(const LinkC &lk, int li, const float R[9], const float x[3],
+                                                      const float vw[3], const float vl[3], float IA[21], float pa[3], float pl[3],
+                                                      const float aw[3], const float al[3], float F[3], float T[3],
+                                                      int cp_first, int cp_step) const {
+        ObjPose P; obj_load_pose(P);
+        const float hb[3] = {m->obj_half[0], m->obj_half[1], m->obj_half[2]};
+#pragma unroll 1
+        for (int k = lk.cp_begin + cp_first; k < lk.cp_end; k += cp_step) {
+            const CpC &cp = gr.cps[k];
+            float pc[3]; const float lp[3] = {cp.pos[0], cp.pos[1], cp.pos[2]};
+            matvec(R, lp, pc);
+            pc[0] += x[0]; pc[1] += x[1]; pc[2] += x[2];
+            float pen, n[3];
+            if (!sphere_box(pc, cp.radius, P.c, P.Ro, hb, pen, n)) continue;
+            const float r[3] = {pc[0] - cp.radius * n[0], pc[1] - cp.radius * n[1], pc[2] - cp.radius * n[2]};
+            obj_contact_point<ACCUM>(P, r, n, pen, x, vw, vl, IA, pa, pl, aw, al, F, T);
+        }
+        if (cp_first != 0) return;
+#pragma unroll 1
+        for (int b = 0; b < m->nbox; b++) {
+            if (m->box_link[b] != li) continue;
+            float Rwb[9], xb[3];
+            matmul(R, m->box_R[b], Rwb);
+            const float bp[3] = {m->box_pos[b][0], m->box_pos[b][1], m->box_pos[b][2]};
+            matvec(R, bp, xb);
+            xb[0] += x[0]; xb[1] += x[1]; xb[2] += x[2];
+            const float bh[3] = {m->box_half[b][0], m->box_half[b][1], m->box_half[b][2]};
+#pragma unroll 1
+            for (int cn = 0; cn < 8; cn++) {
+                const float lc[3] = {(cn & 1) ? hb[0] : -hb[0], (cn & 2) ? hb[1] : -hb[1], (cn & 4) ? hb[2] : -hb[2]};
+                float pc[3]; matvec(P.Ro, lc, pc);
+                pc[0] += P.c[0]; pc[1] += P.c[1]; pc[2] += P.c[2];
+                float pen, nout[3];
+                if (!sphere_box(pc, 0.f, xb, Rwb, bh, pen, nout)) continue;      // the corner is inside the link's box
+                const float n[3] = {-nout[0], -nout[1], -nout[2]};              // the link is pushed away from the corner
+                obj_contact_point<ACCUM>(P, pc, n, pen, x, vw, vl, IA, pa, pl, aw, al, F, T);
+            }
+        }
+    }
+    // the object's own dynamics for this sub-step: summed contact terms + ground + rigid-body terms -> 6x6 solve -> integrate
+    __device__ __forceinline__ void obj_advance(const RootState &rs, ObjState &ob) const {
+        const float h = m->h;
+        ObjPose P; obj_load_pose(P);
+        float Io[21], pao[3], plo[3];
+        {
+            float t[28];
+#pragma unroll
+            for (int k = 0; k < ACC_F4; k++) { const float4 v = A4(m->obj_acc, k); t[4 * k] = v.x; t[4 * k + 1] = v.y; t[4 * k + 2] = v.z; t[4 * k + 3] = v.w; }
+#pragma unroll
+            for (int c = 0; c < 21; c++) Io[c] = t[c];
+#pragma unroll
+            for (int c = 0; c < 3; c++) { pao[c] = t[21 + c]; plo[c] = t[24 + c]; }
+        }
+        // corners against the ground plane, dealt round-robin to the lanes
+        const float gn = m->obj_cn + h * m->obj_kn;
+#pragma unroll 1
+        for (int cn = lane; cn < 8; cn += L) {
+            const float lc[3] = {(cn & 1) ? m->obj_half[0] : -m->obj_half[0], (cn & 2) ? m->obj_half[1] : -m->obj_half[1], (cn & 4) ? m->obj_half[2] : -m->obj_half[2]};
+            float r[3]; matvec(P.Ro, lc, r);
+            r[0] += P.c[0]; r[1] += P.c[1]; r[2] += P.c[2];
+            const float d = -(rs.rp[2] + r[2]);
+            if (d <= 0.f) continue;
+            float oxr[3]; cross(P.w, r, oxr);
+            const float u[3] = {P.vO[0] + oxr[0], P.vO[1] + oxr[1], P.vO[2] + oxr[2]};
+            const float Fn = m->obj_kn * d - gn * u[2];
+            if (Fn <= 0.f) continue;
+            const float gam = m->obj_mu * Fn * rsqrtf(u[0] * u[0] + u[1] * u[1] + m->vs2);
+            const float F0[3] = {-gam * u[0], -gam * u[1], Fn}, ez[3] = {0.f, 0.f, 1.f};
+            contact_inertia(Io, h, gam, gn, r, ez);
+            float rxF[3]; cross(r, F0, rxF);
+#pragma unroll
+            for (int c = 0; c < 3; c++) { pao[c] -= rxF[c]; plo[c] -= F0[c]; }
+        }
+#pragma unroll
+        for (int c = 0; c < 21; c++) Io[c] = lane_sum<L>(Io[c]);
+#pragma unroll
+        for (int c = 0; c < 3; c++) { pao[c] = lane_sum<L>(pao[c]); plo[c] = lane_sum<L>(plo[c]); }
+        {   // rigid-body terms about O: Icw = Ro diag(I) Ro^T
+            const float *Ro = P.Ro, i0 = m->obj_I[0], i1 = m->obj_I[1], i2 = m->obj_I[2];
+            float Icw[6];
+            Icw[0] = i0 * Ro[0] * Ro[0] + i1 * Ro[1] * Ro[1] + i2 * Ro[2] * Ro[2];
+            Icw[1] = i0 * Ro[3] * Ro[3] + i1 * Ro[4] * Ro[4] + i2 * Ro[5] * Ro[5];
+            Icw[2] = i0 * Ro[6] * Ro[6] + i1 * Ro[7] * Ro[7] + i2 * Ro[8] * Ro[8];
+            Icw[3] = i0 * Ro[0] * Ro[3] + i1 * Ro[1] * Ro[4] + i2 * Ro[2] * Ro[5];
+            Icw[4] = i0 * Ro[0] * Ro[6] + i1 * Ro[1] * Ro[7] + i2 * Ro[2] * Ro[8];
+            Icw[5] = i0 * Ro[3] * Ro[6] + i1 * Ro[4] * Ro[7] + i2 * Ro[5] * Ro[8];
+            const float go[3] = {m->obj_g[0], m->obj_g[1], m->obj_g[2]};
+            float I[21], qa[3], ql[3];
+            spatial_inertia(m->obj_mass, 1.f, Icw, P.c, P.w, P.vO, go, I, qa, ql);
+#pragma unroll
+            for (int c = 0; c < 21; c++) Io[c] += I[c];
+#pragma unroll
+            for (int c = 0; c < 3; c++) { pao[c] += qa[c]; plo[c] += ql[c]; }
+        }
+        float ao_w[3], ao_l[3];
+        const float ba[3] = {-pao[0], -pao[1], -pao[2]}, bl[3] = {-plo[0], -plo[1], -plo[2]};
+        sym6_solve(Io, ba, bl, ao_w, ao_l);
+        // classical acceleration of the COM: a_c = a_O + alpha x c + w x v_c
+        float axc[3], wxv[3]; cross(ao_w, P.c, axc); cross(ob.w, ob.v, wxv);
+#pragma unroll
+        for (int c = 0; c < 3; c++) { ob.w[c] += h * ao_w[c]; ob.v[c] += h * (ao_l[c] + axc[c] + wxv[c]); }
+#pragma unroll
+        for (int c = 0; c < 3; c++) ob.p[c] += h * ob.v[c];
+        integrate_quat(ob.q, ob.w, h);
+    }
+    __device__ __forceinline__ static void integrate_quat(float q[4], const float w[3], float h) {
+        const float wn2 = dot3(w, w);
+        float dq[4];
+        if (wn2 > 1e-24f) {
+            const float wn = sqrtf(wn2);
+            float sn, cs; b2g_sincos(0.5f * wn * h, &sn, &cs);
+            const float k = sn / wn;
+            dq[0] = w[0] * k; dq[1] = w[1] * k; dq[2] = w[2] * k; dq[3] = cs;
+        } else { dq[0] = 0.5f * h * w[0]; dq[1] = 0.5f * h * w[1]; dq[2] = 0.5f * h * w[2]; dq[3] = 1.f; }
+        const float qx = q[0], qy = q[1], qz = q[2], qw = q[3];
+        const float nq[4] = {dq[3] * qx + dq[0] * qw + dq[1] * qz - dq[2] * qy,
+                             dq[3] * qy - dq[0] * qz + dq[1] * qw + dq[2] * qx,
+                             dq[3] * qz + dq[0] * qy - dq[1] * qx + dq[2] * qw,
+                             dq[3] * qw - dq[0] * qx - dq[1] * qy - dq[2] * qz};
+        const float inv = rsqrtf(nq[0] * nq[0] + nq[1] * nq[1] + nq[2] * nq[2] + nq[3] * nq[3]);
+#pragma unroll
+        for (int c = 0; c < 4; c++) q[c] = nq[c] * inv;
+    }
+
+    __device__ __forceinline__ void substep(RootState &rs, const bool LAST, const Outputs &o, ObjState *ob = nullptr) const {
+        const float h = m->h;
+        const int NS = m->ns;
+        const float g[3] = {m->g[0], m->g[1], m->g[2]};
+        const bool fixed = m->root_fixed != 0;
+
+        pass1(rs);
+        if (OBJ) {
+            obj_store_pose(rs, *ob);
+#pragma unroll
+            for (int k = 0; k < ACC_F4; k++) A4(m->obj_acc, k) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
 
         // ================= pass 2: articulated inertias (leaves -> root)
@@ -562,6 +847,7 @@ struct Stepper {
                     link_inertia(lk, lk.mass, 1.f, R, x, vw, vl, g, I, qa, ql);
                     float dummy[3];
                     link_contacts<true, HF>(m, gr, lk, rs.rp, R, x, vw, vl, I, qa, ql, dummy, dummy, dummy, dummy, 0, 1);
+                    if (OBJ) obj_link_contacts<true>(lk, sr.link, R, x, vw, vl, I, qa, ql, dummy, dummy, dummy, dummy, 0, 1);
                     if (carry) {
 #pragma unroll
                         for (int c = 0; c < 21; c++) I[c] += IA[c];
@@ -645,6 +931,7 @@ struct Stepper {
             root_pose(rs, Rr, vwr, vlr);
             link_inertia(lk, mine ? lk.mass : 0.f, mine ? 1.f : 0.f, Rr, xr, vwr, vlr, g, I, qa, ql);
             link_contacts<true, HF>(m, gr, lk, rs.rp, Rr, xr, vwr, vlr, I, qa, ql, dummy, dummy, dummy, dummy, lane, L);
+            if (OBJ) obj_link_contacts<true>(lk, 0, Rr, xr, vwr, vlr, I, qa, ql, dummy, dummy, dummy, dummy, lane, L);
 #pragma unroll
             for (int c = 0; c < 21; c++) IA[c] += I[c];               // IA holds slot 0's contribution (or zeros)
 #pragma unroll
@@ -672,6 +959,7 @@ struct Stepper {
             if (LAST) {
                 float F[3] = {0.f, 0.f, 0.f}, T[3] = {0.f, 0.f, 0.f};
                 link_contacts<false, HF>(m, gr, lk, rs.rp, Rr, xr, vwr, vlr, I, qa, ql, awr, alr, F, T, lane, L);
+                if (OBJ) obj_link_contacts<false>(lk, 0, Rr, xr, vwr, vlr, I, qa, ql, awr, alr, F, T, lane, L);
 #pragma unroll
                 for (int c = 0; c < 3; c++) { F[c] = lane_sum<L>(F[c]); T[c] = lane_sum<L>(T[c]); }
                 if (lane == 0) emit_wrench(0, lk, Rr, F, T, o);
@@ -720,6 +1008,7 @@ struct Stepper {
                             float R[9], x[3], F[3] = {0.f, 0.f, 0.f}, T[3] = {0.f, 0.f, 0.f}, dI[1], d3[3];
                             load_pose(s, R, x, vw, vl);
                             link_contacts<false, HF>(m, gr, lk, rs.rp, R, x, vw, vl, dI, d3, d3, awc, alc, F, T, 0, 1);
+                            if (OBJ) obj_link_contacts<false>(lk, li, R, x, vw, vl, dI, d3, d3, awc, alc, F, T, 0, 1);
                             emit_wrench(li, lk, R, F, T, o);
                         } else if (lk.sensor >= 0 || (o.net_contact && m->link_body[li] >= 0)) {
                             float R[9], x[3]; const float z[3] = {0.f, 0.f, 0.f};
@@ -736,6 +1025,8 @@ struct Stepper {
             }
         }
 
+        if (OBJ) obj_advance(rs, *ob);
+
         // ================= root integration (classical acceleration of the origin = spatial + w x v)
         if (!fixed) {
             float wxv[3]; cross(rs.rw, rs.rv, wxv);
@@ -743,22 +1034,7 @@ struct Stepper {
             for (int c = 0; c < 3; c++) { rs.rw[c] += h * awr[c]; rs.rv[c] += h * (alr[c] + wxv[c]); }
 #pragma unroll
             for (int c = 0; c < 3; c++) rs.rp[c] += h * rs.rv[c];
-            const float wn2 = dot3(rs.rw, rs.rw);
-            float dq[4];
-            if (wn2 > 1e-24f) {
-                const float wn = sqrtf(wn2);
-                float sn, cs; b2g_sincos(0.5f * wn * h, &sn, &cs);
-                const float k = sn / wn;
-                dq[0] = rs.rw[0] * k; dq[1] = rs.rw[1] * k; dq[2] = rs.rw[2] * k; dq[3] = cs;
-            } else { dq[0] = 0.5f * h * rs.rw[0]; dq[1] = 0.5f * h * rs.rw[1]; dq[2] = 0.5f * h * rs.rw[2]; dq[3] = 1.f; }
-            const float qx = rs.rq[0], qy = rs.rq[1], qz = rs.rq[2], qw = rs.rq[3];
-            const float nq[4] = {dq[3] * qx + dq[0] * qw + dq[1] * qz - dq[2] * qy,
-                                 dq[3] * qy - dq[0] * qz + dq[1] * qw + dq[2] * qx,
-                                 dq[3] * qz + dq[0] * qy - dq[1] * qx + dq[2] * qw,
-                                 dq[3] * qw - dq[0] * qx - dq[1] * qy - dq[2] * qz};
-            const float inv = rsqrtf(nq[0] * nq[0] + nq[1] * nq[1] + nq[2] * nq[2] + nq[3] * nq[3]);
-#pragma unroll
-            for (int c = 0; c < 4; c++) rs.rq[c] = nq[c] * inv;
+            integrate_quat(rs.rq, rs.rw, h);
         }
     }
 
@@ -781,6 +1057,12 @@ struct Stepper {
         Icw[3] = T_[0] * R[3] + T_[1] * R[4] + T_[2] * R[5];
         Icw[4] = T_[0] * R[6] + T_[1] * R[7] + T_[2] * R[8];
         Icw[5] = T_[3] * R[6] + T_[4] * R[7] + T_[5] * R[8];
+        spatial_inertia(mass, sc, Icw, cw_, vw, vl, g, I, pa, pl);
+    }
+    // same from the rotational inertia about the COM in world axes (Icw) and the COM position about O (cw_)
+    __device__ __forceinline__ static void spatial_inertia(float mass, float sc, const float Icw[6], const float cw_[3],
+                                                           const float vw[3], const float vl[3], const float g[3],
+                                                           float I[21], float pa[3], float pl[3]) {
         const float hm[3] = {mass * cw_[0], mass * cw_[1], mass * cw_[2]};
         const float c2 = dot3(cw_, cw_);
         I[0] = sc * Icw[0] + mass * (c2 - cw_[0] * cw_[0]);

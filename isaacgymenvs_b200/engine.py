@@ -51,6 +51,52 @@ class CModel(C.Structure):
                [("contact_kn", C.c_float), ("contact_cn", C.c_float), ("contact_vs", C.c_float)]
 
 
+class CModelExt(C.Structure):
+    _fields_ = [("actors_per_env", C.c_int32), ("obj_actor", C.c_int32), ("obj_gravity_on", C.c_int32), ("pad0", C.c_int32),
+                ("obj_mass", C.c_float), ("obj_inertia", C.c_float * 3), ("obj_half", C.c_float * 3),
+                ("obj_kn", C.c_float), ("obj_cn", C.c_float), ("obj_mu", C.c_float),
+                ("nbox", C.c_int32), ("box_link", C.c_int32 * 4), ("box_pos", (C.c_float * 3) * 4),
+                ("box_quat", (C.c_float * 4) * 4), ("box_half", (C.c_float * 3) * 4),
+                ("nten", C.c_int32), ("ten_dof", (C.c_int32 * 2) * 4), ("ten_coef", (C.c_float * 2) * 4),
+                ("ten_range", (C.c_float * 2) * 4), ("ten_k", C.c_float), ("ten_d", C.c_float)]
+
+
+def object_contact_gains(mass):
+    """Penalty gains of every contact of the free object (DESIGN.md "free object"): the object is light, so the
+    gains scale with ITS mass; critically damped for the two-body reduced mass."""
+    kn = 10000.0 * mass
+    return kn, 2.0 * float(np.sqrt(kn * mass / 4.0))
+
+
+def pack_model_ext(model, obj=None, actors_per_env=1, tendons=None, tendon_k=0.0, tendon_d=0.0):
+    """obj: dict(mass, inertia(3), half(3), mu, gravity_on) of the free box (actor 1), or None."""
+    ex = CModelExt()
+    ex.actors_per_env = int(actors_per_env)
+    ex.obj_actor = -1
+    if obj is not None:
+        ex.obj_actor, ex.obj_gravity_on = 1, int(obj.get("gravity_on", 1))
+        ex.obj_mass = float(obj["mass"])
+        ex.obj_inertia = (C.c_float * 3)(*obj["inertia"]); ex.obj_half = (C.c_float * 3)(*obj["half"])
+        kn, cn = object_contact_gains(ex.obj_mass)
+        ex.obj_kn, ex.obj_cn, ex.obj_mu = kn, cn, float(obj.get("mu", 1.0))
+        bl = getattr(model, "box_link", None)
+        ex.nbox = 0 if bl is None else len(bl)
+        for b in range(ex.nbox):
+            ex.box_link[b] = int(model.box_link[b])
+            for c in range(3):
+                ex.box_pos[b][c] = float(model.box_pos[b][c]); ex.box_half[b][c] = float(model.box_half[b][c])
+            for c in range(4):
+                ex.box_quat[b][c] = float(model.box_quat[b][c])
+    dn = list(model.dof_names)
+    ix = lambda d: int(d) if isinstance(d, (int, np.integer)) else dn.index(d)
+    ex.nten = len(tendons or [])
+    for t, td in enumerate(tendons or []):
+        for k in range(2):
+            ex.ten_dof[t][k] = ix(td["dofs"][k]); ex.ten_coef[t][k] = float(td["coefs"][k]); ex.ten_range[t][k] = float(td["range"][k])
+    ex.ten_k, ex.ten_d = float(tendon_k), float(tendon_d)
+    return ex
+
+
 class CSimParams(C.Structure):
     _fields_ = [("dt", C.c_float), ("substeps", C.c_int32), ("gravity", C.c_float * 3), ("hf_samples", C.c_void_p),
                 ("hf_nx", C.c_int32), ("hf_ny", C.c_int32), ("hf_horizontal_scale", C.c_float),
@@ -89,13 +135,13 @@ def lib():
         _lib.b2g_last_error.restype = C.c_char_p
         _lib.b2g_launch_count.restype = C.c_int64
         _lib.b2g_launch_count.argtypes = [C.c_void_p]
-        for fn in ("b2g_create", "b2g_destroy", "b2g_bind", "b2g_simulate", "b2g_refresh_rigid_body_state",
+        for fn in ("b2g_create", "b2g_create_ext", "b2g_destroy", "b2g_bind", "b2g_simulate", "b2g_refresh_rigid_body_state",
                    "b2g_set_task", "b2g_set_anymal_task", "b2g_task_step", "b2g_task_step_host"):
             getattr(_lib, fn).restype = C.c_int
     return _lib
 
 
-EXPORTS = ("b2g_create", "b2g_destroy", "b2g_bind", "b2g_simulate", "b2g_refresh_rigid_body_state", "b2g_set_task",
+EXPORTS = ("b2g_create", "b2g_create_ext", "b2g_destroy", "b2g_bind", "b2g_simulate", "b2g_refresh_rigid_body_state", "b2g_set_task",
            "b2g_set_anymal_task", "b2g_task_step", "b2g_task_step_host", "b2g_launch_count", "b2g_last_error", "b2g_version")
 
 
@@ -135,8 +181,9 @@ class Sim:
     """N identical single-actor environments on one GPU (gym.create_sim .. prepare_sim)."""
 
     def __init__(self, model, num_envs, dt, substeps, gravity=(0.0, 0.0, -9.81), ground_mu=1.0, device="cuda:0",
-                 hfield=None, hf_horizontal_scale=1.0, hf_vertical_scale=1.0, hf_origin=(0.0, 0.0)):
+                 hfield=None, hf_horizontal_scale=1.0, hf_vertical_scale=1.0, hf_origin=(0.0, 0.0), ext=None):
         self.model = model
+        self.actors_per_env = int(ext.actors_per_env) if ext is not None else 1
         self.num_envs = int(num_envs)
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -156,12 +203,16 @@ class Sim:
             sp.hf_origin_x, sp.hf_origin_y = hf_origin
         self._h = C.c_void_p()
         idx = self.device.index if self.device.index is not None else 0
-        _check(lib().b2g_create(C.byref(cm), C.byref(sp), C.c_int32(self.num_envs), C.c_int32(idx), C.byref(self._h)),
-               "b2g_create")
+        if ext is not None:
+            _check(lib().b2g_create_ext(C.byref(cm), C.byref(ext), C.byref(sp), C.c_int32(self.num_envs), C.c_int32(idx),
+                                        C.byref(self._h)), "b2g_create_ext")
+        else:
+            _check(lib().b2g_create(C.byref(cm), C.byref(sp), C.c_int32(self.num_envs), C.c_int32(idx), C.byref(self._h)),
+                   "b2g_create")
         self.tensors = {}
         N = self.num_envs
         z = lambda *s, dtype=torch.float32: torch.zeros(*s, dtype=dtype, device=self.device)
-        self.root_state = self._bind(T_ROOT_STATE, z(N, 13))
+        self.root_state = self._bind(T_ROOT_STATE, z(N * self.actors_per_env, 13))
         self.root_state[:, 6] = 1.0
         self.dof_state = self._bind(T_DOF_STATE, z(N * max(self.nd, 1), 2))
         self.dof_actuation = self._bind(T_DOF_ACTUATION, z(N, max(self.nd, 1)))
@@ -184,7 +235,7 @@ class Sim:
         if slot in self.tensors:
             return self.tensors[slot]
         N = self.num_envs
-        shape = {T_RIGID_BODY_STATE: (N * self.nb, 13), T_FORCE_SENSOR: (N * max(self.ns, 1), 6),
+        shape = {T_RIGID_BODY_STATE: (N * (self.nb + self.actors_per_env - 1), 13), T_FORCE_SENSOR: (N * max(self.ns, 1), 6),
                  T_DOF_FORCE: (N * max(self.nd, 1),), T_NET_CONTACT: (N * self.nb, 3)}[slot]
         return self._bind(slot, torch.zeros(*shape, dtype=torch.float32, device=self.device))
 

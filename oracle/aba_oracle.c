@@ -350,7 +350,10 @@ static void substep(const OracleModel *m, real h, real *root, real *dof, const r
         memset(Ao, 0, sizeof(Ao));
         for (int a_ = 0; a_ < 3; a_++) { for (int b_ = 0; b_ < 3; b_++) Ao[6 * a_ + b_] = Iw[3 * a_ + b_]; Ao[6 * (a_ + 3) + a_ + 3] = (real)m->obj_mass; }
         real Iww[3], gyro[3]; mat3_vec(Iw, obj + 10, Iww); cross3(obj + 10, Iww, gyro);
-        for (int k = 0; k < 3; k++) { bo[k] = -gyro[k]; bo[3 + k] = m->obj_gravity_on ? (real)m->obj_mass * (real)m->gravity[k] : 0; }
+        /* unknown = SPATIAL acceleration (alpha ; a_c - w x v_c) so that J*a is the rate of change of the velocity field
+         * at the contact point, the same quantity the articulation's contacts use */
+        real wxv0[3]; cross3(obj + 10, obj + 7, wxv0);
+        for (int k = 0; k < 3; k++) { bo[k] = -gyro[k]; bo[3 + k] = (m->obj_gravity_on ? (real)m->obj_mass * (real)m->gravity[k] : 0) - (real)m->obj_mass * wxv0[k]; }
         real okn = (real)m->obj_kn, ocn = (real)m->obj_cn, ogn = ocn + h * okn, hb[3] = {(real)m->obj_half[0], (real)m->obj_half[1], (real)m->obj_half[2]};
         /* helper macro: one contact at world point pc with normal nrm (direction of the force on the LINK), penetration pen */
 #define OBJ_CONTACT(LI, BI, CPI, PC, NRM, PEN, MU) do {                                                                       \
@@ -507,7 +510,8 @@ static void substep(const OracleModel *m, real h, real *root, real *dof, const r
         }
         real ao[6];
         spd6_solve(Ao, bo, ao);
-        for (int k = 0; k < 3; k++) { obj[10 + k] += h * ao[k]; obj[7 + k] += h * ao[3 + k]; }
+        real wxv1[3]; cross3(obj + 10, obj + 7, wxv1);
+        for (int k = 0; k < 3; k++) { obj[10 + k] += h * ao[k]; obj[7 + k] += h * (ao[3 + k] + wxv1[k]); }
         for (int k = 0; k < 3; k++) obj[k] += h * obj[7 + k];
         real w[3] = {obj[10], obj[11], obj[12]};
         real wn = SQRT(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]), th = wn * h, dq[4];

@@ -101,7 +101,8 @@ class OracleSim:
         if tendons:
             dn = list(m.dof_names)
             cm.nten = len(tendons)
-            cm.ten_dof = arr("ten_dof", [[dn.index(t["dofs"][0]), dn.index(t["dofs"][1])] for t in tendons], np.int32)
+            ix = lambda d: d if isinstance(d, (int, np.integer)) else dn.index(d)
+            cm.ten_dof = arr("ten_dof", [[ix(t["dofs"][0]), ix(t["dofs"][1])] for t in tendons], np.int32)
             cm.ten_coef = arr("ten_coef", [t["coefs"] for t in tendons], np.float64)
             cm.ten_range = arr("ten_range", [t["range"] for t in tendons], np.float64)
             cm.ten_k, cm.ten_d = tendon_k, tendon_d

@@ -1,0 +1,40 @@
+"""Shared set-up of the ShadowHand + cube environment for the oracle / engine tests."""
+import copy
+import numpy as np
+
+from isaacgymenvs_b200.assets import load_compiled
+
+FINGERTIPS = ["robot0:ffdistal", "robot0:mfdistal", "robot0:rfdistal", "robot0:lfdistal", "robot0:thdistal"]
+RELEVANT_TENDONS = ["robot0:T_FFJ1c", "robot0:T_MFJ1c", "robot0:T_RFJ1c", "robot0:T_LFJ1c"]   # shadow_hand.py:258
+DT, SUBSTEPS = 0.01667, 2                                                                       # ShadowHand.yaml sim
+G = (0.0, 0.0, -9.81)
+
+
+def hand_setup():
+    m = copy.deepcopy(load_compiled("shadow_hand"))
+    cube = load_compiled("cube")
+    m.sensor_body = np.array([m.body_names.index(n) for n in FINGERTIPS], dtype=np.int32)
+    m.sensor_pos = np.zeros((5, 3)); m.sensor_quat = np.tile([0, 0, 0, 1.0], (5, 1))
+    obj = dict(mass=float(cube.mass[0]), inertia=[float(cube.inertia[0][k]) for k in range(3)], half=[0.025] * 3, mu=1.0,
+               gravity_on=1)
+    tendons = [t for t in m.tendons if t["name"] in RELEVANT_TENDONS]
+    return m, obj, tendons
+
+
+def settled_states(n, steps, seed, precision="f64", threads=8):
+    """Contact-rich states: the cube dropped onto the hand while the fingers chase random targets (fp64 oracle)."""
+    from oracle.oracle import OracleSim
+    m, obj, tendons = hand_setup()
+    rng = np.random.default_rng(seed)
+    orc = OracleSim(m, DT, SUBSTEPS, G, precision=precision, obj=obj, tendons=tendons, tendon_k=30.0, tendon_d=0.1, threads=threads)
+    dt_ = np.float64 if precision == "f64" else np.float32
+    root = np.zeros((n, 13), dt_); root[:, 2] = 0.5; root[:, 3:7] = m.default_root_quat
+    dof = np.zeros((n, m.ndof, 2), dt_)
+    o = np.zeros((n, 13), dt_)
+    o[:, 0:3] = np.array([0.0, -0.39, 0.56]) + rng.uniform(-1, 1, size=(n, 3)) * np.array([0.02, 0.03, 0.02])
+    q = rng.normal(size=(n, 4)); o[:, 3:7] = q / np.linalg.norm(q, axis=1, keepdims=True)
+    lo, hi = m.lower[1:], m.upper[1:]
+    tgt = (lo + (hi - lo) * rng.uniform(0.0, 0.7, size=(n, m.ndof))).astype(dt_)
+    for _ in range(steps):
+        orc.simulate(root, dof, target=tgt, obj=o)
+    return m, obj, tendons, orc, root, dof, o, tgt

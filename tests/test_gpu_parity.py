@@ -460,3 +460,85 @@ def test_generic_gym_api_path_matches_fused_step():
         assert torch.allclose(root[keep], env.root_states[keep], atol=1e-5, rtol=1e-4)
         assert torch.allclose(dof.view(n, 8, 2)[keep], env.dof_state.view(n, 8, 2)[keep], atol=1e-4, rtol=1e-3)
         assert torch.allclose(sens.view(n, 24), env.vec_sensor_tensor, atol=1e-2, rtol=1e-3)
+
+
+# ---------------------------------------------------------------------------------------------
+# ShadowHand: fixed-base 24-DOF hand + free cube (second actor) + goal marker (third actor)
+def _hand_sim(n, m, obj, tendons):
+    from isaacgymenvs_b200 import engine
+    from tests.hand_common import DT, SUBSTEPS, G as HG
+    ext = engine.pack_model_ext(m, obj=obj, actors_per_env=3, tendons=tendons, tendon_k=30.0, tendon_d=0.1)
+    sim = engine.Sim(m, n, DT, SUBSTEPS, HG, ground_mu=1.0, ext=ext)
+    for slot in (engine.T_FORCE_SENSOR, engine.T_DOF_FORCE, engine.T_NET_CONTACT):
+        sim.acquire(slot)
+    return sim
+
+
+def _hand_load(sim, root, dof, o, tgt):
+    n = root.shape[0]
+    rs = np.zeros((n, 3, 13), np.float32); rs[:, 0] = root; rs[:, 1] = o; rs[:, 2, 6] = 1; rs[:, 2, 0:3] = [-0.2, -0.45, 0.68]
+    sim.root_state.copy_(torch.tensor(rs.reshape(-1, 13)))
+    sim.dof_state.copy_(torch.tensor(dof.reshape(-1, 2), dtype=torch.float32))
+    sim.dof_target.copy_(torch.tensor(tgt, dtype=torch.float32))
+
+
+def test_hand_object_simulate_matches_oracle():
+    """One gym.simulate() from contact-rich hand+cube states (cube on the palm / between fingers / on the ground):
+    engine (world-axes ABA about O, fp32, 4 lanes) against the oracle (body-coordinate ABA, fp64)."""
+    from isaacgymenvs_b200 import engine
+    from tests.hand_common import settled_states
+    n = 512
+    m, obj, tendons, orc, root, dof, o, tgt = settled_states(n, 40, 5)
+    sim = _hand_sim(n, m, obj, tendons)
+    _hand_load(sim, root, dof, o, tgt)
+    rs = sim.root_state.cpu().numpy().astype(np.float64).reshape(n, 3, 13)
+    r64 = np.ascontiguousarray(rs[:, 0]); o64 = np.ascontiguousarray(rs[:, 1])
+    d64 = sim.dof_state.cpu().numpy().astype(np.float64).reshape(n, m.ndof, 2)
+    t64 = sim.dof_target.cpu().numpy().astype(np.float64)
+    sim.simulate(); torch.cuda.synchronize()
+    out = orc.simulate(r64, d64, target=t64, obj=o64)
+    rg = sim.root_state.cpu().numpy().astype(np.float64).reshape(n, 3, 13)
+    dg = sim.dof_state.cpu().numpy().astype(np.float64).reshape(n, m.ndof, 2)
+    assert np.array_equal(rg[:, 0], rs[:, 0]) and np.array_equal(rg[:, 2], rs[:, 2])      # fixed base, goal marker untouched
+    assert np.abs(rg[:, 1, :3] - o64[:, :3]).max() < 5e-5
+    qd = np.minimum(np.abs(rg[:, 1, 3:7] - o64[:, 3:7]).max(-1), np.abs(rg[:, 1, 3:7] + o64[:, 3:7]).max(-1))
+    assert qd.max() < 2e-4, qd.max()
+    verr = np.abs(rg[:, 1, 7:] - o64[:, 7:]) / np.maximum(1.0, np.abs(o64[:, 7:]))
+    assert verr.max() < 5e-3, verr.max()
+    assert np.abs(dg[..., 0] - d64[..., 0]).max() < 1e-4
+    qerr = np.abs(dg[..., 1] - d64[..., 1]) / np.maximum(1.0, np.abs(d64[..., 1]))
+    assert qerr.max() < 5e-3, qerr.max()
+    sg = sim.tensors[engine.T_FORCE_SENSOR].cpu().numpy().reshape(n, -1, 6)
+    assert np.abs(out["sensor"]).max() > 0.1                                              # the fingertips do touch the cube
+    assert np.abs(sg - out["sensor"]).max() < 5e-3 * max(1.0, np.abs(out["sensor"]).max())
+    fg = sim.tensors[engine.T_DOF_FORCE].cpu().numpy().reshape(n, -1)
+    assert np.abs(fg - out["dof_force"]).max() < 5e-3 * max(1.0, np.abs(out["dof_force"]).max())
+    # fingertip / object / goal rows of the rigid-body state tensor (shadow_hand.py:456)
+    bs = sim.refresh_rigid_body_state(); torch.cuda.synchronize()
+    bg = bs.cpu().numpy().reshape(n, m.nb + 2, 13)
+    bo = orc.body_states(r64, d64)
+    assert np.abs(bg[:, :m.nb, :3] - bo[..., :3]).max() < 3e-5
+    assert np.array_equal(bg[:, m.nb], sim.root_state.cpu().numpy().reshape(n, 3, 13)[:, 1])
+    sim.close()
+
+
+def test_hand_rollout_tracks_oracle():
+    """60 control steps of the cube dropped on the hand: medians stay together (round-off, not a model difference)."""
+    from tests.hand_common import settled_states
+    n = 128
+    m, obj, tendons, orc, root, dof, o, tgt = settled_states(n, 0, 11)
+    sim = _hand_sim(n, m, obj, tendons)
+    _hand_load(sim, root, dof, o, tgt)
+    rs = sim.root_state.cpu().numpy().astype(np.float64).reshape(n, 3, 13)
+    r64 = np.ascontiguousarray(rs[:, 0]); o64 = np.ascontiguousarray(rs[:, 1])
+    d64 = sim.dof_state.cpu().numpy().astype(np.float64).reshape(n, m.ndof, 2)
+    t64 = sim.dof_target.cpu().numpy().astype(np.float64)
+    for _ in range(60):
+        sim.simulate()
+        orc.simulate(r64, d64, target=t64, obj=o64)
+    torch.cuda.synchronize()
+    rg = sim.root_state.cpu().numpy().reshape(n, 3, 13); dg = sim.dof_state.cpu().numpy().reshape(n, m.ndof, 2)
+    assert np.isfinite(rg).all() and np.isfinite(dg).all()
+    assert np.median(np.abs(rg[:, 1, :3] - o64[:, :3]).max(1)) < 2e-3
+    assert np.median(np.abs(dg[..., 0] - d64[..., 0]).max(1)) < 5e-3
+    sim.close()
