@@ -139,11 +139,20 @@ enum {
     B2G_T_BASE_SCRATCH = 32,   /* f32 (N,12) base_lin_vel, base_ang_vel, projected_gravity handed from kernel 1 to 2 */
     B2G_T_REDUCE_SCRATCH = 33, /* f32 (>= 1024 + 16) per-block partials of the reset-set norm (anymal_terrain.py:432) + extras sums */
     B2G_T_ENV_FRICTION = 34,   /* f32 (N)   per-env shape friction (friction buckets, anymal_terrain.py:235-281); NULL = the model's */
-    B2G_T_COUNT = 35
+    /* ShadowHand state (shadow_hand.py:183-200,398-408) */
+    B2G_T_GOAL_STATES = 35,    /* f32 (N,13)  goal_states */
+    B2G_T_PREV_TARGETS = 36,   /* f32 (N,D)   prev_targets (cur_targets is the DOF_TARGET tensor itself) */
+    B2G_T_SUCCESSES = 37,      /* f32 (N) */
+    B2G_T_CONSECUTIVE_SUCCESSES = 38, /* f32 (4): [0] consecutive_successes, [1..3] reduction scratch (sum resets, sum finished, ticket) */
+    B2G_T_RESET_GOAL = 39,     /* i64 (N)     reset_goal_buf */
+    B2G_T_GOAL_RESET_COUNT = 40,/* i32 (N)    per-env goal-only reset counter feeding the Philox stream */
+    B2G_T_COUNT = 41
 };
 
 /* fused per-task control steps */
-enum { B2G_TASK_NONE = 0, B2G_TASK_CARTPOLE = 1, B2G_TASK_ANT = 2, B2G_TASK_HUMANOID = 3, B2G_TASK_ANYMAL_TERRAIN = 4 };
+enum { B2G_TASK_NONE = 0, B2G_TASK_CARTPOLE = 1, B2G_TASK_ANT = 2, B2G_TASK_HUMANOID = 3, B2G_TASK_ANYMAL_TERRAIN = 4,
+       B2G_TASK_SHADOW_HAND = 5 };
+enum { B2G_HAND_OBS_OPENAI = 0, B2G_HAND_OBS_FULL_NO_VEL = 1, B2G_HAND_OBS_FULL = 2, B2G_HAND_OBS_FULL_STATE = 3 };
 
 /* Scalars of the locomotion tasks (cfg/task/Ant.yaml:13-29, Humanoid.yaml; ant.py:47-68). */
 typedef struct {
@@ -194,6 +203,30 @@ typedef struct {
     int32_t env_id_offset, pad2;
 } b2g_anymal_params;
 
+/* Scalars of ShadowHand (cfg/task/ShadowHand.yaml, shadow_hand.py:52-130).  The sim must have been created with
+ * b2g_create_ext: actors hand (0), object (1), goal marker (2).  INITIAL_ROOT holds, per env, the hand start state,
+ * object_init_state and goal_init_state (shadow_hand.py:343-346,398-402). */
+typedef struct {
+    int32_t num_obs, num_actions;          /* 42 / 77 / 157 / 211 ; 20 */
+    int32_t obs_type;                      /* B2G_HAND_OBS_* (shadow_hand.py:101-113) */
+    int32_t control_freq_inv;
+    float clip_actions, clip_obs;
+    float max_episode_length;
+    int32_t use_relative_control, max_consecutive_successes;
+    float dof_speed_scale, act_moving_average, dt;
+    float dist_reward_scale, rot_reward_scale, rot_eps, action_penalty_scale, success_tolerance, reach_goal_bonus,
+          fall_dist, fall_penalty, av_factor;
+    float vel_obs_scale, force_torque_obs_scale;               /* 0.2, 10.0: shadow_hand.py:62-63 */
+    float reset_position_noise, reset_dof_pos_noise, reset_dof_vel_noise;
+    float goal_displacement[3];                                /* shadow_hand.py:311 */
+    int32_t actuated_dof[B2G_MAX_LINKS];                       /* action k drives DOF actuated_dof[k], shadow_hand.py:268-269 */
+    float dof_lower[B2G_MAX_LINKS], dof_upper[B2G_MAX_LINKS], dof_default_pos[B2G_MAX_LINKS], dof_default_vel[B2G_MAX_LINKS];
+    int32_t fingertip_body[5];                                 /* shadow_hand.py:120,289 */
+    int32_t pad0;
+    uint64_t seed;
+    int32_t env_id_offset, pad1;
+} b2g_hand_params;
+
 typedef struct b2g_sim b2g_sim;
 
 /* gymapi.acquire_gym() + gym.create_sim() + create_env/create_actor x N + gym.prepare_sim()
@@ -224,6 +257,9 @@ int b2g_set_task(b2g_sim *sim, const b2g_task_params *task);
 /* AnymalTerrain (tasks/anymal_terrain.py:441-485): b2g_task_step then launches two kernels, physics +
  * termination + reward, and reset (terrain curriculum) + observations. */
 int b2g_set_anymal_task(b2g_sim *sim, const b2g_anymal_params *task);
+/* ShadowHand (tasks/shadow_hand.py:661-705 pre_physics_step with reset_idx / reset_target_pose, simulate,
+ * :707-712 post_physics_step with compute_observations and compute_hand_reward): one kernel launch. */
+int b2g_set_hand_task(b2g_sim *sim, const b2g_hand_params *task);
 int b2g_task_step(b2g_sim *sim, const float *actions, void *stream);
 
 /* Same step with HOST buffers (pinned or pageable): copies actions in, runs the step, copies

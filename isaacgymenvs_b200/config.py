@@ -73,6 +73,28 @@ def _builtin_task(name, root):
                         "asset": {"assetFileName": "mjcf/nv_humanoid.xml"}, "enableCameraSensors": False},
                 "sim": _sim(root, _physx(root)),
                 "task": {"randomize": False, "randomization_params": {}}}
+    if name == "ShadowHand":
+        sim = _sim(root, _physx(root, num_position_iterations=8, contact_offset=0.002, max_depenetration_velocity=1000.0))
+        sim.update({"dt": 0.01667, "substeps": 2})
+        return {"name": "ShadowHand", "physics_engine": root["physics_engine"],
+                "env": {"numEnvs": _num_envs(root, 16384), "envSpacing": 0.75, "episodeLength": 600, "enableDebugVis": False,
+                        "aggregateMode": 1, "clipObservations": 5.0, "clipActions": 1.0, "stiffnessScale": 1.0,
+                        "forceLimitScale": 1.0, "useRelativeControl": False, "dofSpeedScale": 20.0,
+                        "actionsMovingAverage": 1.0, "controlFrequencyInv": 1, "startPositionNoise": 0.01,
+                        "startRotationNoise": 0.0, "resetPositionNoise": 0.01, "resetRotationNoise": 0.0,
+                        "resetDofPosRandomInterval": 0.2, "resetDofVelRandomInterval": 0.0, "forceScale": 0.0,
+                        "forceProbRange": [0.001, 0.1], "forceDecay": 0.99, "forceDecayInterval": 0.08,
+                        "distRewardScale": -10.0, "rotRewardScale": 1.0, "rotEps": 0.1, "actionPenaltyScale": -0.0002,
+                        "reachGoalBonus": 250, "fallDistance": 0.24, "fallPenalty": 0.0, "objectType": "block",
+                        "observationType": "full_state", "asymmetric_observations": False, "successTolerance": 0.1,
+                        "printNumSuccesses": False, "maxConsecutiveSuccesses": 0,
+                        "asset": {"assetFileName": "mjcf/open_ai_assets/hand/shadow_hand.xml",
+                                  "assetFileNameBlock": "urdf/objects/cube_multicolor.urdf",
+                                  "assetFileNameEgg": "mjcf/open_ai_assets/hand/egg.xml",
+                                  "assetFileNamePen": "mjcf/open_ai_assets/hand/pen.xml"},
+                        "enableCameraSensors": False},
+                "sim": sim,
+                "task": {"randomize": False, "randomization_params": {}}}
     if name == "AnymalTerrain":
         sim = _sim(root, _physx(root, num_velocity_iterations=1, max_depenetration_velocity=100.0, contact_collection=1))
         sim.update({"dt": 0.005, "substeps": 1})

@@ -500,6 +500,7 @@ __global__ void __launch_bounds__(BLOCK) cartpole_step_kernel(const DevModel *__
 }
 
 #include "b2g_anymal.cuh"
+#include "b2g_hand.cuh"
 
 // -------------------------------------------------------------------------------------------
 // gym.refresh_rigid_body_state_tensor(): forward kinematics, one thread per env, any topology
@@ -577,7 +578,9 @@ struct b2g_sim {
     size_t buf_bytes[B2G_T_COUNT];
     b2g_task_params task;
     b2g_anymal_params anymal;
-    bool has_task = false, has_anymal = false;
+    b2g_hand_params hand;
+    HandDev hand_dev;
+    bool has_task = false, has_anymal = false, has_hand = false;
     unsigned step_counter = 0;   // common_step_counter, anymal_terrain.py:459
     float *d_actions_stage = nullptr;    // device staging for b2g_task_step_host
     int64_t launches = 0;
@@ -827,6 +830,11 @@ extern "C" int b2g_bind(b2g_sim *s, int32_t slot, void *ptr, size_t bytes) {
         case B2G_T_RIGID_BODY_STATE: need = (size_t)N * (nb + s->hm.root_stride - 1) * 13 * 4; break;
         case B2G_T_FORCE_SENSOR: need = (size_t)N * ns * 6 * 4; break;
         case B2G_T_NET_CONTACT: need = (size_t)N * nb * 3 * 4; break;
+        case B2G_T_GOAL_STATES: need = (size_t)N * 13 * 4; break;
+        case B2G_T_PREV_TARGETS: need = (size_t)N * nd * 4; break;
+        case B2G_T_SUCCESSES: case B2G_T_GOAL_RESET_COUNT: need = (size_t)N * 4; break;
+        case B2G_T_CONSECUTIVE_SUCCESSES: need = 16; break;
+        case B2G_T_RESET_GOAL: need = (size_t)N * 8; break;
         case B2G_T_REW: case B2G_T_POTENTIALS: case B2G_T_PREV_POTENTIALS: case B2G_T_RESET_COUNT: need = (size_t)N * 4; break;
         case B2G_T_RESET: case B2G_T_PROGRESS: need = (size_t)N * 8; break;
         case B2G_T_TIMEOUT: need = (size_t)N; break;
@@ -912,7 +920,7 @@ extern "C" int b2g_set_task(b2g_sim *s, const b2g_task_params *t) {
     } else return fail(B2G_E_UNSUPPORTED, "b2g_set_task: unknown task id");
     if (t->control_freq_inv < 0) return fail(B2G_E_INVALID, "control_freq_inv < 0");
     if (s->hm.root_stride != 1) return fail(B2G_E_UNSUPPORTED, "b2g_set_task: single-actor environments only");
-    s->task = *t; s->has_task = true; s->has_anymal = false;
+    s->task = *t; s->has_task = true; s->has_anymal = false; s->has_hand = false;
     return B2G_OK;
 }
 
@@ -923,7 +931,81 @@ extern "C" int b2g_set_anymal_task(b2g_sim *s, const b2g_anymal_params *t) {
         return fail(B2G_E_UNSUPPORTED, "AnymalTerrain needs the 4-leg x 3-DOF articulation, 12 actions, 188 observations");
     if (t->decimation < 0 || t->control_freq_inv < 0) return fail(B2G_E_INVALID, "negative simulate count");
     if (s->hm.root_stride != 1) return fail(B2G_E_UNSUPPORTED, "b2g_set_anymal_task: single-actor environments only");
-    s->anymal = *t; s->has_anymal = true; s->has_task = false; s->step_counter = 0;
+    s->anymal = *t; s->has_anymal = true; s->has_task = false; s->has_hand = false; s->step_counter = 0;
+    return B2G_OK;
+}
+
+extern "C" int b2g_set_hand_task(b2g_sim *s, const b2g_hand_params *t) {
+    if (!s || !t) return fail(B2G_E_INVALID, "b2g_set_hand_task: null argument");
+    const DevModel &h = s->hm;
+    const int nd = h.nl - 1;
+    if (!h.obj_on || h.root_stride != 3 || h.obj_row != 1 || !h.root_fixed)
+        return fail(B2G_E_UNSUPPORTED, "ShadowHand needs a fixed-base articulation created with b2g_create_ext: actors hand, object, goal");
+    if (t->num_actions < 1 || t->num_actions > nd || h.nsens != 5) return fail(B2G_E_UNSUPPORTED, "ShadowHand: 1..dofs actions and 5 fingertip force sensors expected");
+    if (t->control_freq_inv < 0) return fail(B2G_E_INVALID, "control_freq_inv < 0");
+    HandDev H; memset(&H, 0, sizeof(H));
+    for (int d = 0; d < MAX_LINKS; d++) H.dof_action[d] = -1;
+    for (int k = 0; k < t->num_actions; k++) {
+        const int d = t->actuated_dof[k];
+        if (d < 0 || d >= nd || H.dof_action[d] >= 0) return fail(B2G_E_INVALID, "ShadowHand: bad actuated_dof table");
+        H.dof_action[d] = k;
+    }
+    for (int f = 0; f < 5; f++) {
+        const int b = t->fingertip_body[f];
+        if (b < 0 || b >= h.nb || h.sensor_body[f] != b) return fail(B2G_E_INVALID, "ShadowHand: fingertip bodies must be the five force-sensor bodies, in order");
+        const int link = h.body_link[b];
+        int ref = -1;
+        for (int sl = 0; sl < h.ns && ref < 0; sl++) for (int l = 0; l < h.lanes; l++) if (h.slots[sl][l].link == link) { ref = (l << 8) | sl; break; }
+        if (ref < 0) return fail(B2G_E_UNSUPPORTED, "ShadowHand: a fingertip rides on the root link");
+        H.ft_ref[f] = ref;
+        for (int c = 0; c < 3; c++) H.ft_bpos[f][c] = h.body_pos[b][c];
+        const float *q = h.body_quat[b];
+        float x = q[0], y = q[1], z = q[2], w = q[3], n = sqrtf(x * x + y * y + z * z + w * w);
+        x /= n; y /= n; z /= n; w /= n;
+        const float R[9] = {1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
+                            2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
+                            2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)};
+        memcpy(H.ft_bR[f], R, sizeof(R));
+    }
+    // observation layouts, shadow_hand.py:460-592
+    const int A = t->num_actions;
+    H.o_dofpos = H.o_dofvel = H.o_dofforce = H.o_objpose = H.o_objvel = H.o_goalpose = H.o_sens = -1;
+    int expect = 0;
+    switch (t->obs_type) {
+        case B2G_HAND_OBS_OPENAI:      H.o_ft = 0; H.ft_stride = 3; H.o_objpose = 15; H.n_objpose = 3; H.o_qdiff = 18; H.o_act = 22; expect = 22 + A; break;
+        case B2G_HAND_OBS_FULL_NO_VEL: H.o_dofpos = 0; H.o_objpose = nd; H.n_objpose = 7; H.o_goalpose = nd + 7; H.o_qdiff = nd + 14; H.o_ft = nd + 18; H.ft_stride = 3;
+                                       H.o_act = nd + 33; expect = nd + 33 + A; break;
+        case B2G_HAND_OBS_FULL:        H.o_dofpos = 0; H.o_dofvel = nd; H.o_objpose = 2 * nd; H.n_objpose = 7; H.o_objvel = 2 * nd + 7; H.o_goalpose = 2 * nd + 13;
+                                       H.o_qdiff = 2 * nd + 20; H.o_ft = 2 * nd + 24; H.ft_stride = 13; H.o_act = 2 * nd + 89; expect = 2 * nd + 89 + A; break;
+        case B2G_HAND_OBS_FULL_STATE:  H.o_dofpos = 0; H.o_dofvel = nd; H.o_dofforce = 2 * nd; H.o_objpose = 3 * nd; H.n_objpose = 7; H.o_objvel = 3 * nd + 7;
+                                       H.o_goalpose = 3 * nd + 13; H.o_qdiff = 3 * nd + 20; H.o_ft = 3 * nd + 24; H.ft_stride = 13; H.o_sens = 3 * nd + 89;
+                                       H.o_act = 3 * nd + 119; expect = 3 * nd + 119 + A; break;
+        default: return fail(B2G_E_INVALID, "ShadowHand: unknown observation type");
+    }
+    if (t->num_obs != expect) return fail(B2G_E_UNSUPPORTED, "ShadowHand: observation size does not match the layout of this observation type");
+    s->hand = *t; s->hand_dev = H; s->has_hand = true; s->has_task = false; s->has_anymal = false;
+    return B2G_OK;
+}
+
+static int hand_step(b2g_sim *s, const float *actions, void *stream) {
+    const b2g_hand_params &P = s->hand;
+    int rc = require(s, {B2G_T_ROOT_STATE, B2G_T_DOF_STATE, B2G_T_DOF_TARGET, B2G_T_OBS, B2G_T_REW, B2G_T_RESET, B2G_T_PROGRESS, B2G_T_RESET_COUNT,
+                         B2G_T_INITIAL_ROOT, B2G_T_GOAL_STATES, B2G_T_PREV_TARGETS, B2G_T_SUCCESSES, B2G_T_CONSECUTIVE_SUCCESSES,
+                         B2G_T_RESET_GOAL, B2G_T_GOAL_RESET_COUNT}, "b2g_task_step(ShadowHand)");
+    if (rc) return rc;
+    if (s->hand_dev.o_sens >= 0) { rc = require(s, {B2G_T_FORCE_SENSOR, B2G_T_DOF_FORCE}, "b2g_task_step(ShadowHand, full_state)"); if (rc) return rc; }
+    const size_t N = s->num_envs;
+    if (s->buf_bytes[B2G_T_OBS] < N * P.num_obs * 4) return fail(B2G_E_INVALID, "OBS buffer too small");
+    CUDA_TRY(cudaSetDevice(s->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int blk = s->block, grid = ((int)N * s->lanes + blk - 1) / blk;
+    if (s->lanes == 4 && blk == 128) B2G_LAUNCH((hand_step_kernel<4, 128>), s->dm, s->buf, P, s->hand_dev, actions, (int)N);
+    else if (s->lanes == 4 && blk == 64) B2G_LAUNCH((hand_step_kernel<4, 64>), s->dm, s->buf, P, s->hand_dev, actions, (int)N);
+    else if (s->lanes == 4 && blk == 32) B2G_LAUNCH((hand_step_kernel<4, 32>), s->dm, s->buf, P, s->hand_dev, actions, (int)N);
+    else if (s->lanes == 1 && blk == 32) B2G_LAUNCH((hand_step_kernel<1, 32>), s->dm, s->buf, P, s->hand_dev, actions, (int)N);
+    else return fail(B2G_E_UNSUPPORTED, "no ShadowHand kernel instantiated for this (lanes, CTA size) combination");
+    s->launches++;
+    CUDA_TRY(cudaGetLastError());
     return B2G_OK;
 }
 
@@ -958,6 +1040,7 @@ static int anymal_step(b2g_sim *s, const float *actions, void *stream) {
 extern "C" int b2g_task_step(b2g_sim *s, const float *actions, void *stream) {
     if (!s || !actions) return fail(B2G_E_INVALID, "b2g_task_step: null argument");
     if (s->has_anymal) return anymal_step(s, actions, stream);
+    if (s->has_hand) return hand_step(s, actions, stream);
     if (!s->has_task) return fail(B2G_E_INVALID, "b2g_task_step: call b2g_set_task first");
     int rc = require(s, {B2G_T_ROOT_STATE, B2G_T_DOF_STATE, B2G_T_OBS, B2G_T_REW, B2G_T_RESET, B2G_T_PROGRESS, B2G_T_RESET_COUNT}, "b2g_task_step");
     if (rc) return rc;
@@ -1022,11 +1105,11 @@ extern "C" int b2g_task_step(b2g_sim *s, const float *actions, void *stream) {
 extern "C" int b2g_task_step_host(b2g_sim *s, const float *h_actions, float *h_obs, float *h_rew, int64_t *h_reset,
                                   uint8_t *h_timeout, void *stream) {
     if (!s || !h_actions) return fail(B2G_E_INVALID, "b2g_task_step_host: null argument");
-    if (!s->has_task && !s->has_anymal) return fail(B2G_E_INVALID, "b2g_task_step_host: call b2g_set_task first");
+    if (!s->has_task && !s->has_anymal && !s->has_hand) return fail(B2G_E_INVALID, "b2g_task_step_host: call b2g_set_task first");
     CUDA_TRY(cudaSetDevice(s->device));
     cudaStream_t st = (cudaStream_t)stream;
-    const int n_act = s->has_anymal ? s->anymal.num_actions : s->task.num_actions;
-    const int n_obs = s->has_anymal ? s->anymal.num_obs : s->task.num_obs;
+    const int n_act = s->has_anymal ? s->anymal.num_actions : (s->has_hand ? s->hand.num_actions : s->task.num_actions);
+    const int n_obs = s->has_anymal ? s->anymal.num_obs : (s->has_hand ? s->hand.num_obs : s->task.num_obs);
     const size_t N = s->num_envs, abytes = N * n_act * 4;
     if (!s->d_actions_stage) CUDA_TRY(cudaMalloc(&s->d_actions_stage, abytes));
     CUDA_TRY(cudaMemcpyAsync(s->d_actions_stage, h_actions, abytes, cudaMemcpyHostToDevice, st));

@@ -21,8 +21,26 @@ MAXL = 32
  T_NET_CONTACT, T_ACTIONS, T_OBS, T_REW, T_RESET, T_PROGRESS, T_TIMEOUT, T_POTENTIALS, T_PREV_POTENTIALS,
  T_UP_VEC, T_HEADING_VEC, T_INITIAL_ROOT, T_RESET_COUNT, T_OBS_CLIPPED, T_COMMANDS, T_LAST_ACTIONS, T_LAST_DOF_VEL,
  T_FEET_AIR_TIME, T_TORQUES, T_EPISODE_SUMS, T_TERRAIN_LEVELS, T_TERRAIN_TYPES, T_ENV_ORIGINS, T_TERRAIN_ORIGINS,
- T_NOISE_SCALE, T_BASE_SCRATCH, T_REDUCE_SCRATCH, T_ENV_FRICTION) = range(35)
-TASK_NONE, TASK_CARTPOLE, TASK_ANT, TASK_HUMANOID, TASK_ANYMAL_TERRAIN = 0, 1, 2, 3, 4
+ T_NOISE_SCALE, T_BASE_SCRATCH, T_REDUCE_SCRATCH, T_ENV_FRICTION, T_GOAL_STATES, T_PREV_TARGETS, T_SUCCESSES,
+ T_CONSECUTIVE_SUCCESSES, T_RESET_GOAL, T_GOAL_RESET_COUNT) = range(41)
+TASK_NONE, TASK_CARTPOLE, TASK_ANT, TASK_HUMANOID, TASK_ANYMAL_TERRAIN, TASK_SHADOW_HAND = 0, 1, 2, 3, 4, 5
+HAND_OBS = {"openai": 0, "full_no_vel": 1, "full": 2, "full_state": 3}
+
+
+class CHandParams(C.Structure):
+    _fields_ = [("num_obs", C.c_int32), ("num_actions", C.c_int32), ("obs_type", C.c_int32), ("control_freq_inv", C.c_int32),
+                ("clip_actions", C.c_float), ("clip_obs", C.c_float), ("max_episode_length", C.c_float),
+                ("use_relative_control", C.c_int32), ("max_consecutive_successes", C.c_int32),
+                ("dof_speed_scale", C.c_float), ("act_moving_average", C.c_float), ("dt", C.c_float),
+                ("dist_reward_scale", C.c_float), ("rot_reward_scale", C.c_float), ("rot_eps", C.c_float),
+                ("action_penalty_scale", C.c_float), ("success_tolerance", C.c_float), ("reach_goal_bonus", C.c_float),
+                ("fall_dist", C.c_float), ("fall_penalty", C.c_float), ("av_factor", C.c_float),
+                ("vel_obs_scale", C.c_float), ("force_torque_obs_scale", C.c_float),
+                ("reset_position_noise", C.c_float), ("reset_dof_pos_noise", C.c_float), ("reset_dof_vel_noise", C.c_float),
+                ("goal_displacement", C.c_float * 3), ("actuated_dof", C.c_int32 * 32),
+                ("dof_lower", C.c_float * 32), ("dof_upper", C.c_float * 32), ("dof_default_pos", C.c_float * 32),
+                ("dof_default_vel", C.c_float * 32), ("fingertip_body", C.c_int32 * 5), ("pad0", C.c_int32),
+                ("seed", C.c_uint64), ("env_id_offset", C.c_int32), ("pad1", C.c_int32)]
 
 
 class CAnymalParams(C.Structure):
@@ -136,13 +154,13 @@ def lib():
         _lib.b2g_launch_count.restype = C.c_int64
         _lib.b2g_launch_count.argtypes = [C.c_void_p]
         for fn in ("b2g_create", "b2g_create_ext", "b2g_destroy", "b2g_bind", "b2g_simulate", "b2g_refresh_rigid_body_state",
-                   "b2g_set_task", "b2g_set_anymal_task", "b2g_task_step", "b2g_task_step_host"):
+                   "b2g_set_task", "b2g_set_anymal_task", "b2g_set_hand_task", "b2g_task_step", "b2g_task_step_host"):
             getattr(_lib, fn).restype = C.c_int
     return _lib
 
 
 EXPORTS = ("b2g_create", "b2g_create_ext", "b2g_destroy", "b2g_bind", "b2g_simulate", "b2g_refresh_rigid_body_state", "b2g_set_task",
-           "b2g_set_anymal_task", "b2g_task_step", "b2g_task_step_host", "b2g_launch_count", "b2g_last_error", "b2g_version")
+           "b2g_set_anymal_task", "b2g_set_hand_task", "b2g_task_step", "b2g_task_step_host", "b2g_launch_count", "b2g_last_error", "b2g_version")
 
 
 class EngineError(RuntimeError):
@@ -256,6 +274,8 @@ class Sim:
         self.task = params
         if isinstance(params, CAnymalParams):
             _check(lib().b2g_set_anymal_task(self._h, C.byref(params)), "b2g_set_anymal_task")
+        elif isinstance(params, CHandParams):
+            _check(lib().b2g_set_hand_task(self._h, C.byref(params)), "b2g_set_hand_task")
         else:
             _check(lib().b2g_set_task(self._h, C.byref(params)), "b2g_set_task")
 

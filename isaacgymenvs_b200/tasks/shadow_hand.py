@@ -1,0 +1,194 @@
+"""ShadowHand with the reference class's surface (`isaacgymenvs/tasks/shadow_hand.py`): three actors per env (hand,
+object, goal marker), the same public tensors, one fused kernel per step (csrc/b2g_hand.cuh)."""
+import copy
+import numpy as np
+import torch
+
+from .. import engine
+from ..assets import load_asset_file
+from ..importer.model import BuildOptions
+from .base.vec_task import VecTask
+from .locomotion import _asset_root
+
+FINGERTIPS = ["robot0:ffdistal", "robot0:mfdistal", "robot0:rfdistal", "robot0:lfdistal", "robot0:thdistal"]   # shadow_hand.py:120
+RELEVANT_TENDONS = ["robot0:T_FFJ1c", "robot0:T_MFJ1c", "robot0:T_RFJ1c", "robot0:T_LFJ1c"]                    # shadow_hand.py:258
+NUM_OBS = {"openai": 42, "full_no_vel": 77, "full": 157, "full_state": 211}                                     # shadow_hand.py:108-113
+
+
+class ShadowHand(VecTask):
+    def __init__(self, cfg, rl_device, sim_device, graphics_device_id, headless, virtual_screen_capture=False,
+                 force_render=False):
+        self.cfg = cfg
+        e = cfg["env"]
+        self.randomize = cfg["task"]["randomize"]
+        if self.randomize:
+            raise NotImplementedError("domain randomisation is outside the hot path (SURVEY.md 8f rank 3)")
+        self.dist_reward_scale = e["distRewardScale"]; self.rot_reward_scale = e["rotRewardScale"]
+        self.action_penalty_scale = e["actionPenaltyScale"]; self.success_tolerance = e["successTolerance"]
+        self.reach_goal_bonus = e["reachGoalBonus"]; self.fall_dist = e["fallDistance"]; self.fall_penalty = e["fallPenalty"]
+        self.rot_eps = e["rotEps"]
+        self.vel_obs_scale = 0.2; self.force_torque_obs_scale = 10.0                                            # shadow_hand.py:62-63
+        self.reset_position_noise = e["resetPositionNoise"]; self.reset_rotation_noise = e["resetRotationNoise"]
+        self.reset_dof_pos_noise = e["resetDofPosRandomInterval"]; self.reset_dof_vel_noise = e["resetDofVelRandomInterval"]
+        self.force_scale = e.get("forceScale", 0.0)
+        if self.force_scale > 0.0:
+            raise NotImplementedError("random object forces (forceScale > 0, shadow_hand.py:700-709) are not in the fused step")
+        self.shadow_hand_dof_speed_scale = e["dofSpeedScale"]; self.use_relative_control = e["useRelativeControl"]
+        self.act_moving_average = e["actionsMovingAverage"]
+        self.max_episode_length = e["episodeLength"]
+        self.reset_time = e.get("resetTime", -1.0)
+        self.print_success_stat = e["printNumSuccesses"]
+        self.max_consecutive_successes = e["maxConsecutiveSuccesses"]
+        self.av_factor = e.get("averFactor", 0.1)
+        self.object_type = e["objectType"]
+        if self.object_type != "block":
+            raise NotImplementedError("objectType egg / pen: only the block (BASELINE.json config 5) has a contact model here")
+        self.obs_type = e["observationType"]
+        if self.obs_type not in NUM_OBS:
+            raise Exception("Unknown type of observations!\\nobservationType should be one of: [openai, full_no_vel, full, full_state]")
+        if e["asymmetric_observations"]:
+            raise NotImplementedError("asymmetric observations (states_buf) are not produced by the fused step")
+        self.fingertips = list(FINGERTIPS); self.num_fingertips = 5
+        cfg["env"]["numObservations"] = NUM_OBS[self.obs_type]
+        cfg["env"]["numStates"] = 0
+        cfg["env"]["numActions"] = 20
+        self.up_axis, self.up_axis_idx = "z", 2
+        super().__init__(config=cfg, rl_device=rl_device, sim_device=sim_device, graphics_device_id=graphics_device_id,
+                         headless=headless, virtual_screen_capture=virtual_screen_capture, force_render=force_render)
+        if self.reset_time > 0.0:                                                                              # shadow_hand.py:147-151
+            self.max_episode_length = int(round(self.reset_time / (self.control_freq_inv * self.dt)))
+            self._bind_task()
+
+    # ---- shadow_hand.py:225-300
+    def _build_model(self):
+        a = self.cfg["env"].get("asset", {})
+        opts = BuildOptions(fix_base_link=True, collapse_fixed_joints=True, disable_gravity=True, angular_damping=0.01,
+                            capsule_mid_spheres=1)
+        model = copy.deepcopy(load_asset_file(_asset_root(), a.get("assetFileName", "mjcf/open_ai_assets/hand/shadow_hand.xml"), opts))
+        cube = load_asset_file(_asset_root(), a.get("assetFileNameBlock", "urdf/objects/cube_multicolor.urdf"), BuildOptions())
+        self.fingertip_handles_np = np.array([model.body_names.index(n) for n in self.fingertips], dtype=np.int32)
+        model.sensor_body = self.fingertip_handles_np.copy()                                                   # :292-296
+        model.sensor_pos = np.zeros((5, 3)); model.sensor_quat = np.tile([0, 0, 0, 1.0], (5, 1))
+        self.num_shadow_hand_dofs = self.num_dof = model.ndof
+        self.num_shadow_hand_bodies = model.nb
+        names = list(model.dof_names)
+        self.actuated_dof_indices_np = np.array([names.index(j) for j in model.actuator_joint], dtype=np.int32)  # :268-269
+        self.object_model = cube
+        half = [float(v) for v in np.asarray(cube.geom_size)[0][:3]]                                           # box half extents
+        self._obj = dict(mass=float(cube.mass[0]), inertia=[float(cube.inertia[0][k]) for k in range(3)], half=half,
+                         mu=1.0, gravity_on=1)
+        self._tendons = [t for t in model.tendons if t["name"] in RELEVANT_TENDONS]                             # :255-266
+        return model
+
+    def create_sim(self):
+        model = self._build_model()
+        sim_cfg = self.cfg["sim"]
+        self.model = model
+        ext = engine.pack_model_ext(model, obj=self._obj, actors_per_env=3, tendons=self._tendons, tendon_k=30.0, tendon_d=0.1)
+        self.sim = sim = engine.Sim(model, self.num_envs, dt=sim_cfg["dt"], substeps=sim_cfg["substeps"],
+                                    gravity=tuple(sim_cfg["gravity"]), ground_mu=1.0, device=self.device, ext=ext)
+        dev, N = self.device, self.num_envs
+        # start poses, shadow_hand.py:299-317
+        hand_p = np.array([0.0, 0.0, 0.5]); hand_q = np.asarray(model.default_root_quat, dtype=np.float64)
+        obj_p = hand_p + np.array([0.0, -0.39, 0.10])
+        self.goal_displacement_tensor = torch.tensor([-0.2, -0.06, 0.12], device=dev)
+        rs = sim.root_state.view(N, 3, 13)
+        rs[:, :, 6] = 1.0
+        rs[:, 0, 0:3] = torch.tensor(hand_p, dtype=torch.float32, device=dev)
+        rs[:, 0, 3:7] = torch.tensor(hand_q, dtype=torch.float32, device=dev)
+        rs[:, 1, 0:3] = torch.tensor(obj_p, dtype=torch.float32, device=dev)
+        goal_p = torch.tensor(obj_p, dtype=torch.float32, device=dev) + self.goal_displacement_tensor
+        goal_p[2] -= 0.04
+        rs[:, 2, 0:3] = goal_p
+        self.root_state_tensor = sim.root_state                                                                # (N*3, 13), :183
+        self.hand_indices = torch.arange(0, 3 * N, 3, device=dev)
+        self.object_indices = self.hand_indices + 1
+        self.goal_object_indices = self.hand_indices + 2
+        self.hand_start_states = rs[:, 0].clone()
+        self.object_init_state = rs[:, 1].clone()                                                              # :398
+        self.goal_states = self.object_init_state.clone()
+        self.goal_states[:, 2] -= 0.04                                                                         # :399-401
+        self.goal_init_state = self.goal_states.clone()
+        self.initial_root_states = torch.stack([self.hand_start_states, self.object_init_state, self.goal_init_state], 1).reshape(3 * N, 13).contiguous()
+        # tensors of __init__, shadow_hand.py:157-200
+        self.dof_state = sim.dof_state
+        self.shadow_hand_dof_state = self.dof_state.view(N, -1, 2)[:, :self.num_shadow_hand_dofs]
+        self.shadow_hand_dof_pos = self.shadow_hand_dof_state[..., 0]
+        self.shadow_hand_dof_vel = self.shadow_hand_dof_state[..., 1]
+        self.vec_sensor_tensor = sim.acquire(engine.T_FORCE_SENSOR).view(N, 30)
+        self.dof_force_tensor = sim.acquire(engine.T_DOF_FORCE).view(N, self.num_shadow_hand_dofs)
+        self.num_bodies = model.nb + 2
+        self.num_dofs = self.num_shadow_hand_dofs
+        self.cur_targets = sim.dof_target
+        self.prev_targets = torch.zeros((N, self.num_dofs), dtype=torch.float, device=dev)
+        self.actuated_dof_indices = torch.tensor(self.actuated_dof_indices_np, dtype=torch.long, device=dev)
+        self.shadow_hand_dof_lower_limits = torch.tensor(model.lower[1:], dtype=torch.float, device=dev)
+        self.shadow_hand_dof_upper_limits = torch.tensor(model.upper[1:], dtype=torch.float, device=dev)
+        self.shadow_hand_dof_default_pos = torch.zeros(self.num_dofs, dtype=torch.float, device=dev)
+        self.shadow_hand_dof_default_vel = torch.zeros(self.num_dofs, dtype=torch.float, device=dev)
+        self.fingertip_handles = torch.tensor(self.fingertip_handles_np, dtype=torch.long, device=dev)
+        self.reset_goal_buf = torch.ones(N, device=dev, dtype=torch.long)                                      # reset_buf.clone(), :192
+        self.successes = torch.zeros(N, dtype=torch.float, device=dev)
+        self._cons = torch.zeros(4, dtype=torch.float, device=dev)
+        self.consecutive_successes = self._cons[0:1]
+        self.goal_reset_count = torch.zeros(N, dtype=torch.int32, device=dev)
+        self.object_rb_masses = torch.tensor([self._obj["mass"]], dtype=torch.float, device=dev)
+        self.total_successes = 0; self.total_resets = 0
+        return sim
+
+    @property
+    def rigid_body_states(self):
+        """(N, bodies, 13) like gym.refresh_rigid_body_state_tensor + the view of shadow_hand.py:180 (computed on demand)."""
+        return self.sim.refresh_rigid_body_state().view(self.num_envs, -1, 13)
+
+    @property
+    def object_pos(self):
+        return self.root_state_tensor[self.object_indices, 0:3]
+
+    @property
+    def object_rot(self):
+        return self.root_state_tensor[self.object_indices, 3:7]
+
+    @property
+    def goal_pos(self):
+        return self.goal_states[:, 0:3]
+
+    @property
+    def goal_rot(self):
+        return self.goal_states[:, 3:7]
+
+    def _task_buffers(self):
+        E = engine
+        return {E.T_INITIAL_ROOT: self.initial_root_states, E.T_GOAL_STATES: self.goal_states, E.T_PREV_TARGETS: self.prev_targets,
+                E.T_SUCCESSES: self.successes, E.T_CONSECUTIVE_SUCCESSES: self._cons, E.T_RESET_GOAL: self.reset_goal_buf,
+                E.T_GOAL_RESET_COUNT: self.goal_reset_count}
+
+    def _task_params(self):
+        p = engine.CHandParams()
+        p.obs_type = engine.HAND_OBS[self.obs_type]
+        p.max_episode_length = float(self.max_episode_length)
+        p.use_relative_control = int(bool(self.use_relative_control))
+        p.max_consecutive_successes = int(self.max_consecutive_successes)
+        p.dof_speed_scale = float(self.shadow_hand_dof_speed_scale)
+        p.act_moving_average = float(self.act_moving_average)
+        p.dt = float(self.dt)
+        p.dist_reward_scale, p.rot_reward_scale, p.rot_eps = float(self.dist_reward_scale), float(self.rot_reward_scale), float(self.rot_eps)
+        p.action_penalty_scale, p.success_tolerance = float(self.action_penalty_scale), float(self.success_tolerance)
+        p.reach_goal_bonus, p.fall_dist, p.fall_penalty = float(self.reach_goal_bonus), float(self.fall_dist), float(self.fall_penalty)
+        p.av_factor = float(self.av_factor)
+        p.vel_obs_scale, p.force_torque_obs_scale = float(self.vel_obs_scale), float(self.force_torque_obs_scale)
+        p.reset_position_noise = float(self.reset_position_noise)
+        p.reset_dof_pos_noise, p.reset_dof_vel_noise = float(self.reset_dof_pos_noise), float(self.reset_dof_vel_noise)
+        p.goal_displacement = (engine.C.c_float * 3)(-0.2, -0.06, 0.12)
+        for k, d in enumerate(self.actuated_dof_indices_np):
+            p.actuated_dof[k] = int(d)
+        lo, hi = self.model.lower[1:], self.model.upper[1:]
+        for d in range(self.num_dofs):
+            p.dof_lower[d], p.dof_upper[d] = float(lo[d]), float(hi[d])
+            p.dof_default_pos[d] = 0.0; p.dof_default_vel[d] = 0.0
+        for f in range(5):
+            p.fingertip_body[f] = int(self.fingertip_handles_np[f])
+        return p
+
+    def _fill_extras(self):
+        self.extras['consecutive_successes'] = self.consecutive_successes.mean()                                # shadow_hand.py:424

@@ -38,3 +38,33 @@ def settled_states(n, steps, seed, precision="f64", threads=8):
     for _ in range(steps):
         orc.simulate(root, dof, target=tgt, obj=o)
     return m, obj, tendons, orc, root, dof, o, tgt
+
+
+# ---------------------------------------------------------------------------------------------
+# golden cases of tests/golden/shadow_hand.npz (make_golden_hand.py)
+CASES = {"a": dict(relative=False, mcs=0, mavg=1.0, fall_penalty=0.0), "b": dict(relative=True, mcs=50, mavg=1.0, fall_penalty=-50.0),
+         "c": dict(relative=False, mcs=0, mavg=0.3, fall_penalty=0.0)}
+
+
+def golden_case(gold, case, obs_type="full_state"):
+    """-> (st, P, actions): the numpy-restatement view of one golden case's inputs."""
+    m, _, _ = hand_setup()
+    g = lambda k: gold[f"{case}_in_{k}"].copy()
+    n = g("reset").shape[0]
+    D = m.ndof
+    ds = g("dof_state").reshape(n, D, 2)
+    st = dict(root=g("root").reshape(n, 3, 13), dof_pos=np.ascontiguousarray(ds[..., 0]), dof_vel=np.ascontiguousarray(ds[..., 1]),
+              cur_targets=g("cur_targets"), prev_targets=g("prev_targets"), goal_states=g("goal_states"), reset=g("reset"),
+              reset_goal=g("reset_goal"), progress=g("progress"), successes=g("successes"), reset_count=g("reset_count"),
+              goal_reset_count=g("goal_reset_count"))
+    kw = CASES[case]
+    P = dict(seed=int(gold["seed"]), goal_init=g("goal_init"), object_init=g("object_init"),
+             goal_displacement=np.array([-0.2, -0.06, 0.12], np.float32), reset_position_noise=0.01, reset_dof_pos_noise=0.2,
+             reset_dof_vel_noise=0.05, lower=m.lower[1:].astype(np.float32), upper=m.upper[1:].astype(np.float32),
+             default_pos=np.zeros(D, np.float32), default_vel=np.zeros(D, np.float32), clip_actions=1.0,
+             actuated=gold["actuated"].astype(np.int64), use_relative_control=kw["relative"], dof_speed_scale=20.0, dt=0.01667,
+             act_moving_average=kw["mavg"], obs_type=obs_type, vel_obs_scale=0.2, force_torque_obs_scale=10.0,
+             dist_reward_scale=-10.0, rot_reward_scale=1.0, rot_eps=0.1, action_penalty_scale=-0.0002, success_tolerance=0.1,
+             reach_goal_bonus=250.0, fall_dist=0.24, fall_penalty=kw["fall_penalty"], max_consecutive_successes=kw["mcs"],
+             max_episode_length=600.0, av_factor=0.1)
+    return st, P, g("actions")

@@ -542,3 +542,90 @@ def test_hand_rollout_tracks_oracle():
     assert np.median(np.abs(rg[:, 1, :3] - o64[:, :3]).max(1)) < 2e-3
     assert np.median(np.abs(dg[..., 0] - d64[..., 0]).max(1)) < 5e-3
     sim.close()
+
+
+def _hand_env(n, case, obs_type):
+    from tests.hand_common import CASES as HC
+    kw = HC[case]
+    return _make("ShadowHand", n, controlFrequencyInv=0, observationType=obs_type, useRelativeControl=kw["relative"],
+                 maxConsecutiveSuccesses=kw["mcs"], actionsMovingAverage=kw["mavg"], fallPenalty=kw["fall_penalty"],
+                 resetDofVelRandomInterval=0.05)
+
+
+@pytest.mark.parametrize("case,obs_type", [("a", "full_state"), ("a", "full"), ("a", "full_no_vel"), ("a", "openai"),
+                                           ("b", "full_state"), ("c", "full_state")])
+def test_hand_step_matches_reference_golden(case, obs_type):
+    """One fused ShadowHand step without physics (controlFrequencyInv=0) from the golden inputs: reset_idx /
+    reset_target_pose / targets / observations / compute_hand_reward against the reference's own methods."""
+    gold = np.load(os.path.join(GOLD, "shadow_hand.npz"))
+    gi = lambda k: gold[f"{case}_in_{k}"]
+    go = lambda k: gold[f"{case}_out_{k}"]
+    n = gi("reset").shape[0]
+    env = _hand_env(n, case, obs_type)
+    assert env.seed == int(gold["seed"])
+    assert np.array_equal(env.actuated_dof_indices_np, gold["actuated"]) and np.array_equal(env.fingertip_handles_np, gold["fingertips"])
+    dev = env.device
+    t = lambda a, dt=torch.float32: torch.tensor(np.asarray(a), dtype=dt, device=dev)
+    env.root_state_tensor.copy_(t(gi("root")))
+    env.initial_root_states.view(n, 3, 13)[:, 1].copy_(t(gi("object_init")))
+    env.initial_root_states.view(n, 3, 13)[:, 2].copy_(t(gi("goal_init")))
+    env.dof_state.copy_(t(gi("dof_state")))
+    env.prev_targets.copy_(t(gi("prev_targets"))); env.cur_targets.copy_(t(gi("cur_targets")))
+    env.goal_states.copy_(t(gi("goal_states")))
+    env.vec_sensor_tensor.copy_(t(gi("sensors"))); env.dof_force_tensor.copy_(t(gi("dof_force")))
+    env.reset_buf.copy_(t(gi("reset"), torch.long)); env.reset_goal_buf.copy_(t(gi("reset_goal"), torch.long))
+    env.progress_buf.copy_(t(gi("progress"), torch.long)); env.successes.copy_(t(gi("successes")))
+    env._cons[0] = float(gi("cons")[0])
+    env.reset_count.copy_(t(gi("reset_count"), torch.int32)); env.goal_reset_count.copy_(t(gi("goal_reset_count"), torch.int32))
+    env.step(t(gi("actions")))
+    torch.cuda.synchronize()
+    c = lambda x: x.detach().cpu().numpy()
+    np.testing.assert_allclose(c(env.root_state_tensor), go("root"), rtol=0, atol=1e-6)
+    np.testing.assert_allclose(c(env.goal_states), go("goal_states"), rtol=0, atol=1e-6)
+    np.testing.assert_allclose(c(env.cur_targets), go("cur_targets"), rtol=0, atol=1e-6)
+    np.testing.assert_allclose(c(env.prev_targets), go("prev_targets"), rtol=0, atol=1e-6)
+    np.testing.assert_allclose(c(env.dof_state), go("dof_state"), rtol=0, atol=1e-6)
+    ref_obs = go("obs") if obs_type == "full_state" else go(f"obs_{obs_type}")
+    obs = c(env.obs_buf).copy()
+    # fingertip block: forward kinematics in fp32 (3e-5) and a quaternion's overall sign is free
+    ft0 = {"full_state": 96, "full": 72}.get(obs_type)
+    mask = np.ones(obs.shape[1], bool)
+    if ft0 is not None:
+        for f in range(5):
+            sl = slice(ft0 + 13 * f + 3, ft0 + 13 * f + 7)
+            sgn = np.sign((obs[:, sl] * ref_obs[:, sl]).sum(-1, keepdims=True))
+            obs[:, sl] *= sgn
+            mask[ft0 + 13 * f: ft0 + 13 * f + 13] = False
+        err = np.abs(obs[:, ~mask] - ref_obs[:, ~mask]) / np.maximum(1.0, np.abs(ref_obs[:, ~mask]))
+        assert err.max() < 1e-4, err.max()
+    else:
+        ft0 = {"full_no_vel": 42, "openai": 0}[obs_type]
+        mask[ft0:ft0 + 15] = False
+        assert np.abs(obs[:, ~mask] - ref_obs[:, ~mask]).max() < 5e-5
+    np.testing.assert_allclose(obs[:, mask], ref_obs[:, mask], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(c(env.obs_clipped), np.clip(c(env.obs_buf), -5.0, 5.0), rtol=0, atol=0)
+    if obs_type == "full_state":
+        np.testing.assert_allclose(c(env.rew_buf), go("rew"), rtol=3e-6, atol=3e-5)
+        assert np.array_equal(c(env.reset_buf), go("reset")) and np.array_equal(c(env.reset_goal_buf), go("reset_goal"))
+        assert np.array_equal(c(env.progress_buf), go("progress")) and np.array_equal(c(env.successes), go("successes"))
+        assert np.array_equal(c(env.timeout_buf), go("timeout"))
+        np.testing.assert_allclose(c(env.consecutive_successes)[0], go("cons")[0], rtol=1e-6)
+        assert float(env.extras["consecutive_successes"]) == pytest.approx(float(go("cons")[0]), rel=1e-6)
+    env.sim.close()
+
+
+def test_hand_env_runs_and_resets():
+    """The full ShadowHand env (physics on): finite, cubes that fall get reset, lanes agree."""
+    env = _make("ShadowHand", 512)
+    torch.manual_seed(0)
+    resets = 0
+    for k in range(120):
+        obs, rew, reset, extras = env.step(torch.rand(512, 20, device=env.device) * 2 - 1)
+        resets += int(reset.sum())
+    torch.cuda.synchronize()
+    assert torch.isfinite(obs["obs"]).all() and torch.isfinite(rew).all() and torch.isfinite(env.root_state_tensor).all()
+    assert obs["obs"].shape == (512, 211) and resets > 0
+    z = env.root_state_tensor.view(512, 3, 13)[:, 1, 2]
+    assert (z > 0.2).all()                       # nothing is left lying on the ground: fallen cubes were reset
+    assert "consecutive_successes" in extras
+    env.sim.close()

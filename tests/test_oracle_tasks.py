@@ -113,3 +113,44 @@ def test_anymal_terrain_restatement_matches_reference_methods():
     obs = T.anymal_observations(g["base_lin_vel"], g["base_ang_vel"], g["projected_gravity"], g["commands"], g["dof_pos"], g["dof_vel"],
                                 root, g["measured_heights"], g["actions"])
     assert np.allclose(obs, g["obs"], atol=2e-6)
+
+
+# ---------------------------------------------------------------------------------------------
+# ShadowHand: numpy restatement against the reference's own methods (tests/golden/shadow_hand.npz)
+@pytest.mark.parametrize("case", ["a", "b", "c"])
+def test_hand_step_restatement_matches_reference(case):
+    from tests.hand_common import golden_case, hand_setup, DT, SUBSTEPS, G as GRAV
+    from oracle.oracle import OracleSim
+    gold = np.load(os.path.join(G, "shadow_hand.npz"))
+    obs_types = ["full_state", "full", "full_no_vel", "openai"] if case == "a" else ["full_state"]
+    m, obj, tendons = hand_setup()
+    orc = OracleSim(m, DT, SUBSTEPS, GRAV, obj=obj, tendons=tendons)
+    for ot in obs_types:
+        st, P, actions = golden_case(gold, case, ot)
+        n = actions.shape[0]
+        a = T.hand_pre_physics(st, actions, P)
+        out = lambda k: gold[f"{case}_out_{k}"]
+        assert np.array_equal(st["root"].reshape(-1, 13)[1::3][:, 7:], out("root")[1::3][:, 7:])
+        np.testing.assert_allclose(st["root"].reshape(-1, 13), out("root"), rtol=0, atol=2e-7)
+        np.testing.assert_allclose(st["goal_states"], out("goal_states"), rtol=0, atol=2e-7)
+        np.testing.assert_allclose(st["cur_targets"], out("cur_targets"), rtol=0, atol=3e-7)
+        np.testing.assert_allclose(st["prev_targets"], out("prev_targets"), rtol=0, atol=3e-7)
+        ds = out("dof_state").reshape(n, -1, 2)
+        np.testing.assert_allclose(st["dof_pos"], ds[..., 0], rtol=0, atol=2e-7)
+        np.testing.assert_allclose(st["dof_vel"], ds[..., 1], rtol=0, atol=2e-7)
+        # post_physics_step: progress, observations (fingertips by the oracle's forward kinematics), reward
+        st["progress"] += 1
+        root64 = np.ascontiguousarray(st["root"][:, 0].astype(np.float64))
+        dof64 = np.ascontiguousarray(np.stack([st["dof_pos"], st["dof_vel"]], -1).astype(np.float64))
+        ft = orc.body_states(root64, dof64)[:, gold["fingertips"]].astype(np.float32)
+        np.testing.assert_allclose(ft, out("fingertip_state"), rtol=0, atol=1e-6)
+        obs = T.hand_observations(st, a, ft, gold[f"{case}_in_sensors"], gold[f"{case}_in_dof_force"], P)
+        ref_obs = out("obs") if ot == "full_state" else out(f"obs_{ot}")
+        np.testing.assert_allclose(obs, ref_obs, rtol=0, atol=2e-6)
+        if ot == "full_state":
+            rew, cons = T.hand_reward(st, a, float(gold[f"{case}_in_cons"][0]), P)
+            np.testing.assert_allclose(rew, out("rew"), rtol=2e-6, atol=2e-5)
+            assert np.array_equal(st["reset"], out("reset")) and np.array_equal(st["reset_goal"], out("reset_goal"))
+            assert np.array_equal(st["progress"], out("progress")) and np.array_equal(st["successes"], out("successes"))
+            np.testing.assert_allclose(cons, out("cons")[0], rtol=1e-6)
+            assert out("reset").sum() > 10 and out("reset_goal").sum() > 10          # the case does exercise both branches
