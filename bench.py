@@ -26,6 +26,7 @@ WORKLOADS = {   # name -> (task, num_envs per GPU, algorithmic bytes per env-ste
     "humanoid": ("Humanoid", 8192, 1161),
     "cartpole": ("Cartpole", 16384, 89),
     "anymal": ("AnymalTerrain", 4096, 2250),
+    "shadow_hand": ("ShadowHand", 4096, 3640),    # BASELINE.json config 5: 32768 envs over 8 GPUs
 }
 METRIC = "env-steps/s at num_envs=16384 (Ant), 1/2/4/8 B200; %HBM roofline"
 
@@ -137,6 +138,55 @@ def cpu_pipeline(task, n_envs, steps, threads):
     return n_envs * steps / dt, dt
 
 
+def cpu_pipeline_hand(n_envs, steps, threads):
+    """ShadowHand control step on host cores: oracle physics of hand + cube, numpy restatement of the task."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from tests.hand_common import hand_setup, DT, SUBSTEPS, G
+    from oracle.oracle import OracleSim
+    from oracle import tasks_np as T
+    f32 = np.float32
+    m, obj, tendons = hand_setup()
+    sim = OracleSim(m, DT, SUBSTEPS, G, precision="f32", obj=obj, tendons=tendons, tendon_k=30.0, tendon_d=0.1, threads=threads)
+    D = m.ndof
+    names = list(m.dof_names)
+    rng = np.random.default_rng(42)
+    root = np.zeros((n_envs, 3, 13), f32); root[:, :, 6] = 1
+    root[:, 0, 0:3] = [0, 0, 0.5]; root[:, 0, 3:7] = m.default_root_quat
+    obj_init = np.zeros((n_envs, 13), f32); obj_init[:, 0:3] = [0, -0.39, 0.6]; obj_init[:, 6] = 1
+    goal_init = obj_init.copy(); goal_init[:, 2] -= 0.04
+    st = dict(root=root, dof_pos=np.zeros((n_envs, D), f32), dof_vel=np.zeros((n_envs, D), f32), cur_targets=np.zeros((n_envs, D), f32),
+              prev_targets=np.zeros((n_envs, D), f32), goal_states=goal_init.copy(), reset=np.ones(n_envs, np.int64),
+              reset_goal=np.ones(n_envs, np.int64), progress=np.zeros(n_envs, np.int64), successes=np.zeros(n_envs, f32),
+              reset_count=np.zeros(n_envs, np.int32), goal_reset_count=np.zeros(n_envs, np.int32))
+    P = dict(seed=42, goal_init=goal_init, object_init=obj_init, goal_displacement=f32([-0.2, -0.06, 0.12]), reset_position_noise=0.01,
+             reset_dof_pos_noise=0.2, reset_dof_vel_noise=0.0, lower=m.lower[1:].astype(f32), upper=m.upper[1:].astype(f32),
+             default_pos=np.zeros(D, f32), default_vel=np.zeros(D, f32), clip_actions=1.0,
+             actuated=np.array([names.index(j) for j in m.actuator_joint]), use_relative_control=False, dof_speed_scale=20.0, dt=DT,
+             act_moving_average=1.0, obs_type="full_state", vel_obs_scale=0.2, force_torque_obs_scale=10.0, dist_reward_scale=-10.0,
+             rot_reward_scale=1.0, rot_eps=0.1, action_penalty_scale=-0.0002, success_tolerance=0.1, reach_goal_bonus=250.0,
+             fall_dist=0.24, fall_penalty=0.0, max_consecutive_successes=0, max_episode_length=600.0, av_factor=0.1)
+    cons = f32(0)
+    ft_idx = m.sensor_body
+
+    def one():
+        nonlocal cons
+        a = T.hand_pre_physics(st, rng.uniform(-1, 1, size=(n_envs, 20)).astype(f32), P)
+        hand = np.ascontiguousarray(st["root"][:, 0]); o = np.ascontiguousarray(st["root"][:, 1])
+        dof = np.ascontiguousarray(np.stack([st["dof_pos"], st["dof_vel"]], -1))
+        out = sim.simulate(hand, dof, target=st["cur_targets"], obj=o)
+        st["root"][:, 1] = o; st["dof_pos"][:] = dof[..., 0]; st["dof_vel"][:] = dof[..., 1]
+        st["progress"] += 1
+        ft = out["body_state"][:, ft_idx]
+        T.hand_observations(st, a, ft, out["sensor"], out["dof_force"], P)
+        _, cons = T.hand_reward(st, a, cons, P)
+    one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = time.perf_counter() - t0
+    return n_envs * steps / dt, dt
+
+
 def run_reference_arm(args):
     """`--impl reference`: the reference's CPU pipeline cannot run here (closed Isaac Gym binary,
     SURVEY.md 8c), so this arm times the CPU PORT of the path (oracle/) on all host cores."""
@@ -147,8 +197,9 @@ def run_reference_arm(args):
     cores = os.cpu_count() or 1
     n_sample = min(n_full, 4096)
     # warm-up + K steps, each step a bounded sample (n_sample envs) of the workload
-    cpu_pipeline(task, n_sample, max(1, args.warmup), cores)
-    v, secs = cpu_pipeline(task, n_sample, args.steps, cores)
+    pipe = (lambda n_, k_, c_: cpu_pipeline_hand(n_, k_, c_)) if task == "ShadowHand" else (lambda n_, k_, c_: cpu_pipeline(task, n_, k_, c_))
+    pipe(n_sample, max(1, args.warmup), cores)
+    v, secs = pipe(n_sample, args.steps, cores)
     line = {"metric": METRIC, "impl": "reference", "value": v, "unit": "env-steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -266,7 +317,9 @@ def run_gpu_arm(args):
         cores = os.cpu_count() or 1
         ns = n                                            # the workload's own env count ...
         ks = max(5, min(200, int(15000 * cores / ns)))    # ... for a bounded number of control steps (a few seconds of wall time)
-        v, secs = cpu_pipeline(task, ns, ks, cores) if task == "Ant" else (None, 0)
+        if task == "ShadowHand":
+            ks = max(3, min(50, int(1500 * cores / ns)))
+        v, secs = cpu_pipeline(task, ns, ks, cores) if task == "Ant" else (cpu_pipeline_hand(ns, ks, cores) if task == "ShadowHand" else (None, 0))
         line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
                                 "sample": f"{ns} envs x {ks} control steps, {secs:.1f} s (oracle f32 physics + numpy obs/reward)"}
     print(json.dumps(line), flush=True)

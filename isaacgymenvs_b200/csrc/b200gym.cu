@@ -81,8 +81,13 @@ __device__ __forceinline__ Stepper<L, HF, BLOCK, OBJ> make_stepper(const DevMode
     Stepper<L, HF, BLOCK, OBJ> st;
     st.m = sm; st.gr = Ground{sm, hf, sm->cps, -1.f};
     st.slots = &sm->slots[0][0]; st.links = sm->links;
-    st.ss = b2g_dyn_smem + threadIdx.x;
-    st.acc = b2g_dyn_smem + sm->ns * SLOT_F4 * BLOCK + threadIdx.x;
+    if (OBJ) {      // [link][k][env] layout: the env's column
+        st.ss = b2g_dyn_smem + threadIdx.x / L;
+        st.acc = b2g_dyn_smem + (sm->nl - 1) * SLOT_F4 * Stepper<L, HF, BLOCK, OBJ>::KS + threadIdx.x / L;
+    } else {
+        st.ss = b2g_dyn_smem + threadIdx.x;
+        st.acc = b2g_dyn_smem + sm->ns * SLOT_F4 * BLOCK + threadIdx.x;
+    }
     st.lane = lane;
     return st;
 }
@@ -597,7 +602,7 @@ extern "C" int64_t b2g_launch_count(const b2g_sim *sim) { return sim ? sim->laun
 // Build the lanes' slot programs: list-schedule the links over `L` lanes, critical path first; a lane
 // keeps following a chain (parent at step s-1 in the same lane -> state travels in registers), any
 // other parent/child relation goes through shared memory (parked inertia / pose / acceleration).
-static int schedule(const b2g_model *m, int L, DevModel &h) {
+static int schedule(const b2g_model *m, int L, DevModel &h, bool compact = false) {
     const int nl = m->nl;
     std::vector<int> height(nl, 1);
     for (int i = nl - 1; i >= 1; i--) height[m->parent[i]] = std::max(height[m->parent[i]], height[i] + 1);
@@ -636,20 +641,24 @@ static int schedule(const b2g_model *m, int L, DevModel &h) {
     std::vector<int> nacc(L, 0);
     bool need_root_acc = false;
     for (int i = 1; i < nl; i++) if (m->parent[i] == 0 && t_of[i] > 0) need_root_acc = true;
-    if (need_root_acc) { h.root_acc = 0; for (int l = 0; l < L; l++) nacc[l] = 1; }
+    // compact (env-wide) accumulator ids: per-lane ones take L consecutive ids, parked inertias one each
+    int gacc = 0;
+    if (compact && m->root_fixed) need_root_acc = false;                 // nothing collects a fixed root's children
+    if (need_root_acc) { h.root_acc = 0; for (int l = 0; l < L; l++) nacc[l] = 1; gacc = L; }
     for (int i = 1; i < nl; i++) {
         const int l = lane_of[i], s = t_of[i], p = m->parent[i];
         SlotRec &r = h.slots[s][l];
         if (p == 0) {
             r.parent = 0;
             r.out = (s == 0) ? -1 : h.root_acc;
+            if (compact && m->root_fixed) r.out = (s == 0) ? -1 : -2;
         } else {
             const int lp = lane_of[p], sp = t_of[p];
             r.parent = (lp << 8) | (sp + 1);
             if (lp != l) h.cross_lane = 1;
             if (lp == l && sp == s - 1) r.out = -1;
             else {
-                r.out = nacc[l]++;
+                r.out = compact ? gacc++ : nacc[l]++;
                 SlotRec &pr = h.slots[sp][lp];
                 int c = 0; while (c < MAX_CHILD_REFS && pr.child[c] >= 0) c++;
                 if (c == MAX_CHILD_REFS) return -2;
@@ -660,6 +669,7 @@ static int schedule(const b2g_model *m, int L, DevModel &h) {
     }
     h.nacc = 0;
     for (int l = 0; l < L; l++) h.nacc = std::max(h.nacc, nacc[l]);
+    if (compact) h.nacc = gacc;
     return 0;
 }
 static int pick_lanes(const b2g_model *m, bool single) {
@@ -705,7 +715,8 @@ extern "C" int b2g_create_ext(const b2g_model *m, const b2g_model_ext *ext, cons
     h.ground_mu = sp->ground_friction;
     // topology
     const char *force1 = getenv("B2G_SINGLE_LANE");
-    if (schedule(m, pick_lanes(m, force1 && force1[0] == '1'), h) != 0) { delete s; return fail(B2G_E_INVALID, "b2g_create: the articulation does not fit the slot program limits"); }
+    const bool compact = ext && ext->obj_actor > 0;                     // [link][k][env] state layout (Stepper<.., OBJ>)
+    if (schedule(m, pick_lanes(m, force1 && force1[0] == '1'), h, compact) != 0) { delete s; return fail(B2G_E_INVALID, "b2g_create: the articulation does not fit the slot program limits"); }
     s->lanes = h.lanes;
     h.root_stride = ext ? ext->actors_per_env : 1;
     h.obj_on = 0; h.obj_acc = h.obj_pose_acc = -1;
@@ -714,7 +725,7 @@ extern "C" int b2g_create_ext(const b2g_model *m, const b2g_model_ext *ext, cons
             h.obj_on = 1; h.obj_row = ext->obj_actor; h.obj_gravity_on = ext->obj_gravity_on;
             h.obj_mass = ext->obj_mass; h.obj_kn = ext->obj_kn; h.obj_cn = ext->obj_cn; h.obj_mu = ext->obj_mu;
             for (int c = 0; c < 3; c++) { h.obj_I[c] = ext->obj_inertia[c]; h.obj_half[c] = ext->obj_half[c]; }
-            h.obj_acc = h.nacc; h.obj_pose_acc = h.nacc + 1; h.nacc += 2;
+            h.obj_acc = h.nacc; h.obj_pose_acc = h.nacc + h.lanes; h.nacc += h.lanes + 1;   // env-wide ids: one sum per lane, one pose
             // the object's gravity does not follow the articulation's disable_gravity flag (shadow_hand.py:239,279-282)
             for (int c = 0; c < 3; c++) h.obj_g[c] = ext->obj_gravity_on ? sp->gravity[c] : 0.f;
         }
@@ -740,7 +751,23 @@ extern "C" int b2g_create_ext(const b2g_model *m, const b2g_model_ext *ext, cons
         }
         if (h.nten > 0 && !h.obj_on) { delete s; return fail(B2G_E_UNSUPPORTED, "b2g_create_ext: tendons are only compiled into the object-enabled kernels"); }
     }
-    {   // CTA size: the per-thread slot state must fit in shared memory, preferably several CTAs per SM
+    if (compact) {
+        // per-env rows; one CTA = `blk / lanes` envs (+1 column of padding when that is even).  Prefer the CTA size that
+        // puts the most envs on an SM (registers: ~248 per thread in these kernels -> at most 256 threads per SM)
+        const size_t rows = (size_t)(h.nl - 1) * SLOT_F4 + (size_t)h.nacc * ACC_F4;
+        const size_t static_smem = sizeof(DevModel) + 64;
+        int best = 0; size_t best_envs = 0;
+        for (int blk : {128, 64, 32}) {
+            const int epb = blk / h.lanes;
+            if (epb < 1) continue;
+            const size_t bytes = rows * (size_t)(epb | 1) * sizeof(float4);
+            if (bytes + static_smem > 200 * 1024) continue;
+            const size_t ctas = std::min<size_t>((227 * 1024) / (bytes + static_smem + 1024), 256 / blk);
+            if (ctas * epb > best_envs) { best_envs = ctas * epb; best = blk; }
+        }
+        if (!best) { delete s; return fail(B2G_E_INVALID, "b2g_create: articulation too large for shared-memory slot state"); }
+        s->block = best; s->dyn_smem = rows * (size_t)((best / h.lanes) | 1) * sizeof(float4);
+    } else {   // CTA size: the per-thread slot state must fit in shared memory, preferably several CTAs per SM
         const size_t per_thread = ((size_t)h.ns * SLOT_F4 + (size_t)h.nacc * ACC_F4) * sizeof(float4);
         int blk = 128;
         while (blk > 32 && per_thread * blk > 104 * 1024) blk >>= 1;

@@ -443,13 +443,25 @@ struct Stepper {
     float4 *acc;              // this thread's column of the accumulator pool
     int lane;
 
-    __device__ __forceinline__ float4 &S4(int s, int k) const { return ss[(s * SLOT_F4 + k) * BLOCK]; }
-    // slot state of another lane of the same env (cross-lane parents): thread column offset by (ln - lane)
-    __device__ __forceinline__ const float4 &S4x(int ln, int s, int k) const { return ss[(s * SLOT_F4 + k) * BLOCK + (ln - lane)]; }
-    __device__ __forceinline__ float4 &A4(int a, int k) const { return acc[(a * ACC_F4 + k) * BLOCK]; }
-    __device__ __forceinline__ const float4 &A4x(int ln, int a, int k) const { return acc[(a * ACC_F4 + k) * BLOCK + (ln - lane)]; }
+    // Two layouts of the per-slot state.  Default: [slot][k][thread] -- every thread owns ns rows (idle slots included),
+    // 128-bit accesses are conflict-free.  OBJ (few, large environments: the shared memory per env decides how many
+    // fit on the chip): [link][k][env] -- one row per LINK of the env, whichever lane processes it, so no storage
+    // for idle slots; ss / acc then point at the ENV's column and accumulators carry env-wide ids.
+    static constexpr int EPB = BLOCK / L;
+    static constexpr int KS = OBJ ? (EPB | 1) : BLOCK;       // float4 stride between consecutive k (odd in OBJ mode: banks)
     __device__ __forceinline__ const SlotRec &rec(int s) const { return slots[s * MAX_LANES + lane]; }
     __device__ __forceinline__ int link_of(int s) const { return slots[s * MAX_LANES + lane].link; }
+    __device__ __forceinline__ float4 &S4(int s, int k) const {
+        return OBJ ? ss[((link_of(s) - 1) * SLOT_F4 + k) * KS] : ss[(s * SLOT_F4 + k) * KS];
+    }
+    // slot state of another lane of the same env (cross-lane parents)
+    __device__ __forceinline__ const float4 &S4x(int ln, int s, int k) const {
+        return OBJ ? ss[((slots[s * MAX_LANES + ln].link - 1) * SLOT_F4 + k) * KS] : ss[(s * SLOT_F4 + k) * KS + (ln - lane)];
+    }
+    __device__ __forceinline__ float4 &A4(int a, int k) const { return acc[(a * ACC_F4 + k) * KS]; }
+    __device__ __forceinline__ const float4 &A4x(int ln, int a, int k) const { return OBJ ? acc[(a * ACC_F4 + k) * KS] : acc[(a * ACC_F4 + k) * KS + (ln - lane)]; }
+    // accumulators every lane owns one of (OBJ layout: consecutive env-wide ids, one per lane)
+    __device__ __forceinline__ int lane_acc(int a) const { return OBJ ? a + lane : a; }
 
     __device__ __forceinline__ void set_joint(int s, float q, float qd, float act) const {
         float4 v = S4(s, 6); v.z = q; v.w = qd; S4(s, 6) = v;
@@ -615,12 +627,16 @@ struct Stepper {
         float Ro[9]; quat_to_mat(ob.q, Ro);
         const float c[3] = {ob.p[0] - rs.rp[0], ob.p[1] - rs.rp[1], ob.p[2] - rs.rp[2]};
         float wxc[3]; cross(ob.w, c, wxc);
-        const int a = m->obj_pose_acc;
-        A4(a, 0) = make_float4(Ro[0], Ro[1], Ro[2], Ro[3]);
-        A4(a, 1) = make_float4(Ro[4], Ro[5], Ro[6], Ro[7]);
-        A4(a, 2) = make_float4(Ro[8], c[0], c[1], c[2]);
-        A4(a, 3) = make_float4(ob.w[0], ob.w[1], ob.w[2], ob.v[0] - wxc[0]);
-        A4(a, 4) = make_float4(ob.v[1] - wxc[1], ob.v[2] - wxc[2], 0.f, 0.f);
+        const int a = m->obj_pose_acc;                       // one copy per env: lane 0 writes, every lane reads
+        if (L > 1) __syncwarp();                             // the previous sub-step's readers are done
+        if (lane == 0) {
+            A4(a, 0) = make_float4(Ro[0], Ro[1], Ro[2], Ro[3]);
+            A4(a, 1) = make_float4(Ro[4], Ro[5], Ro[6], Ro[7]);
+            A4(a, 2) = make_float4(Ro[8], c[0], c[1], c[2]);
+            A4(a, 3) = make_float4(ob.w[0], ob.w[1], ob.w[2], ob.v[0] - wxc[0]);
+            A4(a, 4) = make_float4(ob.v[1] - wxc[1], ob.v[2] - wxc[2], 0.f, 0.f);
+        }
+        if (L > 1) __syncwarp();
     }
     __device__ __forceinline__ void obj_load_pose(ObjPose &P) const {
         const int ai = m->obj_pose_acc;
@@ -656,7 +672,7 @@ struct Stepper {
             for (int c = 0; c < 21; c++) IA[c] += dM[c];
 #pragma unroll
             for (int c = 0; c < 3; c++) { pa[c] -= rxF[c]; pl[c] -= F0[c]; }
-            const int ai = m->obj_acc;
+            const int ai = lane_acc(m->obj_acc);
             float t[28];
 #pragma unroll
             for (int c = 0; c < 21; c++) t[c] = dM[c];
@@ -730,7 +746,7 @@ struct Stepper {
         {
             float t[28];
 #pragma unroll
-            for (int k = 0; k < ACC_F4; k++) { const float4 v = A4(m->obj_acc, k); t[4 * k] = v.x; t[4 * k + 1] = v.y; t[4 * k + 2] = v.z; t[4 * k + 3] = v.w; }
+            for (int k = 0; k < ACC_F4; k++) { const float4 v = A4(lane_acc(m->obj_acc), k); t[4 * k] = v.x; t[4 * k + 1] = v.y; t[4 * k + 2] = v.z; t[4 * k + 3] = v.w; }
 #pragma unroll
             for (int c = 0; c < 21; c++) Io[c] = t[c];
 #pragma unroll
@@ -817,16 +833,17 @@ struct Stepper {
         if (OBJ) {
             obj_store_pose(rs, *ob);
 #pragma unroll
-            for (int k = 0; k < ACC_F4; k++) A4(m->obj_acc, k) = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int k = 0; k < ACC_F4; k++) A4(lane_acc(m->obj_acc), k) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
 
         // ================= pass 2: articulated inertias (leaves -> root)
         // A slot's projected inertia either travels in registers to the next-lower slot of the lane
         // (chains; finally from slot 0 to the root) or is parked in one of this thread's accumulators,
         // from where its parent -- possibly in another lane -- collects it (SlotRec::child).
-        if (m->root_acc >= 0) {
+        const int racc = m->root_acc >= 0 ? lane_acc(m->root_acc) : -1;
+        if (racc >= 0) {
 #pragma unroll
-            for (int k = 0; k < ACC_F4; k++) A4(m->root_acc, k) = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int k = 0; k < ACC_F4; k++) A4(racc, k) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         float IA[21], pa[3], pl[3];
 #pragma unroll
@@ -884,8 +901,10 @@ struct Stepper {
                     const float ud = u_ * di;
 #pragma unroll
                     for (int c = 0; c < 3; c++) { qa[c] += ya[c] + Ua[c] * ud; ql[c] += yl[c] + Ul[c] * ud; }
-                    carry = (sr.out < 0);
-                    if (carry) {
+                    carry = (sr.out == -1);
+                    if (sr.out == -2) {
+                        // child of a fixed root: nothing collects its inertia
+                    } else if (carry) {
 #pragma unroll
                         for (int c = 0; c < 21; c++) IA[c] = I[c];
 #pragma unroll
@@ -900,9 +919,9 @@ struct Stepper {
                         if (sr.out == m->root_acc) {                      // several root children share the root accumulator
 #pragma unroll
                             for (int k = 0; k < ACC_F4; k++) {
-                                float4 v = A4(sr.out, k);
+                                float4 v = A4(racc, k);
                                 v.x += t[4 * k]; v.y += t[4 * k + 1]; v.z += t[4 * k + 2]; v.w += t[4 * k + 3];
-                                A4(sr.out, k) = v;
+                                A4(racc, k) = v;
                             }
                         } else {
 #pragma unroll
@@ -936,10 +955,10 @@ struct Stepper {
             for (int c = 0; c < 21; c++) IA[c] += I[c];               // IA holds slot 0's contribution (or zeros)
 #pragma unroll
             for (int c = 0; c < 3; c++) { pa[c] += qa[c]; pl[c] += ql[c]; }
-            if (m->root_acc >= 0) {
+            if (racc >= 0) {
                 float t[28];
 #pragma unroll
-                for (int k = 0; k < ACC_F4; k++) { const float4 v = A4(m->root_acc, k); t[4 * k] = v.x; t[4 * k + 1] = v.y; t[4 * k + 2] = v.z; t[4 * k + 3] = v.w; }
+                for (int k = 0; k < ACC_F4; k++) { const float4 v = A4(racc, k); t[4 * k] = v.x; t[4 * k + 1] = v.y; t[4 * k + 2] = v.z; t[4 * k + 3] = v.w; }
 #pragma unroll
                 for (int c = 0; c < 21; c++) IA[c] += t[c];
 #pragma unroll
