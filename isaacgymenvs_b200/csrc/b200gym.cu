@@ -677,7 +677,7 @@ static int pick_lanes(const b2g_model *m, bool single) {
     int root_children = 0;
     for (int i = 1; i < m->nl; i++) if (m->parent[i] == 0) root_children++;
     const char *env = getenv("B2G_LANES");
-    if (env && (env[0] == '1' || env[0] == '2' || env[0] == '4') && env[1] == 0) return env[0] - '0';
+    if (env && (env[0] == '1' || env[0] == '2' || env[0] == '4' || env[0] == '8') && env[1] == 0) return env[0] - '0';
     if (m->nl - 1 >= 16) return 4;                 // long trees (Humanoid, hands): chains run in parallel lanes
     if (root_children >= 4) return 4;              // quadrupeds
     if (root_children >= 2) return 2;
@@ -732,6 +732,7 @@ extern "C" int b2g_create_ext(const b2g_model *m, const b2g_model_ext *ext, cons
         h.nbox = ext->nbox;
         for (int b = 0; b < ext->nbox; b++) {
             h.box_link[b] = ext->box_link[b];
+            if (ext->box_link[b] < 0 || ext->box_link[b] >= m->nl) { delete s; return fail(B2G_E_INVALID, "b2g_create_ext: box link out of range"); }
             const float *q = ext->box_quat[b];
             float x = q[0], y = q[1], z = q[2], w = q[3], n = sqrtf(x * x + y * y + z * z + w * w);
             x /= n; y /= n; z /= n; w /= n;
@@ -820,6 +821,21 @@ extern "C" int b2g_create_ext(const b2g_model *m, const b2g_model_ext *ext, cons
         LinkC &l = h.links[m->cp_link[src]];
         if (l.cp_end == 0 && l.cp_begin == 0) l.cp_begin = k;
         l.cp_end = k + 1;
+    }
+    if (ext) for (int b = 0; b < ext->nbox; b++) h.links[ext->box_link[b]].flags |= LF_HAS_BOX;
+    {   // reach: bound on the distance of any contact sphere's far side from the root origin, over all joint positions
+        std::vector<float> dist(m->nl, 0.f);
+        for (int i = 1; i < m->nl; i++) {
+            const float *lp = m->lpos + 3 * i;
+            float d = sqrtf(lp[0] * lp[0] + lp[1] * lp[1] + lp[2] * lp[2]);
+            if (m->jtype[i] == 1) d += m->limited[i] ? std::max(fabsf(m->lower[i]), fabsf(m->upper[i])) : 1e30f;
+            dist[i] = dist[m->parent[i]] + d;
+        }
+        h.reach = 0.f;
+        for (int k = 0; k < m->ncp; k++) {
+            const float *cp = m->cp_pos + 3 * k;
+            h.reach = std::max(h.reach, dist[m->cp_link[k]] + sqrtf(cp[0] * cp[0] + cp[1] * cp[1] + cp[2] * cp[2]) + m->cp_radius[k]);
+        }
     }
     // height field
     if (sp->hf_samples) {
@@ -912,7 +928,9 @@ extern "C" int b2g_simulate(b2g_sim *s, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const int N = s->num_envs, blk = s->block, grid = (N * s->lanes + blk - 1) / blk;
     if (s->hm.obj_on) {
-        if (s->lanes == 4 && blk == 128) B2G_LAUNCH((simulate_kernel<4, false, 128, true>), s->dm, s->d_hf, s->buf, N);
+        if (s->lanes == 8 && blk == 128) B2G_LAUNCH((simulate_kernel<8, false, 128, true>), s->dm, s->d_hf, s->buf, N);
+        else if (s->lanes == 8 && blk == 64) B2G_LAUNCH((simulate_kernel<8, false, 64, true>), s->dm, s->d_hf, s->buf, N);
+        else if (s->lanes == 4 && blk == 128) B2G_LAUNCH((simulate_kernel<4, false, 128, true>), s->dm, s->d_hf, s->buf, N);
         else if (s->lanes == 4 && blk == 64) B2G_LAUNCH((simulate_kernel<4, false, 64, true>), s->dm, s->d_hf, s->buf, N);
         else if (s->lanes == 4 && blk == 32) B2G_LAUNCH((simulate_kernel<4, false, 32, true>), s->dm, s->d_hf, s->buf, N);
         else if (s->lanes == 1 && blk == 32) B2G_LAUNCH((simulate_kernel<1, false, 32, true>), s->dm, s->d_hf, s->buf, N);
@@ -1026,7 +1044,9 @@ static int hand_step(b2g_sim *s, const float *actions, void *stream) {
     CUDA_TRY(cudaSetDevice(s->device));
     cudaStream_t st = (cudaStream_t)stream;
     const int blk = s->block, grid = ((int)N * s->lanes + blk - 1) / blk;
-    if (s->lanes == 4 && blk == 128) B2G_LAUNCH((hand_step_kernel<4, 128>), s->dm, s->buf, P, s->hand_dev, actions, (int)N);
+    if (s->lanes == 8 && blk == 128) B2G_LAUNCH((hand_step_kernel<8, 128>), s->dm, s->buf, P, s->hand_dev, actions, (int)N);
+    else if (s->lanes == 8 && blk == 64) B2G_LAUNCH((hand_step_kernel<8, 64>), s->dm, s->buf, P, s->hand_dev, actions, (int)N);
+    else if (s->lanes == 4 && blk == 128) B2G_LAUNCH((hand_step_kernel<4, 128>), s->dm, s->buf, P, s->hand_dev, actions, (int)N);
     else if (s->lanes == 4 && blk == 64) B2G_LAUNCH((hand_step_kernel<4, 64>), s->dm, s->buf, P, s->hand_dev, actions, (int)N);
     else if (s->lanes == 4 && blk == 32) B2G_LAUNCH((hand_step_kernel<4, 32>), s->dm, s->buf, P, s->hand_dev, actions, (int)N);
     else if (s->lanes == 1 && blk == 32) B2G_LAUNCH((hand_step_kernel<1, 32>), s->dm, s->buf, P, s->hand_dev, actions, (int)N);

@@ -38,12 +38,12 @@ constexpr int MAX_BOX = 4;      // box primitives of the articulation the free o
 constexpr int MAX_TEN = 4;      // fixed two-joint tendons
 constexpr int MAX_SENS = 8;
 constexpr int MAX_SLOTS = 24;
-constexpr int MAX_LANES = 4;
+constexpr int MAX_LANES = 8;
 
 // ---------------------------------------------------------------------------------------------
 // model constants (global memory -> shared memory at kernel start; strides are odd so that the
 // L lanes of an env, which read different links at the same time, hit different banks)
-enum : int { LF_SLIDE = 1, LF_LIMITED = 2, LF_POSDRIVE = 4, LF_R0_IDENTITY = 8 };
+enum : int { LF_SLIDE = 1, LF_LIMITED = 2, LF_POSDRIVE = 4, LF_R0_IDENTITY = 8, LF_HAS_BOX = 16 };
 struct LinkC {
     float R0[9];          // link frame in the parent link frame at q = 0, row-major
     float lpos[3];
@@ -97,6 +97,7 @@ struct alignas(16) DevModel {
     float ground_mu;      // friction of the ground material (combined per contact as the average, PhysX default)
     // ---- optional second actor per env: a free box (ShadowHand's cube, shadow_hand.py:372-378) + fixed tendons
     int obj_on, obj_gravity_on, nbox, nten;
+    float reach;          // no contact sphere can be farther than this from the root origin (ground test short-cut)
     int root_stride;      // actors per env in the root-state tensor (row of the articulation = env * root_stride)
     int obj_row;          // the object's row inside an env's actors
     int obj_acc, obj_pose_acc;             // accumulator indices: object inertia/bias sum, object pose of the sub-step
@@ -331,6 +332,7 @@ template <int L>
 __device__ __forceinline__ float lane_sum(float v) {
     if (L >= 2) v += __shfl_xor_sync(0xffffffffu, v, 1);
     if (L >= 4) v += __shfl_xor_sync(0xffffffffu, v, 2);
+    if (L >= 8) v += __shfl_xor_sync(0xffffffffu, v, 4);
     return v;
 }
 
@@ -716,7 +718,7 @@ struct Stepper {
             const float r[3] = {pc[0] - cp.radius * n[0], pc[1] - cp.radius * n[1], pc[2] - cp.radius * n[2]};
             obj_contact_point<ACCUM>(P, r, n, pen, x, vw, vl, IA, pa, pl, aw, al, F, T);
         }
-        if (cp_first != 0) return;
+        if (cp_first != 0 || !(lk.flags & LF_HAS_BOX)) return;
 #pragma unroll 1
         for (int b = 0; b < m->nbox; b++) {
             if (m->box_link[b] != li) continue;
@@ -830,6 +832,9 @@ struct Stepper {
         const bool fixed = m->root_fixed != 0;
 
         pass1(rs);
+        // OBJ kernels (table-top manipulators): when the root is higher than the articulation can reach, skip the
+        // ground scan of every link
+        const bool ground = !OBJ || HF || rs.rp[2] < m->reach;
         if (OBJ) {
             obj_store_pose(rs, *ob);
 #pragma unroll
@@ -863,7 +868,7 @@ struct Stepper {
                     float I[21], qa[3], ql[3];
                     link_inertia(lk, lk.mass, 1.f, R, x, vw, vl, g, I, qa, ql);
                     float dummy[3];
-                    link_contacts<true, HF>(m, gr, lk, rs.rp, R, x, vw, vl, I, qa, ql, dummy, dummy, dummy, dummy, 0, 1);
+                    if (ground) link_contacts<true, HF>(m, gr, lk, rs.rp, R, x, vw, vl, I, qa, ql, dummy, dummy, dummy, dummy, 0, 1);
                     if (OBJ) obj_link_contacts<true>(lk, sr.link, R, x, vw, vl, I, qa, ql, dummy, dummy, dummy, dummy, 0, 1);
                     if (carry) {
 #pragma unroll
@@ -949,7 +954,7 @@ struct Stepper {
             const float xr[3] = {0.f, 0.f, 0.f};
             root_pose(rs, Rr, vwr, vlr);
             link_inertia(lk, mine ? lk.mass : 0.f, mine ? 1.f : 0.f, Rr, xr, vwr, vlr, g, I, qa, ql);
-            link_contacts<true, HF>(m, gr, lk, rs.rp, Rr, xr, vwr, vlr, I, qa, ql, dummy, dummy, dummy, dummy, lane, L);
+            if (ground) link_contacts<true, HF>(m, gr, lk, rs.rp, Rr, xr, vwr, vlr, I, qa, ql, dummy, dummy, dummy, dummy, lane, L);
             if (OBJ) obj_link_contacts<true>(lk, 0, Rr, xr, vwr, vlr, I, qa, ql, dummy, dummy, dummy, dummy, lane, L);
 #pragma unroll
             for (int c = 0; c < 21; c++) IA[c] += I[c];               // IA holds slot 0's contribution (or zeros)
@@ -977,7 +982,7 @@ struct Stepper {
             }
             if (LAST) {
                 float F[3] = {0.f, 0.f, 0.f}, T[3] = {0.f, 0.f, 0.f};
-                link_contacts<false, HF>(m, gr, lk, rs.rp, Rr, xr, vwr, vlr, I, qa, ql, awr, alr, F, T, lane, L);
+                if (ground) link_contacts<false, HF>(m, gr, lk, rs.rp, Rr, xr, vwr, vlr, I, qa, ql, awr, alr, F, T, lane, L);
                 if (OBJ) obj_link_contacts<false>(lk, 0, Rr, xr, vwr, vlr, I, qa, ql, awr, alr, F, T, lane, L);
 #pragma unroll
                 for (int c = 0; c < 3; c++) { F[c] = lane_sum<L>(F[c]); T[c] = lane_sum<L>(T[c]); }
@@ -1026,7 +1031,7 @@ struct Stepper {
                         if (lk.cp_end > lk.cp_begin && (lk.sensor >= 0 || o.net_contact)) {
                             float R[9], x[3], F[3] = {0.f, 0.f, 0.f}, T[3] = {0.f, 0.f, 0.f}, dI[1], d3[3];
                             load_pose(s, R, x, vw, vl);
-                            link_contacts<false, HF>(m, gr, lk, rs.rp, R, x, vw, vl, dI, d3, d3, awc, alc, F, T, 0, 1);
+                            if (ground) link_contacts<false, HF>(m, gr, lk, rs.rp, R, x, vw, vl, dI, d3, d3, awc, alc, F, T, 0, 1);
                             if (OBJ) obj_link_contacts<false>(lk, li, R, x, vw, vl, dI, d3, d3, awc, alc, F, T, 0, 1);
                             emit_wrench(li, lk, R, F, T, o);
                         } else if (lk.sensor >= 0 || (o.net_contact && m->link_body[li] >= 0)) {
