@@ -187,7 +187,7 @@ struct TileArgs {
 };
 
 template <int L, bool HF, bool HUM, int BLOCK, bool TILES>
-__global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? B2G_MINBLOCKS : 1)) loco_step_kernel(
+__global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? B2G_MINBLOCKS : (BLOCK == 64 && !HUM ? 2 * B2G_MINBLOCKS : 1))) loco_step_kernel(
     const DevModel *__restrict__ gm, const int16_t *__restrict__ hf, Buffers B, const __grid_constant__ b2g_task_params P,
     const float *__restrict__ actions_in, int N, TileArgs ta) {
     __shared__ alignas(8) uint64_t mbar;
@@ -771,6 +771,8 @@ extern "C" int b2g_create_ext(const b2g_model *m, const b2g_model_ext *ext, cons
     } else {   // CTA size: the per-thread slot state must fit in shared memory, preferably several CTAs per SM
         const size_t per_thread = ((size_t)h.ns * SLOT_F4 + (size_t)h.nacc * ACC_F4) * sizeof(float4);
         int blk = 128;
+        const char *fb = getenv("B2G_BLOCK");                       // experiment hook: force a smaller CTA
+        if (fb && (atoi(fb) == 64 || atoi(fb) == 32)) blk = atoi(fb);
         while (blk > 32 && per_thread * blk > 104 * 1024) blk >>= 1;
         if (per_thread * blk > 200 * 1024) { delete s; return fail(B2G_E_INVALID, "b2g_create: articulation too large for shared-memory slot state"); }
         s->block = blk; s->dyn_smem = per_thread * blk;
@@ -1132,6 +1134,7 @@ extern "C" int b2g_task_step(b2g_sim *s, const float *actions, void *stream) {
 #define LOCO(LN, HM, BK) do { if (tiles) LOCO_T(LN, HM, BK, true); else LOCO_T(LN, HM, BK, false); } while (0)
         if (s->d_hf) return fail(B2G_E_UNSUPPORTED, "locomotion tasks run on the ground plane");
         if (!hum && s->lanes == 4 && blk == 128) LOCO(4, false, 128);
+        else if (!hum && s->lanes == 4 && blk == 64) LOCO(4, false, 64);
         else if (!hum && s->lanes == 1 && blk == 128) LOCO(1, false, 128);
         else if (hum && s->lanes == 4 && blk == 128) LOCO(4, true, 128);
         else if (hum && s->lanes == 4 && blk == 64) LOCO(4, true, 64);

@@ -80,7 +80,7 @@ typedef struct {
      * articulation's contact spheres, with its box primitives and with the ground */
     int obj_on, obj_gravity_on, nbx, pad1;
     double obj_mass, obj_inertia[3], obj_half[3], obj_kn, obj_cn, obj_mu;
-    const int *box_link;                    /* nbx */
+    const int *box_link, *box_body;         /* nbx: link carrying the box, body it belongs to */
     const double *box_pos, *box_quat, *box_half;   /* nbx x 3,4,3 (link frame) */
     /* fixed tendons (shared.xml:54-69): length = c0 q[d0] + c1 q[d1], penalty outside [lo, hi] */
     int nten, pad2;
@@ -339,7 +339,7 @@ static void substep(const OracleModel *m, real h, real *root, real *dof, const r
 
     /* ---- the free object: contacts with the articulation (block-Jacobi implicit: each body sees its own
      * acceleration implicitly, the other's velocity explicitly), with the ground, then its own 6x6 solve */
-    static __thread real oF0[MAXCP + 64][3], oG[MAXCP + 64][9], oJ[MAXCP + 64][18]; static __thread int olink[MAXCP + 64], obody[MAXCP + 64], ocp[MAXCP + 64];
+    static __thread real oF0[MAXCP + 64][3], oG[MAXCP + 64][9], oJ[MAXCP + 64][18]; static __thread int olink[MAXCP + 64], obody[MAXCP + 64]; static __thread real oPc[MAXCP + 64][3];
     int noc = 0;
     real Ao[36], bo[6], Ro[9];
     if (m->obj_on && obj) {
@@ -384,7 +384,7 @@ static void substep(const OracleModel *m, real h, real *root, real *dof, const r
                 for (int a_ = 0; a_ < 6; a_++) for (int b_ = 0; b_ < 6; b_++) { real s_ = 0; for (int k = 0; k < 3; k++) s_ += Jo_[6 * k + a_] * GJo_[6 * k + b_]; Ao[6 * a_ + b_] += h * s_; } \
                 for (int a_ = 0; a_ < 6; a_++) { real s_ = 0; for (int k = 0; k < 3; k++) s_ += Jo_[6 * k + a_] * F0_[k]; bo[a_] -= s_; } \
                 memcpy(oF0[noc], F0_, sizeof(F0_)); memcpy(oG[noc], Gw_, sizeof(Gw_)); memcpy(oJ[noc], J_, sizeof(J_));          \
-                olink[noc] = LI; obody[noc] = BI; ocp[noc] = CPI; noc++;                                                          \
+                olink[noc] = LI; obody[noc] = BI; memcpy(oPc[noc], (PC), 3 * sizeof(real)); noc++;                                \
             }                                                                                                                    \
         } while (0)
         /* S1: the articulation's contact spheres against the object's box */
@@ -409,7 +409,7 @@ static void substep(const OracleModel *m, real h, real *root, real *dof, const r
                 mat3_vec(Ro, lc, pc); for (int k = 0; k < 3; k++) pc[k] += obj[k];
                 if (!sphere_box(pc, 0, xb, Rwb, bh, &pen, nout)) continue;       /* corner inside the link's box */
                 real nrm[3] = {-nout[0], -nout[1], -nout[2]};                  /* force on the LINK pushes it away from the corner */
-                OBJ_CONTACT(i, -1, -1, pc, nrm, pen, (real)m->obj_mu);
+                OBJ_CONTACT(i, m->box_body[b], -1, pc, nrm, pen, (real)m->obj_mu);
             }
         }
 #undef OBJ_CONTACT
@@ -496,15 +496,9 @@ static void substep(const OracleModel *m, real h, real *root, real *dof, const r
             real Ja[3], F[3];
             for (int a_ = 0; a_ < 3; a_++) { real s_ = 0; for (int k = 0; k < 6; k++) s_ += oJ[n][6 * a_ + k] * a[i][k]; Ja[a_] = s_; }
             for (int a_ = 0; a_ < 3; a_++) { real s_ = 0; for (int k = 0; k < 3; k++) s_ += oG[n][3 * a_ + k] * Ja[k]; F[a_] = oF0[n][a_] - h * s_; }
-            /* contact point in world: recover from J (J = Rw [-rc^x 1]) is awkward -> recompute from the sphere */
-            int cpi = ocp[n];
-            real lp[3] = {(real)m->cp_pos[3 * cpi], (real)m->cp_pos[3 * cpi + 1], (real)m->cp_pos[3 * cpi + 2]}, wc[3], pen, nrm[3];
-            real hb[3] = {(real)m->obj_half[0], (real)m->obj_half[1], (real)m->obj_half[2]};
-            mat3_vec(Rw[i], lp, wc); for (int k = 0; k < 3; k++) wc[k] += pw[i][k];
-            sphere_box(wc, (real)m->cp_radius[cpi], obj, Ro, hb, &pen, nrm);
             real bp[3] = {(real)m->body_pos[3 * b], (real)m->body_pos[3 * b + 1], (real)m->body_pos[3 * b + 2]}, wb[3], arm[3], tq[3];
             mat3_vec(Rw[i], bp, wb);
-            for (int k = 0; k < 3; k++) arm[k] = (wc[k] - (real)m->cp_radius[cpi] * nrm[k]) - (pw[i][k] + wb[k]);
+            for (int k = 0; k < 3; k++) arm[k] = oPc[n][k] - (pw[i][k] + wb[k]);
             cross3(arm, F, tq);
             for (int k = 0; k < 3; k++) { cf_body[3 * b + k] += F[k]; cf_torque_body[3 * b + k] += tq[k]; }
         }

@@ -34,7 +34,7 @@ class _CModel(C.Structure):
                 ("obj_on", C.c_int), ("obj_gravity_on", C.c_int), ("nbx", C.c_int), ("pad1", C.c_int),
                 ("obj_mass", C.c_double), ("obj_inertia", C.c_double * 3), ("obj_half", C.c_double * 3),
                 ("obj_kn", C.c_double), ("obj_cn", C.c_double), ("obj_mu", C.c_double),
-                ("box_link", C.c_void_p), ("box_pos", C.c_void_p), ("box_quat", C.c_void_p), ("box_half", C.c_void_p),
+                ("box_link", C.c_void_p), ("box_body", C.c_void_p), ("box_pos", C.c_void_p), ("box_quat", C.c_void_p), ("box_half", C.c_void_p),
                 ("nten", C.c_int), ("pad2", C.c_int), ("ten_dof", C.c_void_p), ("ten_coef", C.c_void_p),
                 ("ten_range", C.c_void_p), ("ten_k", C.c_double), ("ten_d", C.c_double)]
 
@@ -95,6 +95,7 @@ class OracleSim:
             cm.nbx = 0 if bl is None else len(bl)
             if cm.nbx:
                 cm.box_link = arr("box_link", m.box_link, np.int32)
+                cm.box_body = arr("box_body", m.box_body, np.int32)
                 for n in ("box_pos", "box_quat", "box_half"):
                     setattr(cm, n, arr(n, getattr(m, n), np.float64))
         cm.nten = 0

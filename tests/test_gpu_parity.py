@@ -513,6 +513,11 @@ def test_hand_object_simulate_matches_oracle():
     assert np.abs(sg - out["sensor"]).max() < 5e-3 * max(1.0, np.abs(out["sensor"]).max())
     fg = sim.tensors[engine.T_DOF_FORCE].cpu().numpy().reshape(n, -1)
     assert np.abs(fg - out["dof_force"]).max() < 5e-3 * max(1.0, np.abs(out["dof_force"]).max())
+    # net contact force per LINK (the engine reports a link's contacts on its first body, the oracle per body)
+    cg = sim.tensors[engine.T_NET_CONTACT].cpu().numpy().reshape(n, m.nb, 3)
+    agg = lambda a: np.stack([a[:, np.nonzero(m.body_link == li)[0]].sum(1) for li in range(m.nl)], 1)
+    assert np.abs(out["contact_force"]).max() > 0.1
+    assert np.abs(agg(cg) - agg(out["contact_force"])).max() < 5e-3 * max(1.0, np.abs(out["contact_force"]).max())
     # fingertip / object / goal rows of the rigid-body state tensor (shadow_hand.py:456)
     bs = sim.refresh_rigid_body_state(); torch.cuda.synchronize()
     bg = bs.cpu().numpy().reshape(n, m.nb + 2, 13)

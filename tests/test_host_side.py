@@ -26,13 +26,13 @@ def test_struct_layouts_match_header_sizes():
     """ctypes mirrors must have the size the C compiler gives the header's structs."""
     import subprocess, tempfile
     from isaacgymenvs_b200 import engine
-    src = '#include "b200gym.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu\\n", sizeof(b2g_model), sizeof(b2g_sim_params), sizeof(b2g_task_params), sizeof(b2g_anymal_params));return 0;}\n'
+    src = '#include "b200gym.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(b2g_model), sizeof(b2g_sim_params), sizeof(b2g_task_params), sizeof(b2g_anymal_params), sizeof(b2g_model_ext), sizeof(b2g_hand_params));return 0;}\n'
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "t.c"), "w").write(src)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "t"), os.path.join(d, "t.c")])
         sizes = [int(x) for x in subprocess.check_output([os.path.join(d, "t")]).split()]
     assert sizes == [ctypes.sizeof(engine.CModel), ctypes.sizeof(engine.CSimParams), ctypes.sizeof(engine.CTaskParams),
-                     ctypes.sizeof(engine.CAnymalParams)]
+                     ctypes.sizeof(engine.CAnymalParams), ctypes.sizeof(engine.CModelExt), ctypes.sizeof(engine.CHandParams)]
 
 
 def test_no_cpu_fallback():
@@ -48,7 +48,7 @@ def test_no_cpu_fallback():
 
 
 @needs_reference
-@pytest.mark.parametrize("task", ["Cartpole", "Ant", "Humanoid"])
+@pytest.mark.parametrize("task", ["Cartpole", "Ant", "Humanoid", "ShadowHand"])
 def test_reference_yaml_loads_unmodified_and_matches_builtin(task):
     from isaacgymenvs_b200 import config
     ref = config.load_reference_cfg(os.path.join(REFERENCE, "isaacgymenvs", "cfg"), task, {"num_envs": 64})

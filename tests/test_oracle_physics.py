@@ -126,3 +126,57 @@ def test_contact_rest_and_sensor():
     assert np.abs(root[0, 7:13]).max() < 0.02 and np.abs(dof[0, :, 1]).max() < 0.05
     assert 0.05 < root[0, 2] < 0.6
     assert out["sensor"].shape == (1, 4, 6)
+
+
+# ---------------------------------------------------------------------------------------------
+# the free object (ShadowHand's cube): closed-form and balance checks of the two-body extension
+def _hand_orc(**kw):
+    from tests.hand_common import hand_setup, DT, SUBSTEPS, G as HG
+    m, obj, tendons = hand_setup()
+    return m, obj, OracleSim(m, DT, SUBSTEPS, HG, obj=obj, tendons=tendons, tendon_k=30.0, tendon_d=0.1, **kw), DT
+
+
+def test_object_free_flight_is_ballistic_and_torque_free():
+    """Away from the hand the cube is a free rigid body: parabola for the COM, constant angular momentum."""
+    m, obj, orc, dt = _hand_orc()
+    root = np.zeros((1, 13)); root[0, 2] = 0.5; root[0, 3:7] = m.default_root_quat
+    dof = np.zeros((1, m.ndof, 2))
+    o = np.zeros((1, 13)); o[0, 0:3] = [1.0, 1.0, 3.0]; o[0, 6] = 1
+    o[0, 7:10] = [0.3, -0.2, 1.0]; o[0, 10:13] = [2.0, -1.0, 0.5]
+    v0, p0, w0 = o[0, 7:10].copy(), o[0, 0:3].copy(), o[0, 10:13].copy()
+    n = 30
+    for _ in range(n):
+        orc.simulate(root, dof, target=np.zeros((1, m.ndof)), obj=o)
+    t = n * dt
+    assert np.allclose(o[0, 7:10], v0 + np.array([0, 0, -9.81]) * t, atol=1e-9)
+    # semi-implicit Euler: position error vs the parabola is g*h*t/2 with h the sub-step
+    assert np.abs(o[0, 0:3] - (p0 + v0 * t + 0.5 * np.array([0, 0, -9.81]) * t * t)).max() < 9.81 * (dt / 2) * t / 2 * 1.01
+    assert np.allclose(o[0, 10:13], w0, atol=1e-9)        # isotropic inertia: w itself is constant
+    assert abs(np.linalg.norm(o[0, 3:7]) - 1) < 1e-12
+
+
+def test_cube_rests_on_the_palm_and_forces_balance():
+    """Dropped on the open hand the cube settles; the hand's net contact force equals the cube's weight (Newton III
+    through the penalty contact), and the cube stays where the palm is."""
+    m, obj, orc, dt = _hand_orc()
+    root = np.zeros((1, 13)); root[0, 2] = 0.5; root[0, 3:7] = m.default_root_quat
+    dof = np.zeros((1, m.ndof, 2))
+    o = np.zeros((1, 13)); o[0, 0:3] = [0.0, -0.39, 0.56]; o[0, 6] = 1
+    for _ in range(150):
+        out = orc.simulate(root, dof, target=np.zeros((1, m.ndof)), obj=o)
+    W = obj["mass"] * 9.81
+    F = out["contact_force"][0].sum(0)                     # on the hand's bodies, world axes
+    assert abs(-F[2] - W) / W < 0.03, (F, W)
+    assert np.abs(o[0, 7:13]).max() < 0.02
+    assert 0.5 < o[0, 2] < 0.56 and abs(o[0, 1] + 0.39) < 0.02
+
+
+def test_object_rests_on_the_ground():
+    m, obj, orc, dt = _hand_orc()
+    root = np.zeros((1, 13)); root[0, 2] = 0.5; root[0, 3:7] = m.default_root_quat
+    dof = np.zeros((1, m.ndof, 2))
+    o = np.zeros((1, 13)); o[0, 0:3] = [1.0, 1.0, 0.1]; o[0, 6] = 1
+    for _ in range(200):
+        orc.simulate(root, dof, target=np.zeros((1, m.ndof)), obj=o)
+    pen = obj["mass"] * 9.81 / 4 / (10000.0 * obj["mass"])            # four corners share the weight
+    assert abs(o[0, 2] - (0.025 - pen)) < 2e-4 and np.abs(o[0, 7:13]).max() < 1e-3
