@@ -1,7 +1,7 @@
 """`isaacgym.gymapi` look-alike backed by the B200 engine (SURVEY.md 8b "required exports").
 
-Only what `tasks/base/vec_task.py` and the single-actor-per-env tasks of the reference touch is
-provided; every method cites a representative call site.  Actors, assets and envs are RECORDED
+Only what `tasks/base/vec_task.py`, the single-actor-per-env tasks and ShadowHand's three-actor envs (articulation +
+free box + gravity-less marker, `shadow_hand.py:338-383`) touch is provided; every method cites a representative call site.  Actors, assets and envs are RECORDED
 here (create_actor is called num_envs times in a Python loop, `ant.py:185-197`, so it must cost
 microseconds); the engine is created once, in `prepare_sim`.
 """
@@ -103,6 +103,10 @@ class _Asset:
         self.model = model
         self.options = options
         self.sensors = []           # (body index, Transform)
+        # fixed tendons as gym.get_asset_tendon_properties sees them (shadow_hand.py:255-266): inactive until a
+        # limit stiffness is set
+        self.tendon_props = [types.SimpleNamespace(limit_stiffness=0.0, damping=0.0, stiffness=0.0, lower_limit=float(t["range"][0]),
+                                                   upper_limit=float(t["range"][1])) for t in (model.tendons or [])]
         self.shape_props = [types.SimpleNamespace(friction=float(f), restitution=0.0) for f in model.geom_friction]
 
 
@@ -110,6 +114,7 @@ class _Env:
     def __init__(self, index):
         self.index = index
         self.actors = []
+        self.actor_ids = []
 
 
 class _Sim:
@@ -118,9 +123,11 @@ class _Sim:
         self.params = params
         self.ground = None
         self.envs = []
-        self.asset = None           # one asset, one actor per env (the BASELINE locomotion tasks)
-        self.start_poses = []
+        self.asset = None           # the articulation (actor 0 of every env)
+        self.extra_assets = []      # further actors of an env, in creation order: single rigid bodies
+        self.start_poses = []       # per env: [Transform per actor]
         self.engine = None
+        self.num_actors = 0
         self.frame = 0
 
 
@@ -150,12 +157,38 @@ class Gym:
         model.sensor_pos = np.zeros((len(a.sensors), 3)); model.sensor_quat = np.tile([0, 0, 0, 1.0], (len(a.sensors), 1))
         mu = sim.ground.dynamic_friction if sim.ground is not None else 1.0
         g = p.gravity
+        ext = None
+        apr = 1 + len(sim.extra_assets)
+        if sim.extra_assets:
+            # further actors: single free bodies.  The first one with gravity is the simulated object (a box);
+            # gravity-less ones are markers the engine never moves (goal object, shadow_hand.py:281-282,380)
+            obj, obj_row = None, -1
+            for k, xa in enumerate(sim.extra_assets):
+                xm = xa.model
+                if xm.ndof != 0 or xm.nb != 1:
+                    raise NotImplementedError("extra actors of an env must be single rigid bodies")
+                if xa.options.disable_gravity:
+                    continue
+                if obj is not None or k != 0:
+                    raise NotImplementedError("one simulated free object per env, created right after the articulation")
+                if len(xm.geom_type) != 1 or int(xm.geom_type[0]) != 2:
+                    raise NotImplementedError("the free object must be a single box primitive")
+                obj = dict(mass=float(xm.mass[0]), inertia=[float(xm.inertia[0][c]) for c in range(3)],
+                           half=[float(v) for v in np.asarray(xm.geom_size)[0][:3]], mu=float(xa.shape_props[0].friction), gravity_on=1)
+                obj_row = 1
+            tend = [dict(t) for t, tp in zip(model.tendons or [], a.tendon_props) if tp.limit_stiffness > 0.0]
+            ks = {(tp.limit_stiffness, tp.damping) for tp in a.tendon_props if tp.limit_stiffness > 0.0}
+            if len(ks) > 1:
+                raise NotImplementedError("all active tendons share one limit stiffness / damping")
+            tk, td = next(iter(ks)) if ks else (0.0, 0.0)
+            if obj is None:
+                tend = []
+            ext = engine.pack_model_ext(model, obj=obj, actors_per_env=apr, tendons=tend, tendon_k=tk, tendon_d=td)
         sim.engine = engine.Sim(model, len(sim.envs), dt=p.dt, substeps=p.substeps, gravity=(g.x, g.y, g.z), ground_mu=mu,
-                                device=f"cuda:{sim.compute_device}")
-        rs = sim.engine.root_state
-        for i, pose in enumerate(sim.start_poses):
-            rs[i, 0:3] = torch.tensor([pose.p.x, pose.p.y, pose.p.z])
-            rs[i, 3:7] = torch.tensor([pose.r.x, pose.r.y, pose.r.z, pose.r.w])
+                                device=f"cuda:{sim.compute_device}", ext=ext)
+        poses = torch.tensor([[[q.p.x, q.p.y, q.p.z, q.r.x, q.r.y, q.r.z, q.r.w] for q in env_poses] for env_poses in sim.start_poses],
+                             dtype=torch.float32)
+        sim.engine.root_state.view(len(sim.envs), apr, 13)[:, :, 0:7] = poses.to(sim.engine.root_state.device)
         return True
 
     def simulate(self, sim):
@@ -180,8 +213,10 @@ class Gym:
         opts = BuildOptions(fix_base_link=o.fix_base_link, collapse_fixed_joints=o.collapse_fixed_joints,
                             replace_cylinder_with_capsule=o.replace_cylinder_with_capsule, armature=o.armature,
                             density=o.density, angular_damping=o.angular_damping, linear_damping=o.linear_damping,
-                            disable_gravity=o.disable_gravity, default_dof_drive_mode=o.default_dof_drive_mode)
-        return _Asset(load_asset_file(root, file, opts), o)
+                            disable_gravity=o.disable_gravity, default_dof_drive_mode=o.default_dof_drive_mode,
+                            # fixed-base arms meet objects, not just the ground: one more sphere per capsule
+                            capsule_mid_spheres=1 if o.fix_base_link else 0)
+        return _Asset(load_asset_file(root, file, opts), copy.copy(o))   # the caller may go on mutating `options` (shadow_hand.py:279-282)
 
     def get_asset_dof_count(self, asset):
         return asset.model.ndof
@@ -233,6 +268,19 @@ class Gym:
         p["stiffness"], p["damping"], p["armature"] = m.kp[1:], m.kd[1:], m.armature[1:]
         return p
 
+    # ---- tendons (shadow_hand.py:253-266)
+    def get_asset_tendon_count(self, asset):
+        return len(asset.tendon_props)
+
+    def get_asset_tendon_name(self, asset, i):
+        return asset.model.tendons[i]["name"]
+
+    def get_asset_tendon_properties(self, asset):
+        return asset.tendon_props
+
+    def set_asset_tendon_properties(self, asset, props):
+        asset.tendon_props = props
+
     def get_asset_rigid_shape_properties(self, asset):
         return asset.shape_props
 
@@ -252,13 +300,22 @@ class Gym:
 
     def create_actor(self, env, asset, pose, name, group, filter, seg_id=0):
         sim = env.sim
-        if sim.asset is None:
-            sim.asset = asset
-        elif sim.asset is not asset or env.actors:
-            raise NotImplementedError("the B200 engine steps one actor of one asset per env (SURVEY.md 8f for the rest)")
+        k = len(env.actors)
+        if k == 0:
+            if sim.asset is None:
+                sim.asset = asset
+            elif sim.asset is not asset:
+                raise NotImplementedError("every env holds the same articulation as its first actor")
+            sim.start_poses.append([])
+        elif env.index == 0:
+            sim.extra_assets.append(asset)
+        elif k - 1 >= len(sim.extra_assets) or sim.extra_assets[k - 1] is not asset:
+            raise NotImplementedError("every env holds the same actors in the same order")
         env.actors.append(name)
-        sim.start_poses.append(Transform(Vec3(pose.p.x, pose.p.y, pose.p.z), Quat(pose.r.x, pose.r.y, pose.r.z, pose.r.w)))
-        return 0
+        env.actor_ids.append(sim.num_actors)            # sim-domain index: creation order (shadow_hand.py:356,369,376)
+        sim.num_actors += 1
+        sim.start_poses[env.index].append(Transform(Vec3(pose.p.x, pose.p.y, pose.p.z), Quat(pose.r.x, pose.r.y, pose.r.z, pose.r.w)))
+        return k
 
     def begin_aggregate(self, *a):
         pass
@@ -285,10 +342,10 @@ class Gym:
         return env.sim.asset.model.body_names.index(name)
 
     def get_actor_index(self, env, actor, domain):
-        return env.index
+        return env.actor_ids[int(actor)] if domain == DOMAIN_SIM else int(actor)
 
     def get_actor_rigid_body_properties(self, env, actor):
-        m = env.sim.asset.model
+        m = env.sim.asset.model if int(actor) == 0 else env.sim.extra_assets[int(actor) - 1].model
         return [types.SimpleNamespace(mass=float(m.mass[m.body_link[b]])) for b in range(m.nb)]
 
     def get_sim_dof_count(self, sim):
@@ -335,6 +392,18 @@ class Gym:
         sim.engine.dof_target.view(-1).copy_(t.view(-1))
         return True
 
+    def set_dof_position_target_tensor_indexed(self, sim, t, idx, n):       # shadow_hand.py:646-648; idx = actor indices
+        nd = sim.asset.model.ndof
+        i = idx[:n].long() // (1 + len(sim.extra_assets))
+        sim.engine.dof_target.view(-1, nd)[i] = t.view(-1, nd)[i]
+        return True
+
+    def apply_rigid_body_force_tensors(self, sim, forces=None, torques=None, space=ENV_SPACE):   # shadow_hand.py:709
+        for t in (forces, torques):
+            if t is not None and bool((t != 0).any()):
+                raise NotImplementedError("external rigid-body forces are not applied by the engine")
+        return True
+
     def set_actor_root_state_tensor(self, sim, t):
         if t.data_ptr() != sim.engine.root_state.data_ptr():
             sim.engine.root_state.copy_(t.view_as(sim.engine.root_state))
@@ -354,7 +423,7 @@ class Gym:
     def set_dof_state_tensor_indexed(self, sim, t, idx, n):
         if t.data_ptr() != sim.engine.dof_state.data_ptr():
             nd = sim.asset.model.ndof
-            i = idx[:n].long()
+            i = idx[:n].long() // (1 + len(sim.extra_assets))     # actor index of the articulation -> env
             sim.engine.dof_state.view(-1, nd, 2)[i] = t.view(-1, nd, 2)[i]
         return True
 

@@ -15,18 +15,19 @@ from tests.conftest import needs_reference, REFERENCE
 
 
 class _FakeSim:
-    def __init__(self, model, num_envs, dt, substeps, gravity=(0, 0, -9.81), ground_mu=1.0, device="cpu", **kw):
+    def __init__(self, model, num_envs, dt, substeps, gravity=(0, 0, -9.81), ground_mu=1.0, device="cpu", ext=None, **kw):
         from isaacgymenvs_b200 import engine as E
-        self.model, self.num_envs = model, num_envs
+        self.model, self.num_envs, self.ext = model, num_envs, ext
+        self.actors_per_env = int(ext.actors_per_env) if ext is not None else 1
         self.nd, self.nb, self.ns = model.ndof, model.nb, len(model.sensor_body)
-        self.root_state = torch.zeros(num_envs, 13); self.root_state[:, 6] = 1
+        self.root_state = torch.zeros(num_envs * self.actors_per_env, 13); self.root_state[:, 6] = 1
         self.dof_state = torch.zeros(num_envs * max(self.nd, 1), 2)
         self.dof_actuation = torch.zeros(num_envs, max(self.nd, 1)); self.dof_target = torch.zeros_like(self.dof_actuation)
         self.tensors, self.E, self.steps = {}, E, 0
 
     def acquire(self, slot):
         E, N = self.E, self.num_envs
-        shape = {E.T_RIGID_BODY_STATE: (N * self.nb, 13), E.T_FORCE_SENSOR: (N * max(self.ns, 1), 6),
+        shape = {E.T_RIGID_BODY_STATE: (N * (self.nb + self.actors_per_env - 1), 13), E.T_FORCE_SENSOR: (N * max(self.ns, 1), 6),
                  E.T_DOF_FORCE: (N * max(self.nd, 1),), E.T_NET_CONTACT: (N * self.nb, 3)}[slot]
         return self.tensors.setdefault(slot, torch.zeros(*shape))
 
@@ -95,3 +96,37 @@ def test_unmodified_reference_task_runs_on_the_shim(compat_cpu, task, module, cl
         assert sim.dof_actuation.abs().max() > 1.0
     obs2, rew2, reset2, _ = env.step(torch.zeros(n, nact))
     assert (env.progress_buf == 1).all()
+
+
+@needs_reference
+def test_unmodified_reference_shadow_hand_runs_on_the_shim(compat_cpu):
+    """Three actors per env (hand, cube, goal marker), tendon properties, actor-indexed setters, the 211-d full_state
+    observation: the reference's own shadow_hand.py drives the shim unmodified."""
+    import importlib
+    mod = importlib.import_module("isaacgymenvs.tasks.shadow_hand")
+    assert os.path.realpath(mod.__file__).startswith(REFERENCE)
+    n = 8
+    env = mod.ShadowHand(cfg=_cfg("ShadowHand", n), rl_device="cpu", sim_device="cpu", graphics_device_id=-1, headless=True,
+                         virtual_screen_capture=False, force_render=False)
+    sim = env.sim.engine
+    assert env.num_obs == 211 and env.num_acts == 20 and env.num_shadow_hand_dofs == 24 and env.num_shadow_hand_actuators == 20
+    # the engine was created with the multi-actor extras the task's calls imply
+    ext = sim.ext
+    assert ext.actors_per_env == 3 and ext.obj_actor == 1 and ext.nten == 4 and abs(ext.ten_k - 30.0) < 1e-6 and abs(ext.ten_d - 0.1) < 1e-6
+    assert abs(ext.obj_mass - 0.070875) < 1e-6 and [round(v, 4) for v in ext.obj_half] == [0.025, 0.025, 0.025] and ext.nbox >= 1
+    assert env.root_state_tensor.shape == (3 * n, 13) and env.root_state_tensor.data_ptr() == sim.root_state.data_ptr()
+    assert env.hand_indices.tolist() == list(range(0, 3 * n, 3)) and env.object_indices.tolist() == list(range(1, 3 * n, 3))
+    assert env.rigid_body_states.shape[1] == sim.nb + 2 and len(env.fingertip_handles) == 5
+    rs = sim.root_state.view(n, 3, 13)
+    assert torch.allclose(rs[:, 0, 0:3], torch.tensor([0.0, 0.0, 0.5])) and torch.allclose(rs[:, 1, 0:3], torch.tensor([0.0, -0.39, 0.6]))
+    torch.manual_seed(0)
+    obs, rew, reset, extras = env.step(2 * torch.rand(n, 20) - 1)          # first step resets every env and every goal
+    assert sim.steps == 1 and obs["obs"].shape == (n, 211) and torch.isfinite(obs["obs"]).all() and torch.isfinite(rew).all()
+    lo, hi = env.shadow_hand_dof_lower_limits, env.shadow_hand_dof_upper_limits
+    assert ((env.shadow_hand_dof_pos >= lo - 1e-6) & (env.shadow_hand_dof_pos <= hi + 1e-6)).all()
+    # position targets reached the engine's tensor, clamped to the joint range (shadow_hand.py:684-698)
+    assert ((sim.dof_target >= lo - 1e-6) & (sim.dof_target <= hi + 1e-6)).all() and sim.dof_target.abs().sum() > 0
+    # reset_target_pose moved the goal marker's row; the cube was re-posed with noise
+    assert (rs[:, 2, 3:7].norm(dim=-1) - 1).abs().max() < 1e-5 and (rs[:, 2, 3:7] - torch.tensor([0.0, 0, 0, 1])).abs().max() > 1e-3
+    assert (rs[:, 1, 0:3] - torch.tensor([0.0, -0.39, 0.6])).abs().max() < 0.011
+    assert "consecutive_successes" in extras and "time_outs" in extras

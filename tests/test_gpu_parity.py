@@ -634,3 +634,77 @@ def test_hand_env_runs_and_resets():
     assert (z > 0.2).all()                       # nothing is left lying on the ground: fallen cubes were reset
     assert "consecutive_successes" in extras
     env.sim.close()
+
+
+def test_generic_gym_api_path_matches_fused_hand_step():
+    """The compatibility path for a three-actor env: driven the way the reference's shadow_hand.py drives `gym`
+    (assets, tendon properties, fingertip sensors, three create_actor per env, position targets -> simulate), the shim's
+    engine and the fused ShadowHand step produce the same hand / cube states, sensors and joint forces."""
+    from isaacgymenvs_b200 import compat
+    compat.install()
+    from isaacgym import gymapi, gymtorch
+    n = 64
+    env = _make("ShadowHand", n)
+    g = torch.Generator(device=env.device).manual_seed(5)
+    env.step(2 * torch.rand(n, 20, device=env.device, generator=g) - 1)         # resets everything
+    gym = gymapi.acquire_gym()
+    sp = gymapi.SimParams(); sp.dt, sp.substeps, sp.up_axis, sp.gravity, sp.use_gpu_pipeline = 0.01667, 2, gymapi.UP_AXIS_Z, gymapi.Vec3(0, 0, -9.81), True
+    sim = gym.create_sim(0, -1, gymapi.SIM_PHYSX, sp)
+    gym.add_ground(sim, gymapi.PlaneParams())
+    ao = gymapi.AssetOptions()
+    ao.fix_base_link, ao.collapse_fixed_joints, ao.disable_gravity, ao.thickness, ao.angular_damping = True, True, True, 0.001, 0.01
+    ao.default_dof_drive_mode = gymapi.DOF_MODE_NONE
+    hand = gym.load_asset(sim, "/no/such/checkout/assets", "mjcf/open_ai_assets/hand/shadow_hand.xml", ao)
+    assert gym.get_asset_dof_count(hand) == 24 and gym.get_asset_actuator_count(hand) == 20 and gym.get_asset_tendon_count(hand) >= 4
+    tp = gym.get_asset_tendon_properties(hand)
+    for i in range(gym.get_asset_tendon_count(hand)):
+        if gym.get_asset_tendon_name(hand, i) in ("robot0:T_FFJ1c", "robot0:T_MFJ1c", "robot0:T_RFJ1c", "robot0:T_LFJ1c"):
+            tp[i].limit_stiffness, tp[i].damping = 30, 0.1
+    gym.set_asset_tendon_properties(hand, tp)
+    for name in ["robot0:ffdistal", "robot0:mfdistal", "robot0:rfdistal", "robot0:lfdistal", "robot0:thdistal"]:
+        gym.create_asset_force_sensor(hand, gym.find_asset_rigid_body_index(hand, name), gymapi.Transform())
+    oo = gymapi.AssetOptions()
+    cube = gym.load_asset(sim, "/no/such/checkout/assets", "urdf/objects/cube_multicolor.urdf", oo)
+    oo.disable_gravity = True
+    goal = gym.load_asset(sim, "/no/such/checkout/assets", "urdf/objects/cube_multicolor.urdf", oo)
+    props = gym.get_asset_dof_properties(hand)
+    hp = gymapi.Transform(); hp.p = gymapi.Vec3(0, 0, 0.5)
+    op = gymapi.Transform(); op.p = gymapi.Vec3(0, -0.39, 0.6)
+    gp = gymapi.Transform(); gp.p = gymapi.Vec3(-0.2, -0.45, 0.68)
+    for i in range(n):
+        e = gym.create_env(sim, gymapi.Vec3(-0.75, -0.75, 0), gymapi.Vec3(0.75, 0.75, 0.75), 8)
+        h = gym.create_actor(e, hand, hp, "hand", i, -1, 0)
+        gym.set_actor_dof_properties(e, h, props)
+        assert gym.get_actor_index(e, h, gymapi.DOMAIN_SIM) == 3 * i
+        o = gym.create_actor(e, cube, op, "object", i, 0, 0)
+        k = gym.create_actor(e, goal, gp, "goal_object", i + n, 0, 0)
+        assert gym.get_actor_index(e, o, gymapi.DOMAIN_SIM) == 3 * i + 1 and gym.get_actor_index(e, k, gymapi.DOMAIN_SIM) == 3 * i + 2
+    gym.prepare_sim(sim)
+    root = gymtorch.wrap_tensor(gym.acquire_actor_root_state_tensor(sim))
+    dof = gymtorch.wrap_tensor(gym.acquire_dof_state_tensor(sim))
+    sens = gymtorch.wrap_tensor(gym.acquire_force_sensor_tensor(sim)).view(n, 30)
+    dfrc = gymtorch.wrap_tensor(gym.acquire_dof_force_tensor(sim)).view(n, 24)
+    assert root.shape == (3 * n, 13) and abs(float(root[1, 2]) - 0.6) < 1e-6
+    # the fixed base keeps the pose the asset file gives the hand; the shim's start pose has identity rotation like the reference's
+    root.view(n, 3, 13)[:, 0].copy_(env.root_state_tensor.view(n, 3, 13)[:, 0])
+    touched = 0.0
+    for _ in range(30):
+        pre_reset = env.reset_buf.clone()
+        root.copy_(env.root_state_tensor); dof.copy_(env.dof_state)
+        a = 2 * torch.rand(n, 20, device=env.device, generator=g) - 1
+        env.step(a)
+        gym.set_dof_position_target_tensor(sim, gymtorch.unwrap_tensor(env.cur_targets))
+        gym.simulate(sim)
+        torch.cuda.synchronize()
+        keep = pre_reset == 0                      # envs reset inside this fused step started from another state
+        r1, r2 = root.view(n, 3, 13)[keep], env.root_state_tensor.view(n, 3, 13)[keep]
+        assert torch.allclose(r1[:, 1], r2[:, 1], atol=2e-5, rtol=1e-3)
+        assert torch.allclose(dof.view(n, 24, 2)[keep], env.dof_state.view(n, 24, 2)[keep], atol=1e-4, rtol=2e-3)
+        assert torch.allclose(sens[keep], env.vec_sensor_tensor[keep], atol=1e-2, rtol=2e-3)
+        assert torch.allclose(dfrc[keep], env.dof_force_tensor[keep], atol=1e-3, rtol=2e-3)
+        touched = max(touched, float(env.vec_sensor_tensor.abs().max()))
+    assert touched > 0.05                          # fingertips did press on the cube at some point
+    bs = gymtorch.wrap_tensor(gym.acquire_rigid_body_state_tensor(sim)).view(n, -1, 13)
+    gym.refresh_rigid_body_state_tensor(sim)
+    assert bs.shape[1] == env.model.nb + 2 and torch.equal(bs[:, -2], root.view(n, 3, 13)[:, 1])
+    env.sim.close()
