@@ -184,9 +184,16 @@ struct TileArgs {
     int on;          // whole tiles + bulk copies
     int io_f4;       // float4 offset (per block) of the in/out tile region inside dynamic smem
     int model_f4;    // float4 offset of the packed model
+    // b2g_task_step_host with PINNED host buffers: the kernel reads its action tile from, and writes its result tiles
+    // to, host memory directly (unified addressing, plain coalesced 16-byte loads / stores -- not TMA), so the step
+    // needs no separate copy launches.  Null = off.
+    const float *h_act;
+    float *h_obs, *h_rew;
+    long long *h_reset;
+    uint8_t *h_timeout;
 };
 
-template <int L, bool HF, bool HUM, int BLOCK, bool TILES>
+template <int L, bool HF, bool HUM, int BLOCK, bool TILES, bool HOSTIO = false>
 __global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? B2G_MINBLOCKS : (BLOCK == 64 && !HUM ? 2 * B2G_MINBLOCKS : 1))) loco_step_kernel(
     const DevModel *__restrict__ gm, const int16_t *__restrict__ hf, Buffers B, const __grid_constant__ b2g_task_params P,
     const float *__restrict__ actions_in, int N, TileArgs ta) {
@@ -230,10 +237,16 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? B2G_MINBLOCKS : (BLOCK 
     asm volatile("griddepcontrol.wait;" ::: "memory");                     // previous step's writes are now visible
     if (tiles && threadIdx.x == 0) {
         const uint32_t rb = EPB * 13 * 4, db = (uint32_t)(EPB * nd * 8), ab = (uint32_t)(EPB * nd * 4);
-        mbar_expect_tx(&mbar2, rb + db + ab);
+        mbar_expect_tx(&mbar2, rb + db + (HOSTIO ? 0u : ab));
         bulk_g2s(s_root, (const float *)B.p[B2G_T_ROOT_STATE] + (size_t)env0 * 13, rb, &mbar2);
         bulk_g2s(s_dof, (const float *)B.p[B2G_T_DOF_STATE] + (size_t)env0 * nd * 2, db, &mbar2);
-        bulk_g2s(s_act, actions_in + (size_t)env0 * nd, ab, &mbar2);
+        if (!HOSTIO) bulk_g2s(s_act, actions_in + (size_t)env0 * nd, ab, &mbar2);
+    }
+    if (tiles && HOSTIO) {         // actions straight from pinned host memory
+        const float4 *src = reinterpret_cast<const float4 *>(ta.h_act + (size_t)env0 * nd);
+        float4 *dst = reinterpret_cast<float4 *>(s_act);
+        for (int i = threadIdx.x; i < EPB * nd / 4; i += BLOCK) dst[i] = src[i];
+        __syncthreads();
     }
     // per-env scalars of post_physics_step: issued now, consumed after the physics
     const long long progress_in = progress_b[e_pre];
@@ -444,7 +457,20 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? B2G_MINBLOCKS : (BLOCK 
             bulk_s2g(reset_b + e0, t_reset, EPB * 8);
             bulk_s2g(progress_b + e0, t_prog, EPB * 8);
             if (B.p[B2G_T_TIMEOUT]) bulk_s2g((uint8_t *)B.p[B2G_T_TIMEOUT] + e0, t_to, EPB);
+
             bulk_commit_wait();
+        }
+        // host copies of what VecTask.step returns (vec_task.py:402-408), straight over PCIe: coalesced 16-byte stores
+        if (HOSTIO) {
+            const size_t e0 = (size_t)env0;
+            auto copy16 = [&](void *dst, const void *src, int bytes) {
+                float4 *d = reinterpret_cast<float4 *>(dst); const float4 *sp = reinterpret_cast<const float4 *>(src);
+                for (int i = threadIdx.x; i < bytes / 16; i += BLOCK) d[i] = sp[i];
+            };
+            if (ta.h_obs) copy16(ta.h_obs + e0 * O, g_obsc ? t_obsc : t_obs, EPB * O * 4);
+            if (ta.h_rew) copy16(ta.h_rew + e0, t_rew, EPB * 4);
+            if (ta.h_reset) copy16(ta.h_reset + e0, t_reset, EPB * 8);
+            if (ta.h_timeout) copy16(ta.h_timeout + e0, t_to, EPB);
         }
     }
 }
@@ -588,6 +614,7 @@ struct b2g_sim {
     bool has_task = false, has_anymal = false, has_hand = false;
     unsigned step_counter = 0;   // common_step_counter, anymal_terrain.py:459
     float *d_actions_stage = nullptr;    // device staging for b2g_task_step_host
+    struct { bool on = false; float *obs = nullptr, *rew = nullptr; long long *reset = nullptr; uint8_t *timeout = nullptr; } zero_copy;
     int64_t launches = 0;
 };
 
@@ -1119,16 +1146,22 @@ extern "C" int b2g_task_step(b2g_sim *s, const float *actions, void *stream) {
         const size_t io_used = tiles ? io_bytes : 16;
         const size_t dyn = state_bytes + io_used + model_bytes;
         TileArgs ta; ta.on = tiles ? 1 : 0; ta.io_f4 = (int)(state_bytes / 16); ta.model_f4 = (int)((state_bytes + io_used) / 16);
-#define LOCO_T(LN, HM, BK, TL)                                                                                            \
+        ta.h_act = nullptr; ta.h_obs = ta.h_rew = nullptr; ta.h_reset = nullptr; ta.h_timeout = nullptr;
+        if (s->zero_copy.on) {
+            if (!tiles) return fail(B2G_E_UNSUPPORTED, "zero-copy host step needs the tiled kernel");
+            ta.h_act = actions; ta.h_obs = s->zero_copy.obs; ta.h_rew = s->zero_copy.rew; ta.h_reset = s->zero_copy.reset; ta.h_timeout = s->zero_copy.timeout;
+        }
+#define LOCO_T(LN, HM, BK, TL) do { if (TL && s->zero_copy.on) LOCO_K(LN, HM, BK, TL, TL); else LOCO_K(LN, HM, BK, TL, false); } while (0)
+#define LOCO_K(LN, HM, BK, TL, HIO)                                                                                       \
     do {                                                                                                                   \
-        int rc_ = set_smem(loco_step_kernel<LN, false, HM, BK, TL>, dyn); if (rc_) return rc_;                            \
+        int rc_ = set_smem(loco_step_kernel<LN, false, HM, BK, TL, HIO>, dyn); if (rc_) return rc_;                       \
         cudaLaunchConfig_t lc = {};                                                                                        \
         lc.gridDim = dim3(grid); lc.blockDim = dim3(blk); lc.dynamicSmemBytes = dyn; lc.stream = st;                       \
         cudaLaunchAttribute at[1];                                                                                         \
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                                     \
         at[0].val.programmaticStreamSerializationAllowed = 1;                                                              \
         lc.attrs = at; lc.numAttrs = 1;                                                                                    \
-        CUDA_TRY(cudaLaunchKernelEx(&lc, loco_step_kernel<LN, false, HM, BK, TL>, (const DevModel *)s->dm,                 \
+        CUDA_TRY(cudaLaunchKernelEx(&lc, loco_step_kernel<LN, false, HM, BK, TL, HIO>, (const DevModel *)s->dm,            \
                                     (const int16_t *)s->d_hf, s->buf, P, actions, (int)N, ta));                            \
     } while (0)
 #define LOCO(LN, HM, BK) do { if (tiles) LOCO_T(LN, HM, BK, true); else LOCO_T(LN, HM, BK, false); } while (0)
@@ -1146,6 +1179,7 @@ extern "C" int b2g_task_step(b2g_sim *s, const float *actions, void *stream) {
         else return fail(B2G_E_UNSUPPORTED, "no locomotion kernel instantiated for this (lanes, CTA size) combination");
 #undef LOCO
 #undef LOCO_T
+#undef LOCO_K
     }
     s->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -1161,6 +1195,26 @@ extern "C" int b2g_task_step_host(b2g_sim *s, const float *h_actions, float *h_o
     const int n_act = s->has_anymal ? s->anymal.num_actions : (s->has_hand ? s->hand.num_actions : s->task.num_actions);
     const int n_obs = s->has_anymal ? s->anymal.num_obs : (s->has_hand ? s->hand.num_obs : s->task.num_obs);
     const size_t N = s->num_envs, abytes = N * n_act * 4;
+    // fast path (Ant / Humanoid tiled kernel, every host buffer pinned): no copy launches at all
+    if (s->has_task && s->task.task != B2G_TASK_CARTPOLE && !getenv("B2G_NO_ZERO_COPY")) {
+        auto pinned = [](const void *p) {
+            if (!p) return true;
+            cudaPointerAttributes a;
+            if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+            return a.type == cudaMemoryTypeHost;
+        };
+        const int epb = s->block / s->lanes, ndof = s->hm.nl - 1;
+        const bool tiles_ok = (N % epb == 0) && (epb % 16 == 0) && ((epb * ndof * 4) % 16 == 0) && ((epb * 6 * s->hm.nsens * 4) % 16 == 0) &&
+                              ((epb * n_obs * 4) % 16 == 0) && s->buf.p[B2G_T_ACTIONS] && !s->d_hf;
+        if (tiles_ok && pinned(h_actions) && pinned(h_obs) && pinned(h_rew) && pinned(h_reset) && pinned(h_timeout)) {
+            s->zero_copy.on = true; s->zero_copy.obs = h_obs; s->zero_copy.rew = h_rew;
+            s->zero_copy.reset = (long long *)h_reset; s->zero_copy.timeout = h_timeout;
+            int rc = b2g_task_step(s, h_actions, stream);
+            s->zero_copy.on = false;
+            if (rc == B2G_OK) { CUDA_TRY(cudaStreamSynchronize(st)); return B2G_OK; }
+            if (rc != B2G_E_UNSUPPORTED) return rc;       // else: the generic path below
+        }
+    }
     if (!s->d_actions_stage) CUDA_TRY(cudaMalloc(&s->d_actions_stage, abytes));
     CUDA_TRY(cudaMemcpyAsync(s->d_actions_stage, h_actions, abytes, cudaMemcpyHostToDevice, st));
     int rc = b2g_task_step(s, s->d_actions_stage, stream); if (rc) return rc;

@@ -279,17 +279,25 @@ def test_single_lane_and_four_lane_ant_agree():
     assert rel(res[0][0], res[1][0]) < 2e-3 and rel(res[0][1], res[1][1]) < 5e-3
 
 
-def test_host_buffer_step_and_launch_count():
-    n = 128
-    env = _make("Ant", n)
-    h_a = torch.rand(n, 8).pin_memory() * 2 - 1
-    h_obs = torch.zeros(n, 60).pin_memory(); h_rew = torch.zeros(n).pin_memory()
-    h_reset = torch.zeros(n, dtype=torch.long).pin_memory()
-    c0 = env.sim.launch_count()
-    env.step_host(h_a, h_obs, h_rew, h_reset)
-    assert env.sim.launch_count() == c0 + 1
-    assert torch.equal(h_obs, env.obs_buf.cpu()) and torch.equal(h_rew, env.rew_buf.cpu())
-    assert torch.equal(h_reset, env.reset_buf.cpu())
+@pytest.mark.parametrize("task,nact,nobs,pinned", [("Ant", 8, 60, False), ("Ant", 8, 60, True), ("Humanoid", 21, 108, True)])
+def test_host_buffer_step_and_launch_count(task, nact, nobs, pinned):
+    """b2g_task_step_host: pageable buffers go through staged copies; pinned buffers are read / written by the kernel
+    itself over PCIe (no copy launches).  Either way the host sees exactly what the device buffers hold."""
+    n = 256
+    env = _make(task, n)
+    pin = (lambda t: t.pin_memory()) if pinned else (lambda t: t)
+    h_obs = pin(torch.zeros(n, nobs)); h_rew = pin(torch.zeros(n)); h_reset = pin(torch.zeros(n, dtype=torch.long))
+    h_to = pin(torch.zeros(n, dtype=torch.uint8))
+    g = torch.Generator().manual_seed(1)
+    for k in range(5):
+        h_a = pin(torch.rand(n, nact, generator=g) * 2 - 1)
+        c0 = env.sim.launch_count()
+        env.step_host(h_a, h_obs, h_rew, h_reset, h_to)
+        assert env.sim.launch_count() == c0 + 1
+        assert torch.equal(h_obs, env.obs_clipped.cpu()) and torch.equal(h_rew, env.rew_buf.cpu())
+        assert torch.equal(h_reset, env.reset_buf.cpu()) and torch.equal(h_to.bool(), env.timeout_buf.cpu())
+        assert torch.equal(env.actions.cpu(), h_a.clamp(-1, 1))
+    assert h_obs.abs().sum() > 0 and (env.progress_buf == 4).all()
 
 
 # ------------------------------------------------------------------------------------ AnymalTerrain
