@@ -308,12 +308,16 @@ def run_gpu_arm(args):
     peak, peak_kind = measured_peak()
     kernel_ms = total_ms / args.steps
     achieved = n * bytes_per / (kernel_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, flop = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-            traffic = json.load(f).get(args.workload)
+            prof = json.load(f)
+        traffic = prof.get(args.workload)
+        flop = prof.get(args.workload + "_fp32_flop_per_launch")
     except Exception:
         pass
+    if flop is not None and n != WORKLOADS[args.workload][1]:
+        flop = flop * n / WORKLOADS[args.workload][1]
     line = {
         "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -334,6 +338,10 @@ def run_gpu_arm(args):
                      "algorithmic_bytes_per_env_step": bytes_per},
         "clocks": clocks,
     }
+    if flop is not None:    # SURVEY 8d cross-check: the kernel is FP32-issue-bound, not HBM-bound
+        tf = flop / (kernel_ms * 1e-3) / 1e12
+        line["roofline"]["fp32"] = {"flop_per_launch": flop, "achieved": tf, "peak": 74.4, "unit": "TFLOP/s", "frac": tf / 74.4,
+                                    "note": "FFMA x2 + FADD + FMUL thread-instructions from the ncu capture in profiles/; peak = 148 SM x 128 lanes x 2 x 1.965 GHz"}
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         ns = n                                            # the workload's own env count ...
