@@ -334,22 +334,36 @@ __global__ void __launch_bounds__(BLOCK) anymal_reset_obs_kernel(Buffers B, cons
         qy[2] /= nq; qy[3] /= nq;
         const float bz = root[2];
         constexpr int PER = (140 + L - 1) / L;
-        for (int p = lane * PER; p < min(140, (lane + 1) * PER); p++) {
-            const int ix = p / 10, iy = p % 10;
-            const int xi = (ix < 7) ? ix - 8 : ix - 5;            // -8..-2, 2..8
-            const int yi = (iy < 5) ? iy - 5 : iy - 4;            // -5..-1, 1..5
-            const float pt[3] = {0.1f * (float)xi, 0.1f * (float)yi, 0.f};
-            float w[3]; t_quat_apply(qy, pt, w);
-            float h = 0.f;
-            if (hs) {
-                const float fx = (w[0] + root[0] + P.border_size) / P.terrain_hscale;
-                const float fy = (w[1] + root[1] + P.border_size) / P.terrain_hscale;
-                int px = (int)fx, py = (int)fy;                   // .long(): truncation toward zero
-                px = max(0, min(px, P.hs_rows - 2)); py = max(0, min(py, P.hs_cols - 2));
-                const int h1 = hs[(size_t)px * P.hs_cols + py], h2 = hs[(size_t)(px + 1) * P.hs_cols + py + 1];
-                h = (float)min(h1, h2) * P.terrain_vscale;
+        const float rx = root[0], ry = root[1];
+        // the two height samples of a point are independent global loads: fetch a chunk of points' samples together
+        // (their latencies overlap), then emit the chunk's observations
+        constexpr int CH = 7;
+        const int p_end = min(140, (lane + 1) * PER);
+#pragma unroll 1
+        for (int p0 = lane * PER; p0 < p_end; p0 += CH) {
+            int hmin[CH];
+#pragma unroll
+            for (int j = 0; j < CH; j++) {
+                const int p = min(p0 + j, 139);
+                const int ix = p / 10, iy = p % 10;
+                const int xi = (ix < 7) ? ix - 8 : ix - 5;            // -8..-2, 2..8
+                const int yi = (iy < 5) ? iy - 5 : iy - 4;            // -5..-1, 1..5
+                const float pt[3] = {0.1f * (float)xi, 0.1f * (float)yi, 0.f};
+                float w[3]; t_quat_apply(qy, pt, w);
+                hmin[j] = 0;
+                if (hs) {
+                    const float fx = (w[0] + rx + P.border_size) / P.terrain_hscale;
+                    const float fy = (w[1] + ry + P.border_size) / P.terrain_hscale;
+                    int px = (int)fx, py = (int)fy;                   // .long(): truncation toward zero
+                    px = max(0, min(px, P.hs_rows - 2)); py = max(0, min(py, P.hs_cols - 2));
+                    const int h1 = __ldg(hs + (size_t)px * P.hs_cols + py), h2 = __ldg(hs + (size_t)(px + 1) * P.hs_cols + py + 1);
+                    hmin[j] = min(h1, h2);
+                }
             }
-            put(12 + 2 * nd + p, fminf(fmaxf(bz - 0.5f - h, -1.f), 1.f) * P.height_meas_scale);
+#pragma unroll
+            for (int j = 0; j < CH; j++) {
+                if (p0 + j < p_end) put(12 + 2 * nd + p0 + j, fminf(fmaxf(bz - 0.5f - (float)hmin[j] * P.terrain_vscale, -1.f), 1.f) * P.height_meas_scale);
+            }
         }
     }
     if (lane == 0) {
