@@ -146,7 +146,8 @@ enum {
     B2G_T_CONSECUTIVE_SUCCESSES = 38, /* f32 (4): [0] consecutive_successes, [1..3] reduction scratch (sum resets, sum finished, ticket) */
     B2G_T_RESET_GOAL = 39,     /* i64 (N)     reset_goal_buf */
     B2G_T_GOAL_RESET_COUNT = 40,/* i32 (N)    per-env goal-only reset counter feeding the Philox stream */
-    B2G_T_COUNT = 41
+    B2G_T_STATES = 41,         /* f32 (N,S)  states_buf, vec_task.py:306 (asymmetric observations; unclipped, get_state clamps) */
+    B2G_T_COUNT = 42
 };
 
 /* fused per-task control steps */
@@ -222,7 +223,7 @@ typedef struct {
     int32_t actuated_dof[B2G_MAX_LINKS];                       /* action k drives DOF actuated_dof[k], shadow_hand.py:268-269 */
     float dof_lower[B2G_MAX_LINKS], dof_upper[B2G_MAX_LINKS], dof_default_pos[B2G_MAX_LINKS], dof_default_vel[B2G_MAX_LINKS];
     int32_t fingertip_body[5];                                 /* shadow_hand.py:120,289 */
-    int32_t pad0;
+    int32_t num_states;                                        /* 0, or the full_state size: states_buf is filled too (asymmetric_obs, :457-458) */
     uint64_t seed;
     int32_t env_id_offset, pad1;
 } b2g_hand_params;

@@ -1043,19 +1043,25 @@ extern "C" int b2g_set_hand_task(b2g_sim *s, const b2g_hand_params *t) {
     }
     // observation layouts, shadow_hand.py:460-592
     const int A = t->num_actions;
-    H.o_dofpos = H.o_dofvel = H.o_dofforce = H.o_objpose = H.o_objvel = H.o_goalpose = H.o_sens = -1;
-    int expect = 0;
-    switch (t->obs_type) {
-        case B2G_HAND_OBS_OPENAI:      H.o_ft = 0; H.ft_stride = 3; H.o_objpose = 15; H.n_objpose = 3; H.o_qdiff = 18; H.o_act = 22; expect = 22 + A; break;
-        case B2G_HAND_OBS_FULL_NO_VEL: H.o_dofpos = 0; H.o_objpose = nd; H.n_objpose = 7; H.o_goalpose = nd + 7; H.o_qdiff = nd + 14; H.o_ft = nd + 18; H.ft_stride = 3;
-                                       H.o_act = nd + 33; expect = nd + 33 + A; break;
-        case B2G_HAND_OBS_FULL:        H.o_dofpos = 0; H.o_dofvel = nd; H.o_objpose = 2 * nd; H.n_objpose = 7; H.o_objvel = 2 * nd + 7; H.o_goalpose = 2 * nd + 13;
-                                       H.o_qdiff = 2 * nd + 20; H.o_ft = 2 * nd + 24; H.ft_stride = 13; H.o_act = 2 * nd + 89; expect = 2 * nd + 89 + A; break;
-        case B2G_HAND_OBS_FULL_STATE:  H.o_dofpos = 0; H.o_dofvel = nd; H.o_dofforce = 2 * nd; H.o_objpose = 3 * nd; H.n_objpose = 7; H.o_objvel = 3 * nd + 7;
-                                       H.o_goalpose = 3 * nd + 13; H.o_qdiff = 3 * nd + 20; H.o_ft = 3 * nd + 24; H.ft_stride = 13; H.o_sens = 3 * nd + 89;
-                                       H.o_act = 3 * nd + 119; expect = 3 * nd + 119 + A; break;
-        default: return fail(B2G_E_INVALID, "ShadowHand: unknown observation type");
-    }
+    auto layout = [&](int type, HandDev::Layout &Y) -> int {
+        Y.o_dofpos = Y.o_dofvel = Y.o_dofforce = Y.o_objpose = Y.o_objvel = Y.o_goalpose = Y.o_sens = -1; Y.n_objpose = 0;
+        switch (type) {
+            case B2G_HAND_OBS_OPENAI:      Y.o_ft = 0; Y.ft_stride = 3; Y.o_objpose = 15; Y.n_objpose = 3; Y.o_qdiff = 18; Y.o_act = 22; return 22 + A;
+            case B2G_HAND_OBS_FULL_NO_VEL: Y.o_dofpos = 0; Y.o_objpose = nd; Y.n_objpose = 7; Y.o_goalpose = nd + 7; Y.o_qdiff = nd + 14; Y.o_ft = nd + 18; Y.ft_stride = 3;
+                                           Y.o_act = nd + 33; return nd + 33 + A;
+            case B2G_HAND_OBS_FULL:        Y.o_dofpos = 0; Y.o_dofvel = nd; Y.o_objpose = 2 * nd; Y.n_objpose = 7; Y.o_objvel = 2 * nd + 7; Y.o_goalpose = 2 * nd + 13;
+                                           Y.o_qdiff = 2 * nd + 20; Y.o_ft = 2 * nd + 24; Y.ft_stride = 13; Y.o_act = 2 * nd + 89; return 2 * nd + 89 + A;
+            case B2G_HAND_OBS_FULL_STATE:  Y.o_dofpos = 0; Y.o_dofvel = nd; Y.o_dofforce = 2 * nd; Y.o_objpose = 3 * nd; Y.n_objpose = 7; Y.o_objvel = 3 * nd + 7;
+                                           Y.o_goalpose = 3 * nd + 13; Y.o_qdiff = 3 * nd + 20; Y.o_ft = 3 * nd + 24; Y.ft_stride = 13; Y.o_sens = 3 * nd + 89;
+                                           Y.o_act = 3 * nd + 119; return 3 * nd + 119 + A;
+            default: return -1;
+        }
+    };
+    const int expect = layout(t->obs_type, H.lay[0]);
+    if (expect < 0) return fail(B2G_E_INVALID, "ShadowHand: unknown observation type");
+    const int expect_states = layout(B2G_HAND_OBS_FULL_STATE, H.lay[1]);
+    if (t->num_states != 0 && t->num_states != expect_states) return fail(B2G_E_UNSUPPORTED, "ShadowHand: num_states must be 0 or the full_state size");
+    H.num_states = t->num_states;
     if (t->num_obs != expect) return fail(B2G_E_UNSUPPORTED, "ShadowHand: observation size does not match the layout of this observation type");
     s->hand = *t; s->hand_dev = H; s->has_hand = true; s->has_task = false; s->has_anymal = false;
     return B2G_OK;
@@ -1067,7 +1073,11 @@ static int hand_step(b2g_sim *s, const float *actions, void *stream) {
                          B2G_T_INITIAL_ROOT, B2G_T_GOAL_STATES, B2G_T_PREV_TARGETS, B2G_T_SUCCESSES, B2G_T_CONSECUTIVE_SUCCESSES,
                          B2G_T_RESET_GOAL, B2G_T_GOAL_RESET_COUNT}, "b2g_task_step(ShadowHand)");
     if (rc) return rc;
-    if (s->hand_dev.o_sens >= 0) { rc = require(s, {B2G_T_FORCE_SENSOR, B2G_T_DOF_FORCE}, "b2g_task_step(ShadowHand, full_state)"); if (rc) return rc; }
+    if (s->hand_dev.lay[0].o_sens >= 0 || s->hand_dev.num_states > 0) { rc = require(s, {B2G_T_FORCE_SENSOR, B2G_T_DOF_FORCE}, "b2g_task_step(ShadowHand, full_state)"); if (rc) return rc; }
+    if (s->hand_dev.num_states > 0) {
+        rc = require(s, {B2G_T_STATES}, "b2g_task_step(ShadowHand, asymmetric observations)"); if (rc) return rc;
+        if (s->buf_bytes[B2G_T_STATES] < (size_t)s->num_envs * s->hand_dev.num_states * 4) return fail(B2G_E_INVALID, "STATES buffer too small");
+    }
     const size_t N = s->num_envs;
     if (s->buf_bytes[B2G_T_OBS] < N * P.num_obs * 4) return fail(B2G_E_INVALID, "OBS buffer too small");
     CUDA_TRY(cudaSetDevice(s->device));

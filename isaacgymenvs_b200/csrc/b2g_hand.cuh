@@ -14,7 +14,10 @@ struct HandDev {                      // host-derived tables (b2g_set_hand_task)
     int ft_ref[5];                    // ((lane << 8) | slot) of each fingertip's link
     float ft_bpos[5][3], ft_bR[5][9]; // fingertip body frame in its link frame
     int dof_action[MAX_LINKS];        // action index driving a DOF, -1: not actuated
-    int o_dofpos, o_dofvel, o_dofforce, o_objpose, n_objpose, o_objvel, o_goalpose, o_qdiff, o_ft, ft_stride, o_sens, o_act;
+    // offsets of the pieces inside an observation vector (-1: absent); [0] = obs_buf in the configured layout,
+    // [1] = states_buf, always the full_state layout (asymmetric observations, shadow_hand.py:457-458,529-556)
+    struct Layout { int o_dofpos, o_dofvel, o_dofforce, o_objpose, n_objpose, o_objvel, o_goalpose, o_qdiff, o_ft, ft_stride, o_sens, o_act; } lay[2];
+    int num_states;                   // 0: no states_buf
 };
 
 // quat_from_angle_axis (torch_jit_utils.py:118-123) about a unit coordinate axis, then quat_unit
@@ -170,11 +173,18 @@ __global__ void __launch_bounds__(BLOCK) hand_step_kernel(const DevModel *__rest
     float *obsc = (float *)B.p[B2G_T_OBS_CLIPPED];
     obsc = (obsc && obsc != (float *)B.p[B2G_T_OBS]) ? obsc + (size_t)e * O : nullptr;
     const float clipo = P.clip_obs;
-    auto put = [&](int idx, float v) {
+    float *const states = (H.num_states > 0 && B.p[B2G_T_STATES]) ? (float *)B.p[B2G_T_STATES] + (size_t)e * H.num_states : nullptr;
+    // put(piece, i, v): element i of an observation piece, into obs_buf (+ its clipped copy) and, if present, states_buf
+    auto put = [&](int HandDev::Layout::*piece, int i, float v) {
         if (!valid) return;
-        obs[idx] = v;
-        if (obsc) obsc[idx] = fminf(fmaxf(v, -clipo), clipo);
+        const int io = H.lay[0].*piece;
+        if (io >= 0) {
+            obs[io + i] = v;
+            if (obsc) obsc[io + i] = fminf(fmaxf(v, -clipo), clipo);
+        }
+        if (states) { const int is = H.lay[1].*piece; if (is >= 0) states[is + i] = v; }
     };
+    using LY = HandDev::Layout;
     float action_penalty = 0.f;
 #pragma unroll 1
     for (int s = 0; s < NS; s++) {
@@ -182,13 +192,13 @@ __global__ void __launch_bounds__(BLOCK) hand_step_kernel(const DevModel *__rest
         if (link < 0) continue;
         const float2 qv = st.get_q(s);
         if (valid) row_dof[d] = qv;
-        if (H.o_dofpos >= 0) put(H.o_dofpos + d, t_unscale(qv.x, P.dof_lower[d], P.dof_upper[d]));
-        if (H.o_dofvel >= 0) put(H.o_dofvel + d, P.vel_obs_scale * qv.y);
-        if (H.o_dofforce >= 0) put(H.o_dofforce + d, P.force_torque_obs_scale * (g_dfrc ? g_dfrc[d] : 0.f));
+        put(&LY::o_dofpos, d, t_unscale(qv.x, P.dof_lower[d], P.dof_upper[d]));
+        put(&LY::o_dofvel, d, P.vel_obs_scale * qv.y);
+        put(&LY::o_dofforce, d, P.force_torque_obs_scale * (g_dfrc ? g_dfrc[d] : 0.f));
         const int k = H.dof_action[d];
         if (k >= 0) {
             const float a = fminf(fmaxf(actions_in[(size_t)e * NA + k], -P.clip_actions), P.clip_actions);
-            put(H.o_act + k, a);
+            put(&LY::o_act, k, a);
             action_penalty += a * a;
         }
     }
@@ -202,22 +212,27 @@ __global__ void __launch_bounds__(BLOCK) hand_step_kernel(const DevModel *__rest
         const float bp[3] = {H.ft_bpos[f][0], H.ft_bpos[f][1], H.ft_bpos[f][2]};
         float wb[3]; matvec(R, bp, wb);
         const float xb[3] = {x[0] + wb[0], x[1] + wb[1], x[2] + wb[2]};
-        const int o0 = H.o_ft + H.ft_stride * f;
+        // fingertip block: 3 (position only) or 13 floats per fingertip, per destination layout
+        float Rwb[9], q[4], wxr[3];
+        matmul(R, H.ft_bR[f], Rwb); mat_to_quat(Rwb, q);
+        cross(vw, xb, wxr);
+        auto put_ft = [&](float *dst, float *dstc, const HandDev::Layout &ly) {
+            if (!valid || !dst || ly.o_ft < 0) return;
+            const int o0 = ly.o_ft + ly.ft_stride * f;
+            float v[13] = {rs.rp[0] + xb[0], rs.rp[1] + xb[1], rs.rp[2] + xb[2], q[0], q[1], q[2], q[3],
+                           vl[0] + wxr[0], vl[1] + wxr[1], vl[2] + wxr[2], vw[0], vw[1], vw[2]};
 #pragma unroll
-        for (int c = 0; c < 3; c++) put(o0 + c, rs.rp[c] + xb[c]);
-        if (H.ft_stride == 13) {
-            float Rwb[9], q[4], wxr[3];
-            matmul(R, H.ft_bR[f], Rwb); mat_to_quat(Rwb, q);
-            cross(vw, xb, wxr);
+            for (int c = 0; c < 13; c++) {
+                if (c < ly.ft_stride) {
+                    dst[o0 + c] = v[c];
+                    if (dstc) dstc[o0 + c] = fminf(fmaxf(v[c], -clipo), clipo);
+                }
+            }
+        };
+        put_ft(obs, obsc, H.lay[0]);
+        put_ft(states, nullptr, H.lay[1]);
 #pragma unroll
-            for (int c = 0; c < 4; c++) put(o0 + 3 + c, q[c]);
-#pragma unroll
-            for (int c = 0; c < 3; c++) { put(o0 + 7 + c, vl[c] + wxr[c]); put(o0 + 10 + c, vw[c]); }
-        }
-        if (H.o_sens >= 0) {
-#pragma unroll
-            for (int c = 0; c < 6; c++) put(H.o_sens + 6 * f + c, P.force_torque_obs_scale * (g_sens ? g_sens[6 * f + c] : 0.f));
-        }
+        for (int c = 0; c < 6; c++) put(&LY::o_sens, 6 * f + c, P.force_torque_obs_scale * (g_sens ? g_sens[6 * f + c] : 0.f));
     }
     action_penalty = lane_sum<L>(action_penalty);
 
@@ -225,26 +240,26 @@ __global__ void __launch_bounds__(BLOCK) hand_step_kernel(const DevModel *__rest
     const float gconj[4] = {-goal_rot[0], -goal_rot[1], -goal_rot[2], goal_rot[3]};
     float qdiff[4]; t_quat_mul(ob.q, gconj, qdiff);
     if (lane == 0) {
-        if (H.o_objpose >= 0) {
 #pragma unroll
-            for (int c = 0; c < 3; c++) put(H.o_objpose + c, ob.p[c]);
-            if (H.n_objpose == 7) {
+        for (int c = 0; c < 3; c++) put(&LY::o_objpose, c, ob.p[c]);
+        if (valid) {       // orientation only where the layout carries the full pose
+            if (H.lay[0].o_objpose >= 0 && H.lay[0].n_objpose == 7) {
 #pragma unroll
-                for (int c = 0; c < 4; c++) put(H.o_objpose + 3 + c, ob.q[c]);
+                for (int c = 0; c < 4; c++) { obs[H.lay[0].o_objpose + 3 + c] = ob.q[c]; if (obsc) obsc[H.lay[0].o_objpose + 3 + c] = fminf(fmaxf(ob.q[c], -clipo), clipo); }
+            }
+            if (states) {
+#pragma unroll
+                for (int c = 0; c < 4; c++) states[H.lay[1].o_objpose + 3 + c] = ob.q[c];
             }
         }
-        if (H.o_objvel >= 0) {
 #pragma unroll
-            for (int c = 0; c < 3; c++) { put(H.o_objvel + c, ob.v[c]); put(H.o_objvel + 3 + c, P.vel_obs_scale * ob.w[c]); }
-        }
-        if (H.o_goalpose >= 0) {
+        for (int c = 0; c < 3; c++) { put(&LY::o_objvel, c, ob.v[c]); put(&LY::o_objvel, 3 + c, P.vel_obs_scale * ob.w[c]); }
 #pragma unroll
-            for (int c = 0; c < 3; c++) put(H.o_goalpose + c, goal_pos[c]);
+        for (int c = 0; c < 3; c++) put(&LY::o_goalpose, c, goal_pos[c]);
 #pragma unroll
-            for (int c = 0; c < 4; c++) put(H.o_goalpose + 3 + c, goal_rot[c]);
-        }
+        for (int c = 0; c < 4; c++) put(&LY::o_goalpose, 3 + c, goal_rot[c]);
 #pragma unroll
-        for (int c = 0; c < 4; c++) put(H.o_qdiff + c, qdiff[c]);
+        for (int c = 0; c < 4; c++) put(&LY::o_qdiff, c, qdiff[c]);
     }
     {
         const float dx = ob.p[0] - goal_pos[0], dy = ob.p[1] - goal_pos[1], dz = ob.p[2] - goal_pos[2];

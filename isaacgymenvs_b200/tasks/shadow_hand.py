@@ -46,11 +46,10 @@ class ShadowHand(VecTask):
         self.obs_type = e["observationType"]
         if self.obs_type not in NUM_OBS:
             raise Exception("Unknown type of observations!\\nobservationType should be one of: [openai, full_no_vel, full, full_state]")
-        if e["asymmetric_observations"]:
-            raise NotImplementedError("asymmetric observations (states_buf) are not produced by the fused step")
+        self.asymmetric_obs = bool(e["asymmetric_observations"])
         self.fingertips = list(FINGERTIPS); self.num_fingertips = 5
         cfg["env"]["numObservations"] = NUM_OBS[self.obs_type]
-        cfg["env"]["numStates"] = 0
+        cfg["env"]["numStates"] = 211 if self.asymmetric_obs else 0                                            # shadow_hand.py:126-128
         cfg["env"]["numActions"] = 20
         self.up_axis, self.up_axis_idx = "z", 2
         super().__init__(config=cfg, rl_device=rl_device, sim_device=sim_device, graphics_device_id=graphics_device_id,
@@ -159,13 +158,15 @@ class ShadowHand(VecTask):
 
     def _task_buffers(self):
         E = engine
-        return {E.T_INITIAL_ROOT: self.initial_root_states, E.T_GOAL_STATES: self.goal_states, E.T_PREV_TARGETS: self.prev_targets,
+        extra = {E.T_STATES: self.states_buf} if self.asymmetric_obs else {}
+        return {**extra, E.T_INITIAL_ROOT: self.initial_root_states, E.T_GOAL_STATES: self.goal_states, E.T_PREV_TARGETS: self.prev_targets,
                 E.T_SUCCESSES: self.successes, E.T_CONSECUTIVE_SUCCESSES: self._cons, E.T_RESET_GOAL: self.reset_goal_buf,
                 E.T_GOAL_RESET_COUNT: self.goal_reset_count}
 
     def _task_params(self):
         p = engine.CHandParams()
         p.obs_type = engine.HAND_OBS[self.obs_type]
+        p.num_states = int(self.num_states)
         p.max_episode_length = float(self.max_episode_length)
         p.use_relative_control = int(bool(self.use_relative_control))
         p.max_consecutive_successes = int(self.max_consecutive_successes)

@@ -557,10 +557,10 @@ def test_hand_rollout_tracks_oracle():
     sim.close()
 
 
-def _hand_env(n, case, obs_type):
+def _hand_env(n, case, obs_type, **more):
     from tests.hand_common import CASES as HC
     kw = HC[case]
-    return _make("ShadowHand", n, controlFrequencyInv=0, observationType=obs_type, useRelativeControl=kw["relative"],
+    return _make("ShadowHand", n, controlFrequencyInv=0, observationType=obs_type, useRelativeControl=kw["relative"], **more,
                  maxConsecutiveSuccesses=kw["mcs"], actionsMovingAverage=kw["mavg"], fallPenalty=kw["fall_penalty"],
                  resetDofVelRandomInterval=0.05)
 
@@ -715,4 +715,67 @@ def test_generic_gym_api_path_matches_fused_hand_step():
     bs = gymtorch.wrap_tensor(gym.acquire_rigid_body_state_tensor(sim)).view(n, -1, 13)
     gym.refresh_rigid_body_state_tensor(sim)
     assert bs.shape[1] == env.model.nb + 2 and torch.equal(bs[:, -2], root.view(n, 3, 13)[:, 1])
+    env.sim.close()
+
+
+def test_hand_asymmetric_states_buffer():
+    """asymmetric_observations: obs_buf in the openai layout, states_buf in the full_state layout (shadow_hand.py:457-458),
+    both against the golden vectors of the same step."""
+    gold = np.load(os.path.join(GOLD, "shadow_hand.npz"))
+    gi = lambda k: gold[f"a_in_{k}"]
+    n = gi("reset").shape[0]
+    env = _hand_env(n, "a", "openai", asymmetric_observations=True)
+    assert env.num_states == 211 and env.states_buf.shape == (n, 211) and env.num_obs == 42
+    dev = env.device
+    t = lambda a, dt=torch.float32: torch.tensor(np.asarray(a), dtype=dt, device=dev)
+    env.root_state_tensor.copy_(t(gi("root")))
+    env.initial_root_states.view(n, 3, 13)[:, 1].copy_(t(gi("object_init"))); env.initial_root_states.view(n, 3, 13)[:, 2].copy_(t(gi("goal_init")))
+    env.dof_state.copy_(t(gi("dof_state"))); env.prev_targets.copy_(t(gi("prev_targets"))); env.cur_targets.copy_(t(gi("cur_targets")))
+    env.goal_states.copy_(t(gi("goal_states"))); env.vec_sensor_tensor.copy_(t(gi("sensors"))); env.dof_force_tensor.copy_(t(gi("dof_force")))
+    env.reset_buf.copy_(t(gi("reset"), torch.long)); env.reset_goal_buf.copy_(t(gi("reset_goal"), torch.long))
+    env.progress_buf.copy_(t(gi("progress"), torch.long)); env.successes.copy_(t(gi("successes")))
+    env.reset_count.copy_(t(gi("reset_count"), torch.int32)); env.goal_reset_count.copy_(t(gi("goal_reset_count"), torch.int32))
+    obs, rew, reset, extras = env.step(t(gi("actions")))
+    torch.cuda.synchronize()
+    st = env.states_buf.cpu().numpy().copy(); ref = gold["a_out_obs"]
+    mask = np.ones(211, bool)
+    for f in range(5):
+        sl = slice(96 + 13 * f + 3, 96 + 13 * f + 7)
+        st[:, sl] *= np.sign((st[:, sl] * ref[:, sl]).sum(-1, keepdims=True))
+        mask[96 + 13 * f: 96 + 13 * f + 13] = False
+    np.testing.assert_allclose(st[:, mask], ref[:, mask], rtol=0, atol=2e-6)
+    assert (np.abs(st[:, ~mask] - ref[:, ~mask]) / np.maximum(1.0, np.abs(ref[:, ~mask]))).max() < 1e-4
+    ob = env.obs_buf.cpu().numpy(); ro = gold["a_out_obs_openai"]
+    assert np.abs(ob[:, 15:] - ro[:, 15:]).max() < 2e-6 and np.abs(ob[:, :15] - ro[:, :15]).max() < 5e-5
+    assert torch.equal(obs["states"], torch.clamp(env.states_buf, -5.0, 5.0))
+    np.testing.assert_allclose(rew.cpu().numpy(), gold["a_out_rew"], rtol=3e-6, atol=3e-5)
+    env.sim.close()
+
+
+@pytest.mark.parametrize("task", ["Ant", "ShadowHand"])
+def test_rlgames_style_driver_loop(task):
+    """The calls rl_games' vec-env wrapper makes (utils/rlgames_utils.py:242-295: get_env_info, reset, step, reset_done,
+    get_number_of_agents, set_train_info, get/set_env_state) and the shapes / dtypes / devices a PPO rollout buffer expects."""
+    n = 64
+    env = _make(task, n)
+    info = {"action_space": env.action_space, "observation_space": env.observation_space}
+    assert info["action_space"].shape == (env.num_acts,) and info["observation_space"].shape == (env.num_obs,)
+    assert env.get_number_of_agents() == 1 and env.num_states == 0
+    env.set_train_info(0); assert env.get_env_state() is None; env.set_env_state(None)
+    obs = env.reset()
+    assert set(obs) == {"obs"} and obs["obs"].shape == (n, env.num_obs) and obs["obs"].device.type == "cuda"
+    ep_ret = torch.zeros(n, device=env.device)
+    for k in range(40):
+        a = 2 * torch.rand(n, env.num_acts, device=env.device) - 1
+        obs, rew, dones, infos = env.step(a)
+        assert obs["obs"].shape == (n, env.num_obs) and rew.shape == (n,) and dones.shape == (n,) and dones.dtype == torch.long
+        assert infos["time_outs"].shape == (n,) and infos["time_outs"].dtype == torch.bool
+        assert (obs["obs"].abs() <= env.clip_obs + 1e-6).all()
+        ep_ret += rew
+        if k == 20:
+            env.reset_idx(torch.arange(0, n, 2, device=env.device))          # force a reset of half the envs
+            od, ids = env.reset_done()
+            assert ids.numel() >= n // 2 and od["obs"].shape == (n, env.num_obs)
+    assert torch.isfinite(ep_ret).all()
+    assert (env.progress_buf[0::2] <= 20).all()                               # the forced resets restarted those episodes
     env.sim.close()
