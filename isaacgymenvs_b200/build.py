@@ -23,6 +23,7 @@ def build(force=False, verbose=False, extra=()):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
            "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared", "-o", OUT, SRC]
+    cmd += os.environ.get("B2G_NVCC_FLAGS", "").split()      # experiment hook
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += list(extra)
