@@ -1,5 +1,5 @@
 #!/bin/bash
-# One GPU-box pass over everything the round-end driver runs, plus the evidence files copied into profiles/.
+# Run from the repo root (./tools/final_check.sh).  One GPU-box pass over everything the round-end driver runs, plus the evidence files copied into profiles/.
 set -x
 mkdir -p gpurun_out
 timeout 400 python -m pytest tests -q -m gpu 2>&1 | tail -4

@@ -1,6 +1,6 @@
 """CPU sanity for the ShadowHand physics (oracle): cube dropped on the open hand."""
-import sys, numpy as np
-sys.path.insert(0, "/root/repo")
+import os, sys, numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from isaacgymenvs_b200.assets import load_compiled as load_asset
 from oracle.oracle import OracleSim
 

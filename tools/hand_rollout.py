@@ -1,6 +1,6 @@
 """Long ShadowHand rollout under random actions: finiteness, speeds, reset statistics (run on a GPU box)."""
-import sys, torch
-sys.path.insert(0, ".")
+import os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import isaacgymenvs_b200
 from isaacgymenvs_b200 import config
 n = 4096

@@ -1,5 +1,5 @@
 """Attribute an ncu capture's SASS-level samples / executed instructions to CUDA source lines.
-    python tools_ncu_lines.py <report.ncu-rep> <lib.so> <kernel mangled-name substring> [top]
+    python tools/ncu_lines.py <report.ncu-rep> <lib.so> <kernel mangled-name substring> [top]
 Joins `ncu --page source --csv` (one row per SASS instruction, in order) with `nvdisasm -g` line annotations."""
 import csv, os, subprocess, sys, tempfile, collections, io
 

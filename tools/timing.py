@@ -1,7 +1,7 @@
 """Developer timing probe: kernel time vs control_freq_inv (0 = prologue+epilogue only)."""
 import sys, os, json
 import torch
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import isaacgymenvs_b200
 from isaacgymenvs_b200 import config
 
