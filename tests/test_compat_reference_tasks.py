@@ -130,3 +130,23 @@ def test_unmodified_reference_shadow_hand_runs_on_the_shim(compat_cpu):
     assert (rs[:, 2, 3:7].norm(dim=-1) - 1).abs().max() < 1e-5 and (rs[:, 2, 3:7] - torch.tensor([0.0, 0, 0, 1])).abs().max() > 1e-3
     assert (rs[:, 1, 0:3] - torch.tensor([0.0, -0.39, 0.6])).abs().max() < 0.011
     assert "consecutive_successes" in extras and "time_outs" in extras
+
+
+@needs_reference
+def test_unmodified_reference_flat_anymal_runs_on_the_shim(compat_cpu):
+    """tasks/anymal.py drives PhysX position drives (DOF_MODE_POS via set_actor_dof_properties,
+    set_dof_position_target_tensor) and reads net contact forces -- unmodified on the shim."""
+    import importlib
+    mod = importlib.import_module("isaacgymenvs.tasks.anymal")
+    assert os.path.realpath(mod.__file__).startswith(REFERENCE)
+    n = 8
+    env = mod.Anymal(cfg=_cfg("Anymal", n), rl_device="cpu", sim_device="cpu", graphics_device_id=-1, headless=True,
+                     virtual_screen_capture=False, force_render=False)
+    sim = env.sim.engine
+    assert env.num_obs == 48 and env.num_acts == 12
+    m = sim.model
+    assert (m.drive_mode[1:] == 1).all() and np.allclose(m.kp[1:], 85.0) and np.allclose(m.kd[1:], 2.0)     # anymal.py:199-203
+    obs, rew, reset, extras = env.step(2 * torch.rand(n, 12) - 1)
+    assert obs["obs"].shape == (n, 48) and torch.isfinite(obs["obs"]).all() and torch.isfinite(rew).all()
+    # targets = action_scale * actions + default_dof_pos reached the engine's target tensor (anymal.py:226-229)
+    assert torch.allclose(sim.dof_target, 0.5 * env.actions + env.default_dof_pos)

@@ -779,3 +779,50 @@ def test_rlgames_style_driver_loop(task):
     assert torch.isfinite(ep_ret).all()
     assert (env.progress_buf[0::2] <= 20).all()                               # the forced resets restarted those episodes
     env.sim.close()
+
+
+def test_generic_gym_api_position_drive_anymal_stands():
+    """PhysX-style position drives through the generic path (tasks/anymal.py:199-203,226-229): ANYmal with stiffness 85 /
+    damping 2 holding its default joint angles on the plane settles on its feet; net contact forces carry its weight."""
+    from isaacgymenvs_b200 import compat
+    compat.install()
+    from isaacgym import gymapi, gymtorch
+    n = 32
+    gym = gymapi.acquire_gym()
+    sp = gymapi.SimParams(); sp.dt, sp.substeps, sp.up_axis, sp.gravity, sp.use_gpu_pipeline = 0.02, 2, gymapi.UP_AXIS_Z, gymapi.Vec3(0, 0, -9.81), True
+    sim = gym.create_sim(0, -1, gymapi.SIM_PHYSX, sp)
+    gym.add_ground(sim, gymapi.PlaneParams())
+    ao = gymapi.AssetOptions()
+    ao.default_dof_drive_mode, ao.collapse_fixed_joints, ao.replace_cylinder_with_capsule = gymapi.DOF_MODE_NONE, True, True
+    ao.density, ao.angular_damping, ao.linear_damping, ao.armature, ao.thickness = 0.001, 0.0, 0.0, 0.0, 0.01
+    asset = gym.load_asset(sim, "/no/such/checkout/assets", "urdf/anymal_c/urdf/anymal_minimal.urdf", ao)
+    assert gym.get_asset_dof_count(asset) == 12
+    names = gym.get_asset_dof_names(asset)
+    default = torch.tensor([{"HAA": 0.03 if nm.startswith("L") else -0.03, "HFE": 0.4 if nm[1] == "F" else -0.4,
+                             "KFE": -0.8 if nm[1] == "F" else 0.8}[nm[3:6]] for nm in names], device="cuda:0")
+    props = gym.get_asset_dof_properties(asset)
+    props["driveMode"][:] = gymapi.DOF_MODE_POS; props["stiffness"][:] = 85.0; props["damping"][:] = 2.0
+    pose = gymapi.Transform(); pose.p = gymapi.Vec3(0, 0, 0.62)
+    for i in range(n):
+        e = gym.create_env(sim, gymapi.Vec3(-2, -2, 0), gymapi.Vec3(2, 2, 2), 8)
+        h = gym.create_actor(e, asset, pose, "anymal", i, 1, 0)
+        gym.set_actor_dof_properties(e, h, props)
+    gym.prepare_sim(sim)
+    root = gymtorch.wrap_tensor(gym.acquire_actor_root_state_tensor(sim))
+    dof = gymtorch.wrap_tensor(gym.acquire_dof_state_tensor(sim)).view(n, 12, 2)
+    cf = gymtorch.wrap_tensor(gym.acquire_net_contact_force_tensor(sim)).view(n, -1, 3)
+    dof[:, :, 0] = default
+    gym.set_dof_state_tensor(sim, gymtorch.unwrap_tensor(dof))
+    targets = default.repeat(n, 1).contiguous()
+    for _ in range(150):
+        gym.set_dof_position_target_tensor(sim, gymtorch.unwrap_tensor(targets))
+        gym.simulate(sim)
+    torch.cuda.synchronize()
+    assert torch.isfinite(root).all() and torch.isfinite(dof).all()
+    assert ((root[:, 2] > 0.4) & (root[:, 2] < 0.65)).all(), root[:, 2]
+    assert (dof[:, :, 0] - default).abs().max() < 0.12 and dof[:, :, 1].abs().max() < 0.2 and root[:, 7:13].abs().max() < 0.1
+    up_z = 1 - 2 * (root[:, 3] ** 2 + root[:, 4] ** 2)
+    assert (up_z > 0.98).all()
+    W = float(sim.asset.model.total_mass()) * 9.81
+    Fz = cf[:, :, 2].sum(1)
+    assert ((Fz - W).abs() / W < 0.05).all(), (Fz, W)
