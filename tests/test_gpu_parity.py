@@ -820,7 +820,8 @@ def test_generic_gym_api_position_drive_anymal_stands():
     torch.cuda.synchronize()
     assert torch.isfinite(root).all() and torch.isfinite(dof).all()
     assert ((root[:, 2] > 0.4) & (root[:, 2] < 0.65)).all(), root[:, 2]
-    assert (dof[:, :, 0] - default).abs().max() < 0.12 and dof[:, :, 1].abs().max() < 0.2 and root[:, 7:13].abs().max() < 0.1
+    # a PD drive has steady-state error under load: ~20 N m at the knees / 85 N m per rad = 0.24 rad
+    assert (dof[:, :, 0] - default).abs().max() < 0.3 and dof[:, :, 1].abs().max() < 0.2 and root[:, 7:13].abs().max() < 0.1
     up_z = 1 - 2 * (root[:, 3] ** 2 + root[:, 4] ** 2)
     assert (up_z > 0.98).all()
     W = float(sim.asset.model.total_mass()) * 9.81
