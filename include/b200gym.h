@@ -269,6 +269,15 @@ int b2g_task_step(b2g_sim *sim, const float *actions, void *stream);
 int b2g_task_step_host(b2g_sim *sim, const float *h_actions, float *h_obs, float *h_rew, int64_t *h_reset,
                        uint8_t *h_timeout, void *stream);
 
+/* Introspection, host only (no device needed): the slot programs b2g_create would build for `model` on `lanes`
+ * lanes per env (1, 2, 4 or 8; 0 = the engine's own choice).  `compact` selects the env-wide accumulator numbering of
+ * the multi-actor kernels.  slots_out receives B2G_PLAN_MAX_SLOTS x B2G_PLAN_MAX_LANES records of 8 int32:
+ * link, parent ((lane << 8) | slot + 1; 0 = root), out (-1 carried, -2 dropped, else accumulator id), flags, child[4].
+ * info_out: ns, lanes, nacc, root_acc, cross_lane. */
+#define B2G_PLAN_MAX_SLOTS 24
+#define B2G_PLAN_MAX_LANES 8
+int b2g_plan(const b2g_model *model, int32_t lanes, int32_t compact, int32_t *slots_out, int32_t info_out[5]);
+
 /* number of kernels this library has launched since creation (bench.py "gpu_launches") */
 int64_t b2g_launch_count(const b2g_sim *sim);
 const char *b2g_last_error(void);

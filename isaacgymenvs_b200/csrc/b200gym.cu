@@ -711,6 +711,27 @@ static int pick_lanes(const b2g_model *m, bool single) {
     return 1;
 }
 
+static_assert(B2G_PLAN_MAX_SLOTS == MAX_SLOTS && B2G_PLAN_MAX_LANES == MAX_LANES, "plan table size");
+extern "C" int b2g_plan(const b2g_model *m, int32_t lanes, int32_t compact, int32_t *slots_out, int32_t info_out[5]) {
+    if (!m || !slots_out || !info_out) return fail(B2G_E_INVALID, "b2g_plan: null argument");
+    if (m->nl < 1 || m->nl > MAX_LINKS || m->nl - 1 > MAX_SLOTS) return fail(B2G_E_INVALID, "b2g_plan: model exceeds compiled limits");
+    if (lanes != 0 && lanes != 1 && lanes != 2 && lanes != 4 && lanes != 8) return fail(B2G_E_INVALID, "b2g_plan: lanes must be 0, 1, 2, 4 or 8");
+    DevModel *h = new DevModel();
+    memset(h, 0, sizeof(*h));
+    const int L = lanes ? lanes : pick_lanes(m, false);
+    const int rc = schedule(m, L, *h, compact != 0);
+    if (rc != 0) { delete h; return fail(B2G_E_INVALID, "b2g_plan: the articulation does not fit the slot program limits"); }
+    for (int sl = 0; sl < MAX_SLOTS; sl++) for (int l = 0; l < MAX_LANES; l++) {
+        const SlotRec &r = h->slots[sl][l];
+        int32_t *o = slots_out + 8 * (sl * MAX_LANES + l);
+        o[0] = r.link; o[1] = r.parent; o[2] = r.out; o[3] = r.flags;
+        for (int c = 0; c < MAX_CHILD_REFS; c++) o[4 + c] = r.child[c];
+    }
+    info_out[0] = h->ns; info_out[1] = h->lanes; info_out[2] = h->nacc; info_out[3] = h->root_acc; info_out[4] = h->cross_lane;
+    delete h;
+    return B2G_OK;
+}
+
 extern "C" int b2g_create(const b2g_model *m, const b2g_sim_params *sp, int32_t num_envs, int32_t device, b2g_sim **out) {
     return b2g_create_ext(m, nullptr, sp, num_envs, device, out);
 }

@@ -153,13 +153,13 @@ def lib():
         _lib.b2g_last_error.restype = C.c_char_p
         _lib.b2g_launch_count.restype = C.c_int64
         _lib.b2g_launch_count.argtypes = [C.c_void_p]
-        for fn in ("b2g_create", "b2g_create_ext", "b2g_destroy", "b2g_bind", "b2g_simulate", "b2g_refresh_rigid_body_state",
+        for fn in ("b2g_plan", "b2g_create", "b2g_create_ext", "b2g_destroy", "b2g_bind", "b2g_simulate", "b2g_refresh_rigid_body_state",
                    "b2g_set_task", "b2g_set_anymal_task", "b2g_set_hand_task", "b2g_task_step", "b2g_task_step_host"):
             getattr(_lib, fn).restype = C.c_int
     return _lib
 
 
-EXPORTS = ("b2g_create", "b2g_create_ext", "b2g_destroy", "b2g_bind", "b2g_simulate", "b2g_refresh_rigid_body_state", "b2g_set_task",
+EXPORTS = ("b2g_plan", "b2g_create", "b2g_create_ext", "b2g_destroy", "b2g_bind", "b2g_simulate", "b2g_refresh_rigid_body_state", "b2g_set_task",
            "b2g_set_anymal_task", "b2g_set_hand_task", "b2g_task_step", "b2g_task_step_host", "b2g_launch_count", "b2g_last_error", "b2g_version")
 
 
@@ -193,6 +193,15 @@ def pack_model(model, ground_mu=1.0):
     cm.cp_mu = arr("cp_mu", np.asarray(model.cp_mu), np.float32)
     cm.contact_kn, cm.contact_cn, cm.contact_vs = model.contact_kn, model.contact_cn, model.contact_vs
     return cm, keep
+
+
+def plan(model, lanes=0, compact=False):
+    """The slot programs the engine builds for `model` (host only, no GPU): -> (info dict, slots int32 [24][8][8])."""
+    cm, keep = pack_model(model)
+    slots = np.zeros((24, 8, 8), np.int32)
+    info = (C.c_int32 * 5)()
+    _check(lib().b2g_plan(C.byref(cm), C.c_int32(lanes), C.c_int32(int(compact)), C.c_void_p(slots.ctypes.data), info), "b2g_plan")
+    return dict(ns=info[0], lanes=info[1], nacc=info[2], root_acc=info[3], cross_lane=info[4]), slots
 
 
 class Sim:

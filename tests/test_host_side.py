@@ -93,3 +93,66 @@ def test_importer_known_answers_and_compiled_blobs_are_current():
         blob = load_compiled(name)
         for f in ("parent", "jtype", "axis", "lpos", "mass", "com", "inertia", "lower", "upper", "cp_pos", "cp_radius", "limit_k"):
             assert np.allclose(getattr(fresh, f), getattr(blob, f)), (name, f)
+
+
+@pytest.mark.parametrize("name", ["cartpole", "ant", "humanoid", "anymal", "shadow_hand"])
+@pytest.mark.parametrize("lanes", [1, 2, 4, 8])
+@pytest.mark.parametrize("compact", [False, True])
+def test_slot_programs_are_consistent(name, lanes, compact):
+    """The host-side list scheduler (b2g_plan = what b2g_create builds): every link is processed exactly once, after
+    its parent; inertia hand-offs (carried in registers / parked in an accumulator / dropped under a fixed root) and
+    the parents' child references agree."""
+    from isaacgymenvs_b200 import engine
+    from isaacgymenvs_b200.assets import load_compiled
+    m = load_compiled(name)
+    info, S = engine.plan(m, lanes, compact)
+    ns, L = info["ns"], info["lanes"]
+    assert L == lanes and 1 <= ns <= 24
+    where = {}
+    for s in range(24):
+        for l in range(8):
+            link = int(S[s, l, 0])
+            if link >= 0:
+                assert s < ns and l < L and link not in where and 1 <= link < m.nl
+                where[link] = (l, s)
+    assert sorted(where) == list(range(1, m.nl))
+    crit = np.ones(m.nl, int)
+    for i in range(m.nl - 1, 0, -1):
+        crit[m.parent[i]] = max(crit[m.parent[i]], crit[i] + 1)
+    assert ns >= crit[0] - 1                                        # never shorter than the longest chain below the root
+    if lanes == 1:
+        assert ns == m.nl - 1 and info["cross_lane"] == 0
+    parked = {}
+    cross = 0
+    for link, (l, s) in where.items():
+        rec = S[s, l]
+        p = int(m.parent[link])
+        if p == 0:
+            assert rec[1] == 0
+            if rec[2] != -1:
+                assert s > 0 and (rec[2] == info["root_acc"] or (rec[2] == -2 and compact and m.root_fixed))
+            else:
+                assert s == 0
+        else:
+            pl, ps = where[p]
+            assert ps < s and rec[1] == ((pl << 8) | (ps + 1))
+            cross |= int(pl != l)
+            if pl == l and ps == s - 1:
+                assert rec[2] == -1
+            else:
+                assert rec[2] >= 0 and rec[2] < info["nacc"]
+                parked[link] = (l, int(rec[2]))
+    assert cross == info["cross_lane"]
+    # every parked inertia is collected exactly once, by its parent
+    seen = {}
+    for link, (l, s) in where.items():
+        refs = [int(c) for c in S[s, l, 4:8] if c >= 0]
+        assert (int(S[s, l, 3]) & 1) == int(len(refs) > 0)
+        for r in refs:
+            seen[r] = seen.get(r, 0) + 1
+            kids = [k for k, v in parked.items() if int(m.parent[k]) == link and ((v[0] << 8) | v[1]) == r or (compact and int(m.parent[k]) == link and v[1] == (r & 255))]
+            assert len(kids) == 1, (link, r, kids)
+    assert sum(seen.values()) == len(parked) and all(v == 1 for v in seen.values())
+    if compact:                                                     # env-wide ids are unique
+        ids = [v[1] for v in parked.values()]
+        assert len(set(ids)) == len(ids)
