@@ -13,14 +13,19 @@
 //     contact spring-damper-friction are integrated implicitly by augmenting the joint-space
 //     diagonal and the link inertia (DESIGN.md "time stepping").
 //
-// Work decomposition: an environment is owned by L lanes of a warp (L = 1, 2 or 4).  Each lane owns
-// whole sub-trees hanging off the root as a sequence of "slots" (one 1-DOF link each, parents
-// before children); the root is replicated on the L lanes and the lanes' sub-tree contributions
-// meet in an xor-butterfly (warp shuffles).  The three ABA sweeps are ROLLED loops over the slots:
-// per-slot state (48 floats) lives in shared memory laid out [slot][float4][thread] (conflict-free
-// 128-bit accesses), the articulated inertia being swept travels in registers along chains.  This
-// keeps the kernel ~1/5 the code size and ~1/2 the registers of the fully unrolled first version
-// (profiles/r1_v1_*: 88 KB of SASS, 255 registers, 24 % of issue stalls "no instruction").
+// Work decomposition: an environment is owned by L lanes of a warp (L = 1, 2, 4 or 8).  Each lane runs a
+// "slot program" (one 1-DOF link per step, parents before children; the host list-schedules the links
+// over the lanes, b200gym.cu schedule()); the root is replicated on the L lanes and the lanes'
+// contributions meet in an xor-butterfly (warp shuffles).  The three ABA sweeps are ROLLED loops over
+// the slots: per-slot state (10 float4) lives in shared memory -- [slot][k][thread] (conflict-free
+// 128-bit accesses) or, for the multi-actor kernels, [link][k][env] (no storage for idle slots) --
+// and the articulated inertia being swept travels in registers along chains, through parked
+// accumulators otherwise.  This keeps the kernel ~1/5 the code size and ~1/2 the registers of the
+// fully unrolled first version (profiles/r1_v1_*: 88 KB of SASS, 255 registers, 24 % of issue stalls
+// "no instruction").
+//
+// OBJ = true adds a second, free rigid body per env (a box: ShadowHand's cube) in contact with the
+// articulation's spheres and box primitives and with the ground, plus fixed two-joint tendons.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
