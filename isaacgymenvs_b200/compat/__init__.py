@@ -22,7 +22,7 @@ def install(reference_root=None):
     pkg.terrain_utils = types.ModuleType("isaacgym.terrain_utils")
     from .. import terrain as _t
     for n in ("SubTerrain", "random_uniform_terrain", "pyramid_sloped_terrain", "pyramid_stairs_terrain",
-              "discrete_obstacles_terrain", "stepping_stones_terrain"):
+              "discrete_obstacles_terrain", "stepping_stones_terrain", "convert_heightfield_to_trimesh"):
         setattr(pkg.terrain_utils, n, getattr(_t, n))
     sys.modules["isaacgym"] = pkg
     sys.modules["isaacgym.gymapi"] = gymapi

@@ -122,6 +122,7 @@ class _Sim:
         self.compute_device = compute_device
         self.params = params
         self.ground = None
+        self.terrain = None         # height field behind an add_triangle_mesh
         self.envs = []
         self.asset = None           # the articulation (actor 0 of every env)
         self.extra_assets = []      # further actors of an env, in creation order: single rigid bodies
@@ -146,6 +147,17 @@ class Gym:
     def add_ground(self, sim, plane_params):
         sim.ground = plane_params
 
+    def add_triangle_mesh(self, sim, vertices, triangles, params):
+        """anymal_terrain.py:196-208.  The engine collides with height fields, not general meshes: the mesh must come
+        from `terrain_utils.convert_heightfield_to_trimesh` (which tags its arrays with the samples they were built from);
+        the engine then gets the height field itself, placed at params.transform.p."""
+        src = getattr(vertices, "source", None)
+        if src is None:
+            raise NotImplementedError("add_triangle_mesh: only meshes built by terrain_utils.convert_heightfield_to_trimesh "
+                                      "are supported (height-field collision)")
+        sim.terrain = dict(src, origin=(float(params.transform.p.x), float(params.transform.p.y)), z0=float(params.transform.p.z),
+                           friction=float(params.dynamic_friction))
+
     def prepare_sim(self, sim):
         if sim.engine is not None:
             return True
@@ -157,6 +169,14 @@ class Gym:
         model.sensor_pos = np.zeros((len(a.sensors), 3)); model.sensor_quat = np.tile([0, 0, 0, 1.0], (len(a.sensors), 1))
         mu = sim.ground.dynamic_friction if sim.ground is not None else 1.0
         g = p.gravity
+        hf_kw = {}
+        if sim.terrain is not None:
+            t = sim.terrain
+            if t["z0"] != 0.0:
+                raise NotImplementedError("add_triangle_mesh: vertical offset of the terrain")
+            mu = t["friction"]
+            hf_kw = dict(hfield=t["height_field"], hf_horizontal_scale=t["horizontal_scale"], hf_vertical_scale=t["vertical_scale"],
+                         hf_origin=t["origin"])
         ext = None
         apr = 1 + len(sim.extra_assets)
         if sim.extra_assets:
@@ -184,8 +204,10 @@ class Gym:
             if obj is None:
                 tend = []
             ext = engine.pack_model_ext(model, obj=obj, actors_per_env=apr, tendons=tend, tendon_k=tk, tendon_d=td)
+        if ext is not None and hf_kw:
+            raise NotImplementedError("multi-actor envs run on the ground plane")
         sim.engine = engine.Sim(model, len(sim.envs), dt=p.dt, substeps=p.substeps, gravity=(g.x, g.y, g.z), ground_mu=mu,
-                                device=f"cuda:{sim.compute_device}", ext=ext)
+                                device=f"cuda:{sim.compute_device}", ext=ext, **hf_kw)
         poses = torch.tensor([[[q.p.x, q.p.y, q.p.z, q.r.x, q.r.y, q.r.z, q.r.w] for q in env_poses] for env_poses in sim.start_poses],
                              dtype=torch.float32)
         sim.engine.root_state.view(len(sim.envs), apr, 13)[:, :, 0:7] = poses.to(sim.engine.root_state.device)

@@ -203,3 +203,51 @@ class Terrain:
                 else:
                     stepping_stones_terrain(t, stone_size=stepping_stones_size, stone_distance=0.1, max_height=0., platform_size=3., rng=r)
                 self._place(t, i, j)
+
+
+class HeightfieldMesh(np.ndarray):
+    """Vertex / triangle array of a mesh built from a height field; remembers the samples and scales it came from, through
+    `.flatten()` and slicing, so `gym.add_triangle_mesh` can hand the engine the height field itself."""
+
+    def __new__(cls, arr, source=None):
+        obj = np.asarray(arr).view(cls)
+        obj.source = source
+        return obj
+
+    def __array_finalize__(self, obj):
+        self.source = getattr(obj, "source", None)
+
+
+def convert_heightfield_to_trimesh(height_field_raw, horizontal_scale, vertical_scale, slope_threshold=None):
+    """isaacgym.terrain_utils.convert_heightfield_to_trimesh as its call site uses it (anymal_terrain.py:576): one vertex
+    per sample at (i*hs, j*hs, h*vs), two triangles per cell; where the slope between neighbours exceeds `slope_threshold`
+    the vertex on the low side is moved by one cell so that the step becomes a vertical wall.  Returns (vertices (n,3)
+    float32, triangles (m,3) uint32), tagged with the source height field."""
+    hf = np.asarray(height_field_raw)
+    rows, cols = hf.shape
+    y = np.linspace(0, (cols - 1) * horizontal_scale, cols)
+    x = np.linspace(0, (rows - 1) * horizontal_scale, rows)
+    yy, xx = np.meshgrid(y, x)
+    if slope_threshold is not None:
+        t = slope_threshold * horizontal_scale / vertical_scale
+        move_x = np.zeros((rows, cols)); move_y = np.zeros((rows, cols)); move_c = np.zeros((rows, cols))
+        move_x[:rows - 1, :] += (hf[1:, :] - hf[:rows - 1, :] > t)
+        move_x[1:, :] -= (hf[:rows - 1, :] - hf[1:, :] > t)
+        move_y[:, :cols - 1] += (hf[:, 1:] - hf[:, :cols - 1] > t)
+        move_y[:, 1:] -= (hf[:, :cols - 1] - hf[:, 1:] > t)
+        move_c[:rows - 1, :cols - 1] += (hf[1:, 1:] - hf[:rows - 1, :cols - 1] > t)
+        move_c[1:, 1:] -= (hf[:rows - 1, :cols - 1] - hf[1:, 1:] > t)
+        xx = xx + (move_x + move_c * (move_x == 0)) * horizontal_scale
+        yy = yy + (move_y + move_c * (move_y == 0)) * horizontal_scale
+    vertices = np.zeros((rows * cols, 3), dtype=np.float32)
+    vertices[:, 0] = xx.flatten(); vertices[:, 1] = yy.flatten(); vertices[:, 2] = hf.flatten() * vertical_scale
+    triangles = -np.ones((2 * (rows - 1) * (cols - 1), 3), dtype=np.uint32)
+    for i in range(rows - 1):
+        ind0 = np.arange(0, cols - 1) + i * cols
+        ind1, ind2, ind3 = ind0 + 1, ind0 + cols, ind0 + cols + 1
+        start, stop = 2 * i * (cols - 1), 2 * i * (cols - 1) + 2 * (cols - 1)
+        triangles[start:stop:2, 0] = ind0; triangles[start:stop:2, 1] = ind3; triangles[start:stop:2, 2] = ind1
+        triangles[start + 1:stop:2, 0] = ind0; triangles[start + 1:stop:2, 1] = ind2; triangles[start + 1:stop:2, 2] = ind3
+    src = dict(height_field=np.ascontiguousarray(hf, dtype=np.int16), horizontal_scale=float(horizontal_scale),
+               vertical_scale=float(vertical_scale))
+    return HeightfieldMesh(vertices, src), HeightfieldMesh(triangles, src)

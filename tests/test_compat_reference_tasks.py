@@ -17,7 +17,7 @@ from tests.conftest import needs_reference, REFERENCE
 class _FakeSim:
     def __init__(self, model, num_envs, dt, substeps, gravity=(0, 0, -9.81), ground_mu=1.0, device="cpu", ext=None, **kw):
         from isaacgymenvs_b200 import engine as E
-        self.model, self.num_envs, self.ext = model, num_envs, ext
+        self.model, self.num_envs, self.ext, self.kw = model, num_envs, ext, kw
         self.actors_per_env = int(ext.actors_per_env) if ext is not None else 1
         self.nd, self.nb, self.ns = model.ndof, model.nb, len(model.sensor_body)
         self.root_state = torch.zeros(num_envs * self.actors_per_env, 13); self.root_state[:, 6] = 1
@@ -150,3 +150,29 @@ def test_unmodified_reference_flat_anymal_runs_on_the_shim(compat_cpu):
     assert obs["obs"].shape == (n, 48) and torch.isfinite(obs["obs"]).all() and torch.isfinite(rew).all()
     # targets = action_scale * actions + default_dof_pos reached the engine's target tensor (anymal.py:226-229)
     assert torch.allclose(sim.dof_target, 0.5 * env.actions + env.default_dof_pos)
+
+
+@needs_reference
+def test_unmodified_reference_anymal_terrain_runs_on_the_shim(compat_cpu):
+    """tasks/anymal_terrain.py builds its terrain with isaacgym.terrain_utils (restated in isaacgymenvs_b200/terrain.py),
+    converts it to a triangle mesh and calls gym.add_triangle_mesh; the shim hands the engine the underlying height field."""
+    import importlib
+    mod = importlib.import_module("isaacgymenvs.tasks.anymal_terrain")
+    assert os.path.realpath(mod.__file__).startswith(REFERENCE)
+    n = 16
+    cfg = _cfg("AnymalTerrain", n)
+    cfg["env"]["terrain"]["numLevels"] = 2; cfg["env"]["terrain"]["numTerrains"] = 2
+    env = mod.AnymalTerrain(cfg=cfg, rl_device="cpu", sim_device="cpu", graphics_device_id=-1, headless=True,
+                            virtual_screen_capture=False, force_render=False)
+    sim = env.sim.engine
+    assert env.num_obs == 188 and env.num_acts == 12
+    t = env.terrain
+    assert np.array_equal(sim.kw["hfield"], t.height_field_raw) and sim.kw["hfield"].dtype == np.int16
+    assert sim.kw["hf_horizontal_scale"] == t.horizontal_scale and sim.kw["hf_vertical_scale"] == t.vertical_scale
+    assert sim.kw["hf_origin"] == (-t.border_size, -t.border_size)
+    assert t.vertices.shape == (t.tot_rows * t.tot_cols, 3) and t.triangles.shape == (2 * (t.tot_rows - 1) * (t.tot_cols - 1), 3)
+    # the mesh follows the samples: every vertex height is its sample's
+    assert np.allclose(np.asarray(t.vertices)[:, 2].reshape(t.tot_rows, t.tot_cols), t.height_field_raw * t.vertical_scale)
+    obs, rew, reset, extras = env.step(2 * torch.rand(n, 12) - 1)
+    assert sim.steps == env.decimation + env.control_freq_inv and obs["obs"].shape == (n, 188) and torch.isfinite(obs["obs"]).all()
+    assert torch.isfinite(rew).all() and "time_outs" in extras
