@@ -141,6 +141,12 @@ class VecTask(Env):
         self.viewer = None
         self.first_randomization = True
         self.dr_randomizations = {}
+        # domain randomisation: observation / action noise only (utils/dr.py); physical parameters raise
+        self.randomizer = None
+        task_cfg = self.cfg.get("task", {}) if isinstance(self.cfg, dict) else {}
+        if task_cfg.get("randomize", False):
+            from ...utils.dr import Randomizer
+            self.randomizer = Randomizer(task_cfg.get("randomization_params", {}))
         if self.device == "cpu":
             raise engine.EngineError(
                 "sim_device=cpu / pipeline=cpu: the B200-native stepper has no CPU path (north_star: no CPU "
@@ -169,6 +175,7 @@ class VecTask(Env):
         self.reset_count = torch.zeros(self.num_envs, device=dev, dtype=torch.int32)
         # clamp(obs, +-clip_obs) is a separate tensor only when the clip is finite (vec_task.py:402)
         self.obs_clipped = self.obs_buf if not np.isfinite(self.clip_obs) else torch.zeros_like(self.obs_buf)
+        self._obs_engine = self.obs_buf            # the tensor bound to the engine (obs_buf may be rebound by observation noise)
         self.extras = {}
 
     def create_sim(self):
@@ -195,7 +202,7 @@ class VecTask(Env):
 
     def _bind_task(self):
         E = engine
-        bufs = {E.T_ACTIONS: self.actions, E.T_OBS: self.obs_buf, E.T_REW: self.rew_buf, E.T_RESET: self.reset_buf,
+        bufs = {E.T_ACTIONS: self.actions, E.T_OBS: self._obs_engine, E.T_REW: self.rew_buf, E.T_RESET: self.reset_buf,
                 E.T_PROGRESS: self.progress_buf, E.T_TIMEOUT: self.timeout_buf.view(torch.uint8),
                 E.T_RESET_COUNT: self.reset_count, E.T_OBS_CLIPPED: self.obs_clipped}
         bufs.update(self._task_buffers())
@@ -213,6 +220,10 @@ class VecTask(Env):
 
     # ---- vec_task.py:360-408
     def step(self, actions: torch.Tensor) -> Tuple[Dict[str, torch.Tensor], torch.Tensor, torch.Tensor, Dict[str, Any]]:
+        if self.randomizer is not None:         # apply_randomizations, vec_task.py:610-718 (non-physical part)
+            if self.randomizer.update(self.control_steps * max(int(self.control_freq_inv), 1)):
+                for key, model in self.randomizer.models.items():
+                    self.dr_randomizations[key] = {"noise_lambda": model}
         if self.dr_randomizations.get('actions', None):
             actions = self.dr_randomizations['actions']['noise_lambda'](actions)
         a = actions.to(device=self.device, dtype=torch.float32)
@@ -220,11 +231,15 @@ class VecTask(Env):
             a = a.view(self.num_envs, -1)
         self.sim.task_step(a.contiguous())      # clamp + pre_physics + simulate + post_physics + timeout + clip
         self.control_steps += 1
-        if self.dr_randomizations.get('observations', None):
-            self.obs_buf = self.dr_randomizations['observations']['noise_lambda'](self.obs_buf)
         self._fill_extras()
         self.extras["time_outs"] = self.timeout_buf.to(self.rl_device)
-        self.obs_dict["obs"] = self.obs_clipped.to(self.rl_device)
+        if self.dr_randomizations.get('observations', None):
+            # vec_task.py:397-402: noise on the observation, then the clamp.  The engine keeps writing the tensor it is
+            # bound to (_obs_engine); obs_buf is the noisy copy the caller sees
+            self.obs_buf = self.dr_randomizations['observations']['noise_lambda'](self._obs_engine)
+            self.obs_dict["obs"] = torch.clamp(self.obs_buf, -self.clip_obs, self.clip_obs).to(self.rl_device)
+        else:
+            self.obs_dict["obs"] = self.obs_clipped.to(self.rl_device)
         if self.num_states > 0:
             self.obs_dict["states"] = self.get_state()
         return self.obs_dict, self.rew_buf.to(self.rl_device), self.reset_buf.to(self.rl_device), self.extras

@@ -48,8 +48,7 @@ class _Locomotion(VecTask):
         self.plane_static_friction = e["plane"]["staticFriction"]
         self.plane_dynamic_friction = e["plane"]["dynamicFriction"]
         self.plane_restitution = e["plane"]["restitution"]
-        if self.randomize:
-            raise NotImplementedError("domain randomisation is outside the hot path (SURVEY.md 8f rank 3)")
+        # randomize: observation / action noise is applied by the base class; physical randomisation raises there
         cfg["env"]["numObservations"] = self.NUM_OBS
         cfg["env"]["numActions"] = self.NUM_ACT
         self.up_axis_idx = 2

@@ -21,8 +21,7 @@ class ShadowHand(VecTask):
         self.cfg = cfg
         e = cfg["env"]
         self.randomize = cfg["task"]["randomize"]
-        if self.randomize:
-            raise NotImplementedError("domain randomisation is outside the hot path (SURVEY.md 8f rank 3)")
+        # randomize: observation / action noise is applied by the base class; physical randomisation raises there
         self.dist_reward_scale = e["distRewardScale"]; self.rot_reward_scale = e["rotRewardScale"]
         self.action_penalty_scale = e["actionPenaltyScale"]; self.success_tolerance = e["successTolerance"]
         self.reach_goal_bonus = e["reachGoalBonus"]; self.fall_dist = e["fallDistance"]; self.fall_penalty = e["fallPenalty"]

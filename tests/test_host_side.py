@@ -184,3 +184,33 @@ def test_bench_reference_arm_other_ranks_exit_quietly():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--gpus", "2"],
                          capture_output=True, text=True, timeout=120, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_domain_randomisation_noise_matches_reference():
+    """isaacgymenvs_b200.utils.dr.NoiseModel against the lambdas the reference's own VecTask.apply_randomizations
+    installs (tests/golden/make_golden_dr.py): same torch seed -> same numbers, for gaussian / uniform, additive /
+    scaling, linear / constant / no schedule, first call (draws the correlated sample) and second call (re-uses it)."""
+    import sys, torch
+    from isaacgymenvs_b200.utils.dr import NoiseModel, Randomizer
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_golden_dr as G
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "dr_noise.npz"))
+    checked = 0
+    for cname, params in G.CASES.items():
+        for frame in G.FRAMES:
+            for key in ("observations", "actions"):
+                if key not in params:
+                    continue
+                x = torch.tensor(gold[f"x_{key}"])
+                nm = NoiseModel(params[key], frame)
+                torch.manual_seed(1000 + frame)
+                y1 = nm(x.clone()); y2 = nm(x.clone())
+                np.testing.assert_allclose(y1.numpy(), gold[f"{cname}_{frame}_{key}_1"], rtol=0, atol=1e-7)
+                np.testing.assert_allclose(y2.numpy(), gold[f"{cname}_{frame}_{key}_2"], rtol=0, atol=1e-7)
+                checked += 1
+    assert checked == 25
+    # frequency gating (vec_task.py:619-640): first call always, then every `frequency` frames
+    r = Randomizer({"frequency": 10, "observations": G.CASES["uniform_scale"]["observations"]})
+    assert r.update(0) and not r.update(5) and r.update(10) and not r.update(19) and r.update(20)
+    with pytest.raises(NotImplementedError):
+        Randomizer({"frequency": 1, "sim_params": {}})
