@@ -50,3 +50,27 @@ def test_two_rank_gloo():
     assert t0 == [2.0, 5.0] and t1 == [2.0, 5.0]              # max over ranks
     from oracle import tasks_np as T
     assert u0 is None and np.allclose(u1, T.reset_uniforms(42, 11, 0, 4))   # sharding-independent stream
+
+
+def test_hand_resets_do_not_depend_on_the_sharding():
+    """ShadowHand's reset_idx / reset_target_pose draw from a stream keyed by the GLOBAL env id (env_id_offset), so 16 envs
+    stepped as one shard or as two shards of 8 come out identical (numpy restatement of the kernel's host contract)."""
+    import os as _os
+    from oracle import tasks_np as T
+    from tests.hand_common import golden_case
+    gold = np.load(_os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden", "shadow_hand.npz"))
+    st, P, actions = golden_case(gold, "a")
+    n = 16
+    cut = lambda d, sl: {k: (v[sl].copy() if isinstance(v, np.ndarray) and v.shape[:1] == (256,) else v) for k, v in d.items()}
+    whole, Pw = cut(st, slice(0, n)), cut(P, slice(0, n))
+    whole["reset"][:] = 1
+    T.hand_pre_physics(whole, actions[:n], dict(Pw, env_id_offset=0))
+    parts = []
+    for r in range(2):
+        sl = slice(8 * r, 8 * r + 8)
+        s_, P_ = cut(st, sl), cut(P, sl)
+        s_["reset"][:] = 1
+        T.hand_pre_physics(s_, actions[sl], dict(P_, env_id_offset=8 * r))
+        parts.append(s_)
+    for k in ("root", "dof_pos", "dof_vel", "cur_targets", "goal_states"):
+        assert np.array_equal(whole[k], np.concatenate([p[k] for p in parts], 0)), k
