@@ -180,3 +180,34 @@ def test_object_rests_on_the_ground():
         orc.simulate(root, dof, target=np.zeros((1, m.ndof)), obj=o)
     pen = obj["mass"] * 9.81 / 4 / (10000.0 * obj["mass"])            # four corners share the weight
     assert abs(o[0, 2] - (0.025 - pen)) < 2e-4 and np.abs(o[0, 7:13]).max() < 1e-3
+
+
+def test_aba_satisfies_inverse_dynamics_position_drives():
+    """The fixed-base ShadowHand articulation (24 DOF, position drives from the MJCF <position kp forcerange>, gravity off):
+    the accelerations the oracle produces need exactly the PD + passive joint forces the scheme applies (independent
+    Newton-Euler inverse dynamics), as long as no drive saturates."""
+    from tests.hand_common import hand_setup
+    m, _, _ = hand_setup()
+    dt, sub = 0.01667, 2
+    sim = OracleSim(m, dt, sub, G)
+    h = dt / sub
+    rng = np.random.default_rng(3)
+    for trial in range(5):
+        root = np.zeros(13); root[2] = 0.5; root[3:7] = m.default_root_quat
+        lo, hi = m.lower[1:], m.upper[1:]
+        q = lo + (hi - lo) * (0.3 + 0.05 * rng.uniform(-1, 1, size=m.ndof))      # inside the limits ...
+        cap = np.where(m.kp[1:] > 0, 0.6 * m.effort[1:] / np.maximum(m.kp[1:], 1e-9), np.inf)
+        q = np.sign(q) * np.minimum(np.abs(q), cap)                               # ... and the drives (target 0) unsaturated
+        qd = 0.2 * rng.normal(size=m.ndof)
+        dof = np.stack([q, qd], -1)
+        qdd, ra, da = sim.forward_dynamics(root, dof, np.zeros(m.ndof))         # position targets = 0
+        tau_req, _ = rnea_np.inverse_dynamics(m, root, q, qd, qdd, (np.zeros(3), np.zeros(3)), (0.0, 0.0, 0.0))
+        qd1 = qd + h * qdd; q1 = q + h * qd1
+        pos = m.drive_mode[1:] == 1
+        pd = np.where(pos, m.kp[1:] * (0.0 - q1) - m.kd[1:] * qd1, 0.0)
+        assert (np.abs(m.kp[1:] * (0.0 - (q + h * qd)) - m.kd[1:] * qd)[pos] < m.effort[1:][pos]).all()      # no saturation here
+        inside = (q > lo) & (q < hi)
+        assert inside.all()
+        applied = pd - m.damping[1:] * qd1 - m.stiffness[1:] * q1 - m.armature[1:] * qdd
+        scale = max(1.0, np.abs(applied).max())
+        assert np.allclose(tau_req, applied, atol=1e-8 * scale, rtol=1e-7), (trial, np.abs(tau_req - applied).max())
