@@ -211,3 +211,31 @@ def test_aba_satisfies_inverse_dynamics_position_drives():
         applied = pd - m.damping[1:] * qd1 - m.stiffness[1:] * q1 - m.armature[1:] * qdd
         scale = max(1.0, np.abs(applied).max())
         assert np.allclose(tau_req, applied, atol=1e-8 * scale, rtol=1e-7), (trial, np.abs(tau_req - applied).max())
+
+
+def test_object_collision_exchanges_momentum():
+    """A cube thrown at a free-floating Ant in zero gravity: the contact pushes both.  The block-Jacobi coupling (each body
+    implicit in its OWN acceleration only) does not apply exactly opposite impulses: the total linear momentum drifts by
+    about cn*h*dv (13 % of the incoming momentum at h = 4 ms for this 2 m/s hit, 7 % at 1 ms) and the drift shrinks with the
+    step.  Recorded here as a known property of the scheme (DESIGN.md 7b lists the symmetric coupling as next work)."""
+    m = load_compiled("ant")
+    obj = dict(mass=0.5, inertia=[0.5 * 0.1 ** 2 / 6 * 4] * 3, half=[0.1, 0.1, 0.1], mu=0.5, gravity_on=0)
+
+    def run(dt, T=0.6):
+        sim = OracleSim(m, dt, 1, (0.0, 0.0, 0.0), obj=obj)
+        root = np.zeros((1, 13)); root[0, 2] = 5.0; root[0, 6] = 1
+        q0 = np.where(m.lower[1:] > 0, m.lower[1:], np.where(m.upper[1:] < 0, m.upper[1:], 0.0))
+        dof = np.zeros((1, m.ndof, 2)); dof[0, :, 0] = q0
+        o = np.zeros((1, 13)); o[0, 0:3] = [-0.8, 0.02, 5.03]; o[0, 6] = 1; o[0, 7] = 2.0          # flying at the torso along +x
+        P0, _ = rnea_np.momentum(m, root[0], dof[0, :, 0], dof[0, :, 1])
+        p0 = P0 + obj["mass"] * o[0, 7:10]
+        for _ in range(int(round(T / dt))):
+            sim.simulate(root, dof, np.zeros((1, m.ndof)), obj=o)
+        P1, _ = rnea_np.momentum(m, root[0], dof[0, :, 0], dof[0, :, 1])
+        return p0, P1 + obj["mass"] * o[0, 7:10], P1, o[0, 7:10].copy()
+    p0, p1, Pant, vobj = run(0.004)
+    assert Pant[0] > 0.3 and vobj[0] < 1.5                       # they did collide: the Ant took momentum, the cube slowed down
+    e1 = np.abs(p1 - p0).max()
+    _, p2, _, _ = run(0.001)
+    e2 = np.abs(p2 - p0).max()
+    assert e1 < 0.15 * np.abs(p0).max() and e2 < 0.6 * e1 + 1e-6, (e1, e2)
