@@ -78,7 +78,10 @@ typedef struct {
     double dt;
     /* optional second body per env: a free box (ShadowHand's cube, shadow_hand.py:372) in contact with the
      * articulation's contact spheres, with its box primitives and with the ground */
-    int obj_on, obj_gravity_on, nbx, pad1;
+    int obj_on, obj_gravity_on, nbx;
+    int obj_coupling;   /* 0: block-Jacobi (what the CUDA engine does): both bodies implicit in their own acceleration.
+                           1: Gauss-Seidel (EXPERIMENT): the articulation as in 0, then the object receives exactly
+                              the opposite of the forces applied to the links -> linear momentum is conserved */
     double obj_mass, obj_inertia[3], obj_half[3], obj_kn, obj_cn, obj_mu;
     const int *box_link, *box_body;         /* nbx: link carrying the box, body it belongs to */
     const double *box_pos, *box_quat, *box_half;   /* nbx x 3,4,3 (link frame) */
@@ -381,8 +384,10 @@ static void substep(const OracleModel *m, real h, real *root, real *dof, const r
                 real Jo_[18], rox_[9], GJo_[18]; skew(ro_, rox_);                                                                \
                 for (int a_ = 0; a_ < 3; a_++) for (int b_ = 0; b_ < 3; b_++) { Jo_[6 * a_ + b_] = -rox_[3 * a_ + b_]; Jo_[6 * a_ + 3 + b_] = (a_ == b_); } \
                 for (int a_ = 0; a_ < 3; a_++) for (int b_ = 0; b_ < 6; b_++) { real s_ = 0; for (int k = 0; k < 3; k++) s_ += Gw_[3 * a_ + k] * Jo_[6 * k + b_]; GJo_[6 * a_ + b_] = s_; } \
+                if (m->obj_coupling == 0) {                                                                                      \
                 for (int a_ = 0; a_ < 6; a_++) for (int b_ = 0; b_ < 6; b_++) { real s_ = 0; for (int k = 0; k < 3; k++) s_ += Jo_[6 * k + a_] * GJo_[6 * k + b_]; Ao[6 * a_ + b_] += h * s_; } \
                 for (int a_ = 0; a_ < 6; a_++) { real s_ = 0; for (int k = 0; k < 3; k++) s_ += Jo_[6 * k + a_] * F0_[k]; bo[a_] -= s_; } \
+                }                                                                                                                \
                 memcpy(oF0[noc], F0_, sizeof(F0_)); memcpy(oG[noc], Gw_, sizeof(Gw_)); memcpy(oJ[noc], J_, sizeof(J_));          \
                 olink[noc] = LI; obody[noc] = BI; memcpy(oPc[noc], (PC), 3 * sizeof(real)); noc++;                                \
             }                                                                                                                    \
@@ -490,12 +495,17 @@ static void substep(const OracleModel *m, real h, real *root, real *dof, const r
 
     /* ---- hand-object contacts: forces applied to the articulation's bodies (sensors), then the object itself */
     if (m->obj_on && obj) {
-        for (int n = 0; n < noc && cf_body; n++) {
+        for (int n = 0; n < noc; n++) {
             int i = olink[n], b = obody[n];
-            if (b < 0) continue;
             real Ja[3], F[3];
             for (int a_ = 0; a_ < 3; a_++) { real s_ = 0; for (int k = 0; k < 6; k++) s_ += oJ[n][6 * a_ + k] * a[i][k]; Ja[a_] = s_; }
             for (int a_ = 0; a_ < 3; a_++) { real s_ = 0; for (int k = 0; k < 3; k++) s_ += oG[n][3 * a_ + k] * Ja[k]; F[a_] = oF0[n][a_] - h * s_; }
+            if (m->obj_coupling == 1) {        /* the object gets the opposite of what the link got */
+                real ro_[3] = {oPc[n][0] - obj[0], oPc[n][1] - obj[1], oPc[n][2] - obj[2]}, mF[3] = {-F[0], -F[1], -F[2]}, tq_[3];
+                cross3(ro_, mF, tq_);
+                for (int k = 0; k < 3; k++) { bo[k] += tq_[k]; bo[3 + k] += mF[k]; }
+            }
+            if (b < 0 || !cf_body) continue;
             real bp[3] = {(real)m->body_pos[3 * b], (real)m->body_pos[3 * b + 1], (real)m->body_pos[3 * b + 2]}, wb[3], arm[3], tq[3];
             mat3_vec(Rw[i], bp, wb);
             for (int k = 0; k < 3; k++) arm[k] = oPc[n][k] - (pw[i][k] + wb[k]);

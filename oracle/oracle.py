@@ -31,7 +31,7 @@ class _CModel(C.Structure):
                [("hf_nx", C.c_int), ("hf_ny", C.c_int), ("hf_scale", C.c_double), ("hf_ox", C.c_double),
                 ("hf_oy", C.c_double), ("kn", C.c_double), ("cn", C.c_double), ("vs", C.c_double),
                 ("gravity", C.c_double * 3), ("dt", C.c_double),
-                ("obj_on", C.c_int), ("obj_gravity_on", C.c_int), ("nbx", C.c_int), ("pad1", C.c_int),
+                ("obj_on", C.c_int), ("obj_gravity_on", C.c_int), ("nbx", C.c_int), ("obj_coupling", C.c_int),
                 ("obj_mass", C.c_double), ("obj_inertia", C.c_double * 3), ("obj_half", C.c_double * 3),
                 ("obj_kn", C.c_double), ("obj_cn", C.c_double), ("obj_mu", C.c_double),
                 ("box_link", C.c_void_p), ("box_body", C.c_void_p), ("box_pos", C.c_void_p), ("box_quat", C.c_void_p), ("box_half", C.c_void_p),
@@ -87,6 +87,7 @@ class OracleSim:
         cm.obj_on = 0
         if obj is not None:
             cm.obj_on, cm.obj_gravity_on = 1, int(obj.get("gravity_on", 1))
+            cm.obj_coupling = int(obj.get("coupling", 0))      # 0 = the engine's block-Jacobi; 1 = Gauss-Seidel experiment
             cm.obj_mass = float(obj["mass"])
             cm.obj_inertia = (C.c_double * 3)(*obj["inertia"]); cm.obj_half = (C.c_double * 3)(*obj["half"])
             kn, cn = object_contact_gains(cm.obj_mass)
