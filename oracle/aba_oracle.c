@@ -81,7 +81,9 @@ typedef struct {
     int obj_on, obj_gravity_on, nbx;
     int obj_coupling;   /* 0: block-Jacobi (what the CUDA engine does): both bodies implicit in their own acceleration.
                            1: Gauss-Seidel (EXPERIMENT): the articulation as in 0, then the object receives exactly
-                              the opposite of the forces applied to the links -> linear momentum is conserved */
+                              the opposite of the forces applied to the links -> linear momentum is conserved
+                           k >= 2: EXPERIMENT: (k-1) extra sweeps of the two block solves on the coupled implicit law
+                              F = F0 - h G (J a_link - Jo a_obj), both bodies implicit in both accelerations at convergence */
     double obj_mass, obj_inertia[3], obj_half[3], obj_kn, obj_cn, obj_mu;
     const int *box_link, *box_body;         /* nbx: link carrying the box, body it belongs to */
     const double *box_pos, *box_quat, *box_half;   /* nbx x 3,4,3 (link frame) */
@@ -343,6 +345,7 @@ static void substep(const OracleModel *m, real h, real *root, real *dof, const r
     /* ---- the free object: contacts with the articulation (block-Jacobi implicit: each body sees its own
      * acceleration implicitly, the other's velocity explicitly), with the ground, then its own 6x6 solve */
     static __thread real oF0[MAXCP + 64][3], oG[MAXCP + 64][9], oJ[MAXCP + 64][18]; static __thread int olink[MAXCP + 64], obody[MAXCP + 64]; static __thread real oPc[MAXCP + 64][3];
+    static __thread real IA0[MAXL][36], pA0[MAXL][6], qdd_[MAXL];
     int noc = 0;
     real Ao[36], bo[6], Ro[9];
     if (m->obj_on && obj) {
@@ -384,7 +387,7 @@ static void substep(const OracleModel *m, real h, real *root, real *dof, const r
                 real Jo_[18], rox_[9], GJo_[18]; skew(ro_, rox_);                                                                \
                 for (int a_ = 0; a_ < 3; a_++) for (int b_ = 0; b_ < 3; b_++) { Jo_[6 * a_ + b_] = -rox_[3 * a_ + b_]; Jo_[6 * a_ + 3 + b_] = (a_ == b_); } \
                 for (int a_ = 0; a_ < 3; a_++) for (int b_ = 0; b_ < 6; b_++) { real s_ = 0; for (int k = 0; k < 3; k++) s_ += Gw_[3 * a_ + k] * Jo_[6 * k + b_]; GJo_[6 * a_ + b_] = s_; } \
-                if (m->obj_coupling == 0) {                                                                                      \
+                if (m->obj_coupling != 1) {                                                                                      \
                 for (int a_ = 0; a_ < 6; a_++) for (int b_ = 0; b_ < 6; b_++) { real s_ = 0; for (int k = 0; k < 3; k++) s_ += Jo_[6 * k + a_] * GJo_[6 * k + b_]; Ao[6 * a_ + b_] += h * s_; } \
                 for (int a_ = 0; a_ < 6; a_++) { real s_ = 0; for (int k = 0; k < 3; k++) s_ += Jo_[6 * k + a_] * F0_[k]; bo[a_] -= s_; } \
                 }                                                                                                                \
@@ -442,6 +445,22 @@ static void substep(const OracleModel *m, real h, real *root, real *dof, const r
         }
     }
 
+    /* coupled-implicit experiment: repeat the two block solves, each seeing the other's latest acceleration */
+    const int sweeps = (m->obj_on && obj && m->obj_coupling >= 2) ? m->obj_coupling : 1;
+    real ao_prev[6] = {0, 0, 0, 0, 0, 0}, bo0[6];
+    if (m->obj_on && obj) memcpy(bo0, bo, sizeof(bo0));
+    if (sweeps > 1) { memcpy(IA0, IA, sizeof(real) * 36 * nl); memcpy(pA0, pA, sizeof(real) * 6 * nl); }
+    for (int sweep = 0; sweep < sweeps; sweep++) {
+    if (sweep > 0) {
+        memcpy(IA, IA0, sizeof(real) * 36 * nl); memcpy(pA, pA0, sizeof(real) * 6 * nl);
+        for (int n = 0; n < noc; n++) {        /* the link also feels + h G (Jo a_obj) */
+            real ro_[3] = {oPc[n][0] - obj[0], oPc[n][1] - obj[1], oPc[n][2] - obj[2]}, axr[3], Jao[3], cf_[3];
+            cross3(ao_prev, ro_, axr);
+            for (int k = 0; k < 3; k++) Jao[k] = ao_prev[3 + k] + axr[k];
+            for (int a_ = 0; a_ < 3; a_++) { real s_ = 0; for (int k = 0; k < 3; k++) s_ += oG[n][3 * a_ + k] * Jao[k]; cf_[a_] = h * s_; }
+            for (int a_ = 0; a_ < 6; a_++) { real s_ = 0; for (int k = 0; k < 3; k++) s_ += oJ[n][6 * k + a_] * cf_[k]; pA[olink[n]][a_] -= s_; }
+        }
+    }
     /* ---- pass 2: articulated inertias, leaf -> root */
     for (int i = nl - 1; i >= 1; i--) {
         int p = m->parent[i];
@@ -469,6 +488,24 @@ static void substep(const OracleModel *m, real h, real *root, real *dof, const r
         real Ua = 0; for (int k = 0; k < 6; k++) Ua += U[i][k] * a[i][k];
         real qdd = (u[i] - Ua) / Dd[i];
         for (int k = 0; k < 6; k++) a[i][k] += S[i][k] * qdd;
+        qdd_[i] = qdd;
+    }
+    if (sweeps > 1) {      /* the object, seeing the links' accelerations of this sweep: bo = bo0 + sum Jo^T h G (J a_link) */
+        real bo_[6], ro_[3], Ja[3], f_[3], tq_[3];
+        memcpy(bo_, bo0, sizeof(bo_));
+        for (int n = 0; n < noc; n++) {
+            for (int a_ = 0; a_ < 3; a_++) { real s_ = 0; for (int k = 0; k < 6; k++) s_ += oJ[n][6 * a_ + k] * a[olink[n]][k]; Ja[a_] = s_; }
+            for (int a_ = 0; a_ < 3; a_++) { real s_ = 0; for (int k = 0; k < 3; k++) s_ += oG[n][3 * a_ + k] * Ja[k]; f_[a_] = h * s_; }
+            for (int k = 0; k < 3; k++) ro_[k] = oPc[n][k] - obj[k];
+            cross3(ro_, f_, tq_);
+            for (int k = 0; k < 3; k++) { bo_[k] += tq_[k]; bo_[3 + k] += f_[k]; }
+        }
+        spd6_solve(Ao, bo_, ao_prev);
+        memcpy(bo, bo_, sizeof(bo_));
+    }
+    }   /* sweeps */
+    for (int i = 1; i < nl; i++) {
+        real qdd = qdd_[i];
         if (dof_force) dof_force[i - 1] = tau[i] - (diag[i] - (real)m->armature[i]) * qdd;
         dof[2 * (i - 1) + 1] += h * qdd;
         dof[2 * (i - 1)] += h * dof[2 * (i - 1) + 1];
