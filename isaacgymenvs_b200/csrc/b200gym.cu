@@ -11,15 +11,13 @@
 #include "../../include/b200gym.h"
 #include "b2g_device.cuh"
 #include "b2g_tasks.cuh"
+#include "b2g_common.cuh"
 
 using namespace b2g;
 
 // ============================================================================================
 // kernels
 // ============================================================================================
-struct Buffers {
-    void *p[B2G_T_COUNT];
-};
 
 // whole-struct copy (forward-kinematics kernel, which also reads the cold tables)
 __device__ __forceinline__ void load_model_full(DevModel *sm, const DevModel *__restrict__ gm) {
@@ -74,7 +72,6 @@ __device__ __forceinline__ Tiles prologue(DevModel *sm, uint64_t *mbar, const De
     return t;
 }
 
-extern __shared__ float4 b2g_dyn_smem[];
 
 template <int L, bool HF, int BLOCK, bool OBJ = false>
 __device__ __forceinline__ Stepper<L, HF, BLOCK, OBJ> make_stepper(const DevModel *sm, const int16_t *hf, int lane) {
@@ -90,31 +87,6 @@ __device__ __forceinline__ Stepper<L, HF, BLOCK, OBJ> make_stepper(const DevMode
     }
     st.lane = lane;
     return st;
-}
-
-__device__ __forceinline__ void load_root(const float *r, RootState &rs) {
-    rs.rp[0] = r[0]; rs.rp[1] = r[1]; rs.rp[2] = r[2];
-    rs.rq[0] = r[3]; rs.rq[1] = r[4]; rs.rq[2] = r[5]; rs.rq[3] = r[6];
-    rs.rv[0] = r[7]; rs.rv[1] = r[8]; rs.rv[2] = r[9];
-    rs.rw[0] = r[10]; rs.rw[1] = r[11]; rs.rw[2] = r[12];
-}
-__device__ __forceinline__ void load_obj(const float *r, ObjState &ob) {
-    ob.p[0] = r[0]; ob.p[1] = r[1]; ob.p[2] = r[2];
-    ob.q[0] = r[3]; ob.q[1] = r[4]; ob.q[2] = r[5]; ob.q[3] = r[6];
-    ob.v[0] = r[7]; ob.v[1] = r[8]; ob.v[2] = r[9];
-    ob.w[0] = r[10]; ob.w[1] = r[11]; ob.w[2] = r[12];
-}
-__device__ __forceinline__ void store_obj(float *r, const ObjState &ob) {
-    r[0] = ob.p[0]; r[1] = ob.p[1]; r[2] = ob.p[2];
-    r[3] = ob.q[0]; r[4] = ob.q[1]; r[5] = ob.q[2]; r[6] = ob.q[3];
-    r[7] = ob.v[0]; r[8] = ob.v[1]; r[9] = ob.v[2];
-    r[10] = ob.w[0]; r[11] = ob.w[1]; r[12] = ob.w[2];
-}
-__device__ __forceinline__ void store_root(float *r, const RootState &rs) {
-    r[0] = rs.rp[0]; r[1] = rs.rp[1]; r[2] = rs.rp[2];
-    r[3] = rs.rq[0]; r[4] = rs.rq[1]; r[5] = rs.rq[2]; r[6] = rs.rq[3];
-    r[7] = rs.rv[0]; r[8] = rs.rv[1]; r[9] = rs.rv[2];
-    r[10] = rs.rw[0]; r[11] = rs.rw[1]; r[12] = rs.rw[2];
 }
 
 template <class ST>
@@ -180,18 +152,6 @@ __global__ void __launch_bounds__(BLOCK) simulate_kernel(const DevModel *__restr
 #ifndef B2G_MINBLOCKS
 #define B2G_MINBLOCKS 4
 #endif
-struct TileArgs {
-    int on;          // whole tiles + bulk copies
-    int io_f4;       // float4 offset (per block) of the in/out tile region inside dynamic smem
-    int model_f4;    // float4 offset of the packed model
-    // b2g_task_step_host with PINNED host buffers: the kernel reads its action tile from, and writes its result tiles
-    // to, host memory directly (unified addressing, plain coalesced 16-byte loads / stores -- not TMA), so the step
-    // needs no separate copy launches.  Null = off.
-    const float *h_act;
-    float *h_obs, *h_rew;
-    long long *h_reset;
-    uint8_t *h_timeout;
-};
 
 template <int L, bool HF, bool HUM, int BLOCK, bool TILES, bool HOSTIO = false>
 __global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? B2G_MINBLOCKS : (BLOCK == 64 && !HUM ? 2 * B2G_MINBLOCKS : 1))) loco_step_kernel(
@@ -532,6 +492,8 @@ __global__ void __launch_bounds__(BLOCK) cartpole_step_kernel(const DevModel *__
 
 #include "b2g_anymal.cuh"
 #include "b2g_hand.cuh"
+#include "b2g_quad_kernels.cuh"
+#include "b2g_quad_host.h"
 
 // -------------------------------------------------------------------------------------------
 // gym.refresh_rigid_body_state_tensor(): forward kinematics, one thread per env, any topology
@@ -616,6 +578,12 @@ struct b2g_sim {
     float *d_actions_stage = nullptr;    // device staging for b2g_task_step_host
     struct { bool on = false; float *obs = nullptr, *rew = nullptr; long long *reset = nullptr; uint8_t *timeout = nullptr; } zero_copy;
     int64_t launches = 0;
+    // quad path (b2g_quad.cuh): chain length (2 Ant-like, 3 ANYmal-like) or 0 = generic Stepper; the packed constants
+    int quad_ns = 0;
+    int quad_block = 128;
+    float4 *d_qm = nullptr;
+    std::vector<const void *> smem_set;      // kernels whose dynamic shared-memory limit has been raised (once per sim)
+    bool no_zero_copy = false;
 };
 
 static thread_local std::string g_err;
@@ -898,6 +866,20 @@ extern "C" int b2g_create_ext(const b2g_model *m, const b2g_model_ext *ext, cons
     }
     CUDA_TRY(cudaMalloc(&s->dm, sizeof(DevModel)));
     CUDA_TRY(cudaMemcpy(s->dm, &h, sizeof(DevModel), cudaMemcpyHostToDevice));
+    {   // the specialised path of "four hinge chains on a free base" (Ant, ANYmal): b2g_quad.cuh
+        const char *nq = getenv("B2G_NO_QUAD"), *qb = getenv("B2G_QUAD_BLOCK"), *nz = getenv("B2G_NO_ZERO_COPY");
+        s->no_zero_copy = nz != nullptr;
+        if (qb && (atoi(qb) == 64 || atoi(qb) == 128)) s->quad_block = atoi(qb);
+        if (!(nq && nq[0] == '1') && !ext && !(force1 && force1[0] == '1') && !getenv("B2G_LANES") && !getenv("B2G_BLOCK")) {
+            std::vector<float> qm; int leg_link[12];
+            const int ns = quad_build(m, sp, qm, leg_link);
+            if (ns) {
+                CUDA_TRY(cudaMalloc(&s->d_qm, qm.size() * sizeof(float)));
+                CUDA_TRY(cudaMemcpy(s->d_qm, qm.data(), qm.size() * sizeof(float), cudaMemcpyHostToDevice));
+                s->quad_ns = ns;
+            }
+        }
+    }
     *out = s;
     return B2G_OK;
 }
@@ -908,6 +890,7 @@ extern "C" int b2g_destroy(b2g_sim *s) {
     if (s->dm) cudaFree(s->dm);
     if (s->d_hf) cudaFree(s->d_hf);
     if (s->d_actions_stage) cudaFree(s->d_actions_stage);
+    if (s->d_qm) cudaFree(s->d_qm);
     delete s;
     return B2G_OK;
 }
@@ -944,14 +927,19 @@ static int require(const b2g_sim *s, std::initializer_list<int> slots, const cha
     return B2G_OK;
 }
 
+// raise a kernel's dynamic shared-memory limit, once per (sim, kernel): the attribute call costs microseconds of host
+// time, comparable to a whole step when issued before every launch
 template <typename K>
-static int set_smem(K kernel, size_t bytes) {
-    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+static int set_smem(b2g_sim *s, K kernel, size_t bytes) {
+    const void *key = reinterpret_cast<const void *>(kernel);
+    for (const void *k : s->smem_set) if (k == key) return B2G_OK;
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 > (int)bytes ? 200 * 1024 : (int)bytes));
+    s->smem_set.push_back(key);
     return B2G_OK;
 }
 #define B2G_LAUNCH(KERNEL, ...)                                                                  \
     do {                                                                                          \
-        int rc_ = set_smem(KERNEL, s->dyn_smem); if (rc_) return rc_;                             \
+        int rc_ = set_smem(s, KERNEL, s->dyn_smem); if (rc_) return rc_;                          \
         KERNEL<<<grid, blk, s->dyn_smem, st>>>(__VA_ARGS__);                                      \
     } while (0)
 // dispatch on (lanes, height field, CTA size)
@@ -976,6 +964,24 @@ extern "C" int b2g_simulate(b2g_sim *s, void *stream) {
     int rc = require(s, {B2G_T_ROOT_STATE, B2G_T_DOF_STATE}, "b2g_simulate"); if (rc) return rc;
     CUDA_TRY(cudaSetDevice(s->device));
     cudaStream_t st = (cudaStream_t)stream;
+    if (s->quad_ns) {
+        constexpr int QB = 128;
+        const int N = s->num_envs, grid = (N * 4 + QB - 1) / QB;
+        const size_t dyn = ((size_t)quad_park_f4(s->quad_ns) * QB + quad_model_f4(s->quad_ns)) * sizeof(float4);
+#define QSIM(NS_, HF_)                                                                                              \
+        do {                                                                                                        \
+            int rc_ = set_smem(s, quad_simulate_kernel<NS_, HF_, QB>, dyn); if (rc_) return rc_;                    \
+            quad_simulate_kernel<NS_, HF_, QB><<<grid, QB, dyn, st>>>(s->d_qm, s->d_hf, s->buf, N, s->hm.substeps);                 \
+        } while (0)
+        if (s->quad_ns == 2 && !s->d_hf) QSIM(2, false);
+        else if (s->quad_ns == 2) QSIM(2, true);
+        else if (s->quad_ns == 3 && !s->d_hf) QSIM(3, false);
+        else QSIM(3, true);
+#undef QSIM
+        s->launches++;
+        CUDA_TRY(cudaGetLastError());
+        return B2G_OK;
+    }
     const int N = s->num_envs, blk = s->block, grid = (N * s->lanes + blk - 1) / blk;
     if (s->hm.obj_on) {
         if (s->lanes == 8 && blk == 128) B2G_LAUNCH((simulate_kernel<8, false, 128, true>), s->dm, s->d_hf, s->buf, N);
@@ -1132,10 +1138,10 @@ static int anymal_step(b2g_sim *s, const float *actions, void *stream) {
     if (s->buf_bytes[B2G_T_REDUCE_SCRATCH] < (REDUCE_PARTIALS + 16) * 4) return fail(B2G_E_INVALID, "REDUCE_SCRATCH too small");
     s->step_counter++;                                   // common_step_counter += 1 (:459) before the push test
     if (s->d_hf) {
-        rc = set_smem(anymal_physics_kernel<4, true, 128>, s->dyn_smem); if (rc) return rc;
+        rc = set_smem(s, anymal_physics_kernel<4, true, 128>, s->dyn_smem); if (rc) return rc;
         anymal_physics_kernel<4, true, 128><<<grid, blk, s->dyn_smem, st>>>(s->dm, s->d_hf, s->buf, P, actions, N, s->step_counter);
     } else {
-        rc = set_smem(anymal_physics_kernel<4, false, 128>, s->dyn_smem); if (rc) return rc;
+        rc = set_smem(s, anymal_physics_kernel<4, false, 128>, s->dyn_smem); if (rc) return rc;
         anymal_physics_kernel<4, false, 128><<<grid, blk, s->dyn_smem, st>>>(s->dm, s->d_hf, s->buf, P, actions, N, s->step_counter);
     }
     anymal_reset_obs_kernel<4, 128><<<grid, blk, 0, st>>>(s->buf, P, s->d_hf, N, s->hm.nl - 1, grid, s->step_counter);
@@ -1164,6 +1170,38 @@ extern "C" int b2g_task_step(b2g_sim *s, const float *actions, void *stream) {
     } else {
         rc = require(s, {B2G_T_POTENTIALS, B2G_T_PREV_POTENTIALS, B2G_T_INITIAL_ROOT}, "b2g_task_step"); if (rc) return rc;
         const bool hum = P.task == B2G_TASK_HUMANOID;
+        if (!hum && s->quad_ns == 2 && !s->d_hf) {           // Ant on the quad sub-step (whole tiles only)
+            const int qb = s->quad_block, epb = qb / 4, nd_ = 8, O = P.num_obs, ns6 = 6 * s->hm.nsens;
+            const bool clip_sep = s->buf.p[B2G_T_OBS_CLIPPED] && s->buf.p[B2G_T_OBS_CLIPPED] != s->buf.p[B2G_T_OBS];
+            const size_t park_bytes = (size_t)quad_park_f4(2) * qb * sizeof(float4);
+            const size_t io_bytes = ((size_t)epb * (13 + 3 * nd_ + ns6) * 4 + 15) & ~(size_t)15;
+            const size_t out_bytes = (size_t)epb * ((clip_sep ? 2 : 1) * O * 4 + 4 * 3 + 12 * 2 + 8 * 2 + 1);
+            const bool ok = (N % epb == 0) && ((epb * ns6 * 4) % 16 == 0) && ((epb * O * 4) % 16 == 0) && out_bytes <= park_bytes;
+            if (ok) {
+                const size_t dyn = park_bytes + io_bytes + (size_t)quad_model_f4(2) * sizeof(float4);
+                TileArgs ta; ta.on = 1; ta.io_f4 = (int)(park_bytes / 16); ta.model_f4 = (int)((park_bytes + io_bytes) / 16);
+                ta.h_act = nullptr; ta.h_obs = ta.h_rew = nullptr; ta.h_reset = nullptr; ta.h_timeout = nullptr;
+                if (s->zero_copy.on) { ta.h_act = actions; ta.h_obs = s->zero_copy.obs; ta.h_rew = s->zero_copy.rew; ta.h_reset = s->zero_copy.reset; ta.h_timeout = s->zero_copy.timeout; }
+                const int qgrid = (int)N / epb;
+#define QLOCO(BK, HIO)                                                                                                    \
+    do {                                                                                                                   \
+        int rc_ = set_smem(s, quad_loco_kernel<2, BK, HIO>, dyn); if (rc_) return rc_;                                     \
+        cudaLaunchConfig_t lc = {};                                                                                        \
+        lc.gridDim = dim3(qgrid); lc.blockDim = dim3(BK); lc.dynamicSmemBytes = dyn; lc.stream = st;                       \
+        cudaLaunchAttribute at[1];                                                                                         \
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                                     \
+        at[0].val.programmaticStreamSerializationAllowed = 1;                                                              \
+        lc.attrs = at; lc.numAttrs = 1;                                                                                    \
+        CUDA_TRY(cudaLaunchKernelEx(&lc, quad_loco_kernel<2, BK, HIO>, (const float4 *)s->d_qm, s->buf, P, actions, (int)N, (int)s->hm.substeps, ta)); \
+    } while (0)
+                if (qb == 128) { if (s->zero_copy.on) QLOCO(128, true); else QLOCO(128, false); }
+                else { if (s->zero_copy.on) QLOCO(64, true); else QLOCO(64, false); }
+#undef QLOCO
+                s->launches++;
+                CUDA_TRY(cudaGetLastError());
+                return B2G_OK;
+            }
+        }
         // tiles by bulk copy: whole blocks only, every tile a multiple of 16 bytes at a 16-byte-aligned address
         const int epb = blk / s->lanes, ndof = s->hm.nl - 1, O = P.num_obs, ns6 = 6 * s->hm.nsens;
         const bool clip_sep = s->buf.p[B2G_T_OBS_CLIPPED] && s->buf.p[B2G_T_OBS_CLIPPED] != s->buf.p[B2G_T_OBS];
@@ -1185,7 +1223,7 @@ extern "C" int b2g_task_step(b2g_sim *s, const float *actions, void *stream) {
 #define LOCO_T(LN, HM, BK, TL) do { if (TL && s->zero_copy.on) LOCO_K(LN, HM, BK, TL, TL); else LOCO_K(LN, HM, BK, TL, false); } while (0)
 #define LOCO_K(LN, HM, BK, TL, HIO)                                                                                       \
     do {                                                                                                                   \
-        int rc_ = set_smem(loco_step_kernel<LN, false, HM, BK, TL, HIO>, dyn); if (rc_) return rc_;                       \
+        int rc_ = set_smem(s, loco_step_kernel<LN, false, HM, BK, TL, HIO>, dyn); if (rc_) return rc_;                       \
         cudaLaunchConfig_t lc = {};                                                                                        \
         lc.gridDim = dim3(grid); lc.blockDim = dim3(blk); lc.dynamicSmemBytes = dyn; lc.stream = st;                       \
         cudaLaunchAttribute at[1];                                                                                         \
@@ -1227,7 +1265,7 @@ extern "C" int b2g_task_step_host(b2g_sim *s, const float *h_actions, float *h_o
     const int n_obs = s->has_anymal ? s->anymal.num_obs : (s->has_hand ? s->hand.num_obs : s->task.num_obs);
     const size_t N = s->num_envs, abytes = N * n_act * 4;
     // fast path (Ant / Humanoid tiled kernel, every host buffer pinned): no copy launches at all
-    if (s->has_task && s->task.task != B2G_TASK_CARTPOLE && !getenv("B2G_NO_ZERO_COPY")) {
+    if (s->has_task && s->task.task != B2G_TASK_CARTPOLE && !s->no_zero_copy) {
         auto pinned = [](const void *p) {
             if (!p) return true;
             cudaPointerAttributes a;

@@ -35,6 +35,8 @@
 #define B2G_FAST_TRIG 1
 #endif
 
+#define B2G_HD __host__ __device__ __forceinline__
+
 namespace b2g {
 
 constexpr int MAX_LINKS = 32;
@@ -158,32 +160,32 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 
 // ---------------------------------------------------------------------------------------------
 // small vector helpers (all fully inlined, arrays are register-resident after unrolling)
-__device__ __forceinline__ void cross(const float a[3], const float b[3], float o[3]) {
+B2G_HD void cross(const float a[3], const float b[3], float o[3]) {
     o[0] = a[1] * b[2] - a[2] * b[1];
     o[1] = a[2] * b[0] - a[0] * b[2];
     o[2] = a[0] * b[1] - a[1] * b[0];
 }
-__device__ __forceinline__ float dot3(const float a[3], const float b[3]) {
+B2G_HD float dot3(const float a[3], const float b[3]) {
     return a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
 }
-__device__ __forceinline__ void matvec(const float R[9], const float v[3], float o[3]) {
+B2G_HD void matvec(const float R[9], const float v[3], float o[3]) {
     o[0] = R[0] * v[0] + R[1] * v[1] + R[2] * v[2];
     o[1] = R[3] * v[0] + R[4] * v[1] + R[5] * v[2];
     o[2] = R[6] * v[0] + R[7] * v[1] + R[8] * v[2];
 }
-__device__ __forceinline__ void matTvec(const float R[9], const float v[3], float o[3]) {
+B2G_HD void matTvec(const float R[9], const float v[3], float o[3]) {
     o[0] = R[0] * v[0] + R[3] * v[1] + R[6] * v[2];
     o[1] = R[1] * v[0] + R[4] * v[1] + R[7] * v[2];
     o[2] = R[2] * v[0] + R[5] * v[1] + R[8] * v[2];
 }
-__device__ __forceinline__ void matmul(const float A[9], const float B[9], float C[9]) {
+B2G_HD void matmul(const float A[9], const float B[9], float C[9]) {
 #pragma unroll
     for (int i = 0; i < 3; i++)
 #pragma unroll
         for (int j = 0; j < 3; j++)
             C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
 }
-__device__ __forceinline__ void quat_to_mat(const float q[4], float R[9]) {
+B2G_HD void quat_to_mat(const float q[4], float R[9]) {
     float x = q[0], y = q[1], z = q[2], w = q[3];
     float inv = rsqrtf(x * x + y * y + z * z + w * w);
     x *= inv; y *= inv; z *= inv; w *= inv;
@@ -191,7 +193,7 @@ __device__ __forceinline__ void quat_to_mat(const float q[4], float R[9]) {
     R[3] = 2.f * (x * y + z * w); R[4] = 1.f - 2.f * (x * x + z * z); R[5] = 2.f * (y * z - x * w);
     R[6] = 2.f * (x * z - y * w); R[7] = 2.f * (y * z + x * w); R[8] = 1.f - 2.f * (x * x + y * y);
 }
-__device__ __forceinline__ void mat_to_quat(const float R[9], float q[4]) {
+B2G_HD void mat_to_quat(const float R[9], float q[4]) {
     float t = R[0] + R[4] + R[8], s;
     if (t > 0.f) { s = sqrtf(t + 1.f) * 2.f; q[3] = 0.25f * s; q[0] = (R[7] - R[5]) / s; q[1] = (R[2] - R[6]) / s; q[2] = (R[3] - R[1]) / s; }
     else if (R[0] > R[4] && R[0] > R[8]) { s = sqrtf(1.f + R[0] - R[4] - R[8]) * 2.f; q[3] = (R[7] - R[5]) / s; q[0] = 0.25f * s; q[1] = (R[1] + R[3]) / s; q[2] = (R[2] + R[6]) / s; }
@@ -199,8 +201,8 @@ __device__ __forceinline__ void mat_to_quat(const float R[9], float q[4]) {
     else { s = sqrtf(1.f + R[8] - R[0] - R[4]) * 2.f; q[3] = (R[3] - R[1]) / s; q[0] = (R[2] + R[6]) / s; q[1] = (R[5] + R[7]) / s; q[2] = 0.25f * s; }
     if (q[3] < 0.f) { q[0] = -q[0]; q[1] = -q[1]; q[2] = -q[2]; q[3] = -q[3]; }
 }
-__device__ __forceinline__ void b2g_sincos(float a, float *s, float *c) {
-#if B2G_FAST_TRIG
+B2G_HD void b2g_sincos(float a, float *s, float *c) {
+#if B2G_FAST_TRIG && defined(__CUDA_ARCH__)
     __sincosf(a, s, c);
 #else
     sincosf(a, s, c);
@@ -209,7 +211,7 @@ __device__ __forceinline__ void b2g_sincos(float a, float *s, float *c) {
 
 // packed symmetric 6x6:  IA[0..5] = A (xx yy zz xy xz yz), IA[6..14] = B row-major (ang x lin),
 // IA[15..20] = C (xx yy zz xy xz yz).   y = IA * (a ; l)
-__device__ __forceinline__ void sym6_mul(const float IA[21], const float a[3], const float l[3], float ya[3], float yl[3]) {
+B2G_HD void sym6_mul(const float IA[21], const float a[3], const float l[3], float ya[3], float yl[3]) {
     const float *A = IA, *B = IA + 6, *C = IA + 15;
     ya[0] = A[0] * a[0] + A[3] * a[1] + A[4] * a[2] + B[0] * l[0] + B[1] * l[1] + B[2] * l[2];
     ya[1] = A[3] * a[0] + A[1] * a[1] + A[5] * a[2] + B[3] * l[0] + B[4] * l[1] + B[5] * l[2];
@@ -219,7 +221,7 @@ __device__ __forceinline__ void sym6_mul(const float IA[21], const float a[3], c
     yl[2] = B[2] * a[0] + B[5] * a[1] + B[8] * a[2] + C[4] * l[0] + C[5] * l[1] + C[2] * l[2];
 }
 // IA += s * (ja; jl)(ja; jl)^T
-__device__ __forceinline__ void sym6_rank1(float IA[21], float s, const float ja[3], const float jl[3]) {
+B2G_HD void sym6_rank1(float IA[21], float s, const float ja[3], const float jl[3]) {
     float sa0 = s * ja[0], sa1 = s * ja[1], sa2 = s * ja[2];
     float sl0 = s * jl[0], sl1 = s * jl[1], sl2 = s * jl[2];
     IA[0] += sa0 * ja[0]; IA[1] += sa1 * ja[1]; IA[2] += sa2 * ja[2];
@@ -232,7 +234,7 @@ __device__ __forceinline__ void sym6_rank1(float IA[21], float s, const float ja
 }
 
 // solve the SPD system  IA * (xa; xl) = (ba; bl)  (root of a floating base) by Cholesky
-__device__ __forceinline__ void sym6_solve(const float IA[21], const float ba[3], const float bl[3], float xa[3], float xl[3]) {
+B2G_HD void sym6_solve(const float IA[21], const float ba[3], const float bl[3], float xa[3], float xl[3]) {
     float M[6][6];
     const float *A = IA, *B = IA + 6, *C = IA + 15;
     M[0][0] = A[0]; M[1][1] = A[1]; M[2][2] = A[2]; M[1][0] = A[3]; M[2][0] = A[4]; M[2][1] = A[5];
