@@ -263,6 +263,11 @@ int b2g_set_anymal_task(b2g_sim *sim, const b2g_anymal_params *task);
 int b2g_set_hand_task(b2g_sim *sim, const b2g_hand_params *task);
 int b2g_task_step(b2g_sim *sim, const float *actions, void *stream);
 
+/* VecTask.reset_done() (vec_task.py:440-455): run reset_idx (ant.py:252-279, humanoid.py:253-279, cartpole.py:144-157,
+ * shadow_hand.py:594-659, anymal_terrain.py:384-425) for every env whose RESET flag is set, now, and clear the flag the
+ * way the task's reset_idx does.  Observations are refreshed by the next step, as in the reference. */
+int b2g_reset_flagged(b2g_sim *sim, void *stream);
+
 /* Same step with HOST buffers (pinned or pageable): copies actions in, runs the step, copies
  * obs / rew / reset / timeout out and synchronises the stream: the call an rl_device="cpu" user
  * makes through VecTask.step (vec_task.py:402,408 `.to(rl_device)`). Any output may be NULL. */
@@ -277,6 +282,10 @@ int b2g_task_step_host(b2g_sim *sim, const float *h_actions, float *h_obs, float
 #define B2G_PLAN_MAX_SLOTS 24
 #define B2G_PLAN_MAX_LANES 8
 int b2g_plan(const b2g_model *model, int32_t lanes, int32_t compact, int32_t *slots_out, int32_t info_out[5]);
+
+/* Which formulation of the sub-step the sim runs: 0 = the generic slot-program stepper, 2 / 3 = the specialised
+ * "four hinge chains of this length on a free base" stepper (Ant / ANYmal class articulations).  Same physics. */
+int b2g_quad_chain_length(const b2g_sim *sim);
 
 /* number of kernels this library has launched since creation (bench.py "gpu_launches") */
 int64_t b2g_launch_count(const b2g_sim *sim);

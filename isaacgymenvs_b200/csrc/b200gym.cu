@@ -494,6 +494,7 @@ __global__ void __launch_bounds__(BLOCK) cartpole_step_kernel(const DevModel *__
 #include "b2g_hand.cuh"
 #include "b2g_quad_kernels.cuh"
 #include "b2g_quad_host.h"
+#include "b2g_reset.cuh"
 
 // -------------------------------------------------------------------------------------------
 // gym.refresh_rigid_body_state_tensor(): forward kinematics, one thread per env, any topology
@@ -593,6 +594,7 @@ static int fail(int code, const std::string &msg) { g_err = msg; return code; }
 extern "C" const char *b2g_last_error(void) { return g_err.c_str(); }
 extern "C" int b2g_version(void) { return B2G_VERSION; }
 extern "C" int64_t b2g_launch_count(const b2g_sim *sim) { return sim ? sim->launches : 0; }
+extern "C" int b2g_quad_chain_length(const b2g_sim *sim) { return sim ? sim->quad_ns : 0; }
 
 // Build the lanes' slot programs: list-schedule the links over `L` lanes, critical path first; a lane
 // keeps following a chain (parent at step s-1 in the same lane -> state travels in registers), any
@@ -1137,14 +1139,25 @@ static int anymal_step(b2g_sim *s, const float *actions, void *stream) {
     if (grid > REDUCE_PARTIALS) return fail(B2G_E_INVALID, "AnymalTerrain: too many blocks for the reduction scratch (num_envs <= 32768)");
     if (s->buf_bytes[B2G_T_REDUCE_SCRATCH] < (REDUCE_PARTIALS + 16) * 4) return fail(B2G_E_INVALID, "REDUCE_SCRATCH too small");
     s->step_counter++;                                   // common_step_counter += 1 (:459) before the push test
-    if (s->d_hf) {
+    if (s->quad_ns == 3) {                               // the specialised sub-step (b2g_quad.cuh), joint state in registers
+        const size_t dyn = ((size_t)quad_park_f4(3) * 128 + quad_model_f4(3)) * sizeof(float4);
+        if (s->d_hf) {
+            rc = set_smem(s, quad_anymal_physics_kernel<true, 128>, dyn); if (rc) return rc;
+            quad_anymal_physics_kernel<true, 128><<<grid, blk, dyn, st>>>(s->d_qm, s->d_hf, s->buf, P, actions, N, s->hm.substeps, s->step_counter);
+        } else {
+            rc = set_smem(s, quad_anymal_physics_kernel<false, 128>, dyn); if (rc) return rc;
+            quad_anymal_physics_kernel<false, 128><<<grid, blk, dyn, st>>>(s->d_qm, s->d_hf, s->buf, P, actions, N, s->hm.substeps, s->step_counter);
+        }
+    } else if (s->d_hf) {
         rc = set_smem(s, anymal_physics_kernel<4, true, 128>, s->dyn_smem); if (rc) return rc;
         anymal_physics_kernel<4, true, 128><<<grid, blk, s->dyn_smem, st>>>(s->dm, s->d_hf, s->buf, P, actions, N, s->step_counter);
     } else {
         rc = set_smem(s, anymal_physics_kernel<4, false, 128>, s->dyn_smem); if (rc) return rc;
         anymal_physics_kernel<4, false, 128><<<grid, blk, s->dyn_smem, st>>>(s->dm, s->d_hf, s->buf, P, actions, N, s->step_counter);
     }
-    anymal_reset_obs_kernel<4, 128><<<grid, blk, 0, st>>>(s->buf, P, s->d_hf, N, s->hm.nl - 1, grid, s->step_counter);
+    // kernel 2: one WARP per env -- the 140-point height gather (anymal_terrain.py:515-538) and the 188 observation
+    // stores dominate it; with 4 lanes per env the 4096-env workload was 512 warps on 592 schedulers
+    anymal_reset_obs_kernel<32, 128><<<(N * 32 + 127) / 128, 128, 0, st>>>(s->buf, P, s->d_hf, N, s->hm.nl - 1, grid, s->step_counter, 0);
     s->launches += 2;
     CUDA_TRY(cudaGetLastError());
     return B2G_OK;
@@ -1249,6 +1262,31 @@ extern "C" int b2g_task_step(b2g_sim *s, const float *actions, void *stream) {
 #undef LOCO
 #undef LOCO_T
 #undef LOCO_K
+    }
+    s->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return B2G_OK;
+}
+
+// VecTask.reset_done() (vec_task.py:440-455): reset_idx of every env whose reset_buf is set, right now (stream-ordered)
+extern "C" int b2g_reset_flagged(b2g_sim *s, void *stream) {
+    if (!s) return fail(B2G_E_INVALID, "b2g_reset_flagged: null sim");
+    if (!s->has_task && !s->has_anymal && !s->has_hand) return fail(B2G_E_INVALID, "b2g_reset_flagged: call b2g_set_task first");
+    CUDA_TRY(cudaSetDevice(s->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int N = s->num_envs, nd = s->hm.nl - 1;
+    int rc = require(s, {B2G_T_ROOT_STATE, B2G_T_DOF_STATE, B2G_T_RESET, B2G_T_PROGRESS, B2G_T_RESET_COUNT}, "b2g_reset_flagged"); if (rc) return rc;
+    if (s->has_anymal) {
+        rc = require(s, {B2G_T_COMMANDS, B2G_T_FEET_AIR_TIME, B2G_T_EPISODE_SUMS, B2G_T_REDUCE_SCRATCH}, "b2g_reset_flagged(AnymalTerrain)"); if (rc) return rc;
+        if (s->anymal.custom_origins) { rc = require(s, {B2G_T_ENV_ORIGINS, B2G_T_TERRAIN_LEVELS, B2G_T_TERRAIN_TYPES, B2G_T_TERRAIN_ORIGINS}, "b2g_reset_flagged(AnymalTerrain)"); if (rc) return rc; }
+        CUDA_TRY(cudaMemsetAsync((float *)s->buf.p[B2G_T_REDUCE_SCRATCH] + REDUCE_PARTIALS, 0, 16 * sizeof(float), st));
+        anymal_reset_obs_kernel<32, 128><<<(N * 32 + 127) / 128, 128, 0, st>>>(s->buf, s->anymal, s->d_hf, N, nd, 0, s->step_counter, 1);
+    } else if (s->has_hand) {
+        rc = require(s, {B2G_T_INITIAL_ROOT, B2G_T_GOAL_STATES, B2G_T_DOF_TARGET, B2G_T_PREV_TARGETS, B2G_T_SUCCESSES, B2G_T_RESET_GOAL}, "b2g_reset_flagged(ShadowHand)"); if (rc) return rc;
+        hand_reset_kernel<<<(N + 127) / 128, 128, 0, st>>>(s->buf, s->hand, N, nd);
+    } else {
+        if (s->task.task != B2G_TASK_CARTPOLE) { rc = require(s, {B2G_T_POTENTIALS, B2G_T_PREV_POTENTIALS, B2G_T_INITIAL_ROOT}, "b2g_reset_flagged"); if (rc) return rc; }
+        loco_reset_kernel<<<(N + 127) / 128, 128, 0, st>>>(s->buf, s->task, N, nd);
     }
     s->launches++;
     CUDA_TRY(cudaGetLastError());

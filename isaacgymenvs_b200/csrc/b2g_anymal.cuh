@@ -15,32 +15,6 @@
 
 namespace b2g {
 
-// uniform in [0,1) number `idx` of stream (env, step, tag)
-__device__ __forceinline__ float anymal_uniform(uint64_t seed, uint32_t env, uint32_t step, uint32_t tag, int idx) {
-    uint32_t r[4];
-    philox4x32_10((uint32_t)(idx >> 2), step, env, tag, (uint32_t)seed, (uint32_t)(seed >> 32), r);
-    return (float)(r[idx & 3] >> 8) * (1.0f / 16777216.0f);
-}
-__device__ __forceinline__ float t_rand_float(float lo, float hi, float u) { return (hi - lo) * u + lo; }   // torch_rand_float, torch_jit_utils.py:215-218
-
-// wrap_to_pi, anymal_terrain.py:683-687: the in-place `%=` is aten::fmod_ (keeps the dividend's sign)
-__device__ __forceinline__ float t_wrap_to_pi(float a) {
-    a = fmodf(a, 6.2831855f);
-    return a - 6.2831855f * ((a > 3.1415927f) ? 1.f : 0.f);
-}
-// quat_apply, torch_jit_utils.py:70-77
-__device__ __forceinline__ void t_quat_apply(const float q[4], const float b[3], float o[3]) {
-    float t[3], u[3];
-    cross(q, b, t);
-    t[0] *= 2.f; t[1] *= 2.f; t[2] *= 2.f;
-    cross(q, t, u);
-#pragma unroll
-    for (int c = 0; c < 3; c++) o[c] = b[c] + q[3] * t[c] + u[c];
-}
-
-enum { TAG_PUSH = 1, TAG_RESET = 2, TAG_NOISE = 3 };
-constexpr int REDUCE_PARTIALS = 1024;      // REDUCE_SCRATCH: [0,1024) block partials, then 16 floats of extras sums
-
 template <int L, bool HF, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) anymal_physics_kernel(const DevModel *__restrict__ gm, const int16_t *__restrict__ hf,
                                                                 Buffers B, const __grid_constant__ b2g_anymal_params P,
@@ -218,11 +192,18 @@ __global__ void __launch_bounds__(BLOCK) anymal_physics_kernel(const DevModel *_
 template <int L, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) anymal_reset_obs_kernel(Buffers B, const __grid_constant__ b2g_anymal_params P,
                                                                   const int16_t *__restrict__ hs, int N, int nd,
-                                                                  int nblocks1, unsigned step_counter) {
+                                                                  int nblocks1, unsigned step_counter, int reset_only) {
+    // reset_only (VecTask.reset_done, vec_task.py:440-455 -> reset_idx :384-425 of the flagged envs, no step): the norm
+    // over the reset set is summed here from the flags themselves; observations and last_* are left to the next step
     __shared__ float s_norm;
     if (threadIdx.x < 32) {
         const float *red = (const float *)B.p[B2G_T_REDUCE_SCRATCH];
         float t = 0.f;
+        if (reset_only) {
+            const long long *rb = (const long long *)B.p[B2G_T_RESET];
+            const float *cm = (const float *)B.p[B2G_T_COMMANDS];
+            for (int i = threadIdx.x; i < N; i += 32) t += (rb[i] != 0) ? cm[4 * i] * cm[4 * i] + cm[4 * i + 1] * cm[4 * i + 1] : 0.f;
+        } else
         for (int i = threadIdx.x; i < nblocks1; i += 32) t += red[i];
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
@@ -289,6 +270,7 @@ __global__ void __launch_bounds__(BLOCK) anymal_reset_obs_kernel(Buffers B, cons
         }
     }
     __syncwarp();
+    if (reset_only) return;
     // ---- compute_observations (:302-313) + noise (:481-482)
     float *obs = (float *)B.p[B2G_T_OBS] + (size_t)e * P.num_obs;
     float *obsc = (float *)B.p[B2G_T_OBS_CLIPPED];
@@ -337,7 +319,7 @@ __global__ void __launch_bounds__(BLOCK) anymal_reset_obs_kernel(Buffers B, cons
         const float rx = root[0], ry = root[1];
         // the two height samples of a point are independent global loads: fetch a chunk of points' samples together
         // (their latencies overlap), then emit the chunk's observations
-        constexpr int CH = 7;
+        constexpr int CH = PER < 7 ? PER : 7;
         const int p_end = min(140, (lane + 1) * PER);
 #pragma unroll 1
         for (int p0 = lane * PER; p0 < p_end; p0 += CH) {

@@ -5,6 +5,7 @@
 //   quad_loco_kernel       one whole VecTask.step() of Ant (vec_task.py:360-408 + ant.py:281-297), tiles by bulk copy
 #pragma once
 #include "b2g_quad.cuh"
+#include "b2g_tasks.cuh"
 
 namespace b2g {
 
@@ -277,6 +278,180 @@ __global__ void __launch_bounds__(BLOCK, B2G_QUAD_MINBLOCKS(BLOCK)) quad_loco_ke
         if (ta.h_rew) copy16(ta.h_rew + e0, t_rew, EPB * 4);
         if (ta.h_reset) copy16(ta.h_reset + e0, t_reset, EPB * 8);
         if (ta.h_timeout) copy16(ta.h_timeout + e0, t_to, EPB);
+    }
+}
+
+
+// -------------------------------------------------------------------------------------------
+// AnymalTerrain kernel 1 on the quad sub-step (same contract as anymal_physics_kernel, b2g_anymal.cuh): pre_physics_step
+// (PD torque + gym.simulate x decimation, anymal_terrain.py:441-451) + the control_freq_inv simulates of VecTask.step
+// (vec_task.py:379-382) + post_physics_step up to compute_reward (:453-475).  The joint state stays in registers across
+// the 5 sub-steps; the PD law reads it there.
+template <bool HF, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) quad_anymal_physics_kernel(const float4 *__restrict__ gqm, const int16_t *__restrict__ hf,
+                                                                    Buffers B, const __grid_constant__ b2g_anymal_params P,
+                                                                    const float *__restrict__ actions_in, int N, int substeps, unsigned step_counter) {
+    constexpr int NS = 3, nd = 12;
+    __shared__ float s_part[BLOCK / 32];
+    float4 *const park = b2g_dyn_smem;
+    float4 *const qm = b2g_dyn_smem + quad_park_f4(NS) * BLOCK;
+    for (int i = threadIdx.x; i < quad_model_f4(NS); i += BLOCK) qm[i] = gqm[i];
+    __syncthreads();
+    const int gt = blockIdx.x * BLOCK + threadIdx.x;
+    const int env = gt >> 2, lane = gt & 3;
+    const bool valid = env < N;
+    const int e = valid ? env : N - 1;
+    QLane<NS, HF> L = make_qlane<NS, HF>(qm, hf, park, BLOCK, lane);
+    const float *envmu = (const float *)B.p[B2G_T_ENV_FRICTION];
+    if (envmu) L.env_mu = 0.5f * (envmu[e] + qm[18].x);
+    RootState rs; load_root((const float *)B.p[B2G_T_ROOT_STATE] + 13 * (size_t)e, rs);
+    const float2 *dofs = (const float2 *)B.p[B2G_T_DOF_STATE] + (size_t)e * nd;
+    float *act_out = (float *)B.p[B2G_T_ACTIONS] + (size_t)e * nd;
+    float *torq = (float *)B.p[B2G_T_TORQUES] + (size_t)e * nd;
+    const float *last_a = (const float *)B.p[B2G_T_LAST_ACTIONS] + (size_t)e * nd;
+    const float *last_v = (const float *)B.p[B2G_T_LAST_DOF_VEL] + (size_t)e * nd;
+    int dofi[NS];
+    float a_cl[NS], tq[NS] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+        dofi[s] = q_f2i(L.LK(s, 16).w);
+        const float2 v = dofs[dofi[s]];
+        a_cl[s] = fminf(fmaxf(actions_in[(size_t)e * nd + dofi[s]], -P.clip_actions), P.clip_actions);
+        if (valid) act_out[dofi[s]] = a_cl[s];
+        L.q[s] = v.x; L.qd[s] = v.y; L.act[s] = 0.f;
+    }
+    QOutputs o;
+    o.write = valid; o.sensor = nullptr; o.dof_force = nullptr;
+    o.net_contact = (float *)B.p[B2G_T_NET_CONTACT] + (size_t)e * (q_f2i(qm[7].w) >> 8) * 3;
+    const int total = (P.decimation + P.control_freq_inv) * substeps;
+    const int pd_until = P.decimation * substeps;
+#pragma unroll 1
+    for (int k = 0; k < total; k++) {
+        if (k < pd_until && (k % substeps) == 0) {
+#pragma unroll
+            for (int s = 0; s < NS; s++) {
+                float t = P.kp * (P.action_scale * a_cl[s] + P.default_dof_pos[dofi[s]] - L.q[s]) - P.kd * L.qd[s];
+                t = fminf(fmaxf(t, -P.torque_limit), P.torque_limit);
+                L.act[s] = t; tq[s] = t;
+            }
+        }
+        L.substep(rs, k == total - 1, o);
+    }
+
+    // ---- post_physics_step (:453-475)
+    long long *progress_b = (long long *)B.p[B2G_T_PROGRESS];
+    long long *reset_b = (long long *)B.p[B2G_T_RESET];
+    const long long progress = progress_b[e] + 1;
+    const uint32_t gid = (uint32_t)(e + P.env_id_offset);
+    if (P.push_robots && P.push_interval > 0 && (step_counter % (unsigned)P.push_interval) == 0) {   // push_robots :437-439
+        rs.rv[0] = t_rand_float(-1.f, 1.f, anymal_uniform(P.seed, gid, step_counter, TAG_PUSH, 0));
+        rs.rv[1] = t_rand_float(-1.f, 1.f, anymal_uniform(P.seed, gid, step_counter, TAG_PUSH, 1));
+    }
+    float2 *dw = (float2 *)B.p[B2G_T_DOF_STATE] + (size_t)e * nd;
+    float s_torque = 0.f, s_jacc = 0.f, s_arate = 0.f, s_hip = 0.f;
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+        const int d = dofi[s];
+        if (valid) { dw[d] = make_float2(L.q[s], L.qd[s]); if (total > 0 && pd_until > 0) torq[d] = tq[s]; }
+        const float t = (total > 0 && pd_until > 0) ? tq[s] : torq[d], a = a_cl[s];
+        s_torque += t * t;
+        const float dv = last_v[d] - L.qd[s]; s_jacc += dv * dv;
+        const float da = last_a[d] - a; s_arate += da * da;
+        if (d % 3 == 0) s_hip += fabsf(L.q[s] - P.default_dof_pos[d]);          // dof_pos[:, [0,3,6,9]]
+    }
+    if (valid && lane == 0) store_root((float *)B.p[B2G_T_ROOT_STATE] + 13 * (size_t)e, rs);
+    s_torque = lane_sum<4>(s_torque); s_jacc = lane_sum<4>(s_jacc); s_arate = lane_sum<4>(s_arate); s_hip = lane_sum<4>(s_hip);
+
+    // contact-force terms: every lane looks at bodies base / knee[lane] / foot[lane]
+    const float *cf = o.net_contact;
+    float *fat_b = (float *)B.p[B2G_T_FEET_AIR_TIME] + (size_t)e * 4;
+    float n_knee = 0.f, n_stumble = 0.f, air = 0.f;
+    bool knee_hit = false;
+    __syncwarp();
+    {
+        const int k = lane;
+        const float *fk = cf + 3 * P.knee_bodies[k], *ff = cf + 3 * P.feet_bodies[k];
+        const bool kc = sqrtf(fk[0] * fk[0] + fk[1] * fk[1] + fk[2] * fk[2]) > 1.f;
+        knee_hit = kc;
+        n_knee += kc ? 1.f : 0.f;
+        n_stumble += ((sqrtf(ff[0] * ff[0] + ff[1] * ff[1]) > 5.f) && (fabsf(ff[2]) < 1.f)) ? 1.f : 0.f;
+        const bool contact = ff[2] > 1.f;
+        float fat = fat_b[k];
+        const bool first = (fat > 0.f) && contact;
+        fat += P.dt;
+        air += (fat - 0.5f) * (first ? 1.f : 0.f);
+        fat = contact ? 0.f : fat;
+        if (valid) fat_b[k] = fat;
+    }
+    n_knee = lane_sum<4>(n_knee); n_stumble = lane_sum<4>(n_stumble); air = lane_sum<4>(air);
+    const float any_knee = lane_sum<4>(knee_hit ? 1.f : 0.f);
+
+    // prepare quantities (:464-471)
+    float *cmd = (float *)B.p[B2G_T_COMMANDS] + (size_t)e * 4;
+    const float gvec[3] = {0.f, 0.f, -1.f}, fvec[3] = {1.f, 0.f, 0.f};
+    float blv[3], bav[3], pg[3], fwd[3];
+    t_quat_rotate(rs.rq, rs.rv, blv, -1.f);
+    t_quat_rotate(rs.rq, rs.rw, bav, -1.f);
+    t_quat_rotate(rs.rq, gvec, pg, -1.f);
+    t_quat_apply(rs.rq, fvec, fwd);
+    const float heading = atan2f(fwd[1], fwd[0]);
+    const float c0 = cmd[0], c1 = cmd[1], c3 = cmd[3];
+    const float c2 = fminf(fmaxf(0.5f * t_wrap_to_pi(c3 - heading), -1.f), 1.f);
+
+    // check_termination (:294-300)
+    const float *fb = cf + 3 * P.base_body;
+    bool reset = sqrtf(fb[0] * fb[0] + fb[1] * fb[1] + fb[2] * fb[2]) > 1.f;
+    if (!P.allow_knee_contacts) reset = reset || (any_knee > 0.f);
+    if (progress >= (long long)P.max_episode_length - 1) reset = true;
+
+    float part = 0.f;
+    if (lane == 0 && valid) {
+        // compute_reward (:315-382)
+        const float *R = P.rew_scales;
+        const float ex = c0 - blv[0], ey = c1 - blv[1];
+        const float lin_err = ex * ex + ey * ey;
+        const float ang_err = (c2 - bav[2]) * (c2 - bav[2]);
+        float t[13];
+        t[0] = expf(-lin_err / 0.25f) * R[1];                    // lin_vel_xy
+        t[1] = blv[2] * blv[2] * R[2];                           // lin_vel_z
+        t[2] = expf(-ang_err / 0.25f) * R[3];                    // ang_vel_z
+        t[3] = (bav[0] * bav[0] + bav[1] * bav[1]) * R[4];       // ang_vel_xy
+        t[4] = (pg[0] * pg[0] + pg[1] * pg[1]) * R[5];           // orient
+        t[5] = s_torque * R[6];                                  // torques
+        t[6] = s_jacc * R[7];                                    // joint_acc
+        t[7] = (rs.rp[2] - 0.52f) * (rs.rp[2] - 0.52f) * R[8];   // base_height
+        t[8] = air * R[9] * ((sqrtf(c0 * c0 + c1 * c1) > 0.1f) ? 1.f : 0.f);   // air_time
+        t[9] = n_knee * R[10];                                   // collision
+        t[10] = n_stumble * R[11];                               // stumble
+        t[11] = s_arate * R[12];                                 // action_rate
+        t[12] = s_hip * R[13];                                   // hip
+        float rew = t[0] + t[2] + t[1] + t[3] + t[4] + t[7] + t[5] + t[6] + t[9] + t[11] + t[8] + t[12] + t[10];
+        rew = fmaxf(rew, 0.f);
+        const uint8_t *to = (const uint8_t *)B.p[B2G_T_TIMEOUT];
+        rew += R[0] * (reset ? 1.f : 0.f) * ((to && to[e]) ? 0.f : 1.f);
+        ((float *)B.p[B2G_T_REW])[e] = rew;
+        float *es = (float *)B.p[B2G_T_EPISODE_SUMS];
+#pragma unroll
+        for (int k = 0; k < 13; k++) es[(size_t)k * N + e] += t[k];
+        reset_b[e] = reset ? 1 : 0;
+        progress_b[e] = progress;
+        cmd[2] = c2;
+        float *bs = (float *)B.p[B2G_T_BASE_SCRATCH] + (size_t)e * 12;
+        bs[0] = blv[0]; bs[1] = blv[1]; bs[2] = blv[2]; bs[3] = bav[0]; bs[4] = bav[1]; bs[5] = bav[2];
+        bs[6] = pg[0]; bs[7] = pg[1]; bs[8] = pg[2];
+        if (reset) part = c0 * c0 + c1 * c1;
+    }
+    // deterministic per-block partial of sum over the reset set of |commands_xy|^2
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tot = 0.f;
+        for (int w = 0; w < BLOCK / 32; w++) tot += s_part[w];
+        float *red = (float *)B.p[B2G_T_REDUCE_SCRATCH];
+        red[blockIdx.x] = tot;
+        if (blockIdx.x == 0) for (int k = 0; k < 16; k++) red[REDUCE_PARTIALS + k] = 0.f;
     }
 }
 

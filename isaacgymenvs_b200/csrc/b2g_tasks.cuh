@@ -138,4 +138,31 @@ __device__ __forceinline__ void cartpole_reward(float pole_angle, float pole_vel
     rew = reward;
 }
 
+// ------------------------------------------------------------------ AnymalTerrain helpers (tasks/anymal_terrain.py)
+// uniform in [0,1) number `idx` of stream (env, step, tag)
+__device__ __forceinline__ float anymal_uniform(uint64_t seed, uint32_t env, uint32_t step, uint32_t tag, int idx) {
+    uint32_t r[4];
+    philox4x32_10((uint32_t)(idx >> 2), step, env, tag, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    return (float)(r[idx & 3] >> 8) * (1.0f / 16777216.0f);
+}
+__device__ __forceinline__ float t_rand_float(float lo, float hi, float u) { return (hi - lo) * u + lo; }   // torch_rand_float, torch_jit_utils.py:215-218
+
+// wrap_to_pi, anymal_terrain.py:683-687: the in-place `%=` is aten::fmod_ (keeps the dividend's sign)
+__device__ __forceinline__ float t_wrap_to_pi(float a) {
+    a = fmodf(a, 6.2831855f);
+    return a - 6.2831855f * ((a > 3.1415927f) ? 1.f : 0.f);
+}
+// quat_apply, torch_jit_utils.py:70-77
+__device__ __forceinline__ void t_quat_apply(const float q[4], const float b[3], float o[3]) {
+    float t[3], u[3];
+    cross(q, b, t);
+    t[0] *= 2.f; t[1] *= 2.f; t[2] *= 2.f;
+    cross(q, t, u);
+#pragma unroll
+    for (int c = 0; c < 3; c++) o[c] = b[c] + q[3] * t[c] + u[c];
+}
+
+enum { TAG_PUSH = 1, TAG_RESET = 2, TAG_NOISE = 3 };
+constexpr int REDUCE_PARTIALS = 1024;      // REDUCE_SCRATCH: [0,1024) block partials, then 16 floats of extras sums
+
 }  // namespace b2g

@@ -154,17 +154,24 @@ def lib():
         _lib.b2g_launch_count.restype = C.c_int64
         _lib.b2g_launch_count.argtypes = [C.c_void_p]
         for fn in ("b2g_plan", "b2g_create", "b2g_create_ext", "b2g_destroy", "b2g_bind", "b2g_simulate", "b2g_refresh_rigid_body_state",
-                   "b2g_set_task", "b2g_set_anymal_task", "b2g_set_hand_task", "b2g_task_step", "b2g_task_step_host"):
+                   "b2g_set_task", "b2g_set_anymal_task", "b2g_set_hand_task", "b2g_task_step", "b2g_task_step_host", "b2g_reset_flagged"):
             getattr(_lib, fn).restype = C.c_int
     return _lib
 
 
 EXPORTS = ("b2g_plan", "b2g_create", "b2g_create_ext", "b2g_destroy", "b2g_bind", "b2g_simulate", "b2g_refresh_rigid_body_state", "b2g_set_task",
-           "b2g_set_anymal_task", "b2g_set_hand_task", "b2g_task_step", "b2g_task_step_host", "b2g_launch_count", "b2g_last_error", "b2g_version")
+           "b2g_set_anymal_task", "b2g_set_hand_task", "b2g_task_step", "b2g_task_step_host", "b2g_launch_count", "b2g_last_error", "b2g_version",
+           "b2g_quad_chain_length", "b2g_reset_flagged")
 
 
 class EngineError(RuntimeError):
     pass
+
+
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+if _raw_stream is None:                                     # older torch: the public (slower) accessor
+    def _raw_stream(index):
+        return torch.cuda.current_stream(index).cuda_stream
 
 
 def _check(rc, what):
@@ -237,6 +244,9 @@ class Sim:
             _check(lib().b2g_create(C.byref(cm), C.byref(sp), C.c_int32(self.num_envs), C.c_int32(idx), C.byref(self._h)),
                    "b2g_create")
         self.tensors = {}
+        self._dev_index = idx
+        self._step_fn = lib().b2g_task_step
+        self._step_fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         N = self.num_envs
         z = lambda *s, dtype=torch.float32: torch.zeros(*s, dtype=dtype, device=self.device)
         self.root_state = self._bind(T_ROOT_STATE, z(N * self.actors_per_env, 13))
@@ -289,8 +299,13 @@ class Sim:
             _check(lib().b2g_set_task(self._h, C.byref(params)), "b2g_set_task")
 
     def task_step(self, actions: torch.Tensor):
-        assert actions.is_contiguous() and actions.dtype == torch.float32 and actions.device == self.device
-        _check(lib().b2g_task_step(self._h, C.c_void_p(actions.data_ptr()), self._stream()), "b2g_task_step")
+        """b2g_task_step on the current torch stream; the hot call of VecTask.step (argument conversion pre-bound, raw
+        stream handle: a few microseconds of host time per step matter next to a ~10 us kernel)."""
+        if actions.dtype is not torch.float32 or not actions.is_cuda or not actions.is_contiguous():
+            raise EngineError("task_step: actions must be a contiguous float32 CUDA tensor")
+        rc = self._step_fn(self._h, actions.data_ptr(), _raw_stream(self._dev_index))
+        if rc != 0:
+            _check(rc, "b2g_task_step")
 
     def task_step_host(self, h_actions, h_obs=None, h_rew=None, h_reset=None, h_timeout=None):
         """Host-buffer step (CPU torch tensors, ideally pinned); synchronises."""
@@ -298,8 +313,17 @@ class Sim:
         _check(lib().b2g_task_step_host(self._h, p(h_actions), p(h_obs), p(h_rew), p(h_reset), p(h_timeout),
                                         self._stream()), "b2g_task_step_host")
 
+    def reset_flagged(self):
+        """reset_idx of every env whose reset flag is set (VecTask.reset_done)."""
+        _check(lib().b2g_reset_flagged(self._h, self._stream()), "b2g_reset_flagged")
+
     def launch_count(self):
         return int(lib().b2g_launch_count(self._h))
+
+    def quad_ns(self):
+        """0: generic stepper; 2 / 3: the specialised four-chain stepper (b2g_quad.cuh) with this chain length."""
+        lib().b2g_quad_chain_length.argtypes = [C.c_void_p]
+        return int(lib().b2g_quad_chain_length(self._h))
 
     def close(self):
         if self._h:

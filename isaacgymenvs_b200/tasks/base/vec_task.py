@@ -157,9 +157,9 @@ class VecTask(Env):
         self.sim_initialized = False
         self.create_sim()
         self.sim_initialized = True
+        self.obs_dict = {}
         self.allocate_buffers()
         self._bind_task()
-        self.obs_dict = {}
 
     # ---- vec_task.py:301-324
     def allocate_buffers(self):
@@ -214,6 +214,14 @@ class VecTask(Env):
         p.seed = self.seed
         p.env_id_offset = self.env_id_offset
         self.sim.set_task(p, bufs)
+        # what step() hands back when nothing has to be converted (rl_device == sim device, no observation noise, no
+        # asymmetric states): the same tensor objects every step, as the reference returns its own buffers
+        # (vec_task.py:402-408 -- `.to(rl_device)` of a tensor already there is the tensor itself)
+        self._same_device = torch.device(self.rl_device) == torch.device(self.device)
+        self._torch_device = torch.device(self.device)
+        self.extras["time_outs"] = self.timeout_buf
+        self.obs_dict["obs"] = self.obs_clipped
+        self._step_ret = (self.obs_dict, self.rew_buf, self.reset_buf, self.extras)
 
     def get_state(self):
         return torch.clamp(self.states_buf, -self.clip_obs, self.clip_obs).to(self.rl_device)
@@ -226,12 +234,16 @@ class VecTask(Env):
                     self.dr_randomizations[key] = {"noise_lambda": model}
         if self.dr_randomizations.get('actions', None):
             actions = self.dr_randomizations['actions']['noise_lambda'](actions)
-        a = actions.to(device=self.device, dtype=torch.float32)
-        if a.dim() == 1:
-            a = a.view(self.num_envs, -1)
-        self.sim.task_step(a.contiguous())      # clamp + pre_physics + simulate + post_physics + timeout + clip
+        a = actions
+        if a.dtype is not torch.float32 or a.device != self._torch_device or not a.is_contiguous():
+            a = a.to(device=self.device, dtype=torch.float32).contiguous()
+        self.sim.task_step(a)                   # clamp + pre_physics + simulate + post_physics + timeout + clip
         self.control_steps += 1
         self._fill_extras()
+        if self._same_device and self.num_states == 0 and not self.dr_randomizations.get('observations', None):
+            self.extras["time_outs"] = self.timeout_buf      # the buffers themselves: `.to()` of a tensor already there
+            self.obs_dict["obs"] = self.obs_clipped
+            return self._step_ret
         self.extras["time_outs"] = self.timeout_buf.to(self.rl_device)
         if self.dr_randomizations.get('observations', None):
             # vec_task.py:397-402: noise on the observation, then the clamp.  The engine keeps writing the tensor it is
@@ -246,7 +258,10 @@ class VecTask(Env):
 
     def step_host(self, h_actions, h_obs, h_rew, h_reset, h_timeout=None):
         """rl_device='cpu' fast path: the same step with host (pinned) buffers through
-        b2g_task_step_host -- H2D actions, fused step, D2H obs/rew/reset, stream sync."""
+        b2g_task_step_host -- H2D actions, fused step, D2H obs/rew/reset, stream sync.  It runs none of step()'s
+        randomisation hooks, so it refuses to run with them configured rather than silently skipping the noise."""
+        if self.randomizer is not None or self.dr_randomizations:
+            raise engine.EngineError("step_host: domain randomisation is configured; use step() (the noise lambdas run on device tensors)")
         self.sim.task_step_host(h_actions, h_obs, h_rew, h_reset, h_timeout)
         self.control_steps += 1
 
@@ -269,8 +284,11 @@ class VecTask(Env):
         return self.obs_dict
 
     def reset_done(self):
-        """vec_task.py:440-455.  Flagged envs are re-initialised inside the next fused step."""
+        """vec_task.py:440-455: reset_idx(nonzero(reset_buf)) right at the call (one small launch, b2g_reset_flagged),
+        then the clamped observation buffer -- the reference's order of events."""
         done_env_ids = self.reset_buf.nonzero(as_tuple=False).flatten()
+        if len(done_env_ids) > 0:
+            self.sim.reset_flagged()
         self.obs_dict["obs"] = torch.clamp(self.obs_buf, -self.clip_obs, self.clip_obs).to(self.rl_device)
         if self.num_states > 0:
             self.obs_dict["states"] = self.get_state()

@@ -148,7 +148,8 @@ class _Locomotion(VecTask):
         return p
 
     def _fill_extras(self):
-        self.extras['true_objective'] = self.root_states[:, 7]   # ant.py:245-250
+        if 'true_objective' not in self.extras:                  # ant.py:245-250; a view of the bound root tensor: set once
+            self.extras['true_objective'] = self.root_states[:, 7]
 
 
 class Ant(_Locomotion):

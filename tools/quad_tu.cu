@@ -7,3 +7,4 @@
 template __global__ void b2g::quad_loco_kernel<2, 128, false>(const float4 *, Buffers, const __grid_constant__ b2g_task_params, const float *, int, int, TileArgs);
 template __global__ void b2g::quad_loco_kernel<2, 64, false>(const float4 *, Buffers, const __grid_constant__ b2g_task_params, const float *, int, int, TileArgs);
 template __global__ void b2g::quad_simulate_kernel<2, false, 128>(const float4 *, const int16_t *, Buffers, int, int);
+template __global__ void b2g::quad_anymal_physics_kernel<true, 128>(const float4 *, const int16_t *, Buffers, const __grid_constant__ b2g_anymal_params, const float *, int, int, unsigned);
