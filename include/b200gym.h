@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define B2G_VERSION 1
+#define B2G_VERSION 2
 #define B2G_MAX_LINKS 32
 #define B2G_MAX_CONTACT_POINTS 96
 #define B2G_MAX_BOXES 4
@@ -59,6 +59,10 @@ typedef struct {
     const float *cp_pos, *cp_radius, *cp_mu;   /* ncp x 3, 1, 1 (mu = the shape's own friction) */
     const float *body_pos, *body_quat;         /* nb x 3, 4: body frame in its link frame */
     float contact_kn, contact_cn, contact_vs;
+    /* gymapi.AssetOptions.angular_damping / linear_damping / max_angular_velocity (humanoid.py:153-154,
+     * anymal_terrain.py:225-226): damping acceleration -d v on every link's COM twist; clamp of the base's angular speed
+     * (0 = no clamp) */
+    float angular_damping, linear_damping, max_angular_velocity;
 } b2g_model;
 
 /* Optional extras of an environment with more than one actor (tasks/shadow_hand.py:338-383: hand, object, goal
@@ -82,6 +86,7 @@ typedef struct {
     int32_t ten_dof[B2G_MAX_TENDONS][2];
     float ten_coef[B2G_MAX_TENDONS][2], ten_range[B2G_MAX_TENDONS][2];
     float ten_k, ten_d;
+    float obj_angular_damping, obj_linear_damping;   /* the object's own AssetOptions (defaults 0.5 / 0, shadow_hand.py:279-282) */
 } b2g_model_ext;
 
 /* gymapi.SimParams subset that changes the physics (tasks/base/vec_task.py:514-562) */

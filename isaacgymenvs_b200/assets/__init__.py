@@ -26,6 +26,31 @@ def load_compiled(name) -> Model:
         return Model.from_json(f.read())
 
 
+# options that only set scalars on the compiled model: applied to the blob.  Every other option changes the compiled
+# structure (link / body / contact-sphere tables, inertias): a blob compiled with a different value is the wrong model.
+_SCALAR_OPTS = ("angular_damping", "linear_damping", "max_angular_velocity", "disable_gravity", "default_dof_drive_mode", "armature")
+
+
+def _apply_options(model: Model, opts: BuildOptions, path):
+    if opts is None:
+        return model
+    have = model.build_options or {}
+    want = {k: (float(v) if isinstance(v, float) else int(v) if isinstance(v, (bool, int)) else v) for k, v in opts.__dict__.items()}
+    bad = {k: (have.get(k), v) for k, v in want.items() if k not in _SCALAR_OPTS and k in have and have[k] != v}
+    if bad:
+        raise ValueError(f"{path}: the XML is not available here and the committed model was compiled with different "
+                         f"structural options {bad} (compiled, requested); recompile with isaacgymenvs_b200.assets.compile_assets")
+    import numpy as np
+    model.angular_damping, model.linear_damping = float(opts.angular_damping), float(opts.linear_damping)
+    model.max_angular_velocity = float(opts.max_angular_velocity)
+    model.gravity_on = not opts.disable_gravity
+    if "armature" in have and have["armature"] != want["armature"]:
+        model.armature = model.armature + np.where(model.jtype >= 0, want["armature"] - have["armature"], 0.0)
+    if "default_dof_drive_mode" in have and have["default_dof_drive_mode"] != want["default_dof_drive_mode"]:
+        model.drive_mode = np.full(model.nl, want["default_dof_drive_mode"], dtype=np.int32)
+    return model
+
+
 def load_asset_file(asset_root, asset_file, opts: BuildOptions = None) -> Model:
     """gym.load_asset(): parse from the XML when it exists, else fall back to the committed blob
     compiled from the same file with the options the reference task passes."""
@@ -39,5 +64,5 @@ def load_asset_file(asset_root, asset_file, opts: BuildOptions = None) -> Model:
     norm = os.path.normpath(path).replace("\\", "/")
     for key, blob in KNOWN.items():
         if norm.endswith(key):
-            return load_compiled(blob)
+            return _apply_options(load_compiled(blob), opts, path)
     raise FileNotFoundError(f"asset {path} not found and no compiled model is registered for it")

@@ -10,8 +10,8 @@ from ..importer.urdf import load_urdf
 
 SPECS = {
     "ant": ("mjcf/nv_ant.xml", BuildOptions()),
-    "humanoid": ("mjcf/nv_humanoid.xml", BuildOptions(angular_damping=0.01)),
-    "cartpole": ("urdf/cartpole.urdf", BuildOptions(fix_base_link=True)),
+    "humanoid": ("mjcf/nv_humanoid.xml", BuildOptions(angular_damping=0.01, max_angular_velocity=100.0)),
+    "cartpole": ("urdf/cartpole.urdf", BuildOptions(fix_base_link=True, angular_damping=0.5)),
     "shadow_hand": ("mjcf/open_ai_assets/hand/shadow_hand.xml",
                     BuildOptions(fix_base_link=True, collapse_fixed_joints=True, disable_gravity=True, angular_damping=0.01,
                                  capsule_mid_spheres=1)),

@@ -194,7 +194,8 @@ class Gym:
                 if len(xm.geom_type) != 1 or int(xm.geom_type[0]) != 2:
                     raise NotImplementedError("the free object must be a single box primitive")
                 obj = dict(mass=float(xm.mass[0]), inertia=[float(xm.inertia[0][c]) for c in range(3)],
-                           half=[float(v) for v in np.asarray(xm.geom_size)[0][:3]], mu=float(xa.shape_props[0].friction), gravity_on=1)
+                           half=[float(v) for v in np.asarray(xm.geom_size)[0][:3]], mu=float(xa.shape_props[0].friction), gravity_on=1,
+                           angular_damping=float(xa.options.angular_damping), linear_damping=float(xa.options.linear_damping))
                 obj_row = 1
             tend = [dict(t) for t, tp in zip(model.tendons or [], a.tendon_props) if tp.limit_stiffness > 0.0]
             ks = {(tp.limit_stiffness, tp.damping) for tp in a.tendon_props if tp.limit_stiffness > 0.0}
@@ -235,6 +236,7 @@ class Gym:
         opts = BuildOptions(fix_base_link=o.fix_base_link, collapse_fixed_joints=o.collapse_fixed_joints,
                             replace_cylinder_with_capsule=o.replace_cylinder_with_capsule, armature=o.armature,
                             density=o.density, angular_damping=o.angular_damping, linear_damping=o.linear_damping,
+                            max_angular_velocity=o.max_angular_velocity,
                             disable_gravity=o.disable_gravity, default_dof_drive_mode=o.default_dof_drive_mode,
                             # fixed-base arms meet objects, not just the ground: one more sphere per capsule
                             capsule_mid_spheres=1 if o.fix_base_link else 0)

@@ -102,6 +102,8 @@ struct alignas(16) DevModel {
     int root_acc;         // accumulator index collecting this lane's root children other than slot 0's (-1: none)
     int cross_lane;       // some slot's parent lives in another lane (needs the shared-memory handoff + __syncwarp)
     float ground_mu;      // friction of the ground material (combined per contact as the average, PhysX default)
+    float ang_damp, lin_damp, max_angvel;   // AssetOptions.angular_damping / linear_damping / max_angular_velocity (0: no clamp)
+    float obj_ang_damp, obj_lin_damp;       // the free object's own
     // ---- optional second actor per env: a free box (ShadowHand's cube, shadow_hand.py:372-378) + fixed tendons
     int obj_on, obj_gravity_on, nbox, nten;
     float reach;          // no contact sphere can be farther than this from the root origin (ground test short-cut)
@@ -796,7 +798,7 @@ struct Stepper {
             Icw[5] = i0 * Ro[3] * Ro[6] + i1 * Ro[4] * Ro[7] + i2 * Ro[5] * Ro[8];
             const float go[3] = {m->obj_g[0], m->obj_g[1], m->obj_g[2]};
             float I[21], qa[3], ql[3];
-            spatial_inertia(m->obj_mass, 1.f, Icw, P.c, P.w, P.vO, go, I, qa, ql);
+            spatial_inertia(m->obj_mass, 1.f, Icw, P.c, P.w, P.vO, go, I, qa, ql, m->obj_ang_damp, m->obj_lin_damp);
 #pragma unroll
             for (int c = 0; c < 21; c++) Io[c] += I[c];
 #pragma unroll
@@ -873,7 +875,7 @@ struct Stepper {
                     load_pose(s, R, x, vw, vl);
                     load_axis(s, w, sl);
                     float I[21], qa[3], ql[3];
-                    link_inertia(lk, lk.mass, 1.f, R, x, vw, vl, g, I, qa, ql);
+                    link_inertia(lk, lk.mass, 1.f, R, x, vw, vl, g, I, qa, ql, m->ang_damp, m->lin_damp);
                     float dummy[3];
                     if (ground) link_contacts<true, HF>(m, gr, lk, rs.rp, R, x, vw, vl, I, qa, ql, dummy, dummy, dummy, dummy, 0, 1);
                     if (OBJ) obj_link_contacts<true>(lk, sr.link, R, x, vw, vl, I, qa, ql, dummy, dummy, dummy, dummy, 0, 1);
@@ -960,7 +962,7 @@ struct Stepper {
             float I[21], qa[3], ql[3], dummy[3], Rr[9], vwr[3], vlr[3];
             const float xr[3] = {0.f, 0.f, 0.f};
             root_pose(rs, Rr, vwr, vlr);
-            link_inertia(lk, mine ? lk.mass : 0.f, mine ? 1.f : 0.f, Rr, xr, vwr, vlr, g, I, qa, ql);
+            link_inertia(lk, mine ? lk.mass : 0.f, mine ? 1.f : 0.f, Rr, xr, vwr, vlr, g, I, qa, ql, m->ang_damp, m->lin_damp);
             if (ground) link_contacts<true, HF>(m, gr, lk, rs.rp, Rr, xr, vwr, vlr, I, qa, ql, dummy, dummy, dummy, dummy, lane, L);
             if (OBJ) obj_link_contacts<true>(lk, 0, Rr, xr, vwr, vlr, I, qa, ql, dummy, dummy, dummy, dummy, lane, L);
 #pragma unroll
@@ -1065,6 +1067,10 @@ struct Stepper {
             for (int c = 0; c < 3; c++) { rs.rw[c] += h * awr[c]; rs.rv[c] += h * (alr[c] + wxv[c]); }
 #pragma unroll
             for (int c = 0; c < 3; c++) rs.rp[c] += h * rs.rv[c];
+            if (m->max_angvel > 0.f) {                                 // AssetOptions.max_angular_velocity
+                const float wn2 = dot3(rs.rw, rs.rw);
+                if (wn2 > m->max_angvel * m->max_angvel) { const float k = m->max_angvel * rsqrtf(wn2); rs.rw[0] *= k; rs.rw[1] *= k; rs.rw[2] *= k; }
+            }
             integrate_quat(rs.rq, rs.rw, h);
         }
     }
@@ -1073,7 +1079,7 @@ struct Stepper {
     // p = v x* (I v) - gravity wrench
     __device__ __forceinline__ static void link_inertia(const LinkC &lk, float mass, float sc, const float R[9], const float x[3],
                                                          const float vw[3], const float vl[3], const float g[3],
-                                                         float I[21], float pa[3], float pl[3]) {
+                                                         float I[21], float pa[3], float pl[3], float da = 0.f, float dl = 0.f) {
         const float cl_[3] = {lk.com[0], lk.com[1], lk.com[2]};
         float cw_[3]; matvec(R, cl_, cw_);
 #pragma unroll
@@ -1088,12 +1094,14 @@ struct Stepper {
         Icw[3] = T_[0] * R[3] + T_[1] * R[4] + T_[2] * R[5];
         Icw[4] = T_[0] * R[6] + T_[1] * R[7] + T_[2] * R[8];
         Icw[5] = T_[3] * R[6] + T_[4] * R[7] + T_[5] * R[8];
-        spatial_inertia(mass, sc, Icw, cw_, vw, vl, g, I, pa, pl);
+        spatial_inertia(mass, sc, Icw, cw_, vw, vl, g, I, pa, pl, da, dl);
     }
     // same from the rotational inertia about the COM in world axes (Icw) and the COM position about O (cw_)
+    // da / dl: damping accelerations of the COM twist (AssetOptions.angular_damping / linear_damping): wrench
+    // (-da Icw w ; -dl m v_c) at the COM, explicit
     __device__ __forceinline__ static void spatial_inertia(float mass, float sc, const float Icw[6], const float cw_[3],
                                                            const float vw[3], const float vl[3], const float g[3],
-                                                           float I[21], float pa[3], float pl[3]) {
+                                                           float I[21], float pa[3], float pl[3], float da = 0.f, float dl = 0.f) {
         const float hm[3] = {mass * cw_[0], mass * cw_[1], mass * cw_[2]};
         const float c2 = dot3(cw_, cw_);
         I[0] = sc * Icw[0] + mass * (c2 - cw_[0] * cw_[0]);
@@ -1112,6 +1120,15 @@ struct Stepper {
         cross(vw, na, t1); cross(vl, nf, t2); cross(vw, nf, t3); cross(hm, g, hxg);
 #pragma unroll
         for (int c = 0; c < 3; c++) { pa[c] = t1[c] + t2[c] - hxg[c]; pl[c] = t3[c] - mass * g[c]; }
+        if (da != 0.f || dl != 0.f) {
+            float vxc[3]; cross(vw, cw_, vxc);
+            const float f[3] = {dl * mass * (vl[0] + vxc[0]), dl * mass * (vl[1] + vxc[1]), dl * mass * (vl[2] + vxc[2])};   // minus the damping force
+            const float hc[3] = {sc * (Icw[0] * vw[0] + Icw[3] * vw[1] + Icw[4] * vw[2]), sc * (Icw[3] * vw[0] + Icw[1] * vw[1] + Icw[5] * vw[2]),
+                                 sc * (Icw[4] * vw[0] + Icw[5] * vw[1] + Icw[2] * vw[2])};
+            float cxf[3]; cross(cw_, f, cxf);
+#pragma unroll
+            for (int c = 0; c < 3; c++) { pa[c] += da * hc[c] + cxf[c]; pl[c] += f[c]; }
+        }
     }
 
     // contact wrench of a link (world axes, torque about the link origin) -> force sensor (body

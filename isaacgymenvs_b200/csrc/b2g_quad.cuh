@@ -28,7 +28,7 @@ namespace b2g {
 //  H0: h g0 g1 g2            H1: kn cn vs2 gn(=cn+h*kn)      H2: hf_inv_scale hf_vscale hf_ox hf_oy
 //  H3: (int) hf_nx hf_ny ncp_root root_sensor                H4: root com xyz, mass
 //  H5: root Ab xx yy zz xy   H6: Ab xz yz, (int) root_body, (int) substeps  (Ab: rotational inertia about the ROOT ORIGIN, root axes)
-//  H7: root sensor body origin xyz (link frame), (int) nsens | nb << 8           H8..15: root spheres (pos, radius)   H16,17: their friction (combined)  H18: ground_mu - - -
+//  H7: root sensor body origin xyz (link frame), (int) nsens | nb << 8           H8..15: root spheres (pos, radius)   H16,17: their friction (combined)  H18: ground_mu ang_damp lin_damp max_angvel
 // link block k: 0..6 M0 M1 M2 axp[0] | 7: axp[1] axp[2] lpos[0] lpos[1] | 8: lpos[2] com xyz | 9: Ic xx yy zz xy
 //  10: Ic xz yz, mass, dg0 | 11: damping stiffness lower upper | 12: effort limit_k limit_d limit_dg | 13,14: spheres (pos, radius; radius<0 unused)
 //  15: mu0 mu1 sbpos.x sbpos.y | 16: sbpos.z (int)sensor (int)body (int)dof | 17: armature - - -
@@ -182,8 +182,9 @@ struct QLane {
 
     // rigid-body spatial inertia about O (world axes) and bias force p = v x* (I v) - gravity wrench, from the
     // rotational inertia about the COM in world axes (Icw), the COM about O (c) and the twist about O
+    // da, dl: AssetOptions.angular_damping / linear_damping -- wrench (-da Icw w ; -dl m v_c) at the COM, explicit
     B2G_HD static void rigid_terms(float mass, const float Icw[6], const float c[3], const float vw[3], const float vl[3],
-                                   const float g[3], float I[21], float pa[3], float pl[3]) {
+                                   const float g[3], float da, float dl, float I[21], float pa[3], float pl[3]) {
         float vxc[3]; cross(vw, c, vxc);
         const float l[3] = {mass * (vl[0] + vxc[0]), mass * (vl[1] + vxc[1]), mass * (vl[2] + vxc[2])};   // linear momentum
         const float hc[3] = {Icw[0] * vw[0] + Icw[3] * vw[1] + Icw[4] * vw[2],
@@ -191,9 +192,9 @@ struct QLane {
                              Icw[4] * vw[0] + Icw[5] * vw[1] + Icw[2] * vw[2]};                           // angular momentum about the COM
         float t1[3], t2[3];
         cross(vw, l, t1);
-        pl[0] = t1[0] - mass * g[0]; pl[1] = t1[1] - mass * g[1]; pl[2] = t1[2] - mass * g[2];
+        pl[0] = t1[0] - mass * g[0] + dl * l[0]; pl[1] = t1[1] - mass * g[1] + dl * l[1]; pl[2] = t1[2] - mass * g[2] + dl * l[2];
         cross(vw, hc, t1); cross(c, pl, t2);
-        pa[0] = t1[0] + t2[0]; pa[1] = t1[1] + t2[1]; pa[2] = t1[2] + t2[2];
+        pa[0] = t1[0] + t2[0] + da * hc[0]; pa[1] = t1[1] + t2[1] + da * hc[1]; pa[2] = t1[2] + t2[2] + da * hc[2];
         const float hm[3] = {mass * c[0], mass * c[1], mass * c[2]};
         const float c2 = dot3(c, c);
         I[0] = Icw[0] + mass * c2 - hm[0] * c[0];
@@ -239,6 +240,7 @@ struct QLane {
         const float4 H0 = qm[0];
         const float h = H0.x;
         const float g[3] = {H0.y, H0.z, H0.w};
+        const float da = qm[18].y, dl = qm[18].z;
         float Rr[9]; quat_to_mat(rs.rq, Rr);
         constexpr int IROW = NS * QPOSE_F4;           // first parked-inertia row
         {
@@ -288,7 +290,7 @@ struct QLane {
                 float c_[3]; matvec(R, cm_, c_);
                 c_[0] += x[0]; c_[1] += x[1]; c_[2] += x[2];
                 float Icw[6]; rotate_inertia(R, k9.x, k9.y, k9.z, k9.w, k10.x, k10.y, Icw);
-                rigid_terms(k10.z, Icw, c_, vw, vl, g, I, qa, ql);
+                rigid_terms(k10.z, Icw, c_, vw, vl, g, da, dl, I, qa, ql);
                 {
                     const float4 c0 = LK(s, 13), c1 = LK(s, 14), k15 = LK(s, 15);
                     float dummy[3];
@@ -364,8 +366,20 @@ struct QLane {
                 float a1[3], a2[3], a3[3], a4[3];
                 cross(vw, nO, a1); cross(vl, l, a2); cross(vw, l, a3); cross(hm, g, a4);
                 const float on = (lane == 0) ? 1.f : 0.f;
+                // damping wrench at the COM moved to O: linear momentum l = m v_c; angular momentum about the COM hc = nO - c x l
+                float dpa[3] = {0.f, 0.f, 0.f}, dpl[3] = {0.f, 0.f, 0.f};
+                if (da != 0.f || dl != 0.f) {
+                    const float inv_m = 1.f / mass;
+                    const float cc[3] = {hm[0] * inv_m, hm[1] * inv_m, hm[2] * inv_m};
+                    float cxl[3], cxf[3]; cross(cc, l, cxl);
 #pragma unroll
-                for (int c = 0; c < 3; c++) { qa[c] = on * (a1[c] + a2[c] - a4[c]); ql[c] = on * (a3[c] - mass * g[c]); }
+                    for (int c = 0; c < 3; c++) dpl[c] = dl * l[c];
+                    cross(cc, dpl, cxf);
+#pragma unroll
+                    for (int c = 0; c < 3; c++) dpa[c] = da * (nO[c] - cxl[c]) + cxf[c];
+                }
+#pragma unroll
+                for (int c = 0; c < 3; c++) { qa[c] = on * (a1[c] + a2[c] - a4[c] + dpa[c]); ql[c] = on * (a3[c] - mass * g[c] + dpl[c]); }
 #pragma unroll
                 for (int c = 0; c < 6; c++) I[c] = on * A[c];
                 I[6] = 0.f; I[7] = -on * hm[2]; I[8] = on * hm[1];
@@ -476,7 +490,9 @@ struct QLane {
         for (int c = 0; c < 3; c++) { rs.rw[c] += h * awr[c]; rs.rv[c] += h * (alr[c] + wxv[c]); }
 #pragma unroll
         for (int c = 0; c < 3; c++) rs.rp[c] += h * rs.rv[c];
-        const float wn2 = dot3(rs.rw, rs.rw);
+        float wn2 = dot3(rs.rw, rs.rw);
+        const float mx = qm[18].w;                                   // AssetOptions.max_angular_velocity (0: no clamp)
+        if (mx > 0.f && wn2 > mx * mx) { const float k = mx * q_rsqrt(wn2); rs.rw[0] *= k; rs.rw[1] *= k; rs.rw[2] *= k; wn2 = mx * mx; }
         float dq[4];
         if (wn2 > 1e-24f) {
             const float inv = q_rsqrt(wn2), wn = wn2 * inv;

@@ -71,7 +71,7 @@ static inline int quad_build(const b2g_model *m, const b2g_sim_params *sp, std::
         B[0] = I6[4] - ms * c[0] * c[2]; B[1] = I6[5] - ms * c[1] * c[2]; B[2] = q_i2f(link_body[0]); B[3] = q_i2f(sp->substeps);
         if (link_sensor[0] >= 0) { const float *bp = m->body_pos + 3 * m->sensor_body[link_sensor[0]]; float *S = F4(7); S[0] = bp[0]; S[1] = bp[1]; S[2] = bp[2]; }
         F4(7)[3] = q_i2f(m->nsens | (m->nb << 8));
-        F4(18)[0] = sp->ground_friction;
+        F4(18)[0] = sp->ground_friction; F4(18)[1] = m->angular_damping; F4(18)[2] = m->linear_damping; F4(18)[3] = m->max_angular_velocity;
         int k0 = 0;
         for (int k = 0; k < m->ncp; k++) if (m->cp_link[k] == 0) {
             float *P = F4(8 + k0);

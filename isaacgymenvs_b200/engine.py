@@ -66,7 +66,8 @@ class CModel(C.Structure):
                                           "sensor_body", "axis", "lpos", "lquat", "mass", "com", "inertia", "armature",
                                           "damping", "stiffness", "lower", "upper", "effort", "kp", "kd", "limit_k",
                                           "limit_d", "cp_pos", "cp_radius", "cp_mu", "body_pos", "body_quat")] + \
-               [("contact_kn", C.c_float), ("contact_cn", C.c_float), ("contact_vs", C.c_float)]
+               [("contact_kn", C.c_float), ("contact_cn", C.c_float), ("contact_vs", C.c_float),
+                ("angular_damping", C.c_float), ("linear_damping", C.c_float), ("max_angular_velocity", C.c_float)]
 
 
 class CModelExt(C.Structure):
@@ -76,7 +77,8 @@ class CModelExt(C.Structure):
                 ("nbox", C.c_int32), ("box_link", C.c_int32 * 4), ("box_pos", (C.c_float * 3) * 4),
                 ("box_quat", (C.c_float * 4) * 4), ("box_half", (C.c_float * 3) * 4),
                 ("nten", C.c_int32), ("ten_dof", (C.c_int32 * 2) * 4), ("ten_coef", (C.c_float * 2) * 4),
-                ("ten_range", (C.c_float * 2) * 4), ("ten_k", C.c_float), ("ten_d", C.c_float)]
+                ("ten_range", (C.c_float * 2) * 4), ("ten_k", C.c_float), ("ten_d", C.c_float),
+                ("obj_angular_damping", C.c_float), ("obj_linear_damping", C.c_float)]
 
 
 def object_contact_gains(mass):
@@ -94,6 +96,7 @@ def pack_model_ext(model, obj=None, actors_per_env=1, tendons=None, tendon_k=0.0
     if obj is not None:
         ex.obj_actor, ex.obj_gravity_on = 1, int(obj.get("gravity_on", 1))
         ex.obj_mass = float(obj["mass"])
+        ex.obj_angular_damping, ex.obj_linear_damping = float(obj.get("angular_damping", 0.0)), float(obj.get("linear_damping", 0.0))
         ex.obj_inertia = (C.c_float * 3)(*obj["inertia"]); ex.obj_half = (C.c_float * 3)(*obj["half"])
         kn, cn = object_contact_gains(ex.obj_mass)
         ex.obj_kn, ex.obj_cn, ex.obj_mu = kn, cn, float(obj.get("mu", 1.0))
@@ -199,6 +202,9 @@ def pack_model(model, ground_mu=1.0):
     cm.effort = arr("effort", np.minimum(model.effort, 3e38), np.float32)
     cm.cp_mu = arr("cp_mu", np.asarray(model.cp_mu), np.float32)
     cm.contact_kn, cm.contact_cn, cm.contact_vs = model.contact_kn, model.contact_cn, model.contact_vs
+    cm.angular_damping = float(getattr(model, "angular_damping", 0.0) or 0.0)
+    cm.linear_damping = float(getattr(model, "linear_damping", 0.0) or 0.0)
+    cm.max_angular_velocity = float(getattr(model, "max_angular_velocity", 0.0) or 0.0)
     return cm, keep
 
 

@@ -180,6 +180,13 @@ class Model:
     contact_cn: float = 0.0
     contact_vs: float = 0.02
     gravity_on: bool = True
+    # AssetOptions.angular_damping / linear_damping / max_angular_velocity (humanoid.py:153-154, anymal_terrain.py:225-226):
+    # every link's COM twist is damped with acceleration -d * v (a wrench -d_a Ic w, -d_l m v_c on the link), the base's
+    # angular speed is clamped after integration (DESIGN.md "physics model")
+    angular_damping: float = 0.0
+    linear_damping: float = 0.0
+    max_angular_velocity: float = 64.0
+    build_options: dict = None           # the BuildOptions this model was compiled with (checked when a committed blob stands in for the XML)
     default_root_pos: np.ndarray = None  # body pose from the file (Ant overrides it at create_actor)
     default_root_quat: np.ndarray = None
 
@@ -256,6 +263,7 @@ class BuildOptions:
     density: float = 1000.0           # used when a body has neither <inertial> nor a geom density
     angular_damping: float = 0.0
     linear_damping: float = 0.0
+    max_angular_velocity: float = 64.0 # AssetOptions default (rad/s)
     disable_gravity: bool = False
     default_dof_drive_mode: int = DRIVE_NONE
     capsule_mid_spheres: int = 0       # extra contact spheres along a capsule's axis (hands: the cylinder part must touch objects too)
@@ -429,6 +437,9 @@ def build_model(name, root: IRBody, has_free_root: bool, opts: BuildOptions) -> 
     m.contact_kn = opts.contact_kn_per_kg * M
     m.contact_cn = 2.0 * opts.contact_zeta * np.sqrt(m.contact_kn * M / 4.0)
     m.gravity_on = not opts.disable_gravity
+    m.angular_damping, m.linear_damping = float(opts.angular_damping), float(opts.linear_damping)
+    m.max_angular_velocity = float(opts.max_angular_velocity)
+    m.build_options = {k: (float(v) if isinstance(v, float) else int(v) if isinstance(v, (bool, int)) else v) for k, v in opts.__dict__.items()}
     m.default_root_pos = np.asarray(root.pos, float)
     m.default_root_quat = rot.mat_to_quat(root.R)
     return m

@@ -24,7 +24,7 @@ class Cartpole(VecTask):
 
     def _build_model(self):
         asset_file = self.cfg["env"].get("asset", {}).get("assetFileName", "urdf/cartpole.urdf")
-        model = copy.deepcopy(load_asset_file(_asset_root(), asset_file, BuildOptions(fix_base_link=True)))  # cartpole.py:86-88
+        model = copy.deepcopy(load_asset_file(_asset_root(), asset_file, BuildOptions(fix_base_link=True, angular_damping=0.5)))  # cartpole.py:86-88: AssetOptions defaults otherwise (angular_damping 0.5)
         self.num_dof = model.ndof
         return model
 

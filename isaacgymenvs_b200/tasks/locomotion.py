@@ -58,7 +58,8 @@ class _Locomotion(VecTask):
     # ---- ant.py:135-212 / humanoid.py:133-218
     def _build_model(self):
         asset_file = self.cfg["env"].get("asset", {}).get("assetFileName", self.DEFAULT_ASSET)
-        opts = BuildOptions(angular_damping=0.01 if self.HUMANOID else 0.0)
+        opts = BuildOptions(angular_damping=0.01 if self.HUMANOID else 0.0,
+                            max_angular_velocity=100.0 if self.HUMANOID else 64.0)     # humanoid.py:153-154, ant.py:151
         model = copy.deepcopy(load_asset_file(_asset_root(), asset_file, opts))
         if self.HUMANOID:
             feet = [model.body_names.index("right_foot"), model.body_names.index("left_foot")]   # humanoid.py:164-168

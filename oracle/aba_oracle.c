@@ -92,6 +92,10 @@ typedef struct {
     const int *ten_dof;                     /* nten x 2 (dof indices) */
     const double *ten_coef, *ten_range;     /* nten x 2 */
     double ten_k, ten_d;
+    /* AssetOptions.angular_damping / linear_damping / max_angular_velocity (humanoid.py:153-154, anymal_terrain.py:225-226):
+     * every link's COM twist is damped with acceleration -d v (wrench -d_a Ic w ; -d_l m v_c, explicit), the base's angular
+     * speed is clamped after integration; same for the free object (its own AssetOptions, shadow_hand.py:279-282) */
+    double angular_damping, linear_damping, max_angular_velocity, obj_angular_damping, obj_linear_damping;
 } OracleModel;
 
 /* ---------------------------------------------------------------- small linear algebra */
@@ -303,6 +307,16 @@ static void substep(const OracleModel *m, real h, real *root, real *dof, const r
         /* gravity as an explicit force: f_g = I * [0; R^T g] */
         real ag[6] = {0, 0, 0, 0, 0, 0}, fg[6]; mat3T_vec(Rw[i], g, ag + 3); mat6_vec(IA[i], ag, fg);
         for (int k = 0; k < 6; k++) pA[i][k] -= fg[k];
+        if (m->angular_damping != 0 || m->linear_damping != 0) {
+            /* link coordinates: torque about the COM -d_a Ic w, force -d_l m v_c; moved to the link origin */
+            real da = (real)m->angular_damping, dl = (real)m->linear_damping, ms = (real)m->mass[i];
+            real Iw3[3] = {Ic[0] * v[i][0] + Ic[3] * v[i][1] + Ic[4] * v[i][2], Ic[3] * v[i][0] + Ic[1] * v[i][1] + Ic[5] * v[i][2],
+                           Ic[4] * v[i][0] + Ic[5] * v[i][1] + Ic[2] * v[i][2]};
+            real wxc[3], f[3], cxf[3]; cross3(v[i], cm, wxc);
+            for (int k = 0; k < 3; k++) f[k] = -dl * ms * (v[i][3 + k] + wxc[k]);
+            cross3(cm, f, cxf);
+            for (int k = 0; k < 3; k++) { pA[i][k] -= -da * Iw3[k] + cxf[k]; pA[i][3 + k] -= f[k]; }
+        }
     }
 
     /* ---- contacts: explicit force + implicit augmentation of the link inertia */
@@ -360,6 +374,7 @@ static void substep(const OracleModel *m, real h, real *root, real *dof, const r
          * at the contact point, the same quantity the articulation's contacts use */
         real wxv0[3]; cross3(obj + 10, obj + 7, wxv0);
         for (int k = 0; k < 3; k++) { bo[k] = -gyro[k]; bo[3 + k] = (m->obj_gravity_on ? (real)m->obj_mass * (real)m->gravity[k] : 0) - (real)m->obj_mass * wxv0[k]; }
+        for (int k = 0; k < 3; k++) { bo[k] -= (real)m->obj_angular_damping * Iww[k]; bo[3 + k] -= (real)m->obj_linear_damping * (real)m->obj_mass * obj[7 + k]; }
         real okn = (real)m->obj_kn, ocn = (real)m->obj_cn, ogn = ocn + h * okn, hb[3] = {(real)m->obj_half[0], (real)m->obj_half[1], (real)m->obj_half[2]};
         /* helper macro: one contact at world point pc with normal nrm (direction of the force on the LINK), penetration pen */
 #define OBJ_CONTACT(LI, BI, CPI, PC, NRM, PEN, MU) do {                                                                       \
@@ -573,6 +588,10 @@ static void substep(const OracleModel *m, real h, real *root, real *dof, const r
         mat3_vec(R0, a[0], dw); mat3_vec(R0, t1, dv); (void)al;
         for (int k = 0; k < 3; k++) { root[10 + k] += h * dw[k]; root[7 + k] += h * dv[k]; }
         for (int k = 0; k < 3; k++) root[k] += h * root[7 + k];
+        if (m->max_angular_velocity > 0) {
+            real wn2 = root[10] * root[10] + root[11] * root[11] + root[12] * root[12], mx = (real)m->max_angular_velocity;
+            if (wn2 > mx * mx) { real sc = mx / SQRT(wn2); root[10] *= sc; root[11] *= sc; root[12] *= sc; }
+        }
         real w[3] = {root[10], root[11], root[12]};
         real wn = SQRT(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]), th = wn * h, dq[4];
         if (wn > 1e-12) { real s = SIN(th / 2) / wn; dq[0] = w[0] * s; dq[1] = w[1] * s; dq[2] = w[2] * s; dq[3] = COS(th / 2); }

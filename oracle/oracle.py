@@ -36,7 +36,9 @@ class _CModel(C.Structure):
                 ("obj_kn", C.c_double), ("obj_cn", C.c_double), ("obj_mu", C.c_double),
                 ("box_link", C.c_void_p), ("box_body", C.c_void_p), ("box_pos", C.c_void_p), ("box_quat", C.c_void_p), ("box_half", C.c_void_p),
                 ("nten", C.c_int), ("pad2", C.c_int), ("ten_dof", C.c_void_p), ("ten_coef", C.c_void_p),
-                ("ten_range", C.c_void_p), ("ten_k", C.c_double), ("ten_d", C.c_double)]
+                ("ten_range", C.c_void_p), ("ten_k", C.c_double), ("ten_d", C.c_double),
+                ("angular_damping", C.c_double), ("linear_damping", C.c_double), ("max_angular_velocity", C.c_double),
+                ("obj_angular_damping", C.c_double), ("obj_linear_damping", C.c_double)]
 
 
 def object_contact_gains(mass):
@@ -83,12 +85,16 @@ class OracleSim:
         cm.kn, cm.cn, cm.vs = m.contact_kn, m.contact_cn, m.contact_vs
         cm.gravity = (C.c_double * 3)(*gravity)
         cm.dt = dt
+        cm.angular_damping = float(getattr(m, "angular_damping", 0.0) or 0.0)
+        cm.linear_damping = float(getattr(m, "linear_damping", 0.0) or 0.0)
+        cm.max_angular_velocity = float(getattr(m, "max_angular_velocity", 0.0) or 0.0)
         # free object (ShadowHand's cube): obj = dict(mass, inertia(3), half(3), mu, gravity_on)
         cm.obj_on = 0
         if obj is not None:
             cm.obj_on, cm.obj_gravity_on = 1, int(obj.get("gravity_on", 1))
             cm.obj_coupling = int(obj.get("coupling", 0))      # 0 = the engine's block-Jacobi; 1 = Gauss-Seidel experiment
             cm.obj_mass = float(obj["mass"])
+            cm.obj_angular_damping, cm.obj_linear_damping = float(obj.get("angular_damping", 0.0)), float(obj.get("linear_damping", 0.0))
             cm.obj_inertia = (C.c_double * 3)(*obj["inertia"]); cm.obj_half = (C.c_double * 3)(*obj["half"])
             kn, cn = object_contact_gains(cm.obj_mass)
             cm.obj_kn, cm.obj_cn, cm.obj_mu = kn, cn, float(obj.get("mu", 1.0))

@@ -56,6 +56,10 @@ def inverse_dynamics(m, root, q, qd, qdd, root_acc, gravity, ext=None):
         ac = a[i] + np.cross(al[i], c) + np.cross(w[i], np.cross(w[i], c))
         F = m.mass[i] * ac - m.mass[i] * g
         N = Iw @ al[i] + np.cross(w[i], Iw @ w[i])
+        # AssetOptions.angular_damping / linear_damping: an external wrench -d_a Iw w, -d_l m v_c at the COM (classical form)
+        da, dl = float(getattr(m, "angular_damping", 0.0) or 0.0), float(getattr(m, "linear_damping", 0.0) or 0.0)
+        F = F + dl * m.mass[i] * (v[i] + np.cross(w[i], c))
+        N = N + da * (Iw @ w[i])
         f[i] = f[i] + F
         n[i] = n[i] + N + np.cross(c, F)
         if ext:

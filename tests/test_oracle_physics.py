@@ -246,3 +246,25 @@ def test_object_collision_exchanges_momentum():
     # extra sweeps of the two block solves on the coupled implicit law stay stable and reduce the drift, slowly
     _, p4, _, _ = run(0.004, coupling=4)
     assert np.abs(p4 - p0).max() < 0.7 * e1
+
+
+def test_asset_damping_and_angular_speed_clamp():
+    """AssetOptions.angular_damping / linear_damping / max_angular_velocity on a free single body (the cube asset, gravity
+    off): the twist decays like exp(-d t) (explicit Euler: (1 - d h)^n) and the angular speed is clamped."""
+    import copy
+    m = copy.deepcopy(load_compiled("cube"))
+    m.angular_damping, m.linear_damping, m.max_angular_velocity = 0.5, 0.25, 64.0
+    dt, sub = 0.01, 1
+    sim = OracleSim(m, dt, sub, (0.0, 0.0, 0.0))
+    root = np.zeros((1, 13)); root[0, 6] = 1; root[0, 2] = 5.0
+    root[0, 7:10] = [1.0, -2.0, 0.5]; root[0, 10:13] = [0.0, 0.0, 3.0]          # spin about a principal axis
+    dof = np.zeros((1, 0, 2))
+    n = 100
+    for _ in range(n):
+        sim.simulate(root, dof, np.zeros((1, 0)))
+    assert np.allclose(root[0, 10:13], np.array([0, 0, 3.0]) * (1 - 0.5 * dt) ** n, rtol=1e-6, atol=1e-9)
+    assert np.allclose(root[0, 7:10], np.array([1.0, -2.0, 0.5]) * (1 - 0.25 * dt) ** n, rtol=1e-6)
+    assert abs((1 - 0.5 * dt) ** n - np.exp(-0.5)) < 2e-3
+    root[0, 10:13] = [0.0, 80.0, 60.0]                                            # |w| = 100 > 64
+    sim.simulate(root, dof, np.zeros((1, 0)))
+    assert abs(np.linalg.norm(root[0, 10:13]) - 64.0) < 1e-9

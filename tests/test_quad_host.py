@@ -91,10 +91,13 @@ def _compare(m, rg, dg, out_g, r64, d64, out):
     assert np.abs(nc - out["contact_force"]).max() < 2e-3 * max(1.0, np.abs(out["contact_force"]).max())
 
 
-@pytest.mark.parametrize("name,zlo,zhi,tscale,dt,sub", [("ant", 0.15, 0.8, 15.0, 0.0166, 2), ("anymal", 0.3, 0.9, 40.0, 0.005, 1)])
-def test_quad_substep_matches_oracle(name, zlo, zhi, tscale, dt, sub):
+@pytest.mark.parametrize("name,zlo,zhi,tscale,dt,sub,damp", [("ant", 0.15, 0.8, 15.0, 0.0166, 2, None), ("anymal", 0.3, 0.9, 40.0, 0.005, 1, None),
+                                                               ("ant", 0.15, 0.8, 15.0, 0.0166, 2, (0.8, 0.5, 3.0))])
+def test_quad_substep_matches_oracle(name, zlo, zhi, tscale, dt, sub, damp):
     lib = _lib()
     m = _model(name)
+    if damp:          # AssetOptions.angular_damping / linear_damping / max_angular_velocity, exaggerated so that they matter in one step
+        m.angular_damping, m.linear_damping, m.max_angular_velocity = damp
     n = 512
     rng = np.random.default_rng(7)
     root, dof = _random_states(m, n, rng, zlo, zhi)
