@@ -581,6 +581,7 @@ struct b2g_sim {
     int64_t launches = 0;
     // quad path (b2g_quad.cuh): chain length (2 Ant-like, 3 ANYmal-like) or 0 = generic Stepper; the packed constants
     int quad_ns = 0;
+    int quad_spec = 0;                        // QLane specialisation flags the constants are packed for (b2g_quad.cuh)
     int quad_block = 128;
     float4 *d_qm = nullptr;
     std::vector<const void *> smem_set;      // kernels whose dynamic shared-memory limit has been raised (once per sim)
@@ -875,8 +876,10 @@ extern "C" int b2g_create_ext(const b2g_model *m, const b2g_model_ext *ext, cons
         s->no_zero_copy = nz != nullptr;
         if (qb && (atoi(qb) == 64 || atoi(qb) == 128)) s->quad_block = atoi(qb);
         if (!(nq && nq[0] == '1') && !ext && !(force1 && force1[0] == '1') && !getenv("B2G_LANES") && !getenv("B2G_BLOCK")) {
-            std::vector<float> qm; int leg_link[12];
-            const int ns = quad_build(m, sp, qm, leg_link);
+            std::vector<float> qm; int leg_link[12], spec = 0;
+            const char *nsp = getenv("B2G_QUAD_NO_SPEC");
+            const int ns = quad_build(m, sp, qm, leg_link, &spec, (nsp && nsp[0] == '1') ? 0 : 3);
+            s->quad_spec = spec;
             if (ns) {
                 CUDA_TRY(cudaMalloc(&s->d_qm, qm.size() * sizeof(float)));
                 CUDA_TRY(cudaMemcpy(s->d_qm, qm.data(), qm.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -972,15 +975,16 @@ extern "C" int b2g_simulate(b2g_sim *s, void *stream) {
         constexpr int QB = 128;
         const int N = s->num_envs, grid = (N * 4 + QB - 1) / QB;
         const size_t dyn = ((size_t)quad_park_f4(s->quad_ns) * QB + quad_model_f4(s->quad_ns)) * sizeof(float4);
-#define QSIM(NS_, HF_)                                                                                              \
+#define QSIM(NS_, HF_, SP_)                                                                                         \
         do {                                                                                                        \
-            int rc_ = set_smem(s, quad_simulate_kernel<NS_, HF_, QB>, dyn); if (rc_) return rc_;                    \
-            quad_simulate_kernel<NS_, HF_, QB><<<grid, QB, dyn, st>>>(s->d_qm, s->d_hf, s->buf, N, s->hm.substeps);                 \
+            int rc_ = set_smem(s, quad_simulate_kernel<NS_, HF_, SP_, QB>, dyn); if (rc_) return rc_;               \
+            quad_simulate_kernel<NS_, HF_, SP_, QB><<<grid, QB, dyn, st>>>(s->d_qm, s->d_hf, s->buf, N, s->hm.substeps); \
         } while (0)
-        if (s->quad_ns == 2 && !s->d_hf) QSIM(2, false);
-        else if (s->quad_ns == 2) QSIM(2, true);
-        else if (s->quad_ns == 3 && !s->d_hf) QSIM(3, false);
-        else QSIM(3, true);
+        const bool sp3 = s->quad_spec == 3;
+        if (s->quad_ns == 2 && !s->d_hf) { if (sp3) QSIM(2, false, 3); else QSIM(2, false, 0); }
+        else if (s->quad_ns == 2) { if (sp3) QSIM(2, true, 3); else QSIM(2, true, 0); }
+        else if (s->quad_ns == 3 && !s->d_hf) { if (sp3) QSIM(3, false, 3); else QSIM(3, false, 0); }
+        else { if (sp3) QSIM(3, true, 3); else QSIM(3, true, 0); }
 #undef QSIM
         s->launches++;
         CUDA_TRY(cudaGetLastError());
@@ -1198,19 +1202,21 @@ extern "C" int b2g_task_step(b2g_sim *s, const float *actions, void *stream) {
                 ta.h_act = nullptr; ta.h_obs = ta.h_rew = nullptr; ta.h_reset = nullptr; ta.h_timeout = nullptr;
                 if (s->zero_copy.on) { ta.h_act = actions; ta.h_obs = s->zero_copy.obs; ta.h_rew = s->zero_copy.rew; ta.h_reset = s->zero_copy.reset; ta.h_timeout = s->zero_copy.timeout; }
                 const int qgrid = (int)N / epb;
-#define QLOCO(BK, HIO)                                                                                                    \
+#define QLOCO(SP_, BK, HIO)                                                                                               \
     do {                                                                                                                   \
-        int rc_ = set_smem(s, quad_loco_kernel<2, BK, HIO>, dyn); if (rc_) return rc_;                                     \
+        int rc_ = set_smem(s, quad_loco_kernel<2, SP_, BK, HIO>, dyn); if (rc_) return rc_;                                \
         cudaLaunchConfig_t lc = {};                                                                                        \
         lc.gridDim = dim3(qgrid); lc.blockDim = dim3(BK); lc.dynamicSmemBytes = dyn; lc.stream = st;                       \
         cudaLaunchAttribute at[1];                                                                                         \
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                                     \
         at[0].val.programmaticStreamSerializationAllowed = 1;                                                              \
         lc.attrs = at; lc.numAttrs = 1;                                                                                    \
-        CUDA_TRY(cudaLaunchKernelEx(&lc, quad_loco_kernel<2, BK, HIO>, (const float4 *)s->d_qm, s->buf, P, actions, (int)N, (int)s->hm.substeps, ta)); \
+        CUDA_TRY(cudaLaunchKernelEx(&lc, quad_loco_kernel<2, SP_, BK, HIO>, (const float4 *)s->d_qm, s->buf, P, actions, (int)N, (int)s->hm.substeps, ta)); \
     } while (0)
-                if (qb == 128) { if (s->zero_copy.on) QLOCO(128, true); else QLOCO(128, false); }
-                else { if (s->zero_copy.on) QLOCO(64, true); else QLOCO(64, false); }
+#define QLOCO_S(BK, HIO) do { if (s->quad_spec == 3) QLOCO(3, BK, HIO); else QLOCO(0, BK, HIO); } while (0)
+                if (qb == 128) { if (s->zero_copy.on) QLOCO_S(128, true); else QLOCO_S(128, false); }
+                else { if (s->zero_copy.on) QLOCO_S(64, true); else QLOCO_S(64, false); }
+#undef QLOCO_S
 #undef QLOCO
                 s->launches++;
                 CUDA_TRY(cudaGetLastError());

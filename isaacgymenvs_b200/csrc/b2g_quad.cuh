@@ -69,7 +69,11 @@ struct QOutputs {
     bool write;
 };
 
-template <int NS, bool HF>
+// SP: specialisation flags decided on the host from the model (quad_build):
+//   bit 0  every chain link's inertia about its COM is axisymmetric (a 1 + bm u u^T: capsules, spheres, cylinders) --
+//          rows 9/10 of the link block then hold (u, a | bm) and the congruence R Ic R^T (45 ops) becomes a 1 + bm (R u)(R u)^T (18);
+//   bit 1  the base's inertia is axisymmetric AND its COM is at its origin: no first-moment terms at all.
+template <int NS, bool HF, int SP = 0>
 struct QLane {
     const float4 *qm;         // quad model (shared memory on the device)
     const int16_t *hf;        // height samples (global) or null
@@ -289,7 +293,16 @@ struct QLane {
                 const float cm_[3] = {k8.y, k8.z, k8.w};
                 float c_[3]; matvec(R, cm_, c_);
                 c_[0] += x[0]; c_[1] += x[1]; c_[2] += x[2];
-                float Icw[6]; rotate_inertia(R, k9.x, k9.y, k9.z, k9.w, k10.x, k10.y, Icw);
+                float Icw[6];
+                if (SP & 1) {
+                    const float ul[3] = {k9.x, k9.y, k9.z};
+                    float uw[3]; matvec(R, ul, uw);
+                    const float b0 = k10.x * uw[0], b1 = k10.x * uw[1], b2 = k10.x * uw[2];
+                    Icw[0] = k9.w + b0 * uw[0]; Icw[1] = k9.w + b1 * uw[1]; Icw[2] = k9.w + b2 * uw[2];
+                    Icw[3] = b0 * uw[1]; Icw[4] = b0 * uw[2]; Icw[5] = b1 * uw[2];
+                } else {
+                    rotate_inertia(R, k9.x, k9.y, k9.z, k9.w, k10.x, k10.y, Icw);
+                }
                 rigid_terms(k10.z, Icw, c_, vw, vl, g, da, dl, I, qa, ql);
                 {
                     const float4 c0 = LK(s, 13), c1 = LK(s, 14), k15 = LK(s, 15);
@@ -344,18 +357,34 @@ struct QLane {
 #pragma unroll
             for (int c = 0; c < 3; c++) { pa[c] = qa[c]; pl[c] = ql[c]; }
         }
-        // ---- the base: its own rigid-body terms (lane 0 contributes them), its spheres dealt round-robin to the lanes
+        // ---- the base: its own rigid-body terms (lane 0 contributes them), its spheres dealt round-robin to the lanes;
+        // everything is accumulated straight onto the chain's contribution (no separate 27-value sum, no adds of zeros)
         {
             const float4 H3 = qm[3], H4 = qm[4], H5 = qm[5], H6 = qm[6];
             const float xr[3] = {0.f, 0.f, 0.f};
-            float I[21], qa[3], ql[3];
-            {
+            const float on = (lane == 0) ? 1.f : 0.f;
+            const float *vw = rs.rw, *vl = rs.rv;
+            if (SP & 2) {
+                // axisymmetric base with its COM at the origin: A = a 1 + bm (R u)(R u)^T, no first moment
+                const float ul[3] = {H5.x, H5.y, H5.z};
+                float uw[3]; matvec(Rr, ul, uw);
+                const float am = on * H5.w, bm = on * H6.x, mo = on * H4.w;
+                const float s_ = bm * dot3(uw, vw);
+                const float nO[3] = {am * vw[0] + s_ * uw[0], am * vw[1] + s_ * uw[1], am * vw[2] + s_ * uw[2]};     // A vw
+                float a1[3], a3[3];
+                cross(vw, nO, a1); cross(vw, vl, a3);
+#pragma unroll
+                for (int c = 0; c < 3; c++) { pa[c] += a1[c] + da * nO[c]; pl[c] += mo * (a3[c] - g[c] + dl * vl[c]); }
+                const float b0 = bm * uw[0], b1 = bm * uw[1], b2 = bm * uw[2];
+                IA[0] += am + b0 * uw[0]; IA[1] += am + b1 * uw[1]; IA[2] += am + b2 * uw[2];
+                IA[3] += b0 * uw[1]; IA[4] += b0 * uw[2]; IA[5] += b1 * uw[2];
+                IA[15] += mo; IA[16] += mo; IA[17] += mo;
+            } else {
                 // about the root origin directly: A = R Ab R^T, first moment hm = R (m com)
                 float A[6]; rotate_inertia(Rr, H5.x, H5.y, H5.z, H5.w, H6.x, H6.y, A);
                 const float mass = H4.w;
                 const float cb[3] = {H4.x * mass, H4.y * mass, H4.z * mass};
                 float hm[3]; matvec(Rr, cb, hm);
-                const float *vw = rs.rw, *vl = rs.rv;
                 // momentum about O: n = A vw + hm x vl ; l = m vl - hm x vw
                 float t1[3], t2[3];
                 cross(hm, vl, t1); cross(hm, vw, t2);
@@ -365,7 +394,6 @@ struct QLane {
                 const float l[3] = {mass * vl[0] - t2[0], mass * vl[1] - t2[1], mass * vl[2] - t2[2]};
                 float a1[3], a2[3], a3[3], a4[3];
                 cross(vw, nO, a1); cross(vl, l, a2); cross(vw, l, a3); cross(hm, g, a4);
-                const float on = (lane == 0) ? 1.f : 0.f;
                 // damping wrench at the COM moved to O: linear momentum l = m v_c; angular momentum about the COM hc = nO - c x l
                 float dpa[3] = {0.f, 0.f, 0.f}, dpl[3] = {0.f, 0.f, 0.f};
                 if (da != 0.f || dl != 0.f) {
@@ -379,13 +407,13 @@ struct QLane {
                     for (int c = 0; c < 3; c++) dpa[c] = da * (nO[c] - cxl[c]) + cxf[c];
                 }
 #pragma unroll
-                for (int c = 0; c < 3; c++) { qa[c] = on * (a1[c] + a2[c] - a4[c] + dpa[c]); ql[c] = on * (a3[c] - mass * g[c] + dpl[c]); }
+                for (int c = 0; c < 3; c++) { pa[c] += on * (a1[c] + a2[c] - a4[c] + dpa[c]); pl[c] += on * (a3[c] - mass * g[c] + dpl[c]); }
 #pragma unroll
-                for (int c = 0; c < 6; c++) I[c] = on * A[c];
-                I[6] = 0.f; I[7] = -on * hm[2]; I[8] = on * hm[1];
-                I[9] = on * hm[2]; I[10] = 0.f; I[11] = -on * hm[0];
-                I[12] = -on * hm[1]; I[13] = on * hm[0]; I[14] = 0.f;
-                I[15] = on * mass; I[16] = on * mass; I[17] = on * mass; I[18] = 0.f; I[19] = 0.f; I[20] = 0.f;
+                for (int c = 0; c < 6; c++) IA[c] += on * A[c];
+                IA[7] -= on * hm[2]; IA[8] += on * hm[1];
+                IA[9] += on * hm[2]; IA[11] -= on * hm[0];
+                IA[12] -= on * hm[1]; IA[13] += on * hm[0];
+                IA[15] += on * mass; IA[16] += on * mass; IA[17] += on * mass;
             }
             const int ncp = q_f2i(H3.z);
             float dummy[3];
@@ -393,12 +421,8 @@ struct QLane {
             for (int k = lane; k < ncp; k += 4) {
                 const float4 cp = qm[8 + k];
                 const float mu = reinterpret_cast<const float *>(qm + 16)[k];
-                sphere<true>(cp, mu, rs.rp, Rr, xr, rs.rw, rs.rv, I, qa, ql, dummy, dummy, dummy, dummy);
+                sphere<true>(cp, mu, rs.rp, Rr, xr, rs.rw, rs.rv, IA, pa, pl, dummy, dummy, dummy, dummy);
             }
-#pragma unroll
-            for (int c = 0; c < 21; c++) IA[c] += I[c];
-#pragma unroll
-            for (int c = 0; c < 3; c++) { pa[c] += qa[c]; pl[c] += ql[c]; }
         }
     }
 
@@ -417,7 +441,10 @@ struct QLane {
         }
     }
     // force sensor (body frame, torque about the body origin) / net contact force of one link
-    B2G_HD static void emit(const QOutputs &o, int sensor, int body, const float sb[3], const float R[9], const float F[3], const float T[3]) {
+    // keep (optional, 6 floats): the sensor reading also stays with the caller (the fused step kernels put it into the
+    // observation without reading the tensor back)
+    B2G_HD static void emit(const QOutputs &o, int sensor, int body, const float sb[3], const float R[9], const float F[3], const float T[3],
+                            float *keep = nullptr) {
         if (!o.write) return;
         if (sensor >= 0 && o.sensor) {
             float wb[3], bxF[3], Tb_[3], Fb[3], Tb[3];
@@ -426,6 +453,7 @@ struct QLane {
             matTvec(R, F, Fb); matTvec(R, Tb_, Tb);
             float *d = o.sensor + 6 * sensor;
             d[0] = Fb[0]; d[1] = Fb[1]; d[2] = Fb[2]; d[3] = Tb[0]; d[4] = Tb[1]; d[5] = Tb[2];
+            if (keep) { keep[0] = Fb[0]; keep[1] = Fb[1]; keep[2] = Fb[2]; keep[3] = Tb[0]; keep[4] = Tb[1]; keep[5] = Tb[2]; }
         }
         if (o.net_contact && body >= 0) {
             float *d = o.net_contact + 3 * body;

@@ -12,9 +12,40 @@ namespace b2g {
 
 static inline float q_i2f(int i) { float f; memcpy(&f, &i, 4); return f; }
 
+// Is the symmetric inertia (xx yy zz xy xz yz) of the form a 1 + bm u u^T (two equal principal moments)?  Jacobi
+// eigen-decomposition in double; equal within 1e-6 of the largest moment.
+static inline bool quad_axisymmetric(const float I6[6], float u[3], float *a, float *bm) {
+    double A[3][3] = {{I6[0], I6[3], I6[4]}, {I6[3], I6[1], I6[5]}, {I6[4], I6[5], I6[2]}}, V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int sweep = 0; sweep < 32; sweep++) {
+        double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
+        if (off < 1e-300) break;
+        for (int p_ = 0; p_ < 2; p_++) for (int q_ = p_ + 1; q_ < 3; q_++) {
+            if (fabs(A[p_][q_]) < 1e-300) continue;
+            const double th = (A[q_][q_] - A[p_][p_]) / (2 * A[p_][q_]);
+            const double t = (th >= 0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1)), c = 1 / sqrt(t * t + 1), s_ = t * c;
+            for (int k = 0; k < 3; k++) { const double x = A[k][p_], y = A[k][q_]; A[k][p_] = c * x - s_ * y; A[k][q_] = s_ * x + c * y; }
+            for (int k = 0; k < 3; k++) { const double x = A[p_][k], y = A[q_][k]; A[p_][k] = c * x - s_ * y; A[q_][k] = s_ * x + c * y; }
+            for (int k = 0; k < 3; k++) { const double x = V[k][p_], y = V[k][q_]; V[k][p_] = c * x - s_ * y; V[k][q_] = s_ * x + c * y; }
+        }
+    }
+    const double l[3] = {A[0][0], A[1][1], A[2][2]};
+    const double big = fmax(fabs(l[0]), fmax(fabs(l[1]), fabs(l[2])));
+    int odd = -1;
+    if (fabs(l[0] - l[1]) <= 1e-6 * big) odd = 2;
+    else if (fabs(l[0] - l[2]) <= 1e-6 * big) odd = 1;
+    else if (fabs(l[1] - l[2]) <= 1e-6 * big) odd = 0;
+    if (odd < 0) return false;
+    const double aa = 0.5 * (l[(odd + 1) % 3] + l[(odd + 2) % 3]);
+    *a = (float)aa; *bm = (float)(l[odd] - aa);
+    for (int k = 0; k < 3; k++) u[k] = (float)V[k][odd];
+    return true;
+}
+
 // Returns the chain length NS (2 or 3) and fills `qm` (quad_model_f4(NS) float4, as floats) when the model fits the
 // quad path; 0 otherwise (the generic Stepper handles it).  leg_link[l * NS + s] = link of lane l, slot s.
-static inline int quad_build(const b2g_model *m, const b2g_sim_params *sp, std::vector<float> &qm, int leg_link[12]) {
+// *spec receives the QLane specialisation flags the packed constants are laid out for (0 or 3; want_spec = 0 forces the
+// general layout).
+static inline int quad_build(const b2g_model *m, const b2g_sim_params *sp, std::vector<float> &qm, int leg_link[12], int *spec = nullptr, int want_spec = 3) {
     if (m->root_fixed || m->nl < 9) return 0;
     const int nd = m->nl - 1;
     if (nd != 8 && nd != 12) return 0;
@@ -45,6 +76,19 @@ static inline int quad_build(const b2g_model *m, const b2g_sim_params *sp, std::
     }
     for (int b = m->nb - 1; b >= 0; b--) link_body[m->body_link[b]] = b;
 
+    // specialisation: every chain link axisymmetric about its COM (bit 0) and an axisymmetric base with its COM at its origin (bit 1)
+    int sflags = want_spec;
+    std::vector<float> ax(4 * 5 * 3 + 5, 0.f);            // per link (u, a, bm), link order of leg_link; last 5: the base
+    if (sflags) {
+        for (int k = 0; k < 4 * NS && sflags; k++) {
+            const int li = leg_link[k];
+            if (!quad_axisymmetric(m->inertia + 6 * li, &ax[5 * k], &ax[5 * k + 3], &ax[5 * k + 4])) sflags = 0;
+        }
+        float *rb = &ax[5 * 12];
+        if (sflags && !(quad_axisymmetric(m->inertia, rb, rb + 3, rb + 4) && m->com[0] == 0.f && m->com[1] == 0.f && m->com[2] == 0.f)) sflags = 0;
+    }
+    if (spec) *spec = sflags;
+
     qm.assign((size_t)quad_model_f4(NS) * 4, 0.f);
     auto F4 = [&](int idx) { return qm.data() + 4 * (size_t)idx; };
     const float h = sp->dt / (float)sp->substeps;
@@ -69,6 +113,7 @@ static inline int quad_build(const b2g_model *m, const b2g_sim_params *sp, std::
         A[3] = I6[3] - ms * c[0] * c[1];
         float *B = F4(6);
         B[0] = I6[4] - ms * c[0] * c[2]; B[1] = I6[5] - ms * c[1] * c[2]; B[2] = q_i2f(link_body[0]); B[3] = q_i2f(sp->substeps);
+        if (sflags & 2) { const float *rb = &ax[5 * 12]; A[0] = rb[0]; A[1] = rb[1]; A[2] = rb[2]; A[3] = rb[3]; B[0] = rb[4]; B[1] = 0.f; }
         if (link_sensor[0] >= 0) { const float *bp = m->body_pos + 3 * m->sensor_body[link_sensor[0]]; float *S = F4(7); S[0] = bp[0]; S[1] = bp[1]; S[2] = bp[2]; }
         F4(7)[3] = q_i2f(m->nsens | (m->nb << 8));
         F4(18)[0] = sp->ground_friction; F4(18)[1] = m->angular_damping; F4(18)[2] = m->linear_damping; F4(18)[3] = m->max_angular_velocity;
@@ -111,6 +156,7 @@ static inline int quad_build(const b2g_model *m, const b2g_sim_params *sp, std::
         for (int i = 0; i < 3; i++) L[27 + i] = R0[3 * i] * a[0] + R0[3 * i + 1] * a[1] + R0[3 * i + 2] * a[2];   // axis in the parent frame
         for (int c = 0; c < 3; c++) { L[30 + c] = m->lpos[3 * li + c]; L[33 + c] = m->com[3 * li + c]; }
         for (int c = 0; c < 6; c++) L[36 + c] = m->inertia[6 * li + c];
+        if (sflags & 1) { const float *a5 = &ax[5 * (l * NS + s)]; L[36] = a5[0]; L[37] = a5[1]; L[38] = a5[2]; L[39] = a5[3]; L[40] = a5[4]; L[41] = 0.f; }
         L[42] = m->mass[li];
         L[43] = m->armature[li] + h * m->damping[li] + h * h * m->stiffness[li];           // dg0
         L[44] = m->damping[li]; L[45] = m->stiffness[li];

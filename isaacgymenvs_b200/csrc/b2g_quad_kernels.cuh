@@ -10,14 +10,14 @@
 namespace b2g {
 
 // dynamic shared memory of the quad kernels: [park: quad_park_f4(NS) x BLOCK float4][tiles ...][quad model]
-template <int NS, bool HF>
-__device__ __forceinline__ QLane<NS, HF> make_qlane(const float4 *qm, const int16_t *hf, float4 *park_base, int block, int lane) {
-    QLane<NS, HF> L;
+template <int NS, bool HF, int SP>
+__device__ __forceinline__ QLane<NS, HF, SP> make_qlane(const float4 *qm, const int16_t *hf, float4 *park_base, int block, int lane) {
+    QLane<NS, HF, SP> L;
     L.qm = qm; L.hf = hf; L.park = park_base + threadIdx.x; L.pstride = block; L.lane = lane; L.env_mu = -1.f;
     return L;
 }
 
-template <int NS, bool HF, int BLOCK>
+template <int NS, bool HF, int SP, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) quad_simulate_kernel(const float4 *__restrict__ gqm, const int16_t *__restrict__ hf, Buffers B, int N, int substeps) {
     float4 *const park = b2g_dyn_smem;
     float4 *const qm = b2g_dyn_smem + quad_park_f4(NS) * BLOCK;
@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(BLOCK) quad_simulate_kernel(const float4 *__re
     const bool valid = env < N;
     const int e = valid ? env : N - 1;
     constexpr int nd = 4 * NS;
-    QLane<NS, HF> L = make_qlane<NS, HF>(qm, hf, park, BLOCK, lane);
+    QLane<NS, HF, SP> L = make_qlane<NS, HF, SP>(qm, hf, park, BLOCK, lane);
     float *const root_row = (float *)B.p[B2G_T_ROOT_STATE] + 13 * (size_t)e;
     RootState rs; load_root(root_row, rs);
     float2 *const d = (float2 *)B.p[B2G_T_DOF_STATE] + (size_t)e * nd;
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(BLOCK) quad_simulate_kernel(const float4 *__re
 #ifndef B2G_QUAD_MINBLOCKS
 #define B2G_QUAD_MINBLOCKS(BLOCK) ((BLOCK) == 128 ? 4 : ((BLOCK) == 64 ? 7 : 14))
 #endif
-template <int NS, int BLOCK, bool HOSTIO>
+template <int NS, int SP, int BLOCK, bool HOSTIO>
 __global__ void __launch_bounds__(BLOCK, B2G_QUAD_MINBLOCKS(BLOCK)) quad_loco_kernel(
     const float4 *__restrict__ gqm, Buffers B, const __grid_constant__ b2g_task_params P, const float *__restrict__ actions_in, int N, int substeps, TileArgs ta) {
     __shared__ alignas(8) uint64_t mbar, mbar2;
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(BLOCK, B2G_QUAD_MINBLOCKS(BLOCK)) quad_loco_ke
     mbar_wait(&mbar2, 0);
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-    QLane<NS, false> L = make_qlane<NS, false>(qm, nullptr, park, BLOCK, lane);
+    QLane<NS, false, SP> L = make_qlane<NS, false, SP>(qm, nullptr, park, BLOCK, lane);
     float *const row_root = s_root + 13 * el;
     float2 *const row_dof = reinterpret_cast<float2 *>(s_dof + 2 * nd * el);
     float *const row_act = s_act + nd * el;
@@ -189,19 +189,48 @@ __global__ void __launch_bounds__(BLOCK, B2G_QUAD_MINBLOCKS(BLOCK)) quad_loco_ke
     float *const obs = t_obs + (size_t)el * O;
     float *const obsc = g_obsc ? t_obsc + (size_t)el * O : nullptr;
 
-    // compute_observations (ant.py:374-408)
-    LocoRootObs ro;
-    loco_root_obs(P, rs.rp, rs.rq, rs.rv, rs.rw, false, ro);
-    const float prev_potentials = potentials;
-    potentials = ro.potentials;
+    // compute_observations (ant.py:374-408).  The three Euler / heading angles are three atan2f calls on different
+    // arguments: the lanes of the env take one each (same instruction stream, different data) and hand it to lane 0.
+    const float to_t[3] = {P.target[0] - rs.rp[0], P.target[1] - rs.rp[1], 0.f};
+    const float prev_potentials = potentials;                  // prev_potentials_new = potentials.clone(), ant.py:390
+    potentials = t_potential(to_t[0], to_t[1], P.dt);
+    const float isr[4] = {-0.f, -0.f, -0.f, 1.f};
+    float tq[4]; t_quat_mul(rs.rq, isr, tq);                   // compute_heading_and_up, torch_jit_utils.py:247-262
+    float ang_mine;
+    {
+        const float qx = tq[0], qy = tq[1], qz = tq[2], qw = tq[3];
+        // get_euler_xyz :175-195 (roll, yaw) and compute_rot :265-276 (walk_target_angle); lane 3 duplicates lane 0
+        const float ay = (lane == 1) ? 2.0f * (qw * qx + qy * qz) : (lane == 2) ? P.target[2] - rs.rp[2] : 2.0f * (qw * qz + qx * qy);
+        const float ax = (lane == 1) ? qw * qw - qx * qx - qy * qy + qz * qz : (lane == 2) ? P.target[0] - rs.rp[0] : qw * qw + qx * qx - qy * qy - qz * qz;
+        const float a = atan2f(ay, ax);
+        // torch.remainder(a, 2 pi) for a in [-pi, pi] (fmod leaves such an `a` unchanged); the walk angle is not wrapped
+        ang_mine = (lane != 2 && a < 0.f) ? a + 6.2831855f : a;
+    }
+    const float roll = __shfl_sync(0xffffffffu, ang_mine, (threadIdx.x & 28) | 1);
+    const float walk = __shfl_sync(0xffffffffu, ang_mine, (threadIdx.x & 28) | 2);
+    const float yaw = __shfl_sync(0xffffffffu, ang_mine, (threadIdx.x & 28));
     const float clipo = P.clip_obs;
     auto put = [&](int idx, float v) {
         obs[idx] = v;
         if (obsc) obsc[idx] = fminf(fmaxf(v, -clipo), clipo);
     };
+    float up_proj = 0.f, heading_proj = 0.f;
+    float up_vec[3], heading_vec[3];
     if (lane == 0) {
-#pragma unroll
-        for (int c = 0; c < 12; c++) put(c, ro.o[c]);
+        const float nrm = fmaxf(sqrtf(to_t[0] * to_t[0] + to_t[1] * to_t[1] + 0.f), 1e-9f);
+        const float td[3] = {to_t[0] / nrm, to_t[1] / nrm, 0.f / nrm};
+        const float b0[3] = {1.f, 0.f, 0.f}, b1[3] = {0.f, 0.f, 1.f};
+        t_quat_rotate(tq, b1, up_vec, 1.f);
+        t_quat_rotate(tq, b0, heading_vec, 1.f);
+        up_proj = up_vec[2];
+        heading_proj = (heading_vec[0] * td[0] + heading_vec[1] * td[1]) + heading_vec[2] * td[2];
+        float vloc[3], wloc[3];
+        t_quat_rotate(tq, rs.rv, vloc, -1.f);
+        t_quat_rotate(tq, rs.rw, wloc, -1.f);
+        put(0, rs.rp[2]);
+        put(1, vloc[0]); put(2, vloc[1]); put(3, vloc[2]);
+        put(4, wloc[0]); put(5, wloc[1]); put(6, wloc[2]);
+        put(7, yaw); put(8, roll); put(9, walk - yaw); put(10, up_proj); put(11, heading_proj);
     }
     // layout: ant.py:401-406  [12 | nd pos | nd vel | 6*nsens sensors | nd actions]
     const int o_pos = 12, o_vel = 12 + nd, o_sens = 12 + 2 * nd, o_act = o_sens + nsens6;
@@ -213,26 +242,38 @@ __global__ void __launch_bounds__(BLOCK, B2G_QUAD_MINBLOCKS(BLOCK)) quad_loco_ke
         const float ps = t_unscale(L.q[s], P.dof_limits_lower[d], P.dof_limits_upper[d]);
         const float vs = L.qd[s] * P.dof_vel_scale;
         put(o_pos + d, ps); put(o_vel + d, vs); put(o_act + d, a);
-        if (sens[s] >= 0 && o.sensor) {
+        if (sens[s] >= 0) {                                    // typed pointers: shared-memory loads of the staged tile, not generic ones
+            float sv[6];
+            if (stage_out) {
+                const float *sp_ = s_sens + nsens6 * el + 6 * sens[s];
 #pragma unroll
-            for (int c = 0; c < 6; c++) put(o_sens + 6 * sens[s] + c, o.sensor[6 * sens[s] + c] * P.contact_force_scale);
+                for (int c = 0; c < 6; c++) sv[c] = sp_[c];
+            } else {                                           // no simulate: the tensor as it stands (golden-vector mode)
+#pragma unroll
+                for (int c = 0; c < 6; c++) sv[c] = g_sens ? g_sens[(size_t)e * nsens6 + 6 * sens[s] + c] : 0.f;
+            }
+            if (stage_out || g_sens) {
+#pragma unroll
+                for (int c = 0; c < 6; c++) put(o_sens + 6 * sens[s] + c, sv[c] * P.contact_force_scale);
+            }
         }
         actions_cost += a * a;                                 // compute_ant_reward, ant.py:353-355
         at_limit += (ps > 0.99f) ? 1.f : 0.f;
         electricity += fabsf(a * vs);
     }
     {
-        const int rsens = q_f2i(qm[3].w);
-        if (lane == 0 && rsens >= 0 && o.sensor) {
+        const int rsens = q_f2i(qm[3].w);                      // a sensor on the base itself (not Ant): through the tensor
+        const float *sp_ = stage_out ? s_sens + nsens6 * el : (g_sens ? g_sens + (size_t)e * nsens6 : nullptr);
+        if (lane == 0 && rsens >= 0 && sp_) {
 #pragma unroll
-            for (int c = 0; c < 6; c++) put(o_sens + 6 * rsens + c, o.sensor[6 * rsens + c] * P.contact_force_scale);
+            for (int c = 0; c < 6; c++) put(o_sens + 6 * rsens + c, sp_[6 * rsens + c] * P.contact_force_scale);
         }
     }
     actions_cost = lane_sum<4>(actions_cost);
     electricity = lane_sum<4>(electricity);
     at_limit = lane_sum<4>(at_limit);
     if (lane == 0) {
-        const float heading_proj = ro.o[11], up_proj = ro.o[10], height = ro.o[0];
+        const float height = rs.rp[2];
         const float heading_reward = (heading_proj > 0.8f) ? P.heading_weight : P.heading_weight * heading_proj / 0.8f;
         const float up_reward = (up_proj > 0.93f) ? P.up_weight : 0.f;
         const float progress_reward = potentials - prev_potentials;
@@ -243,29 +284,35 @@ __global__ void __launch_bounds__(BLOCK, B2G_QUAD_MINBLOCKS(BLOCK)) quad_loco_ke
         if ((float)progress >= P.max_episode_length - 1.f) reset = 1;
         const uint8_t tout = (uint8_t)(((float)progress >= P.max_episode_length - 1.f) && reset != 0);   // vec_task.py:394
         t_rew[el] = total_r; t_reset[el] = reset; t_prog[el] = progress; t_pot[el] = potentials; t_ppot[el] = prev_potentials;
-        t_up[3 * el] = ro.up_vec[0]; t_up[3 * el + 1] = ro.up_vec[1]; t_up[3 * el + 2] = ro.up_vec[2];
-        t_head[3 * el] = ro.heading_vec[0]; t_head[3 * el + 1] = ro.heading_vec[1]; t_head[3 * el + 2] = ro.heading_vec[2];
+        t_up[3 * el] = up_vec[0]; t_up[3 * el + 1] = up_vec[1]; t_up[3 * el + 2] = up_vec[2];
+        t_head[3 * el] = heading_vec[0]; t_head[3 * el + 1] = heading_vec[1]; t_head[3 * el + 2] = heading_vec[2];
         t_to[el] = tout;
     }
     fence_async_smem();
     __syncthreads();
-    if (threadIdx.x == 0) {
+    // one bulk-async (TMA) store per output tensor; the 15 stores are dealt to the first lanes of the CTA's warps so that
+    // their issue (address arithmetic + UBLKCP each) runs in parallel instead of as one thread's serial tail
+    if ((threadIdx.x & 31) == 0) {
         const size_t e0 = (size_t)env0;
         float *const g_act_out = (float *)B.p[B2G_T_ACTIONS];
-        bulk_s2g((float *)B.p[B2G_T_ROOT_STATE] + e0 * 13, s_root, EPB * 13 * 4);
-        bulk_s2g((float *)B.p[B2G_T_DOF_STATE] + e0 * nd * 2, s_dof, (uint32_t)(EPB * nd * 8));
-        if (g_act_out) bulk_s2g(g_act_out + e0 * nd, s_act, (uint32_t)(EPB * nd * 4));
-        if (stage_out && g_sens && nsens6) bulk_s2g(g_sens + e0 * nsens6, s_sens, (uint32_t)(EPB * nsens6 * 4));
-        bulk_s2g(g_obs + e0 * O, t_obs, (uint32_t)(EPB * O * 4));
-        if (g_obsc) bulk_s2g(g_obsc + e0 * O, t_obsc, (uint32_t)(EPB * O * 4));
-        bulk_s2g((float *)B.p[B2G_T_REW] + e0, t_rew, EPB * 4);
-        bulk_s2g(pot_b + e0, t_pot, EPB * 4);
-        bulk_s2g(ppot_b + e0, t_ppot, EPB * 4);
-        if (B.p[B2G_T_UP_VEC]) bulk_s2g((float *)B.p[B2G_T_UP_VEC] + 3 * e0, t_up, EPB * 12);
-        if (B.p[B2G_T_HEADING_VEC]) bulk_s2g((float *)B.p[B2G_T_HEADING_VEC] + 3 * e0, t_head, EPB * 12);
-        bulk_s2g(reset_b + e0, t_reset, EPB * 8);
-        bulk_s2g(progress_b + e0, t_prog, EPB * 8);
-        if (B.p[B2G_T_TIMEOUT]) bulk_s2g((uint8_t *)B.p[B2G_T_TIMEOUT] + e0, t_to, EPB);
+        constexpr int NW = BLOCK / 32;
+        const int wq = threadIdx.x >> 5;
+        int k = 0;
+        auto mine = [&]() { return (k++ % NW) == wq; };
+        if (mine()) bulk_s2g(g_obs + e0 * O, t_obs, (uint32_t)(EPB * O * 4));
+        if (g_obsc && mine()) bulk_s2g(g_obsc + e0 * O, t_obsc, (uint32_t)(EPB * O * 4));
+        if (mine()) bulk_s2g((float *)B.p[B2G_T_ROOT_STATE] + e0 * 13, s_root, EPB * 13 * 4);
+        if (mine()) bulk_s2g((float *)B.p[B2G_T_DOF_STATE] + e0 * nd * 2, s_dof, (uint32_t)(EPB * nd * 8));
+        if (g_act_out && mine()) bulk_s2g(g_act_out + e0 * nd, s_act, (uint32_t)(EPB * nd * 4));
+        if (stage_out && g_sens && nsens6 && mine()) bulk_s2g(g_sens + e0 * nsens6, s_sens, (uint32_t)(EPB * nsens6 * 4));
+        if (mine()) bulk_s2g((float *)B.p[B2G_T_REW] + e0, t_rew, EPB * 4);
+        if (mine()) bulk_s2g(pot_b + e0, t_pot, EPB * 4);
+        if (mine()) bulk_s2g(ppot_b + e0, t_ppot, EPB * 4);
+        if (B.p[B2G_T_UP_VEC] && mine()) bulk_s2g((float *)B.p[B2G_T_UP_VEC] + 3 * e0, t_up, EPB * 12);
+        if (B.p[B2G_T_HEADING_VEC] && mine()) bulk_s2g((float *)B.p[B2G_T_HEADING_VEC] + 3 * e0, t_head, EPB * 12);
+        if (mine()) bulk_s2g(reset_b + e0, t_reset, EPB * 8);
+        if (mine()) bulk_s2g(progress_b + e0, t_prog, EPB * 8);
+        if (B.p[B2G_T_TIMEOUT] && mine()) bulk_s2g((uint8_t *)B.p[B2G_T_TIMEOUT] + e0, t_to, EPB);
         bulk_commit_wait();
     }
     if (HOSTIO) {                  // host copies of what VecTask.step returns (vec_task.py:402-408), straight over PCIe
@@ -301,7 +348,7 @@ __global__ void __launch_bounds__(BLOCK) quad_anymal_physics_kernel(const float4
     const int env = gt >> 2, lane = gt & 3;
     const bool valid = env < N;
     const int e = valid ? env : N - 1;
-    QLane<NS, HF> L = make_qlane<NS, HF>(qm, hf, park, BLOCK, lane);
+    QLane<NS, HF, 0> L = make_qlane<NS, HF, 0>(qm, hf, park, BLOCK, lane);
     const float *envmu = (const float *)B.p[B2G_T_ENV_FRICTION];
     if (envmu) L.env_mu = 0.5f * (envmu[e] + qm[18].x);
     RootState rs; load_root((const float *)B.p[B2G_T_ROOT_STATE] + 13 * (size_t)e, rs);

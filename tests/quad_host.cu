@@ -8,14 +8,14 @@
 
 using namespace b2g;
 
-template <int NS, bool HF>
+template <int NS, bool HF, int SP>
 static void run(const std::vector<float> &qmv, const int16_t *hf, int N, int substeps, float *root, float *dof, const float *act,
                 float *sensor, int nsens, float *dof_force, float *net_contact, int nb, const int *leg_link) {
     const float4 *qm = reinterpret_cast<const float4 *>(qmv.data());
     const int nd = 4 * NS;
     std::vector<float4> park((size_t)4 * quad_park_f4(NS));
     for (int e = 0; e < N; e++) {
-        QLane<NS, HF> L[4];
+        QLane<NS, HF, SP> L[4];
         RootState rs;
         const float *r = root + 13 * (size_t)e;
         for (int c = 0; c < 3; c++) { rs.rp[c] = r[c]; rs.rv[c] = r[7 + c]; rs.rw[c] = r[10 + c]; }
@@ -43,7 +43,7 @@ static void run(const std::vector<float> &qmv, const int16_t *hf, int N, int sub
                 for (int c = 0; c < 3; c++) { pa[c] += a[c]; pl[c] += b[c]; }
             }
             float awr[3], alr[3];
-            QLane<NS, HF>::solve_base(IA, pa, pl, awr, alr);
+            QLane<NS, HF, SP>::solve_base(IA, pa, pl, awr, alr);
             if (LAST && L[0].root_emits(o)) {
                 float F[3] = {0, 0, 0}, T[3] = {0, 0, 0};
                 for (int l = 0; l < 4; l++) {
@@ -66,17 +66,21 @@ static void run(const std::vector<float> &qmv, const int16_t *hf, int N, int sub
     }
 }
 
-// returns NS (2 / 3) when the model runs on the quad path, 0 when it does not fit, <0 on error
+// returns NS (2 / 3) when the model runs on the quad path, 0 when it does not fit, <0 on error.  want_spec: 3 = let the
+// builder use the axisymmetric-inertia specialisation when the model allows it, 0 = general layout; *spec_out = what was used
 extern "C" int quad_host_simulate(const b2g_model *m, const b2g_sim_params *sp, int N, float *root, float *dof, const float *act,
-                                  float *sensor, float *dof_force, float *net_contact) {
+                                  float *sensor, float *dof_force, float *net_contact, int want_spec, int *spec_out) {
     std::vector<float> qm;
-    int leg_link[12];
-    const int NS = quad_build(m, sp, qm, leg_link);
+    int leg_link[12], spec = 0;
+    const int NS = quad_build(m, sp, qm, leg_link, &spec, want_spec);
+    if (spec_out) *spec_out = spec;
     if (NS == 0) return 0;
     const bool hf = sp->hf_samples != nullptr;
-    if (NS == 2 && !hf) run<2, false>(qm, nullptr, N, sp->substeps, root, dof, act, sensor, m->nsens, dof_force, net_contact, m->nb, leg_link);
-    else if (NS == 2) run<2, true>(qm, sp->hf_samples, N, sp->substeps, root, dof, act, sensor, m->nsens, dof_force, net_contact, m->nb, leg_link);
-    else if (NS == 3 && !hf) run<3, false>(qm, nullptr, N, sp->substeps, root, dof, act, sensor, m->nsens, dof_force, net_contact, m->nb, leg_link);
-    else run<3, true>(qm, sp->hf_samples, N, sp->substeps, root, dof, act, sensor, m->nsens, dof_force, net_contact, m->nb, leg_link);
+#define RUN(NS_, HF_, SP_) run<NS_, HF_, SP_>(qm, HF_ ? sp->hf_samples : nullptr, N, sp->substeps, root, dof, act, sensor, m->nsens, dof_force, net_contact, m->nb, leg_link)
+    if (NS == 2 && !hf) { if (spec == 3) RUN(2, false, 3); else RUN(2, false, 0); }
+    else if (NS == 2) { if (spec == 3) RUN(2, true, 3); else RUN(2, true, 0); }
+    else if (NS == 3 && !hf) { if (spec == 3) RUN(3, false, 3); else RUN(3, false, 0); }
+    else { if (spec == 3) RUN(3, true, 3); else RUN(3, true, 0); }
+#undef RUN
     return NS;
 }

@@ -441,7 +441,8 @@ def test_generic_gym_api_path_matches_fused_step():
     sim = gym.create_sim(0, -1, gymapi.SIM_PHYSX, sp)
     pp = gymapi.PlaneParams(); pp.static_friction = pp.dynamic_friction = 1.0
     gym.add_ground(sim, pp)
-    asset = gym.load_asset(sim, "/no/such/checkout/assets/mjcf", "nv_ant.xml", gymapi.AssetOptions())
+    ao = gymapi.AssetOptions(); ao.angular_damping = 0.0                        # as ant.py:151 sets it (the AssetOptions default is 0.5)
+    asset = gym.load_asset(sim, "/no/such/checkout/assets/mjcf", "nv_ant.xml", ao)
     assert gym.get_asset_dof_count(asset) == 8 and gym.get_asset_rigid_body_count(asset) == 9
     gears = torch.tensor([p.motor_effort for p in gym.get_asset_actuator_properties(asset)], device=env.device)
     for name in [s for s in gym.get_asset_rigid_body_names(asset) if "foot" in s]:

@@ -54,7 +54,8 @@ def _random_states(m, n, rng, zlo, zhi):
     return root, np.stack([qpos, qvel], -1)
 
 
-def _host_simulate(lib, m, dt, sub, root32, dof32, tau32, hfield=None, hf_scale=1.0, hf_vscale=1.0, hf_origin=(0.0, 0.0), ground_mu=1.0):
+def _host_simulate(lib, m, dt, sub, root32, dof32, tau32, hfield=None, hf_scale=1.0, hf_vscale=1.0, hf_origin=(0.0, 0.0), ground_mu=1.0, want_spec=3,
+                   spec_out=None):
     cm, keep = engine.pack_model(m)
     sp = engine.CSimParams()
     sp.dt, sp.substeps = dt, sub
@@ -72,7 +73,10 @@ def _host_simulate(lib, m, dt, sub, root32, dof32, tau32, hfield=None, hf_scale=
     dfrc = np.zeros((n, m.ndof), np.float32)
     nc = np.zeros((n, m.nb, 3), np.float32)
     p = lambda a: C.c_void_p(a.ctypes.data)
-    ns = lib.quad_host_simulate(C.byref(cm), C.byref(sp), C.c_int(n), p(root32), p(dof32), p(tau32), p(sensor), p(dfrc), p(nc))
+    spec = C.c_int(-1)
+    ns = lib.quad_host_simulate(C.byref(cm), C.byref(sp), C.c_int(n), p(root32), p(dof32), p(tau32), p(sensor), p(dfrc), p(nc), C.c_int(want_spec), C.byref(spec))
+    if spec_out is not None:
+        spec_out.append(spec.value)
     return ns, sensor[:, :len(m.sensor_body)], dfrc, nc
 
 
@@ -91,9 +95,13 @@ def _compare(m, rg, dg, out_g, r64, d64, out):
     assert np.abs(nc - out["contact_force"]).max() < 2e-3 * max(1.0, np.abs(out["contact_force"]).max())
 
 
-@pytest.mark.parametrize("name,zlo,zhi,tscale,dt,sub,damp", [("ant", 0.15, 0.8, 15.0, 0.0166, 2, None), ("anymal", 0.3, 0.9, 40.0, 0.005, 1, None),
-                                                               ("ant", 0.15, 0.8, 15.0, 0.0166, 2, (0.8, 0.5, 3.0))])
-def test_quad_substep_matches_oracle(name, zlo, zhi, tscale, dt, sub, damp):
+@pytest.mark.parametrize("name,zlo,zhi,tscale,dt,sub,damp,want,got", [
+    ("ant", 0.15, 0.8, 15.0, 0.0166, 2, None, 3, 3),          # Ant: capsule links + symmetric torso -> the axisymmetric specialisation
+    ("ant", 0.15, 0.8, 15.0, 0.0166, 2, None, 0, 0),          # ... and the general layout on the same model
+    ("anymal", 0.3, 0.9, 40.0, 0.005, 1, None, 3, 0),         # ANYmal: general inertias -> the builder falls back by itself
+    ("ant", 0.15, 0.8, 15.0, 0.0166, 2, (0.8, 0.5, 3.0), 3, 3),
+    ("ant", 0.15, 0.8, 15.0, 0.0166, 2, (0.8, 0.5, 3.0), 0, 0)])
+def test_quad_substep_matches_oracle(name, zlo, zhi, tscale, dt, sub, damp, want, got):
     lib = _lib()
     m = _model(name)
     if damp:          # AssetOptions.angular_damping / linear_damping / max_angular_velocity, exaggerated so that they matter in one step
@@ -106,8 +114,9 @@ def test_quad_substep_matches_oracle(name, zlo, zhi, tscale, dt, sub, damp):
     r64 = root32.astype(np.float64); d64 = dof32.astype(np.float64); t64 = tau32.astype(np.float64)
     orc = OracleSim(m, dt, sub, G, ground_mu=1.0, threads=8)
     out = orc.simulate(r64, d64, t64)
-    ns, sensor, dfrc, nc = _host_simulate(lib, m, dt, sub, root32, dof32, tau32)
-    assert ns == (2 if name == "ant" else 3)
+    used = []
+    ns, sensor, dfrc, nc = _host_simulate(lib, m, dt, sub, root32, dof32, tau32, want_spec=want, spec_out=used)
+    assert ns == (2 if name == "ant" else 3) and used == [got]
     _compare(m, root32.astype(np.float64), dof32.astype(np.float64), (sensor, dfrc, nc), r64, d64, out)
     # contacts were exercised
     assert (np.abs(out["contact_force"]).max(-1) > 0).mean() > 0.05
