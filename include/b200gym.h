@@ -142,7 +142,9 @@ enum {
     B2G_T_TERRAIN_ORIGINS = 30,/* f32 (rows,cols,3) */
     B2G_T_NOISE_SCALE = 31,    /* f32 (O)   noise_scale_vec, anymal_terrain.py:174-186 */
     B2G_T_BASE_SCRATCH = 32,   /* f32 (N,12) base_lin_vel, base_ang_vel, projected_gravity handed from kernel 1 to 2 */
-    B2G_T_REDUCE_SCRATCH = 33, /* f32 (>= 1024 + 16) per-block partials of the reset-set norm (anymal_terrain.py:432) + extras sums */
+    B2G_T_REDUCE_SCRATCH = 33, /* f32 (>= 1024 + 48) per-block partials of the reset-set norm (anymal_terrain.py:432); then [0,13) sums of
+                                  the reset envs' episode sums, 13 their count, 15 ticket, [16,29) extras['episode'] means, 29 mean terrain level,
+                                  32 running sum of TERRAIN_LEVELS (the caller initialises it) */
     B2G_T_ENV_FRICTION = 34,   /* f32 (N)   per-env shape friction (friction buckets, anymal_terrain.py:235-281); NULL = the model's */
     /* ShadowHand state (shadow_hand.py:183-200,398-408) */
     B2G_T_GOAL_STATES = 35,    /* f32 (N,13)  goal_states */
@@ -152,7 +154,12 @@ enum {
     B2G_T_RESET_GOAL = 39,     /* i64 (N)     reset_goal_buf */
     B2G_T_GOAL_RESET_COUNT = 40,/* i32 (N)    per-env goal-only reset counter feeding the Philox stream */
     B2G_T_STATES = 41,         /* f32 (N,S)  states_buf, vec_task.py:306 (asymmetric observations; unclipped, get_state clamps) */
-    B2G_T_COUNT = 42
+    /* physical domain randomisation (vec_task.py:720-828 writes these per actor through gym.set_actor_*_properties; here they
+     * are per-env parameter arrays the step kernels read).  NULL = the model's own values.  Implemented by the four-chain
+     * ("quad") kernels: Ant, ANYmal; other articulations answer B2G_E_UNSUPPORTED when they are bound. */
+    B2G_T_ENV_MASS_SCALE = 42, /* f32 (N,L)   factor on every link's MASS (inertia tensor unchanged: rigid_body_properties.mass) */
+    B2G_T_ENV_DOF_PROPS = 43,  /* f32 (N,D,4) damping, stiffness, lower, upper of every DOF (dof_properties) */
+    B2G_T_COUNT = 44
 };
 
 /* fused per-task control steps */

@@ -31,6 +31,20 @@ def build(force=False, verbose=False, extra=()):
     return OUT
 
 
+def build_exact_trig(force=False):
+    """The same library with B2G_FAST_TRIG=0 (sincosf instead of __sincosf): only tests/test_gpu_parity2.py loads it, to bound
+    the fast-trigonometry build against it (B2G_LIB selects it)."""
+    out = os.path.join(HERE, "libb200gym_exacttrig.so")
+    if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in DEPS):
+        return out
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--expt-relaxed-constexpr",
+                           "-Xcompiler", "-fPIC", "-shared", "-DB2G_FAST_TRIG=0", "-o", out, SRC])
+    return out
+
+
 if __name__ == "__main__":
     build(force=True, verbose="-v" in sys.argv)
+    if "--exact-trig" in sys.argv:
+        build_exact_trig(force=True)
     print(OUT)

@@ -922,9 +922,14 @@ extern "C" int b2g_bind(b2g_sim *s, int32_t slot, void *ptr, size_t bytes) {
         case B2G_T_RESET: case B2G_T_PROGRESS: need = (size_t)N * 8; break;
         case B2G_T_TIMEOUT: need = (size_t)N; break;
         case B2G_T_UP_VEC: case B2G_T_HEADING_VEC: need = (size_t)N * 12; break;
+        case B2G_T_ENV_MASS_SCALE: need = (size_t)N * (nd + 1) * 4; break;
+        case B2G_T_ENV_DOF_PROPS: need = (size_t)N * nd * 16; break;
+        case B2G_T_ENV_FRICTION: need = (size_t)N * 4; break;
         default: need = 0; break;   // ACTIONS / OBS / OBS_CLIPPED are checked against the task in b2g_set_task
     }
     if (ptr && bytes < need) return fail(B2G_E_INVALID, "b2g_bind: buffer smaller than the tensor's layout requires");
+    if (ptr && (slot == B2G_T_ENV_MASS_SCALE || slot == B2G_T_ENV_DOF_PROPS) && !s->quad_ns)
+        return fail(B2G_E_UNSUPPORTED, "per-env link masses / joint properties are read by the four-chain (quad) kernels only (Ant, ANYmal)");
     s->buf.p[slot] = ptr; s->buf_bytes[slot] = bytes;
     return B2G_OK;
 }
@@ -1143,7 +1148,7 @@ static int anymal_step(b2g_sim *s, const float *actions, void *stream) {
     const int N = s->num_envs, blk = 128, grid = (N * 4 + blk - 1) / blk;
     if (s->block != 128) return fail(B2G_E_UNSUPPORTED, "AnymalTerrain: unexpected CTA size");
     if (grid > REDUCE_PARTIALS) return fail(B2G_E_INVALID, "AnymalTerrain: too many blocks for the reduction scratch (num_envs <= 32768)");
-    if (s->buf_bytes[B2G_T_REDUCE_SCRATCH] < (REDUCE_PARTIALS + 16) * 4) return fail(B2G_E_INVALID, "REDUCE_SCRATCH too small");
+    if (s->buf_bytes[B2G_T_REDUCE_SCRATCH] < (REDUCE_PARTIALS + 48) * 4) return fail(B2G_E_INVALID, "REDUCE_SCRATCH too small");
     s->step_counter++;                                   // common_step_counter += 1 (:459) before the push test
     if (s->quad_ns == 3) {                               // the specialised sub-step (b2g_quad.cuh), joint state in registers
         const size_t dyn = ((size_t)quad_park_f4(3) * 128 + quad_model_f4(3)) * sizeof(float4);

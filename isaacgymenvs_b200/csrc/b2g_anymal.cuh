@@ -196,6 +196,8 @@ __global__ void __launch_bounds__(BLOCK) anymal_reset_obs_kernel(Buffers B, cons
     // reset_only (VecTask.reset_done, vec_task.py:440-455 -> reset_idx :384-425 of the flagged envs, no step): the norm
     // over the reset set is summed here from the flags themselves; observations and last_* are left to the next step
     __shared__ float s_norm;
+    __shared__ int s_done;
+    if (threadIdx.x == 0) s_done = 0;
     if (threadIdx.x < 32) {
         const float *red = (const float *)B.p[B2G_T_REDUCE_SCRATCH];
         float t = 0.f;
@@ -243,6 +245,7 @@ __global__ void __launch_bounds__(BLOCK) anymal_reset_obs_kernel(Buffers B, cons
                     level -= (dist < s_norm * P.max_episode_length_s * 0.25f) ? 1 : 0;
                     level += (dist > P.env_length / 2.f) ? 1 : 0;
                     level = (level < 0 ? 0 : level) % P.env_rows;
+                    atomicAdd((float *)B.p[B2G_T_REDUCE_SCRATCH] + REDUCE_PARTIALS + 32, (float)(level - lv[e]));   // running sum of terrain_levels (integer-valued)
                     lv[e] = level;
                     const float *to = (const float *)B.p[B2G_T_TERRAIN_ORIGINS] + 3 * ((size_t)level * P.env_cols + ty);
                     eo[0] = to[0]; eo[1] = to[1]; eo[2] = to[2];
@@ -351,6 +354,29 @@ __global__ void __launch_bounds__(BLOCK) anymal_reset_obs_kernel(Buffers B, cons
     if (lane == 0) {
         uint8_t *to = (uint8_t *)B.p[B2G_T_TIMEOUT];                                // vec_task.py:394
         if (to) to[e] = (uint8_t)((progress_b[e] >= (long long)P.max_episode_length - 1) && reset_b[e] != 0);
+    }
+    // extras["episode"] (reset_idx :420-425): the last warp of the grid to get here turns this step's sums over the reset
+    // envs into the per-second means the task publishes (kept as they are when no env was reset), so that the host side
+    // of VecTask.step issues no torch kernels for them.  Layout after the 1024 partials: [0,13) sums, 13 count,
+    // 15 ticket, [16,29) means, 29 mean terrain level, 32 running sum of terrain_levels.
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) {
+        const int first_env = blockIdx.x * (BLOCK / L);
+        const int nwarps = min(BLOCK / 32, (N - first_env) * (L / 32));            // warps of this block that own an env (L == 32)
+        __threadfence();
+        if (atomicAdd(&s_done, 1) == nwarps - 1) {
+            float *red = (float *)B.p[B2G_T_REDUCE_SCRATCH] + REDUCE_PARTIALS;
+            unsigned *ticket = reinterpret_cast<unsigned *>(red + 15);
+            if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+                __threadfence();
+                const float cnt = atomicAdd(red + 13, 0.f);
+                if (cnt > 0.f) {
+                    for (int k = 0; k < 13; k++) red[16 + k] = atomicAdd(red + k, 0.f) / cnt / P.max_episode_length_s;
+                    red[29] = atomicAdd(red + 32, 0.f) / (float)N;
+                }
+                *ticket = 0u;
+            }
+        }
     }
 }
 

@@ -81,6 +81,10 @@ struct QLane {
     int pstride;
     int lane;
     float env_mu;             // >= 0: this env's combined friction (friction buckets), else the sphere's own
+    // physical domain randomisation (null = the model's values): this env's per-link mass factors (nl) and per-DOF
+    // (damping, stiffness, lower, upper) (nd float4)
+    const float *dr_mass;
+    const float4 *dr_dof;
     // joint state and actuation of this lane's chain
     float q[NS], qd[NS], act[NS];
     // carried from the sweeps to the acceleration pass
@@ -279,7 +283,13 @@ struct QLane {
 #pragma unroll
                 for (int c = 0; c < 3; c++) { vw[c] = vwp[c] + wq[c]; vl[c] = vlp[c] + slq[c]; }
                 // ---- joint force: explicit part + implicit diagonal (linear terms at the end of the sub-step)
-                const float4 k10 = LK(s, 10), k11 = LK(s, 11), k12 = LK(s, 12);
+                float4 k10 = LK(s, 10), k11 = LK(s, 11);
+                const float4 k12 = LK(s, 12);
+                if (dr_dof || dr_mass) {                              // per-env joint properties / link mass (domain randomisation)
+                    const int dof = q_f2i(LK(s, 16).w);
+                    if (dr_dof) { k11 = dr_dof[dof]; k10.w = LK(s, 17).x + h * k11.x + h * h * k11.y; }
+                    if (dr_mass) k10.z *= dr_mass[dof + 1];
+                }
                 {
                     const float qp = q[s] + h * qds;
                     float f = -k11.x * qds - k11.y * qp + fminf(fmaxf(act[s], -k12.x), k12.x);
@@ -364,11 +374,12 @@ struct QLane {
             const float xr[3] = {0.f, 0.f, 0.f};
             const float on = (lane == 0) ? 1.f : 0.f;
             const float *vw = rs.rw, *vl = rs.rv;
+            const float msc = dr_mass ? dr_mass[0] : 1.f;             // domain randomisation: the base's mass factor
             if (SP & 2) {
                 // axisymmetric base with its COM at the origin: A = a 1 + bm (R u)(R u)^T, no first moment
                 const float ul[3] = {H5.x, H5.y, H5.z};
                 float uw[3]; matvec(Rr, ul, uw);
-                const float am = on * H5.w, bm = on * H6.x, mo = on * H4.w;
+                const float am = on * H5.w, bm = on * H6.x, mo = on * H4.w * msc;
                 const float s_ = bm * dot3(uw, vw);
                 const float nO[3] = {am * vw[0] + s_ * uw[0], am * vw[1] + s_ * uw[1], am * vw[2] + s_ * uw[2]};     // A vw
                 float a1[3], a3[3];
@@ -381,8 +392,14 @@ struct QLane {
                 IA[15] += mo; IA[16] += mo; IA[17] += mo;
             } else {
                 // about the root origin directly: A = R Ab R^T, first moment hm = R (m com)
-                float A[6]; rotate_inertia(Rr, H5.x, H5.y, H5.z, H5.w, H6.x, H6.y, A);
-                const float mass = H4.w;
+                float Ab[6] = {H5.x, H5.y, H5.z, H5.w, H6.x, H6.y};
+                const float mass = H4.w * msc;
+                if (dr_mass) {                                        // Ab = Ic + m (c^2 1 - c c^T): the parallel-axis part follows the mass
+                    const float dm = mass - H4.w, c2 = H4.x * H4.x + H4.y * H4.y + H4.z * H4.z;
+                    Ab[0] += dm * (c2 - H4.x * H4.x); Ab[1] += dm * (c2 - H4.y * H4.y); Ab[2] += dm * (c2 - H4.z * H4.z);
+                    Ab[3] -= dm * H4.x * H4.y; Ab[4] -= dm * H4.x * H4.z; Ab[5] -= dm * H4.y * H4.z;
+                }
+                float A[6]; rotate_inertia(Rr, Ab[0], Ab[1], Ab[2], Ab[3], Ab[4], Ab[5], A);
                 const float cb[3] = {H4.x * mass, H4.y * mass, H4.z * mass};
                 float hm[3]; matvec(Rr, cb, hm);
                 // momentum about O: n = A vw + hm x vl ; l = m vl - hm x vw
@@ -417,11 +434,15 @@ struct QLane {
             }
             const int ncp = q_f2i(H3.z);
             float dummy[3];
+            // software-pipelined: the next sphere's constants are in flight while this one is processed
+            float4 cp = qm[8 + lane];
+            float mu = reinterpret_cast<const float *>(qm + 16)[lane];
 #pragma unroll 1
             for (int k = lane; k < ncp; k += 4) {
-                const float4 cp = qm[8 + k];
-                const float mu = reinterpret_cast<const float *>(qm + 16)[k];
+                const float4 cpn = qm[8 + ((k + 4) & (QROOT_CP - 1))];
+                const float mun = reinterpret_cast<const float *>(qm + 16)[(k + 4) & (QROOT_CP - 1)];
                 sphere<true>(cp, mu, rs.rp, Rr, xr, rs.rw, rs.rv, IA, pa, pl, dummy, dummy, dummy, dummy);
+                cp = cpn; mu = mun;
             }
         }
     }

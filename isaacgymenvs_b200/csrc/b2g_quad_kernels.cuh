@@ -14,7 +14,19 @@ template <int NS, bool HF, int SP>
 __device__ __forceinline__ QLane<NS, HF, SP> make_qlane(const float4 *qm, const int16_t *hf, float4 *park_base, int block, int lane) {
     QLane<NS, HF, SP> L;
     L.qm = qm; L.hf = hf; L.park = park_base + threadIdx.x; L.pstride = block; L.lane = lane; L.env_mu = -1.f;
+    L.dr_mass = nullptr; L.dr_dof = nullptr;
     return L;
+}
+
+// per-env physical parameters (domain randomisation tensors; null = the model's own)
+template <class QL>
+__device__ __forceinline__ void attach_env_params(QL &L, const Buffers &B, int e, int nd) {
+    const float *ms = (const float *)B.p[B2G_T_ENV_MASS_SCALE];
+    const float4 *dp = (const float4 *)B.p[B2G_T_ENV_DOF_PROPS];
+    const float *envmu = (const float *)B.p[B2G_T_ENV_FRICTION];
+    if (ms) L.dr_mass = ms + (size_t)e * (nd + 1);
+    if (dp) L.dr_dof = dp + (size_t)e * nd;
+    if (envmu) L.env_mu = 0.5f * (envmu[e] + L.qm[18].x);             // PhysX default combine mode: the average of the two materials
 }
 
 template <int NS, bool HF, int SP, int BLOCK>
@@ -29,6 +41,7 @@ __global__ void __launch_bounds__(BLOCK) quad_simulate_kernel(const float4 *__re
     const int e = valid ? env : N - 1;
     constexpr int nd = 4 * NS;
     QLane<NS, HF, SP> L = make_qlane<NS, HF, SP>(qm, hf, park, BLOCK, lane);
+    attach_env_params(L, B, e, nd);
     float *const root_row = (float *)B.p[B2G_T_ROOT_STATE] + 13 * (size_t)e;
     RootState rs; load_root(root_row, rs);
     float2 *const d = (float2 *)B.p[B2G_T_DOF_STATE] + (size_t)e * nd;
@@ -111,13 +124,15 @@ __global__ void __launch_bounds__(BLOCK, B2G_QUAD_MINBLOCKS(BLOCK)) quad_loco_ke
     const long long reset_in = reset_b[e];
     const float potentials_in = pot_b[e];
     int *const rc = (int *)B.p[B2G_T_RESET_COUNT];
-    uint32_t count = 0;
-    if (reset_in != 0) count = (uint32_t)rc[e];              // read here, written after the physics: no intra-warp race
+    // read here (unconditionally: a load that depended on reset_in would stall the prologue on it), written after the
+    // physics by lane 0: no intra-warp race
+    const uint32_t count = (uint32_t)rc[e];
     mbar_wait(&mbar, 0);
     mbar_wait(&mbar2, 0);
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     QLane<NS, false, SP> L = make_qlane<NS, false, SP>(qm, nullptr, park, BLOCK, lane);
+    attach_env_params(L, B, e, nd);
     float *const row_root = s_root + 13 * el;
     float2 *const row_dof = reinterpret_cast<float2 *>(s_dof + 2 * nd * el);
     float *const row_act = s_act + nd * el;
@@ -290,30 +305,37 @@ __global__ void __launch_bounds__(BLOCK, B2G_QUAD_MINBLOCKS(BLOCK)) quad_loco_ke
     }
     fence_async_smem();
     __syncthreads();
-    // one bulk-async (TMA) store per output tensor; the 15 stores are dealt to the first lanes of the CTA's warps so that
-    // their issue (address arithmetic + UBLKCP each) runs in parallel instead of as one thread's serial tail
-    if ((threadIdx.x & 31) == 0) {
+    // one bulk-async (TMA) store per output tensor.  The stores are dealt to the FIRST THREAD of each warp at compile time
+    // (`threadIdx.x == 32 w` branches, each a single-thread region the compiler keeps on the uniform datapath): their issue
+    // -- address arithmetic + UBLKCP each -- runs in parallel instead of as one thread's serial tail
+    {
         const size_t e0 = (size_t)env0;
         float *const g_act_out = (float *)B.p[B2G_T_ACTIONS];
         constexpr int NW = BLOCK / 32;
-        const int wq = threadIdx.x >> 5;
-        int k = 0;
-        auto mine = [&]() { return (k++ % NW) == wq; };
-        if (mine()) bulk_s2g(g_obs + e0 * O, t_obs, (uint32_t)(EPB * O * 4));
-        if (g_obsc && mine()) bulk_s2g(g_obsc + e0 * O, t_obsc, (uint32_t)(EPB * O * 4));
-        if (mine()) bulk_s2g((float *)B.p[B2G_T_ROOT_STATE] + e0 * 13, s_root, EPB * 13 * 4);
-        if (mine()) bulk_s2g((float *)B.p[B2G_T_DOF_STATE] + e0 * nd * 2, s_dof, (uint32_t)(EPB * nd * 8));
-        if (g_act_out && mine()) bulk_s2g(g_act_out + e0 * nd, s_act, (uint32_t)(EPB * nd * 4));
-        if (stage_out && g_sens && nsens6 && mine()) bulk_s2g(g_sens + e0 * nsens6, s_sens, (uint32_t)(EPB * nsens6 * 4));
-        if (mine()) bulk_s2g((float *)B.p[B2G_T_REW] + e0, t_rew, EPB * 4);
-        if (mine()) bulk_s2g(pot_b + e0, t_pot, EPB * 4);
-        if (mine()) bulk_s2g(ppot_b + e0, t_ppot, EPB * 4);
-        if (B.p[B2G_T_UP_VEC] && mine()) bulk_s2g((float *)B.p[B2G_T_UP_VEC] + 3 * e0, t_up, EPB * 12);
-        if (B.p[B2G_T_HEADING_VEC] && mine()) bulk_s2g((float *)B.p[B2G_T_HEADING_VEC] + 3 * e0, t_head, EPB * 12);
-        if (mine()) bulk_s2g(reset_b + e0, t_reset, EPB * 8);
-        if (mine()) bulk_s2g(progress_b + e0, t_prog, EPB * 8);
-        if (B.p[B2G_T_TIMEOUT] && mine()) bulk_s2g((uint8_t *)B.p[B2G_T_TIMEOUT] + e0, t_to, EPB);
-        bulk_commit_wait();
+        auto issue = [&](int w) {
+            int k = 0;
+#define B2G_ST(COND, DST, SRC, BYTES) do { if ((k++ % NW) == w) { if (COND) bulk_s2g(DST, SRC, BYTES); } } while (0)
+            B2G_ST(true, g_obs + e0 * O, t_obs, (uint32_t)(EPB * O * 4));
+            B2G_ST(g_obsc != nullptr, g_obsc + e0 * O, t_obsc, (uint32_t)(EPB * O * 4));
+            B2G_ST(true, (float *)B.p[B2G_T_ROOT_STATE] + e0 * 13, s_root, EPB * 13 * 4);
+            B2G_ST(true, (float *)B.p[B2G_T_DOF_STATE] + e0 * nd * 2, s_dof, (uint32_t)(EPB * nd * 8));
+            B2G_ST(g_act_out != nullptr, g_act_out + e0 * nd, s_act, (uint32_t)(EPB * nd * 4));
+            B2G_ST(stage_out && g_sens && nsens6, g_sens + e0 * nsens6, s_sens, (uint32_t)(EPB * nsens6 * 4));
+            B2G_ST(true, (float *)B.p[B2G_T_REW] + e0, t_rew, EPB * 4);
+            B2G_ST(true, pot_b + e0, t_pot, EPB * 4);
+            B2G_ST(true, ppot_b + e0, t_ppot, EPB * 4);
+            B2G_ST(B.p[B2G_T_UP_VEC] != nullptr, (float *)B.p[B2G_T_UP_VEC] + 3 * e0, t_up, EPB * 12);
+            B2G_ST(B.p[B2G_T_HEADING_VEC] != nullptr, (float *)B.p[B2G_T_HEADING_VEC] + 3 * e0, t_head, EPB * 12);
+            B2G_ST(true, reset_b + e0, t_reset, EPB * 8);
+            B2G_ST(true, progress_b + e0, t_prog, EPB * 8);
+            B2G_ST(B.p[B2G_T_TIMEOUT] != nullptr, (uint8_t *)B.p[B2G_T_TIMEOUT] + e0, t_to, EPB);
+#undef B2G_ST
+            bulk_commit_wait();
+        };
+        if (threadIdx.x == 0) issue(0);
+        else if (NW > 1 && threadIdx.x == 32) issue(1);
+        else if (NW > 2 && threadIdx.x == 64) issue(2);
+        else if (NW > 3 && threadIdx.x == 96) issue(3);
     }
     if (HOSTIO) {                  // host copies of what VecTask.step returns (vec_task.py:402-408), straight over PCIe
         const size_t e0 = (size_t)env0;
@@ -349,8 +371,7 @@ __global__ void __launch_bounds__(BLOCK) quad_anymal_physics_kernel(const float4
     const bool valid = env < N;
     const int e = valid ? env : N - 1;
     QLane<NS, HF, 0> L = make_qlane<NS, HF, 0>(qm, hf, park, BLOCK, lane);
-    const float *envmu = (const float *)B.p[B2G_T_ENV_FRICTION];
-    if (envmu) L.env_mu = 0.5f * (envmu[e] + qm[18].x);
+    attach_env_params(L, B, e, nd);
     RootState rs; load_root((const float *)B.p[B2G_T_ROOT_STATE] + 13 * (size_t)e, rs);
     const float2 *dofs = (const float2 *)B.p[B2G_T_DOF_STATE] + (size_t)e * nd;
     float *act_out = (float *)B.p[B2G_T_ACTIONS] + (size_t)e * nd;

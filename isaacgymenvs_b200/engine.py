@@ -22,7 +22,7 @@ MAXL = 32
  T_UP_VEC, T_HEADING_VEC, T_INITIAL_ROOT, T_RESET_COUNT, T_OBS_CLIPPED, T_COMMANDS, T_LAST_ACTIONS, T_LAST_DOF_VEL,
  T_FEET_AIR_TIME, T_TORQUES, T_EPISODE_SUMS, T_TERRAIN_LEVELS, T_TERRAIN_TYPES, T_ENV_ORIGINS, T_TERRAIN_ORIGINS,
  T_NOISE_SCALE, T_BASE_SCRATCH, T_REDUCE_SCRATCH, T_ENV_FRICTION, T_GOAL_STATES, T_PREV_TARGETS, T_SUCCESSES,
- T_CONSECUTIVE_SUCCESSES, T_RESET_GOAL, T_GOAL_RESET_COUNT, T_STATES) = range(42)
+ T_CONSECUTIVE_SUCCESSES, T_RESET_GOAL, T_GOAL_RESET_COUNT, T_STATES, T_ENV_MASS_SCALE, T_ENV_DOF_PROPS) = range(44)
 TASK_NONE, TASK_CARTPOLE, TASK_ANT, TASK_HUMANOID, TASK_ANYMAL_TERRAIN, TASK_SHADOW_HAND = 0, 1, 2, 3, 4, 5
 HAND_OBS = {"openai": 0, "full_no_vel": 1, "full": 2, "full_state": 3}
 

@@ -136,7 +136,9 @@ class AnymalTerrain(VecTask):
         self._episode_sums = torch.zeros(13, N, device=dev)
         self.episode_sums = {k: self._episode_sums[i] for i, k in enumerate(SUM_KEYS)}
         self._base_scratch = torch.zeros(N, 12, device=dev)
-        self._reduce = torch.zeros(1024 + 16, device=dev)
+        self._reduce = torch.zeros(1024 + 48, device=dev)
+        self._reduce[1024 + 32] = float(self.terrain_levels.sum().item())          # running sum of terrain_levels, kept by the reset kernel
+        self._reduce[1024 + 29] = float(self.terrain_levels.float().mean().item())
         self.measured_heights = None
         # initial reset of every env (:148, init_done False -> no curriculum move); host-side, one-off
         u = lambda lo, hi, *shape: ((hi - lo) * torch.rand(*shape, generator=gen) + lo).to(dev)
@@ -212,9 +214,10 @@ class AnymalTerrain(VecTask):
         return p
 
     def _fill_extras(self):
-        # reset_idx fills extras["episode"] for the envs reset this step (:420-425)
-        sums, cnt = self._reduce[1024:1037], self._reduce[1037]
-        mean = sums / torch.clamp(cnt, min=1.0) / self.max_episode_length_s
-        self.extras["episode"] = {"rew_" + k: mean[i] for i, k in enumerate(SUM_KEYS)}
-        self.extras["episode"]["terrain_level"] = torch.mean(self.terrain_levels.float())
+        # reset_idx fills extras["episode"] for the envs reset this step (:420-425): the reset kernel's last warp writes the
+        # means into the scratch tensor; the dict holds views of it, built once (no torch kernels on the step path)
+        if "episode" not in self.extras:
+            means = self._reduce[1024 + 16:1024 + 30]
+            self.extras["episode"] = {"rew_" + k: means[i] for i, k in enumerate(SUM_KEYS)}
+            self.extras["episode"]["terrain_level"] = means[13]
         self.common_step_counter += 1

@@ -144,6 +144,7 @@ class VecTask(Env):
         # domain randomisation: observation / action noise only (utils/dr.py); physical parameters raise
         self.randomizer = None
         task_cfg = self.cfg.get("task", {}) if isinstance(self.cfg, dict) else {}
+        self.physical_randomizer = None
         if task_cfg.get("randomize", False):
             from ...utils.dr import Randomizer
             self.randomizer = Randomizer(task_cfg.get("randomization_params", {}))
@@ -160,6 +161,14 @@ class VecTask(Env):
         self.obs_dict = {}
         self.allocate_buffers()
         self._bind_task()
+        ap = task_cfg.get("randomization_params", {}).get("actor_params") if task_cfg.get("randomize", False) else None
+        if ap:      # physical domain randomisation: per-env parameter tensors read by the step kernel (utils/dr.py)
+            from ...utils.dr import PhysicalRandomizer
+            self.physical_randomizer = PhysicalRandomizer(ap, self.model, self.num_envs, self.device,
+                                                          task_cfg["randomization_params"].get("frequency", 1))
+            self.physical_randomizer.apply(0, self.randomize_buf, self.reset_buf)
+            for slot, t in self.physical_randomizer.tensors(engine).items():
+                self.sim._bind(slot, t)
 
     # ---- vec_task.py:301-324
     def allocate_buffers(self):
@@ -228,6 +237,9 @@ class VecTask(Env):
 
     # ---- vec_task.py:360-408
     def step(self, actions: torch.Tensor) -> Tuple[Dict[str, torch.Tensor], torch.Tensor, torch.Tensor, Dict[str, Any]]:
+        if self.physical_randomizer is not None:   # apply_randomizations for the envs this step is about to reset (vec_task.py:631-637)
+            self.physical_randomizer.apply(self.control_steps * max(int(self.control_freq_inv), 1), self.randomize_buf, self.reset_buf)
+            self.randomize_buf += 1
         if self.randomizer is not None:         # apply_randomizations, vec_task.py:610-718 (non-physical part)
             if self.randomizer.update(self.control_steps * max(int(self.control_freq_inv), 1)):
                 for key, model in self.randomizer.models.items():
@@ -260,7 +272,7 @@ class VecTask(Env):
         """rl_device='cpu' fast path: the same step with host (pinned) buffers through
         b2g_task_step_host -- H2D actions, fused step, D2H obs/rew/reset, stream sync.  It runs none of step()'s
         randomisation hooks, so it refuses to run with them configured rather than silently skipping the noise."""
-        if self.randomizer is not None or self.dr_randomizations:
+        if self.randomizer is not None or self.dr_randomizations or self.physical_randomizer is not None:
             raise engine.EngineError("step_host: domain randomisation is configured; use step() (the noise lambdas run on device tensors)")
         self.sim.task_step_host(h_actions, h_obs, h_rew, h_reset, h_timeout)
         self.control_steps += 1

@@ -10,7 +10,8 @@ using namespace b2g;
 
 template <int NS, bool HF, int SP>
 static void run(const std::vector<float> &qmv, const int16_t *hf, int N, int substeps, float *root, float *dof, const float *act,
-                float *sensor, int nsens, float *dof_force, float *net_contact, int nb, const int *leg_link) {
+                float *sensor, int nsens, float *dof_force, float *net_contact, int nb, const int *leg_link,
+                const float *mass_scale, const float *dof_props, const float *env_friction) {
     const float4 *qm = reinterpret_cast<const float4 *>(qmv.data());
     const int nd = 4 * NS;
     std::vector<float4> park((size_t)4 * quad_park_f4(NS));
@@ -22,6 +23,9 @@ static void run(const std::vector<float> &qmv, const int16_t *hf, int N, int sub
         for (int c = 0; c < 4; c++) rs.rq[c] = r[3 + c];
         for (int l = 0; l < 4; l++) {
             L[l].qm = qm; L[l].hf = hf; L[l].park = park.data() + l; L[l].pstride = 4; L[l].lane = l; L[l].env_mu = -1.f;
+            L[l].dr_mass = mass_scale ? mass_scale + (size_t)e * (nd + 1) : nullptr;
+            L[l].dr_dof = dof_props ? reinterpret_cast<const float4 *>(dof_props) + (size_t)e * nd : nullptr;
+            if (env_friction) L[l].env_mu = 0.5f * (env_friction[e] + qm[18].x);
             for (int s = 0; s < NS; s++) {
                 const int d = leg_link[l * NS + s] - 1;
                 L[l].q[s] = dof[((size_t)e * nd + d) * 2]; L[l].qd[s] = dof[((size_t)e * nd + d) * 2 + 1];
@@ -69,14 +73,15 @@ static void run(const std::vector<float> &qmv, const int16_t *hf, int N, int sub
 // returns NS (2 / 3) when the model runs on the quad path, 0 when it does not fit, <0 on error.  want_spec: 3 = let the
 // builder use the axisymmetric-inertia specialisation when the model allows it, 0 = general layout; *spec_out = what was used
 extern "C" int quad_host_simulate(const b2g_model *m, const b2g_sim_params *sp, int N, float *root, float *dof, const float *act,
-                                  float *sensor, float *dof_force, float *net_contact, int want_spec, int *spec_out) {
+                                  float *sensor, float *dof_force, float *net_contact, int want_spec, int *spec_out,
+                                  const float *mass_scale, const float *dof_props, const float *env_friction) {
     std::vector<float> qm;
     int leg_link[12], spec = 0;
     const int NS = quad_build(m, sp, qm, leg_link, &spec, want_spec);
     if (spec_out) *spec_out = spec;
     if (NS == 0) return 0;
     const bool hf = sp->hf_samples != nullptr;
-#define RUN(NS_, HF_, SP_) run<NS_, HF_, SP_>(qm, HF_ ? sp->hf_samples : nullptr, N, sp->substeps, root, dof, act, sensor, m->nsens, dof_force, net_contact, m->nb, leg_link)
+#define RUN(NS_, HF_, SP_) run<NS_, HF_, SP_>(qm, HF_ ? sp->hf_samples : nullptr, N, sp->substeps, root, dof, act, sensor, m->nsens, dof_force, net_contact, m->nb, leg_link, mass_scale, dof_props, env_friction)
     if (NS == 2 && !hf) { if (spec == 3) RUN(2, false, 3); else RUN(2, false, 0); }
     else if (NS == 2) { if (spec == 3) RUN(2, true, 3); else RUN(2, true, 0); }
     else if (NS == 3 && !hf) { if (spec == 3) RUN(3, false, 3); else RUN(3, false, 0); }

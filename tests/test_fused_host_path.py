@@ -28,6 +28,10 @@ class _FakeFusedSim:
     def set_task(self, params, buffers):
         self.params, self.bound = params, dict(buffers)
 
+    def _bind(self, slot, t):
+        self.bound[slot] = t
+        return t
+
     def task_step(self, actions):
         E = self.E
         self.steps += 1
@@ -113,3 +117,41 @@ def test_fused_task_observation_and_action_noise(fused_cpu):
     assert (bound == 2.0).all() and env.sim.bound[E.T_OBS].data_ptr() == bound.data_ptr() and abs(float(obs2["obs"].mean()) - 2.0) < 0.3
     with pytest.raises(NotImplementedError):
         _make("Ant", n, task_section={"randomize": True, "randomization_params": {"frequency": 1, "sim_params": {"gravity": {}}}})
+
+
+def test_fused_task_physical_domain_randomisation(fused_cpu):
+    """task.randomize with the reference's Ant.yaml actor_params block (cfg/task/Ant.yaml:76-101): per-env parameter tensors
+    are sampled inside the configured ranges, bound to the engine, re-sampled only for envs that are flagged for reset AND
+    whose randomisation counter passed `frequency`; setup_only properties are drawn once."""
+    n = 64
+    dr = {"frequency": 3,
+          "actor_params": {"ant": {"color": True,
+                                   "rigid_body_properties": {"mass": {"range": [0.5, 1.5], "operation": "scaling", "distribution": "uniform", "setup_only": True}},
+                                   "dof_properties": {"damping": {"range": [0.5, 1.5], "operation": "scaling", "distribution": "uniform"},
+                                                      "stiffness": {"range": [0.5, 1.5], "operation": "scaling", "distribution": "uniform"},
+                                                      "lower": {"range": [0, 0.01], "operation": "additive", "distribution": "gaussian"},
+                                                      "upper": {"range": [0, 0.01], "operation": "additive", "distribution": "gaussian"}}}}}
+    torch.manual_seed(0)
+    env = _make("Ant", n, task_section={"randomize": True, "randomization_params": dr})
+    E = env.sim.E
+    pr = env.physical_randomizer
+    ms, dp = env.sim.bound[E.T_ENV_MASS_SCALE], env.sim.bound[E.T_ENV_DOF_PROPS]
+    assert ms.shape == (n, 9) and dp.shape == (n, 8, 4) and E.T_ENV_FRICTION not in env.sim.bound
+    assert (ms >= 0.5).all() and (ms <= 1.5).all() and ms.std() > 0.1
+    og = pr.og_dof
+    assert ((dp[..., 0] >= 0.5 * og[:, 0] - 1e-6) & (dp[..., 0] <= 1.5 * og[:, 0] + 1e-6)).all()        # damping scaled
+    assert (dp[..., 2] - og[:, 2]).abs().max() < 0.06 and (dp[..., 2] - og[:, 2]).abs().max() > 1e-3     # limits shifted by N(0, 0.01)
+    ms0, dp0 = ms.clone(), dp.clone()
+    a = torch.zeros(n, 8)
+    env.step(a)                                                        # counters 0 -> below the frequency: nothing changes
+    assert torch.equal(ms, ms0) and torch.equal(dp, dp0)
+    for _ in range(3):
+        env.step(a)
+    env.reset_buf[: n // 2] = 1                                        # half of the envs are about to reset, their counters are past 3
+    env.step(a)
+    changed = (dp != dp0).any(-1).any(-1)
+    assert changed[: n // 2].all() and not changed[n // 2:].any()
+    assert torch.equal(ms, ms0)                                        # setup_only
+    assert (env.randomize_buf[: n // 2] <= 1).all() and (env.randomize_buf[n // 2:] >= 4).all()
+    with pytest.raises(NotImplementedError):
+        _make("Ant", n, task_section={"randomize": True, "randomization_params": {"frequency": 1, "actor_params": {"ant": {"tendon_properties": {}}}}})

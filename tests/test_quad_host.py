@@ -55,7 +55,7 @@ def _random_states(m, n, rng, zlo, zhi):
 
 
 def _host_simulate(lib, m, dt, sub, root32, dof32, tau32, hfield=None, hf_scale=1.0, hf_vscale=1.0, hf_origin=(0.0, 0.0), ground_mu=1.0, want_spec=3,
-                   spec_out=None):
+                   spec_out=None, mass_scale=None, dof_props=None, env_friction=None):
     cm, keep = engine.pack_model(m)
     sp = engine.CSimParams()
     sp.dt, sp.substeps = dt, sub
@@ -74,17 +74,20 @@ def _host_simulate(lib, m, dt, sub, root32, dof32, tau32, hfield=None, hf_scale=
     nc = np.zeros((n, m.nb, 3), np.float32)
     p = lambda a: C.c_void_p(a.ctypes.data)
     spec = C.c_int(-1)
-    ns = lib.quad_host_simulate(C.byref(cm), C.byref(sp), C.c_int(n), p(root32), p(dof32), p(tau32), p(sensor), p(dfrc), p(nc), C.c_int(want_spec), C.byref(spec))
+    ns = lib.quad_host_simulate(C.byref(cm), C.byref(sp), C.c_int(n), p(root32), p(dof32), p(tau32), p(sensor), p(dfrc), p(nc), C.c_int(want_spec), C.byref(spec),
+                                p(mass_scale) if mass_scale is not None else None, p(dof_props) if dof_props is not None else None,
+                                p(env_friction) if env_friction is not None else None)
     if spec_out is not None:
         spec_out.append(spec.value)
     return ns, sensor[:, :len(m.sensor_body)], dfrc, nc
 
 
-def _compare(m, rg, dg, out_g, r64, d64, out):
+def _compare(m, rg, dg, out_g, r64, d64, out, qtol=5e-5):
     assert np.abs(rg[:, :7] - r64[:, :7]).max() < 2e-5
     verr = np.abs(rg[:, 7:] - r64[:, 7:]) / np.maximum(1.0, np.abs(r64[:, 7:]))
     assert verr.max() < 2e-3, verr.max()
-    assert np.abs(dg[..., 0] - d64[..., 0]).max() < 5e-5
+    dq = np.abs(dg[..., 0] - d64[..., 0])
+    assert dq.max() < qtol and np.quantile(dq, 0.999) < 3e-5, (dq.max(), np.quantile(dq, 0.999))
     qerr = np.abs(dg[..., 1] - d64[..., 1]) / np.maximum(1.0, np.abs(d64[..., 1]))
     assert qerr.max() < 2e-3, qerr.max()
     sensor, dfrc, nc = out_g
@@ -176,3 +179,53 @@ def test_quad_path_rejects_other_topologies():
         dof32 = np.zeros((n, m.ndof, 2), np.float32); tau32 = np.zeros((n, m.ndof), np.float32)
         ns, *_ = _host_simulate(lib, m, 0.0166, 2, root32, dof32, tau32)
         assert ns == 0
+
+
+@pytest.mark.parametrize("name,zlo,zhi,tscale,dt,sub", [("ant", 0.15, 0.8, 15.0, 0.0166, 2), ("anymal", 0.3, 0.9, 40.0, 0.005, 1)])
+def test_quad_per_env_physical_parameters_match_oracle(name, zlo, zhi, tscale, dt, sub):
+    """Physical domain randomisation (vec_task.py:720-828): per-env link-mass factors, joint damping / stiffness / limits and
+    friction, read by the quad sub-step as parameter arrays.  Four groups of envs with different parameter sets; each group
+    must equal the oracle run on a MODEL with those parameters baked in."""
+    lib = _lib()
+    base = _model(name)
+    n, ng = 256, 4
+    rng = np.random.default_rng(21)
+    root, dof = _random_states(base, n, rng, zlo, zhi)
+    tau = rng.uniform(-1, 1, size=(n, base.ndof)) * tscale
+    root32 = np.ascontiguousarray(root, np.float32); dof32 = np.ascontiguousarray(dof, np.float32); tau32 = np.ascontiguousarray(tau, np.float32)
+    nl, nd = base.nl, base.ndof
+    mass_scale = np.ones((n, nl), np.float32); dof_props = np.zeros((n, nd, 4), np.float32); fric = np.zeros(n, np.float32)
+    groups = []
+    for g in range(ng):
+        ms = rng.uniform(0.5, 2.0, size=nl).astype(np.float32) if g else np.full(nl, 2.0, np.float32)     # group 0: every mass doubled
+        dmp = (base.damping[1:] * rng.uniform(0.5, 1.5, size=nd) + 0.05 * g).astype(np.float32)
+        stf = (base.stiffness[1:] * rng.uniform(0.5, 1.5, size=nd) + 0.5 * g).astype(np.float32)
+        lo = (np.where(base.limited[1:] > 0, base.lower[1:], -3e38) + np.where(base.limited[1:] > 0, rng.normal(0, 0.02, size=nd), 0)).astype(np.float32)
+        hi = (np.where(base.limited[1:] > 0, base.upper[1:], 3e38) + np.where(base.limited[1:] > 0, rng.normal(0, 0.02, size=nd), 0)).astype(np.float32)
+        mu = np.float32(0.4 + 0.3 * g)
+        sl = slice(g * n // ng, (g + 1) * n // ng)
+        mass_scale[sl] = ms; dof_props[sl, :, 0] = dmp; dof_props[sl, :, 1] = stf; dof_props[sl, :, 2] = lo; dof_props[sl, :, 3] = hi; fric[sl] = mu
+        groups.append((sl, ms, dmp, stf, lo, hi, mu))
+    r64 = root32.astype(np.float64); d64 = dof32.astype(np.float64); t64 = tau32.astype(np.float64)
+    outs = []
+    for sl, ms, dmp, stf, lo, hi, mu in groups:
+        m = copy.deepcopy(base)
+        m.mass = m.mass * ms.astype(np.float64)
+        m.damping = np.concatenate([[0.0], dmp.astype(np.float64)]); m.stiffness = np.concatenate([[0.0], stf.astype(np.float64)])
+        lim = base.limited[1:] > 0
+        m.lower = np.concatenate([[0.0], np.where(lim, lo.astype(np.float64), base.lower[1:])])
+        m.upper = np.concatenate([[0.0], np.where(lim, hi.astype(np.float64), base.upper[1:])])
+        m.cp_mu = np.full_like(np.asarray(m.cp_mu, float), float(mu))          # friction of every shape of the env
+        orc = OracleSim(m, dt, sub, G, ground_mu=1.0, threads=8)
+        r = np.ascontiguousarray(r64[sl]); d = np.ascontiguousarray(d64[sl])
+        out = orc.simulate(r, d, np.ascontiguousarray(t64[sl]))
+        r64[sl] = r; d64[sl] = d; outs.append(out)
+    ns, sensor, dfrc, nc = _host_simulate(lib, base, dt, sub, root32, dof32, tau32, mass_scale=mass_scale, dof_props=dof_props, env_friction=fric)
+    assert ns in (2, 3)
+    out = {k: np.concatenate([o[k] for o in outs], 0) for k in ("sensor", "dof_force", "contact_force")}
+    # ANYmal's 0.5 kg shanks under 40 N m reach |qd| > 30 rad/s in contact: fp32 round-off of a few 1e-5 rad in single DOFs
+    _compare(base, root32.astype(np.float64), dof32.astype(np.float64), (sensor, dfrc, nc), r64, d64, out, qtol=2e-4 if name == "anymal" else 5e-5)
+    # the parameters matter: the same states with the model's own parameters end up elsewhere
+    rootb = np.ascontiguousarray(root, np.float32); dofb = np.ascontiguousarray(dof, np.float32)
+    _host_simulate(lib, base, dt, sub, rootb, dofb, tau32)
+    assert np.abs(dofb[..., 1] - dof32[..., 1]).max() > 1e-2
