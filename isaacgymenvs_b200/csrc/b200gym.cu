@@ -582,7 +582,7 @@ struct b2g_sim {
     // quad path (b2g_quad.cuh): chain length (2 Ant-like, 3 ANYmal-like) or 0 = generic Stepper; the packed constants
     int quad_ns = 0;
     int quad_spec = 0;                        // QLane specialisation flags the constants are packed for (b2g_quad.cuh)
-    int quad_block = 128;
+    int quad_block = 64;                      // threads per CTA of the quad step kernels (B2G_QUAD_BLOCK: 32 / 64 / 128)
     float4 *d_qm = nullptr;
     std::vector<const void *> smem_set;      // kernels whose dynamic shared-memory limit has been raised (once per sim)
     bool no_zero_copy = false;
@@ -874,7 +874,7 @@ extern "C" int b2g_create_ext(const b2g_model *m, const b2g_model_ext *ext, cons
     {   // the specialised path of "four hinge chains on a free base" (Ant, ANYmal): b2g_quad.cuh
         const char *nq = getenv("B2G_NO_QUAD"), *qb = getenv("B2G_QUAD_BLOCK"), *nz = getenv("B2G_NO_ZERO_COPY");
         s->no_zero_copy = nz != nullptr;
-        if (qb && (atoi(qb) == 64 || atoi(qb) == 128)) s->quad_block = atoi(qb);
+        if (qb && (atoi(qb) == 32 || atoi(qb) == 64 || atoi(qb) == 128)) s->quad_block = atoi(qb);
         if (!(nq && nq[0] == '1') && !ext && !(force1 && force1[0] == '1') && !getenv("B2G_LANES") && !getenv("B2G_BLOCK")) {
             std::vector<float> qm; int leg_link[12], spec = 0;
             const char *nsp = getenv("B2G_QUAD_NO_SPEC");
@@ -1220,6 +1220,7 @@ extern "C" int b2g_task_step(b2g_sim *s, const float *actions, void *stream) {
     } while (0)
 #define QLOCO_S(BK, HIO) do { if (s->quad_spec == 3) QLOCO(3, BK, HIO); else QLOCO(0, BK, HIO); } while (0)
                 if (qb == 128) { if (s->zero_copy.on) QLOCO_S(128, true); else QLOCO_S(128, false); }
+                else if (qb == 32) { if (s->zero_copy.on) QLOCO_S(32, true); else QLOCO_S(32, false); }
                 else { if (s->zero_copy.on) QLOCO_S(64, true); else QLOCO_S(64, false); }
 #undef QLOCO_S
 #undef QLOCO

@@ -270,6 +270,7 @@ __global__ void __launch_bounds__(BLOCK) anymal_reset_obs_kernel(Buffers B, cons
             float *red = (float *)B.p[B2G_T_REDUCE_SCRATCH] + REDUCE_PARTIALS;          // extras["episode"] sums (logging)
             for (int k = 0; k < 13; k++) { atomicAdd(red + k, es[(size_t)k * N + e]); es[(size_t)k * N + e] = 0.f; }
             atomicAdd(red + 13, 1.f);
+            __threadfence();                  // these sums are read by the grid's last warp (ticket below): order them before this warp's arrival
         }
     }
     __syncwarp();
@@ -279,17 +280,38 @@ __global__ void __launch_bounds__(BLOCK) anymal_reset_obs_kernel(Buffers B, cons
     float *obsc = (float *)B.p[B2G_T_OBS_CLIPPED];
     obsc = (obsc && obsc != (float *)B.p[B2G_T_OBS]) ? obsc + (size_t)e * P.num_obs : nullptr;
     const float *nsv = (const float *)B.p[B2G_T_NOISE_SCALE];
-    // observation noise (:481-482): uniform number idx of stream (env, step); one Philox block serves 4 neighbours,
-    // and every lane writes contiguous index ranges, so the block is cached
+    // observation noise (:481-482): uniform number idx of stream (env, step); one Philox block serves 4 neighbours.
+    // Warp-per-env layout: the env's 47 Philox blocks are generated ONCE, spread over the 32 lanes (<= 2 each), and the
+    // noise terms parked in shared memory -- with each lane generating the blocks of the indices it happens to write, the
+    // Philox rounds were most of this kernel's instructions.  Narrower layouts keep the per-lane block cache.
+    constexpr bool WARP_ENV = (L == 32);
+    __shared__ float s_noise[WARP_ENV ? BLOCK / 32 : 1][WARP_ENV ? 192 : 1];
+    float *const my_noise = s_noise[WARP_ENV ? (threadIdx.x >> 5) : 0];
+    if (WARP_ENV && P.add_noise) {
+        for (int blk = lane; 4 * blk < P.num_obs && blk < 48; blk += 32) {
+            uint32_t r4[4];
+            philox4x32_10((uint32_t)blk, step_counter, gid, TAG_NOISE, (uint32_t)P.seed, (uint32_t)(P.seed >> 32), r4);
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const int idx = 4 * blk + c;
+                if (idx < P.num_obs) my_noise[idx] = (2.f * ((float)(r4[c] >> 8) * (1.0f / 16777216.0f)) - 1.f) * nsv[idx];
+            }
+        }
+        __syncwarp();
+    }
     uint32_t nz[4]; int nz_blk = -1;
     auto put = [&](int idx, float v) {
         if (P.add_noise) {
-            if ((idx >> 2) != nz_blk) {
-                nz_blk = idx >> 2;
-                philox4x32_10((uint32_t)nz_blk, step_counter, gid, TAG_NOISE, (uint32_t)P.seed, (uint32_t)(P.seed >> 32), nz);
+            if (WARP_ENV) {
+                v += my_noise[idx];
+            } else {
+                if ((idx >> 2) != nz_blk) {
+                    nz_blk = idx >> 2;
+                    philox4x32_10((uint32_t)nz_blk, step_counter, gid, TAG_NOISE, (uint32_t)P.seed, (uint32_t)(P.seed >> 32), nz);
+                }
+                const float u = (float)(nz[idx & 3] >> 8) * (1.0f / 16777216.0f);
+                v += (2.f * u - 1.f) * nsv[idx];
             }
-            const float u = (float)(nz[idx & 3] >> 8) * (1.0f / 16777216.0f);
-            v += (2.f * u - 1.f) * nsv[idx];
         }
         obs[idx] = v;
         if (obsc) obsc[idx] = fminf(fmaxf(v, -P.clip_obs), P.clip_obs);
@@ -363,7 +385,8 @@ __global__ void __launch_bounds__(BLOCK) anymal_reset_obs_kernel(Buffers B, cons
     if ((threadIdx.x & 31) == 0) {
         const int first_env = blockIdx.x * (BLOCK / L);
         const int nwarps = min(BLOCK / 32, (N - first_env) * (L / 32));            // warps of this block that own an env (L == 32)
-        __threadfence();
+        // (no grid-scope fence here: only the few warps that reset an env touched the sums, and they fenced there; a
+        // __threadfence by every warp invalidates L1 4096 times per launch -- measured +13 us)
         if (atomicAdd(&s_done, 1) == nwarps - 1) {
             float *red = (float *)B.p[B2G_T_REDUCE_SCRATCH] + REDUCE_PARTIALS;
             unsigned *ticket = reinterpret_cast<unsigned *>(red + 15);

@@ -117,20 +117,34 @@ struct QLane {
     }
 
     // ---- one contact sphere (link-frame centre cp.xyz, radius cp.w) of a link posed at (R, x) with twist (vw, vl).
+    // Split in two so that the height-field samples of several spheres (4 global loads each) are in flight together and
+    // overlap the link's inertia arithmetic: sphere_geom = centre about O + ground height / normal under it,
+    // sphere = the contact itself.
     // ACCUM: explicit force into the bias (pa, pl), implicit term h J^T G J into I.  !ACCUM: the force applied over
     // the sub-step, F0 - h G (J a), and its torque about the link origin, added to (F, T).
+    struct SphereGeom { float pc[3], hg, n[3]; };
+    B2G_HD void sphere_geom(const float4 cp, const float rp[3], const float R[9], const float x[3], SphereGeom &g) const {
+        g.pc[0] = x[0] + R[0] * cp.x + R[1] * cp.y + R[2] * cp.z;
+        g.pc[1] = x[1] + R[3] * cp.x + R[4] * cp.y + R[5] * cp.z;
+        g.pc[2] = x[2] + R[6] * cp.x + R[7] * cp.y + R[8] * cp.z;
+        g.hg = 0.f; g.n[0] = 0.f; g.n[1] = 0.f; g.n[2] = 1.f;
+        if (HF) ground(rp[0] + g.pc[0], rp[1] + g.pc[1], g.hg, g.n);
+    }
     template <bool ACCUM>
     B2G_HD void sphere(const float4 cp, float mu, const float rp[3], const float R[9], const float x[3],
                        const float vw[3], const float vl[3], float I[21], float pa[3], float pl[3],
                        const float aw[3], const float al[3], float F[3], float T[3]) const {
+        SphereGeom g; sphere_geom(cp, rp, R, x, g);
+        sphere<ACCUM>(cp, mu, g, rp, x, vw, vl, I, pa, pl, aw, al, F, T);
+    }
+    template <bool ACCUM>
+    B2G_HD void sphere(const float4 cp, float mu, const SphereGeom &g, const float rp[3], const float x[3],
+                       const float vw[3], const float vl[3], float I[21], float pa[3], float pl[3],
+                       const float aw[3], const float al[3], float F[3], float T[3]) const {
         const float4 H0 = qm[0], H1 = qm[1];
         const float h = H0.x, kn = H1.x, vs2 = H1.z, gn = H1.w;
-        float pc[3];
-        pc[0] = x[0] + R[0] * cp.x + R[1] * cp.y + R[2] * cp.z;
-        pc[1] = x[1] + R[3] * cp.x + R[4] * cp.y + R[5] * cp.z;
-        pc[2] = x[2] + R[6] * cp.x + R[7] * cp.y + R[8] * cp.z;
-        float hg = 0.f, n[3] = {0.f, 0.f, 1.f};
-        if (HF) ground(rp[0] + pc[0], rp[1] + pc[1], hg, n);
+        const float *pc = g.pc, *n = g.n;
+        const float hg = g.hg;
         const float d = HF ? cp.w - (rp[2] + pc[2] - hg) * n[2] : cp.w - (rp[2] + pc[2]);
         if (d <= 0.f) return;
         float r[3];
@@ -298,7 +312,13 @@ struct QLane {
                     if (lo || hi) { f += k12.y * ((lo ? k11.z : k11.w) - qp) - k12.z * qds; dg += k12.w; }
                     tau[s] = f; dgv[s] = dg;
                 }
-                // ---- link-local terms: rigid-body inertia and bias about O, contacts
+                // ---- link-local terms: rigid-body inertia and bias about O, contacts (ground samples requested first)
+                const float4 c0 = LK(s, 13), c1 = LK(s, 14), k15 = LK(s, 15);
+                SphereGeom g0, g1;
+                if (HF) {
+                    if (c0.w >= 0.f) sphere_geom(c0, rs.rp, R, x, g0);
+                    if (c1.w >= 0.f) sphere_geom(c1, rs.rp, R, x, g1);
+                }
                 const float4 k9 = LK(s, 9);
                 const float cm_[3] = {k8.y, k8.z, k8.w};
                 float c_[3]; matvec(R, cm_, c_);
@@ -315,10 +335,14 @@ struct QLane {
                 }
                 rigid_terms(k10.z, Icw, c_, vw, vl, g, da, dl, I, qa, ql);
                 {
-                    const float4 c0 = LK(s, 13), c1 = LK(s, 14), k15 = LK(s, 15);
                     float dummy[3];
-                    if (c0.w >= 0.f) sphere<true>(c0, k15.x, rs.rp, R, x, vw, vl, I, qa, ql, dummy, dummy, dummy, dummy);
-                    if (c1.w >= 0.f) sphere<true>(c1, k15.y, rs.rp, R, x, vw, vl, I, qa, ql, dummy, dummy, dummy, dummy);
+                    if (HF) {
+                        if (c0.w >= 0.f) sphere<true>(c0, k15.x, g0, rs.rp, x, vw, vl, I, qa, ql, dummy, dummy, dummy, dummy);
+                        if (c1.w >= 0.f) sphere<true>(c1, k15.y, g1, rs.rp, x, vw, vl, I, qa, ql, dummy, dummy, dummy, dummy);
+                    } else {                                          // plane: nothing to prefetch, one sphere at a time
+                        if (c0.w >= 0.f) sphere<true>(c0, k15.x, rs.rp, R, x, vw, vl, I, qa, ql, dummy, dummy, dummy, dummy);
+                        if (c1.w >= 0.f) sphere<true>(c1, k15.y, rs.rp, R, x, vw, vl, I, qa, ql, dummy, dummy, dummy, dummy);
+                    }
                 }
                 if (park_poses) park_pose(s, R, x, vw, vl);
                 if (s < NS - 1) {     // park the link's own terms until the leaf->root sweep comes back

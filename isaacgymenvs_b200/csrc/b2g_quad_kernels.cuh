@@ -328,10 +328,11 @@ __global__ void __launch_bounds__(BLOCK, B2G_QUAD_MINBLOCKS(BLOCK)) quad_loco_ke
             B2G_ST(B.p[B2G_T_HEADING_VEC] != nullptr, (float *)B.p[B2G_T_HEADING_VEC] + 3 * e0, t_head, EPB * 12);
             B2G_ST(true, reset_b + e0, t_reset, EPB * 8);
             B2G_ST(true, progress_b + e0, t_prog, EPB * 8);
-            B2G_ST(B.p[B2G_T_TIMEOUT] != nullptr, (uint8_t *)B.p[B2G_T_TIMEOUT] + e0, t_to, EPB);
+            if (EPB % 16 == 0) B2G_ST(B.p[B2G_T_TIMEOUT] != nullptr, (uint8_t *)B.p[B2G_T_TIMEOUT] + e0, t_to, EPB);   // bulk copies move multiples of 16 bytes
 #undef B2G_ST
             bulk_commit_wait();
         };
+        if (EPB % 16 != 0 && B.p[B2G_T_TIMEOUT] && threadIdx.x < EPB) ((uint8_t *)B.p[B2G_T_TIMEOUT])[e0 + threadIdx.x] = t_to[threadIdx.x];
         if (threadIdx.x == 0) issue(0);
         else if (NW > 1 && threadIdx.x == 32) issue(1);
         else if (NW > 2 && threadIdx.x == 64) issue(2);
@@ -346,7 +347,10 @@ __global__ void __launch_bounds__(BLOCK, B2G_QUAD_MINBLOCKS(BLOCK)) quad_loco_ke
         if (ta.h_obs) copy16(ta.h_obs + e0 * O, g_obsc ? t_obsc : t_obs, EPB * O * 4);
         if (ta.h_rew) copy16(ta.h_rew + e0, t_rew, EPB * 4);
         if (ta.h_reset) copy16(ta.h_reset + e0, t_reset, EPB * 8);
-        if (ta.h_timeout) copy16(ta.h_timeout + e0, t_to, EPB);
+        if (ta.h_timeout) {
+            if (EPB % 16 == 0) copy16(ta.h_timeout + e0, t_to, EPB);
+            else if (threadIdx.x < EPB) ta.h_timeout[e0 + threadIdx.x] = t_to[threadIdx.x];
+        }
     }
 }
 
