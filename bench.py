@@ -421,6 +421,22 @@ def run_gpu_arm(args):
     s1.record()
     barrier()
     b2b_ms = s0.elapsed_time(s1)
+    # ---- open-loop rollout: VecTask.rollout((KR, n, A) actions) -- KR steps per launch where the task has the fused form (Ant)
+    KR = 16
+    roll_ms, roll_calls = None, 0
+    if task == "Ant" and not args.no_rollout:
+        acts = torch.stack(ring[:KR]).contiguous()
+        for ev_ in envs[:min(R, 4)]:
+            ev_.rollout(acts)
+        roll_calls = max(1, -(-args.steps // KR))
+        barrier()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for j in range(roll_calls):
+            envs[j % R].rollout(acts)
+        r1.record()
+        barrier()
+        roll_ms = r0.elapsed_time(r1)
     # ---- end to end through the public API with HOST buffers (pinned): H2D actions, step, D2H results
     O = env.num_obs
     h_a = [r.cpu().pin_memory() for r in ring]
@@ -441,7 +457,8 @@ def run_gpu_arm(args):
     all_returns = D.gather_returns(env.rew_buf)           # (world*n,) in global env order
     assert all_returns.numel() == world * n
     # ---- max over ranks
-    total_ms, dev_ms, b2b_ms, e2e_ms, flushed_ms = D.max_over_ranks([total_ms, dev_ms, b2b_ms, e2e_ms, flushed_ms], device=device)
+    total_ms, dev_ms, b2b_ms, e2e_ms, flushed_ms, roll_max = D.max_over_ranks([total_ms, dev_ms, b2b_ms, e2e_ms, flushed_ms, roll_ms or 0.0], device=device)
+    roll_ms = roll_max if roll_ms is not None else None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -487,6 +504,12 @@ def run_gpu_arm(args):
                      "algorithmic_bytes_per_env_step": bytes_per},
         "clocks": clocks,
     }
+    if roll_ms is not None:
+        line["rollout"] = {"call": f"VecTask.rollout(actions[{KR}, n, A])", "value": world * n * roll_calls * KR / (roll_ms * 1e-3), "unit": "env-steps/s",
+                           "ms_per_step": roll_ms / (roll_calls * KR), "steps_per_launch": KR,
+                           "note": "open-loop (random-action) rollout, the README benchmark's shape: all KR actions given up front, state stays on chip "
+                                   "between the steps, every step's obs/reward/reset/time_out written to (KR, n, .) outputs; NOT the headline: a policy in "
+                                   "the loop needs step()"}
     if flop is not None:    # SURVEY 8d cross-check: the kernel is FP32-issue-bound, not HBM-bound
         tf = flop / (kernel_ms * 1e-3) / 1e12
         line["roofline"]["fp32"] = {"flop_per_launch": flop, "achieved": tf, "peak": 74.4, "unit": "TFLOP/s", "frac": tf / 74.4,
@@ -514,6 +537,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: the workload's env count on EVERY GPU; strong: the same total split over the GPUs")
     ap.add_argument("--sets", type=int, default=0, help="independent env sets stepped round-robin (0 = enough to exceed 1.5 x L2)")
+    ap.add_argument("--no-rollout", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

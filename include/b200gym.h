@@ -275,6 +275,16 @@ int b2g_set_anymal_task(b2g_sim *sim, const b2g_anymal_params *task);
 int b2g_set_hand_task(b2g_sim *sim, const b2g_hand_params *task);
 int b2g_task_step(b2g_sim *sim, const float *actions, void *stream);
 
+/* K consecutive VecTask.step() calls whose actions are all known up front -- the open-loop, random-action rollout the
+ * reference's README times (README.md:39-51: `for _ in range(K): envs.step(random_actions)`):
+ *     for k in range(K): obs[k], rew[k], reset[k], time_outs[k] = step(actions[k])
+ * `actions` (K,N,A), `obs_out` (K,N,O: the observation step() returns, i.e. clipped when a clip is configured), `rew_out`
+ * (K,N), `reset_out` (K,N) i64, `timeout_out` (K,N) u8 or NULL: DEVICE pointers.  Afterwards every bound tensor holds
+ * what it would hold after the K single steps.  Ant on whole tiles of 16 envs runs as ONE launch (state stays on chip
+ * between the steps); anything else as K single steps with device copies. */
+int b2g_task_rollout(b2g_sim *sim, const float *actions, int32_t K, float *obs_out, float *rew_out, int64_t *reset_out,
+                     uint8_t *timeout_out, void *stream);
+
 /* VecTask.reset_done() (vec_task.py:440-455): run reset_idx (ant.py:252-279, humanoid.py:253-279, cartpole.py:144-157,
  * shadow_hand.py:594-659, anymal_terrain.py:384-425) for every env whose RESET flag is set, now, and clear the flag the
  * way the task's reset_idx does.  Observations are refreshed by the next step, as in the reference. */

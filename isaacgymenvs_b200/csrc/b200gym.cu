@@ -495,6 +495,7 @@ __global__ void __launch_bounds__(BLOCK) cartpole_step_kernel(const DevModel *__
 #include "b2g_quad_kernels.cuh"
 #include "b2g_quad_host.h"
 #include "b2g_reset.cuh"
+#include "b2g_quad_rollout.cuh"
 
 // -------------------------------------------------------------------------------------------
 // gym.refresh_rigid_body_state_tensor(): forward kinematics, one thread per env, any topology
@@ -1277,6 +1278,64 @@ extern "C" int b2g_task_step(b2g_sim *s, const float *actions, void *stream) {
 #undef LOCO_T
 #undef LOCO_K
     }
+    s->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return B2G_OK;
+}
+
+// K x VecTask.step() with the actions of all K steps given up front (open-loop / random-action rollouts)
+extern "C" int b2g_task_rollout(b2g_sim *s, const float *actions, int32_t K, float *obs_out, float *rew_out, int64_t *reset_out,
+                                uint8_t *timeout_out, void *stream) {
+    if (!s || !actions || !obs_out || !rew_out || !reset_out || K < 1) return fail(B2G_E_INVALID, "b2g_task_rollout: null argument or K < 1");
+    if (!s->has_task && !s->has_anymal && !s->has_hand) return fail(B2G_E_INVALID, "b2g_task_rollout: call b2g_set_task first");
+    const size_t N = s->num_envs;
+    const bool fused = s->has_task && s->task.task == B2G_TASK_ANT && s->quad_ns == 2 && !s->d_hf && (N % 16 == 0) &&
+                       ((16 * 6 * s->hm.nsens * 4) % 16 == 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!fused) {
+        // every other task / shape: K single steps, their results copied into the (K, N, .) outputs (same semantics, no fusion)
+        const int A = s->has_anymal ? s->anymal.num_actions : (s->has_hand ? s->hand.num_actions : s->task.num_actions);
+        const int O = s->has_anymal ? s->anymal.num_obs : (s->has_hand ? s->hand.num_obs : s->task.num_obs);
+        const void *obs_src = s->buf.p[B2G_T_OBS_CLIPPED] ? s->buf.p[B2G_T_OBS_CLIPPED] : s->buf.p[B2G_T_OBS];
+        for (int k = 0; k < K; k++) {
+            int rc = b2g_task_step(s, actions + (size_t)k * N * A, stream); if (rc) return rc;
+            CUDA_TRY(cudaMemcpyAsync(obs_out + (size_t)k * N * O, obs_src, N * O * 4, cudaMemcpyDeviceToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(rew_out + (size_t)k * N, s->buf.p[B2G_T_REW], N * 4, cudaMemcpyDeviceToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(reset_out + (size_t)k * N, s->buf.p[B2G_T_RESET], N * 8, cudaMemcpyDeviceToDevice, st));
+            if (timeout_out && s->buf.p[B2G_T_TIMEOUT]) CUDA_TRY(cudaMemcpyAsync(timeout_out + (size_t)k * N, s->buf.p[B2G_T_TIMEOUT], N, cudaMemcpyDeviceToDevice, st));
+        }
+        return B2G_OK;
+    }
+    int rc = require(s, {B2G_T_ROOT_STATE, B2G_T_DOF_STATE, B2G_T_OBS, B2G_T_REW, B2G_T_RESET, B2G_T_PROGRESS, B2G_T_RESET_COUNT,
+                         B2G_T_POTENTIALS, B2G_T_PREV_POTENTIALS, B2G_T_INITIAL_ROOT}, "b2g_task_rollout"); if (rc) return rc;
+    const b2g_task_params &P = s->task;
+    if (s->buf_bytes[B2G_T_OBS] < N * P.num_obs * 4) return fail(B2G_E_INVALID, "OBS buffer too small");
+    CUDA_TRY(cudaSetDevice(s->device));
+    constexpr int QB = 64, EPB = 16;
+    const int nd_ = 8, O = P.num_obs, ns6 = 6 * s->hm.nsens;
+    const size_t park_f4 = (size_t)quad_park_f4(2) * QB;
+    const size_t io_f4 = ((size_t)EPB * (13 + 2 * nd_ + 2 * nd_ + ns6) * 4 + 15) / 16;
+    const size_t model_f4 = quad_model_f4(2);
+    const size_t stage_f4 = ((size_t)EPB * (O * 4 + 4 + 8 + 1) + 15) / 16;
+    if ((size_t)EPB * (O * 4 + 4 * 2 + 12 * 2 + 8) > park_f4 * 16) return fail(B2G_E_UNSUPPORTED, "b2g_task_rollout: observation too large for the last-step staging");
+    RollArgs ra;
+    ra.actions = actions; ra.obs_out = obs_out; ra.rew_out = rew_out; ra.reset_out = (long long *)reset_out; ra.timeout_out = timeout_out;
+    ra.K = K; ra.io_f4 = (int)park_f4; ra.model_f4 = (int)(park_f4 + io_f4); ra.stage_f4 = (int)(park_f4 + io_f4 + model_f4);
+    const size_t dyn = (park_f4 + io_f4 + model_f4 + stage_f4) * 16;
+    const int grid = (int)N / EPB;
+#define QROLL(SP_)                                                                                                         \
+    do {                                                                                                                   \
+        int rc_ = set_smem(s, quad_rollout_kernel<2, SP_>, dyn); if (rc_) return rc_;                                      \
+        cudaLaunchConfig_t lc = {};                                                                                        \
+        lc.gridDim = dim3(grid); lc.blockDim = dim3(QB); lc.dynamicSmemBytes = dyn; lc.stream = st;                        \
+        cudaLaunchAttribute at[1];                                                                                         \
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                                     \
+        at[0].val.programmaticStreamSerializationAllowed = 1;                                                              \
+        lc.attrs = at; lc.numAttrs = 1;                                                                                    \
+        CUDA_TRY(cudaLaunchKernelEx(&lc, quad_rollout_kernel<2, SP_>, (const float4 *)s->d_qm, s->buf, P, (int)N, (int)s->hm.substeps, ra)); \
+    } while (0)
+    if (s->quad_spec == 3) QROLL(3); else QROLL(0);
+#undef QROLL
     s->launches++;
     CUDA_TRY(cudaGetLastError());
     return B2G_OK;

@@ -157,14 +157,14 @@ def lib():
         _lib.b2g_launch_count.restype = C.c_int64
         _lib.b2g_launch_count.argtypes = [C.c_void_p]
         for fn in ("b2g_plan", "b2g_create", "b2g_create_ext", "b2g_destroy", "b2g_bind", "b2g_simulate", "b2g_refresh_rigid_body_state",
-                   "b2g_set_task", "b2g_set_anymal_task", "b2g_set_hand_task", "b2g_task_step", "b2g_task_step_host", "b2g_reset_flagged"):
+                   "b2g_set_task", "b2g_set_anymal_task", "b2g_set_hand_task", "b2g_task_step", "b2g_task_step_host", "b2g_reset_flagged", "b2g_task_rollout"):
             getattr(_lib, fn).restype = C.c_int
     return _lib
 
 
 EXPORTS = ("b2g_plan", "b2g_create", "b2g_create_ext", "b2g_destroy", "b2g_bind", "b2g_simulate", "b2g_refresh_rigid_body_state", "b2g_set_task",
            "b2g_set_anymal_task", "b2g_set_hand_task", "b2g_task_step", "b2g_task_step_host", "b2g_launch_count", "b2g_last_error", "b2g_version",
-           "b2g_quad_chain_length", "b2g_reset_flagged")
+           "b2g_quad_chain_length", "b2g_reset_flagged", "b2g_task_rollout")
 
 
 class EngineError(RuntimeError):
@@ -318,6 +318,15 @@ class Sim:
         p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
         _check(lib().b2g_task_step_host(self._h, p(h_actions), p(h_obs), p(h_rew), p(h_reset), p(h_timeout),
                                         self._stream()), "b2g_task_step_host")
+
+    def task_rollout(self, actions, obs_out, rew_out, reset_out, timeout_out=None):
+        """K x task_step with all actions given up front (K, N, A); results of every step in the (K, N, .) outputs."""
+        for t in (actions, obs_out, rew_out, reset_out):
+            if not t.is_cuda or not t.is_contiguous():
+                raise EngineError("task_rollout: contiguous CUDA tensors expected")
+        p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        _check(lib().b2g_task_rollout(self._h, p(actions), C.c_int32(actions.shape[0]), p(obs_out), p(rew_out), p(reset_out),
+                                      p(timeout_out), self._stream()), "b2g_task_rollout")
 
     def reset_flagged(self):
         """reset_idx of every env whose reset flag is set (VecTask.reset_done)."""

@@ -268,6 +268,23 @@ class VecTask(Env):
             self.obs_dict["states"] = self.get_state()
         return self.obs_dict, self.rew_buf.to(self.rl_device), self.reset_buf.to(self.rl_device), self.extras
 
+    def rollout(self, actions: torch.Tensor):
+        """K steps whose actions are all known up front (K, num_envs, num_actions) -- an open-loop rollout such as the
+        reference's README loop under random actions (README.md:39-51).  Equivalent to
+            for k in range(K): obs[k], rew[k], reset[k], info = self.step(actions[k]); time_outs[k] = info["time_outs"]
+        and returns the stacked (obs, rew, reset, time_outs).  Ant runs the K steps in one launch (b2g_task_rollout)."""
+        if self.randomizer is not None or self.dr_randomizations or self.physical_randomizer is not None:
+            raise engine.EngineError("rollout: domain randomisation is configured; use step()")
+        a = actions.to(device=self.device, dtype=torch.float32).contiguous()
+        K = a.shape[0]
+        dev = self.device
+        obs = torch.empty((K, self.num_envs, self.num_obs), device=dev); rew = torch.empty((K, self.num_envs), device=dev)
+        reset = torch.empty((K, self.num_envs), device=dev, dtype=torch.long); tout = torch.empty((K, self.num_envs), device=dev, dtype=torch.uint8)
+        self.sim.task_rollout(a, obs, rew, reset, tout)
+        self.control_steps += K
+        self._fill_extras()
+        return obs.to(self.rl_device), rew.to(self.rl_device), reset.to(self.rl_device), tout.bool().to(self.rl_device)
+
     def step_host(self, h_actions, h_obs, h_rew, h_reset, h_timeout=None):
         """rl_device='cpu' fast path: the same step with host (pinned) buffers through
         b2g_task_step_host -- H2D actions, fused step, D2H obs/rew/reset, stream sync.  It runs none of step()'s
