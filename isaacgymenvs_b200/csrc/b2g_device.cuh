@@ -187,9 +187,17 @@ B2G_HD void matmul(const float A[9], const float B[9], float C[9]) {
         for (int j = 0; j < 3; j++)
             C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
 }
+// 1/sqrt(x) for x that is never denormal (sums of squares with a positive floor, SPD pivots): one MUFU, no range fix-up
+B2G_HD float b2g_rsqrt(float x) {
+#ifdef __CUDA_ARCH__
+    float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
 B2G_HD void quat_to_mat(const float q[4], float R[9]) {
     float x = q[0], y = q[1], z = q[2], w = q[3];
-    float inv = rsqrtf(x * x + y * y + z * z + w * w);
+    float inv = b2g_rsqrt(x * x + y * y + z * z + w * w);
     x *= inv; y *= inv; z *= inv; w *= inv;
     R[0] = 1.f - 2.f * (y * y + z * z); R[1] = 2.f * (x * y - z * w); R[2] = 2.f * (x * z + y * w);
     R[3] = 2.f * (x * y + z * w); R[4] = 1.f - 2.f * (x * x + z * z); R[5] = 2.f * (y * z - x * w);
@@ -213,6 +221,31 @@ B2G_HD void b2g_sincos(float a, float *s, float *c) {
 
 // packed symmetric 6x6:  IA[0..5] = A (xx yy zz xy xz yz), IA[6..14] = B row-major (ang x lin),
 // IA[15..20] = C (xx yy zz xy xz yz).   y = IA * (a ; l)
+// fused forms (one FMA per product: no separate add of a finished cross product / matrix-vector product)
+// out = c + a x b
+B2G_HD void cross_add(const float a[3], const float b[3], const float c[3], float out[3]) {
+    out[0] = fmaf(a[1], b[2], fmaf(-a[2], b[1], c[0]));
+    out[1] = fmaf(a[2], b[0], fmaf(-a[0], b[2], c[1]));
+    out[2] = fmaf(a[0], b[1], fmaf(-a[1], b[0], c[2]));
+}
+// acc += a x b
+B2G_HD void cross_acc(const float a[3], const float b[3], float acc[3]) {
+    acc[0] = fmaf(a[1], b[2], fmaf(-a[2], b[1], acc[0]));
+    acc[1] = fmaf(a[2], b[0], fmaf(-a[0], b[2], acc[1]));
+    acc[2] = fmaf(a[0], b[1], fmaf(-a[1], b[0], acc[2]));
+}
+// acc -= a x b
+B2G_HD void cross_sub(const float a[3], const float b[3], float acc[3]) {
+    acc[0] = fmaf(-a[1], b[2], fmaf(a[2], b[1], acc[0]));
+    acc[1] = fmaf(-a[2], b[0], fmaf(a[0], b[2], acc[1]));
+    acc[2] = fmaf(-a[0], b[1], fmaf(a[1], b[0], acc[2]));
+}
+// out = c + R v   (R row-major 3x3)
+B2G_HD void matvec_add(const float R[9], const float v[3], const float c[3], float out[3]) {
+    out[0] = fmaf(R[0], v[0], fmaf(R[1], v[1], fmaf(R[2], v[2], c[0])));
+    out[1] = fmaf(R[3], v[0], fmaf(R[4], v[1], fmaf(R[5], v[2], c[1])));
+    out[2] = fmaf(R[6], v[0], fmaf(R[7], v[1], fmaf(R[8], v[2], c[2])));
+}
 B2G_HD void sym6_mul(const float IA[21], const float a[3], const float l[3], float ya[3], float yl[3]) {
     const float *A = IA, *B = IA + 6, *C = IA + 15;
     ya[0] = A[0] * a[0] + A[3] * a[1] + A[4] * a[2] + B[0] * l[0] + B[1] * l[1] + B[2] * l[2];
@@ -221,6 +254,16 @@ B2G_HD void sym6_mul(const float IA[21], const float a[3], const float l[3], flo
     yl[0] = B[0] * a[0] + B[3] * a[1] + B[6] * a[2] + C[0] * l[0] + C[3] * l[1] + C[4] * l[2];
     yl[1] = B[1] * a[0] + B[4] * a[1] + B[7] * a[2] + C[3] * l[0] + C[1] * l[1] + C[5] * l[2];
     yl[2] = B[2] * a[0] + B[5] * a[1] + B[8] * a[2] + C[4] * l[0] + C[5] * l[1] + C[2] * l[2];
+}
+// (ya; yl) += IA (a; l)
+B2G_HD void sym6_mul_acc(const float IA[21], const float a[3], const float l[3], float ya[3], float yl[3]) {
+    const float *A = IA, *B = IA + 6, *C = IA + 15;
+    ya[0] = fmaf(A[0], a[0], fmaf(A[3], a[1], fmaf(A[4], a[2], fmaf(B[0], l[0], fmaf(B[1], l[1], fmaf(B[2], l[2], ya[0]))))));
+    ya[1] = fmaf(A[3], a[0], fmaf(A[1], a[1], fmaf(A[5], a[2], fmaf(B[3], l[0], fmaf(B[4], l[1], fmaf(B[5], l[2], ya[1]))))));
+    ya[2] = fmaf(A[4], a[0], fmaf(A[5], a[1], fmaf(A[2], a[2], fmaf(B[6], l[0], fmaf(B[7], l[1], fmaf(B[8], l[2], ya[2]))))));
+    yl[0] = fmaf(B[0], a[0], fmaf(B[3], a[1], fmaf(B[6], a[2], fmaf(C[0], l[0], fmaf(C[3], l[1], fmaf(C[4], l[2], yl[0]))))));
+    yl[1] = fmaf(B[1], a[0], fmaf(B[4], a[1], fmaf(B[7], a[2], fmaf(C[3], l[0], fmaf(C[1], l[1], fmaf(C[5], l[2], yl[1]))))));
+    yl[2] = fmaf(B[2], a[0], fmaf(B[5], a[1], fmaf(B[8], a[2], fmaf(C[4], l[0], fmaf(C[5], l[1], fmaf(C[2], l[2], yl[2]))))));
 }
 // IA += s * (ja; jl)(ja; jl)^T
 B2G_HD void sym6_rank1(float IA[21], float s, const float ja[3], const float jl[3]) {
@@ -253,7 +296,7 @@ B2G_HD void sym6_solve(const float IA[21], const float ba[3], const float bl[3],
             float s = M[i][j];
 #pragma unroll
             for (int k = 0; k < j; k++) s -= Lm[i][k] * Lm[j][k];
-            if (i == j) { dinv[i] = rsqrtf(s); Lm[i][i] = s * dinv[i]; }
+            if (i == j) { dinv[i] = b2g_rsqrt(s); Lm[i][i] = s * dinv[i]; }
             else Lm[i][j] = s * dinv[j];
         }
     }

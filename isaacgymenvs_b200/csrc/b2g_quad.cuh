@@ -42,7 +42,7 @@ __host__ __device__ constexpr int quad_park_f4(int ns) { return ns * QPOSE_F4 + 
 
 B2G_HD float q_rsqrt(float x) {
 #ifdef __CUDA_ARCH__
-    return rsqrtf(x);
+    float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;   // arguments are sums of squares + a positive floor: never denormal
 #else
     return 1.0f / sqrtf(x);
 #endif
@@ -124,9 +124,8 @@ struct QLane {
     // the sub-step, F0 - h G (J a), and its torque about the link origin, added to (F, T).
     struct SphereGeom { float pc[3], hg, n[3]; };
     B2G_HD void sphere_geom(const float4 cp, const float rp[3], const float R[9], const float x[3], SphereGeom &g) const {
-        g.pc[0] = x[0] + R[0] * cp.x + R[1] * cp.y + R[2] * cp.z;
-        g.pc[1] = x[1] + R[3] * cp.x + R[4] * cp.y + R[5] * cp.z;
-        g.pc[2] = x[2] + R[6] * cp.x + R[7] * cp.y + R[8] * cp.z;
+        const float cpl[3] = {cp.x, cp.y, cp.z};
+        matvec_add(R, cpl, x, g.pc);
         g.hg = 0.f; g.n[0] = 0.f; g.n[1] = 0.f; g.n[2] = 1.f;
         if (HF) ground(rp[0] + g.pc[0], rp[1] + g.pc[1], g.hg, g.n);
     }
@@ -150,8 +149,7 @@ struct QLane {
         float r[3];
         if (HF) { r[0] = pc[0] - cp.w * n[0]; r[1] = pc[1] - cp.w * n[1]; r[2] = pc[2] - cp.w * n[2]; }
         else { r[0] = pc[0]; r[1] = pc[1]; r[2] = pc[2] - cp.w; }
-        float wxr[3]; cross(vw, r, wxr);
-        const float uv[3] = {vl[0] + wxr[0], vl[1] + wxr[1], vl[2] + wxr[2]};
+        float uv[3]; cross_add(vw, r, vl, uv);
         const float un = HF ? dot3(uv, n) : uv[2];
         const float Fn = kn * d - gn * un;
         if (Fn <= 0.f) return;
@@ -163,8 +161,7 @@ struct QLane {
         if (HF) { F0[0] = Fn * n[0] - gam * ut[0]; F0[1] = Fn * n[1] - gam * ut[1]; F0[2] = Fn * n[2] - gam * ut[2]; }
         else { F0[0] = -gam * ut[0]; F0[1] = -gam * ut[1]; F0[2] = Fn; }
         if (ACCUM) {
-            float rxF[3]; cross(r, F0, rxF);
-            pa[0] -= rxF[0]; pa[1] -= rxF[1]; pa[2] -= rxF[2];
+            cross_sub(r, F0, pa);
             pl[0] -= F0[0]; pl[1] -= F0[1]; pl[2] -= F0[2];
             const float hgam = h * gam;
             if (HF) {
@@ -185,8 +182,7 @@ struct QLane {
                 I[15] += hgam; I[16] += hgam; I[17] += hgn;
             }
         } else {
-            float axr[3]; cross(aw, r, axr);
-            const float Ja[3] = {al[0] + axr[0], al[1] + axr[1], al[2] + axr[2]};
+            float Ja[3]; cross_add(aw, r, al, Ja);
             float Fk[3];
             if (HF) {
                 const float Jan = dot3(Ja, n);
@@ -196,9 +192,9 @@ struct QLane {
                 Fk[0] = F0[0] - h * gam * Ja[0]; Fk[1] = F0[1] - h * gam * Ja[1]; Fk[2] = F0[2] - h * gn * Ja[2];
             }
             const float rl[3] = {r[0] - x[0], r[1] - x[1], r[2] - x[2]};
-            float t[3]; cross(rl, Fk, t);
+            cross_acc(rl, Fk, T);
 #pragma unroll
-            for (int c = 0; c < 3; c++) { F[c] += Fk[c]; T[c] += t[c]; }
+            for (int c = 0; c < 3; c++) F[c] += Fk[c];
         }
     }
 
@@ -207,16 +203,15 @@ struct QLane {
     // da, dl: AssetOptions.angular_damping / linear_damping -- wrench (-da Icw w ; -dl m v_c) at the COM, explicit
     B2G_HD static void rigid_terms(float mass, const float Icw[6], const float c[3], const float vw[3], const float vl[3],
                                    const float g[3], float da, float dl, float I[21], float pa[3], float pl[3]) {
-        float vxc[3]; cross(vw, c, vxc);
-        const float l[3] = {mass * (vl[0] + vxc[0]), mass * (vl[1] + vxc[1]), mass * (vl[2] + vxc[2])};   // linear momentum
+        float vc[3]; cross_add(vw, c, vl, vc);
+        const float l[3] = {mass * vc[0], mass * vc[1], mass * vc[2]};                                    // linear momentum
         const float hc[3] = {Icw[0] * vw[0] + Icw[3] * vw[1] + Icw[4] * vw[2],
                              Icw[3] * vw[0] + Icw[1] * vw[1] + Icw[5] * vw[2],
                              Icw[4] * vw[0] + Icw[5] * vw[1] + Icw[2] * vw[2]};                           // angular momentum about the COM
-        float t1[3], t2[3];
-        cross(vw, l, t1);
-        pl[0] = t1[0] - mass * g[0] + dl * l[0]; pl[1] = t1[1] - mass * g[1] + dl * l[1]; pl[2] = t1[2] - mass * g[2] + dl * l[2];
-        cross(vw, hc, t1); cross(c, pl, t2);
-        pa[0] = t1[0] + t2[0] + da * hc[0]; pa[1] = t1[1] + t2[1] + da * hc[1]; pa[2] = t1[2] + t2[2] + da * hc[2];
+        pl[0] = fmaf(dl, l[0], -mass * g[0]); pl[1] = fmaf(dl, l[1], -mass * g[1]); pl[2] = fmaf(dl, l[2], -mass * g[2]);
+        cross_acc(vw, l, pl);
+        pa[0] = da * hc[0]; pa[1] = da * hc[1]; pa[2] = da * hc[2];
+        cross_acc(vw, hc, pa); cross_acc(c, pl, pa);
         const float hm[3] = {mass * c[0], mass * c[1], mass * c[2]};
         const float c2 = dot3(c, c);
         I[0] = Icw[0] + mass * c2 - hm[0] * c[0];
@@ -280,18 +275,14 @@ struct QLane {
                                      k1.z + cs * k3.w + sn * k6.x, k1.w + cs * k4.x + sn * k6.y, k2.x + cs * k4.y + sn * k6.z};
                 float R[9]; matmul(Rp, Rj, R);
                 const float axp[3] = {k6.w, k7.x, k7.y}, lp[3] = {k7.z, k7.w, k8.x};
-                float x[3], dd[3];
+                float x[3];
                 matvec(Rp, axp, w[s]);
-                matvec(Rp, lp, dd);
-                x[0] = xp[0] + dd[0]; x[1] = xp[1] + dd[1]; x[2] = xp[2] + dd[2];
+                matvec_add(Rp, lp, xp, x);
                 cross(x, w[s], sl[s]);
                 const float qds = qd[s];
                 const float wq[3] = {w[s][0] * qds, w[s][1] * qds, w[s][2] * qds}, slq[3] = {sl[s][0] * qds, sl[s][1] * qds, sl[s][2] * qds};
                 {   // velocity-product acceleration c = crm(v)(S qd)
-                    float a1[3], a2[3], a3[3];
-                    cross(vwp, wq, a1); cross(vwp, slq, a2); cross(vlp, wq, a3);
-#pragma unroll
-                    for (int c = 0; c < 3; c++) { cw[s][c] = a1[c]; cl[s][c] = a2[c] + a3[c]; }
+                    cross(vwp, wq, cw[s]); cross(vwp, slq, cl[s]); cross_acc(vlp, wq, cl[s]);
                 }
                 float vw[3], vl[3];
 #pragma unroll
@@ -321,8 +312,7 @@ struct QLane {
                 }
                 const float4 k9 = LK(s, 9);
                 const float cm_[3] = {k8.y, k8.z, k8.w};
-                float c_[3]; matvec(R, cm_, c_);
-                c_[0] += x[0]; c_[1] += x[1]; c_[2] += x[2];
+                float c_[3]; matvec_add(R, cm_, x, c_);
                 float Icw[6];
                 if (SP & 1) {
                     const float ul[3] = {k9.x, k9.y, k9.z};
@@ -374,17 +364,16 @@ struct QLane {
                 }
                 float Ua[3], Ul[3];
                 sym6_mul(I, w[s], sl[s], Ua, Ul);
-                const float D = dot3(w[s], Ua) + dot3(sl[s], Ul) + dgv[s];
+                const float D = fmaf(w[s][0], Ua[0], fmaf(w[s][1], Ua[1], fmaf(w[s][2], Ua[2], fmaf(sl[s][0], Ul[0], fmaf(sl[s][1], Ul[1], fmaf(sl[s][2], Ul[2], dgv[s]))))));
                 const float di = q_rcp(D);
-                const float u_ = tau[s] - (dot3(w[s], qa) + dot3(sl[s], ql));
+                const float u_ = fmaf(-w[s][0], qa[0], fmaf(-w[s][1], qa[1], fmaf(-w[s][2], qa[2], fmaf(-sl[s][0], ql[0], fmaf(-sl[s][1], ql[1], fmaf(-sl[s][2], ql[2], tau[s]))))));
                 U[s][0] = Ua[0]; U[s][1] = Ua[1]; U[s][2] = Ua[2]; U[s][3] = Ul[0]; U[s][4] = Ul[1]; U[s][5] = Ul[2];
                 Dinv[s] = di; u[s] = u_;
                 sym6_rank1(I, -di, Ua, Ul);                           // Ia = IA - U U^T / D
-                float ya[3], yl[3];
-                sym6_mul(I, cw[s], cl[s], ya, yl);
                 const float ud = u_ * di;
 #pragma unroll
-                for (int c = 0; c < 3; c++) { qa[c] += ya[c] + Ua[c] * ud; ql[c] += yl[c] + Ul[c] * ud; }
+                for (int c = 0; c < 3; c++) { qa[c] = fmaf(Ua[c], ud, qa[c]); ql[c] = fmaf(Ul[c], ud, ql[c]); }
+                sym6_mul_acc(I, cw[s], cl[s], qa, ql);
             }
 #pragma unroll
             for (int c = 0; c < 21; c++) IA[c] = I[c];
@@ -406,10 +395,10 @@ struct QLane {
                 const float am = on * H5.w, bm = on * H6.x, mo = on * H4.w * msc;
                 const float s_ = bm * dot3(uw, vw);
                 const float nO[3] = {am * vw[0] + s_ * uw[0], am * vw[1] + s_ * uw[1], am * vw[2] + s_ * uw[2]};     // A vw
-                float a1[3], a3[3];
-                cross(vw, nO, a1); cross(vw, vl, a3);
+                float a3[3];
+                cross_acc(vw, nO, pa); cross(vw, vl, a3);
 #pragma unroll
-                for (int c = 0; c < 3; c++) { pa[c] += a1[c] + da * nO[c]; pl[c] += mo * (a3[c] - g[c] + dl * vl[c]); }
+                for (int c = 0; c < 3; c++) { pa[c] = fmaf(da, nO[c], pa[c]); pl[c] += mo * (a3[c] - g[c] + dl * vl[c]); }
                 const float b0 = bm * uw[0], b1 = bm * uw[1], b2 = bm * uw[2];
                 IA[0] += am + b0 * uw[0]; IA[1] += am + b1 * uw[1]; IA[2] += am + b2 * uw[2];
                 IA[3] += b0 * uw[1]; IA[4] += b0 * uw[2]; IA[5] += b1 * uw[2];
@@ -492,9 +481,8 @@ struct QLane {
                             float *keep = nullptr) {
         if (!o.write) return;
         if (sensor >= 0 && o.sensor) {
-            float wb[3], bxF[3], Tb_[3], Fb[3], Tb[3];
-            matvec(R, sb, wb); cross(wb, F, bxF);
-            Tb_[0] = T[0] - bxF[0]; Tb_[1] = T[1] - bxF[1]; Tb_[2] = T[2] - bxF[2];
+            float wb[3], Tb_[3] = {T[0], T[1], T[2]}, Fb[3], Tb[3];
+            matvec(R, sb, wb); cross_sub(wb, F, Tb_);
             matTvec(R, F, Fb); matTvec(R, Tb_, Tb);
             float *d = o.sensor + 6 * sensor;
             d[0] = Fb[0]; d[1] = Fb[1]; d[2] = Fb[2]; d[3] = Tb[0]; d[4] = Tb[1]; d[5] = Tb[2];
@@ -520,8 +508,8 @@ struct QLane {
         for (int s = 0; s < NS; s++) {
 #pragma unroll
             for (int c = 0; c < 3; c++) { aw[c] += cw[s][c]; al[c] += cl[s][c]; }
-            const float Ua_ = U[s][0] * aw[0] + U[s][1] * aw[1] + U[s][2] * aw[2] + U[s][3] * al[0] + U[s][4] * al[1] + U[s][5] * al[2];
-            const float qdd = (u[s] - Ua_) * Dinv[s];
+            const float r_ = fmaf(-U[s][0], aw[0], fmaf(-U[s][1], aw[1], fmaf(-U[s][2], aw[2], fmaf(-U[s][3], al[0], fmaf(-U[s][4], al[1], fmaf(-U[s][5], al[2], u[s]))))));
+            const float qdd = r_ * Dinv[s];
 #pragma unroll
             for (int c = 0; c < 3; c++) { aw[c] += w[s][c] * qdd; al[c] += sl[s][c] * qdd; }
             qd[s] += h * qdd;
@@ -558,9 +546,9 @@ struct QLane {
     }
     B2G_HD void integrate_base(RootState &rs, const float awr[3], const float alr[3]) const {
         const float h = qm[0].x;
-        float wxv[3]; cross(rs.rw, rs.rv, wxv);
+        float av[3]; cross_add(rs.rw, rs.rv, alr, av);
 #pragma unroll
-        for (int c = 0; c < 3; c++) { rs.rw[c] += h * awr[c]; rs.rv[c] += h * (alr[c] + wxv[c]); }
+        for (int c = 0; c < 3; c++) { rs.rw[c] += h * awr[c]; rs.rv[c] += h * av[c]; }
 #pragma unroll
         for (int c = 0; c < 3; c++) rs.rp[c] += h * rs.rv[c];
         float wn2 = dot3(rs.rw, rs.rw);
