@@ -36,6 +36,17 @@
 #endif
 
 #define B2G_HD __host__ __device__ __forceinline__
+// arithmetic-form switches (see "fused forms" below; measured in DESIGN.md section 6)
+#ifndef B2G_FUSE_ADD
+#define B2G_FUSE_ADD 1
+#endif
+#ifndef B2G_FUSE_ACC
+#define B2G_FUSE_ACC 1
+#endif
+#ifndef B2G_RAW_RSQRT
+#define B2G_RAW_RSQRT 1
+#endif
+
 
 namespace b2g {
 
@@ -189,8 +200,10 @@ B2G_HD void matmul(const float A[9], const float B[9], float C[9]) {
 }
 // 1/sqrt(x) for x that is never denormal (sums of squares with a positive floor, SPD pivots): one MUFU, no range fix-up
 B2G_HD float b2g_rsqrt(float x) {
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) && B2G_RAW_RSQRT
     float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#elif defined(__CUDA_ARCH__)
+    return rsqrtf(x);
 #else
     return 1.0f / sqrtf(x);
 #endif
@@ -221,30 +234,56 @@ B2G_HD void b2g_sincos(float a, float *s, float *c) {
 
 // packed symmetric 6x6:  IA[0..5] = A (xx yy zz xy xz yz), IA[6..14] = B row-major (ang x lin),
 // IA[15..20] = C (xx yy zz xy xz yz).   y = IA * (a ; l)
-// fused forms (one FMA per product: no separate add of a finished cross product / matrix-vector product)
+// fused forms (one FMA per product: no separate add of a finished cross product / matrix-vector product).
+// B2G_FUSE_ADD: "out = c + product" forms (shorten the dependency chain); B2G_FUSE_ACC / the FUSE template argument:
+// "acc += product" forms -- fewer instructions, but the accumulator joins the dependency chain and the live range grows:
+// measured +0.6 us on the register-capped Ant kernel (128 registers, 44 instead of 32 spilled floats), -2 us on ANYmal
+// (196 registers, no spills), so the quad sub-step turns it on per chain length (QLane::FACC)
 // out = c + a x b
 B2G_HD void cross_add(const float a[3], const float b[3], const float c[3], float out[3]) {
+#if B2G_FUSE_ADD
     out[0] = fmaf(a[1], b[2], fmaf(-a[2], b[1], c[0]));
     out[1] = fmaf(a[2], b[0], fmaf(-a[0], b[2], c[1]));
     out[2] = fmaf(a[0], b[1], fmaf(-a[1], b[0], c[2]));
+#else
+    float t[3]; cross(a, b, t);
+    out[0] = c[0] + t[0]; out[1] = c[1] + t[1]; out[2] = c[2] + t[2];
+#endif
 }
 // acc += a x b
+template <bool FUSE = (B2G_FUSE_ACC != 0)>
 B2G_HD void cross_acc(const float a[3], const float b[3], float acc[3]) {
-    acc[0] = fmaf(a[1], b[2], fmaf(-a[2], b[1], acc[0]));
-    acc[1] = fmaf(a[2], b[0], fmaf(-a[0], b[2], acc[1]));
-    acc[2] = fmaf(a[0], b[1], fmaf(-a[1], b[0], acc[2]));
+    if (FUSE) {
+        acc[0] = fmaf(a[1], b[2], fmaf(-a[2], b[1], acc[0]));
+        acc[1] = fmaf(a[2], b[0], fmaf(-a[0], b[2], acc[1]));
+        acc[2] = fmaf(a[0], b[1], fmaf(-a[1], b[0], acc[2]));
+    } else {
+        float t[3]; cross(a, b, t);
+        acc[0] += t[0]; acc[1] += t[1]; acc[2] += t[2];
+    }
 }
 // acc -= a x b
+template <bool FUSE = (B2G_FUSE_ACC != 0)>
 B2G_HD void cross_sub(const float a[3], const float b[3], float acc[3]) {
-    acc[0] = fmaf(-a[1], b[2], fmaf(a[2], b[1], acc[0]));
-    acc[1] = fmaf(-a[2], b[0], fmaf(a[0], b[2], acc[1]));
-    acc[2] = fmaf(-a[0], b[1], fmaf(a[1], b[0], acc[2]));
+    if (FUSE) {
+        acc[0] = fmaf(-a[1], b[2], fmaf(a[2], b[1], acc[0]));
+        acc[1] = fmaf(-a[2], b[0], fmaf(a[0], b[2], acc[1]));
+        acc[2] = fmaf(-a[0], b[1], fmaf(a[1], b[0], acc[2]));
+    } else {
+        float t[3]; cross(a, b, t);
+        acc[0] -= t[0]; acc[1] -= t[1]; acc[2] -= t[2];
+    }
 }
 // out = c + R v   (R row-major 3x3)
 B2G_HD void matvec_add(const float R[9], const float v[3], const float c[3], float out[3]) {
+#if B2G_FUSE_ADD
     out[0] = fmaf(R[0], v[0], fmaf(R[1], v[1], fmaf(R[2], v[2], c[0])));
     out[1] = fmaf(R[3], v[0], fmaf(R[4], v[1], fmaf(R[5], v[2], c[1])));
     out[2] = fmaf(R[6], v[0], fmaf(R[7], v[1], fmaf(R[8], v[2], c[2])));
+#else
+    float t[3]; matvec(R, v, t);
+    out[0] = c[0] + t[0]; out[1] = c[1] + t[1]; out[2] = c[2] + t[2];
+#endif
 }
 B2G_HD void sym6_mul(const float IA[21], const float a[3], const float l[3], float ya[3], float yl[3]) {
     const float *A = IA, *B = IA + 6, *C = IA + 15;
@@ -256,7 +295,9 @@ B2G_HD void sym6_mul(const float IA[21], const float a[3], const float l[3], flo
     yl[2] = B[2] * a[0] + B[5] * a[1] + B[8] * a[2] + C[4] * l[0] + C[5] * l[1] + C[2] * l[2];
 }
 // (ya; yl) += IA (a; l)
+template <bool FUSE = (B2G_FUSE_ACC != 0)>
 B2G_HD void sym6_mul_acc(const float IA[21], const float a[3], const float l[3], float ya[3], float yl[3]) {
+    if (FUSE) {
     const float *A = IA, *B = IA + 6, *C = IA + 15;
     ya[0] = fmaf(A[0], a[0], fmaf(A[3], a[1], fmaf(A[4], a[2], fmaf(B[0], l[0], fmaf(B[1], l[1], fmaf(B[2], l[2], ya[0]))))));
     ya[1] = fmaf(A[3], a[0], fmaf(A[1], a[1], fmaf(A[5], a[2], fmaf(B[3], l[0], fmaf(B[4], l[1], fmaf(B[5], l[2], ya[1]))))));
@@ -264,6 +305,10 @@ B2G_HD void sym6_mul_acc(const float IA[21], const float a[3], const float l[3],
     yl[0] = fmaf(B[0], a[0], fmaf(B[3], a[1], fmaf(B[6], a[2], fmaf(C[0], l[0], fmaf(C[3], l[1], fmaf(C[4], l[2], yl[0]))))));
     yl[1] = fmaf(B[1], a[0], fmaf(B[4], a[1], fmaf(B[7], a[2], fmaf(C[3], l[0], fmaf(C[1], l[1], fmaf(C[5], l[2], yl[1]))))));
     yl[2] = fmaf(B[2], a[0], fmaf(B[5], a[1], fmaf(B[8], a[2], fmaf(C[4], l[0], fmaf(C[5], l[1], fmaf(C[2], l[2], yl[2]))))));
+    } else {
+    float ta[3], tl[3]; sym6_mul(IA, a, l, ta, tl);
+    ya[0] += ta[0]; ya[1] += ta[1]; ya[2] += ta[2]; yl[0] += tl[0]; yl[1] += tl[1]; yl[2] += tl[2];
+    }
 }
 // IA += s * (ja; jl)(ja; jl)^T
 B2G_HD void sym6_rank1(float IA[21], float s, const float ja[3], const float jl[3]) {

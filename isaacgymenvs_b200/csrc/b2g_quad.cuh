@@ -42,7 +42,7 @@ __host__ __device__ constexpr int quad_park_f4(int ns) { return ns * QPOSE_F4 + 
 
 B2G_HD float q_rsqrt(float x) {
 #ifdef __CUDA_ARCH__
-    float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;   // arguments are sums of squares + a positive floor: never denormal
+    return b2g_rsqrt(x);                                     // arguments are sums of squares + a positive floor: never denormal
 #else
     return 1.0f / sqrtf(x);
 #endif
@@ -75,6 +75,9 @@ struct QOutputs {
 //   bit 1  the base's inertia is axisymmetric AND its COM is at its origin: no first-moment terms at all.
 template <int NS, bool HF, int SP = 0>
 struct QLane {
+    // accumulate-into-FMA forms: on for the 3-link chains (ANYmal: 196 registers, nothing spills), off for the 2-link Ant
+    // kernel whose 128-register cap (14 warps per SM = one wave of 16384 envs) turns the longer live ranges into spills
+    static constexpr bool FACC = (B2G_FUSE_ACC != 0) && (NS >= 3);
     const float4 *qm;         // quad model (shared memory on the device)
     const int16_t *hf;        // height samples (global) or null
     float4 *park;             // this thread's parking column: rows at stride `pstride` float4
@@ -161,7 +164,7 @@ struct QLane {
         if (HF) { F0[0] = Fn * n[0] - gam * ut[0]; F0[1] = Fn * n[1] - gam * ut[1]; F0[2] = Fn * n[2] - gam * ut[2]; }
         else { F0[0] = -gam * ut[0]; F0[1] = -gam * ut[1]; F0[2] = Fn; }
         if (ACCUM) {
-            cross_sub(r, F0, pa);
+            cross_sub<FACC>(r, F0, pa);
             pl[0] -= F0[0]; pl[1] -= F0[1]; pl[2] -= F0[2];
             const float hgam = h * gam;
             if (HF) {
@@ -192,7 +195,7 @@ struct QLane {
                 Fk[0] = F0[0] - h * gam * Ja[0]; Fk[1] = F0[1] - h * gam * Ja[1]; Fk[2] = F0[2] - h * gn * Ja[2];
             }
             const float rl[3] = {r[0] - x[0], r[1] - x[1], r[2] - x[2]};
-            cross_acc(rl, Fk, T);
+            cross_acc<FACC>(rl, Fk, T);
 #pragma unroll
             for (int c = 0; c < 3; c++) F[c] += Fk[c];
         }
@@ -201,6 +204,7 @@ struct QLane {
     // rigid-body spatial inertia about O (world axes) and bias force p = v x* (I v) - gravity wrench, from the
     // rotational inertia about the COM in world axes (Icw), the COM about O (c) and the twist about O
     // da, dl: AssetOptions.angular_damping / linear_damping -- wrench (-da Icw w ; -dl m v_c) at the COM, explicit
+    template <bool FUSE>
     B2G_HD static void rigid_terms(float mass, const float Icw[6], const float c[3], const float vw[3], const float vl[3],
                                    const float g[3], float da, float dl, float I[21], float pa[3], float pl[3]) {
         float vc[3]; cross_add(vw, c, vl, vc);
@@ -208,10 +212,18 @@ struct QLane {
         const float hc[3] = {Icw[0] * vw[0] + Icw[3] * vw[1] + Icw[4] * vw[2],
                              Icw[3] * vw[0] + Icw[1] * vw[1] + Icw[5] * vw[2],
                              Icw[4] * vw[0] + Icw[5] * vw[1] + Icw[2] * vw[2]};                           // angular momentum about the COM
+        if (FUSE) {
         pl[0] = fmaf(dl, l[0], -mass * g[0]); pl[1] = fmaf(dl, l[1], -mass * g[1]); pl[2] = fmaf(dl, l[2], -mass * g[2]);
-        cross_acc(vw, l, pl);
+        cross_acc<true>(vw, l, pl);
         pa[0] = da * hc[0]; pa[1] = da * hc[1]; pa[2] = da * hc[2];
-        cross_acc(vw, hc, pa); cross_acc(c, pl, pa);
+        cross_acc<true>(vw, hc, pa); cross_acc<true>(c, pl, pa);
+        } else {
+        float t1[3], t2[3];
+        cross(vw, l, t1);
+        pl[0] = t1[0] - mass * g[0] + dl * l[0]; pl[1] = t1[1] - mass * g[1] + dl * l[1]; pl[2] = t1[2] - mass * g[2] + dl * l[2];
+        cross(vw, hc, t1); cross(c, pl, t2);
+        pa[0] = t1[0] + t2[0] + da * hc[0]; pa[1] = t1[1] + t2[1] + da * hc[1]; pa[2] = t1[2] + t2[2] + da * hc[2];
+        }
         const float hm[3] = {mass * c[0], mass * c[1], mass * c[2]};
         const float c2 = dot3(c, c);
         I[0] = Icw[0] + mass * c2 - hm[0] * c[0];
@@ -282,7 +294,7 @@ struct QLane {
                 const float qds = qd[s];
                 const float wq[3] = {w[s][0] * qds, w[s][1] * qds, w[s][2] * qds}, slq[3] = {sl[s][0] * qds, sl[s][1] * qds, sl[s][2] * qds};
                 {   // velocity-product acceleration c = crm(v)(S qd)
-                    cross(vwp, wq, cw[s]); cross(vwp, slq, cl[s]); cross_acc(vlp, wq, cl[s]);
+                    cross(vwp, wq, cw[s]); cross(vwp, slq, cl[s]); cross_acc<FACC>(vlp, wq, cl[s]);
                 }
                 float vw[3], vl[3];
 #pragma unroll
@@ -323,7 +335,7 @@ struct QLane {
                 } else {
                     rotate_inertia(R, k9.x, k9.y, k9.z, k9.w, k10.x, k10.y, Icw);
                 }
-                rigid_terms(k10.z, Icw, c_, vw, vl, g, da, dl, I, qa, ql);
+                rigid_terms<FACC>(k10.z, Icw, c_, vw, vl, g, da, dl, I, qa, ql);
                 {
                     float dummy[3];
                     if (HF) {
@@ -364,16 +376,22 @@ struct QLane {
                 }
                 float Ua[3], Ul[3];
                 sym6_mul(I, w[s], sl[s], Ua, Ul);
-                const float D = fmaf(w[s][0], Ua[0], fmaf(w[s][1], Ua[1], fmaf(w[s][2], Ua[2], fmaf(sl[s][0], Ul[0], fmaf(sl[s][1], Ul[1], fmaf(sl[s][2], Ul[2], dgv[s]))))));
+                float D, u_;
+                if (FACC) {
+                D = fmaf(w[s][0], Ua[0], fmaf(w[s][1], Ua[1], fmaf(w[s][2], Ua[2], fmaf(sl[s][0], Ul[0], fmaf(sl[s][1], Ul[1], fmaf(sl[s][2], Ul[2], dgv[s]))))));
+                u_ = fmaf(-w[s][0], qa[0], fmaf(-w[s][1], qa[1], fmaf(-w[s][2], qa[2], fmaf(-sl[s][0], ql[0], fmaf(-sl[s][1], ql[1], fmaf(-sl[s][2], ql[2], tau[s]))))));
+                } else {
+                D = dot3(w[s], Ua) + dot3(sl[s], Ul) + dgv[s];
+                u_ = tau[s] - (dot3(w[s], qa) + dot3(sl[s], ql));
+                }
                 const float di = q_rcp(D);
-                const float u_ = fmaf(-w[s][0], qa[0], fmaf(-w[s][1], qa[1], fmaf(-w[s][2], qa[2], fmaf(-sl[s][0], ql[0], fmaf(-sl[s][1], ql[1], fmaf(-sl[s][2], ql[2], tau[s]))))));
                 U[s][0] = Ua[0]; U[s][1] = Ua[1]; U[s][2] = Ua[2]; U[s][3] = Ul[0]; U[s][4] = Ul[1]; U[s][5] = Ul[2];
                 Dinv[s] = di; u[s] = u_;
                 sym6_rank1(I, -di, Ua, Ul);                           // Ia = IA - U U^T / D
                 const float ud = u_ * di;
 #pragma unroll
                 for (int c = 0; c < 3; c++) { qa[c] = fmaf(Ua[c], ud, qa[c]); ql[c] = fmaf(Ul[c], ud, ql[c]); }
-                sym6_mul_acc(I, cw[s], cl[s], qa, ql);
+                sym6_mul_acc<FACC>(I, cw[s], cl[s], qa, ql);
             }
 #pragma unroll
             for (int c = 0; c < 21; c++) IA[c] = I[c];
@@ -396,7 +414,7 @@ struct QLane {
                 const float s_ = bm * dot3(uw, vw);
                 const float nO[3] = {am * vw[0] + s_ * uw[0], am * vw[1] + s_ * uw[1], am * vw[2] + s_ * uw[2]};     // A vw
                 float a3[3];
-                cross_acc(vw, nO, pa); cross(vw, vl, a3);
+                cross_acc<FACC>(vw, nO, pa); cross(vw, vl, a3);
 #pragma unroll
                 for (int c = 0; c < 3; c++) { pa[c] = fmaf(da, nO[c], pa[c]); pl[c] += mo * (a3[c] - g[c] + dl * vl[c]); }
                 const float b0 = bm * uw[0], b1 = bm * uw[1], b2 = bm * uw[2];
@@ -482,7 +500,7 @@ struct QLane {
         if (!o.write) return;
         if (sensor >= 0 && o.sensor) {
             float wb[3], Tb_[3] = {T[0], T[1], T[2]}, Fb[3], Tb[3];
-            matvec(R, sb, wb); cross_sub(wb, F, Tb_);
+            matvec(R, sb, wb); cross_sub<true>(wb, F, Tb_);
             matTvec(R, F, Fb); matTvec(R, Tb_, Tb);
             float *d = o.sensor + 6 * sensor;
             d[0] = Fb[0]; d[1] = Fb[1]; d[2] = Fb[2]; d[3] = Tb[0]; d[4] = Tb[1]; d[5] = Tb[2];
@@ -508,7 +526,8 @@ struct QLane {
         for (int s = 0; s < NS; s++) {
 #pragma unroll
             for (int c = 0; c < 3; c++) { aw[c] += cw[s][c]; al[c] += cl[s][c]; }
-            const float r_ = fmaf(-U[s][0], aw[0], fmaf(-U[s][1], aw[1], fmaf(-U[s][2], aw[2], fmaf(-U[s][3], al[0], fmaf(-U[s][4], al[1], fmaf(-U[s][5], al[2], u[s]))))));
+            const float r_ = FACC ? fmaf(-U[s][0], aw[0], fmaf(-U[s][1], aw[1], fmaf(-U[s][2], aw[2], fmaf(-U[s][3], al[0], fmaf(-U[s][4], al[1], fmaf(-U[s][5], al[2], u[s]))))))
+                                  : u[s] - (U[s][0] * aw[0] + U[s][1] * aw[1] + U[s][2] * aw[2] + U[s][3] * al[0] + U[s][4] * al[1] + U[s][5] * al[2]);
             const float qdd = r_ * Dinv[s];
 #pragma unroll
             for (int c = 0; c < 3; c++) { aw[c] += w[s][c] * qdd; al[c] += sl[s][c] * qdd; }

@@ -171,6 +171,25 @@ class EngineError(RuntimeError):
     pass
 
 
+class UnmodelledPhysicsWarning(UserWarning):
+    """A physical effect the reference configuration switches on is not part of this engine's model."""
+
+
+_warned = set()
+
+
+def warn_self_collision(what, where):
+    """The reference enables self-collision for this actor (create_actor(..., collision_filter=0) or the asset's own
+    filter); the engine tests contact spheres against the ground / height field and the one free object only -- links of
+    one articulation can pass through each other.  Said once per actor kind, never silently dropped."""
+    import warnings
+    if what in _warned:
+        return
+    _warned.add(what)
+    warnings.warn(f"{what}: the reference enables self-collision here ({where}); this engine does not model link-link contact "
+                  "within an articulation (DESIGN.md section 7) -- limbs may interpenetrate", UnmodelledPhysicsWarning, stacklevel=3)
+
+
 _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
 if _raw_stream is None:                                     # older torch: the public (slower) accessor
     def _raw_stream(index):

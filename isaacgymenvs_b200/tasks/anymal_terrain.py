@@ -67,6 +67,7 @@ class AnymalTerrain(VecTask):
         opts = BuildOptions(collapse_fixed_joints=True, replace_cylinder_with_capsule=True, density=0.001,
                             fix_base_link=e["urdfAsset"]["fixBaseLink"], default_dof_drive_mode=DRIVE_EFFORT)
         model = copy.deepcopy(load_asset_file(_asset_root(), e["urdfAsset"]["file"], opts))
+        engine.warn_self_collision("AnymalTerrain", "anymal_terrain.py:282 create_actor(..., i, 0, 0)")
         self.num_dof, self.num_bodies = model.ndof, model.nb
         self.dof_names = list(model.dof_names)
         body_names = list(model.body_names)

@@ -62,6 +62,7 @@ class _Locomotion(VecTask):
                             max_angular_velocity=100.0 if self.HUMANOID else 64.0)     # humanoid.py:153-154, ant.py:151
         model = copy.deepcopy(load_asset_file(_asset_root(), asset_file, opts))
         if self.HUMANOID:
+            engine.warn_self_collision("Humanoid", "humanoid.py:194 create_actor(..., i, 0, 0)")
             feet = [model.body_names.index("right_foot"), model.body_names.index("left_foot")]   # humanoid.py:164-168
         else:
             feet = [i for i, n in enumerate(model.body_names) if "foot" in n]                   # ant.py:167-178

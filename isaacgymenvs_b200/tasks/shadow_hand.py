@@ -63,6 +63,7 @@ class ShadowHand(VecTask):
         opts = BuildOptions(fix_base_link=True, collapse_fixed_joints=True, disable_gravity=True, angular_damping=0.01,
                             capsule_mid_spheres=1)
         model = copy.deepcopy(load_asset_file(_asset_root(), a.get("assetFileName", "mjcf/open_ai_assets/hand/shadow_hand.xml"), opts))
+        engine.warn_self_collision("ShadowHand", "shadow_hand.py:359 create_actor(..., i, -1, 0): the MJCF's own contact pairs, finger vs finger")
         cube = load_asset_file(_asset_root(), a.get("assetFileNameBlock", "urdf/objects/cube_multicolor.urdf"), BuildOptions())
         self.fingertip_handles_np = np.array([model.body_names.index(n) for n in self.fingertips], dtype=np.int32)
         model.sensor_body = self.fingertip_handles_np.copy()                                                   # :292-296

@@ -214,3 +214,16 @@ def test_domain_randomisation_noise_matches_reference():
     assert r.update(0) and not r.update(5) and r.update(10) and not r.update(19) and r.update(20)
     with pytest.raises(NotImplementedError):
         Randomizer({"frequency": 1, "sim_params": {}})
+
+
+def test_self_collision_request_is_never_silent():
+    """Self-collision (create_actor collision_filter 0 / -1: humanoid.py:194, anymal_terrain.py:282, shadow_hand.py:359) is not
+    modelled; asking for it must be audible: one UnmodelledPhysicsWarning per actor kind."""
+    import warnings
+    from isaacgymenvs_b200 import engine
+    engine._warned.discard("probe")
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter("always")
+        engine.warn_self_collision("probe", "create_actor(..., 0, 0)")
+        engine.warn_self_collision("probe", "create_actor(..., 0, 0)")
+    assert len(rec) == 1 and issubclass(rec[0].category, engine.UnmodelledPhysicsWarning) and "self-collision" in str(rec[0].message)

@@ -89,7 +89,9 @@ def _compare(m, rg, dg, out_g, r64, d64, out, qtol=5e-5):
     dq = np.abs(dg[..., 0] - d64[..., 0])
     assert dq.max() < qtol and np.quantile(dq, 0.999) < 3e-5, (dq.max(), np.quantile(dq, 0.999))
     qerr = np.abs(dg[..., 1] - d64[..., 1]) / np.maximum(1.0, np.abs(d64[..., 1]))
-    assert qerr.max() < 2e-3, qerr.max()
+    # fp32 vs fp64 through a stiff contact: a handful of DOFs (feet pressed into the ground at > 30 rad/s) sit at ~2e-3,
+    # the bulk two orders of magnitude lower
+    assert qerr.max() < 4e-3 and np.quantile(qerr, 0.999) < 1e-3 and np.quantile(qerr, 0.99) < 2e-4, (qerr.max(), np.quantile(qerr, 0.999), np.quantile(qerr, 0.99))
     sensor, dfrc, nc = out_g
     if len(m.sensor_body):
         scale = max(1.0, np.abs(out["sensor"]).max())
