@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define B2G_VERSION 2
+#define B2G_VERSION 3
 #define B2G_MAX_LINKS 32
 #define B2G_MAX_CONTACT_POINTS 96
 #define B2G_MAX_BOXES 4
@@ -63,6 +63,13 @@ typedef struct {
      * anymal_terrain.py:225-226): damping acceleration -d v on every link's COM twist; clamp of the base's angular speed
      * (0 = no clamp) */
     float angular_damping, linear_damping, max_angular_velocity;
+    /* Self-collision = gym.create_actor(env, asset, pose, name, group, filter = 0) (humanoid.py:194): contact spheres of links
+     * that are not joint neighbours collide with each other.  self_pairs: ncp x ncp bytes, 1 = the ordered pair may collide
+     * (NULL / self_collide 0 = off).  Same contact law as the ground contact with these gains; generic sub-step only
+     * (ncp <= 64, no second actor); a four-chain model with self_collide set runs on the generic path. */
+    int32_t self_collide, pad_self;
+    const uint8_t *self_pairs;
+    float self_kn, self_cn, self_mu, pad_self2;
 } b2g_model;
 
 /* Optional extras of an environment with more than one actor (tasks/shadow_hand.py:338-383: hand, object, goal

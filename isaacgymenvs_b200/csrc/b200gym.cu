@@ -86,6 +86,7 @@ __device__ __forceinline__ Stepper<L, HF, BLOCK, OBJ> make_stepper(const DevMode
         st.acc = b2g_dyn_smem + sm->ns * SLOT_F4 * BLOCK + threadIdx.x;
     }
     st.lane = lane;
+    st.gmodel = nullptr;
     return st;
 }
 
@@ -116,6 +117,7 @@ __global__ void __launch_bounds__(BLOCK) simulate_kernel(const DevModel *__restr
     const int e = valid ? env : N - 1;
     const int nd = sm.nl - 1, NS = sm.ns;
     ST st = make_stepper<L, HF, BLOCK, OBJ>(&sm, hf, lane);
+    st.gmodel = gm;
     float *const root_row = (float *)B.p[B2G_T_ROOT_STATE] + 13 * (size_t)e * sm.root_stride;
     RootState rs; load_root(root_row, rs);
     ObjState ob;
@@ -223,6 +225,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? B2G_MINBLOCKS : (BLOCK 
     const int el = e - env0;                             // env index inside this block's tiles
     const int NS = sm.ns;
     ST st = make_stepper<L, HF, BLOCK>(&sm, hf, lane);
+    st.gmodel = gm;
     {
         const char *pk = reinterpret_cast<const char *>(&sm) + offsetof(DevModel, slots) + (size_t)sm.ns * MAX_LANES * sizeof(SlotRec);
         st.links = reinterpret_cast<const LinkC *>(pk);
@@ -449,6 +452,7 @@ __global__ void __launch_bounds__(BLOCK) cartpole_step_kernel(const DevModel *__
     const bool valid = env < N;
     const int e = valid ? env : N - 1;
     ST st = make_stepper<1, false, BLOCK>(&sm, nullptr, 0);
+    st.gmodel = gm;
     RootState rs; load_root((const float *)B.p[B2G_T_ROOT_STATE] + 13 * (size_t)e, rs);
     const float2 *dofs = (const float2 *)B.p[B2G_T_DOF_STATE] + (size_t)e * 2;
     const float a = fminf(fmaxf(actions_in[e], -P.clip_actions), P.clip_actions);
@@ -861,6 +865,28 @@ extern "C" int b2g_create_ext(const b2g_model *m, const b2g_model_ext *ext, cons
             h.reach = std::max(h.reach, dist[m->cp_link[k]] + sqrtf(cp[0] * cp[0] + cp[1] * cp[1] + cp[2] * cp[2]) + m->cp_radius[k]);
         }
     }
+    // self-collision tables (create_actor collision filter 0)
+    h.self_on = 0;
+    if (m->self_collide && m->self_pairs) {
+        if (ext && ext->obj_actor >= 0) { delete s; return fail(B2G_E_UNSUPPORTED, "b2g_create_ext: self-collision is not compiled into the object-enabled kernels"); }
+        if (m->ncp > 64 || m->nl > 32) { delete s; return fail(B2G_E_UNSUPPORTED, "b2g_create: self-collision supports at most 64 contact spheres / 32 links"); }
+        h.self_on = 1; h.self_kn = m->self_kn; h.self_cn = m->self_cn; h.self_mu = m->self_mu;
+        std::vector<int> inv(m->ncp);
+        for (int k = 0; k < m->ncp; k++) inv[order[k]] = k;
+        for (int i = 0; i < MAX_LINKS; i++) { h.link_slot[i] = -1; h.link_reach[i] = 0.f; h.link_pairs[i] = 0u; }
+        for (int k = 0; k < MAX_CP; k++) h.cp_pairs[k] = 0ull;
+        for (int a = 0; a < m->ncp; a++) {
+            const float *cp = m->cp_pos + 3 * a;
+            float &rch = h.link_reach[m->cp_link[a]];
+            rch = std::max(rch, sqrtf(cp[0] * cp[0] + cp[1] * cp[1] + cp[2] * cp[2]) + m->cp_radius[a]);
+            for (int b = 0; b < m->ncp; b++) {
+                if (!m->self_pairs[(size_t)a * m->ncp + b]) continue;
+                h.cp_pairs[inv[a]] |= 1ull << inv[b];
+                h.link_pairs[m->cp_link[a]] |= 1u << m->cp_link[b];
+            }
+        }
+        for (int sl = 0; sl < h.ns; sl++) for (int l = 0; l < h.lanes; l++) if (h.slots[sl][l].link > 0) h.link_slot[h.slots[sl][l].link] = (l << 8) | sl;
+    }
     // height field
     if (sp->hf_samples) {
         h.has_hf = 1; h.hf_nx = sp->hf_nx; h.hf_ny = sp->hf_ny;
@@ -876,7 +902,7 @@ extern "C" int b2g_create_ext(const b2g_model *m, const b2g_model_ext *ext, cons
         const char *nq = getenv("B2G_NO_QUAD"), *qb = getenv("B2G_QUAD_BLOCK"), *nz = getenv("B2G_NO_ZERO_COPY");
         s->no_zero_copy = nz != nullptr;
         if (qb && (atoi(qb) == 32 || atoi(qb) == 64 || atoi(qb) == 128)) s->quad_block = atoi(qb);
-        if (!(nq && nq[0] == '1') && !ext && !(force1 && force1[0] == '1') && !getenv("B2G_LANES") && !getenv("B2G_BLOCK")) {
+        if (!(nq && nq[0] == '1') && !ext && !h.self_on && !(force1 && force1[0] == '1') && !getenv("B2G_LANES") && !getenv("B2G_BLOCK")) {
             std::vector<float> qm; int leg_link[12], spec = 0;
             const char *nsp = getenv("B2G_QUAD_NO_SPEC");
             const int ns = quad_build(m, sp, qm, leg_link, &spec, (nsp && nsp[0] == '1') ? 0 : 3);

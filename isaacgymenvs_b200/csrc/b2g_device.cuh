@@ -112,6 +112,7 @@ struct alignas(16) DevModel {
     int ns, lanes, nacc;  // sweep steps per lane, lanes per env, accumulators per thread
     int root_acc;         // accumulator index collecting this lane's root children other than slot 0's (-1: none)
     int cross_lane;       // some slot's parent lives in another lane (needs the shared-memory handoff + __syncwarp)
+    int self_on;          // link-link contacts within the articulation (tables in the cold tail below)
     float ground_mu;      // friction of the ground material (combined per contact as the average, PhysX default)
     float ang_damp, lin_damp, max_angvel;   // AssetOptions.angular_damping / linear_damping / max_angular_velocity (0: no clamp)
     float obj_ang_damp, obj_lin_damp;       // the free object's own
@@ -138,6 +139,13 @@ struct alignas(16) DevModel {
     int link_parent[MAX_LINKS];
     float body_pos[MAX_LINKS][3];
     float body_quat[MAX_LINKS][4];
+    // ---- self-collision (create_actor collision filter 0): read through the GLOBAL copy of the model (Stepper::gmodel),
+    // a few broadcast loads per link and sub-step -- not worth shared memory in every kernel
+    float self_kn, self_cn, self_mu;
+    int link_slot[MAX_LINKS];             // ((lane << 8) | slot) of the link's slot, -1 for the root
+    float link_reach[MAX_LINKS];          // max over the link's spheres of |centre| + radius (link frame): broad phase
+    unsigned link_pairs[MAX_LINKS];       // bit j: some sphere of this link may collide with some sphere of link j
+    unsigned long long cp_pairs[MAX_CP];  // bit k (link-sorted sphere index): this sphere may collide with sphere k (ncp <= 64)
 };
 static_assert(offsetof(DevModel, slots) % 16 == 0 && offsetof(DevModel, links) % 16 == 0 && offsetof(DevModel, cps) % 16 == 0, "bulk-copy alignment");
 
@@ -541,6 +549,7 @@ struct Stepper {
     float4 *ss;               // this thread's column of the slot-state array
     float4 *acc;              // this thread's column of the accumulator pool
     int lane;
+    const DevModel *gmodel;   // the model's copy in global memory (self-collision tables), may be null when self_on == 0
 
     // Two layouts of the per-slot state.  Default: [slot][k][thread] -- every thread owns ns rows (idle slots included),
     // 128-bit accesses are conflict-free.  OBJ (few, large environments: the shared memory per env decides how many
@@ -600,6 +609,91 @@ struct Stepper {
     }
     // lanes of an env exchange slot state through shared memory: order the accesses
     __device__ __forceinline__ void lane_sync() const { if (L > 1 && m->cross_lane) __syncwarp(); }
+
+    // ---- self-collision: the spheres of link `li` (pose R, x, twist vw, vl about O) against the spheres of every link it
+    // may collide with.  Each link takes ITS side of a pair (the partner does the same from its lane): h J^T G J joins this
+    // link's inertia, -J^T F0 its bias -- implicit in its own acceleration, explicit in the partner's velocity (block-Jacobi,
+    // like the hand-object contact).  Broad phase: link-origin distance against the two links' sphere reach.
+    // j_first / j_step: the base's partner links are dealt round-robin to the lanes.
+    template <bool ACCUM>
+    __device__ __forceinline__ void self_contacts(int li, const LinkC &lk, const float R[9], const float x[3], const float vw[3], const float vl[3],
+                                                  float IA[21], float pa[3], float pl[3], const float aw[3], const float al[3],
+                                                  float F[3], float T[3], const RootState &rs, int j_first, int j_step) const {
+        const DevModel *gmd = gmodel;
+        unsigned lm = __ldg(&gmd->link_pairs[li]);
+        if (!lm || lk.cp_end <= lk.cp_begin) return;
+        const float h = m->h, skn = __ldg(&gmd->self_kn), gn = __ldg(&gmd->self_cn) + h * skn, smu = __ldg(&gmd->self_mu);
+        const float reach_i = __ldg(&gmd->link_reach[li]);
+        int jj = 0;
+#pragma unroll 1
+        while (lm) {
+            const int j = __ffs(lm) - 1;
+            lm &= lm - 1;
+            if ((jj++ % j_step) != j_first) continue;
+            float Rj[9], xj[3], vwj[3], vlj[3];
+            if (j == 0) {
+                root_pose(rs, Rj, vwj, vlj);
+                xj[0] = xj[1] = xj[2] = 0.f;
+            } else {
+                const int ref = __ldg(&gmd->link_slot[j]);
+                const float4 c = S4x(ref >> 8, ref & 255, 2);
+                xj[0] = c.y; xj[1] = c.z; xj[2] = c.w;
+            }
+            {
+                const float dx = x[0] - xj[0], dy = x[1] - xj[1], dz = x[2] - xj[2], rr = reach_i + __ldg(&gmd->link_reach[j]);
+                if (dx * dx + dy * dy + dz * dz >= rr * rr) continue;
+            }
+            if (j != 0) { const int ref = __ldg(&gmd->link_slot[j]); load_pose_x(ref >> 8, ref & 255, Rj, xj, vwj, vlj); }
+            const LinkC &lj = links[j];
+#pragma unroll 1
+            for (int n = lk.cp_begin; n < lk.cp_end; n++) {
+                const unsigned long long mask = __ldg(&gmd->cp_pairs[n]);
+                if (!mask) continue;
+                const CpC &cn_ = gr.cps[n];
+                const float pn[3] = {cn_.pos[0], cn_.pos[1], cn_.pos[2]};
+                float ci[3]; matvec_add(R, pn, x, ci);
+#pragma unroll 1
+                for (int k = lj.cp_begin; k < lj.cp_end; k++) {
+                    if (!((mask >> k) & 1ull)) continue;
+                    const CpC &ck_ = gr.cps[k];
+                    const float pk[3] = {ck_.pos[0], ck_.pos[1], ck_.pos[2]};
+                    float cj[3]; matvec_add(Rj, pk, xj, cj);
+                    const float dv[3] = {ci[0] - cj[0], ci[1] - cj[1], ci[2] - cj[2]};
+                    const float d2 = dot3(dv, dv), rsum = cn_.radius + ck_.radius;
+                    if (d2 >= rsum * rsum || d2 < 1e-12f) continue;
+                    const float inv = rsqrtf(d2), dist = d2 * inv, pen = rsum - dist;
+                    const float n[3] = {dv[0] * inv, dv[1] * inv, dv[2] * inv};            // force on THIS link: away from the partner
+                    const float off = cn_.radius - 0.5f * pen;                               // contact point: middle of the overlap
+                    const float r[3] = {ci[0] - off * n[0], ci[1] - off * n[1], ci[2] - off * n[2]};
+                    float ui[3], uj[3];
+                    cross_add(vw, r, vl, ui); cross_add(vwj, r, vlj, uj);
+                    const float rel[3] = {ui[0] - uj[0], ui[1] - uj[1], ui[2] - uj[2]};
+                    const float un = dot3(rel, n);
+                    const float Fn = skn * pen - gn * un;
+                    if (Fn <= 0.f) continue;
+                    const float ut[3] = {rel[0] - un * n[0], rel[1] - un * n[1], rel[2] - un * n[2]};
+                    const float gam = smu * Fn * rsqrtf(dot3(ut, ut) + m->vs2);
+                    const float F0[3] = {Fn * n[0] - gam * ut[0], Fn * n[1] - gam * ut[1], Fn * n[2] - gam * ut[2]};
+                    if (ACCUM) {
+                        contact_inertia(IA, h, gam, gn, r, n);
+                        float rxF[3]; cross(r, F0, rxF);
+#pragma unroll
+                        for (int c = 0; c < 3; c++) { pa[c] -= rxF[c]; pl[c] -= F0[c]; }
+                    } else {
+                        float Ja[3]; cross_add(aw, r, al, Ja);
+                        const float Jan = dot3(Ja, n);
+                        float Fk[3];
+#pragma unroll
+                        for (int c = 0; c < 3; c++) Fk[c] = F0[c] - h * (gam * Ja[c] + (gn - gam) * Jan * n[c]);
+                        const float rl[3] = {r[0] - x[0], r[1] - x[1], r[2] - x[2]};
+                        float tq[3]; cross(rl, Fk, tq);
+#pragma unroll
+                        for (int c = 0; c < 3; c++) { F[c] += Fk[c]; T[c] += tq[c]; }
+                    }
+                }
+            }
+        }
+    }
 
     // ---- one sub-step.  LAST: also produce contact wrench / joint force outputs (see Outputs)
     struct Outputs {
@@ -942,6 +1036,7 @@ struct Stepper {
         // A slot's projected inertia either travels in registers to the next-lower slot of the lane
         // (chains; finally from slot 0 to the root) or is parked in one of this thread's accumulators,
         // from where its parent -- possibly in another lane -- collects it (SlotRec::child).
+        if (!OBJ && L > 1 && m->self_on && !m->cross_lane) __syncwarp();   // every lane's link poses are needed by every other
         const int racc = m->root_acc >= 0 ? lane_acc(m->root_acc) : -1;
         if (racc >= 0) {
 #pragma unroll
@@ -967,6 +1062,7 @@ struct Stepper {
                     float dummy[3];
                     if (ground) link_contacts<true, HF>(m, gr, lk, rs.rp, R, x, vw, vl, I, qa, ql, dummy, dummy, dummy, dummy, 0, 1);
                     if (OBJ) obj_link_contacts<true>(lk, sr.link, R, x, vw, vl, I, qa, ql, dummy, dummy, dummy, dummy, 0, 1);
+                    if (!OBJ && m->self_on) self_contacts<true>(sr.link, lk, R, x, vw, vl, I, qa, ql, dummy, dummy, dummy, dummy, rs, 0, 1);
                     if (carry) {
 #pragma unroll
                         for (int c = 0; c < 21; c++) I[c] += IA[c];
@@ -1053,6 +1149,7 @@ struct Stepper {
             link_inertia(lk, mine ? lk.mass : 0.f, mine ? 1.f : 0.f, Rr, xr, vwr, vlr, g, I, qa, ql, m->ang_damp, m->lin_damp);
             if (ground) link_contacts<true, HF>(m, gr, lk, rs.rp, Rr, xr, vwr, vlr, I, qa, ql, dummy, dummy, dummy, dummy, lane, L);
             if (OBJ) obj_link_contacts<true>(lk, 0, Rr, xr, vwr, vlr, I, qa, ql, dummy, dummy, dummy, dummy, lane, L);
+            if (!OBJ && m->self_on) self_contacts<true>(0, lk, Rr, xr, vwr, vlr, I, qa, ql, dummy, dummy, dummy, dummy, rs, lane, L);
 #pragma unroll
             for (int c = 0; c < 21; c++) IA[c] += I[c];               // IA holds slot 0's contribution (or zeros)
 #pragma unroll
@@ -1081,6 +1178,7 @@ struct Stepper {
                 float F[3] = {0.f, 0.f, 0.f}, T[3] = {0.f, 0.f, 0.f};
                 if (ground) link_contacts<false, HF>(m, gr, lk, rs.rp, Rr, xr, vwr, vlr, I, qa, ql, awr, alr, F, T, lane, L);
                 if (OBJ) obj_link_contacts<false>(lk, 0, Rr, xr, vwr, vlr, I, qa, ql, awr, alr, F, T, lane, L);
+                if (!OBJ && m->self_on) self_contacts<false>(0, lk, Rr, xr, vwr, vlr, I, qa, ql, awr, alr, F, T, rs, lane, L);
 #pragma unroll
                 for (int c = 0; c < 3; c++) { F[c] = lane_sum<L>(F[c]); T[c] = lane_sum<L>(T[c]); }
                 if (lane == 0) emit_wrench(0, lk, Rr, F, T, o);
@@ -1130,6 +1228,7 @@ struct Stepper {
                             load_pose(s, R, x, vw, vl);
                             if (ground) link_contacts<false, HF>(m, gr, lk, rs.rp, R, x, vw, vl, dI, d3, d3, awc, alc, F, T, 0, 1);
                             if (OBJ) obj_link_contacts<false>(lk, li, R, x, vw, vl, dI, d3, d3, awc, alc, F, T, 0, 1);
+                            if (!OBJ && m->self_on) self_contacts<false>(li, lk, R, x, vw, vl, dI, d3, d3, awc, alc, F, T, rs, 0, 1);
                             emit_wrench(li, lk, R, F, T, o);
                         } else if (lk.sensor >= 0 || (o.net_contact && m->link_body[li] >= 0)) {
                             float R[9], x[3]; const float z[3] = {0.f, 0.f, 0.f};

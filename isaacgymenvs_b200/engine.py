@@ -67,7 +67,9 @@ class CModel(C.Structure):
                                           "damping", "stiffness", "lower", "upper", "effort", "kp", "kd", "limit_k",
                                           "limit_d", "cp_pos", "cp_radius", "cp_mu", "body_pos", "body_quat")] + \
                [("contact_kn", C.c_float), ("contact_cn", C.c_float), ("contact_vs", C.c_float),
-                ("angular_damping", C.c_float), ("linear_damping", C.c_float), ("max_angular_velocity", C.c_float)]
+                ("angular_damping", C.c_float), ("linear_damping", C.c_float), ("max_angular_velocity", C.c_float),
+                ("self_collide", C.c_int32), ("pad_self", C.c_int32), ("self_pairs", C.c_void_p),
+                ("self_kn", C.c_float), ("self_cn", C.c_float), ("self_mu", C.c_float), ("pad_self2", C.c_float)]
 
 
 class CModelExt(C.Structure):
@@ -221,6 +223,11 @@ def pack_model(model, ground_mu=1.0):
     cm.effort = arr("effort", np.minimum(model.effort, 3e38), np.float32)
     cm.cp_mu = arr("cp_mu", np.asarray(model.cp_mu), np.float32)
     cm.contact_kn, cm.contact_cn, cm.contact_vs = model.contact_kn, model.contact_cn, model.contact_vs
+    cm.self_collide = 0
+    if getattr(model, "self_collide", False):
+        cm.self_collide = 1
+        cm.self_pairs = arr("self_pairs", model.self_pairs, np.uint8)
+        cm.self_kn, cm.self_cn, cm.self_mu = float(model.self_kn), float(model.self_cn), float(model.self_mu)
     cm.angular_damping = float(getattr(model, "angular_damping", 0.0) or 0.0)
     cm.linear_damping = float(getattr(model, "linear_damping", 0.0) or 0.0)
     cm.max_angular_velocity = float(getattr(model, "max_angular_velocity", 0.0) or 0.0)

@@ -186,6 +186,12 @@ class Model:
     angular_damping: float = 0.0
     linear_damping: float = 0.0
     max_angular_velocity: float = 64.0
+    # self-collision (create_actor collision filter 0: humanoid.py:194, anymal_terrain.py:282): set by enable_self_collision()
+    self_collide: bool = False
+    self_pairs: np.ndarray = None        # (ncp, ncp) uint8, 1 = the ordered pair of contact spheres may collide
+    self_kn: float = 0.0
+    self_cn: float = 0.0
+    self_mu: float = 1.0
     build_options: dict = None           # the BuildOptions this model was compiled with (checked when a committed blob stands in for the XML)
     default_root_pos: np.ndarray = None  # body pose from the file (Ant overrides it at create_actor)
     default_root_quat: np.ndarray = None
@@ -233,6 +239,54 @@ class Model:
                     pass
             setattr(m, k, v)
         return m
+
+
+def enable_self_collision(m: "Model", kn_scale=0.25, mu=1.0):
+    """create_actor(..., collision_filter=0): links of the articulation collide with each other.  Candidate pairs = contact
+    spheres on links that are not joint neighbours (same link, or parent / child through massless intermediate links of a
+    compound joint, never collide -- PhysX filters those too), and whose spheres do not already overlap in the reference
+    pose q = 0 (adjacent capsules of a chain share end spheres by construction).  Gains: a quarter of the ground-contact
+    stiffness (limb against limb: the bodies are a fraction of the actor's mass), critical damping scaled with it;
+    friction mu = the MJCF default geom friction under PhysX's average combine mode."""
+    ncp = len(m.cp_link)
+    carrier = set(int(l) for l in m.body_link)
+
+    def up(l):
+        l = int(m.parent[l])
+        while l >= 0 and l not in carrier:
+            l = int(m.parent[l])
+        return l
+    link = np.array([int(l) for l in m.cp_link])
+    # spheres are attached to links; a massless intermediate link carries none, so "neighbour" is decided on carrying links
+    def carrying(l):
+        while l >= 0 and l not in carrier:
+            l = int(m.parent[l])
+        return l
+    cl = np.array([carrying(int(l)) for l in link])
+    anc = np.array([up(int(l)) if l >= 0 else -1 for l in cl])
+    # reference pose: world centres at q = 0 (root at the origin)
+    from . import rot
+    nl = m.nl
+    Rw = [np.eye(3)] * nl; pw = [np.zeros(3)] * nl
+    for i in range(1, nl):
+        pa = int(m.parent[i])
+        Rw[i] = Rw[pa] @ rot.quat_to_mat(m.lquat[i]); pw[i] = pw[pa] + Rw[pa] @ np.asarray(m.lpos[i], float)
+    wc = np.array([pw[link[n]] + Rw[link[n]] @ np.asarray(m.cp_pos[n], float) for n in range(ncp)])
+    rad = np.asarray(m.cp_radius, float)
+    pairs = np.zeros((ncp, ncp), np.uint8)
+    for a in range(ncp):
+        for b in range(ncp):
+            if cl[a] == cl[b] or anc[a] == cl[b] or anc[b] == cl[a]:
+                continue
+            if np.linalg.norm(wc[a] - wc[b]) < rad[a] + rad[b]:           # overlapping by construction
+                continue
+            pairs[a, b] = 1
+    m.self_pairs = pairs
+    m.self_kn = float(kn_scale * m.contact_kn)
+    m.self_cn = float(np.sqrt(kn_scale) * m.contact_cn)
+    m.self_mu = float(mu)
+    m.self_collide = True
+    return m
 
 
 def finalize_limits(m: "Model", pen_rad=0.02, tau_s=0.01):

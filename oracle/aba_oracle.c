@@ -96,6 +96,13 @@ typedef struct {
      * every link's COM twist is damped with acceleration -d v (wrench -d_a Ic w ; -d_l m v_c, explicit), the base's angular
      * speed is clamped after integration; same for the free object (its own AssetOptions, shadow_hand.py:279-282) */
     double angular_damping, linear_damping, max_angular_velocity, obj_angular_damping, obj_linear_damping;
+    /* self-collision (create_actor collision filter 0: humanoid.py:194, anymal_terrain.py:282): contact spheres of links that
+     * are not joint neighbours against each other.  Same linearised spring / damper / regularised-friction law as the
+     * ground contact with its own gains; block-Jacobi like the hand-object contact: each link is implicit in its own
+     * acceleration (h J^T G J joins ITS articulated inertia), explicit in the other link's velocity. */
+    int self_on, pad3;
+    const unsigned char *self_pairs;        /* ncp x ncp, 1 = this ordered pair may collide */
+    double self_kn, self_cn, self_mu;
 } OracleModel;
 
 /* ---------------------------------------------------------------- small linear algebra */
@@ -356,6 +363,53 @@ static void substep(const OracleModel *m, real h, real *root, real *dof, const r
         for (int a_ = 0; a_ < 6; a_++) { real s = 0; for (int k = 0; k < 3; k++) s += J[6 * k + a_] * cF0[n][k]; pA[i][a_] -= s; }
     }
 
+    /* ---- self-collision: sphere n of link i against sphere k of link j (ordered pairs: each link takes its own side) */
+    static __thread real sF0[4 * MAXCP][3], sG[4 * MAXCP][9], sJ[4 * MAXCP][18], sPc[4 * MAXCP][3]; static __thread int slink[4 * MAXCP], sbody[4 * MAXCP];
+    int nsc = 0;
+    if (m->self_on && m->self_pairs) {
+        static __thread real wcs[MAXCP][3];
+        for (int n = 0; n < m->ncp; n++) {
+            int i = m->cp_link[n];
+            real lp[3] = {(real)m->cp_pos[3 * n], (real)m->cp_pos[3 * n + 1], (real)m->cp_pos[3 * n + 2]};
+            mat3_vec(Rw[i], lp, wcs[n]); for (int k = 0; k < 3; k++) wcs[n][k] += pw[i][k];
+        }
+        const real skn = (real)m->self_kn, sgn = (real)m->self_cn + h * (real)m->self_kn;
+        for (int n = 0; n < m->ncp; n++) for (int k2 = 0; k2 < m->ncp; k2++) {
+            if (!m->self_pairs[n * m->ncp + k2]) continue;
+            real dv[3] = {wcs[n][0] - wcs[k2][0], wcs[n][1] - wcs[k2][1], wcs[n][2] - wcs[k2][2]};
+            real rs_ = (real)m->cp_radius[n] + (real)m->cp_radius[k2];
+            real d2 = dv[0] * dv[0] + dv[1] * dv[1] + dv[2] * dv[2];
+            if (d2 >= rs_ * rs_ || d2 < (real)1e-12 || nsc >= 4 * MAXCP) continue;
+            real dist = SQRT(d2), pen = rs_ - dist;
+            real nrm[3] = {dv[0] / dist, dv[1] / dist, dv[2] / dist};             /* force on link i: away from sphere k2 */
+            real off = (real)m->cp_radius[n] - (real)0.5 * pen;                     /* contact point: middle of the overlap */
+            real pc[3] = {wcs[n][0] - off * nrm[0], wcs[n][1] - off * nrm[1], wcs[n][2] - off * nrm[2]};
+            int i = m->cp_link[n], j = m->cp_link[k2];
+            /* point velocities of both links at pc (world axes) */
+            real ri[3] = {pc[0] - pw[i][0], pc[1] - pw[i][1], pc[2] - pw[i][2]}, rj[3] = {pc[0] - pw[j][0], pc[1] - pw[j][1], pc[2] - pw[j][2]};
+            real ril[3], rjl[3], t_[3], uil[3], ujl[3], uiw[3], ujw[3];
+            mat3T_vec(Rw[i], ri, ril); cross3(v[i], ril, t_); for (int k = 0; k < 3; k++) uil[k] = v[i][3 + k] + t_[k]; mat3_vec(Rw[i], uil, uiw);
+            mat3T_vec(Rw[j], rj, rjl); cross3(v[j], rjl, t_); for (int k = 0; k < 3; k++) ujl[k] = v[j][3 + k] + t_[k]; mat3_vec(Rw[j], ujl, ujw);
+            real rel[3] = {uiw[0] - ujw[0], uiw[1] - ujw[1], uiw[2] - ujw[2]};
+            real un = rel[0] * nrm[0] + rel[1] * nrm[1] + rel[2] * nrm[2];
+            real Fn = skn * pen - sgn * un;
+            if (Fn <= 0) continue;
+            real ut[3] = {rel[0] - un * nrm[0], rel[1] - un * nrm[1], rel[2] - un * nrm[2]};
+            real gam = (real)m->self_mu * Fn / SQRT(ut[0] * ut[0] + ut[1] * ut[1] + ut[2] * ut[2] + (real)(m->vs * m->vs));
+            real F0_[3], Gw_[9], B_[18], rx_[9], J_[18], GJ_[18];
+            for (int k = 0; k < 3; k++) F0_[k] = Fn * nrm[k] - gam * ut[k];
+            for (int a_ = 0; a_ < 3; a_++) for (int b_ = 0; b_ < 3; b_++) Gw_[3 * a_ + b_] = (a_ == b_ ? gam : 0) + (sgn - gam) * nrm[a_] * nrm[b_];
+            skew(ril, rx_);
+            for (int a_ = 0; a_ < 3; a_++) for (int b_ = 0; b_ < 3; b_++) { B_[6 * a_ + b_] = -rx_[3 * a_ + b_]; B_[6 * a_ + 3 + b_] = (a_ == b_); }
+            for (int a_ = 0; a_ < 3; a_++) for (int b_ = 0; b_ < 6; b_++) { real s_ = 0; for (int k = 0; k < 3; k++) s_ += Rw[i][3 * a_ + k] * B_[6 * k + b_]; J_[6 * a_ + b_] = s_; }
+            for (int a_ = 0; a_ < 3; a_++) for (int b_ = 0; b_ < 6; b_++) { real s_ = 0; for (int k = 0; k < 3; k++) s_ += Gw_[3 * a_ + k] * J_[6 * k + b_]; GJ_[6 * a_ + b_] = s_; }
+            for (int a_ = 0; a_ < 6; a_++) for (int b_ = 0; b_ < 6; b_++) { real s_ = 0; for (int k = 0; k < 3; k++) s_ += J_[6 * k + a_] * GJ_[6 * k + b_]; IA[i][6 * a_ + b_] += h * s_; }
+            for (int a_ = 0; a_ < 6; a_++) { real s_ = 0; for (int k = 0; k < 3; k++) s_ += J_[6 * k + a_] * F0_[k]; pA[i][a_] -= s_; }
+            memcpy(sF0[nsc], F0_, sizeof(F0_)); memcpy(sG[nsc], Gw_, sizeof(Gw_)); memcpy(sJ[nsc], J_, sizeof(J_)); memcpy(sPc[nsc], pc, sizeof(pc));
+            slink[nsc] = i; sbody[nsc] = m->cp_body[n]; nsc++;
+        }
+    }
+
     /* ---- the free object: contacts with the articulation (block-Jacobi implicit: each body sees its own
      * acceleration implicitly, the other's velocity explicitly), with the ground, then its own 6x6 solve */
     static __thread real oF0[MAXCP + 64][3], oG[MAXCP + 64][9], oJ[MAXCP + 64][18]; static __thread int olink[MAXCP + 64], obody[MAXCP + 64]; static __thread real oPc[MAXCP + 64][3];
@@ -541,6 +595,20 @@ static void substep(const OracleModel *m, real h, real *root, real *dof, const r
         real bp[3] = {(real)m->body_pos[3 * b], (real)m->body_pos[3 * b + 1], (real)m->body_pos[3 * b + 2]}, wb[3], arm[3], tq[3];
         mat3_vec(Rw[i], bp, wb);
         for (int k = 0; k < 3; k++) arm[k] = (wc[k] - (real)m->cp_radius[n] * nrm[k]) - (pw[i][k] + wb[k]);
+        cross3(arm, F, tq);
+        for (int k = 0; k < 3; k++) { cf_body[3 * b + k] += F[k]; cf_torque_body[3 * b + k] += tq[k]; }
+    }
+
+    /* ---- self-contacts: force applied to each side's own body over the sub-step */
+    for (int n = 0; n < nsc && cf_body; n++) {
+        int i = slink[n], b = sbody[n];
+        real Ja[3], F[3];
+        for (int a_ = 0; a_ < 3; a_++) { real s_ = 0; for (int k = 0; k < 6; k++) s_ += sJ[n][6 * a_ + k] * a[i][k]; Ja[a_] = s_; }
+        for (int a_ = 0; a_ < 3; a_++) { real s_ = 0; for (int k = 0; k < 3; k++) s_ += sG[n][3 * a_ + k] * Ja[k]; F[a_] = sF0[n][a_] - h * s_; }
+        if (b < 0) continue;
+        real bp[3] = {(real)m->body_pos[3 * b], (real)m->body_pos[3 * b + 1], (real)m->body_pos[3 * b + 2]}, wb[3], arm[3], tq[3];
+        mat3_vec(Rw[i], bp, wb);
+        for (int k = 0; k < 3; k++) arm[k] = sPc[n][k] - (pw[i][k] + wb[k]);
         cross3(arm, F, tq);
         for (int k = 0; k < 3; k++) { cf_body[3 * b + k] += F[k]; cf_torque_body[3 * b + k] += tq[k]; }
     }

@@ -38,7 +38,9 @@ class _CModel(C.Structure):
                 ("nten", C.c_int), ("pad2", C.c_int), ("ten_dof", C.c_void_p), ("ten_coef", C.c_void_p),
                 ("ten_range", C.c_void_p), ("ten_k", C.c_double), ("ten_d", C.c_double),
                 ("angular_damping", C.c_double), ("linear_damping", C.c_double), ("max_angular_velocity", C.c_double),
-                ("obj_angular_damping", C.c_double), ("obj_linear_damping", C.c_double)]
+                ("obj_angular_damping", C.c_double), ("obj_linear_damping", C.c_double),
+                ("self_on", C.c_int), ("pad3", C.c_int), ("self_pairs", C.c_void_p),
+                ("self_kn", C.c_double), ("self_cn", C.c_double), ("self_mu", C.c_double)]
 
 
 def object_contact_gains(mass):
@@ -88,6 +90,11 @@ class OracleSim:
         cm.angular_damping = float(getattr(m, "angular_damping", 0.0) or 0.0)
         cm.linear_damping = float(getattr(m, "linear_damping", 0.0) or 0.0)
         cm.max_angular_velocity = float(getattr(m, "max_angular_velocity", 0.0) or 0.0)
+        cm.self_on = 0
+        if getattr(m, "self_collide", False):
+            cm.self_on = 1
+            cm.self_pairs = arr("self_pairs", m.self_pairs, np.uint8)
+            cm.self_kn, cm.self_cn, cm.self_mu = float(m.self_kn), float(m.self_cn), float(m.self_mu)
         # free object (ShadowHand's cube): obj = dict(mass, inertia(3), half(3), mu, gravity_on)
         cm.obj_on = 0
         if obj is not None:
