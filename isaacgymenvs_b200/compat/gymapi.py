@@ -336,8 +336,13 @@ class Gym:
         elif k - 1 >= len(sim.extra_assets) or sim.extra_assets[k - 1] is not asset:
             raise NotImplementedError("every env holds the same actors in the same order")
         if env.index == 0 and filter <= 0 and getattr(asset, "model", None) is not None and getattr(asset.model, "ndof", 0) > 2:
-            from .. import engine as _engine                 # filter 0 / -1: self-collision on in PhysX; not modelled here
-            _engine.warn_self_collision(f"actor '{name}'", f"create_actor(..., collision_filter={filter})")
+            from .. import engine as _engine                 # filter 0: PhysX collides the actor's links with each other
+            from ..importer.model import enable_self_collision, self_collision_supported
+            if filter == 0 and k == 0 and self_collision_supported(asset.model):
+                if not getattr(asset.model, "self_collide", False):
+                    enable_self_collision(asset.model)
+            else:                                            # four-chain kernels, asset-defined pairs (-1), later actors: said, not dropped
+                _engine.warn_self_collision(f"actor '{name}'", f"create_actor(..., collision_filter={filter})")
         env.actors.append(name)
         env.actor_ids.append(sim.num_actors)            # sim-domain index: creation order (shadow_hand.py:356,369,376)
         sim.num_actors += 1

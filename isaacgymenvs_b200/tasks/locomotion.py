@@ -7,7 +7,7 @@ import torch
 
 from .. import engine
 from ..assets import load_asset_file
-from ..importer.model import BuildOptions
+from ..importer.model import BuildOptions, enable_self_collision
 from .base.vec_task import VecTask
 
 _ASSET_ROOT_CANDIDATES = [os.environ.get("B2G_ASSET_ROOT", ""), "/root/reference/assets"]
@@ -62,7 +62,11 @@ class _Locomotion(VecTask):
                             max_angular_velocity=100.0 if self.HUMANOID else 64.0)     # humanoid.py:153-154, ant.py:151
         model = copy.deepcopy(load_asset_file(_asset_root(), asset_file, opts))
         if self.HUMANOID:
-            engine.warn_self_collision("Humanoid", "humanoid.py:194 create_actor(..., i, 0, 0)")
+            # humanoid.py:194 create_actor(..., i, 0, 0): collision filter 0 = the links collide with each other
+            if self.cfg["env"].get("selfCollision", True):
+                enable_self_collision(model)
+            else:
+                engine.warn_self_collision("Humanoid", "humanoid.py:194 create_actor(..., i, 0, 0); disabled by env.selfCollision=False")
             feet = [model.body_names.index("right_foot"), model.body_names.index("left_foot")]   # humanoid.py:164-168
         else:
             feet = [i for i, n in enumerate(model.body_names) if "foot" in n]                   # ant.py:167-178

@@ -499,52 +499,111 @@ def test_rollout_equals_k_single_steps(n, K, ep_len):
     assert (oa - ob).abs().max().item() < 3e-4
 
 
-# ------------------------------------------------------------------------------------ self-collision: not modelled, said loudly, measured
-def test_missing_self_collision_is_warned_and_its_extent_measured():
-    """humanoid.py:194 / anymal_terrain.py:282 create their actors with collision filter 0 (PhysX self-collision on).  The
-    engine has no link-link contact: building those tasks raises UnmodelledPhysicsWarning (never silently accepted), and
-    this test measures what that means for a random-action Humanoid rollout -- the share of sampled env-states in which two
-    contact spheres of bodies that are not joint neighbours overlap by more than 1 cm (DESIGN.md section 7 quotes it)."""
+# ------------------------------------------------------------------------------------ self-collision (collision filter 0)
+def _sphere_overlap(m, orc, root, dof):
+    """deepest overlap (m) between contact spheres of links that may collide (model.self_pairs), per env"""
+    from oracle import tasks_np as T
+    cpb = np.array(m.cp_body)
+    bs = orc.body_states(root, dof)
+    off_p = np.asarray(m.body_pos, f32)[cpb]; off_q = np.asarray(m.body_quat, f32)[cpb]
+    loc = T.quat_rotate_inverse(off_q, np.asarray(m.cp_pos, f32) - off_p)
+    n, ncp = bs.shape[0], len(cpb)
+    wp = bs[:, cpb, 0:3].astype(f32) + T.quat_rotate(bs[:, cpb, 3:7].astype(f32).reshape(-1, 4), np.tile(loc, (n, 1))).reshape(n, ncp, 3)
+    rr = (np.asarray(m.cp_radius)[:, None] + np.asarray(m.cp_radius)[None, :]).astype(f32)
+    d = np.linalg.norm(wp[:, :, None, :] - wp[:, None, :, :], axis=-1)
+    return np.where(np.asarray(m.self_pairs)[None] > 0, rr[None] - d, -1.0).max(axis=(1, 2))
+
+
+def test_self_collision_engine_matches_oracle():
+    """Link-link contact (humanoid.py:194 collision filter 0) in the generic sub-step against the oracle's restatement: one
+    control step from 1024 random Humanoid configurations -- joints anywhere inside their limits, so most states start with
+    limbs touching or overlapping (arms in the torso, legs crossed), some also on the ground."""
+    from oracle.oracle import OracleSim
+    from isaacgymenvs_b200 import engine
+    from isaacgymenvs_b200.importer.model import enable_self_collision
+    m = copy.deepcopy(load_compiled("humanoid"))
+    m.angular_damping, m.max_angular_velocity = 0.01, 100.0
+    enable_self_collision(m)
+    n = 1024
+    rng = np.random.default_rng(5)
+    root = np.zeros((n, 13)); root[:, 2] = rng.uniform(0.9, 2.5, size=n)
+    q = rng.normal(size=(n, 4)) * np.array([0.4, 0.4, 0.4, 0.0]) + np.array([0, 0, 0, 1.0]); root[:, 3:7] = q / np.linalg.norm(q, axis=1, keepdims=True)
+    root[:, 7:13] = rng.normal(size=(n, 6)) * 0.5
+    lo, hi = m.lower[1:], m.upper[1:]
+    dof = np.stack([rng.uniform(lo, hi, size=(n, m.ndof)), rng.normal(size=(n, m.ndof)) * 2.0], -1)
+    tau = rng.uniform(-1, 1, size=(n, m.ndof)) * np.asarray(m.actuator_gear)[None] * 0.3
+    orc = OracleSim(m, 0.0166, 2, G, threads=8)
+    dep = _sphere_overlap(m, orc, root, dof)
+    assert (dep > 0.0).mean() > 0.5, (dep > 0).mean()               # the sample really exercises link-link contact
+    sim = engine.Sim(m, n, 0.0166, 2, G)
+    assert sim.quad_ns() == 0
+    nc = sim.acquire(engine.T_NET_CONTACT)
+    sim.root_state.copy_(torch.tensor(root, dtype=torch.float32)); sim.dof_state.copy_(torch.tensor(dof.reshape(-1, 2), dtype=torch.float32))
+    sim.dof_actuation.copy_(torch.tensor(tau, dtype=torch.float32))
+    r64 = sim.root_state.cpu().numpy().astype(np.float64); d64 = sim.dof_state.cpu().numpy().astype(np.float64).reshape(n, m.ndof, 2)
+    t64 = sim.dof_actuation.cpu().numpy().astype(np.float64)
+    sim.simulate(); torch.cuda.synchronize()
+    out = orc.simulate(r64, d64, t64)
+    rg = sim.root_state.cpu().numpy().astype(np.float64); dg = sim.dof_state.cpu().numpy().astype(np.float64).reshape(n, m.ndof, 2)
+    assert np.isfinite(rg).all() and np.isfinite(dg).all()
+    # stiff contacts between light limbs amplify fp32 round-off more than the ground contact does: layered bounds
+    dp = np.abs(rg[:, :7] - r64[:, :7]).max(1)
+    assert np.quantile(dp, 0.99) < 5e-5 and dp.max() < 1e-3, (np.quantile(dp, 0.99), dp.max())
+    dq = np.abs(dg[..., 0] - d64[..., 0])
+    assert np.quantile(dq, 0.99) < 1e-4 and dq.max() < 5e-3, (np.quantile(dq, 0.99), dq.max())
+    qerr = np.abs(dg[..., 1] - d64[..., 1]) / np.maximum(1.0, np.abs(d64[..., 1]))
+    assert np.quantile(qerr, 0.99) < 2e-3 and np.median(qerr) < 1e-4, (np.quantile(qerr, 0.99), np.median(qerr))
+    cg = nc.cpu().numpy().reshape(n, m.nb, 3); co = out["contact_force"]
+    cerr = np.abs(cg - co).max(axis=(1, 2)) / np.maximum(1.0, np.abs(co).max(axis=(1, 2)))
+    assert np.quantile(cerr, 0.99) < 1e-2 and np.median(cerr) < 1e-3, (np.quantile(cerr, 0.99), np.median(cerr))
+    # and the same model without the flag is a different trajectory (the contact is really applied)
+    m2 = copy.deepcopy(m); m2.self_collide = False
+    s2 = engine.Sim(m2, n, 0.0166, 2, G)
+    s2.root_state.copy_(torch.tensor(root, dtype=torch.float32)); s2.dof_state.copy_(torch.tensor(dof.reshape(-1, 2), dtype=torch.float32))
+    s2.dof_actuation.copy_(torch.tensor(tau, dtype=torch.float32))
+    s2.simulate(); torch.cuda.synchronize()
+    assert (np.abs(s2.dof_state.cpu().numpy().reshape(n, m.ndof, 2)[..., 1] - dg[..., 1]).max(1) > 0.1).mean() > 0.4
+    sim.close(); s2.close()
+
+
+def test_humanoid_limbs_do_not_interpenetrate():
+    """The Humanoid task collides its links with each other like the reference (collision filter 0).  Random-action rollout:
+    the share of sampled env-states with two non-neighbour bodies overlapping by more than 1 cm stays below 6 % (penalty
+    contact under full actuator torque), against > 15 % with env.selfCollision=False -- which must announce itself with an
+    UnmodelledPhysicsWarning, as the four-chain ANYmal kernels (no link-link contact) do."""
     import warnings
     from oracle.oracle import OracleSim
     from isaacgymenvs_b200 import engine
-    engine._warned.discard("Humanoid")
+    share = {}
+    for on in (True, False):
+        engine._warned.discard("Humanoid")
+        with warnings.catch_warnings(record=True) as rec:
+            warnings.simplefilter("always")
+            env = _make("Humanoid", 1024, selfCollision=on)
+        warned = any(issubclass(w.category, engine.UnmodelledPhysicsWarning) for w in rec)
+        assert warned == (not on)
+        m = copy.deepcopy(env.model)
+        if not on:
+            from isaacgymenvs_b200.importer.model import enable_self_collision
+            enable_self_collision(m); m.self_collide = False            # pair table for the measurement only
+        assert bool(getattr(env.model, "self_collide", False)) == on
+        orc = OracleSim(m, 0.0166, 2, G)
+        g = torch.Generator(device="cuda:0"); g.manual_seed(3)
+        hits = samples = 0; worst = 0.0
+        for k in range(120):
+            env.step(torch.rand((1024, env.num_acts), device="cuda:0", generator=g) * 2 - 1)
+            if k % 10 != 9:
+                continue
+            torch.cuda.synchronize()
+            dep = _sphere_overlap(m, orc, env.root_states.cpu().numpy().astype(np.float64), env.dof_state.cpu().numpy().astype(np.float64).reshape(1024, -1, 2))
+            hits += int((dep > 0.01).sum()); samples += 1024; worst = max(worst, float(dep.max()))
+        assert torch.isfinite(env.root_states).all() and torch.isfinite(env.dof_state).all()
+        share[on] = hits / samples
+        print(f"Humanoid, random actions, self-collision {'on' if on else 'off'}: {hits}/{samples} sampled env-states overlap > 1 cm "
+              f"({100.0 * hits / samples:.1f} %), deepest {worst * 100:.1f} cm")
+    assert share[True] < 0.06 and share[False] > 0.15, share
+    engine._warned.discard("AnymalTerrain")
     with warnings.catch_warnings(record=True) as rec:
         warnings.simplefilter("always")
-        env = _make("Humanoid", 1024)
+        _make_anymal(64)
     assert any(issubclass(w.category, engine.UnmodelledPhysicsWarning) for w in rec)
-    m = env.model
-    orc = OracleSim(m, 0.0166, 2, G)
-    # neighbours = spheres on the same link, or on links joined through massless intermediate links (compound joints)
-    carrier = set(int(l) for l in m.body_link)
-    def up(l):                                   # nearest body-carrying ancestor link
-        l = int(m.parent[l])
-        while l >= 0 and l not in carrier:
-            l = int(m.parent[l])
-        return l
-    cpl = np.array([int(m.body_link[b]) for b in m.cp_body])
-    anc = np.array([up(l) for l in cpl])
-    cpb = np.array(m.cp_body)
-    li, lj = np.meshgrid(cpl, cpl, indexing="ij"); ai, aj = np.meshgrid(anc, anc, indexing="ij")
-    pair_ok = (li != lj) & (ai != lj) & (aj != li) & (li < lj)
-    from oracle import tasks_np as T
-    g = torch.Generator(device="cuda:0"); g.manual_seed(3)
-    hits, samples, worst = 0, 0, []
-    off_p = np.asarray(m.body_pos, f32)[cpb]; off_q = np.asarray(m.body_quat, f32)[cpb]
-    loc = T.quat_rotate_inverse(off_q, np.asarray(m.cp_pos, f32) - off_p)                  # sphere centre: link frame -> body frame
-    rr = (np.asarray(m.cp_radius)[:, None] + np.asarray(m.cp_radius)[None, :]).astype(f32)
-    for k in range(120):
-        env.step(torch.rand((1024, env.num_acts), device="cuda:0", generator=g) * 2 - 1)
-        if k % 10 != 9:
-            continue
-        torch.cuda.synchronize()
-        bs = orc.body_states(env.root_states.cpu().numpy().astype(np.float64), env.dof_state.cpu().numpy().astype(np.float64).reshape(1024, -1, 2))
-        n, ncp = bs.shape[0], len(cpb)
-        bp = bs[:, cpb, 0:3].astype(f32); bq = bs[:, cpb, 3:7].astype(f32)
-        wp = bp + T.quat_rotate(bq.reshape(-1, 4), np.tile(loc, (n, 1))).reshape(n, ncp, 3)       # -> world
-        d = np.linalg.norm(wp[:, :, None, :] - wp[:, None, :, :], axis=-1)
-        depth = np.where(pair_ok[None], rr[None] - d, -1.0).max(axis=(1, 2))
-        hits += int((depth > 0.01).sum()); samples += n; worst.append(float(depth.max()))
-    print(f"Humanoid, random actions: {hits}/{samples} sampled env-states have non-neighbour bodies overlapping > 1 cm "
-          f"({100.0 * hits / samples:.1f} %), deepest {max(worst) * 100:.1f} cm")
-    assert samples == 12 * 1024

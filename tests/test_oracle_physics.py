@@ -268,3 +268,106 @@ def test_asset_damping_and_angular_speed_clamp():
     root[0, 10:13] = [0.0, 80.0, 60.0]                                            # |w| = 100 > 64
     sim.simulate(root, dof, np.zeros((1, 0)))
     assert abs(np.linalg.norm(root[0, 10:13]) - 64.0) < 1e-9
+
+
+# ------------------------------------------------------------------------------------ self-collision (collision filter 0)
+def _humanoid_self():
+    import copy
+    from isaacgymenvs_b200.importer.model import enable_self_collision
+    m = copy.deepcopy(load_compiled("humanoid"))
+    m.angular_damping, m.max_angular_velocity = 0.01, 100.0
+    return enable_self_collision(m)
+
+
+def _max_overlap(m, orc, root, dof):
+    """deepest overlap (m) between contact spheres of links that may collide, per env"""
+    from oracle import tasks_np as T
+    f32 = np.float32
+    cpb = np.array(m.cp_body)
+    bs = orc.body_states(root, dof)
+    off_p = np.asarray(m.body_pos, f32)[cpb]; off_q = np.asarray(m.body_quat, f32)[cpb]
+    loc = T.quat_rotate_inverse(off_q, np.asarray(m.cp_pos, f32) - off_p)
+    n, ncp = bs.shape[0], len(cpb)
+    wp = bs[:, cpb, 0:3].astype(f32) + T.quat_rotate(bs[:, cpb, 3:7].astype(f32).reshape(-1, 4), np.tile(loc, (n, 1))).reshape(n, ncp, 3)
+    rr = (np.asarray(m.cp_radius)[:, None] + np.asarray(m.cp_radius)[None, :]).astype(f32)
+    d = np.linalg.norm(wp[:, :, None, :] - wp[:, None, :, :], axis=-1)
+    return np.where(np.asarray(m.self_pairs)[None] > 0, rr[None] - d, -1.0).max(axis=(1, 2))
+
+
+def test_self_collision_pair_table():
+    """Candidate pairs: symmetric, never within a link or between joint neighbours (incl. through the massless links of a
+    compound joint), never between spheres that already overlap at q = 0; the Humanoid's arms may hit the torso, the
+    thighs each other."""
+    m = _humanoid_self()
+    P = np.asarray(m.self_pairs)
+    assert P.shape == (len(m.cp_link),) * 2 and (P == P.T).all() and not P.diagonal().any()
+    body = lambda n: m.body_names[m.cp_body[n]]
+    names = {(body(a), body(b)) for a in range(P.shape[0]) for b in range(P.shape[0]) if P[a, b]}
+    assert ("right_lower_arm", "torso") in names and ("right_thigh", "left_thigh") in names and ("left_foot", "right_shin") in names
+    for a, b in (("right_thigh", "right_shin"), ("right_shin", "right_foot"), ("torso", "head"), ("torso", "lower_waist"),
+                 ("lower_waist", "pelvis"), ("pelvis", "right_thigh"), ("torso", "right_upper_arm"), ("right_lower_arm", "right_hand")):
+        assert (a, b) not in names and (b, a) not in names, (a, b)
+    assert m.self_kn == pytest.approx(m.contact_kn) and m.self_mu == 1.0
+
+
+def test_self_collision_keeps_limbs_apart():
+    """A Humanoid thrown around by full-scale random torques: without link-link contact half of the sampled states have
+    limbs inside each other by more than 1 cm (deepest > 10 cm); with it the share drops below 5 % and the deepest
+    overlap to a few cm (penalty contact: ~1000 N of actuator force against 82 kN/m), and the rollout stays finite and no
+    faster than the uncollided one."""
+    res = {}
+    for on in (False, True):
+        m = _humanoid_self()
+        m.self_collide = on
+        orc = OracleSim(m, 0.0166, 2, G, threads=16)
+        n = 128
+        rng = np.random.default_rng(0)
+        root = np.zeros((n, 13)); root[:, 2] = 1.34; root[:, 6] = 1
+        dof = np.zeros((n, m.ndof, 2)); dof[..., 0] = rng.uniform(-0.1, 0.1, size=(n, m.ndof))
+        gear = np.asarray(m.actuator_gear)
+        hits = tot = 0; worst = 0.0
+        for k in range(120):
+            orc.simulate(root, dof, rng.uniform(-1, 1, size=(n, m.ndof)) * gear[None])
+            if k % 10 == 9:
+                dep = _max_overlap(m, orc, root, dof)
+                hits += int((dep > 0.01).sum()); tot += n; worst = max(worst, float(dep.max()))
+        assert np.isfinite(root).all() and np.isfinite(dof).all()
+        res[on] = (hits / tot, worst, float(np.abs(dof[..., 1]).max()))
+    assert res[False][0] > 0.3 and res[False][1] > 0.08, res
+    assert res[True][0] < 0.05 and res[True][1] < 0.06, res
+    assert res[True][2] < 2.0 * res[False][2], res
+
+
+def test_self_contact_forces_are_equal_and_opposite():
+    """One isolated contact between two limbs in free flight.  The two links compute their sides of the pair independently
+    (block-Jacobi: each implicit in its OWN acceleration only: F_i = F0 - h G J a_i), so the forces reported for the two
+    bodies are exactly opposite only in the limit h -> 0.  Frictionless at h = 20 us they agree to 5 %; at the task's 8.3 ms,
+    with friction, each side's force is reduced by its own response (the lighter limb's more) and only the directions still
+    oppose -- the same documented property as the hand-object contact."""
+    m = _humanoid_self()
+    m.gravity_on = False
+    m0 = _humanoid_self(); m0.gravity_on = False; m0.self_mu = 0.0
+    fine = OracleSim(m0, 0.00002, 1, (0.0, 0.0, 0.0))
+    task = OracleSim(m, 0.0166, 2, (0.0, 0.0, 0.0))
+    rng = np.random.default_rng(3)
+    found, asym_task = 0, []
+    for trial in range(600):
+        root = np.zeros((1, 13)); root[0, 2] = 5.0; root[0, 6] = 1
+        dof = np.zeros((1, m.ndof, 2)); dof[0, :, 0] = rng.uniform(np.maximum(m.lower[1:], -1.5), np.minimum(m.upper[1:], 1.5))
+        dep = _max_overlap(m, fine, root, dof)[0]
+        if not (0.005 < dep < 0.03):
+            continue
+        cf = fine.simulate(root.copy(), dof.copy(), np.zeros((1, m.ndof)))["contact_force"][0]
+        touched = np.where(np.linalg.norm(cf, axis=1) > 1e-9)[0]
+        if len(touched) != 2:
+            continue
+        a, b = touched
+        assert np.linalg.norm(cf[a] + cf[b]) < 0.05 * np.linalg.norm(cf[a]), (m.body_names[a], m.body_names[b], cf[a], cf[b])
+        ct = task.simulate(root.copy(), dof.copy(), np.zeros((1, m.ndof)))["contact_force"][0]
+        asym_task.append(np.linalg.norm(ct[a] + ct[b]) / max(np.linalg.norm(ct[a]), np.linalg.norm(ct[b]), 1e-9))
+        assert np.dot(ct[a], ct[b]) <= 0                                       # pushing apart (or already separated in the 2nd sub-step)
+        found += 1
+        if found >= 6:
+            break
+    assert found >= 3
+    print("block-Jacobi force asymmetry at h = 8.3 ms (with friction):", np.round(asym_task, 2))
