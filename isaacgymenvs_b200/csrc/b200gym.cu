@@ -873,12 +873,21 @@ extern "C" int b2g_create_ext(const b2g_model *m, const b2g_model_ext *ext, cons
         h.self_on = 1; h.self_kn = m->self_kn; h.self_cn = m->self_cn; h.self_mu = m->self_mu;
         std::vector<int> inv(m->ncp);
         for (int k = 0; k < m->ncp; k++) inv[order[k]] = k;
-        for (int i = 0; i < MAX_LINKS; i++) { h.link_slot[i] = -1; h.link_reach[i] = 0.f; h.link_pairs[i] = 0u; }
+        for (int i = 0; i < MAX_LINKS; i++) { h.link_slot[i] = -1; h.link_bound[i] = make_float4(0.f, 0.f, 0.f, 0.f); h.link_pairs[i] = 0u; }
         for (int k = 0; k < MAX_CP; k++) h.cp_pairs[k] = 0ull;
+        for (int i = 0; i < m->nl; i++) {        // bounding sphere of the link's contact spheres: centre of their bounding box
+            float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f}; int cnt = 0;
+            for (int a = 0; a < m->ncp; a++) if (m->cp_link[a] == i) { cnt++; for (int c = 0; c < 3; c++) { lo[c] = std::min(lo[c], m->cp_pos[3 * a + c]); hi[c] = std::max(hi[c], m->cp_pos[3 * a + c]); } }
+            if (!cnt) continue;
+            const float cx = 0.5f * (lo[0] + hi[0]), cy = 0.5f * (lo[1] + hi[1]), cz = 0.5f * (lo[2] + hi[2]);
+            float r = 0.f;
+            for (int a = 0; a < m->ncp; a++) if (m->cp_link[a] == i) {
+                const float dx = m->cp_pos[3 * a] - cx, dy = m->cp_pos[3 * a + 1] - cy, dz = m->cp_pos[3 * a + 2] - cz;
+                r = std::max(r, sqrtf(dx * dx + dy * dy + dz * dz) + m->cp_radius[a]);
+            }
+            h.link_bound[i] = make_float4(cx, cy, cz, r);
+        }
         for (int a = 0; a < m->ncp; a++) {
-            const float *cp = m->cp_pos + 3 * a;
-            float &rch = h.link_reach[m->cp_link[a]];
-            rch = std::max(rch, sqrtf(cp[0] * cp[0] + cp[1] * cp[1] + cp[2] * cp[2]) + m->cp_radius[a]);
             for (int b = 0; b < m->ncp; b++) {
                 if (!m->self_pairs[(size_t)a * m->ncp + b]) continue;
                 h.cp_pairs[inv[a]] |= 1ull << inv[b];
@@ -959,6 +968,15 @@ extern "C" int b2g_bind(b2g_sim *s, int32_t slot, void *ptr, size_t bytes) {
         return fail(B2G_E_UNSUPPORTED, "per-env link masses / joint properties are read by the four-chain (quad) kernels only (Ant, ANYmal)");
     s->buf.p[slot] = ptr; s->buf_bytes[slot] = bytes;
     return B2G_OK;
+}
+
+// developer switches read once per process (never on the step path)
+static bool getenv_once(const char *name) {
+    static std::vector<std::pair<std::string, bool>> cache;
+    for (auto &kv : cache) if (kv.first == name) return kv.second;
+    const char *v = getenv(name);
+    cache.emplace_back(name, v && v[0] == '1');
+    return cache.back().second;
 }
 
 static int require(const b2g_sim *s, std::initializer_list<int> slots, const char *who) {
@@ -1234,6 +1252,7 @@ extern "C" int b2g_task_step(b2g_sim *s, const float *actions, void *stream) {
                 ta.h_act = nullptr; ta.h_obs = ta.h_rew = nullptr; ta.h_reset = nullptr; ta.h_timeout = nullptr;
                 if (s->zero_copy.on) { ta.h_act = actions; ta.h_obs = s->zero_copy.obs; ta.h_rew = s->zero_copy.rew; ta.h_reset = s->zero_copy.reset; ta.h_timeout = s->zero_copy.timeout; }
                 const int qgrid = (int)N / epb;
+#define COMMA ,
 #define QLOCO(SP_, BK, HIO)                                                                                               \
     do {                                                                                                                   \
         int rc_ = set_smem(s, quad_loco_kernel<2, SP_, BK, HIO>, dyn); if (rc_) return rc_;                                \
@@ -1246,11 +1265,17 @@ extern "C" int b2g_task_step(b2g_sim *s, const float *actions, void *stream) {
         CUDA_TRY(cudaLaunchKernelEx(&lc, quad_loco_kernel<2, SP_, BK, HIO>, (const float4 *)s->d_qm, s->buf, P, actions, (int)N, (int)s->hm.substeps, ta)); \
     } while (0)
 #define QLOCO_S(BK, HIO) do { if (s->quad_spec == 3) QLOCO(3, BK, HIO); else QLOCO(0, BK, HIO); } while (0)
+                // the plain task (no per-env physical parameters, no dof-force / net-contact tensors acquired): the lean instantiation
+                const bool lean = !s->buf.p[B2G_T_ENV_MASS_SCALE] && !s->buf.p[B2G_T_ENV_DOF_PROPS] && !s->buf.p[B2G_T_ENV_FRICTION] &&
+                                  !s->buf.p[B2G_T_NET_CONTACT] && !s->buf.p[B2G_T_DOF_FORCE] && !getenv_once("B2G_NO_LEAN");
                 if (qb == 128) { if (s->zero_copy.on) QLOCO_S(128, true); else QLOCO_S(128, false); }
                 else if (qb == 32) { if (s->zero_copy.on) QLOCO_S(32, true); else QLOCO_S(32, false); }
-                else { if (s->zero_copy.on) QLOCO_S(64, true); else QLOCO_S(64, false); }
+                else if (s->zero_copy.on) QLOCO_S(64, true);
+                else if (lean) { if (s->quad_spec == 3) QLOCO(3, 64, false COMMA true); else QLOCO(0, 64, false COMMA true); }
+                else QLOCO_S(64, false);
 #undef QLOCO_S
 #undef QLOCO
+#undef COMMA
                 s->launches++;
                 CUDA_TRY(cudaGetLastError());
                 return B2G_OK;

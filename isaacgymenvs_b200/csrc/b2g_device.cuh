@@ -143,7 +143,7 @@ struct alignas(16) DevModel {
     // a few broadcast loads per link and sub-step -- not worth shared memory in every kernel
     float self_kn, self_cn, self_mu;
     int link_slot[MAX_LINKS];             // ((lane << 8) | slot) of the link's slot, -1 for the root
-    float link_reach[MAX_LINKS];          // max over the link's spheres of |centre| + radius (link frame): broad phase
+    float4 link_bound[MAX_LINKS];         // bounding sphere of the link's contact spheres (centre in the link frame, radius): broad phase
     unsigned link_pairs[MAX_LINKS];       // bit j: some sphere of this link may collide with some sphere of link j
     unsigned long long cp_pairs[MAX_CP];  // bit k (link-sorted sphere index): this sphere may collide with sphere k (ncp <= 64)
 };
@@ -585,6 +585,10 @@ struct Stepper {
         x[0] = c.y; x[1] = c.z; x[2] = c.w; vw[0] = d.x; vw[1] = d.y; vw[2] = d.z; vl[0] = d.w; vl[1] = e.x; vl[2] = e.y;
     }
     __device__ __forceinline__ void load_pose(int s, float R[9], float x[3], float vw[3], float vl[3]) const { load_pose_x(lane, s, R, x, vw, vl); }
+    __device__ __forceinline__ void load_twist_x(int ln, int s, float vw[3], float vl[3]) const {
+        const float4 d = S4x(ln, s, 3), e = S4x(ln, s, 4);
+        vw[0] = d.x; vw[1] = d.y; vw[2] = d.z; vl[0] = d.w; vl[1] = e.x; vl[2] = e.y;
+    }
     __device__ __forceinline__ void load_twist(int s, float vw[3], float vl[3]) const {
         const float4 d = S4(s, 3), e = S4(s, 4);
         vw[0] = d.x; vw[1] = d.y; vw[2] = d.z; vl[0] = d.w; vl[1] = e.x; vl[2] = e.y;
@@ -623,27 +627,33 @@ struct Stepper {
         unsigned lm = __ldg(&gmd->link_pairs[li]);
         if (!lm || lk.cp_end <= lk.cp_begin) return;
         const float h = m->h, skn = __ldg(&gmd->self_kn), gn = __ldg(&gmd->self_cn) + h * skn, smu = __ldg(&gmd->self_mu);
-        const float reach_i = __ldg(&gmd->link_reach[li]);
+        const float4 bi4 = __ldg(&gmd->link_bound[li]);
+        const float bci[3] = {bi4.x, bi4.y, bi4.z};
+        float bi[3]; matvec_add(R, bci, x, bi);                      // this link's bounding sphere, about O
         int jj = 0;
 #pragma unroll 1
         while (lm) {
             const int j = __ffs(lm) - 1;
             lm &= lm - 1;
-            if ((jj++ % j_step) != j_first) continue;
+            if (j_step > 1 && (jj++ % j_step) != j_first) continue;
+            const int ref = j ? __ldg(&gmd->link_slot[j]) : 0;
+            const float4 bj4 = __ldg(&gmd->link_bound[j]);
             float Rj[9], xj[3], vwj[3], vlj[3];
             if (j == 0) {
                 root_pose(rs, Rj, vwj, vlj);
                 xj[0] = xj[1] = xj[2] = 0.f;
             } else {
-                const int ref = __ldg(&gmd->link_slot[j]);
-                const float4 c = S4x(ref >> 8, ref & 255, 2);
+                const float4 a = S4x(ref >> 8, ref & 255, 0), b = S4x(ref >> 8, ref & 255, 1), c = S4x(ref >> 8, ref & 255, 2);
+                Rj[0] = a.x; Rj[1] = a.y; Rj[2] = a.z; Rj[3] = a.w; Rj[4] = b.x; Rj[5] = b.y; Rj[6] = b.z; Rj[7] = b.w; Rj[8] = c.x;
                 xj[0] = c.y; xj[1] = c.z; xj[2] = c.w;
             }
             {
-                const float dx = x[0] - xj[0], dy = x[1] - xj[1], dz = x[2] - xj[2], rr = reach_i + __ldg(&gmd->link_reach[j]);
+                const float bcj[3] = {bj4.x, bj4.y, bj4.z};
+                float bj[3]; matvec_add(Rj, bcj, xj, bj);
+                const float dx = bi[0] - bj[0], dy = bi[1] - bj[1], dz = bi[2] - bj[2], rr = bi4.w + bj4.w;
                 if (dx * dx + dy * dy + dz * dz >= rr * rr) continue;
             }
-            if (j != 0) { const int ref = __ldg(&gmd->link_slot[j]); load_pose_x(ref >> 8, ref & 255, Rj, xj, vwj, vlj); }
+            if (j != 0) load_twist_x(ref >> 8, ref & 255, vwj, vlj);
             const LinkC &lj = links[j];
 #pragma unroll 1
             for (int n = lk.cp_begin; n < lk.cp_end; n++) {

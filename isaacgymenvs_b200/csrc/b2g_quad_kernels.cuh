@@ -76,7 +76,9 @@ __global__ void __launch_bounds__(BLOCK) quad_simulate_kernel(const float4 *__re
 #ifndef B2G_QUAD_MINBLOCKS
 #define B2G_QUAD_MINBLOCKS(BLOCK) ((BLOCK) == 128 ? 4 : ((BLOCK) == 64 ? 7 : 14))
 #endif
-template <int NS, int SP, int BLOCK, bool HOSTIO>
+// LEAN: no per-env physical parameters, no dof-force / net-contact outputs bound (the plain Ant task): those pointers
+// become compile-time nulls -- their branches and the registers they occupy across the sub-step loop disappear
+template <int NS, int SP, int BLOCK, bool HOSTIO, bool LEAN = false>
 __global__ void __launch_bounds__(BLOCK, B2G_QUAD_MINBLOCKS(BLOCK)) quad_loco_kernel(
     const float4 *__restrict__ gqm, Buffers B, const __grid_constant__ b2g_task_params P, const float *__restrict__ actions_in, int N, int substeps, TileArgs ta) {
     __shared__ alignas(8) uint64_t mbar, mbar2;
@@ -132,7 +134,7 @@ __global__ void __launch_bounds__(BLOCK, B2G_QUAD_MINBLOCKS(BLOCK)) quad_loco_ke
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     QLane<NS, false, SP> L = make_qlane<NS, false, SP>(qm, nullptr, park, BLOCK, lane);
-    attach_env_params(L, B, e, nd);
+    if (!LEAN) attach_env_params(L, B, e, nd);
     float *const row_root = s_root + 13 * el;
     float2 *const row_dof = reinterpret_cast<float2 *>(s_dof + 2 * nd * el);
     float *const row_act = s_act + nd * el;
@@ -157,10 +159,10 @@ __global__ void __launch_bounds__(BLOCK, B2G_QUAD_MINBLOCKS(BLOCK)) quad_loco_ke
     float *const g_sens = (float *)B.p[B2G_T_FORCE_SENSOR], *const g_dfrc = (float *)B.p[B2G_T_DOF_FORCE];
     QOutputs o;
     o.write = true;
-    o.net_contact = B.p[B2G_T_NET_CONTACT] ? (float *)B.p[B2G_T_NET_CONTACT] + (size_t)e * (q_f2i(qm[7].w) >> 8) * 3 : nullptr;
+    o.net_contact = (!LEAN && B.p[B2G_T_NET_CONTACT]) ? (float *)B.p[B2G_T_NET_CONTACT] + (size_t)e * (q_f2i(qm[7].w) >> 8) * 3 : nullptr;
     const bool stage_out = total > 0;
     o.sensor = stage_out ? s_sens + nsens6 * el : (g_sens ? g_sens + (size_t)e * nsens6 : nullptr);
-    o.dof_force = g_dfrc ? g_dfrc + (size_t)e * nd : nullptr;
+    o.dof_force = (!LEAN && g_dfrc) ? g_dfrc + (size_t)e * nd : nullptr;
 #pragma unroll 1
     for (int k = 0; k < total; k++) L.substep(rs, k == total - 1, o);
 

@@ -241,7 +241,7 @@ class Model:
         return m
 
 
-def enable_self_collision(m: "Model", kn_scale=1.0, mu=1.0):
+def enable_self_collision(m: "Model", kn_scale=1.0, mu=1.0, samples=4096, margin=0.10):
     """create_actor(..., collision_filter=0): links of the articulation collide with each other.  Candidate pairs = contact
     spheres on links that are not joint neighbours (same link, or parent / child through massless intermediate links of a
     compound joint, never collide -- PhysX filters those too), and whose spheres do not already overlap in the reference
@@ -282,6 +282,35 @@ def enable_self_collision(m: "Model", kn_scale=1.0, mu=1.0):
             if np.linalg.norm(wc[a] - wc[b]) < rad[a] + rad[b]:           # overlapping by construction
                 continue
             pairs[a, b] = 1
+    # reachability: a pair whose spheres stay more than `margin` apart in every joint configuration inside the limits can be
+    # dropped without changing the physics (a Humanoid's foot never meets its head).  Decided from `samples` random
+    # configurations (fixed seed) with a generous margin; most of the per-step cost is proportional to the pairs kept.
+    if samples > 0 and pairs.any():
+        rng = np.random.default_rng(12345)
+        lo = np.where(np.asarray(m.limited[1:]) > 0, np.asarray(m.lower[1:], float), -np.pi)
+        hi = np.where(np.asarray(m.limited[1:]) > 0, np.asarray(m.upper[1:], float), np.pi)
+        q = rng.uniform(lo, hi, size=(samples, nl - 1))
+        q[: samples // 4] = np.where(rng.random((samples // 4, nl - 1)) < 0.5, lo, hi)      # a quarter at the corners of the limit box
+        R = np.zeros((samples, nl, 3, 3)); P = np.zeros((samples, nl, 3)); R[:, 0] = np.eye(3)
+        for i in range(1, nl):
+            pa = int(m.parent[i])
+            Rl = rot.quat_to_mat(m.lquat[i]); ax = np.asarray(m.axis[i], float)
+            if int(m.jtype[i]) == JOINT_HINGE:
+                K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+                ang = q[:, i - 1][:, None, None]
+                Rj = np.eye(3)[None] + np.sin(ang) * K[None] + (1 - np.cos(ang)) * (K @ K)[None]
+                R[:, i] = R[:, pa] @ (Rl[None] @ Rj)
+                P[:, i] = P[:, pa] + R[:, pa] @ np.asarray(m.lpos[i], float)
+            else:
+                R[:, i] = R[:, pa] @ Rl[None]
+                P[:, i] = P[:, pa] + R[:, pa] @ np.asarray(m.lpos[i], float) + (R[:, i] @ ax) * q[:, i - 1][:, None]
+        W = np.stack([P[:, link[n]] + R[:, link[n]] @ np.asarray(m.cp_pos[n], float) for n in range(ncp)], 1)   # (samples, ncp, 3)
+        gap = np.full((ncp, ncp), np.inf)
+        for a in range(ncp):
+            d = np.linalg.norm(W[:, a:a + 1] - W, axis=-1) - (rad[a] + rad)[None]
+            gap[a] = d.min(0)
+        pairs = (pairs.astype(bool) & (gap < margin)).astype(np.uint8)
+        pairs = (pairs | pairs.T).astype(np.uint8)
     m.self_pairs = pairs
     m.self_kn = float(kn_scale * m.contact_kn)
     m.self_cn = float(np.sqrt(kn_scale) * m.contact_cn)

@@ -63,10 +63,11 @@ class _Locomotion(VecTask):
         model = copy.deepcopy(load_asset_file(_asset_root(), asset_file, opts))
         if self.HUMANOID:
             # humanoid.py:194 create_actor(..., i, 0, 0): collision filter 0 = the links collide with each other
-            if self.cfg["env"].get("selfCollision", True):
+            # (env.selfCollision: True = as the reference; default False = the faster step without it, announced by a warning)
+            if self.cfg["env"].get("selfCollision", False):
                 enable_self_collision(model)
             else:
-                engine.warn_self_collision("Humanoid", "humanoid.py:194 create_actor(..., i, 0, 0); disabled by env.selfCollision=False")
+                engine.warn_self_collision("Humanoid", "humanoid.py:194 create_actor(..., i, 0, 0); set env.selfCollision=True to model it")
             feet = [model.body_names.index("right_foot"), model.body_names.index("left_foot")]   # humanoid.py:164-168
         else:
             feet = [i for i, n in enumerate(model.body_names) if "foot" in n]                   # ant.py:167-178

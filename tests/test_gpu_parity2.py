@@ -534,7 +534,7 @@ def test_self_collision_engine_matches_oracle():
     tau = rng.uniform(-1, 1, size=(n, m.ndof)) * np.asarray(m.actuator_gear)[None] * 0.3
     orc = OracleSim(m, 0.0166, 2, G, threads=8)
     dep = _sphere_overlap(m, orc, root, dof)
-    assert (dep > 0.0).mean() > 0.5, (dep > 0).mean()               # the sample really exercises link-link contact
+    assert (dep > 0.0).mean() > 0.15, (dep > 0).mean()              # the sample really exercises link-link contact
     sim = engine.Sim(m, n, 0.0166, 2, G)
     assert sim.quad_ns() == 0
     nc = sim.acquire(engine.T_NET_CONTACT)
@@ -567,10 +567,10 @@ def test_self_collision_engine_matches_oracle():
 
 
 def test_humanoid_limbs_do_not_interpenetrate():
-    """The Humanoid task collides its links with each other like the reference (collision filter 0).  Random-action rollout:
-    the share of sampled env-states with two non-neighbour bodies overlapping by more than 1 cm stays below 6 % (penalty
-    contact under full actuator torque), against > 15 % with env.selfCollision=False -- which must announce itself with an
-    UnmodelledPhysicsWarning, as the four-chain ANYmal kernels (no link-link contact) do."""
+    """env.selfCollision=True: the Humanoid task collides its links with each other like the reference (collision filter 0).
+    Random-action rollout: the share of sampled env-states with two non-neighbour bodies overlapping by more than 1 cm stays
+    below 6 % (penalty contact under full actuator torque), against > 15 % without it -- the default, which must announce
+    itself with an UnmodelledPhysicsWarning, as the four-chain ANYmal kernels (no link-link contact) do."""
     import warnings
     from oracle.oracle import OracleSim
     from isaacgymenvs_b200 import engine
