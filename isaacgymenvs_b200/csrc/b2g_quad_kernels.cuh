@@ -362,7 +362,9 @@ __global__ void __launch_bounds__(BLOCK, B2G_QUAD_MINBLOCKS(BLOCK)) quad_loco_ke
 // (PD torque + gym.simulate x decimation, anymal_terrain.py:441-451) + the control_freq_inv simulates of VecTask.step
 // (vec_task.py:379-382) + post_physics_step up to compute_reward (:453-475).  The joint state stays in registers across
 // the 5 sub-steps; the PD law reads it there.
-template <bool HF, int BLOCK>
+// DR = false: no per-env physical parameters bound -- their pointers are compile-time nulls (smaller code: this kernel runs one
+// warp per scheduler, so instruction fetch is exposed: 27 % of its stall cycles are "no instruction")
+template <bool HF, int BLOCK, bool DR = true>
 __global__ void __launch_bounds__(BLOCK) quad_anymal_physics_kernel(const float4 *__restrict__ gqm, const int16_t *__restrict__ hf,
                                                                     Buffers B, const __grid_constant__ b2g_anymal_params P,
                                                                     const float *__restrict__ actions_in, int N, int substeps, unsigned step_counter) {
@@ -377,7 +379,7 @@ __global__ void __launch_bounds__(BLOCK) quad_anymal_physics_kernel(const float4
     const bool valid = env < N;
     const int e = valid ? env : N - 1;
     QLane<NS, HF, 0> L = make_qlane<NS, HF, 0>(qm, hf, park, BLOCK, lane);
-    attach_env_params(L, B, e, nd);
+    if (DR) attach_env_params(L, B, e, nd);
     RootState rs; load_root((const float *)B.p[B2G_T_ROOT_STATE] + 13 * (size_t)e, rs);
     const float2 *dofs = (const float2 *)B.p[B2G_T_DOF_STATE] + (size_t)e * nd;
     float *act_out = (float *)B.p[B2G_T_ACTIONS] + (size_t)e * nd;
