@@ -87,6 +87,7 @@ __device__ __forceinline__ Stepper<L, HF, BLOCK, OBJ> make_stepper(const DevMode
     }
     st.lane = lane;
     st.gmodel = nullptr;
+    st.scen = OBJ ? nullptr : b2g_dyn_smem + (sm->ns * SLOT_F4 + sm->nacc * ACC_F4) * BLOCK + (threadIdx.x / L) * sm->self_f4;
     return st;
 }
 
@@ -796,12 +797,16 @@ extern "C" int b2g_create_ext(const b2g_model *m, const b2g_model_ext *ext, cons
         s->block = best; s->dyn_smem = rows * (size_t)((best / h.lanes) | 1) * sizeof(float4);
     } else {   // CTA size: the per-thread slot state must fit in shared memory, preferably several CTAs per SM
         const size_t per_thread = ((size_t)h.ns * SLOT_F4 + (size_t)h.nacc * ACC_F4) * sizeof(float4);
+        // self-collision scratch per ENV behind the accumulator pool: sphere centres, hit count, hit list (odd float4 count: banks)
+        h.self_on = (m->self_collide && m->self_pairs) ? 1 : 0;
+        h.self_f4 = h.self_on ? ((m->ncp + 1 + SELF_HITS * 2 / 16) | 1) : 0;
+        auto bytes_of = [&](int b) { return per_thread * b + (size_t)(b / h.lanes) * h.self_f4 * sizeof(float4); };
         int blk = 128;
         const char *fb = getenv("B2G_BLOCK");                       // experiment hook: force a smaller CTA
         if (fb && (atoi(fb) == 64 || atoi(fb) == 32)) blk = atoi(fb);
-        while (blk > 32 && per_thread * blk > 104 * 1024) blk >>= 1;
-        if (per_thread * blk > 200 * 1024) { delete s; return fail(B2G_E_INVALID, "b2g_create: articulation too large for shared-memory slot state"); }
-        s->block = blk; s->dyn_smem = per_thread * blk;
+        while (blk > 32 && bytes_of(blk) > 104 * 1024) blk >>= 1;
+        if (bytes_of(blk) > 200 * 1024) { delete s; return fail(B2G_E_INVALID, "b2g_create: articulation too large for shared-memory slot state"); }
+        s->block = blk; s->dyn_smem = bytes_of(blk);
     }
     // links
     std::vector<int> order(m->ncp);
@@ -845,7 +850,7 @@ extern "C" int b2g_create_ext(const b2g_model *m, const b2g_model_ext *ext, cons
         int src = order[k];
         CpC &c = h.cps[k];
         for (int j = 0; j < 3; j++) c.pos[j] = m->cp_pos[3 * src + j];
-        c.radius = m->cp_radius[src]; c.mu = 0.5f * (m->cp_mu[src] + sp->ground_friction); c.body = m->cp_body[src]; c.pad = 0;
+        c.radius = m->cp_radius[src]; c.mu = 0.5f * (m->cp_mu[src] + sp->ground_friction); c.body = m->cp_body[src]; c.pad = m->cp_link[src];
         LinkC &l = h.links[m->cp_link[src]];
         if (l.cp_end == 0 && l.cp_begin == 0) l.cp_begin = k;
         l.cp_end = k + 1;
@@ -866,33 +871,19 @@ extern "C" int b2g_create_ext(const b2g_model *m, const b2g_model_ext *ext, cons
         }
     }
     // self-collision tables (create_actor collision filter 0)
-    h.self_on = 0;
     if (m->self_collide && m->self_pairs) {
-        if (ext && ext->obj_actor >= 0) { delete s; return fail(B2G_E_UNSUPPORTED, "b2g_create_ext: self-collision is not compiled into the object-enabled kernels"); }
-        if (m->ncp > 64 || m->nl > 32) { delete s; return fail(B2G_E_UNSUPPORTED, "b2g_create: self-collision supports at most 64 contact spheres / 32 links"); }
-        h.self_on = 1; h.self_kn = m->self_kn; h.self_cn = m->self_cn; h.self_mu = m->self_mu;
+        if (compact || (ext && ext->obj_actor >= 0)) { delete s; return fail(B2G_E_UNSUPPORTED, "b2g_create_ext: self-collision is not compiled into the object-enabled kernels"); }
+        if (m->ncp > 64 || m->nl > MAX_LINKS) { delete s; return fail(B2G_E_UNSUPPORTED, "b2g_create: self-collision supports at most 64 contact spheres / 32 links"); }
+        h.self_kn = m->self_kn; h.self_cn = m->self_cn; h.self_mu = m->self_mu;
         std::vector<int> inv(m->ncp);
         for (int k = 0; k < m->ncp; k++) inv[order[k]] = k;
-        for (int i = 0; i < MAX_LINKS; i++) { h.link_slot[i] = -1; h.link_bound[i] = make_float4(0.f, 0.f, 0.f, 0.f); h.link_pairs[i] = 0u; }
-        for (int k = 0; k < MAX_CP; k++) h.cp_pairs[k] = 0ull;
-        for (int i = 0; i < m->nl; i++) {        // bounding sphere of the link's contact spheres: centre of their bounding box
-            float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f}; int cnt = 0;
-            for (int a = 0; a < m->ncp; a++) if (m->cp_link[a] == i) { cnt++; for (int c = 0; c < 3; c++) { lo[c] = std::min(lo[c], m->cp_pos[3 * a + c]); hi[c] = std::max(hi[c], m->cp_pos[3 * a + c]); } }
-            if (!cnt) continue;
-            const float cx = 0.5f * (lo[0] + hi[0]), cy = 0.5f * (lo[1] + hi[1]), cz = 0.5f * (lo[2] + hi[2]);
-            float r = 0.f;
-            for (int a = 0; a < m->ncp; a++) if (m->cp_link[a] == i) {
-                const float dx = m->cp_pos[3 * a] - cx, dy = m->cp_pos[3 * a + 1] - cy, dz = m->cp_pos[3 * a + 2] - cz;
-                r = std::max(r, sqrtf(dx * dx + dy * dy + dz * dz) + m->cp_radius[a]);
-            }
-            h.link_bound[i] = make_float4(cx, cy, cz, r);
-        }
-        for (int a = 0; a < m->ncp; a++) {
-            for (int b = 0; b < m->ncp; b++) {
-                if (!m->self_pairs[(size_t)a * m->ncp + b]) continue;
-                h.cp_pairs[inv[a]] |= 1ull << inv[b];
-                h.link_pairs[m->cp_link[a]] |= 1u << m->cp_link[b];
-            }
+        for (int i = 0; i < MAX_LINKS; i++) h.link_slot[i] = -1;
+        h.npairs = 0;
+        for (int a = 0; a < m->ncp; a++) for (int b = a + 1; b < m->ncp; b++) {
+            if (!m->self_pairs[(size_t)a * m->ncp + b] && !m->self_pairs[(size_t)b * m->ncp + a]) continue;
+            if (h.npairs >= MAX_PAIRS) { delete s; return fail(B2G_E_UNSUPPORTED, "b2g_create: too many self-collision pairs"); }
+            const int ia = std::min(inv[a], inv[b]), ib = std::max(inv[a], inv[b]);
+            h.pair_list[h.npairs++] = (unsigned short)(ia | (ib << 8));
         }
         for (int sl = 0; sl < h.ns; sl++) for (int l = 0; l < h.lanes; l++) if (h.slots[sl][l].link > 0) h.link_slot[h.slots[sl][l].link] = (l << 8) | sl;
     }

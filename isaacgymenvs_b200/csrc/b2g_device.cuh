@@ -52,6 +52,8 @@ namespace b2g {
 
 constexpr int MAX_LINKS = 32;
 constexpr int MAX_CP = 96;
+constexpr int MAX_PAIRS = 1024; // self-collision: candidate sphere pairs
+constexpr int SELF_HITS = 32;   // self-collision: overlapping pairs kept per env and sub-step (64 bytes = 4 float4)
 constexpr int MAX_BOX = 4;      // box primitives of the articulation the free object's corners are tested against
 constexpr int MAX_TEN = 4;      // fixed two-joint tendons
 constexpr int MAX_SENS = 8;
@@ -113,6 +115,7 @@ struct alignas(16) DevModel {
     int root_acc;         // accumulator index collecting this lane's root children other than slot 0's (-1: none)
     int cross_lane;       // some slot's parent lives in another lane (needs the shared-memory handoff + __syncwarp)
     int self_on;          // link-link contacts within the articulation (tables in the cold tail below)
+    int self_f4;          // float4 per env of the self-collision scratch behind the accumulator pool (0 when off)
     float ground_mu;      // friction of the ground material (combined per contact as the average, PhysX default)
     float ang_damp, lin_damp, max_angvel;   // AssetOptions.angular_damping / linear_damping / max_angular_velocity (0: no clamp)
     float obj_ang_damp, obj_lin_damp;       // the free object's own
@@ -139,13 +142,11 @@ struct alignas(16) DevModel {
     int link_parent[MAX_LINKS];
     float body_pos[MAX_LINKS][3];
     float body_quat[MAX_LINKS][4];
-    // ---- self-collision (create_actor collision filter 0): read through the GLOBAL copy of the model (Stepper::gmodel),
-    // a few broadcast loads per link and sub-step -- not worth shared memory in every kernel
+    // ---- self-collision (create_actor collision filter 0): read through the GLOBAL copy of the model (Stepper::gmodel)
     float self_kn, self_cn, self_mu;
-    int link_slot[MAX_LINKS];             // ((lane << 8) | slot) of the link's slot, -1 for the root
-    float4 link_bound[MAX_LINKS];         // bounding sphere of the link's contact spheres (centre in the link frame, radius): broad phase
-    unsigned link_pairs[MAX_LINKS];       // bit j: some sphere of this link may collide with some sphere of link j
-    unsigned long long cp_pairs[MAX_CP];  // bit k (link-sorted sphere index): this sphere may collide with sphere k (ncp <= 64)
+    int npairs;                            // unordered sphere pairs that may collide
+    int link_slot[MAX_LINKS];              // ((lane << 8) | slot) of the link's slot, -1 for the root
+    unsigned short pair_list[MAX_PAIRS];   // (a | b << 8), link-sorted sphere indices, a < b
 };
 static_assert(offsetof(DevModel, slots) % 16 == 0 && offsetof(DevModel, links) % 16 == 0 && offsetof(DevModel, cps) % 16 == 0, "bulk-copy alignment");
 
@@ -550,6 +551,8 @@ struct Stepper {
     float4 *acc;              // this thread's column of the accumulator pool
     int lane;
     const DevModel *gmodel;   // the model's copy in global memory (self-collision tables), may be null when self_on == 0
+    float4 *scen;             // this ENV's self-collision scratch: [0, ncp) sphere centres about O + radius, [ncp].x hit count,
+                              // [ncp + 1, ncp + 5) the overlapping pairs of this sub-step (SELF_HITS x uint16)
 
     // Two layouts of the per-slot state.  Default: [slot][k][thread] -- every thread owns ns rows (idle slots included),
     // 128-bit accesses are conflict-free.  OBJ (few, large environments: the shared memory per env decides how many
@@ -614,94 +617,124 @@ struct Stepper {
     // lanes of an env exchange slot state through shared memory: order the accesses
     __device__ __forceinline__ void lane_sync() const { if (L > 1 && m->cross_lane) __syncwarp(); }
 
-    // ---- self-collision: the spheres of link `li` (pose R, x, twist vw, vl about O) against the spheres of every link it
-    // may collide with.  Each link takes ITS side of a pair (the partner does the same from its lane): h J^T G J joins this
-    // link's inertia, -J^T F0 its bias -- implicit in its own acceleration, explicit in the partner's velocity (block-Jacobi,
-    // like the hand-object contact).  Broad phase: link-origin distance against the two links' sphere reach.
-    // j_first / j_step: the base's partner links are dealt round-robin to the lanes.
-    template <bool ACCUM>
-    __device__ __forceinline__ void self_contacts(int li, const LinkC &lk, const float R[9], const float x[3], const float vw[3], const float vl[3],
-                                                  float IA[21], float pa[3], float pl[3], const float aw[3], const float al[3],
-                                                  float F[3], float T[3], const RootState &rs, int j_first, int j_step) const {
-        const DevModel *gmd = gmodel;
-        unsigned lm = __ldg(&gmd->link_pairs[li]);
-        if (!lm || lk.cp_end <= lk.cp_begin) return;
-        const float h = m->h, skn = __ldg(&gmd->self_kn), gn = __ldg(&gmd->self_cn) + h * skn, smu = __ldg(&gmd->self_mu);
-        const float4 bi4 = __ldg(&gmd->link_bound[li]);
-        const float bci[3] = {bi4.x, bi4.y, bi4.z};
-        float bi[3]; matvec_add(R, bci, x, bi);                      // this link's bounding sphere, about O
-        int jj = 0;
+    // ---- self-collision (collision filter 0).  Detection once per sub-step, cooperatively: every lane writes the world centres
+    // of its links' contact spheres into the env's scratch, then the lanes of the env share the flat list of candidate pairs
+    // (uniform loop: no divergence between links) and append the overlapping ones -- typically none, a handful when limbs
+    // touch -- to a short per-env list.  Application per link (self_apply): each link takes ITS side of a listed pair:
+    // h J^T G J joins this link's inertia, -J^T F0 its bias -- implicit in its own acceleration, explicit in the partner's
+    // velocity (block-Jacobi, like the hand-object contact).
+    __device__ __forceinline__ void self_detect(const RootState &rs) const {
+        const int ncp = m->ncp;
+        if (L > 1) __syncwarp();                       // pass 1 of every lane is complete; last sub-step's readers are done
 #pragma unroll 1
-        while (lm) {
-            const int j = __ffs(lm) - 1;
-            lm &= lm - 1;
-            if (j_step > 1 && (jj++ % j_step) != j_first) continue;
-            const int ref = j ? __ldg(&gmd->link_slot[j]) : 0;
-            const float4 bj4 = __ldg(&gmd->link_bound[j]);
-            float Rj[9], xj[3], vwj[3], vlj[3];
-            if (j == 0) {
-                root_pose(rs, Rj, vwj, vlj);
-                xj[0] = xj[1] = xj[2] = 0.f;
-            } else {
-                const float4 a = S4x(ref >> 8, ref & 255, 0), b = S4x(ref >> 8, ref & 255, 1), c = S4x(ref >> 8, ref & 255, 2);
-                Rj[0] = a.x; Rj[1] = a.y; Rj[2] = a.z; Rj[3] = a.w; Rj[4] = b.x; Rj[5] = b.y; Rj[6] = b.z; Rj[7] = b.w; Rj[8] = c.x;
-                xj[0] = c.y; xj[1] = c.z; xj[2] = c.w;
-            }
-            {
-                const float bcj[3] = {bj4.x, bj4.y, bj4.z};
-                float bj[3]; matvec_add(Rj, bcj, xj, bj);
-                const float dx = bi[0] - bj[0], dy = bi[1] - bj[1], dz = bi[2] - bj[2], rr = bi4.w + bj4.w;
-                if (dx * dx + dy * dy + dz * dz >= rr * rr) continue;
-            }
-            if (j != 0) load_twist_x(ref >> 8, ref & 255, vwj, vlj);
-            const LinkC &lj = links[j];
+        for (int s = 0; s < m->ns; s++) {
+            const int li = link_of(s);
+            if (li < 0) continue;
+            const LinkC &lk = links[li];
+            if (lk.cp_end <= lk.cp_begin) continue;
+            const float4 a = S4(s, 0), b = S4(s, 1), c = S4(s, 2);
+            const float R[9] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x}, x[3] = {c.y, c.z, c.w};
 #pragma unroll 1
             for (int n = lk.cp_begin; n < lk.cp_end; n++) {
-                const unsigned long long mask = __ldg(&gmd->cp_pairs[n]);
-                if (!mask) continue;
-                const CpC &cn_ = gr.cps[n];
-                const float pn[3] = {cn_.pos[0], cn_.pos[1], cn_.pos[2]};
-                float ci[3]; matvec_add(R, pn, x, ci);
-#pragma unroll 1
-                for (int k = lj.cp_begin; k < lj.cp_end; k++) {
-                    if (!((mask >> k) & 1ull)) continue;
-                    const CpC &ck_ = gr.cps[k];
-                    const float pk[3] = {ck_.pos[0], ck_.pos[1], ck_.pos[2]};
-                    float cj[3]; matvec_add(Rj, pk, xj, cj);
-                    const float dv[3] = {ci[0] - cj[0], ci[1] - cj[1], ci[2] - cj[2]};
-                    const float d2 = dot3(dv, dv), rsum = cn_.radius + ck_.radius;
-                    if (d2 >= rsum * rsum || d2 < 1e-12f) continue;
-                    const float inv = rsqrtf(d2), dist = d2 * inv, pen = rsum - dist;
-                    const float n[3] = {dv[0] * inv, dv[1] * inv, dv[2] * inv};            // force on THIS link: away from the partner
-                    const float off = cn_.radius - 0.5f * pen;                               // contact point: middle of the overlap
-                    const float r[3] = {ci[0] - off * n[0], ci[1] - off * n[1], ci[2] - off * n[2]};
-                    float ui[3], uj[3];
-                    cross_add(vw, r, vl, ui); cross_add(vwj, r, vlj, uj);
-                    const float rel[3] = {ui[0] - uj[0], ui[1] - uj[1], ui[2] - uj[2]};
-                    const float un = dot3(rel, n);
-                    const float Fn = skn * pen - gn * un;
-                    if (Fn <= 0.f) continue;
-                    const float ut[3] = {rel[0] - un * n[0], rel[1] - un * n[1], rel[2] - un * n[2]};
-                    const float gam = smu * Fn * rsqrtf(dot3(ut, ut) + m->vs2);
-                    const float F0[3] = {Fn * n[0] - gam * ut[0], Fn * n[1] - gam * ut[1], Fn * n[2] - gam * ut[2]};
-                    if (ACCUM) {
-                        contact_inertia(IA, h, gam, gn, r, n);
-                        float rxF[3]; cross(r, F0, rxF);
-#pragma unroll
-                        for (int c = 0; c < 3; c++) { pa[c] -= rxF[c]; pl[c] -= F0[c]; }
-                    } else {
-                        float Ja[3]; cross_add(aw, r, al, Ja);
-                        const float Jan = dot3(Ja, n);
-                        float Fk[3];
-#pragma unroll
-                        for (int c = 0; c < 3; c++) Fk[c] = F0[c] - h * (gam * Ja[c] + (gn - gam) * Jan * n[c]);
-                        const float rl[3] = {r[0] - x[0], r[1] - x[1], r[2] - x[2]};
-                        float tq[3]; cross(rl, Fk, tq);
-#pragma unroll
-                        for (int c = 0; c < 3; c++) { F[c] += Fk[c]; T[c] += tq[c]; }
-                    }
-                }
+                const CpC &cp = gr.cps[n];
+                const float p[3] = {cp.pos[0], cp.pos[1], cp.pos[2]};
+                float ci[3]; matvec_add(R, p, x, ci);
+                scen[n] = make_float4(ci[0], ci[1], ci[2], cp.radius);
             }
+        }
+        if (lane == 0) {
+            const LinkC &lk = links[0];
+            float Rr[9]; quat_to_mat(rs.rq, Rr);
+            const float xr[3] = {0.f, 0.f, 0.f};
+#pragma unroll 1
+            for (int n = lk.cp_begin; n < lk.cp_end; n++) {
+                const CpC &cp = gr.cps[n];
+                const float p[3] = {cp.pos[0], cp.pos[1], cp.pos[2]};
+                float ci[3]; matvec_add(Rr, p, xr, ci);
+                scen[n] = make_float4(ci[0], ci[1], ci[2], cp.radius);
+            }
+            scen[ncp] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (L > 1) __syncwarp();
+        unsigned *cnt = reinterpret_cast<unsigned *>(scen + ncp);
+        unsigned short *list = reinterpret_cast<unsigned short *>(scen + ncp + 1);
+        const int np = __ldg(&gmodel->npairs);
+#pragma unroll 1
+        for (int p = lane; p < np; p += L) {
+            const unsigned pr = __ldg(&gmodel->pair_list[p]);
+            const float4 ca = scen[pr & 255u], cb = scen[pr >> 8];
+            const float dx = ca.x - cb.x, dy = ca.y - cb.y, dz = ca.z - cb.z, rsum = ca.w + cb.w;
+            const float d2 = dx * dx + dy * dy + dz * dz;
+            if (d2 < rsum * rsum && d2 >= 1e-12f) {
+                const unsigned idx = atomicAdd(cnt, 1u);
+                if (idx < (unsigned)SELF_HITS) list[idx] = (unsigned short)pr;
+            }
+        }
+        if (L > 1) __syncwarp();
+    }
+    // one side of one overlapping pair: sphere n (this link, twist vw / vl, origin x) against sphere k of link j
+    template <bool ACCUM>
+    __device__ __forceinline__ void self_pair(int n, int k, int j, const float x[3], const float vw[3], const float vl[3],
+                                              float IA[21], float pa[3], float pl[3], const float aw[3], const float al[3],
+                                              float F[3], float T[3], const RootState &rs) const {
+        const float h = m->h, skn = __ldg(&gmodel->self_kn), gn = __ldg(&gmodel->self_cn) + h * skn, smu = __ldg(&gmodel->self_mu);
+        const float4 ci = scen[n], cj = scen[k];
+        float vwj[3], vlj[3];
+        if (j == 0) {
+            const bool fixed = m->root_fixed != 0;
+#pragma unroll
+            for (int c = 0; c < 3; c++) { vwj[c] = fixed ? 0.f : rs.rw[c]; vlj[c] = fixed ? 0.f : rs.rv[c]; }
+        } else {
+            const int ref = __ldg(&gmodel->link_slot[j]);
+            load_twist_x(ref >> 8, ref & 255, vwj, vlj);
+        }
+        const float dv[3] = {ci.x - cj.x, ci.y - cj.y, ci.z - cj.z};
+        const float d2 = dot3(dv, dv), rsum = ci.w + cj.w;
+        const float inv = rsqrtf(d2), dist = d2 * inv, pen = rsum - dist;
+        const float n_[3] = {dv[0] * inv, dv[1] * inv, dv[2] * inv};               // force on THIS link: away from the partner
+        const float off = ci.w - 0.5f * pen;                                        // contact point: middle of the overlap
+        const float r[3] = {ci.x - off * n_[0], ci.y - off * n_[1], ci.z - off * n_[2]};
+        float ui[3], uj[3];
+        cross_add(vw, r, vl, ui); cross_add(vwj, r, vlj, uj);
+        const float rel[3] = {ui[0] - uj[0], ui[1] - uj[1], ui[2] - uj[2]};
+        const float un = dot3(rel, n_);
+        const float Fn = skn * pen - gn * un;
+        if (Fn <= 0.f) return;
+        const float ut[3] = {rel[0] - un * n_[0], rel[1] - un * n_[1], rel[2] - un * n_[2]};
+        const float gam = smu * Fn * rsqrtf(dot3(ut, ut) + m->vs2);
+        const float F0[3] = {Fn * n_[0] - gam * ut[0], Fn * n_[1] - gam * ut[1], Fn * n_[2] - gam * ut[2]};
+        if (ACCUM) {
+            contact_inertia(IA, h, gam, gn, r, n_);
+            float rxF[3]; cross(r, F0, rxF);
+#pragma unroll
+            for (int c = 0; c < 3; c++) { pa[c] -= rxF[c]; pl[c] -= F0[c]; }
+        } else {
+            float Ja[3]; cross_add(aw, r, al, Ja);
+            const float Jan = dot3(Ja, n_);
+            float Fk[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) Fk[c] = F0[c] - h * (gam * Ja[c] + (gn - gam) * Jan * n_[c]);
+            const float rl[3] = {r[0] - x[0], r[1] - x[1], r[2] - x[2]};
+            float tq[3]; cross(rl, Fk, tq);
+#pragma unroll
+            for (int c = 0; c < 3; c++) { F[c] += Fk[c]; T[c] += tq[c]; }
+        }
+    }
+    // every listed pair one of whose spheres rides on link li
+    template <bool ACCUM>
+    __device__ __forceinline__ void self_apply(int li, const float x[3], const float vw[3], const float vl[3],
+                                               float IA[21], float pa[3], float pl[3], const float aw[3], const float al[3],
+                                               float F[3], float T[3], const RootState &rs) const {
+        const int ncp = m->ncp;
+        const unsigned cnt = min(*reinterpret_cast<const unsigned *>(scen + ncp), (unsigned)SELF_HITS);
+        const unsigned short *list = reinterpret_cast<const unsigned short *>(scen + ncp + 1);
+#pragma unroll 1
+        for (unsigned e = 0; e < cnt; e++) {
+            const unsigned pr = list[e];
+            const int a = pr & 255u, b = pr >> 8;
+            const int la = gr.cps[a].pad, lb = gr.cps[b].pad;
+            if (la == li) self_pair<ACCUM>(a, b, lb, x, vw, vl, IA, pa, pl, aw, al, F, T, rs);
+            if (lb == li) self_pair<ACCUM>(b, a, la, x, vw, vl, IA, pa, pl, aw, al, F, T, rs);
         }
     }
 
@@ -1046,7 +1079,7 @@ struct Stepper {
         // A slot's projected inertia either travels in registers to the next-lower slot of the lane
         // (chains; finally from slot 0 to the root) or is parked in one of this thread's accumulators,
         // from where its parent -- possibly in another lane -- collects it (SlotRec::child).
-        if (!OBJ && L > 1 && m->self_on && !m->cross_lane) __syncwarp();   // every lane's link poses are needed by every other
+        if (!OBJ && m->self_on) self_detect(rs);
         const int racc = m->root_acc >= 0 ? lane_acc(m->root_acc) : -1;
         if (racc >= 0) {
 #pragma unroll
@@ -1072,7 +1105,7 @@ struct Stepper {
                     float dummy[3];
                     if (ground) link_contacts<true, HF>(m, gr, lk, rs.rp, R, x, vw, vl, I, qa, ql, dummy, dummy, dummy, dummy, 0, 1);
                     if (OBJ) obj_link_contacts<true>(lk, sr.link, R, x, vw, vl, I, qa, ql, dummy, dummy, dummy, dummy, 0, 1);
-                    if (!OBJ && m->self_on) self_contacts<true>(sr.link, lk, R, x, vw, vl, I, qa, ql, dummy, dummy, dummy, dummy, rs, 0, 1);
+                    if (!OBJ && m->self_on) self_apply<true>(sr.link, x, vw, vl, I, qa, ql, dummy, dummy, dummy, dummy, rs);
                     if (carry) {
 #pragma unroll
                         for (int c = 0; c < 21; c++) I[c] += IA[c];
@@ -1159,7 +1192,7 @@ struct Stepper {
             link_inertia(lk, mine ? lk.mass : 0.f, mine ? 1.f : 0.f, Rr, xr, vwr, vlr, g, I, qa, ql, m->ang_damp, m->lin_damp);
             if (ground) link_contacts<true, HF>(m, gr, lk, rs.rp, Rr, xr, vwr, vlr, I, qa, ql, dummy, dummy, dummy, dummy, lane, L);
             if (OBJ) obj_link_contacts<true>(lk, 0, Rr, xr, vwr, vlr, I, qa, ql, dummy, dummy, dummy, dummy, lane, L);
-            if (!OBJ && m->self_on) self_contacts<true>(0, lk, Rr, xr, vwr, vlr, I, qa, ql, dummy, dummy, dummy, dummy, rs, lane, L);
+            if (!OBJ && m->self_on && mine) self_apply<true>(0, xr, vwr, vlr, I, qa, ql, dummy, dummy, dummy, dummy, rs);
 #pragma unroll
             for (int c = 0; c < 21; c++) IA[c] += I[c];               // IA holds slot 0's contribution (or zeros)
 #pragma unroll
@@ -1188,7 +1221,7 @@ struct Stepper {
                 float F[3] = {0.f, 0.f, 0.f}, T[3] = {0.f, 0.f, 0.f};
                 if (ground) link_contacts<false, HF>(m, gr, lk, rs.rp, Rr, xr, vwr, vlr, I, qa, ql, awr, alr, F, T, lane, L);
                 if (OBJ) obj_link_contacts<false>(lk, 0, Rr, xr, vwr, vlr, I, qa, ql, awr, alr, F, T, lane, L);
-                if (!OBJ && m->self_on) self_contacts<false>(0, lk, Rr, xr, vwr, vlr, I, qa, ql, awr, alr, F, T, rs, lane, L);
+                if (!OBJ && m->self_on && mine) self_apply<false>(0, xr, vwr, vlr, I, qa, ql, awr, alr, F, T, rs);
 #pragma unroll
                 for (int c = 0; c < 3; c++) { F[c] = lane_sum<L>(F[c]); T[c] = lane_sum<L>(T[c]); }
                 if (lane == 0) emit_wrench(0, lk, Rr, F, T, o);
@@ -1238,7 +1271,7 @@ struct Stepper {
                             load_pose(s, R, x, vw, vl);
                             if (ground) link_contacts<false, HF>(m, gr, lk, rs.rp, R, x, vw, vl, dI, d3, d3, awc, alc, F, T, 0, 1);
                             if (OBJ) obj_link_contacts<false>(lk, li, R, x, vw, vl, dI, d3, d3, awc, alc, F, T, 0, 1);
-                            if (!OBJ && m->self_on) self_contacts<false>(li, lk, R, x, vw, vl, dI, d3, d3, awc, alc, F, T, rs, 0, 1);
+                            if (!OBJ && m->self_on) self_apply<false>(li, x, vw, vl, dI, d3, d3, awc, alc, F, T, rs);
                             emit_wrench(li, lk, R, F, T, o);
                         } else if (lk.sensor >= 0 || (o.net_contact && m->link_body[li] >= 0)) {
                             float R[9], x[3]; const float z[3] = {0.f, 0.f, 0.f};
