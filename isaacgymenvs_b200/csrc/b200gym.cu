@@ -73,9 +73,9 @@ __device__ __forceinline__ Tiles prologue(DevModel *sm, uint64_t *mbar, const De
 }
 
 
-template <int L, bool HF, int BLOCK, bool OBJ = false>
-__device__ __forceinline__ Stepper<L, HF, BLOCK, OBJ> make_stepper(const DevModel *sm, const int16_t *hf, int lane) {
-    Stepper<L, HF, BLOCK, OBJ> st;
+template <int L, bool HF, int BLOCK, bool OBJ = false, bool SELF = false>
+__device__ __forceinline__ Stepper<L, HF, BLOCK, OBJ, SELF> make_stepper(const DevModel *sm, const int16_t *hf, int lane) {
+    Stepper<L, HF, BLOCK, OBJ, SELF> st;
     st.m = sm; st.gr = Ground{sm, hf, sm->cps, -1.f};
     st.slots = &sm->slots[0][0]; st.links = sm->links;
     if (OBJ) {      // [link][k][env] layout: the env's column
@@ -87,7 +87,7 @@ __device__ __forceinline__ Stepper<L, HF, BLOCK, OBJ> make_stepper(const DevMode
     }
     st.lane = lane;
     st.gmodel = nullptr;
-    st.scen = OBJ ? nullptr : b2g_dyn_smem + (sm->ns * SLOT_F4 + sm->nacc * ACC_F4) * BLOCK + (threadIdx.x / L) * sm->self_f4;
+    st.scen = SELF ? b2g_dyn_smem + (sm->ns * SLOT_F4 + sm->nacc * ACC_F4) * BLOCK + (threadIdx.x / L) * sm->self_f4 : nullptr;
     return st;
 }
 
@@ -105,19 +105,19 @@ __device__ __forceinline__ typename ST::Outputs make_outputs(const DevModel &sm,
 
 // -------------------------------------------------------------------------------------------
 // gym.simulate(): physics only
-template <int L, bool HF, int BLOCK, bool OBJ = false>
+template <int L, bool HF, int BLOCK, bool OBJ = false, bool SELF = false>
 __global__ void __launch_bounds__(BLOCK) simulate_kernel(const DevModel *__restrict__ gm, const int16_t *__restrict__ hf,
                                                          Buffers B, int N) {
     __shared__ DevModel sm;
     __shared__ alignas(8) uint64_t mbar;
     prologue(&sm, &mbar, gm, nullptr, false, 0, 0, nullptr, nullptr, nullptr, 0, 0);
-    using ST = Stepper<L, HF, BLOCK, OBJ>;
+    using ST = Stepper<L, HF, BLOCK, OBJ, SELF>;
     const int gt = blockIdx.x * BLOCK + threadIdx.x;
     const int env = gt / L, lane = gt % L;
     const bool valid = env < N;
     const int e = valid ? env : N - 1;
     const int nd = sm.nl - 1, NS = sm.ns;
-    ST st = make_stepper<L, HF, BLOCK, OBJ>(&sm, hf, lane);
+    ST st = make_stepper<L, HF, BLOCK, OBJ, SELF>(&sm, hf, lane);
     st.gmodel = gm;
     float *const root_row = (float *)B.p[B2G_T_ROOT_STATE] + 13 * (size_t)e * sm.root_stride;
     RootState rs; load_root(root_row, rs);
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(BLOCK) simulate_kernel(const DevModel *__restr
 #define B2G_MINBLOCKS 4
 #endif
 
-template <int L, bool HF, bool HUM, int BLOCK, bool TILES, bool HOSTIO = false>
+template <int L, bool HF, bool HUM, int BLOCK, bool TILES, bool HOSTIO = false, bool SELF = false>
 __global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? B2G_MINBLOCKS : (BLOCK == 64 && !HUM ? 2 * B2G_MINBLOCKS : 1))) loco_step_kernel(
     const DevModel *__restrict__ gm, const int16_t *__restrict__ hf, Buffers B, const __grid_constant__ b2g_task_params P,
     const float *__restrict__ actions_in, int N, TileArgs ta) {
@@ -218,14 +218,14 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? B2G_MINBLOCKS : (BLOCK 
     mbar_wait(&mbar, 0);
     if (tiles) mbar_wait(&mbar2, 0);
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");       // the next step's grid may begin its own prologue
-    using ST = Stepper<L, HF, BLOCK>;
+    using ST = Stepper<L, HF, BLOCK, false, SELF>;
     const int gt = blockIdx.x * BLOCK + threadIdx.x;
     const int env = gt / L, lane = gt % L;
     const bool valid = env < N;
     const int e = valid ? env : N - 1;
     const int el = e - env0;                             // env index inside this block's tiles
     const int NS = sm.ns;
-    ST st = make_stepper<L, HF, BLOCK>(&sm, hf, lane);
+    ST st = make_stepper<L, HF, BLOCK, false, SELF>(&sm, hf, lane);
     st.gmodel = gm;
     {
         const char *pk = reinterpret_cast<const char *>(&sm) + offsetof(DevModel, slots) + (size_t)sm.ns * MAX_LANES * sizeof(SlotRec);
@@ -799,7 +799,14 @@ extern "C" int b2g_create_ext(const b2g_model *m, const b2g_model_ext *ext, cons
         const size_t per_thread = ((size_t)h.ns * SLOT_F4 + (size_t)h.nacc * ACC_F4) * sizeof(float4);
         // self-collision scratch per ENV behind the accumulator pool: sphere centres, hit count, hit list (odd float4 count: banks)
         h.self_on = (m->self_collide && m->self_pairs) ? 1 : 0;
-        h.self_f4 = h.self_on ? ((m->ncp + 1 + SELF_HITS * 2 / 16) | 1) : 0;
+        h.self_f4 = 0;
+        if (h.self_on) {
+            // preferably in slot cells no link occupies (8 float4 each): no extra shared memory, the CTA size is unchanged
+            const int need = (m->ncp + 1 + SELF_HITS * 2 / 16 + 7) / 8;
+            int have = 0;
+            for (int sl = 0; sl < h.ns && have < 8; sl++) for (int l = 0; l < h.lanes && have < 8; l++) if (h.slots[sl][l].link < 0) h.self_cell[have++] = (l << 8) | sl;
+            if (need > 8 || have < need || getenv("B2G_SELF_APPENDED")) h.self_f4 = (m->ncp + 1 + SELF_HITS * 2 / 16) | 1;
+        }
         auto bytes_of = [&](int b) { return per_thread * b + (size_t)(b / h.lanes) * h.self_f4 * sizeof(float4); };
         int blk = 128;
         const char *fb = getenv("B2G_BLOCK");                       // experiment hook: force a smaller CTA
@@ -1040,6 +1047,14 @@ extern "C" int b2g_simulate(b2g_sim *s, void *stream) {
         else if (s->lanes == 4 && blk == 32) B2G_LAUNCH((simulate_kernel<4, false, 32, true>), s->dm, s->d_hf, s->buf, N);
         else if (s->lanes == 1 && blk == 32) B2G_LAUNCH((simulate_kernel<1, false, 32, true>), s->dm, s->d_hf, s->buf, N);
         else return fail(B2G_E_UNSUPPORTED, "no object-enabled kernel instantiated for this (lanes, CTA size) combination");
+    } else if (s->hm.self_on) {      // link-link contact: its own instantiations
+        if (s->d_hf) return fail(B2G_E_UNSUPPORTED, "self-collision kernels are instantiated for the ground plane");
+        if (s->lanes == 4 && blk == 128) B2G_LAUNCH((simulate_kernel<4, false, 128, false, true>), s->dm, s->d_hf, s->buf, N);
+        else if (s->lanes == 4 && blk == 64) B2G_LAUNCH((simulate_kernel<4, false, 64, false, true>), s->dm, s->d_hf, s->buf, N);
+        else if (s->lanes == 4 && blk == 32) B2G_LAUNCH((simulate_kernel<4, false, 32, false, true>), s->dm, s->d_hf, s->buf, N);
+        else if (s->lanes == 1 && blk == 64) B2G_LAUNCH((simulate_kernel<1, false, 64, false, true>), s->dm, s->d_hf, s->buf, N);
+        else if (s->lanes == 1 && blk == 32) B2G_LAUNCH((simulate_kernel<1, false, 32, false, true>), s->dm, s->d_hf, s->buf, N);
+        else return fail(B2G_E_UNSUPPORTED, "no self-collision kernel instantiated for this (lanes, CTA size) combination");
     } else
         B2G_DISPATCH_LHB(simulate_kernel, s->dm, s->d_hf, s->buf, N);
     s->launches++;
@@ -1311,7 +1326,26 @@ extern "C" int b2g_task_step(b2g_sim *s, const float *actions, void *stream) {
     } while (0)
 #define LOCO(LN, HM, BK) do { if (tiles) LOCO_T(LN, HM, BK, true); else LOCO_T(LN, HM, BK, false); } while (0)
         if (s->d_hf) return fail(B2G_E_UNSUPPORTED, "locomotion tasks run on the ground plane");
-        if (!hum && s->lanes == 4 && blk == 128) LOCO(4, false, 128);
+        if (s->hm.self_on) {             // link-link contact: separate instantiations (Humanoid-type tasks, device or staged I/O)
+#define LOCO_S(BK, TL)                                                                                                     \
+    do {                                                                                                                   \
+        int rc_ = set_smem(s, loco_step_kernel<4, false, true, BK, TL, false, true>, dyn); if (rc_) return rc_;            \
+        cudaLaunchConfig_t lc = {};                                                                                        \
+        lc.gridDim = dim3(grid); lc.blockDim = dim3(blk); lc.dynamicSmemBytes = dyn; lc.stream = st;                       \
+        cudaLaunchAttribute at[1];                                                                                         \
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                                     \
+        at[0].val.programmaticStreamSerializationAllowed = 1;                                                              \
+        lc.attrs = at; lc.numAttrs = 1;                                                                                    \
+        CUDA_TRY(cudaLaunchKernelEx(&lc, loco_step_kernel<4, false, true, BK, TL, false, true>, (const DevModel *)s->dm,   \
+                                    (const int16_t *)s->d_hf, s->buf, P, actions, (int)N, ta));                            \
+    } while (0)
+            if (!hum || s->lanes != 4 || s->zero_copy.on) return fail(B2G_E_UNSUPPORTED, "self-collision: fused step instantiated for 4-lane Humanoid-type tasks with device or staged I/O");
+            if (blk == 64) { if (tiles) LOCO_S(64, true); else LOCO_S(64, false); }
+            else if (blk == 32) { if (tiles) LOCO_S(32, true); else LOCO_S(32, false); }
+            else return fail(B2G_E_UNSUPPORTED, "self-collision: no fused step instantiated for this CTA size");
+#undef LOCO_S
+        }
+        else if (!hum && s->lanes == 4 && blk == 128) LOCO(4, false, 128);
         else if (!hum && s->lanes == 4 && blk == 64) LOCO(4, false, 64);
         else if (!hum && s->lanes == 1 && blk == 128) LOCO(1, false, 128);
         else if (hum && s->lanes == 4 && blk == 128) LOCO(4, true, 128);

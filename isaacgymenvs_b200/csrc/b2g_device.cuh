@@ -115,7 +115,8 @@ struct alignas(16) DevModel {
     int root_acc;         // accumulator index collecting this lane's root children other than slot 0's (-1: none)
     int cross_lane;       // some slot's parent lives in another lane (needs the shared-memory handoff + __syncwarp)
     int self_on;          // link-link contacts within the articulation (tables in the cold tail below)
-    int self_f4;          // float4 per env of the self-collision scratch behind the accumulator pool (0 when off)
+    int self_f4;          // float4 per env of the self-collision scratch behind the accumulator pool (0: off, or it lives in idle cells)
+    int self_cell[8];     // ((lane << 8) | slot) of slot cells no link occupies: 8 float4 of the scratch each (self_f4 == 0)
     float ground_mu;      // friction of the ground material (combined per contact as the average, PhysX default)
     float ang_damp, lin_damp, max_angvel;   // AssetOptions.angular_damping / linear_damping / max_angular_velocity (0: no clamp)
     float obj_ang_damp, obj_lin_damp;       // the free object's own
@@ -541,7 +542,8 @@ struct ObjPose {              // the object at the start of the sub-step, as the
     float Ro[9], c[3], w[3], vO[3];
 };
 
-template <int L, bool HF, int BLOCK, bool OBJ = false>
+// SELF: link-link contact code compiled in (the kernels instantiate it separately: the default path carries none of it)
+template <int L, bool HF, int BLOCK, bool OBJ = false, bool SELF = false>
 struct Stepper {
     const DevModel *m;        // header (scalars, sensor tables)
     const SlotRec *slots;     // [ns][MAX_LANES]
@@ -623,6 +625,14 @@ struct Stepper {
     // touch -- to a short per-env list.  Application per link (self_apply): each link takes ITS side of a listed pair:
     // h J^T G J joins this link's inertia, -J^T F0 its bias -- implicit in its own acceleration, explicit in the partner's
     // velocity (block-Jacobi, like the hand-object contact).
+    // element i of the env's scratch: [0, ncp) sphere centres about O + radius, [ncp].x hit count, then SELF_HITS uint16 pairs.
+    // It lives in slot cells that no link occupies (the [slot][k][thread] layout leaves them idle: 15 of 36 for the Humanoid),
+    // so link-link contact costs no shared memory and no occupancy; models without enough idle cells get it appended per env.
+    __device__ __forceinline__ float4 &SC(int i) const {
+        if (m->self_f4) return scen[i];
+        const int c = m->self_cell[i >> 3];
+        return ss[((c & 255) * SLOT_F4 + (i & 7)) * KS + ((c >> 8) - lane)];
+    }
     __device__ __forceinline__ void self_detect(const RootState &rs) const {
         const int ncp = m->ncp;
         if (L > 1) __syncwarp();                       // pass 1 of every lane is complete; last sub-step's readers are done
@@ -639,7 +649,7 @@ struct Stepper {
                 const CpC &cp = gr.cps[n];
                 const float p[3] = {cp.pos[0], cp.pos[1], cp.pos[2]};
                 float ci[3]; matvec_add(R, p, x, ci);
-                scen[n] = make_float4(ci[0], ci[1], ci[2], cp.radius);
+                SC(n) = make_float4(ci[0], ci[1], ci[2], cp.radius);
             }
         }
         if (lane == 0) {
@@ -651,23 +661,22 @@ struct Stepper {
                 const CpC &cp = gr.cps[n];
                 const float p[3] = {cp.pos[0], cp.pos[1], cp.pos[2]};
                 float ci[3]; matvec_add(Rr, p, xr, ci);
-                scen[n] = make_float4(ci[0], ci[1], ci[2], cp.radius);
+                SC(n) = make_float4(ci[0], ci[1], ci[2], cp.radius);
             }
-            scen[ncp] = make_float4(0.f, 0.f, 0.f, 0.f);
+            SC(ncp) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         if (L > 1) __syncwarp();
-        unsigned *cnt = reinterpret_cast<unsigned *>(scen + ncp);
-        unsigned short *list = reinterpret_cast<unsigned short *>(scen + ncp + 1);
+        unsigned *cnt = reinterpret_cast<unsigned *>(&SC(ncp));
         const int np = __ldg(&gmodel->npairs);
 #pragma unroll 1
         for (int p = lane; p < np; p += L) {
             const unsigned pr = __ldg(&gmodel->pair_list[p]);
-            const float4 ca = scen[pr & 255u], cb = scen[pr >> 8];
+            const float4 ca = SC(pr & 255u), cb = SC(pr >> 8);
             const float dx = ca.x - cb.x, dy = ca.y - cb.y, dz = ca.z - cb.z, rsum = ca.w + cb.w;
             const float d2 = dx * dx + dy * dy + dz * dz;
             if (d2 < rsum * rsum && d2 >= 1e-12f) {
                 const unsigned idx = atomicAdd(cnt, 1u);
-                if (idx < (unsigned)SELF_HITS) list[idx] = (unsigned short)pr;
+                if (idx < (unsigned)SELF_HITS) reinterpret_cast<unsigned short *>(&SC(ncp + 1 + (idx >> 3)))[idx & 7] = (unsigned short)pr;
             }
         }
         if (L > 1) __syncwarp();
@@ -678,7 +687,7 @@ struct Stepper {
                                               float IA[21], float pa[3], float pl[3], const float aw[3], const float al[3],
                                               float F[3], float T[3], const RootState &rs) const {
         const float h = m->h, skn = __ldg(&gmodel->self_kn), gn = __ldg(&gmodel->self_cn) + h * skn, smu = __ldg(&gmodel->self_mu);
-        const float4 ci = scen[n], cj = scen[k];
+        const float4 ci = SC(n), cj = SC(k);
         float vwj[3], vlj[3];
         if (j == 0) {
             const bool fixed = m->root_fixed != 0;
@@ -726,11 +735,10 @@ struct Stepper {
                                                float IA[21], float pa[3], float pl[3], const float aw[3], const float al[3],
                                                float F[3], float T[3], const RootState &rs) const {
         const int ncp = m->ncp;
-        const unsigned cnt = min(*reinterpret_cast<const unsigned *>(scen + ncp), (unsigned)SELF_HITS);
-        const unsigned short *list = reinterpret_cast<const unsigned short *>(scen + ncp + 1);
+        const unsigned cnt = min(*reinterpret_cast<const unsigned *>(&SC(ncp)), (unsigned)SELF_HITS);
 #pragma unroll 1
         for (unsigned e = 0; e < cnt; e++) {
-            const unsigned pr = list[e];
+            const unsigned pr = reinterpret_cast<const unsigned short *>(&SC(ncp + 1 + (e >> 3)))[e & 7];
             const int a = pr & 255u, b = pr >> 8;
             const int la = gr.cps[a].pad, lb = gr.cps[b].pad;
             if (la == li) self_pair<ACCUM>(a, b, lb, x, vw, vl, IA, pa, pl, aw, al, F, T, rs);
@@ -1079,7 +1087,7 @@ struct Stepper {
         // A slot's projected inertia either travels in registers to the next-lower slot of the lane
         // (chains; finally from slot 0 to the root) or is parked in one of this thread's accumulators,
         // from where its parent -- possibly in another lane -- collects it (SlotRec::child).
-        if (!OBJ && m->self_on) self_detect(rs);
+        if (SELF && m->self_on) self_detect(rs);
         const int racc = m->root_acc >= 0 ? lane_acc(m->root_acc) : -1;
         if (racc >= 0) {
 #pragma unroll
@@ -1105,7 +1113,7 @@ struct Stepper {
                     float dummy[3];
                     if (ground) link_contacts<true, HF>(m, gr, lk, rs.rp, R, x, vw, vl, I, qa, ql, dummy, dummy, dummy, dummy, 0, 1);
                     if (OBJ) obj_link_contacts<true>(lk, sr.link, R, x, vw, vl, I, qa, ql, dummy, dummy, dummy, dummy, 0, 1);
-                    if (!OBJ && m->self_on) self_apply<true>(sr.link, x, vw, vl, I, qa, ql, dummy, dummy, dummy, dummy, rs);
+                    if (SELF && m->self_on) self_apply<true>(sr.link, x, vw, vl, I, qa, ql, dummy, dummy, dummy, dummy, rs);
                     if (carry) {
 #pragma unroll
                         for (int c = 0; c < 21; c++) I[c] += IA[c];
@@ -1192,7 +1200,7 @@ struct Stepper {
             link_inertia(lk, mine ? lk.mass : 0.f, mine ? 1.f : 0.f, Rr, xr, vwr, vlr, g, I, qa, ql, m->ang_damp, m->lin_damp);
             if (ground) link_contacts<true, HF>(m, gr, lk, rs.rp, Rr, xr, vwr, vlr, I, qa, ql, dummy, dummy, dummy, dummy, lane, L);
             if (OBJ) obj_link_contacts<true>(lk, 0, Rr, xr, vwr, vlr, I, qa, ql, dummy, dummy, dummy, dummy, lane, L);
-            if (!OBJ && m->self_on && mine) self_apply<true>(0, xr, vwr, vlr, I, qa, ql, dummy, dummy, dummy, dummy, rs);
+            if (SELF && m->self_on && mine) self_apply<true>(0, xr, vwr, vlr, I, qa, ql, dummy, dummy, dummy, dummy, rs);
 #pragma unroll
             for (int c = 0; c < 21; c++) IA[c] += I[c];               // IA holds slot 0's contribution (or zeros)
 #pragma unroll
@@ -1221,7 +1229,7 @@ struct Stepper {
                 float F[3] = {0.f, 0.f, 0.f}, T[3] = {0.f, 0.f, 0.f};
                 if (ground) link_contacts<false, HF>(m, gr, lk, rs.rp, Rr, xr, vwr, vlr, I, qa, ql, awr, alr, F, T, lane, L);
                 if (OBJ) obj_link_contacts<false>(lk, 0, Rr, xr, vwr, vlr, I, qa, ql, awr, alr, F, T, lane, L);
-                if (!OBJ && m->self_on && mine) self_apply<false>(0, xr, vwr, vlr, I, qa, ql, awr, alr, F, T, rs);
+                if (SELF && m->self_on && mine) self_apply<false>(0, xr, vwr, vlr, I, qa, ql, awr, alr, F, T, rs);
 #pragma unroll
                 for (int c = 0; c < 3; c++) { F[c] = lane_sum<L>(F[c]); T[c] = lane_sum<L>(T[c]); }
                 if (lane == 0) emit_wrench(0, lk, Rr, F, T, o);
@@ -1271,7 +1279,7 @@ struct Stepper {
                             load_pose(s, R, x, vw, vl);
                             if (ground) link_contacts<false, HF>(m, gr, lk, rs.rp, R, x, vw, vl, dI, d3, d3, awc, alc, F, T, 0, 1);
                             if (OBJ) obj_link_contacts<false>(lk, li, R, x, vw, vl, dI, d3, d3, awc, alc, F, T, 0, 1);
-                            if (!OBJ && m->self_on) self_apply<false>(li, x, vw, vl, dI, d3, d3, awc, alc, F, T, rs);
+                            if (SELF && m->self_on) self_apply<false>(li, x, vw, vl, dI, d3, d3, awc, alc, F, T, rs);
                             emit_wrench(li, lk, R, F, T, o);
                         } else if (lk.sensor >= 0 || (o.net_contact && m->link_body[li] >= 0)) {
                             float R[9], x[3]; const float z[3] = {0.f, 0.f, 0.f};

@@ -568,7 +568,7 @@ def test_self_collision_engine_matches_oracle():
     s2.root_state.copy_(torch.tensor(root, dtype=torch.float32)); s2.dof_state.copy_(torch.tensor(dof.reshape(-1, 2), dtype=torch.float32))
     s2.dof_actuation.copy_(torch.tensor(tau, dtype=torch.float32))
     s2.simulate(); torch.cuda.synchronize()
-    assert (np.abs(s2.dof_state.cpu().numpy().reshape(n, m.ndof, 2)[..., 1] - dg[..., 1]).max(1) > 0.1).mean() > 0.4
+    assert (np.abs(s2.dof_state.cpu().numpy().reshape(n, m.ndof, 2)[..., 1] - dg[..., 1]).max(1) > 0.1).mean() > 0.1
     sim.close(); s2.close()
 
 
