@@ -1204,7 +1204,7 @@ static int anymal_step(b2g_sim *s, const float *actions, void *stream) {
     if (s->quad_ns == 3) {                               // the specialised sub-step (b2g_quad.cuh), joint state in registers
         const size_t dyn = ((size_t)quad_park_f4(3) * 128 + quad_model_f4(3)) * sizeof(float4);
         if (s->d_hf) {
-            const bool dr = s->buf.p[B2G_T_ENV_MASS_SCALE] || s->buf.p[B2G_T_ENV_DOF_PROPS] || s->buf.p[B2G_T_ENV_FRICTION];
+            const bool dr = s->buf.p[B2G_T_ENV_MASS_SCALE] || s->buf.p[B2G_T_ENV_DOF_PROPS];
             if (dr) {
                 rc = set_smem(s, quad_anymal_physics_kernel<true, 128, true>, dyn); if (rc) return rc;
                 quad_anymal_physics_kernel<true, 128, true><<<grid, blk, dyn, st>>>(s->d_qm, s->d_hf, s->buf, P, actions, N, s->hm.substeps, s->step_counter);

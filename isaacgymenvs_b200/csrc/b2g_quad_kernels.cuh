@@ -20,9 +20,9 @@ __device__ __forceinline__ QLane<NS, HF, SP> make_qlane(const float4 *qm, const 
 
 // per-env physical parameters (domain randomisation tensors; null = the model's own)
 template <class QL>
-__device__ __forceinline__ void attach_env_params(QL &L, const Buffers &B, int e, int nd) {
-    const float *ms = (const float *)B.p[B2G_T_ENV_MASS_SCALE];
-    const float4 *dp = (const float4 *)B.p[B2G_T_ENV_DOF_PROPS];
+__device__ __forceinline__ void attach_env_params(QL &L, const Buffers &B, int e, int nd, bool arrays = true) {
+    const float *ms = arrays ? (const float *)B.p[B2G_T_ENV_MASS_SCALE] : nullptr;
+    const float4 *dp = arrays ? (const float4 *)B.p[B2G_T_ENV_DOF_PROPS] : nullptr;
     const float *envmu = (const float *)B.p[B2G_T_ENV_FRICTION];
     if (ms) L.dr_mass = ms + (size_t)e * (nd + 1);
     if (dp) L.dr_dof = dp + (size_t)e * nd;
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(BLOCK, B2G_QUAD_MINBLOCKS(BLOCK)) quad_loco_ke
 // (PD torque + gym.simulate x decimation, anymal_terrain.py:441-451) + the control_freq_inv simulates of VecTask.step
 // (vec_task.py:379-382) + post_physics_step up to compute_reward (:453-475).  The joint state stays in registers across
 // the 5 sub-steps; the PD law reads it there.
-// DR = false: no per-env physical parameters bound -- their pointers are compile-time nulls (smaller code: this kernel runs one
+// DR = false: no per-env link-mass / joint-property arrays bound -- their pointers are compile-time nulls (smaller code: this kernel runs one
 // warp per scheduler, so instruction fetch is exposed: 27 % of its stall cycles are "no instruction")
 template <bool HF, int BLOCK, bool DR = true>
 __global__ void __launch_bounds__(BLOCK) quad_anymal_physics_kernel(const float4 *__restrict__ gqm, const int16_t *__restrict__ hf,
@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(BLOCK) quad_anymal_physics_kernel(const float4
     const bool valid = env < N;
     const int e = valid ? env : N - 1;
     QLane<NS, HF, 0> L = make_qlane<NS, HF, 0>(qm, hf, park, BLOCK, lane);
-    if (DR) attach_env_params(L, B, e, nd);
+    attach_env_params(L, B, e, nd, DR);                      // the per-env friction (terrain buckets, anymal_terrain.py:238-247) is always honoured
     RootState rs; load_root((const float *)B.p[B2G_T_ROOT_STATE] + 13 * (size_t)e, rs);
     const float2 *dofs = (const float2 *)B.p[B2G_T_DOF_STATE] + (size_t)e * nd;
     float *act_out = (float *)B.p[B2G_T_ACTIONS] + (size_t)e * nd;
