@@ -87,7 +87,11 @@ __device__ __forceinline__ Stepper<L, HF, BLOCK, OBJ, SELF> make_stepper(const D
     }
     st.lane = lane;
     st.gmodel = nullptr;
-    st.scen = SELF ? b2g_dyn_smem + (sm->ns * SLOT_F4 + sm->nacc * ACC_F4) * BLOCK + (threadIdx.x / L) * sm->self_f4 : nullptr;
+    st.scen = nullptr; st.scs = 1;
+    if (SELF) {
+        if (sm->self_f4) st.scen = b2g_dyn_smem + (sm->ns * SLOT_F4 + sm->nacc * ACC_F4) * BLOCK + (threadIdx.x / L) * sm->self_f4;
+        else { st.scen = b2g_dyn_smem + (sm->self_cell & 255) * SLOT_F4 * BLOCK + (threadIdx.x - lane + (sm->self_cell >> 8)); st.scs = BLOCK; }
+    }
     return st;
 }
 
@@ -801,11 +805,17 @@ extern "C" int b2g_create_ext(const b2g_model *m, const b2g_model_ext *ext, cons
         h.self_on = (m->self_collide && m->self_pairs) ? 1 : 0;
         h.self_f4 = 0;
         if (h.self_on) {
-            // preferably in slot cells no link occupies (8 float4 each): no extra shared memory, the CTA size is unchanged
-            const int need = (m->ncp + 1 + SELF_HITS * 2 / 16 + 7) / 8;
-            int have = 0;
-            for (int sl = 0; sl < h.ns && have < 8; sl++) for (int l = 0; l < h.lanes && have < 8; l++) if (h.slots[sl][l].link < 0) h.self_cell[have++] = (l << 8) | sl;
-            if (need > 8 || have < need || getenv("B2G_SELF_APPENDED")) h.self_f4 = (m->ncp + 1 + SELF_HITS * 2 / 16) | 1;
+            // preferably in a run of consecutive slot cells of one lane that no link occupies (10 float4 each): no extra shared
+            // memory, the CTA size is unchanged
+            const int need = (m->ncp + 1 + SELF_HITS * 2 / 16 + SLOT_F4 - 1) / SLOT_F4;
+            int found = -1;
+            for (int l = 0; l < h.lanes && found < 0; l++) for (int s0 = 0; s0 + need <= h.ns && found < 0; s0++) {
+                bool idle = true;
+                for (int k = 0; k < need; k++) idle = idle && h.slots[s0 + k][l].link < 0;
+                if (idle) found = (l << 8) | s0;
+            }
+            h.self_cell = found;
+            if (found < 0 || getenv("B2G_SELF_APPENDED")) h.self_f4 = (m->ncp + 1 + SELF_HITS * 2 / 16) | 1;
         }
         auto bytes_of = [&](int b) { return per_thread * b + (size_t)(b / h.lanes) * h.self_f4 * sizeof(float4); };
         int blk = 128;
@@ -892,6 +902,8 @@ extern "C" int b2g_create_ext(const b2g_model *m, const b2g_model_ext *ext, cons
             const int ia = std::min(inv[a], inv[b]), ib = std::max(inv[a], inv[b]);
             h.pair_list[h.npairs++] = (unsigned short)(ia | (ib << 8));
         }
+        while (h.npairs % (4 * h.lanes)) { if (h.npairs >= MAX_PAIRS) { delete s; return fail(B2G_E_UNSUPPORTED, "b2g_create: too many self-collision pairs"); } h.pair_list[h.npairs++] = 0; }
+        h.npairs /= 4;                                              // quads from here on
         for (int sl = 0; sl < h.ns; sl++) for (int l = 0; l < h.lanes; l++) if (h.slots[sl][l].link > 0) h.link_slot[h.slots[sl][l].link] = (l << 8) | sl;
     }
     // height field

@@ -116,7 +116,7 @@ struct alignas(16) DevModel {
     int cross_lane;       // some slot's parent lives in another lane (needs the shared-memory handoff + __syncwarp)
     int self_on;          // link-link contacts within the articulation (tables in the cold tail below)
     int self_f4;          // float4 per env of the self-collision scratch behind the accumulator pool (0: off, or it lives in idle cells)
-    int self_cell[8];     // ((lane << 8) | slot) of slot cells no link occupies: 8 float4 of the scratch each (self_f4 == 0)
+    int self_cell;        // self_f4 == 0: ((lane << 8) | first slot) of a run of consecutive slot cells no link occupies, the scratch's home
     float ground_mu;      // friction of the ground material (combined per contact as the average, PhysX default)
     float ang_damp, lin_damp, max_angvel;   // AssetOptions.angular_damping / linear_damping / max_angular_velocity (0: no clamp)
     float obj_ang_damp, obj_lin_damp;       // the free object's own
@@ -145,9 +145,9 @@ struct alignas(16) DevModel {
     float body_quat[MAX_LINKS][4];
     // ---- self-collision (create_actor collision filter 0): read through the GLOBAL copy of the model (Stepper::gmodel)
     float self_kn, self_cn, self_mu;
-    int npairs;                            // unordered sphere pairs that may collide
+    int npairs;                            // QUADS of candidate pairs (the list is padded to a multiple of 4 x lanes)
     int link_slot[MAX_LINKS];              // ((lane << 8) | slot) of the link's slot, -1 for the root
-    unsigned short pair_list[MAX_PAIRS];   // (a | b << 8), link-sorted sphere indices, a < b
+    alignas(8) unsigned short pair_list[MAX_PAIRS];   // (a | b << 8), link-sorted sphere indices, a < b; padding (0, 0)
 };
 static_assert(offsetof(DevModel, slots) % 16 == 0 && offsetof(DevModel, links) % 16 == 0 && offsetof(DevModel, cps) % 16 == 0, "bulk-copy alignment");
 
@@ -553,8 +553,8 @@ struct Stepper {
     float4 *acc;              // this thread's column of the accumulator pool
     int lane;
     const DevModel *gmodel;   // the model's copy in global memory (self-collision tables), may be null when self_on == 0
-    float4 *scen;             // this ENV's self-collision scratch: [0, ncp) sphere centres about O + radius, [ncp].x hit count,
-                              // [ncp + 1, ncp + 5) the overlapping pairs of this sub-step (SELF_HITS x uint16)
+    float4 *scen;             // this ENV's self-collision scratch, element i at scen[i * scs]: [0, ncp) sphere centres about O +
+    int scs;                  // radius, [ncp].x hit count, [ncp + 1, ncp + 5) the overlapping pairs of this sub-step (SELF_HITS x uint16)
 
     // Two layouts of the per-slot state.  Default: [slot][k][thread] -- every thread owns ns rows (idle slots included),
     // 128-bit accesses are conflict-free.  OBJ (few, large environments: the shared memory per env decides how many
@@ -625,14 +625,10 @@ struct Stepper {
     // touch -- to a short per-env list.  Application per link (self_apply): each link takes ITS side of a listed pair:
     // h J^T G J joins this link's inertia, -J^T F0 its bias -- implicit in its own acceleration, explicit in the partner's
     // velocity (block-Jacobi, like the hand-object contact).
-    // element i of the env's scratch: [0, ncp) sphere centres about O + radius, [ncp].x hit count, then SELF_HITS uint16 pairs.
-    // It lives in slot cells that no link occupies (the [slot][k][thread] layout leaves them idle: 15 of 36 for the Humanoid),
-    // so link-link contact costs no shared memory and no occupancy; models without enough idle cells get it appended per env.
-    __device__ __forceinline__ float4 &SC(int i) const {
-        if (m->self_f4) return scen[i];
-        const int c = m->self_cell[i >> 3];
-        return ss[((c & 255) * SLOT_F4 + (i & 7)) * KS + ((c >> 8) - lane)];
-    }
+    // element i of the env's scratch.  It lives in a run of slot cells that no link occupies (the [slot][k][thread] layout leaves
+    // them idle: the Humanoid's arm lanes use 3 of 9 slots), i.e. at a float4 stride of BLOCK -- link-link contact then costs no
+    // shared memory and no occupancy; models without such a run get it appended per env (stride 1).
+    __device__ __forceinline__ float4 &SC(int i) const { return scen[i * scs]; }
     __device__ __forceinline__ void self_detect(const RootState &rs) const {
         const int ncp = m->ncp;
         if (L > 1) __syncwarp();                       // pass 1 of every lane is complete; last sub-step's readers are done
@@ -667,16 +663,25 @@ struct Stepper {
         }
         if (L > 1) __syncwarp();
         unsigned *cnt = reinterpret_cast<unsigned *>(&SC(ncp));
-        const int np = __ldg(&gmodel->npairs);
+        // 4 pairs per lane and iteration from one 64-bit load (the list is padded with (0, 0), which the d2 >= 1e-12 test rejects):
+        // eight independent shared-memory loads in flight -- this loop runs at one warp per scheduler
+        const int nq = __ldg(&gmodel->npairs);                       // quads
+        const uint2 *quads = reinterpret_cast<const uint2 *>(gmodel->pair_list);
 #pragma unroll 1
-        for (int p = lane; p < np; p += L) {
-            const unsigned pr = __ldg(&gmodel->pair_list[p]);
-            const float4 ca = SC(pr & 255u), cb = SC(pr >> 8);
-            const float dx = ca.x - cb.x, dy = ca.y - cb.y, dz = ca.z - cb.z, rsum = ca.w + cb.w;
-            const float d2 = dx * dx + dy * dy + dz * dz;
-            if (d2 < rsum * rsum && d2 >= 1e-12f) {
-                const unsigned idx = atomicAdd(cnt, 1u);
-                if (idx < (unsigned)SELF_HITS) reinterpret_cast<unsigned short *>(&SC(ncp + 1 + (idx >> 3)))[idx & 7] = (unsigned short)pr;
+        for (int p = lane; p < nq; p += L) {
+            const uint2 q = __ldg(&quads[p]);
+            const unsigned pr[4] = {q.x & 0xffffu, q.x >> 16, q.y & 0xffffu, q.y >> 16};
+            float4 ca[4], cb[4];
+#pragma unroll
+            for (int t = 0; t < 4; t++) { ca[t] = SC(pr[t] & 255u); cb[t] = SC(pr[t] >> 8); }
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                const float dx = ca[t].x - cb[t].x, dy = ca[t].y - cb[t].y, dz = ca[t].z - cb[t].z, rsum = ca[t].w + cb[t].w;
+                const float d2 = dx * dx + dy * dy + dz * dz;
+                if (d2 < rsum * rsum && d2 >= 1e-12f) {
+                    const unsigned idx = atomicAdd(cnt, 1u);
+                    if (idx < (unsigned)SELF_HITS) reinterpret_cast<unsigned short *>(&SC(ncp + 1 + (idx >> 3)))[idx & 7] = (unsigned short)pr[t];
+                }
             }
         }
         if (L > 1) __syncwarp();
