@@ -75,15 +75,24 @@ def main():
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--out", default="")
     ap.add_argument("--device", default="cuda:0")
+    ap.add_argument("--units", default="256,128,64")          # HumanoidPPO.yaml: 400,200,100
+    ap.add_argument("--lr", type=float, default=3e-4)          # HumanoidPPO.yaml: 5e-4
+    ap.add_argument("--mini-epochs", type=int, default=4)      # HumanoidPPO.yaml: 5
+    ap.add_argument("--critic-coef", type=float, default=2.0)  # HumanoidPPO.yaml: 4
+    ap.add_argument("--self-collision", action="store_true")   # Humanoid: env.selfCollision=True
     args = ap.parse_args()
     import isaacgymenvs_b200
     dev = args.device
     torch.manual_seed(args.seed)
-    env = isaacgymenvs_b200.make(seed=args.seed, task=args.task, num_envs=args.num_envs, sim_device=dev, rl_device=dev, headless=True)
+    cfg = None
+    if args.self_collision:
+        from isaacgymenvs_b200 import config
+        cfg = config.builtin_cfg(args.task, {"sim_device": dev, "rl_device": dev}); cfg["task"]["env"]["selfCollision"] = True
+    env = isaacgymenvs_b200.make(seed=args.seed, task=args.task, num_envs=args.num_envs, sim_device=dev, rl_device=dev, headless=True, cfg=cfg)
     N, O, A, T = env.num_envs, env.num_obs, env.num_acts, args.horizon
-    net = ActorCritic(O, A).to(dev)
+    net = ActorCritic(O, A, tuple(int(u) for u in args.units.split(","))).to(dev)
     obs_rms, val_rms = RunningMeanStd((O,)).to(dev), RunningMeanStd(()).to(dev)
-    lr, kl_thr, gamma, tau, e_clip, critic_coef, bounds_coef, rew_scale = 3e-4, 0.008, 0.99, 0.95, 0.2, 2.0, 1e-4, 0.01
+    lr, kl_thr, gamma, tau, e_clip, critic_coef, bounds_coef, rew_scale = args.lr, 0.008, 0.99, 0.95, 0.2, args.critic_coef, 1e-4, 0.01
     opt = torch.optim.Adam(net.parameters(), lr=lr, eps=1e-8)
     obs = env.reset()["obs"].clone()
     ep_ret = torch.zeros(N, device=dev); ep_len = torch.zeros(N, device=dev)
@@ -131,7 +140,7 @@ def main():
             fadv = (fadv - fadv.mean()) / (fadv.std() + 1e-8)
             fon = obs_rms.norm(fo)
         kls = []
-        for _ in range(4):
+        for _ in range(args.mini_epochs):
             perm = torch.randperm(B, device=dev)
             for s in range(0, B, mb):
                 idx = perm[s:s + mb]
@@ -175,7 +184,8 @@ def main():
     summary = dict(task=args.task, num_envs=N, epochs=args.epochs, env_steps=env_steps, wall_s=wall, env_steps_per_s_incl_learner=env_steps / wall,
                    mean_step_reward_first10=sum(first) / len(first), mean_step_reward_last10=sum(lastr) / len(lastr),
                    best_mean_episode_return=max((r["mean_episode_return"] for r in log if r["episodes"] > 0), default=float("nan")),
-                   hyperparameters="cfg/train/AntPPO.yaml (a2c_continuous): lr 3e-4 adaptive kl 0.008, gamma 0.99, tau 0.95, horizon 16, minibatch 32768, 4 mini-epochs, e_clip 0.2")
+                   hyperparameters=f"a2c_continuous as cfg/train/{args.task}PPO.yaml: units {args.units}, lr {args.lr} adaptive kl 0.008, gamma 0.99, tau 0.95, horizon {args.horizon}, minibatch {args.minibatch}, {args.mini_epochs} mini-epochs, e_clip 0.2, critic_coef {args.critic_coef}",
+                   self_collision=bool(args.self_collision))
     print(json.dumps(summary), flush=True)
     if args.out:
         os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
