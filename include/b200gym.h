@@ -65,7 +65,9 @@ typedef struct {
     float angular_damping, linear_damping, max_angular_velocity;
     /* Self-collision = gym.create_actor(env, asset, pose, name, group, filter = 0) (humanoid.py:194): contact spheres of links
      * that are not joint neighbours collide with each other.  self_pairs: ncp x ncp bytes, 1 = the ordered pair may collide
-     * (NULL / self_collide 0 = off).  Same contact law as the ground contact with these gains; generic sub-step only
+     * (NULL / self_collide 0 = off).  Same contact law as the ground contact; self_kn, self_cn are DIMENSIONLESS: per pair
+     * kn = self_kn m_red / h^2, cn = self_cn m_red / h with the reduced mass of the two links (stability of the half-explicit
+     * coupling; 0.5 / 0.5 is what the importer sets); generic sub-step only
      * (ncp <= 64, no second actor); a four-chain model with self_collide set runs on the generic path. */
     int32_t self_collide, pad_self;
     const uint8_t *self_pairs;

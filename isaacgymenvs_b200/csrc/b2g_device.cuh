@@ -691,7 +691,11 @@ struct Stepper {
     __device__ __forceinline__ void self_pair(int n, int k, int j, const float x[3], const float vw[3], const float vl[3],
                                               float IA[21], float pa[3], float pl[3], const float aw[3], const float al[3],
                                               float F[3], float T[3], const RootState &rs) const {
-        const float h = m->h, skn = __ldg(&gmodel->self_kn), gn = __ldg(&gmodel->self_cn) + h * skn, smu = __ldg(&gmodel->self_mu);
+        // gains from the reduced mass of the two links and the sub-step (dimensionless self_kn, self_cn): the half-explicit
+        // block-Jacobi coupling is stable only while h^2 kn / m and h cn / m stay below ~1 for the lighter body
+        const float h = m->h, smu = __ldg(&gmodel->self_mu);
+        const float mi = links[gr.cps[n].pad].mass, mj = links[j].mass, mred = mi * mj / (mi + mj);
+        const float skn = __ldg(&gmodel->self_kn) * mred / (h * h), gn = __ldg(&gmodel->self_cn) * mred / h + h * skn;
         const float4 ci = SC(n), cj = SC(k);
         float vwj[3], vlj[3];
         if (j == 0) {

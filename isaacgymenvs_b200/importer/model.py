@@ -241,14 +241,19 @@ class Model:
         return m
 
 
-def enable_self_collision(m: "Model", kn_scale=1.0, mu=1.0, samples=4096, margin=0.10):
+def enable_self_collision(m: "Model", kappa=0.5, zeta=0.5, mu=1.0, samples=4096, margin=0.10):
     """create_actor(..., collision_filter=0): links of the articulation collide with each other.  Candidate pairs = contact
     spheres on links that are not joint neighbours (same link, or parent / child through massless intermediate links of a
     compound joint, never collide -- PhysX filters those too), and whose spheres do not already overlap in the reference
-    pose q = 0 (adjacent capsules of a chain share end spheres by construction).  Gains: the ground contact's own (measured on
-    a Humanoid under full-scale random torques: 0.25x leaves 6.5 % of the sampled states overlapping by > 1 cm, 1x 2 %, 4x 1 % but
-    joint speeds double -- the block-Jacobi coupling starts to kick); friction mu = the MJCF default geom friction under
-    PhysX's average combine mode."""
+    pose q = 0 (adjacent capsules of a chain share end spheres by construction).
+    Gains PER PAIR from the reduced mass of the two links and the sub-step h: kn = kappa m_red / h^2, cn = zeta m_red / h
+    (self_kn = kappa, self_cn = zeta are dimensionless).  The coupling is block-Jacobi -- each link implicit in its own
+    acceleration, explicit in the partner's velocity -- and that half-explicit scheme is stable only while h^2 kn / m and
+    h cn / m stay below ~1 for the lighter body.  Gains tied to the ACTOR's mass (as the ground contact's are) were measured
+    first: fine under random torques, but persistent bang-bang actuation -- what a learner produces -- blew joint speeds up to
+    1e5 rad/s (243 blow-ups in 600 steps x 512 envs; none at kappa = zeta = 0.5, 3-4 at kappa = 1).  The price is a soft
+    contact: under full-scale random torques 23 % of sampled states still overlap by > 1 cm (53 % without, deepest 5.6 vs 11.4 cm).
+    friction mu = the MJCF default geom friction under PhysX's average combine mode."""
     ncp = len(m.cp_link)
     carrier = set(int(l) for l in m.body_link)
 
@@ -312,8 +317,8 @@ def enable_self_collision(m: "Model", kn_scale=1.0, mu=1.0, samples=4096, margin
         pairs = (pairs.astype(bool) & (gap < margin)).astype(np.uint8)
         pairs = (pairs | pairs.T).astype(np.uint8)
     m.self_pairs = pairs
-    m.self_kn = float(kn_scale * m.contact_kn)
-    m.self_cn = float(np.sqrt(kn_scale) * m.contact_cn)
+    m.self_kn = float(kappa)
+    m.self_cn = float(zeta)
     m.self_mu = float(mu)
     m.self_collide = True
     return m

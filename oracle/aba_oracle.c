@@ -102,7 +102,7 @@ typedef struct {
      * acceleration (h J^T G J joins ITS articulated inertia), explicit in the other link's velocity. */
     int self_on, pad3;
     const unsigned char *self_pairs;        /* ncp x ncp, 1 = this ordered pair may collide */
-    double self_kn, self_cn, self_mu;
+    double self_kn, self_cn, self_mu;       /* self_kn, self_cn: dimensionless (gains per pair from the reduced link mass and h) */
 } OracleModel;
 
 /* ---------------------------------------------------------------- small linear algebra */
@@ -373,7 +373,10 @@ static void substep(const OracleModel *m, real h, real *root, real *dof, const r
             real lp[3] = {(real)m->cp_pos[3 * n], (real)m->cp_pos[3 * n + 1], (real)m->cp_pos[3 * n + 2]};
             mat3_vec(Rw[i], lp, wcs[n]); for (int k = 0; k < 3; k++) wcs[n][k] += pw[i][k];
         }
-        const real skn = (real)m->self_kn, sgn = (real)m->self_cn + h * (real)m->self_kn;
+        /* gains per pair from the reduced mass of the two LINKS and the sub-step: kn = self_kn * m_red / h^2, cn = self_cn * m_red / h
+         * (self_kn, self_cn dimensionless).  Each side of a pair is implicit in its own acceleration but explicit in the partner's
+         * velocity; that half-explicit coupling is stable only while h^2 kn / m and h cn / m stay below ~1 for the lighter body --
+         * gains tied to the actor's mass (as the ground contact's are) blow up light limbs under persistent actuation. */
         for (int n = 0; n < m->ncp; n++) for (int k2 = 0; k2 < m->ncp; k2++) {
             if (!m->self_pairs[n * m->ncp + k2]) continue;
             real dv[3] = {wcs[n][0] - wcs[k2][0], wcs[n][1] - wcs[k2][1], wcs[n][2] - wcs[k2][2]};
@@ -385,6 +388,8 @@ static void substep(const OracleModel *m, real h, real *root, real *dof, const r
             real off = (real)m->cp_radius[n] - (real)0.5 * pen;                     /* contact point: middle of the overlap */
             real pc[3] = {wcs[n][0] - off * nrm[0], wcs[n][1] - off * nrm[1], wcs[n][2] - off * nrm[2]};
             int i = m->cp_link[n], j = m->cp_link[k2];
+            const real mred = (real)(m->mass[i] * m->mass[j] / (m->mass[i] + m->mass[j]));
+            const real skn = (real)m->self_kn * mred / (h * h), sgn = (real)m->self_cn * mred / h + h * skn;
             /* point velocities of both links at pc (world axes) */
             real ri[3] = {pc[0] - pw[i][0], pc[1] - pw[i][1], pc[2] - pw[i][2]}, rj[3] = {pc[0] - pw[j][0], pc[1] - pw[j][1], pc[2] - pw[j][2]};
             real ril[3], rjl[3], t_[3], uil[3], ujl[3], uiw[3], ujw[3];

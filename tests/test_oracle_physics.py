@@ -307,14 +307,14 @@ def test_self_collision_pair_table():
     for a, b in (("right_thigh", "right_shin"), ("right_shin", "right_foot"), ("torso", "head"), ("torso", "lower_waist"),
                  ("lower_waist", "pelvis"), ("pelvis", "right_thigh"), ("torso", "right_upper_arm"), ("right_lower_arm", "right_hand")):
         assert (a, b) not in names and (b, a) not in names, (a, b)
-    assert m.self_kn == pytest.approx(m.contact_kn) and m.self_mu == 1.0
+    assert m.self_kn == 0.5 and m.self_cn == 0.5 and m.self_mu == 1.0         # dimensionless: gains per pair from m_red and h
 
 
 def test_self_collision_keeps_limbs_apart():
     """A Humanoid thrown around by full-scale random torques: without link-link contact half of the sampled states have
-    limbs inside each other by more than 1 cm (deepest > 10 cm); with it the share drops below 5 % and the deepest
-    overlap to a few cm (penalty contact: ~1000 N of actuator force against 82 kN/m), and the rollout stays finite and no
-    faster than the uncollided one."""
+    limbs inside each other by more than 1 cm (deepest > 10 cm); with it the share and the deepest overlap are cut by half
+    (a SOFT penalty contact: its gains are bounded by the stability of the half-explicit coupling, not by the actuators'
+    1000 N), and the rollout stays finite and no faster than the uncollided one."""
     res = {}
     for on in (False, True):
         m = _humanoid_self()
@@ -334,20 +334,53 @@ def test_self_collision_keeps_limbs_apart():
         assert np.isfinite(root).all() and np.isfinite(dof).all()
         res[on] = (hits / tot, worst, float(np.abs(dof[..., 1]).max()))
     assert res[False][0] > 0.3 and res[False][1] > 0.08, res
-    assert res[True][0] < 0.05 and res[True][1] < 0.06, res
-    assert res[True][2] < 2.0 * res[False][2], res
+    assert res[True][0] < 0.6 * res[False][0] and res[True][1] < 0.7 * res[False][1], res
+    assert res[True][2] < 1.5 * res[False][2], res
+
+
+def test_self_collision_is_stable_under_persistent_actuation():
+    """What a learner does, not what a random policy does: bang-bang actions held for 25 steps, 512 Humanoids, 600 steps with
+    resets on falling.  The first gain choice (the ground contact's, tied to the actor's mass) blew joint speeds up to 1e5
+    rad/s here (the block-Jacobi coupling is explicit in the partner's velocity); the per-pair gains from the reduced link
+    mass and the sub-step keep the speeds where they are without link-link contact."""
+    peak = {}
+    for on in (False, True):
+        m = _humanoid_self()
+        m.self_collide = on
+        orc = OracleSim(m, 0.0166, 2, G, threads=16)
+        n = 256
+        rng = np.random.default_rng(0)
+        root = np.zeros((n, 13)); root[:, 2] = 1.34; root[:, 6] = 1
+        dof = np.zeros((n, m.ndof, 2)); dof[..., 0] = rng.uniform(-0.2, 0.2, size=(n, m.ndof))
+        gear = np.asarray(m.actuator_gear)
+        act = rng.uniform(-1, 1, size=(n, m.ndof))
+        worst = 0.0
+        for k in range(400):
+            if k % 25 == 0:
+                flip = rng.random(n) < 0.5
+                act[flip] = np.sign(rng.uniform(-1, 1, size=(int(flip.sum()), m.ndof)))
+            orc.simulate(root, dof, act * gear[None])
+            assert np.isfinite(dof).all() and np.isfinite(root).all(), k
+            worst = max(worst, float(np.abs(dof[..., 1]).max()))
+            fallen = root[:, 2] < 0.6
+            root[fallen] = 0; root[fallen, 2] = 1.34; root[fallen, 6] = 1
+            dof[fallen] = 0; dof[fallen, :, 0] = rng.uniform(-0.2, 0.2, size=(int(fallen.sum()), m.ndof))
+        peak[on] = worst
+    assert peak[True] < 1.5 * peak[False] and peak[True] < 200.0, peak
 
 
 def test_self_contact_forces_are_equal_and_opposite():
     """One isolated contact between two limbs in free flight.  The two links compute their sides of the pair independently
     (block-Jacobi: each implicit in its OWN acceleration only: F_i = F0 - h G J a_i), so the forces reported for the two
-    bodies are exactly opposite only in the limit h -> 0.  Frictionless at h = 20 us they agree to 5 %; at the task's 8.3 ms,
+    bodies are exactly opposite only in the limit h -> 0 (the gains scale with 1 / h^2 and 1 / h, so the limit is taken with kn, cn FIXED at the task step's values).  Frictionless at h = 20 us they agree to 5 %; at the task's 8.3 ms,
     with friction, each side's force is reduced by its own response (the lighter limb's more) and only the directions still
     oppose -- the same documented property as the hand-object contact."""
     m = _humanoid_self()
     m.gravity_on = False
     m0 = _humanoid_self(); m0.gravity_on = False; m0.self_mu = 0.0
-    fine = OracleSim(m0, 0.00002, 1, (0.0, 0.0, 0.0))
+    h_task, h_fine = 0.0166 / 2, 0.00002
+    m0.self_kn *= (h_fine / h_task) ** 2; m0.self_cn *= h_fine / h_task          # the same kn, cn in N/m, N s/m as at the task step
+    fine = OracleSim(m0, h_fine, 1, (0.0, 0.0, 0.0))
     task = OracleSim(m, 0.0166, 2, (0.0, 0.0, 0.0))
     rng = np.random.default_rng(3)
     found, asym_task = 0, []
