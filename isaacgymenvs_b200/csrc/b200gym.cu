@@ -87,12 +87,24 @@ __device__ __forceinline__ Stepper<L, HF, BLOCK, OBJ, SELF> make_stepper(const D
     }
     st.lane = lane;
     st.gmodel = nullptr;
+    st.dr_mass = nullptr; st.dr_dof = nullptr;
     st.scen = nullptr; st.scs = 1;
     if (SELF) {
         if (sm->self_f4) st.scen = b2g_dyn_smem + (sm->ns * SLOT_F4 + sm->nacc * ACC_F4) * BLOCK + (threadIdx.x / L) * sm->self_f4;
         else { st.scen = b2g_dyn_smem + (sm->self_cell & 255) * SLOT_F4 * BLOCK + (threadIdx.x - lane + (sm->self_cell >> 8)); st.scs = BLOCK; }
     }
     return st;
+}
+
+// per-env physical parameters (domain randomisation arrays; null = the model's own), any sub-step
+template <class ST>
+__device__ __forceinline__ void attach_env_params_generic(ST &st, const DevModel &sm, const Buffers &B, int e) {
+    const float *ms = (const float *)B.p[B2G_T_ENV_MASS_SCALE];
+    const float4 *dp = (const float4 *)B.p[B2G_T_ENV_DOF_PROPS];
+    const float *envmu = (const float *)B.p[B2G_T_ENV_FRICTION];
+    if (ms) st.dr_mass = ms + (size_t)e * sm.nl;
+    if (dp) st.dr_dof = dp + (size_t)e * (sm.nl - 1);
+    if (envmu) st.gr.env_mu = 0.5f * (envmu[e] + sm.ground_mu);      // PhysX default combine mode: the average of the two materials
 }
 
 template <class ST>
@@ -123,6 +135,7 @@ __global__ void __launch_bounds__(BLOCK) simulate_kernel(const DevModel *__restr
     const int nd = sm.nl - 1, NS = sm.ns;
     ST st = make_stepper<L, HF, BLOCK, OBJ, SELF>(&sm, hf, lane);
     st.gmodel = gm;
+    attach_env_params_generic(st, sm, B, e);
     float *const root_row = (float *)B.p[B2G_T_ROOT_STATE] + 13 * (size_t)e * sm.root_stride;
     RootState rs; load_root(root_row, rs);
     ObjState ob;
@@ -231,6 +244,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? B2G_MINBLOCKS : (BLOCK 
     const int NS = sm.ns;
     ST st = make_stepper<L, HF, BLOCK, false, SELF>(&sm, hf, lane);
     st.gmodel = gm;
+    attach_env_params_generic(st, sm, B, e);
     {
         const char *pk = reinterpret_cast<const char *>(&sm) + offsetof(DevModel, slots) + (size_t)sm.ns * MAX_LANES * sizeof(SlotRec);
         st.links = reinterpret_cast<const LinkC *>(pk);
@@ -458,6 +472,7 @@ __global__ void __launch_bounds__(BLOCK) cartpole_step_kernel(const DevModel *__
     const int e = valid ? env : N - 1;
     ST st = make_stepper<1, false, BLOCK>(&sm, nullptr, 0);
     st.gmodel = gm;
+    attach_env_params_generic(st, sm, B, e);
     RootState rs; load_root((const float *)B.p[B2G_T_ROOT_STATE] + 13 * (size_t)e, rs);
     const float2 *dofs = (const float2 *)B.p[B2G_T_DOF_STATE] + (size_t)e * 2;
     const float a = fminf(fmaxf(actions_in[e], -P.clip_actions), P.clip_actions);
@@ -974,8 +989,6 @@ extern "C" int b2g_bind(b2g_sim *s, int32_t slot, void *ptr, size_t bytes) {
         default: need = 0; break;   // ACTIONS / OBS / OBS_CLIPPED are checked against the task in b2g_set_task
     }
     if (ptr && bytes < need) return fail(B2G_E_INVALID, "b2g_bind: buffer smaller than the tensor's layout requires");
-    if (ptr && (slot == B2G_T_ENV_MASS_SCALE || slot == B2G_T_ENV_DOF_PROPS) && !s->quad_ns)
-        return fail(B2G_E_UNSUPPORTED, "per-env link masses / joint properties are read by the four-chain (quad) kernels only (Ant, ANYmal)");
     s->buf.p[slot] = ptr; s->buf_bytes[slot] = bytes;
     return B2G_OK;
 }

@@ -31,8 +31,7 @@ __global__ void __launch_bounds__(BLOCK) anymal_physics_kernel(const DevModel *_
     const int nd = sm.nl - 1, NS = sm.ns;
     ST st = make_stepper<L, HF, BLOCK>(&sm, hf, lane);
     st.gmodel = gm;
-    const float *envmu = (const float *)B.p[B2G_T_ENV_FRICTION];
-    if (envmu) st.gr.env_mu = 0.5f * (envmu[e] + sm.ground_mu);
+    attach_env_params_generic(st, sm, B, e);
     RootState rs; load_root((const float *)B.p[B2G_T_ROOT_STATE] + 13 * (size_t)e, rs);
     const float2 *dofs = (const float2 *)B.p[B2G_T_DOF_STATE] + (size_t)e * nd;
     float *act_out = (float *)B.p[B2G_T_ACTIONS];

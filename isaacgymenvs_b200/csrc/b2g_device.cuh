@@ -553,6 +553,8 @@ struct Stepper {
     float4 *acc;              // this thread's column of the accumulator pool
     int lane;
     const DevModel *gmodel;   // the model's copy in global memory (self-collision tables), may be null when self_on == 0
+    const float *dr_mass;     // per-env physical parameters (vec_task.py:720-828 as arrays; null = the model's own): this env's link-mass
+    const float4 *dr_dof;     // factors [nl] (inertia scales with the mass), and per DOF (damping, stiffness, lower, upper)
     float4 *scen;             // this ENV's self-collision scratch, element i at scen[i * scs]: [0, ncp) sphere centres about O +
     int scs;                  // radius, [ncp].x hit count, [ncp + 1, ncp + 5) the overlapping pairs of this sub-step (SELF_HITS x uint16)
 
@@ -848,8 +850,10 @@ struct Stepper {
                     }
                     // joint force: explicit part + implicit diagonal (linear terms at the end of the sub-step)
                     const float qp = q + h * qd;
-                    float f = -lk.damping * qd - lk.stiffness * qp;
-                    float dg = lk.armature + h * lk.damping + h * h * lk.stiffness;
+                    float jd = lk.damping, jk = lk.stiffness, jlo = lk.lower, jhi = lk.upper;
+                    if (dr_dof) { const float4 v = dr_dof[sr.link - 1]; jd = v.x; jk = v.y; jlo = v.z; jhi = v.w; }
+                    float f = -jd * qd - jk * qp;
+                    float dg = lk.armature + h * jd + h * h * jk;
                     if (lk.flags & LF_POSDRIVE) {
                         float pd = lk.kp * (act - qp) - lk.kd * qd;
                         pd = fminf(fmaxf(pd, -lk.effort), lk.effort);
@@ -859,8 +863,8 @@ struct Stepper {
                     }
                     if (OBJ) f += k7in.w;
                     if (lk.flags & LF_LIMITED) {
-                        if (q < lk.lower) { f += lk.limit_k * (lk.lower - qp) - lk.limit_d * qd; dg += h * lk.limit_d + h * h * lk.limit_k; }
-                        else if (q > lk.upper) { f += lk.limit_k * (lk.upper - qp) - lk.limit_d * qd; dg += h * lk.limit_d + h * h * lk.limit_k; }
+                        if (q < jlo) { f += lk.limit_k * (jlo - qp) - lk.limit_d * qd; dg += h * lk.limit_d + h * h * lk.limit_k; }
+                        else if (q > jhi) { f += lk.limit_k * (jhi - qp) - lk.limit_d * qd; dg += h * lk.limit_d + h * h * lk.limit_k; }
                     }
                     S4(s, 0) = make_float4(Rc[0], Rc[1], Rc[2], Rc[3]);
                     S4(s, 1) = make_float4(Rc[4], Rc[5], Rc[6], Rc[7]);
@@ -1118,7 +1122,8 @@ struct Stepper {
                     load_pose(s, R, x, vw, vl);
                     load_axis(s, w, sl);
                     float I[21], qa[3], ql[3];
-                    link_inertia(lk, lk.mass, 1.f, R, x, vw, vl, g, I, qa, ql, m->ang_damp, m->lin_damp);
+                    const float msc = dr_mass ? dr_mass[sr.link] : 1.f;
+                    link_inertia(lk, lk.mass * msc, msc, R, x, vw, vl, g, I, qa, ql, m->ang_damp, m->lin_damp);
                     float dummy[3];
                     if (ground) link_contacts<true, HF>(m, gr, lk, rs.rp, R, x, vw, vl, I, qa, ql, dummy, dummy, dummy, dummy, 0, 1);
                     if (OBJ) obj_link_contacts<true>(lk, sr.link, R, x, vw, vl, I, qa, ql, dummy, dummy, dummy, dummy, 0, 1);
@@ -1206,7 +1211,8 @@ struct Stepper {
             float I[21], qa[3], ql[3], dummy[3], Rr[9], vwr[3], vlr[3];
             const float xr[3] = {0.f, 0.f, 0.f};
             root_pose(rs, Rr, vwr, vlr);
-            link_inertia(lk, mine ? lk.mass : 0.f, mine ? 1.f : 0.f, Rr, xr, vwr, vlr, g, I, qa, ql, m->ang_damp, m->lin_damp);
+            const float msc0 = dr_mass ? dr_mass[0] : 1.f;
+            link_inertia(lk, mine ? lk.mass * msc0 : 0.f, mine ? msc0 : 0.f, Rr, xr, vwr, vlr, g, I, qa, ql, m->ang_damp, m->lin_damp);
             if (ground) link_contacts<true, HF>(m, gr, lk, rs.rp, Rr, xr, vwr, vlr, I, qa, ql, dummy, dummy, dummy, dummy, lane, L);
             if (OBJ) obj_link_contacts<true>(lk, 0, Rr, xr, vwr, vlr, I, qa, ql, dummy, dummy, dummy, dummy, lane, L);
             if (SELF && m->self_on && mine) self_apply<true>(0, xr, vwr, vlr, I, qa, ql, dummy, dummy, dummy, dummy, rs);

@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(BLOCK) hand_step_kernel(const DevModel *__rest
     const bool w0 = valid && lane == 0;
     const int nd = sm.nl - 1, NS = sm.ns, NA = P.num_actions, O = P.num_obs;
     ST st = make_stepper<L, false, BLOCK, true>(&sm, nullptr, lane);
+    attach_env_params_generic(st, sm, B, e);                 // per-env link masses / joint properties / friction, when bound
 
     float *const rows = (float *)B.p[B2G_T_ROOT_STATE] + (size_t)e * 39;          // hand | object | goal marker
     const float *const init_rows = (const float *)B.p[B2G_T_INITIAL_ROOT] + (size_t)e * 39;

@@ -302,10 +302,11 @@ struct QLane {
                 // ---- joint force: explicit part + implicit diagonal (linear terms at the end of the sub-step)
                 float4 k10 = LK(s, 10), k11 = LK(s, 11);
                 const float4 k12 = LK(s, 12);
+                float mfac = 1.f;                                     // link-mass factor: mass AND rotational inertia (recomputeInertia, vec_task.py:773)
                 if (dr_dof || dr_mass) {                              // per-env joint properties / link mass (domain randomisation)
                     const int dof = q_f2i(LK(s, 16).w);
                     if (dr_dof) { k11 = dr_dof[dof]; k10.w = LK(s, 17).x + h * k11.x + h * h * k11.y; }
-                    if (dr_mass) k10.z *= dr_mass[dof + 1];
+                    if (dr_mass) { mfac = dr_mass[dof + 1]; k10.z *= mfac; }
                 }
                 {
                     const float qp = q[s] + h * qds;
@@ -329,11 +330,16 @@ struct QLane {
                 if (SP & 1) {
                     const float ul[3] = {k9.x, k9.y, k9.z};
                     float uw[3]; matvec(R, ul, uw);
-                    const float b0 = k10.x * uw[0], b1 = k10.x * uw[1], b2 = k10.x * uw[2];
-                    Icw[0] = k9.w + b0 * uw[0]; Icw[1] = k9.w + b1 * uw[1]; Icw[2] = k9.w + b2 * uw[2];
+                    const float bmf = k10.x * mfac, af = k9.w * mfac;
+                    const float b0 = bmf * uw[0], b1 = bmf * uw[1], b2 = bmf * uw[2];
+                    Icw[0] = af + b0 * uw[0]; Icw[1] = af + b1 * uw[1]; Icw[2] = af + b2 * uw[2];
                     Icw[3] = b0 * uw[1]; Icw[4] = b0 * uw[2]; Icw[5] = b1 * uw[2];
                 } else {
                     rotate_inertia(R, k9.x, k9.y, k9.z, k9.w, k10.x, k10.y, Icw);
+                    if (dr_mass) {
+#pragma unroll
+                        for (int c = 0; c < 6; c++) Icw[c] *= mfac;
+                    }
                 }
                 rigid_terms<FACC>(k10.z, Icw, c_, vw, vl, g, da, dl, I, qa, ql);
                 {
@@ -410,7 +416,7 @@ struct QLane {
                 // axisymmetric base with its COM at the origin: A = a 1 + bm (R u)(R u)^T, no first moment
                 const float ul[3] = {H5.x, H5.y, H5.z};
                 float uw[3]; matvec(Rr, ul, uw);
-                const float am = on * H5.w, bm = on * H6.x, mo = on * H4.w * msc;
+                const float am = on * H5.w * msc, bm = on * H6.x * msc, mo = on * H4.w * msc;
                 const float s_ = bm * dot3(uw, vw);
                 const float nO[3] = {am * vw[0] + s_ * uw[0], am * vw[1] + s_ * uw[1], am * vw[2] + s_ * uw[2]};     // A vw
                 float a3[3];
@@ -425,10 +431,9 @@ struct QLane {
                 // about the root origin directly: A = R Ab R^T, first moment hm = R (m com)
                 float Ab[6] = {H5.x, H5.y, H5.z, H5.w, H6.x, H6.y};
                 const float mass = H4.w * msc;
-                if (dr_mass) {                                        // Ab = Ic + m (c^2 1 - c c^T): the parallel-axis part follows the mass
-                    const float dm = mass - H4.w, c2 = H4.x * H4.x + H4.y * H4.y + H4.z * H4.z;
-                    Ab[0] += dm * (c2 - H4.x * H4.x); Ab[1] += dm * (c2 - H4.y * H4.y); Ab[2] += dm * (c2 - H4.z * H4.z);
-                    Ab[3] -= dm * H4.x * H4.y; Ab[4] -= dm * H4.x * H4.z; Ab[5] -= dm * H4.y * H4.z;
+                if (dr_mass) {                                        // Ab = Ic + m (c^2 1 - c c^T): both parts follow the mass factor
+#pragma unroll
+                    for (int c = 0; c < 6; c++) Ab[c] *= msc;
                 }
                 float A[6]; rotate_inertia(Rr, Ab[0], Ab[1], Ab[2], Ab[3], Ab[4], Ab[5], A);
                 const float cb[3] = {H4.x * mass, H4.y * mass, H4.z * mass};

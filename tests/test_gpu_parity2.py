@@ -356,11 +356,13 @@ np.savez(sys.argv[1], **out)
 
 
 # ------------------------------------------------------------------------------------ physical domain randomisation
-@pytest.mark.parametrize("name,zlo,zhi,tscale,dt,sub", [("ant", 0.15, 0.8, 15.0, 0.0166, 2), ("anymal", 0.3, 0.9, 40.0, 0.005, 1)])
+@pytest.mark.parametrize("name,zlo,zhi,tscale,dt,sub", [("ant", 0.15, 0.8, 15.0, 0.0166, 2), ("anymal", 0.3, 0.9, 40.0, 0.005, 1),
+                                                        ("humanoid", 0.9, 1.6, 60.0, 0.0166, 2)])
 def test_per_env_physical_parameters_match_oracle(name, zlo, zhi, tscale, dt, sub):
     """B2G_T_ENV_MASS_SCALE / ENV_DOF_PROPS / ENV_FRICTION (vec_task.py:720-828 as parameter arrays): groups of envs with
-    different link masses, joint damping / stiffness / limits and friction; each group equals the oracle run on a model
-    with those values baked in (group 0 has every mass doubled)."""
+    different link masses (the inertia follows: recomputeInertia, utils/dr_utils.py:62), joint damping / stiffness / limits and
+    friction; each group equals the oracle run on a model with those values baked in (group 0 has every mass doubled).  Ant and
+    ANYmal run on the four-chain kernels, the Humanoid on the generic sub-step."""
     from isaacgymenvs_b200 import engine
     from oracle.oracle import OracleSim
     base = copy.deepcopy(load_compiled(name))
@@ -375,7 +377,7 @@ def test_per_env_physical_parameters_match_oracle(name, zlo, zhi, tscale, dt, su
     dof = np.stack([lo0 + (hi0 - lo0) * rng.uniform(-0.05, 1.05, size=(n, nd)), rng.normal(size=(n, nd))], -1)
     tau = rng.uniform(-1, 1, size=(n, nd)) * tscale
     sim = engine.Sim(base, n, dt, sub, G, ground_mu=1.0)
-    assert sim.quad_ns() in (2, 3)
+    assert sim.quad_ns() == {"ant": 2, "anymal": 3, "humanoid": 0}[name]
     sim.acquire(engine.T_NET_CONTACT)
     dev = sim.device
     ms_t = sim._bind(engine.T_ENV_MASS_SCALE, torch.ones(n, nl, device=dev))
@@ -399,6 +401,7 @@ def test_per_env_physical_parameters_match_oracle(name, zlo, zhi, tscale, dt, su
         dp_t[sl] = torch.tensor(np.stack([dmp, stf, lo, hi], -1), device=dev)
         m = copy.deepcopy(base)
         m.mass = m.mass * ms.astype(np.float64)
+        m.inertia = np.asarray(m.inertia, float) * ms.astype(np.float64)[:, None]      # recomputeInertia=True (vec_task.py:773): the inertia follows the mass
         m.damping = np.concatenate([[0.0], dmp.astype(np.float64)]); m.stiffness = np.concatenate([[0.0], stf.astype(np.float64)])
         m.lower = np.concatenate([[0.0], np.where(lim, lo.astype(np.float64), base.lower[1:])])
         m.upper = np.concatenate([[0.0], np.where(lim, hi.astype(np.float64), base.upper[1:])])
@@ -411,19 +414,17 @@ def test_per_env_physical_parameters_match_oracle(name, zlo, zhi, tscale, dt, su
     rg = sim.root_state.cpu().numpy().astype(np.float64); dg = sim.dof_state.cpu().numpy().astype(np.float64).reshape(n, nd, 2)
     assert np.abs(rg[:, :7] - r64[:, :7]).max() < 2e-5
     dq = np.abs(dg[..., 0] - d64[..., 0])
-    assert dq.max() < 2e-4 and np.quantile(dq, 0.999) < 3e-5, (dq.max(), np.quantile(dq, 0.999))
+    assert dq.max() < (5e-4 if name == "humanoid" else 2e-4) and np.quantile(dq, 0.999) < 3e-5, (dq.max(), np.quantile(dq, 0.999))
     qerr = np.abs(dg[..., 1] - d64[..., 1]) / np.maximum(1.0, np.abs(d64[..., 1]))
     assert qerr.max() < 4e-3 and np.quantile(qerr, 0.999) < 1e-3, (qerr.max(), np.quantile(qerr, 0.999))
     cg = sim.tensors[engine.T_NET_CONTACT].cpu().numpy().reshape(n, base.nb, 3)
-    co = np.concatenate(cf, 0)
+    cb = np.concatenate(cf, 0)
+    co = np.zeros_like(cb); first = {}
+    for b in range(base.nb):                                   # the engine reports a link's contact force on the first body riding on it
+        first.setdefault(int(base.body_link[b]), b)
+        co[:, first[int(base.body_link[b])]] += cb[:, b]
     assert np.abs(cg - co).max() < 2e-3 * max(1.0, np.abs(co).max())
     sim.close()
-    # an articulation off the quad path refuses the arrays instead of ignoring them
-    hm = copy.deepcopy(load_compiled("humanoid")); hm.sensor_body = np.zeros(0, np.int32); hm.sensor_pos = np.zeros((0, 3)); hm.sensor_quat = np.zeros((0, 4))
-    s2 = engine.Sim(hm, 8, 0.0166, 2, G)
-    with pytest.raises(engine.EngineError):
-        s2._bind(engine.T_ENV_MASS_SCALE, torch.ones(8, hm.nl, device=s2.device))
-    s2.close()
 
 
 def test_reset_done_resets_at_the_call():

@@ -213,6 +213,7 @@ def test_quad_per_env_physical_parameters_match_oracle(name, zlo, zhi, tscale, d
     for sl, ms, dmp, stf, lo, hi, mu in groups:
         m = copy.deepcopy(base)
         m.mass = m.mass * ms.astype(np.float64)
+        m.inertia = np.asarray(m.inertia, float) * ms.astype(np.float64)[:, None]      # recomputeInertia=True (vec_task.py:773): the inertia follows the mass
         m.damping = np.concatenate([[0.0], dmp.astype(np.float64)]); m.stiffness = np.concatenate([[0.0], stf.astype(np.float64)])
         lim = base.limited[1:] > 0
         m.lower = np.concatenate([[0.0], np.where(lim, lo.astype(np.float64), base.lower[1:])])
