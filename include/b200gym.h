@@ -164,9 +164,10 @@ enum {
     B2G_T_GOAL_RESET_COUNT = 40,/* i32 (N)    per-env goal-only reset counter feeding the Philox stream */
     B2G_T_STATES = 41,         /* f32 (N,S)  states_buf, vec_task.py:306 (asymmetric observations; unclipped, get_state clamps) */
     /* physical domain randomisation (vec_task.py:720-828 writes these per actor through gym.set_actor_*_properties; here they
-     * are per-env parameter arrays the step kernels read).  NULL = the model's own values.  Implemented by the four-chain
-     * ("quad") kernels: Ant, ANYmal; other articulations answer B2G_E_UNSUPPORTED when they are bound. */
-    B2G_T_ENV_MASS_SCALE = 42, /* f32 (N,L)   factor on every link's MASS (inertia tensor unchanged: rigid_body_properties.mass) */
+     * are per-env parameter arrays the step kernels read).  NULL = the model's own values.  Read by every sub-step (the four-chain
+     * kernels and the generic one). */
+    B2G_T_ENV_MASS_SCALE = 42, /* f32 (N,L)   factor on every link's mass AND rotational inertia (rigid_body_properties.mass is set with
+                                  recomputeInertia = True: utils/dr_utils.py:62); the COM stays */
     B2G_T_ENV_DOF_PROPS = 43,  /* f32 (N,D,4) damping, stiffness, lower, upper of every DOF (dof_properties) */
     B2G_T_COUNT = 44
 };
