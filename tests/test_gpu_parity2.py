@@ -497,11 +497,14 @@ def test_rollout_equals_k_single_steps(n, K, ep_len):
     ok = ~off
     assert torch.equal(done[:, ok], torch.stack(ref_d)[:, ok]) and torch.equal(tout[:, ok], torch.stack(ref_t).bool()[:, ok])
     assert done.sum().item() > 0 or ep_len > K
-    assert (rew - torch.stack(ref_r)).abs()[:, ok].max().item() < 2e-4
-    for name in ("root_states", "dof_state", "potentials", "prev_potentials", "obs_buf", "rew_buf", "vec_sensor_tensor"):
+    # (derived quantities amplify what the observation scales down: the progress reward is a position difference / dt = x60,
+    # joint velocities enter the observation x0.2 -- hence the looser bounds on them for envs whose observations agree to 2e-4)
+    assert (rew - torch.stack(ref_r)).abs()[:, ok].max().item() < 2e-2
+    for name, tol in (("root_states", 2e-3), ("dof_state", 2e-3), ("potentials", 2e-2), ("prev_potentials", 2e-2), ("obs_buf", 2e-4),
+                      ("rew_buf", 2e-2), ("vec_sensor_tensor", 2e-2)):
         x, y = getattr(a_env, name), getattr(b_env, name)
         d = (x - y).abs().reshape(n, -1).amax(1)
-        assert d[ok].max().item() < 2e-4, name
+        assert d[ok].max().item() < tol, (name, d[ok].max().item())
     for name in ("progress_buf", "reset_buf", "reset_count"):
         assert torch.equal(getattr(a_env, name)[ok], getattr(b_env, name)[ok]), name
     # and the env keeps stepping normally afterwards
