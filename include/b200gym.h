@@ -169,7 +169,12 @@ enum {
     B2G_T_ENV_MASS_SCALE = 42, /* f32 (N,L)   factor on every link's mass AND rotational inertia (rigid_body_properties.mass is set with
                                   recomputeInertia = True: utils/dr_utils.py:62); the COM stays */
     B2G_T_ENV_DOF_PROPS = 43,  /* f32 (N,D,4) damping, stiffness, lower, upper of every DOF (dof_properties) */
-    B2G_T_COUNT = 44
+    /* gym.acquire_jacobian_tensor / acquire_mass_matrix_tensor (tasks/franka_cube_stack.py:388-392); shapes from b2g_kin_shape:
+     * nc = D for a fixed base, 6 + D for a floating base (base columns first: world linear, world angular velocity of the
+     * root origin); rows = B - 1 for a fixed base (no row for the base body), B otherwise */
+    B2G_T_JACOBIAN = 44,       /* f32 (N,rows,6,nc)  rows 0:3 linear, 3:6 angular velocity of the body-frame origin, world frame */
+    B2G_T_MASS_MATRIX = 45,    /* f32 (N,nc,nc)      joint-space inertia (composite rigid body) + armature on the diagonal */
+    B2G_T_COUNT = 46
 };
 
 /* fused per-task control steps */
@@ -271,6 +276,14 @@ int b2g_simulate(b2g_sim *sim, void *stream);
 /* gym.refresh_rigid_body_state_tensor(sim) (shadow_hand.py:443): forward kinematics into
  * RIGID_BODY_STATE. */
 int b2g_refresh_rigid_body_state(b2g_sim *sim, void *stream);
+
+/* gym.refresh_jacobian_tensors(sim) / gym.refresh_mass_matrix_tensors(sim) (tasks/franka_cube_stack.py:439-440): recompute
+ * JACOBIAN (which & 1) and / or MASS_MATRIX (which & 2) from ROOT_STATE and DOF_STATE -- one launch, one warp per env
+ * (csrc/b2g_kin.cuh).  b2g_kin_shape: shape_out = {rows, nc} of this sim's articulation (host only). */
+#define B2G_KIN_JACOBIAN 1
+#define B2G_KIN_MASS_MATRIX 2
+int b2g_kin_shape(const b2g_sim *sim, int32_t shape_out[2]);
+int b2g_refresh_kinematic_tensors(b2g_sim *sim, int32_t which, void *stream);
 
 /* One whole VecTask.step() (vec_task.py:360-408) for a fused task: clamp actions, pre_physics_step,
  * control_freq_inv x simulate, post_physics_step (progress, reset_idx, observations, reward),

@@ -405,6 +405,22 @@ class Gym:
     def acquire_net_contact_force_tensor(self, sim):
         return _Tensor(sim.engine.acquire(engine.T_NET_CONTACT))
 
+    # franka_cube_stack.py:388-392: `acquire_jacobian_tensor(sim, actor_name)`; one articulation per env here, so the name
+    # only has to be an actor that was created
+    def acquire_jacobian_tensor(self, sim, name):
+        return _Tensor(sim.engine.acquire(engine.T_JACOBIAN))
+
+    def acquire_mass_matrix_tensor(self, sim, name):
+        return _Tensor(sim.engine.acquire(engine.T_MASS_MATRIX))
+
+    def refresh_jacobian_tensors(self, sim):             # franka_cube_stack.py:439
+        sim.engine.refresh_kinematic_tensors(jacobian=True, mass_matrix=False)
+        return True
+
+    def refresh_mass_matrix_tensors(self, sim):          # franka_cube_stack.py:440
+        sim.engine.refresh_kinematic_tensors(jacobian=False, mass_matrix=True)
+        return True
+
     def refresh_actor_root_state_tensor(self, sim):      # written in place by simulate
         return True
 

@@ -12,6 +12,7 @@
 #include "b2g_device.cuh"
 #include "b2g_tasks.cuh"
 #include "b2g_common.cuh"
+#include "b2g_kin_host.h"
 
 using namespace b2g;
 
@@ -609,6 +610,9 @@ struct b2g_sim {
     int quad_spec = 0;                        // QLane specialisation flags the constants are packed for (b2g_quad.cuh)
     int quad_block = 64;                      // threads per CTA of the quad step kernels (B2G_QUAD_BLOCK: 32 / 64 / 128)
     float4 *d_qm = nullptr;
+    KinModel hk;                              // constant tables of the Jacobian / mass-matrix kernel (b2g_kin.cuh)
+    KinModel *d_kin = nullptr;
+    bool kin_ok = false;
     std::vector<const void *> smem_set;      // kernels whose dynamic shared-memory limit has been raised (once per sim)
     bool no_zero_copy = false;
 };
@@ -932,6 +936,11 @@ extern "C" int b2g_create_ext(const b2g_model *m, const b2g_model_ext *ext, cons
     }
     CUDA_TRY(cudaMalloc(&s->dm, sizeof(DevModel)));
     CUDA_TRY(cudaMemcpy(s->dm, &h, sizeof(DevModel), cudaMemcpyHostToDevice));
+    s->kin_ok = kin_build(m, h.root_stride, s->hk) == 0;
+    if (s->kin_ok) {
+        CUDA_TRY(cudaMalloc(&s->d_kin, sizeof(KinModel)));
+        CUDA_TRY(cudaMemcpy(s->d_kin, &s->hk, sizeof(KinModel), cudaMemcpyHostToDevice));
+    }
     {   // the specialised path of "four hinge chains on a free base" (Ant, ANYmal): b2g_quad.cuh
         const char *nq = getenv("B2G_NO_QUAD"), *qb = getenv("B2G_QUAD_BLOCK"), *nz = getenv("B2G_NO_ZERO_COPY");
         s->no_zero_copy = nz != nullptr;
@@ -959,6 +968,7 @@ extern "C" int b2g_destroy(b2g_sim *s) {
     if (s->d_hf) cudaFree(s->d_hf);
     if (s->d_actions_stage) cudaFree(s->d_actions_stage);
     if (s->d_qm) cudaFree(s->d_qm);
+    if (s->d_kin) cudaFree(s->d_kin);
     delete s;
     return B2G_OK;
 }
@@ -986,6 +996,8 @@ extern "C" int b2g_bind(b2g_sim *s, int32_t slot, void *ptr, size_t bytes) {
         case B2G_T_ENV_MASS_SCALE: need = (size_t)N * (nd + 1) * 4; break;
         case B2G_T_ENV_DOF_PROPS: need = (size_t)N * nd * 16; break;
         case B2G_T_ENV_FRICTION: need = (size_t)N * 4; break;
+        case B2G_T_JACOBIAN: need = (size_t)N * s->hk.rows * 6 * s->hk.nc * 4; break;
+        case B2G_T_MASS_MATRIX: need = (size_t)N * s->hk.nc * s->hk.nc * 4; break;
         default: need = 0; break;   // ACTIONS / OBS / OBS_CLIPPED are checked against the task in b2g_set_task
     }
     if (ptr && bytes < need) return fail(B2G_E_INVALID, "b2g_bind: buffer smaller than the tensor's layout requires");
@@ -1093,6 +1105,34 @@ extern "C" int b2g_refresh_rigid_body_state(b2g_sim *s, void *stream) {
     CUDA_TRY(cudaSetDevice(s->device));
     const int N = s->num_envs;
     body_state_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(s->dm, s->buf, N);
+    s->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return B2G_OK;
+}
+
+extern "C" int b2g_kin_shape(const b2g_sim *s, int32_t shape_out[2]) {
+    if (!s || !shape_out) return fail(B2G_E_INVALID, "b2g_kin_shape: null argument");
+    if (!s->kin_ok) return fail(B2G_E_UNSUPPORTED, "b2g_kin_shape: articulation exceeds the kernel's limits");
+    shape_out[0] = s->hk.rows; shape_out[1] = s->hk.nc;
+    return B2G_OK;
+}
+
+extern "C" int b2g_refresh_kinematic_tensors(b2g_sim *s, int32_t which, void *stream) {
+    if (!s) return fail(B2G_E_INVALID, "null sim");
+    if (!s->kin_ok) return fail(B2G_E_UNSUPPORTED, "b2g_refresh_kinematic_tensors: articulation exceeds the kernel's limits");
+    if (!(which & (B2G_KIN_JACOBIAN | B2G_KIN_MASS_MATRIX))) return fail(B2G_E_INVALID, "b2g_refresh_kinematic_tensors: nothing selected");
+    int rc = require(s, {B2G_T_ROOT_STATE, B2G_T_DOF_STATE}, "b2g_refresh_kinematic_tensors"); if (rc) return rc;
+    if (which & B2G_KIN_JACOBIAN) { rc = require(s, {B2G_T_JACOBIAN}, "b2g_refresh_kinematic_tensors"); if (rc) return rc; }
+    if (which & B2G_KIN_MASS_MATRIX) { rc = require(s, {B2G_T_MASS_MATRIX}, "b2g_refresh_kinematic_tensors"); if (rc) return rc; }
+    CUDA_TRY(cudaSetDevice(s->device));
+    const int N = s->num_envs;
+    constexpr int WARPS = 4;
+    // one warp per env; at most a few resident waves of CTAs, the warps stride over the envs
+    const int grid = std::min((N + WARPS - 1) / WARPS, 148 * 8);
+    kin_tensors_kernel<WARPS><<<grid, WARPS * 32, 0, (cudaStream_t)stream>>>(
+        s->d_kin, (const float *)s->buf.p[B2G_T_ROOT_STATE], (const float *)s->buf.p[B2G_T_DOF_STATE],
+        (which & B2G_KIN_JACOBIAN) ? (float *)s->buf.p[B2G_T_JACOBIAN] : nullptr,
+        (which & B2G_KIN_MASS_MATRIX) ? (float *)s->buf.p[B2G_T_MASS_MATRIX] : nullptr, N);
     s->launches++;
     CUDA_TRY(cudaGetLastError());
     return B2G_OK;

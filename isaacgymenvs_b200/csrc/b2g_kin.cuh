@@ -1,0 +1,289 @@
+// b2g_kin.cuh -- Jacobian and joint-space mass-matrix tensors (sm_100a).
+//
+// Stands behind gym.acquire_jacobian_tensor / acquire_mass_matrix_tensor + refresh_jacobian_tensors /
+// refresh_mass_matrix_tensors (reference call sites tasks/franka_cube_stack.py:388-392,439-440; consumer: the
+// operational-space controller :600-627, which reads the end effector's rows of J and the arm's block of M).
+//
+// Layouts (the closed binary defines them, the call sites fix the fixed-base case):
+//   J  (N, rows, 6, nc)   row = body (a fixed base has no row for its base body 0: `jacobian[:, joint_index]`),
+//                         6 = world linear velocity of the body-frame origin (3) | world angular velocity (3),
+//                         nc = nd joint columns, preceded for a FLOATING base by 6 base columns: world linear then
+//                         world angular velocity of the root origin (the order the root-state tensor carries them);
+//   M  (N, nc, nc)        composite-rigid-body inertia in the same coordinates, + joint armature on the diagonal.
+//
+// Formulation (differs on purpose from the oracle's body-coordinate CRBA with 6x6 Pluecker transforms): everything in
+// WORLD-ALIGNED axes about the root origin O.  There a rigid body's inertia is ten additive numbers -- the inertia tensor
+// about O (6), mass x COM offset (3), mass (1) -- so the composite inertia of a sub-tree is a plain sum over descendants,
+// and M[i][j] = S_j . (Ic_i S_i) needs no transforms at all.
+//
+// Work decomposition: ONE WARP PER ENVIRONMENT, lane = link (nl <= 32) for the kinematics / inertias, lane = body for the
+// body origins, lane = output column for the fills, so every global store is a contiguous run of one output row.  Lanes
+// exchange through a per-warp shared-memory scratch ordered by __syncwarp; every phase is a __host__ __device__ function
+// of (lane, tables, scratch), so tests/kin_host.cu runs the exact device arithmetic on the CPU against the fp64 oracle.
+#pragma once
+#include "b2g_device.cuh"
+
+namespace b2g {
+
+// constant tables of one articulation (built on the host by kin_build, b2g_kin_host.h)
+struct alignas(16) KinModel {
+    int nl, nb, nbase, nc;          // links, bodies, base columns (0 fixed / 6 floating), columns
+    int rows, row0;                 // Jacobian rows, first body with a row (1 for a fixed base)
+    int maxdepth, root_stride;      // tree depth; actors per env in the root-state tensor
+    int parent[MAX_LINKS], depth[MAX_LINKS], slide[MAX_LINKS], body_link[MAX_LINKS];
+    unsigned anc[MAX_LINKS];        // bit j set: link j (j >= 1) is link i itself or one of its ancestors
+    float R0[MAX_LINKS][9], lpos[MAX_LINKS][3], axis[MAX_LINKS][3], com[MAX_LINKS][3], Ic[MAX_LINKS][6];
+    float mass[MAX_LINKS], armature[MAX_LINKS], body_pos[MAX_LINKS][3];
+};
+
+// per-warp scratch; odd strides: lane-indexed accesses fall into different banks
+struct KinScratch {
+    float R[MAX_LINKS][9];          // link frame, world axes
+    float x[MAX_LINKS][3];          // link origin relative to the root origin O, world axes
+    float w[MAX_LINKS][3];          // joint axis, world axes
+    float sl[MAX_LINKS][3];         // hinge: velocity of the point at O per unit joint rate (x cross w); slide: unused
+    float in[MAX_LINKS][11];        // the link's own inertia about O: I (xx yy zz xy xz yz), m c (3), m
+    float nf[MAX_LINKS][7];         // Ic_i S_i: angular momentum about O (3), linear momentum (3)
+    float pb[MAX_LINKS][3];         // body-frame origins relative to O
+    float cb[11];                   // composite inertia of the whole articulation (base block of M)
+};
+
+// ---- phase 0: joint transform of link i in its parent's frame -> scratch (overwritten by the world frame in phase 1)
+B2G_HD void kin_local(int i, const KinModel &t, KinScratch &s, const float *root, float q) {
+    if (i == 0) {
+        const float rq[4] = {root[3], root[4], root[5], root[6]};
+        float R[9];
+        // plain normalisation (not the raw rsqrt of the step kernels: this is not a hot loop)
+        const float n = 1.0f / sqrtf(rq[0] * rq[0] + rq[1] * rq[1] + rq[2] * rq[2] + rq[3] * rq[3]);
+        const float x = rq[0] * n, y = rq[1] * n, z = rq[2] * n, w = rq[3] * n;
+        R[0] = 1.f - 2.f * (y * y + z * z); R[1] = 2.f * (x * y - z * w); R[2] = 2.f * (x * z + y * w);
+        R[3] = 2.f * (x * y + z * w); R[4] = 1.f - 2.f * (x * x + z * z); R[5] = 2.f * (y * z - x * w);
+        R[6] = 2.f * (x * z - y * w); R[7] = 2.f * (y * z + x * w); R[8] = 1.f - 2.f * (x * x + y * y);
+#pragma unroll
+        for (int c = 0; c < 9; c++) s.R[0][c] = R[c];
+        s.x[0][0] = s.x[0][1] = s.x[0][2] = 0.f;
+        return;
+    }
+    const float *R0 = t.R0[i], *ax = t.axis[i];
+    if (!t.slide[i]) {
+        float sn, cs; sincosf(q, &sn, &cs);
+        const float oc = 1.f - cs, ux = ax[0], uy = ax[1], uz = ax[2];
+        const float Rj[9] = {cs + ux * ux * oc, ux * uy * oc - uz * sn, ux * uz * oc + uy * sn,
+                             uy * ux * oc + uz * sn, cs + uy * uy * oc, uy * uz * oc - ux * sn,
+                             uz * ux * oc - uy * sn, uz * uy * oc + ux * sn, cs + uz * uz * oc};
+        float R[9]; matmul(R0, Rj, R);
+#pragma unroll
+        for (int c = 0; c < 9; c++) s.R[i][c] = R[c];
+#pragma unroll
+        for (int c = 0; c < 3; c++) s.x[i][c] = t.lpos[i][c];
+    } else {
+        float d[3]; matvec(R0, ax, d);
+#pragma unroll
+        for (int c = 0; c < 9; c++) s.R[i][c] = R0[c];
+#pragma unroll
+        for (int c = 0; c < 3; c++) s.x[i][c] = t.lpos[i][c] + d[c] * q;
+    }
+}
+
+// ---- phase 1 (once per tree level d = 1 .. maxdepth): compose with the parent's world frame
+B2G_HD void kin_level(int i, int d, const KinModel &t, KinScratch &s) {
+    if (i >= t.nl || t.depth[i] != d) return;
+    const int p = t.parent[i];
+    float Rp[9], Rl[9], R[9], r[3], wr[3];
+#pragma unroll
+    for (int c = 0; c < 9; c++) { Rp[c] = s.R[p][c]; Rl[c] = s.R[i][c]; }
+#pragma unroll
+    for (int c = 0; c < 3; c++) r[c] = s.x[i][c];
+    matmul(Rp, Rl, R); matvec(Rp, r, wr);
+#pragma unroll
+    for (int c = 0; c < 9; c++) s.R[i][c] = R[c];
+#pragma unroll
+    for (int c = 0; c < 3; c++) s.x[i][c] = s.x[p][c] + wr[c];
+}
+
+// ---- phase 2: world joint axis, motion subspace, the link's own inertia about O
+B2G_HD void kin_link(int i, const KinModel &t, KinScratch &s) {
+    float R[9], x[3], w[3] = {0.f, 0.f, 0.f}, sl[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < 9; c++) R[c] = s.R[i][c];
+#pragma unroll
+    for (int c = 0; c < 3; c++) x[c] = s.x[i][c];
+    if (i > 0) {
+        const float ax[3] = {t.axis[i][0], t.axis[i][1], t.axis[i][2]};
+        matvec(R, ax, w);
+        if (!t.slide[i]) cross(x, w, sl);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) { s.w[i][c] = w[c]; s.sl[i][c] = sl[c]; }
+    // inertia about the COM in world axes: R Ic R^T, then the parallel-axis term to O
+    const float *I6 = t.Ic[i];
+    const float Il[9] = {I6[0], I6[3], I6[4], I6[3], I6[1], I6[5], I6[4], I6[5], I6[2]};
+    float T[9], Rt[9] = {R[0], R[3], R[6], R[1], R[4], R[7], R[2], R[5], R[8]}, Iw[9];
+    matmul(R, Il, T); matmul(T, Rt, Iw);
+    const float lc[3] = {t.com[i][0], t.com[i][1], t.com[i][2]};
+    float c[3]; matvec(R, lc, c);
+#pragma unroll
+    for (int k = 0; k < 3; k++) c[k] += x[k];
+    const float m = t.mass[i], cc = dot3(c, c);
+    s.in[i][0] = Iw[0] + m * (cc - c[0] * c[0]);
+    s.in[i][1] = Iw[4] + m * (cc - c[1] * c[1]);
+    s.in[i][2] = Iw[8] + m * (cc - c[2] * c[2]);
+    s.in[i][3] = Iw[1] - m * c[0] * c[1];
+    s.in[i][4] = Iw[2] - m * c[0] * c[2];
+    s.in[i][5] = Iw[5] - m * c[1] * c[2];
+    s.in[i][6] = m * c[0]; s.in[i][7] = m * c[1]; s.in[i][8] = m * c[2];
+    s.in[i][9] = m;
+}
+
+// ---- phase 3: composite inertia of the sub-tree rooted at link i (sum over descendants), Ic_i S_i
+B2G_HD void kin_composite(int i, const KinModel &t, KinScratch &s) {
+    float a[10];
+#pragma unroll
+    for (int c = 0; c < 10; c++) a[c] = s.in[i][c];
+    for (int k = i + 1; k < t.nl; k++) {
+        const bool below = (i == 0) || ((t.anc[k] >> i) & 1u);
+        if (below) {
+#pragma unroll
+            for (int c = 0; c < 10; c++) a[c] += s.in[k][c];
+        }
+    }
+    if (i == 0) {
+#pragma unroll
+        for (int c = 0; c < 10; c++) s.cb[c] = a[c];
+        return;
+    }
+    const float w[3] = {s.w[i][0], s.w[i][1], s.w[i][2]}, mc[3] = {a[6], a[7], a[8]};
+    float n[3], f[3];
+    if (!t.slide[i]) {      // S = (w ; sl):  n = I_O w + mc x sl,  f = m sl - mc x w
+        const float sl[3] = {s.sl[i][0], s.sl[i][1], s.sl[i][2]};
+        float t1[3], t2[3];
+        cross(mc, sl, t1); cross(mc, w, t2);
+        n[0] = a[0] * w[0] + a[3] * w[1] + a[4] * w[2] + t1[0];
+        n[1] = a[3] * w[0] + a[1] * w[1] + a[5] * w[2] + t1[1];
+        n[2] = a[4] * w[0] + a[5] * w[1] + a[2] * w[2] + t1[2];
+#pragma unroll
+        for (int c = 0; c < 3; c++) f[c] = a[9] * sl[c] - t2[c];
+    } else {                // S = (0 ; w):   n = mc x w,  f = m w
+        cross(mc, w, n);
+#pragma unroll
+        for (int c = 0; c < 3; c++) f[c] = a[9] * w[c];
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) { s.nf[i][c] = n[c]; s.nf[i][3 + c] = f[c]; }
+}
+
+// ---- phase 2b: origin of body b's frame relative to O
+B2G_HD void kin_body(int b, const KinModel &t, KinScratch &s) {
+    const int l = t.body_link[b];
+    float R[9], o[3];
+#pragma unroll
+    for (int c = 0; c < 9; c++) R[c] = s.R[l][c];
+    const float bp[3] = {t.body_pos[b][0], t.body_pos[b][1], t.body_pos[b][2]};
+    matvec(R, bp, o);
+#pragma unroll
+    for (int c = 0; c < 3; c++) s.pb[b][c] = s.x[l][c] + o[c];
+}
+
+// element [r][k] of the cross-product matrix [p]x = [0 -pz py; pz 0 -px; -py px 0]
+B2G_HD float kin_skew_elem(const float *p, int r, int k) {
+    if (r == k) return 0.f;
+    const int o = 3 - r - k;                                // the remaining axis
+    return ((k - r + 3) % 3 == 1) ? -p[o] : p[o];
+}
+
+// ---- element (body b, component r, column c) of the Jacobian
+B2G_HD float kin_jac_elem(int b, int r, int c, const KinModel &t, const KinScratch &s) {
+    const float *pb = s.pb[b];
+    if (c < t.nbase) {      // v_b = v_0 + w_0 x (p_b - O) = v_0 - [p_b]x w_0
+        if (c < 3) return (r == c) ? 1.f : 0.f;
+        const int k = c - 3;
+        if (r >= 3) return (r - 3 == k) ? 1.f : 0.f;
+        return -kin_skew_elem(pb, r, k);
+    }
+    const int j = c - t.nbase + 1;
+    if (!((t.anc[t.body_link[b]] >> j) & 1u)) return 0.f;
+    const float *w = s.w[j];
+    if (t.slide[j]) return r < 3 ? w[r] : 0.f;
+    if (r >= 3) return w[r - 3];
+    const float d[3] = {pb[0] - s.x[j][0], pb[1] - s.x[j][1], pb[2] - s.x[j][2]};
+    const int r1 = (r + 1) % 3, r2 = (r + 2) % 3;
+    return w[r1] * d[r2] - w[r2] * d[r1];
+}
+
+// ---- element (a, c) of the mass matrix
+B2G_HD float kin_mass_elem(int a, int c, const KinModel &t, const KinScratch &s) {
+    const int nb = t.nbase;
+    if (a < nb && c < nb) {
+        const float *cb = s.cb;
+        if (a < 3 && c < 3) return a == c ? cb[9] : 0.f;
+        if (a >= 3 && c >= 3) {
+            const int i = a - 3, j = c - 3;
+            if (i == j) return cb[i];
+            return cb[2 + i + j];                           // (0,1) -> 3, (0,2) -> 4, (1,2) -> 5
+        }
+        // linear row i / angular column j:  p = w x (m c) = -[mc]x w  ->  -skew(mc)[i][j];  the transpose for (ang, lin)
+        const int i = a < 3 ? a : c, j = a < 3 ? c - 3 : a - 3;
+        return -kin_skew_elem(cb + 6, i, j);
+    }
+    if (a < nb || c < nb) {                                 // base row against joint column (symmetric)
+        const int k = a < nb ? a : c, i = (a < nb ? c : a) - nb + 1;
+        return k < 3 ? s.nf[i][3 + k] : s.nf[i][k - 3];
+    }
+    int i = a - nb + 1, j = c - nb + 1;
+    if (!((t.anc[i] >> j) & 1u)) {                          // j is not on i's path to the root: swap or zero
+        if (!((t.anc[j] >> i) & 1u)) return 0.f;
+        const int tmp = i; i = j; j = tmp;
+    }
+    const float *n = s.nf[i], *f = s.nf[i] + 3, *w = s.w[j];
+    float v;
+    if (t.slide[j]) v = w[0] * f[0] + w[1] * f[1] + w[2] * f[2];
+    else v = w[0] * n[0] + w[1] * n[1] + w[2] * n[2] + s.sl[j][0] * f[0] + s.sl[j][1] * f[1] + s.sl[j][2] * f[2];
+    return i == j ? v + t.armature[i] : v;
+}
+
+#ifdef __CUDACC__
+// One warp per env, grid-stride.  jac / mass may be null (only the other tensor is refreshed).
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) kin_tensors_kernel(const KinModel *__restrict__ gm, const float *__restrict__ g_root,
+                                                                 const float *__restrict__ g_dof, float *__restrict__ jac,
+                                                                 float *__restrict__ mass, int N) {
+    __shared__ KinModel t;
+    __shared__ KinScratch sc[WARPS];
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(gm);
+        uint4 *dst = reinterpret_cast<uint4 *>(&t);
+        for (int i = threadIdx.x; i < (int)(sizeof(KinModel) / 16); i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    KinScratch &s = sc[warp];
+    const int nl = t.nl, nd = nl - 1, nc = t.nc;
+    for (int e = blockIdx.x * WARPS + warp; e < N; e += gridDim.x * WARPS) {
+        const float *root = g_root + 13 * (size_t)e * t.root_stride;
+        const float2 *dof = reinterpret_cast<const float2 *>(g_dof) + (size_t)e * nd;
+        __syncwarp();                                        // the previous env's readers are done with the scratch
+        if (lane < nl) kin_local(lane, t, s, root, lane > 0 ? dof[lane - 1].x : 0.f);
+        for (int d = 1; d <= t.maxdepth; d++) { __syncwarp(); kin_level(lane, d, t, s); }
+        __syncwarp();
+        if (lane < nl) kin_link(lane, t, s);
+        if (jac && lane < t.nb) kin_body(lane, t, s);
+        __syncwarp();
+        if (mass) {
+            if (lane < nl) kin_composite(lane, t, s);
+            __syncwarp();
+            float *M = mass + (size_t)e * nc * nc;
+            for (int a = 0; a < nc; a++)
+                for (int c = lane; c < nc; c += 32) M[a * nc + c] = kin_mass_elem(a, c, t, s);
+        }
+        if (jac) {
+            float *J = jac + (size_t)e * t.rows * 6 * nc;
+            for (int br = 0; br < t.rows * 6; br++) {
+                const int b = t.row0 + br / 6, r = br % 6;
+                for (int c = lane; c < nc; c += 32) J[br * nc + c] = kin_jac_elem(b, r, c, t, s);
+            }
+        }
+    }
+}
+#endif
+
+}   // namespace b2g

@@ -22,7 +22,8 @@ MAXL = 32
  T_UP_VEC, T_HEADING_VEC, T_INITIAL_ROOT, T_RESET_COUNT, T_OBS_CLIPPED, T_COMMANDS, T_LAST_ACTIONS, T_LAST_DOF_VEL,
  T_FEET_AIR_TIME, T_TORQUES, T_EPISODE_SUMS, T_TERRAIN_LEVELS, T_TERRAIN_TYPES, T_ENV_ORIGINS, T_TERRAIN_ORIGINS,
  T_NOISE_SCALE, T_BASE_SCRATCH, T_REDUCE_SCRATCH, T_ENV_FRICTION, T_GOAL_STATES, T_PREV_TARGETS, T_SUCCESSES,
- T_CONSECUTIVE_SUCCESSES, T_RESET_GOAL, T_GOAL_RESET_COUNT, T_STATES, T_ENV_MASS_SCALE, T_ENV_DOF_PROPS) = range(44)
+ T_CONSECUTIVE_SUCCESSES, T_RESET_GOAL, T_GOAL_RESET_COUNT, T_STATES, T_ENV_MASS_SCALE, T_ENV_DOF_PROPS,
+ T_JACOBIAN, T_MASS_MATRIX) = range(46)
 TASK_NONE, TASK_CARTPOLE, TASK_ANT, TASK_HUMANOID, TASK_ANYMAL_TERRAIN, TASK_SHADOW_HAND = 0, 1, 2, 3, 4, 5
 HAND_OBS = {"openai": 0, "full_no_vel": 1, "full": 2, "full_state": 3}
 
@@ -159,14 +160,15 @@ def lib():
         _lib.b2g_launch_count.restype = C.c_int64
         _lib.b2g_launch_count.argtypes = [C.c_void_p]
         for fn in ("b2g_plan", "b2g_create", "b2g_create_ext", "b2g_destroy", "b2g_bind", "b2g_simulate", "b2g_refresh_rigid_body_state",
-                   "b2g_set_task", "b2g_set_anymal_task", "b2g_set_hand_task", "b2g_task_step", "b2g_task_step_host", "b2g_reset_flagged", "b2g_task_rollout"):
+                   "b2g_set_task", "b2g_set_anymal_task", "b2g_set_hand_task", "b2g_task_step", "b2g_task_step_host", "b2g_reset_flagged", "b2g_task_rollout",
+                   "b2g_kin_shape", "b2g_refresh_kinematic_tensors"):
             getattr(_lib, fn).restype = C.c_int
     return _lib
 
 
 EXPORTS = ("b2g_plan", "b2g_create", "b2g_create_ext", "b2g_destroy", "b2g_bind", "b2g_simulate", "b2g_refresh_rigid_body_state", "b2g_set_task",
            "b2g_set_anymal_task", "b2g_set_hand_task", "b2g_task_step", "b2g_task_step_host", "b2g_launch_count", "b2g_last_error", "b2g_version",
-           "b2g_quad_chain_length", "b2g_reset_flagged", "b2g_task_rollout")
+           "b2g_quad_chain_length", "b2g_reset_flagged", "b2g_task_rollout", "b2g_kin_shape", "b2g_refresh_kinematic_tensors")
 
 
 class EngineError(RuntimeError):
@@ -304,6 +306,10 @@ class Sim:
         if slot in self.tensors:
             return self.tensors[slot]
         N = self.num_envs
+        if slot in (T_JACOBIAN, T_MASS_MATRIX):
+            rows, nc = self.kin_shape()
+            shape = (N, rows, 6, nc) if slot == T_JACOBIAN else (N, nc, nc)
+            return self._bind(slot, torch.zeros(*shape, dtype=torch.float32, device=self.device))
         shape = {T_RIGID_BODY_STATE: (N * (self.nb + self.actors_per_env - 1), 13), T_FORCE_SENSOR: (N * max(self.ns, 1), 6),
                  T_DOF_FORCE: (N * max(self.nd, 1),), T_NET_CONTACT: (N * self.nb, 3)}[slot]
         return self._bind(slot, torch.zeros(*shape, dtype=torch.float32, device=self.device))
@@ -316,6 +322,24 @@ class Sim:
         self.acquire(T_RIGID_BODY_STATE)
         _check(lib().b2g_refresh_rigid_body_state(self._h, self._stream()), "b2g_refresh_rigid_body_state")
         return self.tensors[T_RIGID_BODY_STATE]
+
+    def kin_shape(self):
+        """(rows, columns) of the Jacobian tensor: a fixed base has no row for its base body and no base columns; a floating
+        base has six leading columns (world linear, world angular velocity of the root origin)."""
+        out = (C.c_int32 * 2)()
+        lib().b2g_kin_shape.argtypes = [C.c_void_p, C.c_void_p]
+        _check(lib().b2g_kin_shape(self._h, out), "b2g_kin_shape")
+        return int(out[0]), int(out[1])
+
+    def refresh_kinematic_tensors(self, jacobian=True, mass_matrix=True):
+        """gym.refresh_jacobian_tensors / refresh_mass_matrix_tensors (franka_cube_stack.py:439-440), one launch for both."""
+        which = 0
+        if jacobian:
+            self.acquire(T_JACOBIAN); which |= 1
+        if mass_matrix:
+            self.acquire(T_MASS_MATRIX); which |= 2
+        _check(lib().b2g_refresh_kinematic_tensors(self._h, C.c_int32(which), self._stream()), "b2g_refresh_kinematic_tensors")
+        return self.tensors.get(T_JACOBIAN), self.tensors.get(T_MASS_MATRIX)
 
     # ---- fused task step
     def set_task(self, params: CTaskParams, buffers: dict):

@@ -800,3 +800,135 @@ void oracle_forward_dynamics(const OracleModel *m, const real *root_in, const re
     for (int i = 0; i < nd; i++) qdd[i] = (d[2 * i + 1] - dof_in[2 * i + 1]) / h;
     memcpy(root_after, r, sizeof(r)); memcpy(dof_after, d, sizeof(real) * 2 * nd);
 }
+
+/* ------------------------------------------------------------------ kinematic / inertial tensors
+ * gym.acquire_jacobian_tensor / acquire_mass_matrix_tensor + refresh_* (tasks/franka_cube_stack.py:388-392,439-440
+ * in the reference: the operational-space controller reads the end effector's rows of J and the arm's block of M).
+ * The closed binary defines the layouts; what the call sites fix is: J[env, body row, 0:3 linear | 3:6 angular, dof
+ * column] in the world frame, a fixed-base articulation has no row for its base link and no base columns
+ * (`jacobian[:, hand_joint_index, :, :7]` indexes by JOINT), M[env, dof, dof].  For a floating base we put the six base
+ * coordinates FIRST -- world linear velocity of the root origin, then world angular velocity, the way the root-state
+ * tensor carries them -- so J is (nb, 6, 6 + nd) and M is (6 + nd, 6 + nd).  [layout for floating bases unverifiable
+ * here; written down in DESIGN.md]
+ *   J maps generalised velocities to the twist of each BODY-frame origin (what rigid_body_state reports);
+ *   M is the joint-space inertia (composite-rigid-body algorithm, body coordinates -- Featherstone 2008 table 6.2
+ *   extended with the floating base, section 9.4) plus the joint armature on the diagonal.  The implicit-integration
+ *   terms of the sub-step (h b + h^2 k ...) are NOT part of M. */
+static void kin_tree(const OracleModel *m, const real *root, const real *dof, real Rw[][9], real pw[][3], real aw[][3],
+                     real Xup[][36], real S[][6]) {
+    const int nl = m->nl;
+    quat_to_mat(root + 3, Rw[0]);
+    for (int k = 0; k < 3; k++) { pw[0][k] = root[k]; aw[0][k] = 0; }
+    for (int i = 1; i < nl; i++) {
+        int p = m->parent[i];
+        real q = dof[2 * (i - 1)];
+        real Rl[9], Rj[9], R[9], r[3], ax[3] = {(real)m->axis[3 * i], (real)m->axis[3 * i + 1], (real)m->axis[3 * i + 2]};
+        real lq[4] = {(real)m->lquat[4 * i], (real)m->lquat[4 * i + 1], (real)m->lquat[4 * i + 2], (real)m->lquat[4 * i + 3]};
+        quat_to_mat(lq, Rl);
+        for (int k = 0; k < 3; k++) r[k] = (real)m->lpos[3 * i + k];
+        for (int k = 0; k < 6; k++) S[i][k] = 0;
+        if (m->jtype[i] == 0) { axis_angle_mat(ax, q, Rj); mat3_mul(Rl, Rj, R); for (int k = 0; k < 3; k++) S[i][k] = ax[k]; }
+        else { memcpy(R, Rl, sizeof(R)); real d[3]; mat3_vec(Rl, ax, d); for (int k = 0; k < 3; k++) { r[k] += d[k] * q; S[i][3 + k] = ax[k]; } }
+        xform_motion(R, r, Xup[i]);
+        mat3_mul(Rw[p], R, Rw[i]);
+        real wr[3]; mat3_vec(Rw[p], r, wr);
+        for (int k = 0; k < 3; k++) pw[i][k] = pw[p][k] + wr[k];
+        mat3_vec(Rw[i], ax, aw[i]);             /* joint axis in world axes (the joint rotation leaves it fixed) */
+    }
+}
+
+/* jac: (nrows, 6, ncols) with nrows = nb (floating) or nb - 1 (fixed: every body but the base body 0), in body order;
+ * ncols = nd (+ 6 base columns first when floating).  Returns nrows. */
+static int jacobian_env(const OracleModel *m, const real *root, const real *dof, real *jac) {
+    const int nl = m->nl, nd = nl - 1, nbase = m->root_fixed ? 0 : 6, nc = nd + nbase;
+    static __thread real Rw[MAXL][9], pw[MAXL][3], aw[MAXL][3], Xup[MAXL][36], S[MAXL][6];
+    kin_tree(m, root, dof, Rw, pw, aw, Xup, S);
+    int row = 0;
+    for (int b = 0; b < m->nb; b++) {
+        const int l = m->body_link[b];
+        if (m->root_fixed && b == 0) continue;         /* a fixed base: no row for the base body (PhysX: num_links - 1 rows) */
+        real bp[3] = {(real)m->body_pos[3 * b], (real)m->body_pos[3 * b + 1], (real)m->body_pos[3 * b + 2]}, wb[3], pb[3];
+        mat3_vec(Rw[l], bp, wb);
+        for (int k = 0; k < 3; k++) pb[k] = pw[l][k] + wb[k];
+        real *J = jac + (size_t)row * 6 * nc;
+        memset(J, 0, sizeof(real) * 6 * nc);
+        if (nbase) {
+            real r[3] = {pb[0] - pw[0][0], pb[1] - pw[0][1], pb[2] - pw[0][2]}, K[9];
+            skew(r, K);                                   /* v_b = v_0 + w_0 x r = v_0 - [r]x w_0 */
+            for (int k = 0; k < 3; k++) {
+                J[k * nc + k] = 1; J[(3 + k) * nc + 3 + k] = 1;
+                for (int c = 0; c < 3; c++) J[k * nc + 3 + c] = -K[3 * k + c];
+            }
+        }
+        for (int j = l; j > 0; j = m->parent[j]) {         /* the joints between the base and this body's link */
+            const int col = nbase + j - 1;
+            if (m->jtype[j] == 0) {
+                real r[3] = {pb[0] - pw[j][0], pb[1] - pw[j][1], pb[2] - pw[j][2]}, lin[3];
+                cross3(aw[j], r, lin);
+                for (int k = 0; k < 3; k++) { J[k * nc + col] = lin[k]; J[(3 + k) * nc + col] = aw[j][k]; }
+            } else for (int k = 0; k < 3; k++) J[k * nc + col] = aw[j][k];
+        }
+        row++;
+    }
+    return row;
+}
+
+static void mat6T_mat6_mat6(const real X[36], const real I[36], real out[36]) {   /* X^T I X */
+    real t[36];
+    for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) { real s = 0; for (int k = 0; k < 6; k++) s += I[6 * i + k] * X[6 * k + j]; t[6 * i + j] = s; }
+    for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) { real s = 0; for (int k = 0; k < 6; k++) s += X[6 * k + i] * t[6 * k + j]; out[6 * i + j] = s; }
+}
+
+/* M: (nc, nc), nc = nd (+ 6 when floating: base coordinates first, world linear then world angular) */
+static void mass_matrix_env(const OracleModel *m, const real *root, const real *dof, real *M) {
+    const int nl = m->nl, nd = nl - 1, nbase = m->root_fixed ? 0 : 6, nc = nd + nbase;
+    static __thread real Rw[MAXL][9], pw[MAXL][3], aw[MAXL][3], Xup[MAXL][36], S[MAXL][6], Ic[MAXL][36];
+    kin_tree(m, root, dof, Rw, pw, aw, Xup, S);
+    for (int i = 0; i < nl; i++) {
+        real cm[3] = {(real)m->com[3 * i], (real)m->com[3 * i + 1], (real)m->com[3 * i + 2]}, I6[6];
+        for (int k = 0; k < 6; k++) I6[k] = (real)m->inertia[6 * i + k];
+        spatial_inertia((real)m->mass[i], cm, I6, Ic[i]);
+    }
+    for (int i = nl - 1; i > 0; i--) {
+        real t[36]; mat6T_mat6_mat6(Xup[i], Ic[i], t);
+        for (int k = 0; k < 36; k++) Ic[m->parent[i]][k] += t[k];
+    }
+    memset(M, 0, sizeof(real) * nc * nc);
+    /* base coordinates u = (v world, w world); base-link spatial velocity [w_b; v_b] = T u, T = [0 R^T; R^T 0] */
+    real T[36]; memset(T, 0, sizeof(T));
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { T[6 * i + 3 + j] = Rw[0][3 * j + i]; T[6 * (3 + i) + j] = Rw[0][3 * j + i]; }
+    if (nbase) {
+        real B[36]; mat6T_mat6_mat6(T, Ic[0], B);
+        for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) M[i * nc + j] = B[6 * i + j];
+    }
+    for (int i = 1; i < nl; i++) {
+        real F[6]; mat6_vec(Ic[i], S[i], F);
+        real d = 0; for (int k = 0; k < 6; k++) d += S[i][k] * F[k];
+        M[(nbase + i - 1) * nc + nbase + i - 1] = d + (real)m->armature[i];
+        int j = i;
+        while (m->parent[j] > 0) {
+            real G[6]; mat6T_vec(Xup[j], F, G); memcpy(F, G, sizeof(F));
+            j = m->parent[j];
+            real s = 0; for (int k = 0; k < 6; k++) s += S[j][k] * F[k];
+            M[(nbase + i - 1) * nc + nbase + j - 1] = s; M[(nbase + j - 1) * nc + nbase + i - 1] = s;
+        }
+        if (nbase) {
+            real G[6], Fb[6]; mat6T_vec(Xup[j], F, G);       /* now in base-link coordinates */
+            mat6T_vec(T, G, Fb);
+            for (int k = 0; k < 6; k++) { M[k * nc + nbase + i - 1] = Fb[k]; M[(nbase + i - 1) * nc + k] = Fb[k]; }
+        }
+    }
+}
+
+int oracle_jacobian_rows(const OracleModel *m) {
+    int rows = 0;
+    return m->root_fixed ? m->nb - 1 : m->nb;
+}
+void oracle_jacobian(const OracleModel *m, int nenv, const real *root, const real *dof, real *jac) {
+    const int nd = m->nl - 1, nc = nd + (m->root_fixed ? 0 : 6), rows = oracle_jacobian_rows(m);
+    for (int e = 0; e < nenv; e++) jacobian_env(m, root + 13 * e, dof + 2 * nd * e, jac + (size_t)e * rows * 6 * nc);
+}
+void oracle_mass_matrix(const OracleModel *m, int nenv, const real *root, const real *dof, real *M) {
+    const int nd = m->nl - 1, nc = nd + (m->root_fixed ? 0 : 6);
+    for (int e = 0; e < nenv; e++) mass_matrix_env(m, root + 13 * e, dof + 2 * nd * e, M + (size_t)e * nc * nc);
+}

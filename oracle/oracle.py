@@ -158,3 +158,27 @@ class OracleSim:
                                          C.c_void_p(tau.ctypes.data), C.c_void_p(qdd.ctypes.data),
                                          C.c_void_p(ra.ctypes.data), C.c_void_p(da.ctypes.data))
         return qdd[:self.nd], ra, da
+
+    # ---- gym.acquire_jacobian_tensor / acquire_mass_matrix_tensor (franka_cube_stack.py:388-392)
+    def jacobian_shape(self):
+        """(body rows, 6, columns): a fixed base has no row for the base body and no base columns; a floating
+        base has six leading columns (world linear, world angular velocity of the root origin)."""
+        rows = int(self.lib.oracle_jacobian_rows(C.byref(self.cm)))
+        return rows, 6, self.nd + (0 if self.cm.root_fixed else 6)
+
+    def jacobian(self, root, dof):
+        N = root.shape[0]
+        root = np.ascontiguousarray(root, self.dtype); dof = np.ascontiguousarray(dof, self.dtype)
+        J = np.zeros((N,) + self.jacobian_shape(), self.dtype)
+        self.lib.oracle_jacobian(C.byref(self.cm), C.c_int(N), C.c_void_p(root.ctypes.data), C.c_void_p(dof.ctypes.data),
+                                 C.c_void_p(J.ctypes.data))
+        return J
+
+    def mass_matrix(self, root, dof):
+        N = root.shape[0]
+        root = np.ascontiguousarray(root, self.dtype); dof = np.ascontiguousarray(dof, self.dtype)
+        nc = self.nd + (0 if self.cm.root_fixed else 6)
+        M = np.zeros((N, nc, nc), self.dtype)
+        self.lib.oracle_mass_matrix(C.byref(self.cm), C.c_int(N), C.c_void_p(root.ctypes.data), C.c_void_p(dof.ctypes.data),
+                                    C.c_void_p(M.ctypes.data))
+        return M
