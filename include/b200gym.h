@@ -174,7 +174,13 @@ enum {
      * root origin); rows = B - 1 for a fixed base (no row for the base body), B otherwise */
     B2G_T_JACOBIAN = 44,       /* f32 (N,rows,6,nc)  rows 0:3 linear, 3:6 angular velocity of the body-frame origin, world frame */
     B2G_T_MASS_MATRIX = 45,    /* f32 (N,nc,nc)      joint-space inertia (composite rigid body) + armature on the diagonal */
-    B2G_T_COUNT = 46
+    /* gym.apply_rigid_body_force_tensors(sim, forces, None, LOCAL_SPACE) for the free object (shadow_hand.py:700-709,
+     * forceScale > 0): a force at the object's COM in the OBJECT's frame, held over the simulate calls of a step.  The fused
+     * ShadowHand step owns both tensors (decay, redraw with probability RANDOM_FORCE_PROB, zero + redraw the probability on
+     * reset); b2g_simulate only reads OBJ_FORCE.  NULL = no force. */
+    B2G_T_OBJ_FORCE = 46,      /* f32 (N,3) */
+    B2G_T_RANDOM_FORCE_PROB = 47, /* f32 (N)   random_force_prob, shadow_hand.py:198,642 */
+    B2G_T_COUNT = 48
 };
 
 /* fused per-task control steps */
@@ -253,6 +259,10 @@ typedef struct {
     int32_t num_states;                                        /* 0, or the full_state size: states_buf is filled too (asymmetric_obs, :457-458) */
     uint64_t seed;
     int32_t env_id_offset, pad1;
+    /* random forces on the object (shadow_hand.py:69-72,196-201,700-709); force_scale 0 = off.  force_decay_factor =
+     * forceDecay ^ (dt / forceDecayInterval); a new force N(0,1)^3 * object mass * force_scale is drawn when U < random_force_prob,
+     * random_force_prob = exp(force_logp_span * U' + force_logp1) redrawn on reset (force_logp_span = log p0 - log p1) */
+    float force_scale, force_decay_factor, force_logp_span, force_logp1;
 } b2g_hand_params;
 
 typedef struct b2g_sim b2g_sim;

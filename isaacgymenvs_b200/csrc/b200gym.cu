@@ -90,6 +90,7 @@ __device__ __forceinline__ Stepper<L, HF, BLOCK, OBJ, SELF> make_stepper(const D
     st.gmodel = nullptr;
     st.dr_mass = nullptr; st.dr_dof = nullptr;
     st.scen = nullptr; st.scs = 1;
+    st.obj_fext[0] = st.obj_fext[1] = st.obj_fext[2] = 0.f;
     if (SELF) {
         if (sm->self_f4) st.scen = b2g_dyn_smem + (sm->ns * SLOT_F4 + sm->nacc * ACC_F4) * BLOCK + (threadIdx.x / L) * sm->self_f4;
         else { st.scen = b2g_dyn_smem + (sm->self_cell & 255) * SLOT_F4 * BLOCK + (threadIdx.x - lane + (sm->self_cell >> 8)); st.scs = BLOCK; }
@@ -140,7 +141,10 @@ __global__ void __launch_bounds__(BLOCK) simulate_kernel(const DevModel *__restr
     float *const root_row = (float *)B.p[B2G_T_ROOT_STATE] + 13 * (size_t)e * sm.root_stride;
     RootState rs; load_root(root_row, rs);
     ObjState ob;
-    if (OBJ) load_obj(root_row + 13 * sm.obj_row, ob);
+    if (OBJ) {
+        load_obj(root_row + 13 * sm.obj_row, ob);
+        if (const float *of = (const float *)B.p[B2G_T_OBJ_FORCE]) { st.obj_fext[0] = of[3 * (size_t)e]; st.obj_fext[1] = of[3 * (size_t)e + 1]; st.obj_fext[2] = of[3 * (size_t)e + 2]; }
+    }
     const float2 *d = (const float2 *)B.p[B2G_T_DOF_STATE] + (size_t)e * nd;
     const float *act = (const float *)B.p[B2G_T_DOF_ACTUATION];
     const float *tgt = (const float *)B.p[B2G_T_DOF_TARGET];
@@ -996,6 +1000,8 @@ extern "C" int b2g_bind(b2g_sim *s, int32_t slot, void *ptr, size_t bytes) {
         case B2G_T_ENV_MASS_SCALE: need = (size_t)N * (nd + 1) * 4; break;
         case B2G_T_ENV_DOF_PROPS: need = (size_t)N * nd * 16; break;
         case B2G_T_ENV_FRICTION: need = (size_t)N * 4; break;
+        case B2G_T_OBJ_FORCE: need = (size_t)N * 12; break;
+        case B2G_T_RANDOM_FORCE_PROB: need = (size_t)N * 4; break;
         case B2G_T_JACOBIAN: need = (size_t)N * s->hk.rows * 6 * s->hk.nc * 4; break;
         case B2G_T_MASS_MATRIX: need = (size_t)N * s->hk.nc * s->hk.nc * 4; break;
         default: need = 0; break;   // ACTIONS / OBS / OBS_CLIPPED are checked against the task in b2g_set_task
@@ -1234,6 +1240,7 @@ static int hand_step(b2g_sim *s, const float *actions, void *stream) {
         rc = require(s, {B2G_T_STATES}, "b2g_task_step(ShadowHand, asymmetric observations)"); if (rc) return rc;
         if (s->buf_bytes[B2G_T_STATES] < (size_t)s->num_envs * s->hand_dev.num_states * 4) return fail(B2G_E_INVALID, "STATES buffer too small");
     }
+    if (P.force_scale > 0.f) { rc = require(s, {B2G_T_OBJ_FORCE, B2G_T_RANDOM_FORCE_PROB}, "b2g_task_step(ShadowHand, forceScale > 0)"); if (rc) return rc; }
     const size_t N = s->num_envs;
     if (s->buf_bytes[B2G_T_OBS] < N * P.num_obs * 4) return fail(B2G_E_INVALID, "OBS buffer too small");
     CUDA_TRY(cudaSetDevice(s->device));
@@ -1503,6 +1510,7 @@ extern "C" int b2g_reset_flagged(b2g_sim *s, void *stream) {
         anymal_reset_obs_kernel<32, 128><<<(N * 32 + 127) / 128, 128, 0, st>>>(s->buf, s->anymal, s->d_hf, N, nd, 0, s->step_counter, 1);
     } else if (s->has_hand) {
         rc = require(s, {B2G_T_INITIAL_ROOT, B2G_T_GOAL_STATES, B2G_T_DOF_TARGET, B2G_T_PREV_TARGETS, B2G_T_SUCCESSES, B2G_T_RESET_GOAL}, "b2g_reset_flagged(ShadowHand)"); if (rc) return rc;
+        if (s->hand.force_scale > 0.f) { rc = require(s, {B2G_T_OBJ_FORCE, B2G_T_RANDOM_FORCE_PROB}, "b2g_reset_flagged(ShadowHand, forceScale > 0)"); if (rc) return rc; }
         hand_reset_kernel<<<(N + 127) / 128, 128, 0, st>>>(s->buf, s->hand, N, nd);
     } else {
         if (s->task.task != B2G_TASK_CARTPOLE) { rc = require(s, {B2G_T_POTENTIALS, B2G_T_PREV_POTENTIALS, B2G_T_INITIAL_ROOT}, "b2g_reset_flagged"); if (rc) return rc; }

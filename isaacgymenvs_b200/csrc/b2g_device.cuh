@@ -555,6 +555,7 @@ struct Stepper {
     const DevModel *gmodel;   // the model's copy in global memory (self-collision tables), may be null when self_on == 0
     const float *dr_mass;     // per-env physical parameters (vec_task.py:720-828 as arrays; null = the model's own): this env's link-mass
     const float4 *dr_dof;     // factors [nl] (inertia scales with the mass), and per DOF (damping, stiffness, lower, upper)
+    float obj_fext[3];        // OBJ: external force on the free object, in ITS frame, at its COM (apply_rigid_body_force_tensors LOCAL_SPACE)
     float4 *scen;             // this ENV's self-collision scratch, element i at scen[i * scs]: [0, ncp) sphere centres about O +
     int scs;                  // radius, [ncp].x hit count, [ncp + 1, ncp + 5) the overlapping pairs of this sub-step (SELF_HITS x uint16)
 
@@ -1049,6 +1050,11 @@ struct Stepper {
             for (int c = 0; c < 21; c++) Io[c] += I[c];
 #pragma unroll
             for (int c = 0; c < 3; c++) { pao[c] += qa[c]; plo[c] += ql[c]; }
+            // external force (object frame -> world) at the COM: wrench about O is (c x F ; F); biases carry minus the applied wrench
+            float Fw[3], cxF[3];
+            matvec(Ro, obj_fext, Fw); cross(P.c, Fw, cxF);
+#pragma unroll
+            for (int c = 0; c < 3; c++) { pao[c] -= cxF[c]; plo[c] -= Fw[c]; }
         }
         float ao_w[3], ao_l[3];
         const float ba[3] = {-pao[0], -pao[1], -pao[2]}, bl[3] = {-plo[0], -plo[1], -plo[2]};

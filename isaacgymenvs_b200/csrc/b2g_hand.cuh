@@ -42,6 +42,32 @@ __device__ __forceinline__ float hand_rand(uint64_t seed, uint32_t gid, uint32_t
     return 2.0f * reset_uniform(seed, gid, count, idx) + (-1.0f);
 }
 
+// ---- random forces on the object (shadow_hand.py:700-709, forceScale > 0).  The reference draws from torch's global generator;
+// here, like the reset stream, the draws are counter-based: Philox counter (step within the episode, reset count, global
+// env id, 1 | 2), so the result does not depend on the sharding.  f: the force carried over from the previous step.
+__device__ __forceinline__ float hand_force_prob(const b2g_hand_params &P, uint32_t gid, uint32_t count, int nd) {
+    // random_force_prob = exp((log p0 - log p1) * rand + log p1), :198,642; index 2 nd + 7 of the env's reset stream
+    return expf(P.force_logp_span * reset_uniform(P.seed, gid, count, 2 * nd + 7) + P.force_logp1);
+}
+__device__ __forceinline__ void hand_force_update(const b2g_hand_params &P, uint32_t gid, uint32_t rcount, uint32_t step, float mass,
+                                                  float prob, float f[3]) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) f[c] *= P.force_decay_factor;                     // rb_forces *= decay ^ (dt / interval), :701
+    uint32_t r[4];
+    philox4x32_10(step, rcount, gid, 1u, (uint32_t)P.seed, (uint32_t)(P.seed >> 32), r);
+    const float k24 = 1.0f / 16777216.0f;
+    if ((float)(r[0] >> 8) * k24 < prob) {                                        // torch.rand(num_envs) < random_force_prob, :704
+        uint32_t r2[4];
+        philox4x32_10(step, rcount, gid, 2u, (uint32_t)P.seed, (uint32_t)(P.seed >> 32), r2);
+        // Box-Muller: two pairs of uniforms -> three standard normals (torch.randn, :705)
+        const float ra = sqrtf(-2.0f * logf((float)((r[1] >> 8) + 1u) * k24)), ta = 6.2831855f * ((float)(r[2] >> 8) * k24);
+        const float rb = sqrtf(-2.0f * logf((float)((r[3] >> 8) + 1u) * k24)), tb = 6.2831855f * ((float)(r2[0] >> 8) * k24);
+        const float n[3] = {ra * cosf(ta), ra * sinf(ta), rb * cosf(tb)};
+#pragma unroll
+        for (int c = 0; c < 3; c++) f[c] = n[c] * mass * P.force_scale;
+    }
+}
+
 template <int L, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) hand_step_kernel(const DevModel *__restrict__ gm, Buffers B,
                                                           const __grid_constant__ b2g_hand_params P,
@@ -153,6 +179,17 @@ __global__ void __launch_bounds__(BLOCK) hand_step_kernel(const DevModel *__rest
         }
         if (valid) { cur_t[d] = cur; prev_t[d] = prev; }
         st.set_joint(s, qv.x, qv.y, (st.links[link].flags & LF_POSDRIVE) ? cur : 0.f);
+    }
+
+    // ---- random forces on the object (:700-709): every lane of the env computes them, lane 0 stores
+    if (P.force_scale > 0.f) {
+        float *const of = (float *)B.p[B2G_T_OBJ_FORCE] + 3 * (size_t)e, *const pb = (float *)B.p[B2G_T_RANDOM_FORCE_PROB] + e;
+        float f[3] = {of[0], of[1], of[2]}, prob = *pb;
+        if (do_reset) { f[0] = f[1] = f[2] = 0.f; prob = hand_force_prob(P, gid, count, nd); }      // reset_idx, :616,642
+        hand_force_update(P, gid, do_reset ? count + 1u : (uint32_t)rc[e], (uint32_t)progress, sm.obj_mass, prob, f);
+        __syncwarp();                                   // every lane has read the old values
+        if (w0) { of[0] = f[0]; of[1] = f[1]; of[2] = f[2]; *pb = prob; }
+        st.obj_fext[0] = f[0]; st.obj_fext[1] = f[1]; st.obj_fext[2] = f[2];
     }
 
     // ---- control_freq_inv x gym.simulate.  control_freq_inv == 0: no simulate (the observation then reads the

@@ -184,61 +184,75 @@ B2G_HD void kin_body(int b, const KinModel &t, KinScratch &s) {
     for (int c = 0; c < 3; c++) s.pb[b][c] = s.x[l][c] + o[c];
 }
 
-// element [r][k] of the cross-product matrix [p]x = [0 -pz py; pz 0 -px; -py px 0]
-B2G_HD float kin_skew_elem(const float *p, int r, int k) {
-    if (r == k) return 0.f;
-    const int o = 3 - r - k;                                // the remaining axis
-    return ((k - r + 3) % 3 == 1) ? -p[o] : p[o];
+// ---- fills.  A lane owns one COLUMN c of both tensors for the whole env, so what belongs to the column -- the joint's world
+// axis, origin, motion subspace, Ic S and ancestor mask -- is fetched once (KinCol) and every output row costs a few
+// multiply-adds; the stores of a warp are one contiguous run of an output row.
+struct KinCol {
+    int base;               // 0..5: base column (world linear 0..2, world angular 3..5), -1: joint column
+    int link, slide;        // joint column: its link
+    unsigned anc;
+    float w[3], x[3], sl[3], n[3], f[3], arm;
+};
+B2G_HD KinCol kin_col(int c, const KinModel &t, const KinScratch &s) {
+    KinCol k;
+    k.base = c < t.nbase ? c : -1;
+    const int j = c < t.nbase ? 0 : c - t.nbase + 1;
+    k.link = j; k.slide = t.slide[j]; k.anc = t.anc[j]; k.arm = t.armature[j];
+#pragma unroll
+    for (int a = 0; a < 3; a++) { k.w[a] = s.w[j][a]; k.x[a] = s.x[j][a]; k.sl[a] = s.sl[j][a]; k.n[a] = s.nf[j][a]; k.f[a] = s.nf[j][3 + a]; }
+    return k;
 }
 
-// ---- element (body b, component r, column c) of the Jacobian
-B2G_HD float kin_jac_elem(int b, int r, int c, const KinModel &t, const KinScratch &s) {
-    const float *pb = s.pb[b];
-    if (c < t.nbase) {      // v_b = v_0 + w_0 x (p_b - O) = v_0 - [p_b]x w_0
-        if (c < 3) return (r == c) ? 1.f : 0.f;
-        const int k = c - 3;
-        if (r >= 3) return (r - 3 == k) ? 1.f : 0.f;
-        return -kin_skew_elem(pb, r, k);
+B2G_HD float kin_pick(const float v[3], int a) { return a == 0 ? v[0] : (a == 1 ? v[1] : v[2]); }   // no dynamic register indexing
+
+// the six entries (linear 3, angular 3) of body b's Jacobian block in column k
+B2G_HD void kin_jac_col(int b, const KinCol &k, const KinModel &t, const KinScratch &s, float o[6]) {
+    const float pb[3] = {s.pb[b][0], s.pb[b][1], s.pb[b][2]};
+    if (k.base >= 0) {      // v_b = v_0 + w_0 x (p_b - O):  columns (e_k ; 0) and (e_k x p_b ; e_k)
+        const int a = k.base < 3 ? k.base : k.base - 3;
+        const float e[3] = {a == 0 ? 1.f : 0.f, a == 1 ? 1.f : 0.f, a == 2 ? 1.f : 0.f};
+        if (k.base < 3) { o[0] = e[0]; o[1] = e[1]; o[2] = e[2]; o[3] = o[4] = o[5] = 0.f; }
+        else { cross(e, pb, o); o[3] = e[0]; o[4] = e[1]; o[5] = e[2]; }
+        return;
     }
-    const int j = c - t.nbase + 1;
-    if (!((t.anc[t.body_link[b]] >> j) & 1u)) return 0.f;
-    const float *w = s.w[j];
-    if (t.slide[j]) return r < 3 ? w[r] : 0.f;
-    if (r >= 3) return w[r - 3];
-    const float d[3] = {pb[0] - s.x[j][0], pb[1] - s.x[j][1], pb[2] - s.x[j][2]};
-    const int r1 = (r + 1) % 3, r2 = (r + 2) % 3;
-    return w[r1] * d[r2] - w[r2] * d[r1];
+    const bool on = (t.anc[t.body_link[b]] >> k.link) & 1u;     // the joint lies between the base and this body
+    if (!on) { o[0] = o[1] = o[2] = o[3] = o[4] = o[5] = 0.f; return; }
+    if (k.slide) { o[0] = k.w[0]; o[1] = k.w[1]; o[2] = k.w[2]; o[3] = o[4] = o[5] = 0.f; return; }
+    const float d[3] = {pb[0] - k.x[0], pb[1] - k.x[1], pb[2] - k.x[2]};
+    cross(k.w, d, o);
+    o[3] = k.w[0]; o[4] = k.w[1]; o[5] = k.w[2];
 }
 
-// ---- element (a, c) of the mass matrix
-B2G_HD float kin_mass_elem(int a, int c, const KinModel &t, const KinScratch &s) {
+// entry (row a, column k) of the mass matrix
+B2G_HD float kin_mass_col(int a, const KinCol &k, const KinModel &t, const KinScratch &s) {
     const int nb = t.nbase;
-    if (a < nb && c < nb) {
+    if (a < nb) {
+        const int ax = a < 3 ? a : a - 3;
+        if (k.base < 0) return a < 3 ? kin_pick(k.f, ax) : kin_pick(k.n, ax);           // base row against a joint column: Ic_j S_j
         const float *cb = s.cb;
-        if (a < 3 && c < 3) return a == c ? cb[9] : 0.f;
-        if (a >= 3 && c >= 3) {
-            const int i = a - 3, j = c - 3;
-            if (i == j) return cb[i];
-            return cb[2 + i + j];                           // (0,1) -> 3, (0,2) -> 4, (1,2) -> 5
-        }
-        // linear row i / angular column j:  p = w x (m c) = -[mc]x w  ->  -skew(mc)[i][j];  the transpose for (ang, lin)
-        const int i = a < 3 ? a : c, j = a < 3 ? c - 3 : a - 3;
-        return -kin_skew_elem(cb + 6, i, j);
+        const int kx = k.base < 3 ? k.base : k.base - 3;
+        if (a < 3 && k.base < 3) return ax == kx ? cb[9] : 0.f;     // m 1
+        if (a >= 3 && k.base >= 3) return ax == kx ? cb[ax] : cb[2 + ax + kx];   // I_O: (0,1) -> 3, (0,2) -> 4, (1,2) -> 5
+        // linear row i, angular column j: p = w x (m c) -> -[mc]x [i][j]; the (angular, linear) entry is its transpose
+        const int i = a < 3 ? ax : kx, j = a < 3 ? kx : ax;
+        if (i == j) return 0.f;
+        const float v = cb[6 + 3 - i - j];
+        return ((j - i + 3) % 3 == 1) ? v : -v;
     }
-    if (a < nb || c < nb) {                                 // base row against joint column (symmetric)
-        const int k = a < nb ? a : c, i = (a < nb ? c : a) - nb + 1;
-        return k < 3 ? s.nf[i][3 + k] : s.nf[i][k - 3];
-    }
-    int i = a - nb + 1, j = c - nb + 1;
-    if (!((t.anc[i] >> j) & 1u)) {                          // j is not on i's path to the root: swap or zero
-        if (!((t.anc[j] >> i) & 1u)) return 0.f;
-        const int tmp = i; i = j; j = tmp;
-    }
-    const float *n = s.nf[i], *f = s.nf[i] + 3, *w = s.w[j];
+    const int i = a - nb + 1;
+    if (k.base >= 0) { const int kx = k.base < 3 ? k.base : k.base - 3; return k.base < 3 ? s.nf[i][3 + kx] : s.nf[i][kx]; }
+    const int j = k.link;
     float v;
-    if (t.slide[j]) v = w[0] * f[0] + w[1] * f[1] + w[2] * f[2];
-    else v = w[0] * n[0] + w[1] * n[1] + w[2] * n[2] + s.sl[j][0] * f[0] + s.sl[j][1] * f[1] + s.sl[j][2] * f[2];
-    return i == j ? v + t.armature[i] : v;
+    if ((t.anc[i] >> j) & 1u) {             // column joint j on row link i's path:  S_j . (Ic_i S_i)
+        const float *n = s.nf[i], *f = s.nf[i] + 3;
+        v = k.slide ? k.w[0] * f[0] + k.w[1] * f[1] + k.w[2] * f[2]
+                    : k.w[0] * n[0] + k.w[1] * n[1] + k.w[2] * n[2] + k.sl[0] * f[0] + k.sl[1] * f[1] + k.sl[2] * f[2];
+    } else if ((k.anc >> i) & 1u) {         // the transpose:  S_i . (Ic_j S_j)
+        const float *w = s.w[i], *sl = s.sl[i];
+        v = t.slide[i] ? w[0] * k.f[0] + w[1] * k.f[1] + w[2] * k.f[2]
+                       : w[0] * k.n[0] + w[1] * k.n[1] + w[2] * k.n[2] + sl[0] * k.f[0] + sl[1] * k.f[1] + sl[2] * k.f[2];
+    } else return 0.f;                      // different branches of the tree
+    return i == j ? v + k.arm : v;
 }
 
 #ifdef __CUDACC__
@@ -271,15 +285,20 @@ __global__ void __launch_bounds__(WARPS * 32) kin_tensors_kernel(const KinModel 
         if (mass) {
             if (lane < nl) kin_composite(lane, t, s);
             __syncwarp();
-            float *M = mass + (size_t)e * nc * nc;
-            for (int a = 0; a < nc; a++)
-                for (int c = lane; c < nc; c += 32) M[a * nc + c] = kin_mass_elem(a, c, t, s);
         }
-        if (jac) {
-            float *J = jac + (size_t)e * t.rows * 6 * nc;
-            for (int br = 0; br < t.rows * 6; br++) {
-                const int b = t.row0 + br / 6, r = br % 6;
-                for (int c = lane; c < nc; c += 32) J[br * nc + c] = kin_jac_elem(b, r, c, t, s);
+        for (int c = lane; c < nc; c += 32) {                // one pass for nc <= 32, two for the largest floating trees
+            const KinCol k = kin_col(c, t, s);
+            if (mass) {
+                float *M = mass + (size_t)e * nc * nc + c;
+                for (int a = 0; a < nc; a++) M[(size_t)a * nc] = kin_mass_col(a, k, t, s);
+            }
+            if (jac) {
+                float *J = jac + (size_t)e * t.rows * 6 * nc + c;
+                for (int b = 0; b < t.rows; b++) {
+                    float o[6]; kin_jac_col(t.row0 + b, k, t, s, o);
+#pragma unroll
+                    for (int r = 0; r < 6; r++) J[(size_t)(b * 6 + r) * nc] = o[r];
+                }
             }
         }
     }

@@ -76,6 +76,11 @@ __global__ void __launch_bounds__(128) hand_reset_kernel(Buffers B, const __grid
         dof[d] = make_float2(pos, P.dof_default_vel[d] + P.reset_dof_vel_noise * hand_rand(P.seed, gid, count, 5 + nd + d));
         cur_t[d] = pos; prev_t[d] = pos;
     }
+    if (P.force_scale > 0.f) {                                           // rb_forces[env_ids] = 0, new random_force_prob (:616,642)
+        float *const of = (float *)B.p[B2G_T_OBJ_FORCE] + 3 * (size_t)e;
+        of[0] = of[1] = of[2] = 0.f;
+        ((float *)B.p[B2G_T_RANDOM_FORCE_PROB])[e] = hand_force_prob(P, gid, count, nd);
+    }
     ((long long *)B.p[B2G_T_PROGRESS])[e] = 0;
     ((float *)B.p[B2G_T_SUCCESSES])[e] = 0.f;
     reset_b[e] = 0;

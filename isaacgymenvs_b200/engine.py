@@ -23,7 +23,7 @@ MAXL = 32
  T_FEET_AIR_TIME, T_TORQUES, T_EPISODE_SUMS, T_TERRAIN_LEVELS, T_TERRAIN_TYPES, T_ENV_ORIGINS, T_TERRAIN_ORIGINS,
  T_NOISE_SCALE, T_BASE_SCRATCH, T_REDUCE_SCRATCH, T_ENV_FRICTION, T_GOAL_STATES, T_PREV_TARGETS, T_SUCCESSES,
  T_CONSECUTIVE_SUCCESSES, T_RESET_GOAL, T_GOAL_RESET_COUNT, T_STATES, T_ENV_MASS_SCALE, T_ENV_DOF_PROPS,
- T_JACOBIAN, T_MASS_MATRIX) = range(46)
+ T_JACOBIAN, T_MASS_MATRIX, T_OBJ_FORCE, T_RANDOM_FORCE_PROB) = range(48)
 TASK_NONE, TASK_CARTPOLE, TASK_ANT, TASK_HUMANOID, TASK_ANYMAL_TERRAIN, TASK_SHADOW_HAND = 0, 1, 2, 3, 4, 5
 HAND_OBS = {"openai": 0, "full_no_vel": 1, "full": 2, "full_state": 3}
 
@@ -41,7 +41,8 @@ class CHandParams(C.Structure):
                 ("goal_displacement", C.c_float * 3), ("actuated_dof", C.c_int32 * 32),
                 ("dof_lower", C.c_float * 32), ("dof_upper", C.c_float * 32), ("dof_default_pos", C.c_float * 32),
                 ("dof_default_vel", C.c_float * 32), ("fingertip_body", C.c_int32 * 5), ("num_states", C.c_int32),
-                ("seed", C.c_uint64), ("env_id_offset", C.c_int32), ("pad1", C.c_int32)]
+                ("seed", C.c_uint64), ("env_id_offset", C.c_int32), ("pad1", C.c_int32),
+                ("force_scale", C.c_float), ("force_decay_factor", C.c_float), ("force_logp_span", C.c_float), ("force_logp1", C.c_float)]
 
 
 class CAnymalParams(C.Structure):

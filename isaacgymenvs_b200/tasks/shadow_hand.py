@@ -29,9 +29,10 @@ class ShadowHand(VecTask):
         self.vel_obs_scale = 0.2; self.force_torque_obs_scale = 10.0                                            # shadow_hand.py:62-63
         self.reset_position_noise = e["resetPositionNoise"]; self.reset_rotation_noise = e["resetRotationNoise"]
         self.reset_dof_pos_noise = e["resetDofPosRandomInterval"]; self.reset_dof_vel_noise = e["resetDofVelRandomInterval"]
-        self.force_scale = e.get("forceScale", 0.0)
-        if self.force_scale > 0.0:
-            raise NotImplementedError("random object forces (forceScale > 0, shadow_hand.py:700-709) are not in the fused step")
+        self.force_scale = e.get("forceScale", 0.0)                                                             # shadow_hand.py:69-72
+        self.force_prob_range = e.get("forceProbRange", [0.001, 0.1])
+        self.force_decay = e.get("forceDecay", 0.99)
+        self.force_decay_interval = e.get("forceDecayInterval", 0.08)
         self.shadow_hand_dof_speed_scale = e["dofSpeedScale"]; self.use_relative_control = e["useRelativeControl"]
         self.act_moving_average = e["actionsMovingAverage"]
         self.max_episode_length = e["episodeLength"]
@@ -134,6 +135,14 @@ class ShadowHand(VecTask):
         self.consecutive_successes = self._cons[0:1]
         self.goal_reset_count = torch.zeros(N, dtype=torch.int32, device=dev)
         self.object_rb_masses = torch.tensor([self._obj["mass"]], dtype=torch.float, device=dev)
+        # random forces on the object (shadow_hand.py:196-201).  The reference keeps rb_forces (N, bodies, 3) of which only the
+        # object's row is ever non-zero; the engine's tensor is that row (N, 3), in the object's frame (LOCAL_SPACE, :708)
+        self.force_decay = torch.tensor(self.force_decay, dtype=torch.float, device=dev)
+        self.force_prob_range = torch.tensor(self.force_prob_range, dtype=torch.float, device=dev)
+        self.random_force_prob = torch.exp((torch.log(self.force_prob_range[0]) - torch.log(self.force_prob_range[1]))
+                                           * torch.rand(N, device=dev) + torch.log(self.force_prob_range[1])).contiguous()
+        self.object_rb_forces = torch.zeros((N, 3), dtype=torch.float, device=dev)
+        self.object_rb_handles = torch.tensor([model.nb], dtype=torch.long, device=dev)
         self.total_successes = 0; self.total_resets = 0
         return sim
 
@@ -141,6 +150,13 @@ class ShadowHand(VecTask):
     def rigid_body_states(self):
         """(N, bodies, 13) like gym.refresh_rigid_body_state_tensor + the view of shadow_hand.py:180 (computed on demand)."""
         return self.sim.refresh_rigid_body_state().view(self.num_envs, -1, 13)
+
+    @property
+    def rb_forces(self):
+        """(N, bodies, 3) as shadow_hand.py:201 holds it: zero except the object's row (a copy; the engine owns object_rb_forces)."""
+        f = torch.zeros((self.num_envs, self.num_bodies, 3), dtype=torch.float, device=self.device)
+        f[:, self.model.nb] = self.object_rb_forces
+        return f
 
     @property
     def object_pos(self):
@@ -163,7 +179,8 @@ class ShadowHand(VecTask):
         extra = {E.T_STATES: self.states_buf} if self.asymmetric_obs else {}
         return {**extra, E.T_INITIAL_ROOT: self.initial_root_states, E.T_GOAL_STATES: self.goal_states, E.T_PREV_TARGETS: self.prev_targets,
                 E.T_SUCCESSES: self.successes, E.T_CONSECUTIVE_SUCCESSES: self._cons, E.T_RESET_GOAL: self.reset_goal_buf,
-                E.T_GOAL_RESET_COUNT: self.goal_reset_count}
+                E.T_GOAL_RESET_COUNT: self.goal_reset_count, E.T_OBJ_FORCE: self.object_rb_forces,
+                E.T_RANDOM_FORCE_PROB: self.random_force_prob}
 
     def _task_params(self):
         p = engine.CHandParams()
@@ -191,6 +208,11 @@ class ShadowHand(VecTask):
             p.dof_default_pos[d] = 0.0; p.dof_default_vel[d] = 0.0
         for f in range(5):
             p.fingertip_body[f] = int(self.fingertip_handles_np[f])
+        # random object forces (:700-709): the constants in the float32 arithmetic of the reference's tensors
+        p.force_scale = float(self.force_scale)
+        p.force_decay_factor = float(torch.pow(self.force_decay, self.dt / self.force_decay_interval))
+        p.force_logp_span = float(torch.log(self.force_prob_range[0]) - torch.log(self.force_prob_range[1]))
+        p.force_logp1 = float(torch.log(self.force_prob_range[1]))
         return p
 
     def _fill_extras(self):

@@ -239,6 +239,10 @@ static int sphere_box(const real c[3], real r, const real xb[3], const real Rb[9
 
 /* One sub-step for one environment.  root: pos3 quat4(xyzw) linvel3 angvel3 (world); dof: (q,qd)
  * interleaved.  cf_body (nb x 3, world) and dof_force (nd) receive the forces of THIS sub-step. */
+/* external force on the free object's body, in ITS frame, held over the simulate call: gym.apply_rigid_body_force_tensors(sim,
+ * forces, None, LOCAL_SPACE) (shadow_hand.py:708, forceScale > 0).  Set per call by oracle_set_obj_force (nenv,3); acts at the COM. */
+static const real *g_obj_force = 0;
+static __thread const real *t_obj_fl = 0;
 static void substep(const OracleModel *m, real h, real *root, real *dof, const real *tau_act,
                     const real *target, real *cf_body, real *cf_torque_body, real *dof_force,
                     real *Rw_out, real *pw_out, real *vlink_out, real *obj) {
@@ -434,6 +438,7 @@ static void substep(const OracleModel *m, real h, real *root, real *dof, const r
         real wxv0[3]; cross3(obj + 10, obj + 7, wxv0);
         for (int k = 0; k < 3; k++) { bo[k] = -gyro[k]; bo[3 + k] = (m->obj_gravity_on ? (real)m->obj_mass * (real)m->gravity[k] : 0) - (real)m->obj_mass * wxv0[k]; }
         for (int k = 0; k < 3; k++) { bo[k] -= (real)m->obj_angular_damping * Iww[k]; bo[3 + k] -= (real)m->obj_linear_damping * (real)m->obj_mass * obj[7 + k]; }
+        if (t_obj_fl) { real Fw[3]; mat3_vec(Ro, t_obj_fl, Fw); for (int k = 0; k < 3; k++) bo[3 + k] += Fw[k]; }
         real okn = (real)m->obj_kn, ocn = (real)m->obj_cn, ogn = ocn + h * okn, hb[3] = {(real)m->obj_half[0], (real)m->obj_half[1], (real)m->obj_half[2]};
         /* helper macro: one contact at world point pc with normal nrm (direction of the force on the LINK), penetration pen */
 #define OBJ_CONTACT(LI, BI, CPI, PC, NRM, PEN, MU) do {                                                                       \
@@ -738,6 +743,7 @@ static void *simulate_range(void *arg) {
         real cf[3 * MAXL], ct[3 * MAXL], df[MAXL], bs[13 * MAXL];
         real *r = j->root + 13 * e, *d = j->dof + 2 * nd * e;
         real Rw[9 * MAXL], pw[3 * MAXL], vl[6 * MAXL];
+        t_obj_fl = (g_obj_force && j->obj) ? g_obj_force + 3 * e : 0;
         for (int s = 0; s < m->substeps; s++)
             substep(m, h, r, d, j->tau_act ? j->tau_act + nd * e : 0, j->target ? j->target + nd * e : 0, cf, ct, df, Rw, pw, vl, j->obj ? j->obj + 13 * e : 0);
         if (j->dof_force) memcpy(j->dof_force + nd * e, df, sizeof(real) * nd);
@@ -756,6 +762,7 @@ static void *simulate_range(void *arg) {
     return 0;
 }
 
+void oracle_set_obj_force(const real *f) { g_obj_force = f; }      /* NULL: none; the pointer must outlive the simulate call */
 static int g_threads = 1;
 void oracle_set_threads(int n) { g_threads = n < 1 ? 1 : (n > 256 ? 256 : n); }
 

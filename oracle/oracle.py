@@ -124,8 +124,9 @@ class OracleSim:
         self.cm = cm
         self.nd, self.nb, self.ns = m.ndof, m.nb, len(m.sensor_body)
 
-    def simulate(self, root, dof, tau=None, target=None, obj=None):
-        """In-place gym.simulate(): root (N,13), dof (N,nd,2).  Returns dict of derived outputs."""
+    def simulate(self, root, dof, tau=None, target=None, obj=None, obj_force=None):
+        """In-place gym.simulate(): root (N,13), dof (N,nd,2).  Returns dict of derived outputs.  obj_force (N,3): force on the
+        free object's body in its own frame, at the COM (apply_rigid_body_force_tensors LOCAL_SPACE, shadow_hand.py:708)."""
         N = root.shape[0]
         assert root.dtype == self.dtype and dof.dtype == self.dtype and root.flags.c_contiguous and dof.flags.c_contiguous
         tau = None if tau is None else np.ascontiguousarray(tau, dtype=self.dtype)
@@ -135,9 +136,14 @@ class OracleSim:
         p = lambda a: None if a is None else C.c_void_p(a.ctypes.data)
         if obj is not None:
             assert obj.dtype == self.dtype and obj.flags.c_contiguous and obj.shape == (N, 13) and self.cm.obj_on
+        if obj_force is not None:
+            obj_force = np.ascontiguousarray(obj_force, dtype=self.dtype)
+            assert obj is not None and obj_force.shape == (N, 3)
+        self.lib.oracle_set_obj_force(p(obj_force))
         self.lib.oracle_simulate_obj(C.byref(self.cm), C.c_int(N), p(root), p(dof), p(tau), p(target),
                                      p(out["body_state"]), p(out["contact_force"]), p(out["sensor"]),
                                      p(out["dof_force"]), p(obj))
+        self.lib.oracle_set_obj_force(None)
         out["sensor"] = out["sensor"][:, :self.ns]
         out["dof_force"] = out["dof_force"][:, :self.nd]
         return out

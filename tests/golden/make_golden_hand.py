@@ -28,6 +28,7 @@ def load():
     sys.modules["isaacgym"].gymapi = sys.modules["isaacgym.gymapi"]
     sys.modules["isaacgym"].gymutil = sys.modules["isaacgym.gymutil"]
     sys.modules["isaacgym.gymtorch"].unwrap_tensor = lambda t: t
+    sys.modules["isaacgym.gymapi"].LOCAL_SPACE = 1              # only named in the apply_rigid_body_force_tensors call (:708)
     for name in ("isaacgymenvs", "isaacgymenvs.utils", "isaacgymenvs.tasks", "isaacgymenvs.tasks.base"):
         sys.modules.setdefault(name, types.ModuleType(name))
     sys.modules["isaacgymenvs.tasks"].__path__ = []
@@ -65,7 +66,9 @@ class Gym:
         t.rigid_body_states = torch.tensor(full)
 
 
-def make_case(sh, g, n, obs_type, relative, mcs, mavg, fall_penalty, orc, model, act_idx, fingertip_handles):
+def make_case(sh, g, n, obs_type, relative, mcs, mavg, fall_penalty, orc, model, act_idx, fingertip_handles, force=None):
+    """force: None, or dict(scale, prob_range, obj_mass) -- random forces on the object (shadow_hand.py:700-709); the
+    reference's torch.rand / torch.randn draws are then played by the engine's counter-based stream as well."""
     from oracle import tasks_np
     D = model.ndof
     t = object.__new__(sh.ShadowHand)
@@ -133,12 +136,21 @@ def make_case(sh, g, n, obs_type, relative, mcs, mavg, fall_penalty, orc, model,
     reset_count = torch.randint(0, 5, (n,), generator=g).int(); goal_count = torch.randint(0, 5, (n,), generator=g).int()
     actions = torch.rand(n, 20, generator=g) * 2.4 - 1.2
     t.gym = Gym(t, orc, model)
+    force_in = {}
+    if force is not None:
+        t.force_scale = force["scale"]
+        t.force_prob_range = torch.tensor(force["prob_range"], dtype=torch.float)
+        t.random_force_prob = torch.rand(n, generator=g) * 0.6
+        t.object_rb_handles = torch.tensor([model.nb], dtype=torch.long)
+        t.object_rb_masses = torch.tensor([force["obj_mass"]], dtype=torch.float)
+        t.rb_forces[:, model.nb] = torch.randn(n, 3, generator=g) * 0.05
+        force_in = dict(obj_force=t.rb_forces[:, model.nb].numpy().copy(), force_prob=t.random_force_prob.numpy().copy())
     inputs = dict(root=t.root_state_tensor.numpy().copy(), dof_state=t.dof_state.numpy().copy(), prev_targets=t.prev_targets.numpy().copy(),
                   cur_targets=t.cur_targets.numpy().copy(), goal_states=t.goal_states.numpy().copy(), sensors=t.vec_sensor_tensor.numpy().copy(),
                   dof_force=t.dof_force_tensor.numpy().copy(), reset=t.reset_buf.numpy().copy(), reset_goal=t.reset_goal_buf.numpy().copy(),
                   progress=t.progress_buf.numpy().copy(), successes=t.successes.numpy().copy(), cons=t.consecutive_successes.numpy().copy(),
                   reset_count=reset_count.numpy().copy(), goal_reset_count=goal_count.numpy().copy(), actions=actions.numpy().copy(),
-                  object_init=obj_init.numpy().copy(), goal_init=goal_init.numpy().copy())
+                  object_init=obj_init.numpy().copy(), goal_init=goal_init.numpy().copy(), **force_in)
 
     # ---- the engine's Philox numbers behind torch_rand_float
     ctx = {"env_ids": None, "in_reset_idx": False}
@@ -167,20 +179,56 @@ def make_case(sh, g, n, obs_type, relative, mcs, mavg, fall_penalty, orc, model,
             return orig_ri(self, env_ids, goal_env_ids)
         finally:
             ctx["in_reset_idx"] = False
+    # torch.rand / torch.randn of the force block (:704-706) and of reset_idx's random_force_prob (:642), when forces are on
+    class TorchProxy:
+        def __getattr__(self, name):
+            return getattr(torch, name)
+
+        def rand(self, k, device=None):
+            if ctx["in_reset_idx"]:                            # one uniform per env of env_ids: index 2 D + 7 of its reset stream
+                ids = ctx["env_ids"].tolist(); assert k == len(ids)
+                return torch.tensor([float(tasks_np.reset_uniforms(SEED, e, int(reset_count[e]), 2 * D + 8)[2 * D + 7]) for e in ids], dtype=torch.float)
+            assert k == n                                       # the force block: one uniform per env, step = progress, count after resets
+            cnt = reset_count.clone(); cnt[inputs["reset"] != 0] += 1
+            dr = [tasks_np.hand_force_draws(SEED, e, int(cnt[e]), int(t.progress_buf[e])) for e in range(n)]
+            ctx["normals"] = np.stack([d[1] for d in dr])
+            return torch.tensor(np.array([d[0] for d in dr], np.float32))
+
+        def randn(self, shape, device=None):
+            # rows of the envs that drew a new force, in order: what `(rand < prob).nonzero()` selected
+            hit = (torch.tensor(ctx["u_last"]) < t.random_force_prob).nonzero().flatten().tolist()
+            assert tuple(shape) == (len(hit), 1, 3)
+            return torch.tensor(ctx["normals"][hit].reshape(len(hit), 1, 3))
+    proxy = TorchProxy()
+    _rand = proxy.rand
+
+    def rand_keep(k, device=None):
+        r = _rand(k, device)
+        if not ctx["in_reset_idx"]:
+            ctx["u_last"] = r.numpy().copy()
+        return r
+    proxy.rand = rand_keep
     sh.torch_rand_float = rand_float
     sh.ShadowHand.reset_target_pose, sh.ShadowHand.reset_idx = rtp, ri
+    if force is not None:
+        sh.torch = proxy
     try:
         a = torch.clamp(actions, -1.0, 1.0)                    # VecTask.step, vec_task.py:374
         t.pre_physics_step(a)
         t.post_physics_step()                                   # control_freq_inv == 0: no simulate in between
     finally:
         sh.ShadowHand.reset_target_pose, sh.ShadowHand.reset_idx = orig_rtp, orig_ri
+        sh.torch = torch
     timeout = (t.progress_buf >= t.max_episode_length - 1) & (t.reset_buf != 0)                     # vec_task.py:394
     outputs = dict(root=t.root_state_tensor.numpy(), dof_state=t.dof_state.numpy(), prev_targets=t.prev_targets.numpy(),
                    cur_targets=t.cur_targets.numpy(), goal_states=t.goal_states.numpy(), obs=t.obs_buf.numpy(), rew=t.rew_buf.numpy(),
                    reset=t.reset_buf.numpy(), reset_goal=t.reset_goal_buf.numpy(), progress=t.progress_buf.numpy(),
                    successes=t.successes.numpy(), cons=t.consecutive_successes.numpy(), timeout=timeout.numpy(),
                    fingertip_state=t.fingertip_state.numpy())
+    if force is not None:
+        others = t.rb_forces.clone(); others[:, model.nb] = 0
+        outputs.update(obj_force=t.rb_forces[:, model.nb].numpy().copy(), force_prob=t.random_force_prob.numpy().copy(),
+                       other_forces=np.float32(others.abs().sum()))
     return inputs, outputs
 
 
@@ -214,5 +262,34 @@ def main():
     print("wrote shadow_hand.npz;", {k: v.shape for k, v in blob.items() if k.startswith("a_out")})
 
 
+def main_force():
+    """Case "f": forceScale 2.0, forceProbRange [0.05, 0.5] -> tests/golden/shadow_hand_force.npz (separate file: the
+    fixtures of main() stay byte-identical)."""
+    from tests.hand_common import hand_setup, DT, SUBSTEPS, G
+    from oracle.oracle import OracleSim
+    tju, sh = load()
+    model, obj, tendons = hand_setup()
+    orc = OracleSim(model, DT, SUBSTEPS, G, obj=obj, tendons=tendons, tendon_k=30.0, tendon_d=0.1)
+    names = list(model.dof_names)
+    act_idx = [names.index(j) for j in model.actuator_joint]
+    ft = [int(b) for b in model.sensor_body]
+    g = torch.Generator().manual_seed(14)
+    force = dict(scale=2.0, prob_range=[0.05, 0.5], obj_mass=float(obj["mass"]))
+    inp, out = make_case(sh, g, 256, "full_state", relative=False, mcs=0, mavg=1.0, fall_penalty=0.0, orc=orc, model=model,
+                         act_idx=act_idx, fingertip_handles=ft, force=force)
+    blob = {"seed": np.int64(SEED), "actuated": np.array(act_idx, np.int32), "fingertips": np.array(ft, np.int32),
+            "force_scale": np.float32(force["scale"]), "force_prob_range": np.array(force["prob_range"], np.float32),
+            "obj_mass": np.float32(force["obj_mass"])}
+    for k, v in inp.items():
+        blob[f"f_in_{k}"] = v
+    for k, v in out.items():
+        blob[f"f_out_{k}"] = v
+    np.savez_compressed(os.path.join(OUT, "shadow_hand_force.npz"), **blob)
+    print("wrote shadow_hand_force.npz; new forces drawn in", int((out["obj_force"] != inp["obj_force"] * np.float32(0.99 ** (0.01667 / 0.08))).any(1).sum()), "of 256 envs")
+
+
 if __name__ == "__main__":
-    main()
+    if "--force" in sys.argv:
+        main_force()
+    else:
+        main()

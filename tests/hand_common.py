@@ -43,7 +43,18 @@ def settled_states(n, steps, seed, precision="f64", threads=8):
 # ---------------------------------------------------------------------------------------------
 # golden cases of tests/golden/shadow_hand.npz (make_golden_hand.py)
 CASES = {"a": dict(relative=False, mcs=0, mavg=1.0, fall_penalty=0.0), "b": dict(relative=True, mcs=50, mavg=1.0, fall_penalty=-50.0),
-         "c": dict(relative=False, mcs=0, mavg=0.3, fall_penalty=0.0)}
+         "c": dict(relative=False, mcs=0, mavg=0.3, fall_penalty=0.0),
+         # tests/golden/shadow_hand_force.npz (make_golden_hand.py --force): random forces on the object, shadow_hand.py:700-709
+         "f": dict(relative=False, mcs=0, mavg=1.0, fall_penalty=0.0)}
+
+
+def force_constants(gold):
+    """the float32 constants the reference forms from its config tensors (shadow_hand.py:196-198,701)"""
+    import torch
+    pr = torch.tensor(gold["force_prob_range"], dtype=torch.float)
+    return dict(force_scale=float(gold["force_scale"]), obj_mass=float(gold["obj_mass"]),
+                force_decay_factor=float(torch.pow(torch.tensor(0.99), 0.01667 / 0.08)),
+                force_logp_span=float(torch.log(pr[0]) - torch.log(pr[1])), force_logp1=float(torch.log(pr[1])))
 
 
 def golden_case(gold, case, obs_type="full_state"):
@@ -58,6 +69,8 @@ def golden_case(gold, case, obs_type="full_state"):
               reset_goal=g("reset_goal"), progress=g("progress"), successes=g("successes"), reset_count=g("reset_count"),
               goal_reset_count=g("goal_reset_count"))
     kw = CASES[case]
+    if case == "f":
+        st.update(obj_force=g("obj_force"), force_prob=g("force_prob"))
     P = dict(seed=int(gold["seed"]), goal_init=g("goal_init"), object_init=g("object_init"),
              goal_displacement=np.array([-0.2, -0.06, 0.12], np.float32), reset_position_noise=0.01, reset_dof_pos_noise=0.2,
              reset_dof_vel_noise=0.05, lower=m.lower[1:].astype(np.float32), upper=m.upper[1:].astype(np.float32),
@@ -67,4 +80,6 @@ def golden_case(gold, case, obs_type="full_state"):
              dist_reward_scale=-10.0, rot_reward_scale=1.0, rot_eps=0.1, action_penalty_scale=-0.0002, success_tolerance=0.1,
              reach_goal_bonus=250.0, fall_dist=0.24, fall_penalty=kw["fall_penalty"], max_consecutive_successes=kw["mcs"],
              max_episode_length=600.0, av_factor=0.1)
+    if case == "f":
+        P.update(force_constants(gold))
     return st, P, g("actions")

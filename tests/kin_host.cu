@@ -27,12 +27,14 @@ extern "C" int kin_host_tensors(const b2g_model *m, int root_stride, int N, cons
         if (jac) for (int lane = 0; lane < t.nb; lane++) kin_body(lane, t, s);
         if (mass) {
             for (int lane = 0; lane < nl; lane++) kin_composite(lane, t, s);
-            float *M = mass + (size_t)e * nc * nc;
-            for (int a = 0; a < nc; a++) for (int c = 0; c < nc; c++) M[a * nc + c] = kin_mass_elem(a, c, t, s);
         }
-        if (jac) {
-            float *J = jac + (size_t)e * t.rows * 6 * nc;
-            for (int br = 0; br < t.rows * 6; br++) for (int c = 0; c < nc; c++) J[br * nc + c] = kin_jac_elem(t.row0 + br / 6, br % 6, c, t, s);
+        for (int c = 0; c < nc; c++) {
+            const KinCol k = kin_col(c, t, s);
+            if (mass) for (int a = 0; a < nc; a++) mass[(size_t)e * nc * nc + (size_t)a * nc + c] = kin_mass_col(a, k, t, s);
+            if (jac) for (int b = 0; b < t.rows; b++) {
+                float o[6]; kin_jac_col(t.row0 + b, k, t, s, o);
+                for (int r = 0; r < 6; r++) jac[(size_t)e * t.rows * 6 * nc + (size_t)(b * 6 + r) * nc + c] = o[r];
+            }
         }
     }
     delete tp; delete sp;

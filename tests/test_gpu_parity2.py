@@ -628,3 +628,94 @@ def test_humanoid_limbs_do_not_interpenetrate():
         warnings.simplefilter("always")
         _make_anymal(64)
     assert any(issubclass(w.category, engine.UnmodelledPhysicsWarning) for w in rec)
+
+
+# ---------------------------------------------------------------------------------------------
+# random forces on the object (env.forceScale > 0, shadow_hand.py:69-72,196-201,616,642,700-709)
+def test_hand_random_object_forces_match_reference_golden():
+    """The fused ShadowHand step with forceScale = 2 (no physics: controlFrequencyInv = 0) from the inputs of golden case "f":
+    decay of the carried force, zeroing + new probability on reset, redraw where rand < random_force_prob -- against the
+    reference's own pre_physics_step (tests/golden/make_golden_hand.py --force)."""
+    from tests.hand_common import force_constants
+    from tests.test_gpu_parity import _hand_env, GOLD
+    gold = np.load(os.path.join(GOLD, "shadow_hand_force.npz"))
+    gi = lambda k: gold[f"f_in_{k}"]
+    go = lambda k: gold[f"f_out_{k}"]
+    n = gi("reset").shape[0]
+    env = _hand_env(n, "f", "full_state", forceScale=float(gold["force_scale"]), forceProbRange=[float(v) for v in gold["force_prob_range"]])
+    fc = force_constants(gold)
+    assert env.sim.task.force_scale == fc["force_scale"] and env.sim.task.force_decay_factor == np.float32(fc["force_decay_factor"])
+    assert abs(float(env.object_rb_masses[0]) - fc["obj_mass"]) < 1e-9
+    dev = env.device
+    t = lambda a, dt=torch.float32: torch.tensor(np.asarray(a), dtype=dt, device=dev)
+    env.root_state_tensor.copy_(t(gi("root")))
+    env.initial_root_states.view(n, 3, 13)[:, 1].copy_(t(gi("object_init")))
+    env.initial_root_states.view(n, 3, 13)[:, 2].copy_(t(gi("goal_init")))
+    env.dof_state.copy_(t(gi("dof_state")))
+    env.prev_targets.copy_(t(gi("prev_targets"))); env.cur_targets.copy_(t(gi("cur_targets")))
+    env.goal_states.copy_(t(gi("goal_states")))
+    env.vec_sensor_tensor.copy_(t(gi("sensors"))); env.dof_force_tensor.copy_(t(gi("dof_force")))
+    env.reset_buf.copy_(t(gi("reset"), torch.long)); env.reset_goal_buf.copy_(t(gi("reset_goal"), torch.long))
+    env.progress_buf.copy_(t(gi("progress"), torch.long)); env.successes.copy_(t(gi("successes")))
+    env._cons[0] = float(gi("cons")[0])
+    env.reset_count.copy_(t(gi("reset_count"), torch.int32)); env.goal_reset_count.copy_(t(gi("goal_reset_count"), torch.int32))
+    env.object_rb_forces.copy_(t(gi("obj_force"))); env.random_force_prob.copy_(t(gi("force_prob")))
+    env.step(t(gi("actions")))
+    torch.cuda.synchronize()
+    c = lambda x: x.detach().cpu().numpy()
+    # the same envs drew a new force; values to fp32 round-off of log / sqrt / cos (Box-Muller) and exp
+    drew_ref = (go("obj_force") != gi("obj_force") * np.float32(fc["force_decay_factor"])).any(1)
+    drew_gpu = (c(env.object_rb_forces) != gi("obj_force") * np.float32(fc["force_decay_factor"])).any(1)
+    assert np.array_equal(drew_ref | (gi("reset") != 0), drew_gpu | (gi("reset") != 0)) and drew_ref.sum() > 100
+    np.testing.assert_allclose(c(env.object_rb_forces), go("obj_force"), rtol=2e-5, atol=2e-7)
+    np.testing.assert_allclose(c(env.random_force_prob), go("force_prob"), rtol=2e-6)
+    assert np.array_equal(c(env.rb_forces)[:, env.model.nb], c(env.object_rb_forces)) and float(env.rb_forces[:, :env.model.nb].abs().max()) == 0.0
+    # everything else of the step is what it is without forces
+    np.testing.assert_allclose(c(env.root_state_tensor), go("root"), rtol=0, atol=1e-6)
+    np.testing.assert_allclose(c(env.rew_buf), go("rew"), rtol=3e-6, atol=3e-5)
+    assert np.array_equal(c(env.reset_buf), go("reset")) and np.array_equal(c(env.progress_buf), go("progress"))
+    # reset_done (b2g_reset_flagged) zeroes the force and redraws the probability from the reset stream too
+    env.reset_buf.fill_(1); before = c(env.random_force_prob).copy()
+    env.reset_done(); torch.cuda.synchronize()
+    assert float(env.object_rb_forces.abs().max()) == 0.0 and (c(env.random_force_prob) != before).mean() > 0.9
+    lo, hi = [float(v) for v in gold["force_prob_range"]]
+    assert (c(env.random_force_prob) >= lo * (1 - 1e-5)).all() and (c(env.random_force_prob) <= hi * (1 + 1e-5)).all()
+    env.sim.close()
+
+
+def test_hand_object_force_physics_matches_oracle():
+    """gym.apply_rigid_body_force_tensors(..., LOCAL_SPACE) on the object: one gym.simulate() with a force bound to OBJ_FORCE
+    against the oracle given the same force; and a cube in free flight accelerates by g + R f / m."""
+    from isaacgymenvs_b200 import engine
+    from tests.hand_common import settled_states, DT
+    from tests.test_gpu_parity import _hand_sim, _hand_load
+    n = 256
+    m, obj, tendons, orc, root, dof, o, tgt = settled_states(n, 40, 7)
+    rng = np.random.default_rng(3)
+    o[n // 2:, 2] += 1.0                                       # half of the cubes in free flight
+    f = (rng.normal(size=(n, 3)) * obj["mass"] * 20.0).astype(np.float32)
+    sim = _hand_sim(n, m, obj, tendons)
+    _hand_load(sim, root, dof, o, tgt)
+    of = sim._bind(engine.T_OBJ_FORCE, torch.tensor(f, device=sim.device))
+    rs = sim.root_state.cpu().numpy().astype(np.float64).reshape(n, 3, 13)
+    r64 = np.ascontiguousarray(rs[:, 0]); o64 = np.ascontiguousarray(rs[:, 1]); o_in = o64.copy()
+    d64 = sim.dof_state.cpu().numpy().astype(np.float64).reshape(n, m.ndof, 2)
+    t64 = sim.dof_target.cpu().numpy().astype(np.float64)
+    r2, d2, o_no = r64.copy(), d64.copy(), o64.copy()
+    sim.simulate(); torch.cuda.synchronize()
+    orc.simulate(r64, d64, target=t64, obj=o64, obj_force=f.astype(np.float64))
+    rg = sim.root_state.cpu().numpy().astype(np.float64).reshape(n, 3, 13)
+    assert np.abs(rg[:, 1, :3] - o64[:, :3]).max() < 5e-5
+    verr = np.abs(rg[:, 1, 7:] - o64[:, 7:]) / np.maximum(1.0, np.abs(o64[:, 7:]))
+    assert verr.max() < 5e-3, verr.max()
+    # the force matters (the oracle without it lands elsewhere) ...
+    orc.simulate(r2, d2, target=t64, obj=o_no)
+    assert np.abs(o_no[:, 7:10] - o64[:, 7:10]).max() > 0.05
+    # ... and in free flight it is exactly Newton: dv = (g + R f / m) dt  (the body-frame force turns with the cube: tolerance for the spin)
+    from isaacgymenvs_b200.importer import rot
+    fl = slice(n // 2, n)
+    R = np.stack([rot.quat_to_mat(q) for q in o_in[fl, 3:7]])
+    dv = (rg[fl, 1, 7:10] - o_in[fl, 7:10]) / DT
+    want = np.array([0.0, 0.0, -9.81]) + np.einsum("nij,nj->ni", R, f[fl].astype(np.float64)) / obj["mass"]
+    assert np.abs(dv - want).max() < 0.05 * np.abs(want).max()
+    sim.close()

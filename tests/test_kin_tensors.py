@@ -200,9 +200,9 @@ def test_gpu_kinematic_tensors_match_oracle(name, n):
     assert np.isfinite(Jg).all() and np.isfinite(Mg).all()
     assert np.abs(Jg[idx] - Jo).max() < J_TOL, np.abs(Jg[idx] - Jo).max()
     assert np.abs(Mg[idx] - Mo).max() < M_RTOL * np.abs(Mo).max(), (np.abs(Mg[idx] - Mo).max(), np.abs(Mo).max())
-    # ... and equals the host twin of the same arithmetic to rounding of the library trig
+    # ... and equals the host twin of the same arithmetic up to FMA contraction and the library sincos (deep chains accumulate it)
     Jh, Mh = _host_tensors(m, rs[idx, 0], ds[idx])
-    assert np.abs(Jg[idx] - Jh).max() < 2e-6 and np.abs(Mg[idx] - Mh).max() < 2e-6 * np.abs(Mo).max()
+    assert np.abs(Jg[idx] - Jh).max() < 5e-6 and np.abs(Mg[idx] - Mh).max() < 1e-5 * np.abs(Mo).max()
     # size-independent properties on ALL envs: symmetric positive-definite M; the twist J u of every body equals the
     # rigid-body-state tensor's velocities (forward-kinematics kernel, independent code)
     assert float((M - M.transpose(1, 2)).abs().max()) <= 1e-6 * float(M.abs().max())

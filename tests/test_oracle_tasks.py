@@ -117,11 +117,11 @@ def test_anymal_terrain_restatement_matches_reference_methods():
 
 # ---------------------------------------------------------------------------------------------
 # ShadowHand: numpy restatement against the reference's own methods (tests/golden/shadow_hand.npz)
-@pytest.mark.parametrize("case", ["a", "b", "c"])
+@pytest.mark.parametrize("case", ["a", "b", "c", "f"])
 def test_hand_step_restatement_matches_reference(case):
     from tests.hand_common import golden_case, hand_setup, DT, SUBSTEPS, G as GRAV
     from oracle.oracle import OracleSim
-    gold = np.load(os.path.join(G, "shadow_hand.npz"))
+    gold = np.load(os.path.join(G, "shadow_hand_force.npz" if case == "f" else "shadow_hand.npz"))
     obs_types = ["full_state", "full", "full_no_vel", "openai"] if case == "a" else ["full_state"]
     m, obj, tendons = hand_setup()
     orc = OracleSim(m, DT, SUBSTEPS, GRAV, obj=obj, tendons=tendons)
@@ -135,6 +135,10 @@ def test_hand_step_restatement_matches_reference(case):
         np.testing.assert_allclose(st["goal_states"], out("goal_states"), rtol=0, atol=2e-7)
         np.testing.assert_allclose(st["cur_targets"], out("cur_targets"), rtol=0, atol=3e-7)
         np.testing.assert_allclose(st["prev_targets"], out("prev_targets"), rtol=0, atol=3e-7)
+        if case == "f":       # random forces on the object (:700-709): decayed, zeroed on reset, redrawn where rand < prob
+            np.testing.assert_allclose(st["obj_force"], out("obj_force"), rtol=2e-6, atol=1e-8)
+            np.testing.assert_allclose(st["force_prob"], out("force_prob"), rtol=2e-6)
+            assert float(out("other_forces")) == 0.0 and (out("obj_force") != 0).any(1).sum() > 100
         ds = out("dof_state").reshape(n, -1, 2)
         np.testing.assert_allclose(st["dof_pos"], ds[..., 0], rtol=0, atol=2e-7)
         np.testing.assert_allclose(st["dof_vel"], ds[..., 1], rtol=0, atol=2e-7)
