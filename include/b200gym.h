@@ -96,6 +96,10 @@ typedef struct {
     float ten_coef[B2G_MAX_TENDONS][2], ten_range[B2G_MAX_TENDONS][2];
     float ten_k, ten_d;
     float obj_angular_damping, obj_linear_damping;   /* the object's own AssetOptions (defaults 0.5 / 0, shadow_hand.py:279-282) */
+    /* The object is a ROUNDED box: every point within obj_round of the box obj_half.  0 = the block (cube_multicolor.urdf);
+     * obj_half = (0, 0, L), obj_round = r is a capsule along z (objectType pen, open_ai_assets/hand/pen.xml:19);
+     * a prolate spheroid (objectType egg, egg.xml:10) is carried as the capsule with the same polar and equatorial extent. */
+    float obj_round, pad_round;
 } b2g_model_ext;
 
 /* gymapi.SimParams subset that changes the physics (tasks/base/vec_task.py:514-562) */

@@ -18,6 +18,8 @@ KNOWN = {
     "urdf/anymal_c/urdf/anymal_minimal.urdf": "anymal",
     "mjcf/open_ai_assets/hand/shadow_hand.xml": "shadow_hand",
     "urdf/objects/cube_multicolor.urdf": "cube",
+    "mjcf/open_ai_assets/hand/egg.xml": "egg",
+    "mjcf/open_ai_assets/hand/pen.xml": "pen",
 }
 
 

@@ -16,6 +16,9 @@ SPECS = {
                     BuildOptions(fix_base_link=True, collapse_fixed_joints=True, disable_gravity=True, angular_damping=0.01,
                                  capsule_mid_spheres=1)),
     "cube": ("urdf/objects/cube_multicolor.urdf", BuildOptions()),
+    # ShadowHand objectType egg / pen (shadow_hand.py:91-95; object_asset_options = gymapi.AssetOptions(), :279)
+    "egg": ("mjcf/open_ai_assets/hand/egg.xml", BuildOptions()),
+    "pen": ("mjcf/open_ai_assets/hand/pen.xml", BuildOptions()),
     "anymal": ("urdf/anymal_c/urdf/anymal_minimal.urdf",
                BuildOptions(collapse_fixed_joints=True, replace_cylinder_with_capsule=True, density=0.001,
                             default_dof_drive_mode=DRIVE_EFFORT)),

@@ -130,6 +130,8 @@ class _Sim:
         self.engine = None
         self.num_actors = 0
         self.frame = 0
+        self.obj_force = None       # engine tensor behind apply_rigid_body_force_tensors (the free object's row), once used
+        self.obj_force_set = False
 
 
 class _Tensor:
@@ -191,10 +193,10 @@ class Gym:
                     continue
                 if obj is not None or k != 0:
                     raise NotImplementedError("one simulated free object per env, created right after the articulation")
-                if len(xm.geom_type) != 1 or int(xm.geom_type[0]) != 2:
-                    raise NotImplementedError("the free object must be a single box primitive")
+                from ..tasks.shadow_hand import object_shape      # box / capsule / sphere / prolate spheroid -> rounded box
+                half, rnd = object_shape(xm)
                 obj = dict(mass=float(xm.mass[0]), inertia=[float(xm.inertia[0][c]) for c in range(3)],
-                           half=[float(v) for v in np.asarray(xm.geom_size)[0][:3]], mu=float(xa.shape_props[0].friction), gravity_on=1,
+                           half=half, round=rnd, mu=float(xa.shape_props[0].friction), gravity_on=1,
                            angular_damping=float(xa.options.angular_damping), linear_damping=float(xa.options.linear_damping))
                 obj_row = 1
             tend = [dict(t) for t, tp in zip(model.tendons or [], a.tendon_props) if tp.limit_stiffness > 0.0]
@@ -216,6 +218,8 @@ class Gym:
 
     def simulate(self, sim):
         sim.engine.simulate()
+        if sim.obj_force_set:       # applied forces act for one simulate() (the caller re-applies them every step, shadow_hand.py:708)
+            sim.obj_force.zero_(); sim.obj_force_set = False
         sim.frame += 1
 
     def fetch_results(self, sim, wait):
@@ -446,10 +450,36 @@ class Gym:
         sim.engine.dof_target.view(-1, nd)[i] = t.view(-1, nd)[i]
         return True
 
-    def apply_rigid_body_force_tensors(self, sim, forces=None, torques=None, space=ENV_SPACE):   # shadow_hand.py:709
-        for t in (forces, torques):
-            if t is not None and bool((t != 0).any()):
-                raise NotImplementedError("external rigid-body forces are not applied by the engine")
+    def apply_rigid_body_force_tensors(self, sim, forces=None, torques=None, space=ENV_SPACE):   # shadow_hand.py:708
+        """Forces at the centre of mass for the next simulate().  The engine applies them to the simulated free object of an
+        env (the body the reference pushes); a non-zero force on an articulation link or any torque raises."""
+        if torques is not None and bool((torques != 0).any()):
+            raise NotImplementedError("apply_rigid_body_force_tensors: torques are not applied by the engine")
+        if forces is None:
+            return True
+        eng = sim.engine
+        n, nb = eng.num_envs, sim.asset.model.nb
+        f = forces.view(n, -1, 3)
+        if f.shape[1] != nb + len(sim.extra_assets):
+            raise ValueError("apply_rigid_body_force_tensors: expected one row per rigid body of the sim")
+        has_obj = eng.actors_per_env > 1 and len(sim.extra_assets) > 0 and not sim.extra_assets[0].options.disable_gravity
+        others = f.clone()
+        if has_obj:
+            others[:, nb] = 0
+        if bool((others != 0).any()):
+            raise NotImplementedError("apply_rigid_body_force_tensors: only the free object of an env takes external forces")
+        if not has_obj:
+            return True
+        fo = f[:, nb].to(torch.float32)
+        if space != LOCAL_SPACE:                                # env / global axes -> the object's own frame
+            q = eng.root_state.view(n, eng.actors_per_env, 13)[:, 1, 3:7]
+            qv, qw = q[:, :3], q[:, 3:4]
+            a = fo * (2.0 * qw * qw - 1.0); b = torch.cross(qv, fo, dim=-1) * qw * 2.0
+            c = qv * (qv * fo).sum(-1, keepdim=True) * 2.0
+            fo = a - b + c                                      # quat_rotate_inverse, torch_jit_utils.py:72-81
+        if sim.obj_force is None:
+            sim.obj_force = eng._bind(engine.T_OBJ_FORCE, torch.zeros(n, 3, dtype=torch.float32, device=eng.root_state.device))
+        sim.obj_force.copy_(fo); sim.obj_force_set = True
         return True
 
     def set_actor_root_state_tensor(self, sim, t):

@@ -779,6 +779,10 @@ extern "C" int b2g_create_ext(const b2g_model *m, const b2g_model_ext *ext, cons
             h.obj_on = 1; h.obj_row = ext->obj_actor; h.obj_gravity_on = ext->obj_gravity_on;
             h.obj_mass = ext->obj_mass; h.obj_kn = ext->obj_kn; h.obj_cn = ext->obj_cn; h.obj_mu = ext->obj_mu;
             for (int c = 0; c < 3; c++) { h.obj_I[c] = ext->obj_inertia[c]; h.obj_half[c] = ext->obj_half[c]; }
+            h.obj_round = ext->obj_round;
+            if (ext->obj_round < 0.f || (ext->obj_round == 0.f && (ext->obj_half[0] <= 0.f || ext->obj_half[1] <= 0.f || ext->obj_half[2] <= 0.f))) {
+                delete s; return fail(B2G_E_INVALID, "b2g_create_ext: the object needs positive half extents, or a rounding radius");
+            }
             h.obj_acc = h.nacc; h.obj_pose_acc = h.nacc + h.lanes; h.nacc += h.lanes + 1;   // env-wide ids: one sum per lane, one pose
             // the object's gravity does not follow the articulation's disable_gravity flag (shadow_hand.py:239,279-282)
             for (int c = 0; c < 3; c++) h.obj_g[c] = ext->obj_gravity_on ? sp->gravity[c] : 0.f;

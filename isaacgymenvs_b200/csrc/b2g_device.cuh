@@ -127,6 +127,7 @@ struct alignas(16) DevModel {
     int obj_row;          // the object's row inside an env's actors
     int obj_acc, obj_pose_acc;             // accumulator indices: object inertia/bias sum, object pose of the sub-step
     float obj_mass, obj_I[3], obj_half[3], obj_kn, obj_cn, obj_mu, obj_g[3];
+    float obj_round;      // the object is the box obj_half inflated by this radius (0: block; capsule = segment + radius)
     float ten_k, ten_d;
     int box_link[MAX_BOX];
     float box_pos[MAX_BOX][3], box_R[MAX_BOX][9], box_half[MAX_BOX][3];   // link frame
@@ -970,7 +971,7 @@ struct Stepper {
             matvec(R, lp, pc);
             pc[0] += x[0]; pc[1] += x[1]; pc[2] += x[2];
             float pen, n[3];
-            if (!sphere_box(pc, cp.radius, P.c, P.Ro, hb, pen, n)) continue;
+            if (!sphere_box(pc, cp.radius + m->obj_round, P.c, P.Ro, hb, pen, n)) continue;     // rounded box: inflate the sphere instead
             const float r[3] = {pc[0] - cp.radius * n[0], pc[1] - cp.radius * n[1], pc[2] - cp.radius * n[2]};
             obj_contact_point<ACCUM>(P, r, n, pen, x, vw, vl, IA, pa, pl, aw, al, F, T);
         }
@@ -986,15 +987,21 @@ struct Stepper {
             const float bh[3] = {m->box_half[b][0], m->box_half[b][1], m->box_half[b][2]};
 #pragma unroll 1
             for (int cn = 0; cn < 8; cn++) {
+                if (obj_corner_dup(cn, hb)) continue;
                 const float lc[3] = {(cn & 1) ? hb[0] : -hb[0], (cn & 2) ? hb[1] : -hb[1], (cn & 4) ? hb[2] : -hb[2]};
                 float pc[3]; matvec(P.Ro, lc, pc);
                 pc[0] += P.c[0]; pc[1] += P.c[1]; pc[2] += P.c[2];
                 float pen, nout[3];
-                if (!sphere_box(pc, 0.f, xb, Rwb, bh, pen, nout)) continue;      // the corner is inside the link's box
+                if (!sphere_box(pc, m->obj_round, xb, Rwb, bh, pen, nout)) continue; // the corner (sphere) is inside the link's box
                 const float n[3] = {-nout[0], -nout[1], -nout[2]};              // the link is pushed away from the corner
-                obj_contact_point<ACCUM>(P, pc, n, pen, x, vw, vl, IA, pa, pl, aw, al, F, T);
+                const float rc[3] = {pc[0] + m->obj_round * n[0], pc[1] + m->obj_round * n[1], pc[2] + m->obj_round * n[2]};
+                obj_contact_point<ACCUM>(P, rc, n, pen, x, vw, vl, IA, pa, pl, aw, al, F, T);
             }
         }
+    }
+    // corners of a degenerate box (a zero half extent: the capsule's segment has two distinct corners): keep one of each
+    __device__ __forceinline__ static bool obj_corner_dup(int cn, const float hb[3]) {
+        return ((cn & 1) && hb[0] == 0.f) || ((cn & 2) && hb[1] == 0.f) || ((cn & 4) && hb[2] == 0.f);
     }
     // the object's own dynamics for this sub-step: summed contact terms + ground + rigid-body terms -> 6x6 solve -> integrate
     __device__ __forceinline__ void obj_advance(const RootState &rs, ObjState &ob) const {
@@ -1014,11 +1021,14 @@ struct Stepper {
         const float gn = m->obj_cn + h * m->obj_kn;
 #pragma unroll 1
         for (int cn = lane; cn < 8; cn += L) {
-            const float lc[3] = {(cn & 1) ? m->obj_half[0] : -m->obj_half[0], (cn & 2) ? m->obj_half[1] : -m->obj_half[1], (cn & 4) ? m->obj_half[2] : -m->obj_half[2]};
+            const float hbo[3] = {m->obj_half[0], m->obj_half[1], m->obj_half[2]};
+            if (obj_corner_dup(cn, hbo)) continue;
+            const float lc[3] = {(cn & 1) ? hbo[0] : -hbo[0], (cn & 2) ? hbo[1] : -hbo[1], (cn & 4) ? hbo[2] : -hbo[2]};
             float r[3]; matvec(P.Ro, lc, r);
             r[0] += P.c[0]; r[1] += P.c[1]; r[2] += P.c[2];
-            const float d = -(rs.rp[2] + r[2]);
+            const float d = m->obj_round - (rs.rp[2] + r[2]);            // the corner carries a sphere of the rounding radius
             if (d <= 0.f) continue;
+            r[2] -= m->obj_round;                                        // contact point: the sphere's lowest point
             float oxr[3]; cross(P.w, r, oxr);
             const float u[3] = {P.vO[0] + oxr[0], P.vO[1] + oxr[1], P.vO[2] + oxr[2]};
             const float Fn = m->obj_kn * d - gn * u[2];

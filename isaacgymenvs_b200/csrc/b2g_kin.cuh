@@ -14,7 +14,8 @@
 // Formulation (differs on purpose from the oracle's body-coordinate CRBA with 6x6 Pluecker transforms): everything in
 // WORLD-ALIGNED axes about the root origin O.  There a rigid body's inertia is ten additive numbers -- the inertia tensor
 // about O (6), mass x COM offset (3), mass (1) -- so the composite inertia of a sub-tree is a plain sum over descendants,
-// and M[i][j] = S_j . (Ic_i S_i) needs no transforms at all.
+// and M[i][j] = S_j . (Ic_i S_i) needs no transforms at all.  A joint's motion subspace about O is S = (sa ; sb) -- hinge (w ; x cross w),
+// slide (0 ; w), base coordinates (unit vectors) -- so the twist of a body origin p is (sa x p + sb ; sa) for every column kind.
 //
 // Work decomposition: ONE WARP PER ENVIRONMENT, lane = link (nl <= 32) for the kinematics / inertias, lane = body for the
 // body origins, lane = output column for the fills, so every global store is a contiguous run of one output row.  Lanes
@@ -25,6 +26,8 @@
 
 namespace b2g {
 
+constexpr int KIN_MAX_CHILD = 8;
+
 // constant tables of one articulation (built on the host by kin_build, b2g_kin_host.h)
 struct alignas(16) KinModel {
     int nl, nb, nbase, nc;          // links, bodies, base columns (0 fixed / 6 floating), columns
@@ -32,6 +35,7 @@ struct alignas(16) KinModel {
     int maxdepth, root_stride;      // tree depth; actors per env in the root-state tensor
     int parent[MAX_LINKS], depth[MAX_LINKS], slide[MAX_LINKS], body_link[MAX_LINKS];
     unsigned anc[MAX_LINKS];        // bit j set: link j (j >= 1) is link i itself or one of its ancestors
+    int nchild[MAX_LINKS], child[MAX_LINKS][KIN_MAX_CHILD];
     float R0[MAX_LINKS][9], lpos[MAX_LINKS][3], axis[MAX_LINKS][3], com[MAX_LINKS][3], Ic[MAX_LINKS][6];
     float mass[MAX_LINKS], armature[MAX_LINKS], body_pos[MAX_LINKS][3];
 };
@@ -40,9 +44,9 @@ struct alignas(16) KinModel {
 struct KinScratch {
     float R[MAX_LINKS][9];          // link frame, world axes
     float x[MAX_LINKS][3];          // link origin relative to the root origin O, world axes
-    float w[MAX_LINKS][3];          // joint axis, world axes
-    float sl[MAX_LINKS][3];         // hinge: velocity of the point at O per unit joint rate (x cross w); slide: unused
-    float in[MAX_LINKS][11];        // the link's own inertia about O: I (xx yy zz xy xz yz), m c (3), m
+    float sa[MAX_LINKS][3];         // motion subspace S = (sa ; sb) about O: hinge (w ; x cross w), slide (0 ; w)
+    float sb[MAX_LINKS][3];
+    float in[MAX_LINKS][11];        // inertia about O: I (xx yy zz xy xz yz), m c (3), m -- the link's own, then (phase 3) its sub-tree's
     float nf[MAX_LINKS][7];         // Ic_i S_i: angular momentum about O (3), linear momentum (3)
     float pb[MAX_LINKS][3];         // body-frame origins relative to O
     float cb[11];                   // composite inertia of the whole articulation (base block of M)
@@ -103,7 +107,7 @@ B2G_HD void kin_level(int i, int d, const KinModel &t, KinScratch &s) {
 
 // ---- phase 2: world joint axis, motion subspace, the link's own inertia about O
 B2G_HD void kin_link(int i, const KinModel &t, KinScratch &s) {
-    float R[9], x[3], w[3] = {0.f, 0.f, 0.f}, sl[3] = {0.f, 0.f, 0.f};
+    float R[9], x[3], w[3], sa[3] = {0.f, 0.f, 0.f}, sb[3] = {0.f, 0.f, 0.f};
 #pragma unroll
     for (int c = 0; c < 9; c++) R[c] = s.R[i][c];
 #pragma unroll
@@ -111,10 +115,11 @@ B2G_HD void kin_link(int i, const KinModel &t, KinScratch &s) {
     if (i > 0) {
         const float ax[3] = {t.axis[i][0], t.axis[i][1], t.axis[i][2]};
         matvec(R, ax, w);
-        if (!t.slide[i]) cross(x, w, sl);
+        if (!t.slide[i]) { cross(x, w, sb); sa[0] = w[0]; sa[1] = w[1]; sa[2] = w[2]; }
+        else { sb[0] = w[0]; sb[1] = w[1]; sb[2] = w[2]; }
     }
 #pragma unroll
-    for (int c = 0; c < 3; c++) { s.w[i][c] = w[c]; s.sl[i][c] = sl[c]; }
+    for (int c = 0; c < 3; c++) { s.sa[i][c] = sa[c]; s.sb[i][c] = sb[c]; }
     // inertia about the COM in world axes: R Ic R^T, then the parallel-axis term to O
     const float *I6 = t.Ic[i];
     const float Il[9] = {I6[0], I6[3], I6[4], I6[3], I6[1], I6[5], I6[4], I6[5], I6[2]};
@@ -135,41 +140,40 @@ B2G_HD void kin_link(int i, const KinModel &t, KinScratch &s) {
     s.in[i][9] = m;
 }
 
-// ---- phase 3: composite inertia of the sub-tree rooted at link i (sum over descendants), Ic_i S_i
-B2G_HD void kin_composite(int i, const KinModel &t, KinScratch &s) {
+// ---- phase 3 (once per tree level d = maxdepth - 1 .. 0): composite inertia of the sub-tree rooted at link i = its own + its
+// children's (already complete: they are one level deeper).  In place; a fixed order of the children keeps the sums reproducible.
+B2G_HD void kin_composite_level(int i, int d, const KinModel &t, KinScratch &s) {
+    if (i >= t.nl || t.depth[i] != d || t.nchild[i] == 0) return;
     float a[10];
 #pragma unroll
     for (int c = 0; c < 10; c++) a[c] = s.in[i][c];
-    for (int k = i + 1; k < t.nl; k++) {
-        const bool below = (i == 0) || ((t.anc[k] >> i) & 1u);
-        if (below) {
+    for (int q = 0; q < t.nchild[i]; q++) {
+        const int k = t.child[i][q];
 #pragma unroll
-            for (int c = 0; c < 10; c++) a[c] += s.in[k][c];
-        }
+        for (int c = 0; c < 10; c++) a[c] += s.in[k][c];
     }
+#pragma unroll
+    for (int c = 0; c < 10; c++) s.in[i][c] = a[c];
+}
+// ---- phase 4: Ic_i S_i = (angular momentum about O ; linear momentum) of the sub-tree moving with joint i at unit rate
+B2G_HD void kin_momentum(int i, const KinModel &t, KinScratch &s) {
     if (i == 0) {
 #pragma unroll
-        for (int c = 0; c < 10; c++) s.cb[c] = a[c];
+        for (int c = 0; c < 10; c++) s.cb[c] = s.in[0][c];
         return;
     }
-    const float w[3] = {s.w[i][0], s.w[i][1], s.w[i][2]}, mc[3] = {a[6], a[7], a[8]};
-    float n[3], f[3];
-    if (!t.slide[i]) {      // S = (w ; sl):  n = I_O w + mc x sl,  f = m sl - mc x w
-        const float sl[3] = {s.sl[i][0], s.sl[i][1], s.sl[i][2]};
-        float t1[3], t2[3];
-        cross(mc, sl, t1); cross(mc, w, t2);
-        n[0] = a[0] * w[0] + a[3] * w[1] + a[4] * w[2] + t1[0];
-        n[1] = a[3] * w[0] + a[1] * w[1] + a[5] * w[2] + t1[1];
-        n[2] = a[4] * w[0] + a[5] * w[1] + a[2] * w[2] + t1[2];
+    float a[10];
 #pragma unroll
-        for (int c = 0; c < 3; c++) f[c] = a[9] * sl[c] - t2[c];
-    } else {                // S = (0 ; w):   n = mc x w,  f = m w
-        cross(mc, w, n);
+    for (int c = 0; c < 10; c++) a[c] = s.in[i][c];
+    const float sa[3] = {s.sa[i][0], s.sa[i][1], s.sa[i][2]}, sb[3] = {s.sb[i][0], s.sb[i][1], s.sb[i][2]}, mc[3] = {a[6], a[7], a[8]};
+    // n = I_O sa + mc x sb,  f = m sb - mc x sa
+    float t1[3], t2[3];
+    cross(mc, sb, t1); cross(mc, sa, t2);
+    s.nf[i][0] = a[0] * sa[0] + a[3] * sa[1] + a[4] * sa[2] + t1[0];
+    s.nf[i][1] = a[3] * sa[0] + a[1] * sa[1] + a[5] * sa[2] + t1[1];
+    s.nf[i][2] = a[4] * sa[0] + a[5] * sa[1] + a[2] * sa[2] + t1[2];
 #pragma unroll
-        for (int c = 0; c < 3; c++) f[c] = a[9] * w[c];
-    }
-#pragma unroll
-    for (int c = 0; c < 3; c++) { s.nf[i][c] = n[c]; s.nf[i][3 + c] = f[c]; }
+    for (int c = 0; c < 3; c++) s.nf[i][3 + c] = a[9] * sb[c] - t2[c];
 }
 
 // ---- phase 2b: origin of body b's frame relative to O
@@ -191,7 +195,7 @@ struct KinCol {
     int base;               // 0..5: base column (world linear 0..2, world angular 3..5), -1: joint column
     int link, slide;        // joint column: its link
     unsigned anc;
-    float w[3], x[3], sl[3], n[3], f[3], arm;
+    float sa[3], sb[3], n[3], f[3], arm;      // the column's motion subspace about O and Ic S
 };
 B2G_HD KinCol kin_col(int c, const KinModel &t, const KinScratch &s) {
     KinCol k;
@@ -199,28 +203,25 @@ B2G_HD KinCol kin_col(int c, const KinModel &t, const KinScratch &s) {
     const int j = c < t.nbase ? 0 : c - t.nbase + 1;
     k.link = j; k.slide = t.slide[j]; k.anc = t.anc[j]; k.arm = t.armature[j];
 #pragma unroll
-    for (int a = 0; a < 3; a++) { k.w[a] = s.w[j][a]; k.x[a] = s.x[j][a]; k.sl[a] = s.sl[j][a]; k.n[a] = s.nf[j][a]; k.f[a] = s.nf[j][3 + a]; }
+    for (int a = 0; a < 3; a++) {
+        k.sa[a] = c < t.nbase ? ((c >= 3 && c - 3 == a) ? 1.f : 0.f) : s.sa[j][a];      // base: (0 ; e_c) linear, (e_c ; 0) angular
+        k.sb[a] = c < t.nbase ? ((c < 3 && c == a) ? 1.f : 0.f) : s.sb[j][a];
+        k.n[a] = s.nf[j][a]; k.f[a] = s.nf[j][3 + a];
+    }
     return k;
 }
 
 B2G_HD float kin_pick(const float v[3], int a) { return a == 0 ? v[0] : (a == 1 ? v[1] : v[2]); }   // no dynamic register indexing
 
-// the six entries (linear 3, angular 3) of body b's Jacobian block in column k
+// the six entries (linear 3, angular 3) of body b's Jacobian block in column k.  With S = (sa ; sb) about O the twist of a point p
+// riding on the joint's sub-tree is (sa x p + sb ; sa) -- hinge, slide and the six base coordinates alike (base: S = unit vectors,
+// every body rides on it) -- so the lanes of a warp run one branch-free expression.
 B2G_HD void kin_jac_col(int b, const KinCol &k, const KinModel &t, const KinScratch &s, float o[6]) {
     const float pb[3] = {s.pb[b][0], s.pb[b][1], s.pb[b][2]};
-    if (k.base >= 0) {      // v_b = v_0 + w_0 x (p_b - O):  columns (e_k ; 0) and (e_k x p_b ; e_k)
-        const int a = k.base < 3 ? k.base : k.base - 3;
-        const float e[3] = {a == 0 ? 1.f : 0.f, a == 1 ? 1.f : 0.f, a == 2 ? 1.f : 0.f};
-        if (k.base < 3) { o[0] = e[0]; o[1] = e[1]; o[2] = e[2]; o[3] = o[4] = o[5] = 0.f; }
-        else { cross(e, pb, o); o[3] = e[0]; o[4] = e[1]; o[5] = e[2]; }
-        return;
-    }
-    const bool on = (t.anc[t.body_link[b]] >> k.link) & 1u;     // the joint lies between the base and this body
-    if (!on) { o[0] = o[1] = o[2] = o[3] = o[4] = o[5] = 0.f; return; }
-    if (k.slide) { o[0] = k.w[0]; o[1] = k.w[1]; o[2] = k.w[2]; o[3] = o[4] = o[5] = 0.f; return; }
-    const float d[3] = {pb[0] - k.x[0], pb[1] - k.x[1], pb[2] - k.x[2]};
-    cross(k.w, d, o);
-    o[3] = k.w[0]; o[4] = k.w[1]; o[5] = k.w[2];
+    const bool on = k.base >= 0 || ((t.anc[t.body_link[b]] >> k.link) & 1u);     // the joint lies between the base and this body
+    float v[3]; cross(k.sa, pb, v);
+#pragma unroll
+    for (int c = 0; c < 3; c++) { o[c] = on ? v[c] + k.sb[c] : 0.f; o[3 + c] = on ? k.sa[c] : 0.f; }
 }
 
 // entry (row a, column k) of the mass matrix
@@ -242,16 +243,18 @@ B2G_HD float kin_mass_col(int a, const KinCol &k, const KinModel &t, const KinSc
     const int i = a - nb + 1;
     if (k.base >= 0) { const int kx = k.base < 3 ? k.base : k.base - 3; return k.base < 3 ? s.nf[i][3 + kx] : s.nf[i][kx]; }
     const int j = k.link;
-    float v;
-    if ((t.anc[i] >> j) & 1u) {             // column joint j on row link i's path:  S_j . (Ic_i S_i)
-        const float *n = s.nf[i], *f = s.nf[i] + 3;
-        v = k.slide ? k.w[0] * f[0] + k.w[1] * f[1] + k.w[2] * f[2]
-                    : k.w[0] * n[0] + k.w[1] * n[1] + k.w[2] * n[2] + k.sl[0] * f[0] + k.sl[1] * f[1] + k.sl[2] * f[2];
-    } else if ((k.anc >> i) & 1u) {         // the transpose:  S_i . (Ic_j S_j)
-        const float *w = s.w[i], *sl = s.sl[i];
-        v = t.slide[i] ? w[0] * k.f[0] + w[1] * k.f[1] + w[2] * k.f[2]
-                       : w[0] * k.n[0] + w[1] * k.n[1] + w[2] * k.n[2] + sl[0] * k.f[0] + sl[1] * k.f[1] + sl[2] * k.f[2];
-    } else return 0.f;                      // different branches of the tree
+    // S_deeper-or-equal's Ic S against the other's S: column joint j on row link i's path -> S_j . (Ic_i S_i); row link i on column
+    // joint j's path -> S_i . (Ic_j S_j); different branches of the tree -> 0.  Selected without branching: the lanes of a warp
+    // (columns) fall into all three cases in the same row.
+    const bool ja = (t.anc[i] >> j) & 1u, ib = (k.anc >> i) & 1u;
+    float v = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const float sa = ja ? k.sa[c] : s.sa[i][c], sb = ja ? k.sb[c] : s.sb[i][c];
+        const float n = ja ? s.nf[i][c] : k.n[c], f = ja ? s.nf[i][3 + c] : k.f[c];
+        v += sa * n + sb * f;
+    }
+    if (!(ja || ib)) v = 0.f;
     return i == j ? v + k.arm : v;
 }
 
@@ -283,21 +286,23 @@ __global__ void __launch_bounds__(WARPS * 32) kin_tensors_kernel(const KinModel 
         if (jac && lane < t.nb) kin_body(lane, t, s);
         __syncwarp();
         if (mass) {
-            if (lane < nl) kin_composite(lane, t, s);
+            for (int d = t.maxdepth - 1; d >= 0; d--) { kin_composite_level(lane, d, t, s); __syncwarp(); }
+            if (lane < nl) kin_momentum(lane, t, s);
             __syncwarp();
         }
         for (int c = lane; c < nc; c += 32) {                // one pass for nc <= 32, two for the largest floating trees
             const KinCol k = kin_col(c, t, s);
             if (mass) {
                 float *M = mass + (size_t)e * nc * nc + c;
-                for (int a = 0; a < nc; a++) M[(size_t)a * nc] = kin_mass_col(a, k, t, s);
+                for (int a = 0; a < nc; a++, M += nc) *M = kin_mass_col(a, k, t, s);
             }
             if (jac) {
                 float *J = jac + (size_t)e * t.rows * 6 * nc + c;
+                const size_t st = (size_t)nc;
                 for (int b = 0; b < t.rows; b++) {
                     float o[6]; kin_jac_col(t.row0 + b, k, t, s, o);
-#pragma unroll
-                    for (int r = 0; r < 6; r++) J[(size_t)(b * 6 + r) * nc] = o[r];
+                    J[0] = o[0]; J[st] = o[1]; J[2 * st] = o[2]; J[3 * st] = o[3]; J[4 * st] = o[4]; J[5 * st] = o[5];
+                    J += 6 * st;
                 }
             }
         }

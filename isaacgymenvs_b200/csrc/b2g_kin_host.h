@@ -25,6 +25,7 @@ static inline int kin_build(const b2g_model *m, int root_stride, KinModel &k) {
         k.anc[i] = i ? (k.anc[p] | (1u << i)) : 0u;
         if (k.depth[i] > k.maxdepth) k.maxdepth = k.depth[i];
         k.slide[i] = (i && m->jtype[i] == 1) ? 1 : 0;
+        if (i) { if (k.nchild[p] == KIN_MAX_CHILD) return -1; k.child[p][k.nchild[p]++] = i; }
         const float *q = m->lquat + 4 * i;
         float x = q[0], y = q[1], z = q[2], w = q[3], n = sqrtf(x * x + y * y + z * z + w * w);
         x /= n; y /= n; z /= n; w /= n;

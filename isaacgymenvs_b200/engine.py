@@ -82,7 +82,8 @@ class CModelExt(C.Structure):
                 ("box_quat", (C.c_float * 4) * 4), ("box_half", (C.c_float * 3) * 4),
                 ("nten", C.c_int32), ("ten_dof", (C.c_int32 * 2) * 4), ("ten_coef", (C.c_float * 2) * 4),
                 ("ten_range", (C.c_float * 2) * 4), ("ten_k", C.c_float), ("ten_d", C.c_float),
-                ("obj_angular_damping", C.c_float), ("obj_linear_damping", C.c_float)]
+                ("obj_angular_damping", C.c_float), ("obj_linear_damping", C.c_float),
+                ("obj_round", C.c_float), ("pad_round", C.c_float)]
 
 
 def object_contact_gains(mass):
@@ -93,7 +94,7 @@ def object_contact_gains(mass):
 
 
 def pack_model_ext(model, obj=None, actors_per_env=1, tendons=None, tendon_k=0.0, tendon_d=0.0):
-    """obj: dict(mass, inertia(3), half(3), mu, gravity_on) of the free box (actor 1), or None."""
+    """obj: dict(mass, inertia(3), half(3), mu, gravity_on[, round]) of the free (rounded) box (actor 1), or None."""
     ex = CModelExt()
     ex.actors_per_env = int(actors_per_env)
     ex.obj_actor = -1
@@ -102,6 +103,7 @@ def pack_model_ext(model, obj=None, actors_per_env=1, tendons=None, tendon_k=0.0
         ex.obj_mass = float(obj["mass"])
         ex.obj_angular_damping, ex.obj_linear_damping = float(obj.get("angular_damping", 0.0)), float(obj.get("linear_damping", 0.0))
         ex.obj_inertia = (C.c_float * 3)(*obj["inertia"]); ex.obj_half = (C.c_float * 3)(*obj["half"])
+        ex.obj_round = float(obj.get("round", 0.0))
         kn, cn = object_contact_gains(ex.obj_mass)
         ex.obj_kn, ex.obj_cn, ex.obj_mu = kn, cn, float(obj.get("mu", 1.0))
         bl = getattr(model, "box_link", None)

@@ -171,6 +171,8 @@ def load_mjcf(path, opts: BuildOptions = None, name=None):
             if ae.tag not in ("motor", "position", "general"):
                 continue
             a = defaults.resolve(ae, None)
+            if a["joint"] not in model.dof_names:      # an included file's actuator for a joint this file has no body for (pen.xml includes the hand's shared.xml)
+                continue
             names.append(a.get("name", a.get("joint", "")))
             joints.append(a["joint"]); kinds.append(ae.tag)
             gear.append(_floats(a.get("gear", "1"))[0])
@@ -191,6 +193,8 @@ def load_mjcf(path, opts: BuildOptions = None, name=None):
     ten = root.find("tendon")
     if ten is not None:
         for fe in ten.findall("fixed"):
+            if any(j.attrib["joint"] not in model.dof_names for j in fe.findall("joint")):
+                continue
             rng = _floats(fe.attrib.get("range", "0 0"))
             model.tendons.append({
                 "name": fe.attrib.get("name", ""),

@@ -15,6 +15,25 @@ RELEVANT_TENDONS = ["robot0:T_FFJ1c", "robot0:T_MFJ1c", "robot0:T_RFJ1c", "robot
 NUM_OBS = {"openai": 42, "full_no_vel": 77, "full": 157, "full_state": 211}                                     # shadow_hand.py:108-113
 
 
+def object_shape(model):
+    """(half extents, rounding radius) of the free object's contact shape -- a rounded box (include/b200gym.h b2g_model_ext):
+    box -> its half sizes; capsule (pen.xml:19) -> a segment along z + its radius; sphere -> a point + radius; a prolate
+    spheroid (egg.xml:10, size 0.03 0.03 0.04) -> the capsule with the same equatorial radius and polar extent."""
+    from ..importer.model import GEOM_SPHERE, GEOM_CAPSULE, GEOM_BOX, GEOM_ELLIPSOID
+    if len(model.geom_type) != 1:
+        raise NotImplementedError("the free object must be a single collision primitive")
+    t, sz = int(model.geom_type[0]), [float(v) for v in np.asarray(model.geom_size)[0]]
+    if t == GEOM_BOX:
+        return sz[:3], 0.0
+    if t == GEOM_CAPSULE:
+        return [0.0, 0.0, sz[1]], sz[0]
+    if t == GEOM_SPHERE:
+        return [0.0, 0.0, 0.0], sz[0]
+    if t == GEOM_ELLIPSOID and abs(sz[0] - sz[1]) < 1e-9 and sz[2] >= sz[0]:
+        return [0.0, 0.0, sz[2] - sz[0]], sz[0]
+    raise NotImplementedError("free object shape: box, capsule, sphere or a prolate spheroid along z")
+
+
 class ShadowHand(VecTask):
     def __init__(self, cfg, rl_device, sim_device, graphics_device_id, headless, virtual_screen_capture=False,
                  force_render=False):
@@ -41,8 +60,8 @@ class ShadowHand(VecTask):
         self.max_consecutive_successes = e["maxConsecutiveSuccesses"]
         self.av_factor = e.get("averFactor", 0.1)
         self.object_type = e["objectType"]
-        if self.object_type != "block":
-            raise NotImplementedError("objectType egg / pen: only the block (BASELINE.json config 5) has a contact model here")
+        assert self.object_type in ["block", "egg", "pen"]                                                      # shadow_hand.py:87
+        self.ignore_z = (self.object_type == "pen")                                                             # :89
         self.obs_type = e["observationType"]
         if self.obs_type not in NUM_OBS:
             raise Exception("Unknown type of observations!\\nobservationType should be one of: [openai, full_no_vel, full, full_state]")
@@ -65,7 +84,10 @@ class ShadowHand(VecTask):
                             capsule_mid_spheres=1)
         model = copy.deepcopy(load_asset_file(_asset_root(), a.get("assetFileName", "mjcf/open_ai_assets/hand/shadow_hand.xml"), opts))
         engine.warn_self_collision("ShadowHand", "shadow_hand.py:359 create_actor(..., i, -1, 0): the MJCF's own contact pairs, finger vs finger")
-        cube = load_asset_file(_asset_root(), a.get("assetFileNameBlock", "urdf/objects/cube_multicolor.urdf"), BuildOptions())
+        obj_file = {"block": a.get("assetFileNameBlock", "urdf/objects/cube_multicolor.urdf"),                  # :91-99
+                    "egg": a.get("assetFileNameEgg", "mjcf/open_ai_assets/hand/egg.xml"),
+                    "pen": a.get("assetFileNamePen", "mjcf/open_ai_assets/hand/pen.xml")}[self.object_type]
+        cube = load_asset_file(_asset_root(), obj_file, BuildOptions())
         self.fingertip_handles_np = np.array([model.body_names.index(n) for n in self.fingertips], dtype=np.int32)
         model.sensor_body = self.fingertip_handles_np.copy()                                                   # :292-296
         model.sensor_pos = np.zeros((5, 3)); model.sensor_quat = np.tile([0, 0, 0, 1.0], (5, 1))
@@ -74,8 +96,8 @@ class ShadowHand(VecTask):
         names = list(model.dof_names)
         self.actuated_dof_indices_np = np.array([names.index(j) for j in model.actuator_joint], dtype=np.int32)  # :268-269
         self.object_model = cube
-        half = [float(v) for v in np.asarray(cube.geom_size)[0][:3]]                                           # box half extents
-        self._obj = dict(mass=float(cube.mass[0]), inertia=[float(cube.inertia[0][k]) for k in range(3)], half=half,
+        half, rnd = object_shape(cube)
+        self._obj = dict(mass=float(cube.mass[0]), inertia=[float(cube.inertia[0][k]) for k in range(3)], half=half, round=rnd,
                          mu=1.0, gravity_on=1,
                          # object_asset_options = gymapi.AssetOptions() (shadow_hand.py:279): the defaults angular_damping 0.5, linear 0
                          angular_damping=0.5, linear_damping=0.0)
@@ -193,7 +215,8 @@ class ShadowHand(VecTask):
         p.act_moving_average = float(self.act_moving_average)
         p.dt = float(self.dt)
         p.dist_reward_scale, p.rot_reward_scale, p.rot_eps = float(self.dist_reward_scale), float(self.rot_reward_scale), float(self.rot_eps)
-        p.action_penalty_scale, p.success_tolerance = float(self.action_penalty_scale), float(self.success_tolerance)
+        # compute_hand_reward doubles the tolerance when ignore_z_rot (the pen), shadow_hand.py:758-759
+        p.action_penalty_scale, p.success_tolerance = float(self.action_penalty_scale), float(self.success_tolerance) * (2.0 if self.ignore_z else 1.0)
         p.reach_goal_bonus, p.fall_dist, p.fall_penalty = float(self.reach_goal_bonus), float(self.fall_dist), float(self.fall_penalty)
         p.av_factor = float(self.av_factor)
         p.vel_obs_scale, p.force_torque_obs_scale = float(self.vel_obs_scale), float(self.force_torque_obs_scale)

@@ -103,6 +103,9 @@ typedef struct {
     int self_on, pad3;
     const unsigned char *self_pairs;        /* ncp x ncp, 1 = this ordered pair may collide */
     double self_kn, self_cn, self_mu;       /* self_kn, self_cn: dimensionless (gains per pair from the reduced link mass and h) */
+    /* the free object is a ROUNDED box: all points within obj_round of the box obj_half (0: the block; half = (0,0,L) + round r:
+     * a capsule along z -- objectType pen, pen.xml:19; the egg's spheroid, egg.xml:10, is carried as the capsule of equal extent) */
+    double obj_round;
 } OracleModel;
 
 /* ---------------------------------------------------------------- small linear algebra */
@@ -480,7 +483,7 @@ static void substep(const OracleModel *m, real h, real *root, real *dof, const r
             real lp[3] = {(real)m->cp_pos[3 * n], (real)m->cp_pos[3 * n + 1], (real)m->cp_pos[3 * n + 2]}, wc[3], pen, nrm[3];
             mat3_vec(Rw[i], lp, wc); for (int k = 0; k < 3; k++) wc[k] += pw[i][k];
             real rad = (real)m->cp_radius[n];
-            if (!sphere_box(wc, rad, obj, Ro, hb, &pen, nrm)) continue;
+            if (!sphere_box(wc, rad + (real)m->obj_round, obj, Ro, hb, &pen, nrm)) continue;   /* rounded box = inflate the sphere */
             real pc[3] = {wc[0] - rad * nrm[0], wc[1] - rad * nrm[1], wc[2] - rad * nrm[2]};
             OBJ_CONTACT(i, m->cp_body[n], n, pc, nrm, pen, (real)m->obj_mu);
         }
@@ -492,21 +495,25 @@ static void substep(const OracleModel *m, real h, real *root, real *dof, const r
             real bh[3] = {(real)m->box_half[3 * b], (real)m->box_half[3 * b + 1], (real)m->box_half[3 * b + 2]};
             quat_to_mat(bq, Rb); mat3_mul(Rw[i], Rb, Rwb); mat3_vec(Rw[i], bp, xb); for (int k = 0; k < 3; k++) xb[k] += pw[i][k];
             for (int c = 0; c < 8; c++) {
-                real lc[3] = {(c & 1 ? hb[0] : -hb[0]), (c & 2 ? hb[1] : -hb[1]), (c & 4 ? hb[2] : -hb[2])}, pc[3], pen, nout[3];
+                if (((c & 1) && hb[0] == 0) || ((c & 2) && hb[1] == 0) || ((c & 4) && hb[2] == 0)) continue;   /* degenerate box: each distinct corner once */
+                real lc[3] = {(c & 1 ? hb[0] : -hb[0]), (c & 2 ? hb[1] : -hb[1]), (c & 4 ? hb[2] : -hb[2])}, pc[3], pen, nout[3], rr = (real)m->obj_round;
                 mat3_vec(Ro, lc, pc); for (int k = 0; k < 3; k++) pc[k] += obj[k];
-                if (!sphere_box(pc, 0, xb, Rwb, bh, &pen, nout)) continue;       /* corner inside the link's box */
+                if (!sphere_box(pc, rr, xb, Rwb, bh, &pen, nout)) continue;      /* corner (sphere of the rounding radius) inside the link's box */
                 real nrm[3] = {-nout[0], -nout[1], -nout[2]};                  /* force on the LINK pushes it away from the corner */
-                OBJ_CONTACT(i, m->box_body[b], -1, pc, nrm, pen, (real)m->obj_mu);
+                real pcs[3] = {pc[0] + rr * nrm[0], pc[1] + rr * nrm[1], pc[2] + rr * nrm[2]};
+                OBJ_CONTACT(i, m->box_body[b], -1, pcs, nrm, pen, (real)m->obj_mu);
             }
         }
 #undef OBJ_CONTACT
         /* S3: the object's corners against the ground */
         for (int c = 0; c < 8; c++) {
+            if (((c & 1) && hb[0] == 0) || ((c & 2) && hb[1] == 0) || ((c & 4) && hb[2] == 0)) continue;
             real lc[3] = {(c & 1 ? hb[0] : -hb[0]), (c & 2 ? hb[1] : -hb[1]), (c & 4 ? hb[2] : -hb[2])}, ro_[3], pc[3], hgt, nrm[3];
             mat3_vec(Ro, lc, ro_); for (int k = 0; k < 3; k++) pc[k] = ro_[k] + obj[k];
             ground(m, pc[0], pc[1], &hgt, nrm);
-            real d = -(pc[2] - hgt) * nrm[2];
+            real d = (real)m->obj_round - (pc[2] - hgt) * nrm[2];
             if (d <= 0) continue;
+            for (int k = 0; k < 3; k++) ro_[k] -= (real)m->obj_round * nrm[k];      /* contact point on the corner sphere */
             real wo_[3]; cross3(obj + 10, ro_, wo_);
             real u_[3] = {obj[7] + wo_[0], obj[8] + wo_[1], obj[9] + wo_[2]};
             real un_ = u_[0] * nrm[0] + u_[1] * nrm[1] + u_[2] * nrm[2], Fn_ = okn * d - ogn * un_;

@@ -21,10 +21,20 @@ def hand_setup():
     return m, obj, tendons
 
 
-def settled_states(n, steps, seed, precision="f64", threads=8):
-    """Contact-rich states: the cube dropped onto the hand while the fingers chase random targets (fp64 oracle)."""
+def object_dict(name):
+    """the free object of ShadowHand objectType block / egg / pen as the engine and the oracle take it"""
+    from isaacgymenvs_b200.tasks.shadow_hand import object_shape
+    om = load_compiled({"block": "cube"}.get(name, name))
+    half, rnd = object_shape(om)
+    return dict(mass=float(om.mass[0]), inertia=[float(om.inertia[0][k]) for k in range(3)], half=half, round=rnd, mu=1.0, gravity_on=1)
+
+
+def settled_states(n, steps, seed, precision="f64", threads=8, obj_name=None):
+    """Contact-rich states: the cube (or egg / pen) dropped onto the hand while the fingers chase random targets (fp64 oracle)."""
     from oracle.oracle import OracleSim
     m, obj, tendons = hand_setup()
+    if obj_name is not None:
+        obj = object_dict(obj_name)
     rng = np.random.default_rng(seed)
     orc = OracleSim(m, DT, SUBSTEPS, G, precision=precision, obj=obj, tendons=tendons, tendon_k=30.0, tendon_d=0.1, threads=threads)
     dt_ = np.float64 if precision == "f64" else np.float32

@@ -26,7 +26,8 @@ extern "C" int kin_host_tensors(const b2g_model *m, int root_stride, int N, cons
         for (int lane = 0; lane < nl; lane++) kin_link(lane, t, s);
         if (jac) for (int lane = 0; lane < t.nb; lane++) kin_body(lane, t, s);
         if (mass) {
-            for (int lane = 0; lane < nl; lane++) kin_composite(lane, t, s);
+            for (int lv = t.maxdepth - 1; lv >= 0; lv--) for (int lane = 0; lane < 32; lane++) kin_composite_level(lane, lv, t, s);
+            for (int lane = 0; lane < nl; lane++) kin_momentum(lane, t, s);
         }
         for (int c = 0; c < nc; c++) {
             const KinCol k = kin_col(c, t, s);

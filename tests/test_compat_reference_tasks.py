@@ -31,8 +31,13 @@ class _FakeSim:
                  E.T_DOF_FORCE: (N * max(self.nd, 1),), E.T_NET_CONTACT: (N * self.nb, 3)}[slot]
         return self.tensors.setdefault(slot, torch.zeros(*shape))
 
+    def _bind(self, slot, t):
+        self.tensors[slot] = t
+        return t
+
     def simulate(self):
         self.steps += 1
+        self.seen_obj_force = self.tensors[self.E.T_OBJ_FORCE].clone() if self.E.T_OBJ_FORCE in self.tensors else None
 
     def refresh_rigid_body_state(self):
         return self.acquire(self.E.T_RIGID_BODY_STATE)
@@ -130,6 +135,42 @@ def test_unmodified_reference_shadow_hand_runs_on_the_shim(compat_cpu):
     assert (rs[:, 2, 3:7].norm(dim=-1) - 1).abs().max() < 1e-5 and (rs[:, 2, 3:7] - torch.tensor([0.0, 0, 0, 1])).abs().max() > 1e-3
     assert (rs[:, 1, 0:3] - torch.tensor([0.0, -0.39, 0.6])).abs().max() < 0.011
     assert "consecutive_successes" in extras and "time_outs" in extras
+
+
+@needs_reference
+def test_reference_shadow_hand_random_forces_reach_the_engine(compat_cpu):
+    """env.forceScale > 0 (shadow_hand.py:700-709): the reference's own pre_physics_step calls
+    apply_rigid_body_force_tensors(rb_forces, None, LOCAL_SPACE); the shim hands the object's row to the engine for
+    exactly one simulate() and rejects forces it would silently drop."""
+    import importlib
+    from isaacgym import gymapi
+    mod = importlib.import_module("isaacgymenvs.tasks.shadow_hand")
+    n = 64
+    cfg = _cfg("ShadowHand", n)
+    cfg["env"]["forceScale"] = 2.0; cfg["env"]["forceProbRange"] = [0.5, 0.9]
+    env = mod.ShadowHand(cfg=cfg, rl_device="cpu", sim_device="cpu", graphics_device_id=-1, headless=True,
+                         virtual_screen_capture=False, force_render=False)
+    sim = env.sim.engine
+    torch.manual_seed(0)
+    env.step(2 * torch.rand(n, 20) - 1)
+    obj = int(env.object_rb_handles[0])
+    assert obj == sim.nb                                                   # the object's body follows the hand's bodies
+    drew = env.rb_forces[:, obj].abs().sum(-1) > 0
+    assert 0.3 * n < int(drew.sum()) < n                                   # rand < prob with prob in [0.5, 0.9]
+    assert torch.equal(sim.seen_obj_force, env.rb_forces[:, obj])          # what simulate() saw: the LOCAL_SPACE force, unchanged
+    assert float(sim.tensors[sim.E.T_OBJ_FORCE].abs().max()) == 0.0       # cleared after the step, as PhysX clears applied forces
+    gym = env.gym
+    bad = torch.zeros_like(env.rb_forces); bad[:, 3, 0] = 1.0
+    with pytest.raises(NotImplementedError):
+        gym.apply_rigid_body_force_tensors(env.sim, bad, None, gymapi.LOCAL_SPACE)
+    with pytest.raises(NotImplementedError):
+        gym.apply_rigid_body_force_tensors(env.sim, None, bad, gymapi.LOCAL_SPACE)
+    # ENV_SPACE forces are turned into the object's frame
+    f = torch.zeros_like(env.rb_forces); f[:, obj, 2] = 1.0
+    gym.apply_rigid_body_force_tensors(env.sim, f, None, gymapi.ENV_SPACE)
+    from isaacgymenvs.utils.torch_jit_utils import quat_rotate_inverse
+    q = sim.root_state.view(n, 3, 13)[:, 1, 3:7]
+    assert torch.allclose(sim.tensors[sim.E.T_OBJ_FORCE], quat_rotate_inverse(q, f[:, obj]), atol=1e-6)
 
 
 @needs_reference

@@ -719,3 +719,62 @@ def test_hand_object_force_physics_matches_oracle():
     want = np.array([0.0, 0.0, -9.81]) + np.einsum("nij,nj->ni", R, f[fl].astype(np.float64)) / obj["mass"]
     assert np.abs(dv - want).max() < 0.05 * np.abs(want).max()
     sim.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# ShadowHand objectType egg / pen (shadow_hand.py:84-99): the free object as a rounded box
+@pytest.mark.parametrize("name", ["pen", "egg"])
+def test_hand_rounded_object_simulate_matches_oracle(name):
+    """One gym.simulate() from contact-rich states of the hand with the pen (capsule) / the egg (spheroid carried as a capsule):
+    engine against oracle, same tolerances as the cube's test (tests/test_gpu_parity.py::test_hand_object_simulate_matches_oracle)."""
+    from isaacgymenvs_b200 import engine
+    from tests.hand_common import settled_states
+    from tests.test_gpu_parity import _hand_sim, _hand_load
+    n = 512
+    m, obj, tendons, orc, root, dof, o, tgt = settled_states(n, 40, 9, obj_name=name)
+    o[: n // 8, 2] = obj["round"] + 0.3 * obj["half"][2] + 0.001            # some on the ground, tilted
+    sim = _hand_sim(n, m, obj, tendons)
+    _hand_load(sim, root, dof, o, tgt)
+    rs = sim.root_state.cpu().numpy().astype(np.float64).reshape(n, 3, 13)
+    r64 = np.ascontiguousarray(rs[:, 0]); o64 = np.ascontiguousarray(rs[:, 1]); o_in = o64.copy()
+    d64 = sim.dof_state.cpu().numpy().astype(np.float64).reshape(n, m.ndof, 2)
+    t64 = sim.dof_target.cpu().numpy().astype(np.float64)
+    sim.simulate(); torch.cuda.synchronize()
+    out = orc.simulate(r64, d64, target=t64, obj=o64)
+    rg = sim.root_state.cpu().numpy().astype(np.float64).reshape(n, 3, 13)
+    dg = sim.dof_state.cpu().numpy().astype(np.float64).reshape(n, m.ndof, 2)
+    assert np.abs(rg[:, 1, :3] - o64[:, :3]).max() < 5e-5
+    qd = np.minimum(np.abs(rg[:, 1, 3:7] - o64[:, 3:7]).max(-1), np.abs(rg[:, 1, 3:7] + o64[:, 3:7]).max(-1))
+    assert qd.max() < 2e-4, qd.max()
+    verr = np.abs(rg[:, 1, 7:] - o64[:, 7:]) / np.maximum(1.0, np.abs(o64[:, 7:]))
+    assert verr.max() < 5e-3, verr.max()
+    assert np.abs(dg[..., 0] - d64[..., 0]).max() < 1e-4
+    qerr = np.abs(dg[..., 1] - d64[..., 1]) / np.maximum(1.0, np.abs(d64[..., 1]))
+    assert qerr.max() < 5e-3, qerr.max()
+    sg = sim.tensors[engine.T_FORCE_SENSOR].cpu().numpy().reshape(n, -1, 6)
+    assert np.abs(out["sensor"]).max() > 0.05                                            # the fingertips do touch the object
+    assert np.abs(sg - out["sensor"]).max() < 5e-3 * max(1.0, np.abs(out["sensor"]).max())
+    # the object was in contact in a good share of the envs (not a free-flight test)
+    g_only = o_in[:, 7:10] + np.array([0, 0, -9.81]) * 0.01667
+    assert (np.abs(o64[:, 7:10] - g_only).max(-1) > 1e-3).mean() > 0.3
+    sim.close()
+
+
+@pytest.mark.parametrize("name", ["pen", "egg"])
+def test_hand_env_with_egg_and_pen_runs(name):
+    """env.objectType egg / pen through make(): the object shape reaches the engine, the step stays finite, objects that fall
+    are reset, and the pen doubles the success tolerance (ignore_z_rot, shadow_hand.py:758-759)."""
+    env = _make("ShadowHand", 256, objectType=name)
+    assert env.object_type == name and env.ignore_z == (name == "pen")
+    assert env.sim.task.success_tolerance == np.float32(0.1 * (2.0 if name == "pen" else 1.0))
+    g = torch.Generator(device=env.device).manual_seed(1)
+    nres = 0
+    for k in range(120):
+        obs, rew, reset, extras = env.step(2 * torch.rand(256, 20, device=env.device, generator=g) - 1)
+        nres += int(reset.sum())
+    torch.cuda.synchronize()
+    assert torch.isfinite(obs["obs"]).all() and torch.isfinite(rew).all() and torch.isfinite(env.root_state_tensor).all()
+    assert nres > 0                                              # random actions drop the object sooner or later
+    z = env.root_state_tensor.view(256, 3, 13)[:, 1, 2]
+    assert float(z.min()) > -0.01                                # nothing tunnels through the ground
+    env.sim.close()

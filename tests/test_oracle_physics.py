@@ -404,3 +404,86 @@ def test_self_contact_forces_are_equal_and_opposite():
             break
     assert found >= 3
     print("block-Jacobi force asymmetry at h = 8.3 ms (with friction):", np.round(asym_task, 2))
+
+
+# ---------------------------------------------------------------------------------------------
+# ShadowHand objectType egg / pen: the free object as a ROUNDED box (capsule = segment + radius)
+def _obj_of(name):
+    from isaacgymenvs_b200.tasks.shadow_hand import object_shape
+    om = load_compiled(name)
+    half, rnd = object_shape(om)
+    return dict(mass=float(om.mass[0]), inertia=[float(om.inertia[0][k]) for k in range(3)], half=half, round=rnd, mu=1.0, gravity_on=1,
+                angular_damping=0.5), om
+
+
+def test_object_shapes_from_the_reference_assets():
+    pen, pm = _obj_of("pen"); egg, em = _obj_of("egg"); cube, _ = _obj_of("cube")
+    assert pen["half"] == [0.0, 0.0, 0.1] and pen["round"] == 0.008                 # pen.xml:19 capsule size="0.008 0.1"
+    assert egg["half"] == [0.0, 0.0, pytest.approx(0.01)] and egg["round"] == 0.03  # egg.xml:10 ellipsoid size="0.03 0.03 0.04"
+    assert cube["round"] == 0.0 and cube["half"] == [0.025, 0.025, 0.025]
+    # MuJoCo convention: mass = density 1000 x volume
+    r, L = 0.008, 0.1
+    assert pen["mass"] == pytest.approx(1000 * (np.pi * r * r * 2 * L + 4 / 3 * np.pi * r ** 3), rel=1e-9)
+    assert egg["mass"] == pytest.approx(1000 * 4 / 3 * np.pi * 0.03 * 0.03 * 0.04, rel=1e-9)
+    # spheroid inertia: I_xx = m (b^2 + c^2) / 5
+    assert egg["inertia"][0] == pytest.approx(egg["mass"] * (0.03 ** 2 + 0.04 ** 2) / 5, rel=1e-9)
+
+
+@pytest.mark.parametrize("name", ["pen", "egg"])
+def test_rounded_object_rests_on_the_ground_at_its_radius(name):
+    """lying and standing on the plane: the lowest point of the capsule touches, sunk by weight / (contacts x kn)"""
+    from tests.hand_common import hand_setup, DT, SUBSTEPS
+    m, _, _ = hand_setup()
+    obj, _ = _obj_of(name)
+    orc = OracleSim(m, DT, SUBSTEPS, G, obj=obj)
+    n = 2
+    root = np.zeros((n, 13)); root[:, 2] = 0.5; root[:, 3:7] = m.default_root_quat
+    dof = np.zeros((n, m.ndof, 2))
+    o = np.zeros((n, 13)); o[:, 0] = 1.0; o[:, 2] = 0.2
+    o[0, 3:7] = [np.sin(np.pi / 4), 0, 0, np.cos(np.pi / 4)]          # axis horizontal
+    o[1, 3:7] = [0, 0, 0, 1]                                          # axis vertical (unstable equilibrium, unperturbed)
+    for _ in range(300):
+        orc.simulate(root, dof, target=np.zeros((n, m.ndof)), obj=o)
+    kn = 10000.0 * obj["mass"]
+    sink = obj["mass"] * 9.81 / kn
+    L, r = obj["half"][2], obj["round"]
+    assert abs(o[0, 2] - (r - sink / 2)) < 1e-6 and abs(o[1, 2] - (L + r - sink)) < 1e-6
+    assert np.abs(o[:, 7:]).max() < 1e-9
+
+
+def test_pen_is_held_by_a_contact_sphere_along_its_whole_length():
+    """sphere against the capsule: the closest point of the SEGMENT decides, so a sphere pressing anywhere along the pen meets
+    it at distance r_sphere + r_pen (not only near the two end points); beyond the end the end cap's sphere decides"""
+    import copy
+    from tests.hand_common import hand_setup, DT, SUBSTEPS
+    from isaacgymenvs_b200.importer import rot
+    m0, _, _ = hand_setup()
+    m = copy.deepcopy(m0)
+    k = 0                                                          # one contact sphere of the hand, the others removed
+    li, b = int(m.cp_link[k]), int(m.cp_body[k])
+    for a in ("cp_link", "cp_body", "cp_pos", "cp_radius", "cp_mu"):
+        setattr(m, a, np.asarray(getattr(m, a))[k:k + 1].copy())
+    m.box_link = None
+    obj, _ = _obj_of("pen")
+    obj["gravity_on"] = 0
+    orc = OracleSim(m, DT, SUBSTEPS, (0.0, 0.0, 0.0), obj=obj)
+    root = np.zeros((1, 13)); root[:, 2] = 0.5; root[:, 3:7] = m.default_root_quat
+    # the sphere's world centre at q = 0 from the rigid-body state of the body riding on its link (body frame = link frame o offset)
+    assert int(m.body_link[b]) == li
+    bs = orc.body_states(root, np.zeros((1, m.ndof, 2)))[0, b]
+    Rl = rot.quat_to_mat(bs[3:7]) @ rot.quat_to_mat(np.asarray(m.body_quat[b])).T
+    c = bs[:3] - Rl @ np.asarray(m.body_pos[b]) + Rl @ np.asarray(m.cp_pos[0])
+    rad, L = float(m.cp_radius[0]), obj["half"][2]
+    gap = rad + obj["round"] - 0.002                               # 2 mm of overlap; the pen's axis along world z, offset in x
+    for along, touches in ((-0.08, True), (0.0, True), (0.06, True), (L + 0.5 * gap, True), (L + 1.01 * (rad + obj["round"]), False)):
+        dof = np.zeros((1, m.ndof, 2))
+        o = np.zeros((1, 13)); o[0, 3:7] = [0, 0, 0, 1]
+        o[0, :3] = c + np.array([gap if along <= L else 0.0, 0.0, along])     # beyond the end: straight above the cap
+        orc.simulate(root, dof, target=np.zeros((1, m.ndof)), obj=o)
+        v = o[0, 7:10]
+        if not touches:
+            assert np.abs(v).max() == 0.0
+        elif along <= L:
+            assert v[0] > 1e-3 and abs(v[2]) < 0.2 * v[0], (along, v)        # pushed away from the sphere, across the axis (friction adds a little along it once it spins)
+        else:
+            assert v[2] > 1e-3 and abs(v[0]) < 1e-9, (along, v)               # the end cap: pushed along the axis
