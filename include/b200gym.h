@@ -99,7 +99,11 @@ typedef struct {
     /* The object is a ROUNDED box: every point within obj_round of the box obj_half.  0 = the block (cube_multicolor.urdf);
      * obj_half = (0, 0, L), obj_round = r is a capsule along z (objectType pen, open_ai_assets/hand/pen.xml:19);
      * a prolate spheroid (objectType egg, egg.xml:10) is carried as the capsule with the same polar and equatorial extent. */
-    float obj_round, pad_round;
+    float obj_round;
+    /* the object's AssetOptions.max_angular_velocity (gymapi default 64 rad/s): its angular speed is clamped after every
+     * sub-step, 0 = no clamp.  Not cosmetic: a slender object (the pen: I_axial / I_transverse = 1 / 117) that is flicked into a
+     * fast tumble makes the explicitly integrated gyroscopic term diverge; PhysX bounds the same case by this clamp. */
+    float obj_max_angular_velocity;
 } b2g_model_ext;
 
 /* gymapi.SimParams subset that changes the physics (tasks/base/vec_task.py:514-562) */

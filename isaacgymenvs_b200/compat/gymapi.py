@@ -197,7 +197,8 @@ class Gym:
                 half, rnd = object_shape(xm)
                 obj = dict(mass=float(xm.mass[0]), inertia=[float(xm.inertia[0][c]) for c in range(3)],
                            half=half, round=rnd, mu=float(xa.shape_props[0].friction), gravity_on=1,
-                           angular_damping=float(xa.options.angular_damping), linear_damping=float(xa.options.linear_damping))
+                           angular_damping=float(xa.options.angular_damping), linear_damping=float(xa.options.linear_damping),
+                           max_angular_velocity=float(xa.options.max_angular_velocity))
                 obj_row = 1
             tend = [dict(t) for t, tp in zip(model.tendons or [], a.tendon_props) if tp.limit_stiffness > 0.0]
             ks = {(tp.limit_stiffness, tp.damping) for tp in a.tendon_props if tp.limit_stiffness > 0.0}

@@ -779,7 +779,7 @@ extern "C" int b2g_create_ext(const b2g_model *m, const b2g_model_ext *ext, cons
             h.obj_on = 1; h.obj_row = ext->obj_actor; h.obj_gravity_on = ext->obj_gravity_on;
             h.obj_mass = ext->obj_mass; h.obj_kn = ext->obj_kn; h.obj_cn = ext->obj_cn; h.obj_mu = ext->obj_mu;
             for (int c = 0; c < 3; c++) { h.obj_I[c] = ext->obj_inertia[c]; h.obj_half[c] = ext->obj_half[c]; }
-            h.obj_round = ext->obj_round;
+            h.obj_round = ext->obj_round; h.obj_max_angvel = ext->obj_max_angular_velocity;
             if (ext->obj_round < 0.f || (ext->obj_round == 0.f && (ext->obj_half[0] <= 0.f || ext->obj_half[1] <= 0.f || ext->obj_half[2] <= 0.f))) {
                 delete s; return fail(B2G_E_INVALID, "b2g_create_ext: the object needs positive half extents, or a rounding radius");
             }

@@ -127,6 +127,7 @@ struct alignas(16) DevModel {
     int obj_row;          // the object's row inside an env's actors
     int obj_acc, obj_pose_acc;             // accumulator indices: object inertia/bias sum, object pose of the sub-step
     float obj_mass, obj_I[3], obj_half[3], obj_kn, obj_cn, obj_mu, obj_g[3];
+    float obj_max_angvel; // the object's AssetOptions.max_angular_velocity (0: no clamp)
     float obj_round;      // the object is the box obj_half inflated by this radius (0: block; capsule = segment + radius)
     float ten_k, ten_d;
     int box_link[MAX_BOX];
@@ -1073,6 +1074,10 @@ struct Stepper {
         float axc[3], wxv[3]; cross(ao_w, P.c, axc); cross(ob.w, ob.v, wxv);
 #pragma unroll
         for (int c = 0; c < 3; c++) { ob.w[c] += h * ao_w[c]; ob.v[c] += h * (ao_l[c] + axc[c] + wxv[c]); }
+        if (m->obj_max_angvel > 0.f) {                              // the object's AssetOptions.max_angular_velocity
+            const float wn2 = dot3(ob.w, ob.w);
+            if (wn2 > m->obj_max_angvel * m->obj_max_angvel) { const float k = m->obj_max_angvel * rsqrtf(wn2); ob.w[0] *= k; ob.w[1] *= k; ob.w[2] *= k; }
+        }
 #pragma unroll
         for (int c = 0; c < 3; c++) ob.p[c] += h * ob.v[c];
         integrate_quat(ob.q, ob.w, h);

@@ -83,7 +83,7 @@ class CModelExt(C.Structure):
                 ("nten", C.c_int32), ("ten_dof", (C.c_int32 * 2) * 4), ("ten_coef", (C.c_float * 2) * 4),
                 ("ten_range", (C.c_float * 2) * 4), ("ten_k", C.c_float), ("ten_d", C.c_float),
                 ("obj_angular_damping", C.c_float), ("obj_linear_damping", C.c_float),
-                ("obj_round", C.c_float), ("pad_round", C.c_float)]
+                ("obj_round", C.c_float), ("obj_max_angular_velocity", C.c_float)]
 
 
 def object_contact_gains(mass):
@@ -104,6 +104,7 @@ def pack_model_ext(model, obj=None, actors_per_env=1, tendons=None, tendon_k=0.0
         ex.obj_angular_damping, ex.obj_linear_damping = float(obj.get("angular_damping", 0.0)), float(obj.get("linear_damping", 0.0))
         ex.obj_inertia = (C.c_float * 3)(*obj["inertia"]); ex.obj_half = (C.c_float * 3)(*obj["half"])
         ex.obj_round = float(obj.get("round", 0.0))
+        ex.obj_max_angular_velocity = float(obj.get("max_angular_velocity", 64.0))       # gymapi.AssetOptions default
         kn, cn = object_contact_gains(ex.obj_mass)
         ex.obj_kn, ex.obj_cn, ex.obj_mu = kn, cn, float(obj.get("mu", 1.0))
         bl = getattr(model, "box_link", None)

@@ -100,7 +100,8 @@ class ShadowHand(VecTask):
         self._obj = dict(mass=float(cube.mass[0]), inertia=[float(cube.inertia[0][k]) for k in range(3)], half=half, round=rnd,
                          mu=1.0, gravity_on=1,
                          # object_asset_options = gymapi.AssetOptions() (shadow_hand.py:279): the defaults angular_damping 0.5, linear 0
-                         angular_damping=0.5, linear_damping=0.0)
+                         # and max_angular_velocity 64 rad/s
+                         angular_damping=0.5, linear_damping=0.0, max_angular_velocity=64.0)
         self._tendons = [t for t in model.tendons if t["name"] in RELEVANT_TENDONS]                             # :255-266
         return model
 

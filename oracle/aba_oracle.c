@@ -106,6 +106,7 @@ typedef struct {
     /* the free object is a ROUNDED box: all points within obj_round of the box obj_half (0: the block; half = (0,0,L) + round r:
      * a capsule along z -- objectType pen, pen.xml:19; the egg's spheroid, egg.xml:10, is carried as the capsule of equal extent) */
     double obj_round;
+    double obj_max_angular_velocity;        /* the object's AssetOptions.max_angular_velocity: clamp after every sub-step (0: none) */
 } OracleModel;
 
 /* ---------------------------------------------------------------- small linear algebra */
@@ -653,6 +654,10 @@ static void substep(const OracleModel *m, real h, real *root, real *dof, const r
         spd6_solve(Ao, bo, ao);
         real wxv1[3]; cross3(obj + 10, obj + 7, wxv1);
         for (int k = 0; k < 3; k++) { obj[10 + k] += h * ao[k]; obj[7 + k] += h * (ao[3 + k] + wxv1[k]); }
+        if (m->obj_max_angular_velocity > 0) {
+            real wn2 = obj[10] * obj[10] + obj[11] * obj[11] + obj[12] * obj[12], mx = (real)m->obj_max_angular_velocity;
+            if (wn2 > mx * mx) { real k_ = mx / SQRT(wn2); obj[10] *= k_; obj[11] *= k_; obj[12] *= k_; }
+        }
         for (int k = 0; k < 3; k++) obj[k] += h * obj[7 + k];
         real w[3] = {obj[10], obj[11], obj[12]};
         real wn = SQRT(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]), th = wn * h, dq[4];

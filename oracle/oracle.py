@@ -40,7 +40,8 @@ class _CModel(C.Structure):
                 ("angular_damping", C.c_double), ("linear_damping", C.c_double), ("max_angular_velocity", C.c_double),
                 ("obj_angular_damping", C.c_double), ("obj_linear_damping", C.c_double),
                 ("self_on", C.c_int), ("pad3", C.c_int), ("self_pairs", C.c_void_p),
-                ("self_kn", C.c_double), ("self_cn", C.c_double), ("self_mu", C.c_double), ("obj_round", C.c_double)]
+                ("self_kn", C.c_double), ("self_cn", C.c_double), ("self_mu", C.c_double), ("obj_round", C.c_double),
+                ("obj_max_angular_velocity", C.c_double)]
 
 
 def object_contact_gains(mass):
@@ -104,6 +105,7 @@ class OracleSim:
             cm.obj_angular_damping, cm.obj_linear_damping = float(obj.get("angular_damping", 0.0)), float(obj.get("linear_damping", 0.0))
             cm.obj_inertia = (C.c_double * 3)(*obj["inertia"]); cm.obj_half = (C.c_double * 3)(*obj["half"])
             cm.obj_round = float(obj.get("round", 0.0))
+            cm.obj_max_angular_velocity = float(obj.get("max_angular_velocity", 64.0))      # gymapi.AssetOptions default
             kn, cn = object_contact_gains(cm.obj_mass)
             cm.obj_kn, cm.obj_cn, cm.obj_mu = kn, cn, float(obj.get("mu", 1.0))
             bl = getattr(m, "box_link", None)

@@ -487,3 +487,26 @@ def test_pen_is_held_by_a_contact_sphere_along_its_whole_length():
             assert v[0] > 1e-3 and abs(v[2]) < 0.2 * v[0], (along, v)        # pushed away from the sphere, across the axis (friction adds a little along it once it spins)
         else:
             assert v[2] > 1e-3 and abs(v[0]) < 1e-9, (along, v)               # the end cap: pushed along the axis
+
+
+def test_slender_object_in_a_fast_tumble_stays_bounded():
+    """The pen's inertia is 117 : 1; flicked into a tumble of hundreds of rad/s the explicitly integrated gyroscopic term diverged
+    (found by the settling run of the GPU parity test: NaN after 22 steps).  The object's AssetOptions.max_angular_velocity
+    (gymapi default 64 rad/s, the bound PhysX applies too) is consumed: |w| <= 64 and the flight stays ballistic."""
+    from tests.hand_common import hand_setup, DT, SUBSTEPS
+    m, _, _ = hand_setup()
+    obj, _ = _obj_of("pen")
+    obj["max_angular_velocity"] = 64.0
+    orc = OracleSim(m, DT, SUBSTEPS, G, obj=obj)
+    n = 4
+    root = np.zeros((n, 13)); root[:, 2] = 0.5; root[:, 3:7] = m.default_root_quat
+    dof = np.zeros((n, m.ndof, 2))
+    o = np.zeros((n, 13)); o[:, 0] = 2.0; o[:, 2] = 50.0; o[:, 6] = 1.0
+    o[:, 10:13] = [[300.0, 20.0, 150.0], [-50.0, 400.0, 30.0], [10.0, 10.0, 500.0], [60.0, 0.0, 20.0]]
+    vz = []
+    for k in range(120):
+        orc.simulate(root, dof, target=np.zeros((n, m.ndof)), obj=o)
+        vz.append(o[:, 9].copy())
+        assert np.isfinite(o).all() and np.linalg.norm(o[:, 10:13], axis=1).max() <= 64.0 + 1e-9
+    assert np.allclose(vz[-1], -9.81 * DT * 120, rtol=1e-9)
+    assert np.allclose(np.linalg.norm(o[:, 3:7], axis=1), 1.0, atol=1e-12)
