@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define B2G_VERSION 3
+#define B2G_VERSION 4
 #define B2G_MAX_LINKS 32
 #define B2G_MAX_CONTACT_POINTS 96
 #define B2G_MAX_BOXES 4

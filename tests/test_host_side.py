@@ -19,7 +19,7 @@ def test_library_builds_and_exports_the_declared_abi():
     assert declared == set(engine.EXPORTS), declared ^ set(engine.EXPORTS)
     for sym in declared:
         assert hasattr(lib, sym), sym
-    assert lib.b2g_version() == 3
+    assert lib.b2g_version() == 4
 
 
 def test_struct_layouts_match_header_sizes():

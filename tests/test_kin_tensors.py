@@ -256,3 +256,28 @@ def test_compat_gym_jacobian_and_mass_matrix_calls():
     # total mass on the base block's linear diagonal
     mass = float(load_compiled("ant").mass.sum())
     assert abs(float(mm[0, 0, 0]) - mass) < 1e-5 * mass and abs(float(mm[0, 2, 2]) - mass) < 1e-5 * mass
+
+
+@pytest.mark.parametrize("name", ["cartpole", "ant", "humanoid", "anymal"])
+def test_mass_matrix_is_the_inertia_the_aba_step_inverts(name):
+    """The oracle's mass matrix (CRBA) against the oracle's articulated-body algorithm (an O(n) recursion that never forms M):
+    from rest, without gravity and off the ground, one sub-step's accelerations a satisfy
+        (M + diag(h b + h^2 k)) a = (0 ; clip(tau) - k q)
+    -- the implicit joint damping / stiffness terms of the scheme join the diagonal, nothing else."""
+    m = load_compiled(name)
+    dt, sub = 0.0166, 2
+    h = dt / sub
+    orc = OracleSim(m, dt, sub, (0.0, 0.0, 0.0))
+    rng = np.random.default_rng(7)
+    nb = 0 if m.root_fixed else 6
+    for trial in range(4):
+        root, dof = random_state(m, rng, z=5.0)
+        root[7:] = 0; dof[:, 1] = 0
+        tau = rng.normal(size=m.ndof) * 3
+        qdd, ra, da = orc.forward_dynamics(root, dof, tau)
+        acc = np.concatenate([(ra[7:13] - root[7:13]) / h, qdd]) if nb else qdd
+        M = orc.mass_matrix(root[None], dof[None])[0]
+        A = M + np.diag(np.r_[np.zeros(nb), h * m.damping[1:] + h * h * m.stiffness[1:]])
+        rhs = np.r_[np.zeros(nb), np.clip(tau, -m.effort[1:], m.effort[1:]) - m.stiffness[1:] * dof[:, 0]]
+        res = A @ acc - rhs
+        assert np.abs(res).max() < 1e-9 * max(1.0, np.abs(rhs).max()), (name, trial, np.abs(res).max())

@@ -80,6 +80,7 @@ def main():
     ap.add_argument("--mini-epochs", type=int, default=4)      # HumanoidPPO.yaml: 5
     ap.add_argument("--critic-coef", type=float, default=2.0)  # HumanoidPPO.yaml: 4
     ap.add_argument("--self-collision", action="store_true")   # Humanoid: env.selfCollision=True
+    ap.add_argument("--env", default="", help="comma-separated overrides of cfg.task.env, e.g. objectType=pen,forceScale=2.0")
     args = ap.parse_args()
     import isaacgymenvs_b200
     dev = args.device
@@ -88,6 +89,16 @@ def main():
     if args.self_collision:
         from isaacgymenvs_b200 import config
         cfg = config.builtin_cfg(args.task, {"sim_device": dev, "rl_device": dev}); cfg["task"]["env"]["selfCollision"] = True
+    if args.env:
+        from isaacgymenvs_b200 import config
+        cfg = cfg or config.builtin_cfg(args.task, {"sim_device": dev, "rl_device": dev})
+        for kv in args.env.split(","):
+            k, v = kv.split("=")
+            try:
+                v = float(v) if "." in v or "e" in v.lower() else int(v)
+            except ValueError:
+                pass
+            cfg["task"]["env"][k] = v
     env = isaacgymenvs_b200.make(seed=args.seed, task=args.task, num_envs=args.num_envs, sim_device=dev, rl_device=dev, headless=True, cfg=cfg)
     N, O, A, T = env.num_envs, env.num_obs, env.num_acts, args.horizon
     net = ActorCritic(O, A, tuple(int(u) for u in args.units.split(","))).to(dev)
