@@ -90,7 +90,6 @@ __device__ __forceinline__ Stepper<L, HF, BLOCK, OBJ, SELF> make_stepper(const D
     st.gmodel = nullptr;
     st.dr_mass = nullptr; st.dr_dof = nullptr;
     st.scen = nullptr; st.scs = 1;
-    st.obj_fext[0] = st.obj_fext[1] = st.obj_fext[2] = 0.f;
     if (SELF) {
         if (sm->self_f4) st.scen = b2g_dyn_smem + (sm->ns * SLOT_F4 + sm->nacc * ACC_F4) * BLOCK + (threadIdx.x / L) * sm->self_f4;
         else { st.scen = b2g_dyn_smem + (sm->self_cell & 255) * SLOT_F4 * BLOCK + (threadIdx.x - lane + (sm->self_cell >> 8)); st.scs = BLOCK; }
@@ -143,7 +142,9 @@ __global__ void __launch_bounds__(BLOCK) simulate_kernel(const DevModel *__restr
     ObjState ob;
     if (OBJ) {
         load_obj(root_row + 13 * sm.obj_row, ob);
-        if (const float *of = (const float *)B.p[B2G_T_OBJ_FORCE]) { st.obj_fext[0] = of[3 * (size_t)e]; st.obj_fext[1] = of[3 * (size_t)e + 1]; st.obj_fext[2] = of[3 * (size_t)e + 2]; }
+        const float *of = (const float *)B.p[B2G_T_OBJ_FORCE];
+        if (of) st.set_obj_force(of[3 * (size_t)e], of[3 * (size_t)e + 1], of[3 * (size_t)e + 2]);
+        else st.set_obj_force(0.f, 0.f, 0.f);
     }
     const float2 *d = (const float2 *)B.p[B2G_T_DOF_STATE] + (size_t)e * nd;
     const float *act = (const float *)B.p[B2G_T_DOF_ACTUATION];

@@ -557,7 +557,6 @@ struct Stepper {
     const DevModel *gmodel;   // the model's copy in global memory (self-collision tables), may be null when self_on == 0
     const float *dr_mass;     // per-env physical parameters (vec_task.py:720-828 as arrays; null = the model's own): this env's link-mass
     const float4 *dr_dof;     // factors [nl] (inertia scales with the mass), and per DOF (damping, stiffness, lower, upper)
-    float obj_fext[3];        // OBJ: external force on the free object, in ITS frame, at its COM (apply_rigid_body_force_tensors LOCAL_SPACE)
     float4 *scen;             // this ENV's self-collision scratch, element i at scen[i * scs]: [0, ncp) sphere centres about O +
     int scs;                  // radius, [ncp].x hit count, [ncp + 1, ncp + 5) the overlapping pairs of this sub-step (SELF_HITS x uint16)
 
@@ -898,6 +897,12 @@ struct Stepper {
         }
         if (L > 1) __syncwarp();
     }
+    // external force on the free object, in ITS frame, at its COM (gym.apply_rigid_body_force_tensors LOCAL_SPACE), held over the
+    // sub-steps that follow: parked in the free row 5 of the pose accumulator (not in registers: the hand kernels sit at the
+    // register cap).  Call before the first substep(); obj_store_pose's barriers publish it to the env's lanes.
+    __device__ __forceinline__ void set_obj_force(float fx, float fy, float fz) const {
+        if (lane == 0) A4(m->obj_pose_acc, 5) = make_float4(fx, fy, fz, 0.f);
+    }
     __device__ __forceinline__ void obj_load_pose(ObjPose &P) const {
         const int ai = m->obj_pose_acc;
         const float4 a = A4(ai, 0), b = A4(ai, 1), c = A4(ai, 2), d = A4(ai, 3), e = A4(ai, 4);
@@ -1062,8 +1067,10 @@ struct Stepper {
 #pragma unroll
             for (int c = 0; c < 3; c++) { pao[c] += qa[c]; plo[c] += ql[c]; }
             // external force (object frame -> world) at the COM: wrench about O is (c x F ; F); biases carry minus the applied wrench
+            const float4 fe = A4(m->obj_pose_acc, 5);
+            const float fl[3] = {fe.x, fe.y, fe.z};
             float Fw[3], cxF[3];
-            matvec(Ro, obj_fext, Fw); cross(P.c, Fw, cxF);
+            matvec(Ro, fl, Fw); cross(P.c, Fw, cxF);
 #pragma unroll
             for (int c = 0; c < 3; c++) { pao[c] -= cxF[c]; plo[c] -= Fw[c]; }
         }

@@ -189,8 +189,8 @@ __global__ void __launch_bounds__(BLOCK) hand_step_kernel(const DevModel *__rest
         hand_force_update(P, gid, do_reset ? count + 1u : (uint32_t)rc[e], (uint32_t)progress, sm.obj_mass, prob, f);
         __syncwarp();                                   // every lane has read the old values
         if (w0) { of[0] = f[0]; of[1] = f[1]; of[2] = f[2]; *pb = prob; }
-        st.obj_fext[0] = f[0]; st.obj_fext[1] = f[1]; st.obj_fext[2] = f[2];
-    }
+        st.set_obj_force(f[0], f[1], f[2]);
+    } else st.set_obj_force(0.f, 0.f, 0.f);
 
     // ---- control_freq_inv x gym.simulate.  control_freq_inv == 0: no simulate (the observation then reads the
     // sensor / joint-force tensors as they stand); pins the task arithmetic against the reference's golden vectors
