@@ -970,6 +970,7 @@ struct Stepper {
                                                       int cp_first, int cp_step) const {
         ObjPose P; obj_load_pose(P);
         const float hb[3] = {m->obj_half[0], m->obj_half[1], m->obj_half[2]};
+        const float orad = m->obj_round;                   // read once: the sphere loop below is the hot loop of the hand kernels
 #pragma unroll 1
         for (int k = lk.cp_begin + cp_first; k < lk.cp_end; k += cp_step) {
             const CpC &cp = gr.cps[k];
@@ -977,7 +978,7 @@ struct Stepper {
             matvec(R, lp, pc);
             pc[0] += x[0]; pc[1] += x[1]; pc[2] += x[2];
             float pen, n[3];
-            if (!sphere_box(pc, cp.radius + m->obj_round, P.c, P.Ro, hb, pen, n)) continue;     // rounded box: inflate the sphere instead
+            if (!sphere_box(pc, cp.radius + orad, P.c, P.Ro, hb, pen, n)) continue;     // rounded box: inflate the sphere instead
             const float r[3] = {pc[0] - cp.radius * n[0], pc[1] - cp.radius * n[1], pc[2] - cp.radius * n[2]};
             obj_contact_point<ACCUM>(P, r, n, pen, x, vw, vl, IA, pa, pl, aw, al, F, T);
         }
@@ -998,9 +999,9 @@ struct Stepper {
                 float pc[3]; matvec(P.Ro, lc, pc);
                 pc[0] += P.c[0]; pc[1] += P.c[1]; pc[2] += P.c[2];
                 float pen, nout[3];
-                if (!sphere_box(pc, m->obj_round, xb, Rwb, bh, pen, nout)) continue; // the corner (sphere) is inside the link's box
+                if (!sphere_box(pc, orad, xb, Rwb, bh, pen, nout)) continue; // the corner (sphere) is inside the link's box
                 const float n[3] = {-nout[0], -nout[1], -nout[2]};              // the link is pushed away from the corner
-                const float rc[3] = {pc[0] + m->obj_round * n[0], pc[1] + m->obj_round * n[1], pc[2] + m->obj_round * n[2]};
+                const float rc[3] = {pc[0] + orad * n[0], pc[1] + orad * n[1], pc[2] + orad * n[2]};
                 obj_contact_point<ACCUM>(P, rc, n, pen, x, vw, vl, IA, pa, pl, aw, al, F, T);
             }
         }
@@ -1024,17 +1025,17 @@ struct Stepper {
             for (int c = 0; c < 3; c++) { pao[c] = t[21 + c]; plo[c] = t[24 + c]; }
         }
         // corners against the ground plane, dealt round-robin to the lanes
-        const float gn = m->obj_cn + h * m->obj_kn;
+        const float gn = m->obj_cn + h * m->obj_kn, orad = m->obj_round;
+        const float hbo[3] = {m->obj_half[0], m->obj_half[1], m->obj_half[2]};
 #pragma unroll 1
         for (int cn = lane; cn < 8; cn += L) {
-            const float hbo[3] = {m->obj_half[0], m->obj_half[1], m->obj_half[2]};
             if (obj_corner_dup(cn, hbo)) continue;
             const float lc[3] = {(cn & 1) ? hbo[0] : -hbo[0], (cn & 2) ? hbo[1] : -hbo[1], (cn & 4) ? hbo[2] : -hbo[2]};
             float r[3]; matvec(P.Ro, lc, r);
             r[0] += P.c[0]; r[1] += P.c[1]; r[2] += P.c[2];
-            const float d = m->obj_round - (rs.rp[2] + r[2]);            // the corner carries a sphere of the rounding radius
+            const float d = orad - (rs.rp[2] + r[2]);                     // the corner carries a sphere of the rounding radius
             if (d <= 0.f) continue;
-            r[2] -= m->obj_round;                                        // contact point: the sphere's lowest point
+            r[2] -= orad;                                                // contact point: the sphere's lowest point
             float oxr[3]; cross(P.w, r, oxr);
             const float u[3] = {P.vO[0] + oxr[0], P.vO[1] + oxr[1], P.vO[2] + oxr[2]};
             const float Fn = m->obj_kn * d - gn * u[2];
