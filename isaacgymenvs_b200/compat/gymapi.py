@@ -150,15 +150,23 @@ class Gym:
         sim.ground = plane_params
 
     def add_triangle_mesh(self, sim, vertices, triangles, params):
-        """anymal_terrain.py:196-208.  The engine collides with height fields, not general meshes: the mesh must come
-        from `terrain_utils.convert_heightfield_to_trimesh` (which tags its arrays with the samples they were built from);
-        the engine then gets the height field itself, placed at params.transform.p."""
+        """anymal_terrain.py:196-208.  The engine collides with height fields, not general meshes.  A mesh that comes from
+        `terrain_utils.convert_heightfield_to_trimesh` carries the samples it was built from (its arrays are tagged) and the
+        engine gets that height field itself; any other mesh is taken as a terrain surface z(x, y) and sampled onto a grid
+        (`terrain.trimesh_to_heightfield`: node spacing = the mesh's median edge; overhangs collapse to their upper surface).
+        Either way the field is placed at params.transform.p."""
         src = getattr(vertices, "source", None)
+        ox, oy = float(params.transform.p.x), float(params.transform.p.y)
         if src is None:
-            raise NotImplementedError("add_triangle_mesh: only meshes built by terrain_utils.convert_heightfield_to_trimesh "
-                                      "are supported (height-field collision)")
-        sim.terrain = dict(src, origin=(float(params.transform.p.x), float(params.transform.p.y)), z0=float(params.transform.p.z),
-                           friction=float(params.dynamic_friction))
+            from ..terrain import trimesh_to_heightfield
+            nv, nt = int(getattr(params, "nb_vertices", 0) or 0), int(getattr(params, "nb_triangles", 0) or 0)
+            v = np.asarray(vertices, dtype=np.float64).reshape(-1, 3); t = np.asarray(triangles).reshape(-1, 3)
+            if (nv and nv != len(v)) or (nt and nt != len(t)):
+                raise ValueError("add_triangle_mesh: nb_vertices / nb_triangles do not match the arrays")
+            src = trimesh_to_heightfield(v, t)
+            ox, oy = ox + src["offset"][0], oy + src["offset"][1]
+            src = {k: src[k] for k in ("height_field", "horizontal_scale", "vertical_scale")}
+        sim.terrain = dict(src, origin=(ox, oy), z0=float(params.transform.p.z), friction=float(params.dynamic_friction))
 
     def prepare_sim(self, sim):
         if sim.engine is not None:

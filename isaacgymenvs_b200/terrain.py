@@ -251,3 +251,62 @@ def convert_heightfield_to_trimesh(height_field_raw, horizontal_scale, vertical_
     src = dict(height_field=np.ascontiguousarray(hf, dtype=np.int16), horizontal_scale=float(horizontal_scale),
                vertical_scale=float(vertical_scale))
     return HeightfieldMesh(vertices, src), HeightfieldMesh(triangles, src)
+
+
+def trimesh_to_heightfield(vertices, triangles, horizontal_scale=None, vertical_scale=None, max_samples=8_000_000):
+    """A general terrain mesh for `gym.add_triangle_mesh` (anymal_terrain.py:196-208 passes flat vertex / index arrays): the
+    engine collides with height fields, so a mesh that is a terrain -- a surface z(x, y) over its bounding rectangle -- is
+    sampled onto a regular grid (the highest surface point above each grid node; nodes no triangle covers get the lowest
+    vertex).  Overhangs and caves are not representable and collapse to their upper surface.
+
+    horizontal_scale: grid spacing; default = the median horizontal edge length of the mesh (clipped to [0.02, 0.5] m), which
+    reproduces a mesh made from a height field node for node.  vertical_scale: int16 quantum; default keeps the range within
+    +-30000 quanta and is at most 1 mm.  Returns dict(height_field (nx, ny) int16, horizontal_scale, vertical_scale,
+    offset (x0, y0) of sample (0, 0) in the mesh's own coordinates)."""
+    v = np.asarray(vertices, dtype=np.float64).reshape(-1, 3)
+    t = np.asarray(triangles).astype(np.int64).reshape(-1, 3)
+    if len(t) == 0 or t.min() < 0 or t.max() >= len(v):
+        raise ValueError("trimesh_to_heightfield: empty mesh or triangle index out of range")
+    p = v[t]                                                       # (T, 3, 3)
+    if horizontal_scale is None:
+        e = np.concatenate([np.linalg.norm(p[:, a, :2] - p[:, b, :2], axis=1) for a, b in ((0, 1), (1, 2), (2, 0))])
+        e = e[e > 1e-9]
+        horizontal_scale = float(np.clip(np.round(np.median(e), 6), 0.02, 0.5)) if len(e) else 0.1     # float32 vertices: 0.1 arrives as 0.10000001
+    hs = float(horizontal_scale)
+    x0, y0 = float(v[:, 0].min()), float(v[:, 1].min())
+    nx = int(np.floor((v[:, 0].max() - x0) / hs + 1e-4)) + 1
+    ny = int(np.floor((v[:, 1].max() - y0) / hs + 1e-4)) + 1
+    if nx * ny > max_samples:
+        raise ValueError(f"trimesh_to_heightfield: {nx} x {ny} samples at spacing {hs}; pass a coarser horizontal_scale")
+    zlo = float(v[:, 2].min())
+    H = np.full((nx, ny), -np.inf)
+    # triangles in the order of their bounding-box size: the many small ones (a cell or two) are handled in bulk
+    g = (p[:, :, :2] - np.array([x0, y0])) / hs                    # grid coordinates
+    i0 = np.maximum(np.ceil(g[:, :, 0].min(1) - 1e-4).astype(np.int64), 0); i1 = np.minimum(np.floor(g[:, :, 0].max(1) + 1e-4).astype(np.int64), nx - 1)
+    j0 = np.maximum(np.ceil(g[:, :, 1].min(1) - 1e-4).astype(np.int64), 0); j1 = np.minimum(np.floor(g[:, :, 1].max(1) + 1e-4).astype(np.int64), ny - 1)
+    wi, wj = i1 - i0 + 1, j1 - j0 + 1
+    ok = (wi > 0) & (wj > 0)
+    a, b, c = g[:, 0], g[:, 1], g[:, 2]
+    det = (b[:, 0] - a[:, 0]) * (c[:, 1] - a[:, 1]) - (c[:, 0] - a[:, 0]) * (b[:, 1] - a[:, 1])
+    ok &= np.abs(det) > 1e-12                                      # vertical / degenerate triangles carry no height
+    for di in range(int(wi[ok].max()) if ok.any() else 0):
+        for dj in range(int(wj[ok].max())):
+            sel = np.nonzero(ok & (wi > di) & (wj > dj))[0]
+            if len(sel) == 0:
+                continue
+            gi, gj = i0[sel] + di, j0[sel] + dj
+            px, py = gi - a[sel, 0], gj - a[sel, 1]
+            l1 = (px * (c[sel, 1] - a[sel, 1]) - (c[sel, 0] - a[sel, 0]) * py) / det[sel]
+            l2 = ((b[sel, 0] - a[sel, 0]) * py - px * (b[sel, 1] - a[sel, 1])) / det[sel]
+            inside = (l1 >= -1e-4) & (l2 >= -1e-4) & (l1 + l2 <= 1 + 1e-4)         # nodes on an edge belong to both triangles
+            z = p[sel, 0, 2] + l1 * (p[sel, 1, 2] - p[sel, 0, 2]) + l2 * (p[sel, 2, 2] - p[sel, 0, 2])
+            np.maximum.at(H, (gi[inside], gj[inside]), z[inside])
+    H[~np.isfinite(H)] = zlo
+    zr = max(abs(float(H.max())), abs(float(H.min())), 1e-9)
+    if vertical_scale is None:
+        vertical_scale = min(1e-3, zr / 30000.0) if zr / 1e-3 <= 30000 else zr / 30000.0
+    q = np.rint(H / vertical_scale)
+    if np.abs(q).max() > 32767:
+        raise ValueError("trimesh_to_heightfield: heights exceed the int16 range at this vertical_scale")
+    return dict(height_field=np.ascontiguousarray(q.astype(np.int16)), horizontal_scale=hs, vertical_scale=float(vertical_scale),
+                offset=(x0, y0))

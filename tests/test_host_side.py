@@ -227,3 +227,56 @@ def test_self_collision_request_is_never_silent():
         engine.warn_self_collision("probe", "create_actor(..., 0, 0)")
         engine.warn_self_collision("probe", "create_actor(..., 0, 0)")
     assert len(rec) == 1 and issubclass(rec[0].category, engine.UnmodelledPhysicsWarning) and "self-collision" in str(rec[0].message)
+
+
+# ---------------------------------------------------------------------------------------------
+# general triangle-mesh terrain for gym.add_triangle_mesh: sampled onto the engine's height field
+def test_trimesh_terrain_is_sampled_back_onto_its_height_field():
+    from isaacgymenvs_b200 import terrain as T
+    rng = np.random.default_rng(0)
+    hf = (rng.integers(-40, 60, size=(23, 31))).astype(np.int16)
+    hs, vs = 0.25, 0.005
+    v, t = T.convert_heightfield_to_trimesh(hf, hs, vs, None)
+    # strip the tag: what a caller with its own mesh would pass (flat arrays, anymal_terrain.py:206)
+    v0, t0 = np.array(v, dtype=np.float32).flatten(order="C"), np.array(t, dtype=np.uint32).flatten(order="C")
+    out = T.trimesh_to_heightfield(v0, t0)
+    assert out["horizontal_scale"] == pytest.approx(hs) and out["offset"] == (0.0, 0.0)
+    rec = out["height_field"].astype(np.float64) * out["vertical_scale"]
+    assert rec.shape == hf.shape and np.abs(rec - hf * vs).max() <= 0.5 * out["vertical_scale"] + 1e-7
+    # a coarser grid over a tilted plane made of two triangles, not aligned with the origin
+    P = np.array([[1.0, -2.0, 0.1], [5.0, -2.0, 0.5], [5.0, 1.0, 0.8], [1.0, 1.0, 0.4]])
+    tri = np.array([[0, 1, 2], [0, 2, 3]])
+    o2 = T.trimesh_to_heightfield(P, tri, horizontal_scale=0.5)
+    gx = o2["offset"][0] + 0.5 * np.arange(o2["height_field"].shape[0]); gy = o2["offset"][1] + 0.5 * np.arange(o2["height_field"].shape[1])
+    want = 0.1 + 0.1 * (gx[:, None] - 1.0) + 0.1 * (gy[None, :] + 2.0)
+    assert np.abs(o2["height_field"] * o2["vertical_scale"] - want).max() <= 0.5 * o2["vertical_scale"] + 1e-9
+    # a box on a floor: the upper surface wins above the box, its vertical walls carry no height of their own
+    fl = np.array([[0, 0, 0], [4, 0, 0], [4, 4, 0], [0, 4, 0]], float); bx = np.array([[1, 1, 0.5], [3, 1, 0.5], [3, 3, 0.5], [1, 3, 0.5]], float)
+    walls = np.array([[1, 1, 0], [3, 1, 0], [3, 1, 0.5], [1, 1, 0.5]], float)
+    V = np.concatenate([fl, bx, walls]); F = np.array([[0, 1, 2], [0, 2, 3], [4, 5, 6], [4, 6, 7], [8, 9, 10], [8, 10, 11]])
+    o3 = T.trimesh_to_heightfield(V, F, horizontal_scale=0.5)
+    h3 = o3["height_field"] * o3["vertical_scale"]
+    assert h3.shape == (9, 9) and h3[4, 4] == pytest.approx(0.5, abs=1e-3) and h3[0, 0] == 0.0 and h3[2, 2] == pytest.approx(0.5, abs=1e-3) and h3[1, 4] == 0.0
+    with pytest.raises(ValueError):
+        T.trimesh_to_heightfield(V, np.array([[0, 1, 99]]))
+
+
+def test_compat_add_triangle_mesh_accepts_an_untagged_mesh():
+    from isaacgymenvs_b200.compat import gymapi
+    from isaacgymenvs_b200 import terrain as T
+    gym = gymapi.acquire_gym()
+    sp = gymapi.SimParams(); sp.dt = 0.005; sp.substeps = 1
+    sim = gym.create_sim(0, -1, gymapi.SIM_PHYSX, sp)
+    hf = (np.arange(12 * 9).reshape(12, 9) % 7).astype(np.int16)
+    v, t = T.convert_heightfield_to_trimesh(hf, 0.1, 0.005, None)
+    tp = gymapi.TriangleMeshParams()
+    tp.nb_vertices, tp.nb_triangles = v.shape[0], t.shape[0]
+    tp.transform.p.x, tp.transform.p.y, tp.transform.p.z = -2.0, -3.0, 0.0
+    tp.static_friction = tp.dynamic_friction = 0.9
+    gym.add_triangle_mesh(sim, np.array(v).flatten(), np.array(t).flatten(), tp)           # np.array(): the tag is gone
+    tr = sim.terrain
+    assert tr["origin"] == (-2.0, -3.0) and tr["friction"] == pytest.approx(0.9) and tr["height_field"].shape == (12, 9)
+    assert np.abs(tr["height_field"] * tr["vertical_scale"] - hf * 0.005).max() <= 0.5 * tr["vertical_scale"] + 1e-7
+    tp.nb_vertices = 5
+    with pytest.raises(ValueError):
+        gym.add_triangle_mesh(sim, np.array(v).flatten(), np.array(t).flatten(), tp)
