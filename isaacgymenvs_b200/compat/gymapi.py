@@ -153,7 +153,7 @@ class Gym:
         """anymal_terrain.py:196-208.  The engine collides with height fields, not general meshes.  A mesh that comes from
         `terrain_utils.convert_heightfield_to_trimesh` carries the samples it was built from (its arrays are tagged) and the
         engine gets that height field itself; any other mesh is taken as a terrain surface z(x, y) and sampled onto a grid
-        (`terrain.trimesh_to_heightfield`: node spacing = the mesh's median edge; overhangs collapse to their upper surface).
+        (`terrain.trimesh_to_heightfield`: node spacing from the mesh's edge lengths; overhangs collapse to their upper surface).
         Either way the field is placed at params.transform.p."""
         src = getattr(vertices, "source", None)
         ox, oy = float(params.transform.p.x), float(params.transform.p.y)

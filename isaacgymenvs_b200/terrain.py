@@ -259,7 +259,8 @@ def trimesh_to_heightfield(vertices, triangles, horizontal_scale=None, vertical_
     sampled onto a regular grid (the highest surface point above each grid node; nodes no triangle covers get the lowest
     vertex).  Overhangs and caves are not representable and collapse to their upper surface.
 
-    horizontal_scale: grid spacing; default = the median horizontal edge length of the mesh (clipped to [0.02, 0.5] m), which
+    horizontal_scale: grid spacing; default = the 40th percentile of the mesh's horizontal edge lengths (a grid mesh has two
+    axis-aligned edges for every diagonal; clipped to [0.02, 0.5] m), which
     reproduces a mesh made from a height field node for node.  vertical_scale: int16 quantum; default keeps the range within
     +-30000 quanta and is at most 1 mm.  Returns dict(height_field (nx, ny) int16, horizontal_scale, vertical_scale,
     offset (x0, y0) of sample (0, 0) in the mesh's own coordinates)."""
@@ -271,7 +272,7 @@ def trimesh_to_heightfield(vertices, triangles, horizontal_scale=None, vertical_
     if horizontal_scale is None:
         e = np.concatenate([np.linalg.norm(p[:, a, :2] - p[:, b, :2], axis=1) for a, b in ((0, 1), (1, 2), (2, 0))])
         e = e[e > 1e-9]
-        horizontal_scale = float(np.clip(np.round(np.median(e), 6), 0.02, 0.5)) if len(e) else 0.1     # float32 vertices: 0.1 arrives as 0.10000001
+        horizontal_scale = float(np.clip(np.round(np.percentile(e, 40), 6), 0.02, 0.5)) if len(e) else 0.1     # float32 vertices: 0.1 arrives as 0.10000001
     hs = float(horizontal_scale)
     x0, y0 = float(v[:, 0].min()), float(v[:, 1].min())
     nx = int(np.floor((v[:, 0].max() - x0) / hs + 1e-4)) + 1
