@@ -40,17 +40,61 @@ struct alignas(16) KinModel {
     float mass[MAX_LINKS], armature[MAX_LINKS], body_pos[MAX_LINKS][3];
 };
 
-// per-warp scratch; odd strides: lane-indexed accesses fall into different banks
+// per-warp scratch.  Everything a phase hands to another lane is packed into float4 rows: the profile of the first version
+// (profiles/r2_kin_humanoid_ncu_summary.json) showed the LSU pipe 77 % busy with 32-bit shared loads -- one 128-bit load moves
+// four of them.  Lane-indexed accesses at a stride of 3 float4 (12 words) are conflict-free per quarter-warp.
 struct KinScratch {
-    float R[MAX_LINKS][9];          // link frame, world axes
-    float x[MAX_LINKS][3];          // link origin relative to the root origin O, world axes
-    float sa[MAX_LINKS][3];         // motion subspace S = (sa ; sb) about O: hinge (w ; x cross w), slide (0 ; w)
-    float sb[MAX_LINKS][3];
-    float in[MAX_LINKS][11];        // inertia about O: I (xx yy zz xy xz yz), m c (3), m -- the link's own, then (phase 3) its sub-tree's
-    float nf[MAX_LINKS][7];         // Ic_i S_i: angular momentum about O (3), linear momentum (3)
-    float pb[MAX_LINKS][3];         // body-frame origins relative to O
-    float cb[11];                   // composite inertia of the whole articulation (base block of M)
+    float4 Rx[MAX_LINKS][3];        // row k: (R[k][0], R[k][1], R[k][2], x[k]) -- link frame in world axes, origin relative to the root origin O
+    float4 S[MAX_LINKS][3];         // (n.xyz, f.x) (f.yz, sa.xy) (sa.z, sb.xyz): Ic_i S_i = (n ; f) and the motion subspace S = (sa ; sb) about O
+    float4 in[MAX_LINKS][3];        // inertia about O: (Ixx Iyy Izz Ixy) (Ixz Iyz mcx mcy) (mcz m - -) -- the link's own, then its sub-tree's
+    float4 pb[MAX_LINKS];           // body-frame origin relative to O; .w = the ancestor mask of the body's link (bits)
+    float4 cb[3];                   // composite inertia of the whole articulation (base block of M), layout of `in`
 };
+
+B2G_HD float kin_u2f(unsigned u) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+B2G_HD unsigned kin_f2u(float f) {
+#ifdef __CUDA_ARCH__
+    return __float_as_uint(f);
+#else
+    unsigned u; memcpy(&u, &f, 4); return u;
+#endif
+}
+B2G_HD void kin_load_Rx(const KinScratch &s, int i, float R[9], float x[3]) {
+    const float4 a = s.Rx[i][0], b = s.Rx[i][1], c = s.Rx[i][2];
+    R[0] = a.x; R[1] = a.y; R[2] = a.z; R[3] = b.x; R[4] = b.y; R[5] = b.z; R[6] = c.x; R[7] = c.y; R[8] = c.z;
+    x[0] = a.w; x[1] = b.w; x[2] = c.w;
+}
+B2G_HD void kin_store_Rx(KinScratch &s, int i, const float R[9], const float x[3]) {
+    s.Rx[i][0] = make_float4(R[0], R[1], R[2], x[0]);
+    s.Rx[i][1] = make_float4(R[3], R[4], R[5], x[1]);
+    s.Rx[i][2] = make_float4(R[6], R[7], R[8], x[2]);
+}
+B2G_HD void kin_load_in(const float4 v[3], float a[10]) {
+    a[0] = v[0].x; a[1] = v[0].y; a[2] = v[0].z; a[3] = v[0].w; a[4] = v[1].x; a[5] = v[1].y; a[6] = v[1].z; a[7] = v[1].w; a[8] = v[2].x; a[9] = v[2].y;
+}
+B2G_HD void kin_store_in(float4 v[3], const float a[10]) {
+    v[0] = make_float4(a[0], a[1], a[2], a[3]); v[1] = make_float4(a[4], a[5], a[6], a[7]); v[2] = make_float4(a[8], a[9], 0.f, 0.f);
+}
+// the packed (n ; f ; sa ; sb) of link i
+struct KinS { float n[3], f[3], sa[3], sb[3]; };
+B2G_HD KinS kin_load_S(const KinScratch &s, int i) {
+    const float4 a = s.S[i][0], b = s.S[i][1], c = s.S[i][2];
+    KinS r;
+    r.n[0] = a.x; r.n[1] = a.y; r.n[2] = a.z; r.f[0] = a.w; r.f[1] = b.x; r.f[2] = b.y;
+    r.sa[0] = b.z; r.sa[1] = b.w; r.sa[2] = c.x; r.sb[0] = c.y; r.sb[1] = c.z; r.sb[2] = c.w;
+    return r;
+}
+B2G_HD void kin_store_S(KinScratch &s, int i, const KinS &r) {
+    s.S[i][0] = make_float4(r.n[0], r.n[1], r.n[2], r.f[0]);
+    s.S[i][1] = make_float4(r.f[1], r.f[2], r.sa[0], r.sa[1]);
+    s.S[i][2] = make_float4(r.sa[2], r.sb[0], r.sb[1], r.sb[2]);
+}
 
 // ---- phase 0: joint transform of link i in its parent's frame -> scratch (overwritten by the world frame in phase 1)
 B2G_HD void kin_local(int i, const KinModel &t, KinScratch &s, const float *root, float q) {
@@ -63,9 +107,8 @@ B2G_HD void kin_local(int i, const KinModel &t, KinScratch &s, const float *root
         R[0] = 1.f - 2.f * (y * y + z * z); R[1] = 2.f * (x * y - z * w); R[2] = 2.f * (x * z + y * w);
         R[3] = 2.f * (x * y + z * w); R[4] = 1.f - 2.f * (x * x + z * z); R[5] = 2.f * (y * z - x * w);
         R[6] = 2.f * (x * z - y * w); R[7] = 2.f * (y * z + x * w); R[8] = 1.f - 2.f * (x * x + y * y);
-#pragma unroll
-        for (int c = 0; c < 9; c++) s.R[0][c] = R[c];
-        s.x[0][0] = s.x[0][1] = s.x[0][2] = 0.f;
+        const float zero[3] = {0.f, 0.f, 0.f};
+        kin_store_Rx(s, 0, R, zero);
         return;
     }
     const float *R0 = t.R0[i], *ax = t.axis[i];
@@ -76,50 +119,42 @@ B2G_HD void kin_local(int i, const KinModel &t, KinScratch &s, const float *root
                              uy * ux * oc + uz * sn, cs + uy * uy * oc, uy * uz * oc - ux * sn,
                              uz * ux * oc - uy * sn, uz * uy * oc + ux * sn, cs + uz * uz * oc};
         float R[9]; matmul(R0, Rj, R);
-#pragma unroll
-        for (int c = 0; c < 9; c++) s.R[i][c] = R[c];
-#pragma unroll
-        for (int c = 0; c < 3; c++) s.x[i][c] = t.lpos[i][c];
+        const float lp[3] = {t.lpos[i][0], t.lpos[i][1], t.lpos[i][2]};
+        kin_store_Rx(s, i, R, lp);
     } else {
         float d[3]; matvec(R0, ax, d);
-#pragma unroll
-        for (int c = 0; c < 9; c++) s.R[i][c] = R0[c];
-#pragma unroll
-        for (int c = 0; c < 3; c++) s.x[i][c] = t.lpos[i][c] + d[c] * q;
+        const float R[9] = {R0[0], R0[1], R0[2], R0[3], R0[4], R0[5], R0[6], R0[7], R0[8]};
+        const float lp[3] = {t.lpos[i][0] + d[0] * q, t.lpos[i][1] + d[1] * q, t.lpos[i][2] + d[2] * q};
+        kin_store_Rx(s, i, R, lp);
     }
 }
 
 // ---- phase 1 (once per tree level d = 1 .. maxdepth): compose with the parent's world frame
-B2G_HD void kin_level(int i, int d, const KinModel &t, KinScratch &s) {
-    if (i >= t.nl || t.depth[i] != d) return;
-    const int p = t.parent[i];
-    float Rp[9], Rl[9], R[9], r[3], wr[3];
-#pragma unroll
-    for (int c = 0; c < 9; c++) { Rp[c] = s.R[p][c]; Rl[c] = s.R[i][c]; }
-#pragma unroll
-    for (int c = 0; c < 3; c++) r[c] = s.x[i][c];
+B2G_HD void kin_level_do(int i, int p, KinScratch &s) {
+    float Rp[9], xp[3], Rl[9], r[3], R[9], wr[3];
+    kin_load_Rx(s, p, Rp, xp); kin_load_Rx(s, i, Rl, r);
     matmul(Rp, Rl, R); matvec(Rp, r, wr);
-#pragma unroll
-    for (int c = 0; c < 9; c++) s.R[i][c] = R[c];
-#pragma unroll
-    for (int c = 0; c < 3; c++) s.x[i][c] = s.x[p][c] + wr[c];
+    const float x[3] = {xp[0] + wr[0], xp[1] + wr[1], xp[2] + wr[2]};
+    kin_store_Rx(s, i, R, x);
+}
+B2G_HD void kin_level(int i, int d, const KinModel &t, KinScratch &s) {
+    if (i < t.nl && t.depth[i] == d) kin_level_do(i, t.parent[i], s);
 }
 
 // ---- phase 2: world joint axis, motion subspace, the link's own inertia about O
 B2G_HD void kin_link(int i, const KinModel &t, KinScratch &s) {
-    float R[9], x[3], w[3], sa[3] = {0.f, 0.f, 0.f}, sb[3] = {0.f, 0.f, 0.f};
+    float R[9], x[3], w[3];
+    KinS S;
 #pragma unroll
-    for (int c = 0; c < 9; c++) R[c] = s.R[i][c];
-#pragma unroll
-    for (int c = 0; c < 3; c++) x[c] = s.x[i][c];
+    for (int c = 0; c < 3; c++) { S.n[c] = S.f[c] = S.sa[c] = S.sb[c] = 0.f; }
+    kin_load_Rx(s, i, R, x);
     if (i > 0) {
         const float ax[3] = {t.axis[i][0], t.axis[i][1], t.axis[i][2]};
         matvec(R, ax, w);
-        if (!t.slide[i]) { cross(x, w, sb); sa[0] = w[0]; sa[1] = w[1]; sa[2] = w[2]; }
-        else { sb[0] = w[0]; sb[1] = w[1]; sb[2] = w[2]; }
+        if (!t.slide[i]) { cross(x, w, S.sb); S.sa[0] = w[0]; S.sa[1] = w[1]; S.sa[2] = w[2]; }
+        else { S.sb[0] = w[0]; S.sb[1] = w[1]; S.sb[2] = w[2]; }
     }
-#pragma unroll
-    for (int c = 0; c < 3; c++) { s.sa[i][c] = sa[c]; s.sb[i][c] = sb[c]; }
+    kin_store_S(s, i, S);
     // inertia about the COM in world axes: R Ic R^T, then the parallel-axis term to O
     const float *I6 = t.Ic[i];
     const float Il[9] = {I6[0], I6[3], I6[4], I6[3], I6[1], I6[5], I6[4], I6[5], I6[2]};
@@ -130,62 +165,56 @@ B2G_HD void kin_link(int i, const KinModel &t, KinScratch &s) {
 #pragma unroll
     for (int k = 0; k < 3; k++) c[k] += x[k];
     const float m = t.mass[i], cc = dot3(c, c);
-    s.in[i][0] = Iw[0] + m * (cc - c[0] * c[0]);
-    s.in[i][1] = Iw[4] + m * (cc - c[1] * c[1]);
-    s.in[i][2] = Iw[8] + m * (cc - c[2] * c[2]);
-    s.in[i][3] = Iw[1] - m * c[0] * c[1];
-    s.in[i][4] = Iw[2] - m * c[0] * c[2];
-    s.in[i][5] = Iw[5] - m * c[1] * c[2];
-    s.in[i][6] = m * c[0]; s.in[i][7] = m * c[1]; s.in[i][8] = m * c[2];
-    s.in[i][9] = m;
+    const float a[10] = {Iw[0] + m * (cc - c[0] * c[0]), Iw[4] + m * (cc - c[1] * c[1]), Iw[8] + m * (cc - c[2] * c[2]),
+                         Iw[1] - m * c[0] * c[1], Iw[2] - m * c[0] * c[2], Iw[5] - m * c[1] * c[2], m * c[0], m * c[1], m * c[2], m};
+    kin_store_in(s.in[i], a);
 }
 
 // ---- phase 3 (once per tree level d = maxdepth - 1 .. 0): composite inertia of the sub-tree rooted at link i = its own + its
 // children's (already complete: they are one level deeper).  In place; a fixed order of the children keeps the sums reproducible.
-B2G_HD void kin_composite_level(int i, int d, const KinModel &t, KinScratch &s) {
-    if (i >= t.nl || t.depth[i] != d || t.nchild[i] == 0) return;
+B2G_HD void kin_composite_do(int i, int nchild, const KinModel &t, KinScratch &s) {
     float a[10];
+    kin_load_in(s.in[i], a);
+    for (int q = 0; q < nchild; q++) {
+        float b[10];
+        kin_load_in(s.in[t.child[i][q]], b);
 #pragma unroll
-    for (int c = 0; c < 10; c++) a[c] = s.in[i][c];
-    for (int q = 0; q < t.nchild[i]; q++) {
-        const int k = t.child[i][q];
-#pragma unroll
-        for (int c = 0; c < 10; c++) a[c] += s.in[k][c];
+        for (int c = 0; c < 10; c++) a[c] += b[c];
     }
-#pragma unroll
-    for (int c = 0; c < 10; c++) s.in[i][c] = a[c];
+    kin_store_in(s.in[i], a);
+}
+B2G_HD void kin_composite_level(int i, int d, const KinModel &t, KinScratch &s) {
+    if (i < t.nl && t.depth[i] == d && t.nchild[i] > 0) kin_composite_do(i, t.nchild[i], t, s);
 }
 // ---- phase 4: Ic_i S_i = (angular momentum about O ; linear momentum) of the sub-tree moving with joint i at unit rate
 B2G_HD void kin_momentum(int i, const KinModel &t, KinScratch &s) {
     if (i == 0) {
-#pragma unroll
-        for (int c = 0; c < 10; c++) s.cb[c] = s.in[0][c];
+        s.cb[0] = s.in[0][0]; s.cb[1] = s.in[0][1]; s.cb[2] = s.in[0][2];
         return;
     }
     float a[10];
-#pragma unroll
-    for (int c = 0; c < 10; c++) a[c] = s.in[i][c];
-    const float sa[3] = {s.sa[i][0], s.sa[i][1], s.sa[i][2]}, sb[3] = {s.sb[i][0], s.sb[i][1], s.sb[i][2]}, mc[3] = {a[6], a[7], a[8]};
+    kin_load_in(s.in[i], a);
+    KinS S = kin_load_S(s, i);
+    const float mc[3] = {a[6], a[7], a[8]};
     // n = I_O sa + mc x sb,  f = m sb - mc x sa
     float t1[3], t2[3];
-    cross(mc, sb, t1); cross(mc, sa, t2);
-    s.nf[i][0] = a[0] * sa[0] + a[3] * sa[1] + a[4] * sa[2] + t1[0];
-    s.nf[i][1] = a[3] * sa[0] + a[1] * sa[1] + a[5] * sa[2] + t1[1];
-    s.nf[i][2] = a[4] * sa[0] + a[5] * sa[1] + a[2] * sa[2] + t1[2];
+    cross(mc, S.sb, t1); cross(mc, S.sa, t2);
+    S.n[0] = a[0] * S.sa[0] + a[3] * S.sa[1] + a[4] * S.sa[2] + t1[0];
+    S.n[1] = a[3] * S.sa[0] + a[1] * S.sa[1] + a[5] * S.sa[2] + t1[1];
+    S.n[2] = a[4] * S.sa[0] + a[5] * S.sa[1] + a[2] * S.sa[2] + t1[2];
 #pragma unroll
-    for (int c = 0; c < 3; c++) s.nf[i][3 + c] = a[9] * sb[c] - t2[c];
+    for (int c = 0; c < 3; c++) S.f[c] = a[9] * S.sb[c] - t2[c];
+    kin_store_S(s, i, S);
 }
 
-// ---- phase 2b: origin of body b's frame relative to O
+// ---- phase 2b: origin of body b's frame relative to O, with the ancestor mask of its link
 B2G_HD void kin_body(int b, const KinModel &t, KinScratch &s) {
     const int l = t.body_link[b];
-    float R[9], o[3];
-#pragma unroll
-    for (int c = 0; c < 9; c++) R[c] = s.R[l][c];
+    float R[9], x[3], o[3];
+    kin_load_Rx(s, l, R, x);
     const float bp[3] = {t.body_pos[b][0], t.body_pos[b][1], t.body_pos[b][2]};
     matvec(R, bp, o);
-#pragma unroll
-    for (int c = 0; c < 3; c++) s.pb[b][c] = s.x[l][c] + o[c];
+    s.pb[b] = make_float4(x[0] + o[0], x[1] + o[1], x[2] + o[2], kin_u2f(t.anc[l]));
 }
 
 // ---- fills.  A lane owns one COLUMN c of both tensors for the whole env, so what belongs to the column -- the joint's world
@@ -193,7 +222,7 @@ B2G_HD void kin_body(int b, const KinModel &t, KinScratch &s) {
 // multiply-adds; the stores of a warp are one contiguous run of an output row.
 struct KinCol {
     int base;               // 0..5: base column (world linear 0..2, world angular 3..5), -1: joint column
-    int link, slide;        // joint column: its link
+    int link;               // joint column: its link
     unsigned anc;
     float sa[3], sb[3], n[3], f[3], arm;      // the column's motion subspace about O and Ic S
 };
@@ -201,12 +230,13 @@ B2G_HD KinCol kin_col(int c, const KinModel &t, const KinScratch &s) {
     KinCol k;
     k.base = c < t.nbase ? c : -1;
     const int j = c < t.nbase ? 0 : c - t.nbase + 1;
-    k.link = j; k.slide = t.slide[j]; k.anc = t.anc[j]; k.arm = t.armature[j];
+    k.link = j; k.anc = t.anc[j]; k.arm = t.armature[j];
+    const KinS S = kin_load_S(s, j);                                 // base columns read the root's row (zeros), overwritten below
 #pragma unroll
     for (int a = 0; a < 3; a++) {
-        k.sa[a] = c < t.nbase ? ((c >= 3 && c - 3 == a) ? 1.f : 0.f) : s.sa[j][a];      // base: (0 ; e_c) linear, (e_c ; 0) angular
-        k.sb[a] = c < t.nbase ? ((c < 3 && c == a) ? 1.f : 0.f) : s.sb[j][a];
-        k.n[a] = s.nf[j][a]; k.f[a] = s.nf[j][3 + a];
+        k.sa[a] = c < t.nbase ? ((c >= 3 && c - 3 == a) ? 1.f : 0.f) : S.sa[a];      // base: (0 ; e_c) linear, (e_c ; 0) angular
+        k.sb[a] = c < t.nbase ? ((c < 3 && c == a) ? 1.f : 0.f) : S.sb[a];
+        k.n[a] = S.n[a]; k.f[a] = S.f[a];
     }
     return k;
 }
@@ -217,8 +247,9 @@ B2G_HD float kin_pick(const float v[3], int a) { return a == 0 ? v[0] : (a == 1 
 // riding on the joint's sub-tree is (sa x p + sb ; sa) -- hinge, slide and the six base coordinates alike (base: S = unit vectors,
 // every body rides on it) -- so the lanes of a warp run one branch-free expression.
 B2G_HD void kin_jac_col(int b, const KinCol &k, const KinModel &t, const KinScratch &s, float o[6]) {
-    const float pb[3] = {s.pb[b][0], s.pb[b][1], s.pb[b][2]};
-    const bool on = k.base >= 0 || ((t.anc[t.body_link[b]] >> k.link) & 1u);     // the joint lies between the base and this body
+    const float4 pw = s.pb[b];                                                    // one 128-bit broadcast: origin + ancestor mask
+    const float pb[3] = {pw.x, pw.y, pw.z};
+    const bool on = k.base >= 0 || ((kin_f2u(pw.w) >> k.link) & 1u);             // the joint lies between the base and this body
     float v[3]; cross(k.sa, pb, v);
 #pragma unroll
     for (int c = 0; c < 3; c++) { o[c] = on ? v[c] + k.sb[c] : 0.f; o[3 + c] = on ? k.sa[c] : 0.f; }
@@ -230,18 +261,23 @@ B2G_HD float kin_mass_col(int a, const KinCol &k, const KinModel &t, const KinSc
     if (a < nb) {
         const int ax = a < 3 ? a : a - 3;
         if (k.base < 0) return a < 3 ? kin_pick(k.f, ax) : kin_pick(k.n, ax);           // base row against a joint column: Ic_j S_j
-        const float *cb = s.cb;
+        float cb[10]; kin_load_in(s.cb, cb);
         const int kx = k.base < 3 ? k.base : k.base - 3;
         if (a < 3 && k.base < 3) return ax == kx ? cb[9] : 0.f;     // m 1
-        if (a >= 3 && k.base >= 3) return ax == kx ? cb[ax] : cb[2 + ax + kx];   // I_O: (0,1) -> 3, (0,2) -> 4, (1,2) -> 5
+        if (a >= 3 && k.base >= 3) {                                 // I_O: (0,1) -> 3, (0,2) -> 4, (1,2) -> 5
+            const int q = ax == kx ? ax : 2 + ax + kx;
+            return q == 0 ? cb[0] : q == 1 ? cb[1] : q == 2 ? cb[2] : q == 3 ? cb[3] : q == 4 ? cb[4] : cb[5];
+        }
         // linear row i, angular column j: p = w x (m c) -> -[mc]x [i][j]; the (angular, linear) entry is its transpose
         const int i = a < 3 ? ax : kx, j = a < 3 ? kx : ax;
         if (i == j) return 0.f;
-        const float v = cb[6 + 3 - i - j];
+        const float mc[3] = {cb[6], cb[7], cb[8]};
+        const float v = kin_pick(mc, 3 - i - j);
         return ((j - i + 3) % 3 == 1) ? v : -v;
     }
     const int i = a - nb + 1;
-    if (k.base >= 0) { const int kx = k.base < 3 ? k.base : k.base - 3; return k.base < 3 ? s.nf[i][3 + kx] : s.nf[i][kx]; }
+    const KinS R = kin_load_S(s, i);                                // the row link's (Ic S ; S): three 128-bit broadcasts
+    if (k.base >= 0) { const int kx = k.base < 3 ? k.base : k.base - 3; return k.base < 3 ? kin_pick(R.f, kx) : kin_pick(R.n, kx); }
     const int j = k.link;
     // S_deeper-or-equal's Ic S against the other's S: column joint j on row link i's path -> S_j . (Ic_i S_i); row link i on column
     // joint j's path -> S_i . (Ic_j S_j); different branches of the tree -> 0.  Selected without branching: the lanes of a warp
@@ -250,8 +286,8 @@ B2G_HD float kin_mass_col(int a, const KinCol &k, const KinModel &t, const KinSc
     float v = 0.f;
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-        const float sa = ja ? k.sa[c] : s.sa[i][c], sb = ja ? k.sb[c] : s.sb[i][c];
-        const float n = ja ? s.nf[i][c] : k.n[c], f = ja ? s.nf[i][3 + c] : k.f[c];
+        const float sa = ja ? k.sa[c] : R.sa[c], sb = ja ? k.sb[c] : R.sb[c];
+        const float n = ja ? R.n[c] : k.n[c], f = ja ? R.f[c] : k.f[c];
         v += sa * n + sb * f;
     }
     if (!(ja || ib)) v = 0.f;
@@ -275,18 +311,20 @@ __global__ void __launch_bounds__(WARPS * 32) kin_tensors_kernel(const KinModel 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     KinScratch &s = sc[warp];
     const int nl = t.nl, nd = nl - 1, nc = t.nc;
+    // what a lane needs of the tables in the level loops, read once for all the envs this warp processes
+    const int my_depth = lane < nl ? t.depth[lane] : -1, my_parent = lane < nl ? t.parent[lane] : 0, my_nchild = lane < nl ? t.nchild[lane] : 0;
     for (int e = blockIdx.x * WARPS + warp; e < N; e += gridDim.x * WARPS) {
         const float *root = g_root + 13 * (size_t)e * t.root_stride;
         const float2 *dof = reinterpret_cast<const float2 *>(g_dof) + (size_t)e * nd;
         __syncwarp();                                        // the previous env's readers are done with the scratch
         if (lane < nl) kin_local(lane, t, s, root, lane > 0 ? dof[lane - 1].x : 0.f);
-        for (int d = 1; d <= t.maxdepth; d++) { __syncwarp(); kin_level(lane, d, t, s); }
+        for (int d = 1; d <= t.maxdepth; d++) { __syncwarp(); if (my_depth == d) kin_level_do(lane, my_parent, s); }
         __syncwarp();
         if (lane < nl) kin_link(lane, t, s);
         if (jac && lane < t.nb) kin_body(lane, t, s);
         __syncwarp();
         if (mass) {
-            for (int d = t.maxdepth - 1; d >= 0; d--) { kin_composite_level(lane, d, t, s); __syncwarp(); }
+            for (int d = t.maxdepth - 1; d >= 0; d--) { if (my_depth == d && my_nchild > 0) kin_composite_do(lane, my_nchild, t, s); __syncwarp(); }
             if (lane < nl) kin_momentum(lane, t, s);
             __syncwarp();
         }
