@@ -1138,12 +1138,18 @@ extern "C" int b2g_refresh_kinematic_tensors(b2g_sim *s, int32_t which, void *st
     CUDA_TRY(cudaSetDevice(s->device));
     const int N = s->num_envs;
     constexpr int WARPS = 4;
-    // one warp per env; at most a few resident waves of CTAs, the warps stride over the envs
-    const int grid = std::min((N + WARPS - 1) / WARPS, 148 * 8);
-    kin_tensors_kernel<WARPS><<<grid, WARPS * 32, 0, (cudaStream_t)stream>>>(
-        s->d_kin, (const float *)s->buf.p[B2G_T_ROOT_STATE], (const float *)s->buf.p[B2G_T_DOF_STATE],
-        (which & B2G_KIN_JACOBIAN) ? (float *)s->buf.p[B2G_T_JACOBIAN] : nullptr,
-        (which & B2G_KIN_MASS_MATRIX) ? (float *)s->buf.p[B2G_T_MASS_MATRIX] : nullptr, N);
+    const float *root = (const float *)s->buf.p[B2G_T_ROOT_STATE], *dof = (const float *)s->buf.p[B2G_T_DOF_STATE];
+    float *J = (which & B2G_KIN_JACOBIAN) ? (float *)s->buf.p[B2G_T_JACOBIAN] : nullptr;
+    float *M = (which & B2G_KIN_MASS_MATRIX) ? (float *)s->buf.p[B2G_T_MASS_MATRIX] : nullptr;
+    // one warp per env -- or per two envs when links and bodies fit 16 lanes (arms, quadrupeds); at most a few resident waves of
+    // CTAs, the warps stride over the envs
+    if (s->hk.nl <= 16 && s->hk.nb <= 16) {
+        const int grid = std::min((N + 2 * WARPS - 1) / (2 * WARPS), 148 * 8);
+        kin_tensors_kernel<WARPS, 16><<<grid, WARPS * 32, 0, (cudaStream_t)stream>>>(s->d_kin, root, dof, J, M, N);
+    } else {
+        const int grid = std::min((N + WARPS - 1) / WARPS, 148 * 8);
+        kin_tensors_kernel<WARPS, 32><<<grid, WARPS * 32, 0, (cudaStream_t)stream>>>(s->d_kin, root, dof, J, M, N);
+    }
     s->launches++;
     CUDA_TRY(cudaGetLastError());
     return B2G_OK;

@@ -17,7 +17,7 @@
 // and M[i][j] = S_j . (Ic_i S_i) needs no transforms at all.  A joint's motion subspace about O is S = (sa ; sb) -- hinge (w ; x cross w),
 // slide (0 ; w), base coordinates (unit vectors) -- so the twist of a body origin p is (sa x p + sb ; sa) for every column kind.
 //
-// Work decomposition: ONE WARP PER ENVIRONMENT, lane = link (nl <= 32) for the kinematics / inertias, lane = body for the
+// Work decomposition: ONE WARP PER ENVIRONMENT (half a warp when links and bodies fit 16 lanes), lane = link (nl <= 32) for the kinematics / inertias, lane = body for the
 // body origins, lane = output column for the fills, so every global store is a contiguous run of one output row.  Lanes
 // exchange through a per-warp shared-memory scratch ordered by __syncwarp; every phase is a __host__ __device__ function
 // of (lane, tables, scratch), so tests/kin_host.cu runs the exact device arithmetic on the CPU against the fp64 oracle.
@@ -277,12 +277,12 @@ B2G_HD float kin_mass_col(int a, const KinCol &k, const KinModel &t, const KinSc
     }
     const int i = a - nb + 1;
     const KinS R = kin_load_S(s, i);                                // the row link's (Ic S ; S): three 128-bit broadcasts
-    if (k.base >= 0) { const int kx = k.base < 3 ? k.base : k.base - 3; return k.base < 3 ? kin_pick(R.f, kx) : kin_pick(R.n, kx); }
     const int j = k.link;
     // S_deeper-or-equal's Ic S against the other's S: column joint j on row link i's path -> S_j . (Ic_i S_i); row link i on column
     // joint j's path -> S_i . (Ic_j S_j); different branches of the tree -> 0.  Selected without branching: the lanes of a warp
     // (columns) fall into all three cases in the same row.
-    const bool ja = (t.anc[i] >> j) & 1u, ib = (k.anc >> i) & 1u;
+    // A base column is the same expression with S = unit vectors (every link rides on the base), so it takes the first case.
+    const bool ja = k.base >= 0 || ((t.anc[i] >> j) & 1u), ib = (k.anc >> i) & 1u;
     float v = 0.f;
 #pragma unroll
     for (int c = 0; c < 3; c++) {
@@ -295,27 +295,31 @@ B2G_HD float kin_mass_col(int a, const KinCol &k, const KinModel &t, const KinSc
 }
 
 #ifdef __CUDACC__
-// One warp per env, grid-stride.  jac / mass may be null (only the other tensor is refreshed).
-template <int WARPS>
+// G lanes per env (32: one warp per env; 16 / 8: two / four small articulations per warp -- an arm or a quadruped leaves most
+// of a warp idle otherwise), grid-stride over groups of 32 / G envs.  jac / mass may be null (only the other tensor is refreshed).
+template <int WARPS, int G>
 __global__ void __launch_bounds__(WARPS * 32) kin_tensors_kernel(const KinModel *__restrict__ gm, const float *__restrict__ g_root,
                                                                  const float *__restrict__ g_dof, float *__restrict__ jac,
                                                                  float *__restrict__ mass, int N) {
+    constexpr int EPW = 32 / G;                              // envs per warp
     __shared__ KinModel t;
-    __shared__ KinScratch sc[WARPS];
+    __shared__ KinScratch sc[WARPS * EPW];
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(gm);
         uint4 *dst = reinterpret_cast<uint4 *>(&t);
         for (int i = threadIdx.x; i < (int)(sizeof(KinModel) / 16); i += blockDim.x) dst[i] = src[i];
         __syncthreads();
     }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    KinScratch &s = sc[warp];
+    const int lane = (threadIdx.x & 31) % G, grp = (threadIdx.x & 31) / G, warp = threadIdx.x >> 5;
+    KinScratch &s = sc[warp * EPW + grp];
     const int nl = t.nl, nd = nl - 1, nc = t.nc;
     // what a lane needs of the tables in the level loops, read once for all the envs this warp processes
     const int my_depth = lane < nl ? t.depth[lane] : -1, my_parent = lane < nl ? t.parent[lane] : 0, my_nchild = lane < nl ? t.nchild[lane] : 0;
-    for (int e = blockIdx.x * WARPS + warp; e < N; e += gridDim.x * WARPS) {
-        const float *root = g_root + 13 * (size_t)e * t.root_stride;
-        const float2 *dof = reinterpret_cast<const float2 *>(g_dof) + (size_t)e * nd;
+    for (int e0 = (blockIdx.x * WARPS + warp) * EPW; e0 < N; e0 += gridDim.x * WARPS * EPW) {
+        const int e = e0 + grp;
+        const bool valid = e < N;                            // the groups of a warp run in step (warp-wide barriers): a tail group idles
+        const float *root = g_root + 13 * (size_t)(valid ? e : 0) * t.root_stride;
+        const float2 *dof = reinterpret_cast<const float2 *>(g_dof) + (size_t)(valid ? e : 0) * nd;
         __syncwarp();                                        // the previous env's readers are done with the scratch
         if (lane < nl) kin_local(lane, t, s, root, lane > 0 ? dof[lane - 1].x : 0.f);
         for (int d = 1; d <= t.maxdepth; d++) { __syncwarp(); if (my_depth == d) kin_level_do(lane, my_parent, s); }
@@ -328,7 +332,8 @@ __global__ void __launch_bounds__(WARPS * 32) kin_tensors_kernel(const KinModel 
             if (lane < nl) kin_momentum(lane, t, s);
             __syncwarp();
         }
-        for (int c = lane; c < nc; c += 32) {                // one pass for nc <= 32, two for the largest floating trees
+        if (!valid) continue;
+        for (int c = lane; c < nc; c += G) {                 // one pass when the columns fit the group
             const KinCol k = kin_col(c, t, s);
             if (mass) {
                 float *M = mass + (size_t)e * nc * nc + c;

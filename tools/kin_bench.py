@@ -49,7 +49,7 @@ def main():
     peaks = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
     peak = json.load(open(peaks))["hbm_gbs"] if os.path.exists(peaks) else 6650.0
     gbs = per / us * 1e-3
-    print(json.dumps({"kernel": "kin_tensors_kernel<4>", "model": a.model, "num_envs": n, "jacobian": [rows, 6, nc], "mass_matrix": [nc, nc],
+    print(json.dumps({"kernel": "kin_tensors_kernel<4, 32 or 16 lanes per env>", "model": a.model, "num_envs": n, "jacobian": [rows, 6, nc], "mass_matrix": [nc, nc],
                       "us_per_refresh": round(us, 2), "bytes_per_refresh": per, "bytes_per_env": per // n, "sets": len(sims),
                       "roofline": {"bound": "hbm", "achieved": round(gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(gbs / peak, 4)},
                       "peak_source": "MEASURED_PEAKS.json" if os.path.exists(peaks) else "B200_PROFILING.md fallback"}))
