@@ -174,6 +174,26 @@ def test_reference_shadow_hand_random_forces_reach_the_engine(compat_cpu):
 
 
 @needs_reference
+@pytest.mark.parametrize("obj,half,rnd,mass", [("pen", [0.0, 0.0, 0.1], 0.008, 0.042357), ("egg", [0.0, 0.0, 0.01], 0.03, 0.150796)])
+def test_reference_shadow_hand_egg_and_pen_reach_the_engine_as_rounded_boxes(compat_cpu, obj, half, rnd, mass):
+    """env.objectType egg / pen (shadow_hand.py:84-99): the reference loads egg.xml / pen.xml itself; the shim turns the single
+    collision primitive into the engine's rounded box and passes the object's own AssetOptions (speed limit 64 rad/s, damping)."""
+    import importlib
+    mod = importlib.import_module("isaacgymenvs.tasks.shadow_hand")
+    cfg = _cfg("ShadowHand", 4)
+    cfg["env"]["objectType"] = obj
+    env = mod.ShadowHand(cfg=cfg, rl_device="cpu", sim_device="cpu", graphics_device_id=-1, headless=True,
+                         virtual_screen_capture=False, force_render=False)
+    ext = env.sim.engine.ext
+    assert ext.actors_per_env == 3 and ext.obj_actor == 1
+    assert [round(float(v), 6) for v in ext.obj_half] == half and abs(ext.obj_round - rnd) < 1e-7 and abs(ext.obj_mass - mass) < 1e-5
+    assert ext.obj_max_angular_velocity == 64.0 and abs(ext.obj_angular_damping - 0.5) < 1e-7
+    assert env.ignore_z == (obj == "pen")
+    obs, rew, reset, extras = env.step(torch.zeros(4, 20))
+    assert torch.isfinite(obs["obs"]).all()
+
+
+@needs_reference
 def test_unmodified_reference_flat_anymal_runs_on_the_shim(compat_cpu):
     """tasks/anymal.py drives PhysX position drives (DOF_MODE_POS via set_actor_dof_properties,
     set_dof_position_target_tensor) and reads net contact forces -- unmodified on the shim."""

@@ -74,3 +74,39 @@ def test_hand_resets_do_not_depend_on_the_sharding():
         parts.append(s_)
     for k in ("root", "dof_pos", "dof_vel", "cur_targets", "goal_states"):
         assert np.array_equal(whole[k], np.concatenate([p[k] for p in parts], 0)), k
+
+
+def test_hand_random_forces_do_not_depend_on_the_sharding():
+    """The per-step force draws (shadow_hand.py:700-709) are keyed by (step, reset count, GLOBAL env id): one shard of 16 envs
+    and two shards of 8 apply the same forces, with and without a reset in the step."""
+    import os as _os
+    from oracle import tasks_np as T
+    from tests.hand_common import golden_case
+    gold = np.load(_os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden", "shadow_hand_force.npz"))
+    st, P, actions = golden_case(gold, "f")
+    n = 16
+    cut = lambda d, sl: {k: (v[sl].copy() if isinstance(v, np.ndarray) and v.shape[:1] == (256,) else v) for k, v in d.items()}
+    for step in range(2):
+        whole, Pw = cut(st, slice(0, n)), cut(P, slice(0, n))
+        whole["force_prob"][:] = 0.8
+        if step == 1:
+            whole["reset"][:] = 0; whole["reset_goal"][:] = 0
+        T.hand_pre_physics(whole, actions[:n], dict(Pw, env_id_offset=0))
+        parts = []
+        for r in range(2):
+            sl = slice(8 * r, 8 * r + 8)
+            s_, P_ = cut(st, sl), cut(P, sl)
+            s_["force_prob"][:] = 0.8
+            if step == 1:
+                s_["reset"][:] = 0; s_["reset_goal"][:] = 0
+            T.hand_pre_physics(s_, actions[sl], dict(P_, env_id_offset=8 * r))
+            parts.append(s_)
+        for k in ("obj_force", "force_prob"):
+            assert np.array_equal(whole[k], np.concatenate([p[k] for p in parts], 0)), (step, k)
+        assert (np.abs(whole["obj_force"]).sum(1) > 0).sum() >= 8
+        # a different global id draws a different force
+        other = cut(st, slice(0, 8)); other["force_prob"][:] = 0.8
+        if step == 1:
+            other["reset"][:] = 0; other["reset_goal"][:] = 0
+        T.hand_pre_physics(other, actions[:8], dict(cut(P, slice(0, 8)), env_id_offset=1000))
+        assert not np.array_equal(other["obj_force"], whole["obj_force"][:8])
