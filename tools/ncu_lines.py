@@ -13,10 +13,11 @@ with tempfile.TemporaryDirectory() as d:
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=d, capture_output=True)
     cub = [f for f in os.listdir(d) if f.endswith(".cubin")][0]
     dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(d, cub)], capture_output=True, text=True).stdout.splitlines()
-lines = []; cur = ("?", 0); inside = False
+lines = []; cur = ("?", 0); inside = False; seen = False
 for l in dis:
     if l.startswith("//---") and ".text." in l:
-        inside = pat in l
+        inside = pat in l and not seen          # several instantiations may match the pattern: the first one (give a longer pattern to pick another)
+        seen = seen or inside
         continue
     if not inside:
         continue
