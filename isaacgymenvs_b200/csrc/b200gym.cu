@@ -620,6 +620,7 @@ struct b2g_sim {
     bool kin_ok = false;
     std::vector<const void *> smem_set;      // kernels whose dynamic shared-memory limit has been raised (once per sim)
     bool no_zero_copy = false;
+    size_t hostio_pad = 0;                    // extra dynamic shared memory of the host-I/O Ant launch (see b2g_task_step_host)
 };
 
 static thread_local std::string g_err;
@@ -953,6 +954,10 @@ extern "C" int b2g_create_ext(const b2g_model *m, const b2g_model_ext *ext, cons
     {   // the specialised path of "four hinge chains on a free base" (Ant, ANYmal): b2g_quad.cuh
         const char *nq = getenv("B2G_NO_QUAD"), *qb = getenv("B2G_QUAD_BLOCK"), *nz = getenv("B2G_NO_ZERO_COPY");
         s->no_zero_copy = nz != nullptr;
+        if (const char *hc = getenv("B2G_HOSTIO_CTAS")) {      // experiment hook: resident CTAs per SM of the host-I/O Ant step (2..6)
+            const int c = atoi(hc);
+            if (c >= 2 && c <= 6) s->hostio_pad = (size_t)(227 * 1024 / c - 1024 - 32 * 1024) & ~(size_t)15;
+        }
         if (qb && (atoi(qb) == 32 || atoi(qb) == 64 || atoi(qb) == 128)) s->quad_block = atoi(qb);
         if (!(nq && nq[0] == '1') && !ext && !h.self_on && !(force1 && force1[0] == '1') && !getenv("B2G_LANES") && !getenv("B2G_BLOCK")) {
             std::vector<float> qm; int leg_link[12], spec = 0;
@@ -1342,7 +1347,10 @@ extern "C" int b2g_task_step(b2g_sim *s, const float *actions, void *stream) {
             const size_t out_bytes = (size_t)epb * ((clip_sep ? 2 : 1) * O * 4 + 4 * 3 + 12 * 2 + 8 * 2 + 1);
             const bool ok = (N % epb == 0) && ((epb * ns6 * 4) % 16 == 0) && ((epb * O * 4) % 16 == 0) && out_bytes <= park_bytes;
             if (ok) {
-                const size_t dyn = park_bytes + io_bytes + (size_t)quad_model_f4(2) * sizeof(float4);
+                // Host-I/O launches ask for more shared memory than they use: fewer CTAs are resident, the grid runs in several waves,
+                // and a later wave computes while the PCIe writes of an earlier one drain (all CTAs of a single wave reach their
+                // store phase together and the link idles while they compute).
+                const size_t dyn = park_bytes + io_bytes + (size_t)quad_model_f4(2) * sizeof(float4) + (s->zero_copy.on ? s->hostio_pad : 0);
                 TileArgs ta; ta.on = 1; ta.io_f4 = (int)(park_bytes / 16); ta.model_f4 = (int)((park_bytes + io_bytes) / 16);
                 ta.h_act = nullptr; ta.h_obs = ta.h_rew = nullptr; ta.h_reset = nullptr; ta.h_timeout = nullptr;
                 if (s->zero_copy.on) { ta.h_act = actions; ta.h_obs = s->zero_copy.obs; ta.h_rew = s->zero_copy.rew; ta.h_reset = s->zero_copy.reset; ta.h_timeout = s->zero_copy.timeout; }
