@@ -393,6 +393,45 @@ class Gym:
         m = env.sim.asset.model if int(actor) == 0 else env.sim.extra_assets[int(actor) - 1].model
         return [types.SimpleNamespace(mass=float(m.mass[m.body_link[b]])) for b in range(m.nb)]
 
+    def get_sim_actor_count(self, sim):
+        return len(sim.envs) * (1 + len(sim.extra_assets))
+
+    def get_actor_dof_count(self, env, actor):
+        return env.sim.asset.model.ndof if int(actor) == 0 else 0
+
+    def get_actor_rigid_body_count(self, env, actor):
+        return env.sim.asset.model.nb if int(actor) == 0 else 1
+
+    # name -> index maps of the articulation (body / DOF order = the tensors' order)
+    def get_asset_rigid_body_dict(self, asset):
+        return {n: i for i, n in enumerate(asset.model.body_names)}
+
+    def get_asset_dof_dict(self, asset):
+        return {n: i for i, n in enumerate(asset.model.dof_names)}
+
+    def get_actor_rigid_body_dict(self, env, actor):
+        return self.get_asset_rigid_body_dict(env.sim.asset)
+
+    def get_actor_dof_dict(self, env, actor):
+        return self.get_asset_dof_dict(env.sim.asset)
+
+    def get_actor_rigid_body_names(self, env, actor):
+        return list(env.sim.asset.model.body_names)
+
+    def get_actor_dof_names(self, env, actor):
+        return list(env.sim.asset.model.dof_names)
+
+    def find_actor_dof_handle(self, env, actor, name):
+        return env.sim.asset.model.dof_names.index(name)
+
+    def find_actor_dof_index(self, env, actor, name, domain):
+        i = env.sim.asset.model.dof_names.index(name)
+        return i + env.index * env.sim.asset.model.ndof if domain == DOMAIN_SIM else i
+
+    def debug_print_asset(self, asset):
+        m = asset.model
+        print(f"asset: {m.nb} bodies {list(m.body_names)}, {m.ndof} dofs {list(m.dof_names)}")
+
     def get_sim_dof_count(self, sim):
         return sim.asset.model.ndof * len(sim.envs)
 
@@ -447,6 +486,12 @@ class Gym:
     # ---- writes (ant.py:265-285)
     def set_dof_actuation_force_tensor(self, sim, t):
         sim.engine.dof_actuation.view(-1).copy_(t.view(-1))
+        return True
+
+    def set_dof_actuation_force_tensor_indexed(self, sim, t, idx, n):        # idx = actor indices (DOMAIN_SIM), like the other *_indexed setters
+        nd = sim.asset.model.ndof
+        i = idx[:n].long() // (1 + len(sim.extra_assets))
+        sim.engine.dof_actuation.view(-1, nd)[i] = t.view(-1, nd)[i]
         return True
 
     def set_dof_position_target_tensor(self, sim, t):
@@ -519,6 +564,12 @@ class Gym:
         return None
 
     def viewer_camera_look_at(self, *a):
+        pass
+
+    def add_lines(self, *a):             # debug drawing (ant.py:307-321): headless
+        pass
+
+    def clear_lines(self, *a):
         pass
 
 

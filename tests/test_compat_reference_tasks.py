@@ -138,6 +138,29 @@ def test_unmodified_reference_shadow_hand_runs_on_the_shim(compat_cpu):
 
 
 @needs_reference
+def test_name_maps_and_small_accessors_of_the_shim(compat_cpu):
+    """the dictionary / count accessors other reference tasks use around the tensor API (franka_cube_stack.py:391, allegro_hand.py,
+    ant.py:307-321 debug lines): body / DOF order = the tensors' order"""
+    import importlib
+    mod = importlib.import_module("isaacgymenvs.tasks.ant")
+    n = 4
+    env = mod.Ant(cfg=_cfg("Ant", n), rl_device="cpu", sim_device="cpu", graphics_device_id=-1, headless=True,
+                  virtual_screen_capture=False, force_render=False)
+    gym, sim, e0 = env.gym, env.sim, env.envs[0]
+    bd, dd = gym.get_actor_rigid_body_dict(e0, 0), gym.get_actor_dof_dict(e0, 0)
+    assert len(bd) == 9 and len(dd) == 8 and bd["torso"] == 0 and sorted(dd.values()) == list(range(8))
+    assert gym.get_actor_rigid_body_names(e0, 0)[bd["front_left_foot"]] == "front_left_foot"
+    assert gym.find_actor_dof_handle(e0, 0, gym.get_actor_dof_names(e0, 0)[3]) == 3
+    assert gym.get_sim_actor_count(sim) == n and gym.get_actor_dof_count(e0, 0) == 8 and gym.get_actor_rigid_body_count(e0, 0) == 9
+    assert gym.get_asset_rigid_body_dict(sim.asset) == bd and gym.get_asset_dof_dict(sim.asset) == dd
+    f = torch.arange(n * 8, dtype=torch.float32).view(n, 8)
+    gym.set_dof_actuation_force_tensor_indexed(sim, f, torch.tensor([2, 0], dtype=torch.int32), 2)
+    got = sim.engine.dof_actuation.view(n, 8)
+    assert torch.equal(got[2], f[2]) and torch.equal(got[0], f[0]) and float(got[1].abs().sum()) == 0.0
+    gym.add_lines(None, None, 0, [], []); gym.clear_lines(None); gym.debug_print_asset(sim.asset)
+
+
+@needs_reference
 def test_reference_shadow_hand_random_forces_reach_the_engine(compat_cpu):
     """env.forceScale > 0 (shadow_hand.py:700-709): the reference's own pre_physics_step calls
     apply_rigid_body_force_tensors(rb_forces, None, LOCAL_SPACE); the shim hands the object's row to the engine for
