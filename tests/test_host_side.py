@@ -280,3 +280,38 @@ def test_compat_add_triangle_mesh_accepts_an_untagged_mesh():
     tp.nb_vertices = 5
     with pytest.raises(ValueError):
         gym.add_triangle_mesh(sim, np.array(v).flatten(), np.array(t).flatten(), tp)
+
+
+# ---------------------------------------------------------------------------------------------
+# train.py: the reference launcher's override syntax over the demonstration learner
+def test_train_launcher_maps_reference_overrides():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("b2g_train", os.path.join(ROOT, "train.py"))
+    tr = importlib.util.module_from_spec(spec); spec.loader.exec_module(tr)
+    a = tr.to_ppo_argv(tr.parse_overrides(["task=ShadowHand", "headless=True", "num_envs=8192", "max_iterations=300", "seed=7",
+                                           "task.env.objectType=pen", "task.env.forceScale=1.0"]))
+    get = lambda k: a[a.index(k) + 1]
+    assert get("--task") == "ShadowHand" and get("--num-envs") == "8192" and get("--epochs") == "300" and get("--seed") == "7"
+    assert get("--units") == "512,512,256,128" and float(get("--kl-threshold")) == 0.016 and get("--horizon") == "8"
+    assert get("--env") == "objectType=pen,forceScale=1.0"
+    b = tr.to_ppo_argv(tr.parse_overrides(["task=Humanoid", "task.env.selfCollision=True"]))
+    assert "--self-collision" in b and "--env" not in b and b[b.index("--epochs") + 1] == "1000"
+    for bad in (["task=FrankaCabinet"], ["task=Ant", "train.params.config.gamma=0.9"], ["task=Ant", "test=True"], ["Ant"]):
+        with pytest.raises(SystemExit):
+            tr.to_ppo_argv(tr.parse_overrides(bad))
+
+
+@needs_reference
+def test_train_launcher_hyperparameters_are_the_reference_yaml():
+    import importlib.util, yaml
+    spec = importlib.util.spec_from_file_location("b2g_train", os.path.join(ROOT, "train.py"))
+    tr = importlib.util.module_from_spec(spec); spec.loader.exec_module(tr)
+    for task, hp in tr.PPO.items():
+        d = yaml.safe_load(open(os.path.join(REFERENCE, "isaacgymenvs", "cfg", "train", task + "PPO.yaml")))
+        c, n = d["params"]["config"], d["params"]["network"]
+        assert n["mlp"]["units"] == hp["units"] and float(c["learning_rate"]) == hp["lr"] and c["horizon_length"] == hp["horizon"]
+        assert c["minibatch_size"] == hp["minibatch"] and c["mini_epochs"] == hp["mini_epochs"] and c["critic_coef"] == hp["critic_coef"]
+        assert c["kl_threshold"] == hp["kl"] and c["reward_shaper"]["scale_value"] == hp["rew_scale"] and float(c["bounds_loss_coef"]) == hp["bounds"]
+        assert str(hp["epochs"]) in c["max_epochs"] and c["gamma"] == 0.99 and c["tau"] == 0.95 and c["e_clip"] == 0.2
+        t = yaml.safe_load(open(os.path.join(REFERENCE, "isaacgymenvs", "cfg", "task", task + ".yaml")))
+        assert str(hp["num_envs"]) in str(t["env"]["numEnvs"])

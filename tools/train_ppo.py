@@ -65,7 +65,7 @@ def neglogp(a, mu, logstd):
     return 0.5 * (((a - mu) / logstd.exp()) ** 2).sum(-1) + logstd.sum(-1) + 0.5 * a.shape[-1] * 1.8378770664093453
 
 
-def main():
+def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--task", default="Ant")
     ap.add_argument("--num-envs", type=int, default=4096)
@@ -80,8 +80,11 @@ def main():
     ap.add_argument("--mini-epochs", type=int, default=4)      # HumanoidPPO.yaml: 5
     ap.add_argument("--critic-coef", type=float, default=2.0)  # HumanoidPPO.yaml: 4
     ap.add_argument("--self-collision", action="store_true")   # Humanoid: env.selfCollision=True
+    ap.add_argument("--kl-threshold", type=float, default=0.008)   # ShadowHandPPO.yaml: 0.016
+    ap.add_argument("--reward-scale", type=float, default=0.01)    # reward_shaper.scale_value; CartpolePPO.yaml 0.1, AnymalTerrainPPO.yaml 1.0
+    ap.add_argument("--bounds-coef", type=float, default=1e-4)     # bounds_loss_coef; AnymalTerrainPPO.yaml 0
     ap.add_argument("--env", default="", help="comma-separated overrides of cfg.task.env, e.g. objectType=pen,forceScale=2.0")
-    args = ap.parse_args()
+    args = ap.parse_args(argv)
     import isaacgymenvs_b200
     dev = args.device
     torch.manual_seed(args.seed)
@@ -103,7 +106,7 @@ def main():
     N, O, A, T = env.num_envs, env.num_obs, env.num_acts, args.horizon
     net = ActorCritic(O, A, tuple(int(u) for u in args.units.split(","))).to(dev)
     obs_rms, val_rms = RunningMeanStd((O,)).to(dev), RunningMeanStd(()).to(dev)
-    lr, kl_thr, gamma, tau, e_clip, critic_coef, bounds_coef, rew_scale = args.lr, 0.008, 0.99, 0.95, 0.2, args.critic_coef, 1e-4, 0.01
+    lr, kl_thr, gamma, tau, e_clip, critic_coef, bounds_coef, rew_scale = args.lr, args.kl_threshold, 0.99, 0.95, 0.2, args.critic_coef, args.bounds_coef, args.reward_scale
     opt = torch.optim.Adam(net.parameters(), lr=lr, eps=1e-8)
     obs = env.reset()["obs"].clone()
     ep_ret = torch.zeros(N, device=dev); ep_len = torch.zeros(N, device=dev)
