@@ -20,6 +20,7 @@ KNOWN = {
     "urdf/objects/cube_multicolor.urdf": "cube",
     "mjcf/open_ai_assets/hand/egg.xml": "egg",
     "mjcf/open_ai_assets/hand/pen.xml": "pen",
+    "urdf/franka_description/robots/franka_panda_gripper.urdf": "franka",
 }
 
 

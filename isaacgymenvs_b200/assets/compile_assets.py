@@ -19,6 +19,9 @@ SPECS = {
     # ShadowHand objectType egg / pen (shadow_hand.py:91-95; object_asset_options = gymapi.AssetOptions(), :279)
     "egg": ("mjcf/open_ai_assets/hand/egg.xml", BuildOptions()),
     "pen": ("mjcf/open_ai_assets/hand/pen.xml", BuildOptions()),
+    # FrankaCubeStack / FrankaCabinet's arm (franka_cube_stack.py:208-216): no <inertial> -> masses from the collision meshes' volume;
+    # mesh CONTACT is not modelled (the import warns) -- what it serves is the Jacobian / mass-matrix tensors and the arm's dynamics
+    "franka": ("urdf/franka_description/robots/franka_panda_gripper.urdf", BuildOptions(fix_base_link=True)),
     "anymal": ("urdf/anymal_c/urdf/anymal_minimal.urdf",
                BuildOptions(collapse_fixed_joints=True, replace_cylinder_with_capsule=True, density=0.001,
                             default_dof_drive_mode=DRIVE_EFFORT)),

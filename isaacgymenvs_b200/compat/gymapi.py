@@ -262,7 +262,22 @@ class Gym:
         return asset.model.nb
 
     def get_asset_joint_count(self, asset):
-        return asset.model.ndof
+        names = getattr(asset.model, "body_joint_names", None)
+        return asset.model.ndof if not names else len(names) - 1          # one joint per non-root body (fixed ones included)
+
+    def _joint_names(self, model):
+        names = getattr(model, "body_joint_names", None)
+        if not names:
+            raise NotImplementedError("joint names: this compiled model was built before the importer recorded them; load the asset from its XML")
+        return names
+
+    def get_asset_joint_names(self, asset):
+        return list(self._joint_names(asset.model)[1:])
+
+    def get_asset_joint_dict(self, asset):
+        """joint name -> index; joint k connects body k + 1 to its parent, so the index also addresses that body's row of a
+        fixed-base Jacobian tensor (`jacobian[:, joint_dict['panda_hand_joint'], :, :7]`, franka_cube_stack.py:390-391)"""
+        return {n: i for i, n in enumerate(self._joint_names(asset.model)[1:]) if n}
 
     def get_asset_rigid_shape_count(self, asset):
         return len(asset.model.geom_type)
@@ -414,6 +429,15 @@ class Gym:
 
     def get_actor_dof_dict(self, env, actor):
         return self.get_asset_dof_dict(env.sim.asset)
+
+    def get_actor_joint_dict(self, env, actor):
+        return self.get_asset_joint_dict(env.sim.asset)
+
+    def get_actor_joint_names(self, env, actor):
+        return self.get_asset_joint_names(env.sim.asset)
+
+    def get_actor_joint_count(self, env, actor):
+        return self.get_asset_joint_count(env.sim.asset)
 
     def get_actor_rigid_body_names(self, env, actor):
         return list(env.sim.asset.model.body_names)

@@ -131,6 +131,8 @@ def load_mjcf(path, opts: BuildOptions = None, name=None):
             a = defaults.resolve(ge, childclass)
             gt = a.get("type", "sphere")
             if gt not in _GEOM_TYPES:     # mesh / plane / hfield: no primitive -> skipped
+                if gt == "mesh" and int(a.get("contype", 1)) | int(a.get("conaffinity", 1)):       # a COLLIDING mesh: recorded, announced by build_model
+                    b.skipped_geoms.append(a.get("name", a.get("mesh", "mesh")))
                 continue
             size = _floats(a["size"]) if "size" in a else np.zeros(1)
             gpos, gR = frame(a)

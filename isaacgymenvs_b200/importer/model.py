@@ -53,6 +53,11 @@ class IRGeom:
     collide: bool = True
 
 
+class UnmodelledGeometryWarning(UserWarning):
+    """Collision geometry of an asset that the importer cannot turn into a primitive (triangle / convex meshes, SURVEY.md 8f rank
+    4): the bodies it belongs to do not collide through it.  Emitted once per import; Model.unmodelled_geoms lists them."""
+
+
 @dataclass
 class IRBody:
     name: str
@@ -64,6 +69,9 @@ class IRBody:
     children: list = field(default_factory=list)
     sites: dict = field(default_factory=dict)
     collapsed: bool = False       # jointless body merged away (URDF collapse_fixed_joints)
+    parent_joint: str = ""        # name of the joint to the parent body (URDF: every non-root link has exactly one, fixed ones included)
+    skipped_geoms: list = field(default_factory=list)   # collision geometry the importer has no primitive for (meshes): names
+    extra_parts: list = field(default_factory=list)     # (mass, com, inertia 3x3 about it) of such geometry, body frame: counted when the body has no <inertial>
 
 
 def geom_mass_inertia(g):
@@ -376,9 +384,10 @@ class BuildOptions:
 def build_model(name, root: IRBody, has_free_root: bool, opts: BuildOptions) -> Model:
     """Flatten an IR body tree (file order DFS = the reference's DOF/body order) into a Model."""
     L = dict(parent=[], jtype=[], axis=[], lpos=[], lquat=[], parts=[], jref=[])
-    bodies = dict(names=[], link=[], pos=[], quat=[])
+    bodies = dict(names=[], link=[], pos=[], quat=[], joint=[])
     geoms = []
     sites = {}
+    skipped = []
 
     def new_link(parent, jt, axis, lpos, R, j):
         L["parent"].append(parent); L["jtype"].append(jt)
@@ -411,7 +420,10 @@ def build_model(name, root: IRBody, has_free_root: bool, opts: BuildOptions) -> 
         else:
             bodies["names"].append(b.name); bodies["link"].append(li)
             bodies["pos"].append(p_b); bodies["quat"].append(rot.mat_to_quat(R_b))
+            # the joint this body hangs on: a URDF link's one parent joint; an MJCF body's last joint (the one whose link carries it)
+            bodies["joint"].append("" if is_root else (b.parent_joint or (b.joints[-1].name if b.joints else "")))
             bi = len(bodies["names"]) - 1
+        skipped.extend(f"{b.name}:{g}" for g in b.skipped_geoms)
         # inertia of this body, expressed in link li
         if b.inertial is not None:
             m, c, I = b.inertial
@@ -421,6 +433,7 @@ def build_model(name, root: IRBody, has_free_root: bool, opts: BuildOptions) -> 
             for g in b.geoms:
                 m, Ig = geom_mass_inertia(g)
                 parts.append((m, g.pos, g.R @ Ig @ g.R.T))
+            parts.extend(b.extra_parts)
         for m, c, I in parts:
             L["parts"][li].append((m, p_b + R_b @ c, R_b @ I @ R_b.T))
         for g in b.geoms:
@@ -455,6 +468,13 @@ def build_model(name, root: IRBody, has_free_root: bool, opts: BuildOptions) -> 
     m.drive_mode = np.full(nl, opts.default_dof_drive_mode, dtype=np.int32)
     m.dof_names = [j.name for j in L["jref"][1:]]
     m.body_names = bodies["names"]
+    m.body_joint_names = bodies["joint"]        # per body: the joint to its parent ("" for the root / unnamed): gym.get_actor_joint_dict
+    m.unmodelled_geoms = skipped
+    if skipped:
+        import warnings
+        warnings.warn(f"{name}: {len(skipped)} collision geometr{'y' if len(skipped) == 1 else 'ies'} without a primitive (meshes) skipped -- "
+                      f"{', '.join(skipped[:6])}{' ...' if len(skipped) > 6 else ''}: those bodies do not collide through them; "
+                      "their mass properties, where the asset gives none, come from the volume the mesh encloses (DESIGN.md section 7)", UnmodelledGeometryWarning, stacklevel=3)
     m.body_link = np.array(bodies["link"], dtype=np.int32)
     m.body_pos, m.body_quat = np.array(bodies["pos"]), np.array(bodies["quat"])
 

@@ -8,6 +8,7 @@ body list.  A link with a mass but no <inertia> (cartpole.urdf:34-36,55-58) take
 its collision primitives scaled to that mass; a link with no <inertial> takes
 AssetOptions.density over its collision primitives.
 """
+import os
 import xml.etree.ElementTree as ET
 import numpy as np
 
@@ -25,6 +26,19 @@ def _origin(e):
     if o is None:
         return np.zeros(3), np.eye(3)
     return _f(o.attrib.get("xyz"), 3), rot.rpy_to_mat(_f(o.attrib.get("rpy"), 3))
+
+
+def _resolve_mesh(urdf_path, filename):
+    """`package://<pkg>/rest` or a relative path -> an existing file, searched from the URDF's directory upwards (the reference keeps
+    its packages next to each other under assets/urdf); None when it cannot be found."""
+    rest = filename.split("://", 1)[1] if "://" in filename else filename
+    d = os.path.dirname(os.path.abspath(urdf_path))
+    for _ in range(6):
+        for cand in (os.path.join(d, rest), os.path.join(d, rest.split("/", 1)[1]) if "/" in rest else None):
+            if cand and os.path.isfile(cand):
+                return cand
+        d = os.path.dirname(d)
+    return None
 
 
 def load_urdf(path, opts: BuildOptions = None, name=None):
@@ -55,7 +69,21 @@ def load_urdf(path, opts: BuildOptions = None, name=None):
                 c = ge.find("cylinder").attrib
                 g = IRGeom("", GEOM_CYLINDER, gpos, gR, np.array([float(c["radius"]), 0.5 * float(c["length"])]))
             else:
-                continue  # mesh collision: not a primitive
+                # mesh collision: not a primitive -- recorded, announced by build_model.  Its MASS is kept:
+                # links without <inertial> get density x the volume the mesh encloses (what the closed importer does for them)
+                me = ge.find("mesh")
+                b.skipped_geoms.append(os.path.basename(me.attrib.get("filename", "mesh")) if me is not None else "unknown")
+                mp = _resolve_mesh(path, me.attrib.get("filename", "")) if me is not None else None
+                if mp is not None and mp.lower().endswith(".obj"):
+                    from .mesh import load_obj, mass_properties
+                    try:
+                        V, F = load_obj(mp)
+                        V = V * (_f(me.attrib["scale"]) if "scale" in me.attrib else 1.0)
+                        vol, com, I = mass_properties(V, F)
+                        b.extra_parts.append((opts.density * vol, gpos + gR @ com, opts.density * (gR @ I @ gR.T)))
+                    except ValueError:
+                        pass
+                continue
             g.density = opts.density
             g.name = f"{lname}_col{len(b.geoms)}"
             b.geoms.append(g)
@@ -85,9 +113,10 @@ def load_urdf(path, opts: BuildOptions = None, name=None):
                     b.inertial = (mass, ipos, I * (mass / M))
                 else:
                     b.inertial = (mass, ipos, np.eye(3) * 1e-6 * mass)
-        elif not b.geoms:
+        elif not b.geoms and not b.extra_parts:
             b.inertial = (0.0, np.zeros(3), np.zeros((3, 3)))
         if joint_elem is not None:
+            b.parent_joint = joint_elem.attrib.get("name", "")
             jt = joint_elem.attrib["type"]
             if jt in ("revolute", "continuous", "prismatic"):
                 lim = joint_elem.find("limit")

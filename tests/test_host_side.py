@@ -315,3 +315,45 @@ def test_train_launcher_hyperparameters_are_the_reference_yaml():
         assert str(hp["epochs"]) in c["max_epochs"] and c["gamma"] == 0.99 and c["tau"] == 0.95 and c["e_clip"] == 0.2
         t = yaml.safe_load(open(os.path.join(REFERENCE, "isaacgymenvs", "cfg", "task", task + ".yaml")))
         assert str(hp["num_envs"]) in str(t["env"]["numEnvs"])
+
+
+# ---------------------------------------------------------------------------------------------
+# collision meshes: mass properties of the enclosed volume (importer/mesh.py), skipped contact announced
+def test_mesh_mass_properties_are_those_of_the_enclosed_solid(tmp_path):
+    from isaacgymenvs_b200.importer.mesh import load_obj, mass_properties
+    from isaacgymenvs_b200.importer import rot
+    h, c0 = np.array([1.0, 2.0, 3.0]), np.array([0.3, -0.2, 0.5])
+    R = rot.quat_to_mat(np.array([0.2, -0.1, 0.3, 0.9]) / np.linalg.norm([0.2, -0.1, 0.3, 0.9]))
+    corners = np.array([[sx, sy, sz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)], float) * h
+    ix = lambda sx, sy, sz: (0 if sx < 0 else 4) + (0 if sy < 0 else 2) + (0 if sz < 0 else 1)
+    quads = [[ix(1, -1, -1), ix(1, 1, -1), ix(1, 1, 1), ix(1, -1, 1)], [ix(-1, -1, -1), ix(-1, -1, 1), ix(-1, 1, 1), ix(-1, 1, -1)],
+             [ix(-1, 1, -1), ix(-1, 1, 1), ix(1, 1, 1), ix(1, 1, -1)], [ix(-1, -1, -1), ix(1, -1, -1), ix(1, -1, 1), ix(-1, -1, 1)],
+             [ix(-1, -1, 1), ix(1, -1, 1), ix(1, 1, 1), ix(-1, 1, 1)], [ix(-1, -1, -1), ix(-1, 1, -1), ix(1, 1, -1), ix(1, -1, -1)]]
+    V = corners @ R.T + c0
+    p = tmp_path / "box.obj"
+    with open(p, "w") as f:                                   # quads, 1-based, with normal indices: what Meshlab writes
+        f.write("# test\n" + "".join(f"v {x} {y} {z}\n" for x, y, z in V) + "".join("f " + " ".join(f"{i + 1}//{i + 1}" for i in q) + "\n" for q in quads))
+    Vr, F = load_obj(str(p))
+    assert F.shape == (12, 3)
+    vol, com, I = mass_properties(Vr, F)
+    Ibox = 48.0 / 12.0 * np.diag([16 + 36, 4 + 36, 4 + 16.0])
+    assert vol == pytest.approx(48.0, rel=1e-12) and np.allclose(com, c0, atol=1e-12) and np.allclose(I, R @ Ibox @ R.T, atol=1e-9)
+    vol2, com2, I2 = mass_properties(Vr, F[:, ::-1])          # inward-facing triangles: same solid
+    assert vol2 == pytest.approx(48.0) and np.allclose(com2, c0) and np.allclose(I2, I)
+    with pytest.raises(ValueError):
+        mass_properties(np.zeros((3, 3)), np.array([[0, 1, 2]]))
+
+
+@needs_reference
+def test_franka_links_get_their_mass_from_the_collision_meshes():
+    """franka_panda_gripper.urdf has no <inertial>: density x mesh volume (AssetOptions.density 1000) must give a ~20 kg arm, and
+    the skipped mesh CONTACT is announced, not silent."""
+    import warnings
+    from isaacgymenvs_b200.importer.urdf import load_urdf
+    from isaacgymenvs_b200.importer.model import BuildOptions, UnmodelledGeometryWarning
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        m = load_urdf(os.path.join(REFERENCE, "assets/urdf/franka_description/robots/franka_panda_gripper.urdf"), BuildOptions(fix_base_link=True))
+    assert sum(issubclass(x.category, UnmodelledGeometryWarning) for x in w) == 1
+    assert 15.0 < m.total_mass() < 25.0 and (m.mass[:8] > 1.0).all() and (m.inertia[1:8, :3] > 1e-3).all()
+    assert m.body_joint_names[8] == "panda_hand_joint" and m.body_names[8] == "panda_hand" and m.ndof == 9

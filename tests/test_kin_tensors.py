@@ -14,7 +14,7 @@ from oracle.oracle import OracleSim
 from tests import rnea_np
 from tests.test_oracle_physics import random_state
 
-MODELS = ["cartpole", "ant", "humanoid", "anymal", "shadow_hand"]
+MODELS = ["cartpole", "ant", "humanoid", "anymal", "shadow_hand", "franka"]
 
 
 def _states(m, n, seed):
@@ -281,3 +281,44 @@ def test_mass_matrix_is_the_inertia_the_aba_step_inverts(name):
         rhs = np.r_[np.zeros(nb), np.clip(tau, -m.effort[1:], m.effort[1:]) - m.stiffness[1:] * dof[:, 0]]
         res = A @ acc - rhs
         assert np.abs(res).max() < 1e-9 * max(1.0, np.abs(rhs).max()), (name, trial, np.abs(res).max())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the reference's indexing idiom for the operational-space controller (franka_cube_stack.py:388-394, 600-627) on the Franka itself
+from tests.conftest import needs_reference, REFERENCE
+
+
+@needs_reference
+def test_franka_jacobian_is_indexed_by_joint_as_the_reference_does():
+    """`hand_joint_index = gym.get_actor_joint_dict(env, franka)['panda_hand_joint']; j_eef = jacobian[:, hand_joint_index, :, :7]`:
+    with one joint per non-root body the joint index addresses the hand body's row of the fixed-base Jacobian.  Checked on the
+    Franka URDF (mesh collisions skipped with a warning: kinematics and inertias come from <inertial>): J_eef qd = the hand
+    body's twist, and the task-space inertia (J M^-1 J^T)^-1 the controller forms is symmetric positive definite."""
+    import warnings
+    from isaacgymenvs_b200.importer.urdf import load_urdf
+    from isaacgymenvs_b200.importer.model import BuildOptions, UnmodelledGeometryWarning
+    from isaacgymenvs_b200.compat import gymapi
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        m = load_urdf(os.path.join(REFERENCE, "assets/urdf/franka_description/robots/franka_panda_gripper.urdf"), BuildOptions(fix_base_link=True))
+    assert any(issubclass(x.category, UnmodelledGeometryWarning) for x in w) and len(m.unmodelled_geoms) == 11
+    gym = gymapi.acquire_gym()
+    asset = gymapi._Asset(m, gymapi.AssetOptions())
+    jd = gym.get_asset_joint_dict(asset)
+    assert gym.get_asset_joint_count(asset) == m.nb - 1 and jd["panda_joint1"] == 0
+    hand = jd["panda_hand_joint"]
+    assert m.body_names[hand + 1] == "panda_hand"
+    orc = OracleSim(m, 0.0166, 2)
+    root, dof = _states(m, 16, 8)
+    J, M = orc.jacobian(root, dof), orc.mass_matrix(root, dof)
+    Jh, Mh = _host_tensors(m, root, dof)                       # the kernel's arithmetic, on the CPU
+    assert np.abs(Jh - J).max() < J_TOL and np.abs(Mh - M).max() < M_RTOL * np.abs(M).max()
+    j_eef = J[:, hand, :, :7]                                   # (N, 6, 7) as franka_cube_stack.py:391
+    tw = np.einsum("nrc,nc->nr", j_eef, dof[:, :7, 1])
+    dof7 = dof.copy(); dof7[:, 7:, 1] = 0                       # the arm's seven joints are what moves the hand
+    bs = orc.body_states(root, dof7)
+    assert np.abs(tw[:, :3] - bs[:, hand + 1, 7:10]).max() < 1e-10 and np.abs(tw[:, 3:] - bs[:, hand + 1, 10:13]).max() < 1e-10
+    mm = M[:, :7, :7]
+    m_eef_inv = j_eef @ np.linalg.inv(mm) @ j_eef.transpose(0, 2, 1)           # :603-604; the controller inverts it (:605)
+    assert np.abs(m_eef_inv - m_eef_inv.transpose(0, 2, 1)).max() < 1e-9 * np.abs(m_eef_inv).max()
+    assert np.linalg.eigvalsh(0.5 * (m_eef_inv + m_eef_inv.transpose(0, 2, 1))).min() > 0 and np.isfinite(np.linalg.inv(m_eef_inv)).all()
