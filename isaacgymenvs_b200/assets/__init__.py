@@ -67,5 +67,12 @@ def load_asset_file(asset_root, asset_file, opts: BuildOptions = None) -> Model:
     norm = os.path.normpath(path).replace("\\", "/")
     for key, blob in KNOWN.items():
         if norm.endswith(key):
-            return _apply_options(load_compiled(blob), opts, path)
+            m = _apply_options(load_compiled(blob), opts, path)
+            skipped = getattr(m, "unmodelled_geoms", None)
+            if skipped:          # the XML import announces collision meshes it has no primitive for; so does the blob made from it
+                import warnings
+                from ..importer.model import UnmodelledGeometryWarning
+                warnings.warn(f"{blob}: {len(skipped)} collision mesh(es) of the asset are not modelled as contact geometry -- "
+                              f"{', '.join(skipped[:6])}{' ...' if len(skipped) > 6 else ''} (DESIGN.md section 7)", UnmodelledGeometryWarning, stacklevel=2)
+            return m
     raise FileNotFoundError(f"asset {path} not found and no compiled model is registered for it")

@@ -357,3 +357,25 @@ def test_franka_links_get_their_mass_from_the_collision_meshes():
     assert sum(issubclass(x.category, UnmodelledGeometryWarning) for x in w) == 1
     assert 15.0 < m.total_mass() < 25.0 and (m.mass[:8] > 1.0).all() and (m.inertia[1:8, :3] > 1e-3).all()
     assert m.body_joint_names[8] == "panda_hand_joint" and m.body_names[8] == "panda_hand" and m.ndof == 9
+
+
+def test_compiled_models_carry_joint_names_and_announce_skipped_meshes():
+    """what the GPU box sees (no XML there): the blobs know their joint names (gym.get_actor_joint_dict) and the fallback loader
+    repeats the importer's warning about collision meshes without a contact model"""
+    import warnings
+    from isaacgymenvs_b200.assets import load_compiled, load_asset_file, KNOWN
+    from isaacgymenvs_b200.importer.model import BuildOptions, UnmodelledGeometryWarning
+    from isaacgymenvs_b200.compat import gymapi
+    gym = gymapi.acquire_gym()
+    for name in set(KNOWN.values()):
+        m = load_compiled(name)
+        assert len(m.body_joint_names) == m.nb and m.body_joint_names[0] == ""
+        jd = gym.get_asset_joint_dict(gymapi._Asset(m, gymapi.AssetOptions()))
+        assert all(m.body_joint_names[i + 1] == n for n, i in jd.items())
+    assert gym.get_asset_joint_dict(gymapi._Asset(load_compiled("franka"), gymapi.AssetOptions()))["panda_hand_joint"] == 7
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        load_asset_file("/no/such/checkout/assets", "urdf/franka_description/robots/franka_panda_gripper.urdf", BuildOptions(fix_base_link=True))
+        load_asset_file("/no/such/checkout/assets", "mjcf/nv_ant.xml", BuildOptions())
+    hits = [x for x in w if issubclass(x.category, UnmodelledGeometryWarning)]
+    assert len(hits) == 1 and "franka" in str(hits[0].message)
