@@ -255,6 +255,30 @@ class Gym:
                             capsule_mid_spheres=1 if o.fix_base_link else 0)
         return _Asset(load_asset_file(root, file, opts), copy.copy(o))   # the caller may go on mutating `options` (shadow_hand.py:279-282)
 
+    # procedural single-body assets (ball_balance.py:277 create_sphere, franka_cube_stack.py:223-245 create_box): one primitive,
+    # mass = options.density x volume; usable as the free object of an env (the engine's rounded box covers all three)
+    def _primitive(self, name, gtype, size, options):
+        from ..importer.model import IRBody, IRGeom, build_model
+        o = options or AssetOptions()
+        g = IRGeom(name, gtype, np.zeros(3), np.eye(3), np.asarray(size, dtype=np.float64))
+        g.density = float(o.density)
+        body = IRBody(name=name, pos=np.zeros(3), R=np.eye(3), geoms=[g])
+        opts = BuildOptions(fix_base_link=o.fix_base_link, density=o.density, angular_damping=o.angular_damping, linear_damping=o.linear_damping,
+                            max_angular_velocity=o.max_angular_velocity, disable_gravity=o.disable_gravity)
+        return _Asset(build_model(name, body, has_free_root=not o.fix_base_link, opts=opts), copy.copy(o))
+
+    def create_box(self, sim, width, height, depth, options=None):
+        from ..importer.model import GEOM_BOX
+        return self._primitive("box", GEOM_BOX, [0.5 * width, 0.5 * height, 0.5 * depth], options)
+
+    def create_sphere(self, sim, radius, options=None):
+        from ..importer.model import GEOM_SPHERE
+        return self._primitive("sphere", GEOM_SPHERE, [radius], options)
+
+    def create_capsule(self, sim, radius, length, options=None):        # axis along x in gymapi; the object's frame is free, ours is z
+        from ..importer.model import GEOM_CAPSULE
+        return self._primitive("capsule", GEOM_CAPSULE, [radius, 0.5 * length], options)
+
     def get_asset_dof_count(self, asset):
         return asset.model.ndof
 

@@ -138,6 +138,39 @@ def test_unmodified_reference_shadow_hand_runs_on_the_shim(compat_cpu):
 
 
 @needs_reference
+def test_procedural_primitive_assets_become_the_free_object(compat_cpu):
+    """gym.create_sphere / create_box / create_capsule (ball_balance.py:277, franka_cube_stack.py:223-245): one primitive, mass =
+    density x volume, and as the second actor of an env the engine's rounded box (sphere: a point + radius)."""
+    from isaacgym import gymapi
+    import math
+    gym = gymapi.acquire_gym()
+    sp = gymapi.SimParams(); sp.dt, sp.substeps = 0.01, 2
+    sim = gym.create_sim(0, -1, gymapi.SIM_PHYSX, sp)
+    gym.add_ground(sim, gymapi.PlaneParams())
+    ao = gymapi.AssetOptions(); ao.density = 200.0
+    ball = gym.create_sphere(sim, 0.1, ao)
+    assert gym.get_asset_rigid_body_count(ball) == 1 and gym.get_asset_dof_count(ball) == 0
+    assert abs(float(ball.model.mass[0]) - 200.0 * 4 / 3 * math.pi * 1e-3) < 1e-9
+    box = gym.create_box(sim, 0.2, 0.4, 0.6, ao)
+    assert abs(float(box.model.mass[0]) - 200.0 * 0.048) < 1e-9 and [round(float(v), 6) for v in box.model.geom_size[0]] == [0.1, 0.2, 0.3]
+    cap = gym.create_capsule(sim, 0.05, 0.4, ao)
+    assert abs(float(cap.model.mass[0]) - 200.0 * (math.pi * 0.05 ** 2 * 0.4 + 4 / 3 * math.pi * 0.05 ** 3)) < 1e-9
+    # the ball as the free object of a two-actor env (articulation + ball): cartpole stands in for the articulation
+    copt = gymapi.AssetOptions(); copt.fix_base_link = True; copt.angular_damping = 0.5
+    cart = gym.load_asset(sim, os.path.join(REFERENCE, "assets"), "urdf/cartpole.urdf", copt)
+    for i in range(2):
+        e = gym.create_env(sim, gymapi.Vec3(-1, -1, 0), gymapi.Vec3(1, 1, 1), 2)
+        gym.create_actor(e, cart, gymapi.Transform(gymapi.Vec3(0, 0, 2.0)), "cartpole", i, 1, 0)
+        gym.create_actor(e, ball, gymapi.Transform(gymapi.Vec3(0.5, 0, 1.0)), "ball", i, 0, 0)
+    gym.prepare_sim(sim)
+    ext = sim.engine.ext
+    assert ext.actors_per_env == 2 and ext.obj_actor == 1 and [float(v) for v in ext.obj_half] == [0.0, 0.0, 0.0]
+    assert abs(ext.obj_round - 0.1) < 1e-7 and abs(ext.obj_mass - float(ball.model.mass[0])) < 1e-6 and ext.obj_max_angular_velocity == 64.0
+    rs = sim.engine.root_state.view(2, 2, 13)
+    assert torch.allclose(rs[:, 1, 0:3], torch.tensor([0.5, 0.0, 1.0]))
+
+
+@needs_reference
 def test_name_maps_and_small_accessors_of_the_shim(compat_cpu):
     """the dictionary / count accessors other reference tasks use around the tensor API (franka_cube_stack.py:391, allegro_hand.py,
     ant.py:307-321 debug lines): body / DOF order = the tensors' order"""
