@@ -271,6 +271,9 @@ typedef struct {
      * forceDecay ^ (dt / forceDecayInterval); a new force N(0,1)^3 * object mass * force_scale is drawn when U < random_force_prob,
      * random_force_prob = exp(force_logp_span * U' + force_logp1) redrawn on reset (force_logp_span = log p0 - log p1) */
     float force_scale, force_decay_factor, force_logp_span, force_logp1;
+    /* objectType pen (shadow_hand.py:626-629): reset_idx poses the object with randomize_rotation_pen (:810-813: about x by
+     * pi/2 + 0.3 rand0, then about z by pi rand0) instead of randomize_rotation; 0 = block / egg */
+    int32_t object_is_pen, pad2;
 } b2g_hand_params;
 
 typedef struct b2g_sim b2g_sim;

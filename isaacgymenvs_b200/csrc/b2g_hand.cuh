@@ -37,6 +37,19 @@ __device__ __forceinline__ void t_randomize_rotation(float rand0, float rand1, f
     t_quat_axis(rand1 * 3.1415927f, 1, qy);
     t_quat_mul(qx, qy, q);
 }
+// randomize_rotation_pen, shadow_hand.py:810-813 (called with max_angle = tensor(0.3), :627): quat_from_angle_axis(0.5 pi + rand0 *
+// max_angle, x) * quat_from_angle_axis(rand0 pi, z); 0.5 * np.pi enters the float32 tensor arithmetic as 1.5707964
+__device__ __forceinline__ void t_randomize_rotation_pen(float rand0, float q[4]) {
+    float qx[4], qz[4];
+    t_quat_axis(1.5707964f + rand0 * 0.3f, 0, qx);
+    t_quat_axis(rand0 * 3.1415927f, 2, qz);
+    t_quat_mul(qx, qz, q);
+}
+// the object's orientation at reset_idx (:625-629)
+__device__ __forceinline__ void t_object_reset_rotation(const b2g_hand_params &P, float rand0, float rand1, float q[4]) {
+    if (P.object_is_pen) t_randomize_rotation_pen(rand0, q);
+    else t_randomize_rotation(rand0, rand1, q);
+}
 // torch_rand_float(-1, 1): (upper - lower) * rand + lower
 __device__ __forceinline__ float hand_rand(uint64_t seed, uint32_t gid, uint32_t count, int idx) {
     return 2.0f * reset_uniform(seed, gid, count, idx) + (-1.0f);
@@ -141,7 +154,7 @@ __global__ void __launch_bounds__(BLOCK) hand_step_kernel(const DevModel *__rest
         ob.p[0] = init_rows[13] + P.reset_position_noise * rx;
         ob.p[1] = init_rows[14] + P.reset_position_noise * ry;
         ob.p[2] = init_rows[15] + P.reset_position_noise * rz;
-        t_randomize_rotation(hand_rand(P.seed, gid, count, 3), hand_rand(P.seed, gid, count, 4), ob.q);
+        t_object_reset_rotation(P, hand_rand(P.seed, gid, count, 3), hand_rand(P.seed, gid, count, 4), ob.q);
 #pragma unroll
         for (int c = 0; c < 3; c++) { ob.v[c] = 0.f; ob.w[c] = 0.f; }
         progress = 0; successes = 0.f;

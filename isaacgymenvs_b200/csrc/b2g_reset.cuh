@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(128) hand_reset_kernel(Buffers B, const __grid
     rows[13] = init_rows[13] + P.reset_position_noise * hand_rand(P.seed, gid, count, 0);
     rows[14] = init_rows[14] + P.reset_position_noise * hand_rand(P.seed, gid, count, 1);
     rows[15] = init_rows[15] + P.reset_position_noise * hand_rand(P.seed, gid, count, 2);
-    t_randomize_rotation(hand_rand(P.seed, gid, count, 3), hand_rand(P.seed, gid, count, 4), oq);
+    t_object_reset_rotation(P, hand_rand(P.seed, gid, count, 3), hand_rand(P.seed, gid, count, 4), oq);
     for (int c = 0; c < 4; c++) rows[16 + c] = oq[c];
     for (int c = 7; c < 13; c++) rows[13 + c] = 0.f;
     float2 *const dof = (float2 *)B.p[B2G_T_DOF_STATE] + (size_t)e * nd;

@@ -42,7 +42,8 @@ class CHandParams(C.Structure):
                 ("dof_lower", C.c_float * 32), ("dof_upper", C.c_float * 32), ("dof_default_pos", C.c_float * 32),
                 ("dof_default_vel", C.c_float * 32), ("fingertip_body", C.c_int32 * 5), ("num_states", C.c_int32),
                 ("seed", C.c_uint64), ("env_id_offset", C.c_int32), ("pad1", C.c_int32),
-                ("force_scale", C.c_float), ("force_decay_factor", C.c_float), ("force_logp_span", C.c_float), ("force_logp1", C.c_float)]
+                ("force_scale", C.c_float), ("force_decay_factor", C.c_float), ("force_logp_span", C.c_float), ("force_logp1", C.c_float),
+                ("object_is_pen", C.c_int32), ("pad2", C.c_int32)]
 
 
 class CAnymalParams(C.Structure):

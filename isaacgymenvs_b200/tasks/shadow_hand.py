@@ -115,7 +115,7 @@ class ShadowHand(VecTask):
         dev, N = self.device, self.num_envs
         # start poses, shadow_hand.py:299-317
         hand_p = np.array([0.0, 0.0, 0.5]); hand_q = np.asarray(model.default_root_quat, dtype=np.float64)
-        obj_p = hand_p + np.array([0.0, -0.39, 0.10])
+        obj_p = hand_p + np.array([0.0, -0.39, 0.02 if self.object_type == "pen" else 0.10])               # :312-318
         self.goal_displacement_tensor = torch.tensor([-0.2, -0.06, 0.12], device=dev)
         rs = sim.root_state.view(N, 3, 13)
         rs[:, :, 6] = 1.0
@@ -233,6 +233,7 @@ class ShadowHand(VecTask):
         for f in range(5):
             p.fingertip_body[f] = int(self.fingertip_handles_np[f])
         # random object forces (:700-709): the constants in the float32 arithmetic of the reference's tensors
+        p.object_is_pen = int(self.object_type == "pen")            # reset_idx poses the pen with randomize_rotation_pen (:626-629)
         p.force_scale = float(self.force_scale)
         p.force_decay_factor = float(torch.pow(self.force_decay, self.dt / self.force_decay_interval))
         p.force_logp_span = float(torch.log(self.force_prob_range[0]) - torch.log(self.force_prob_range[1]))

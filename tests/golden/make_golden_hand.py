@@ -66,14 +66,14 @@ class Gym:
         t.rigid_body_states = torch.tensor(full)
 
 
-def make_case(sh, g, n, obs_type, relative, mcs, mavg, fall_penalty, orc, model, act_idx, fingertip_handles, force=None):
+def make_case(sh, g, n, obs_type, relative, mcs, mavg, fall_penalty, orc, model, act_idx, fingertip_handles, force=None, object_type="block"):
     """force: None, or dict(scale, prob_range, obj_mass) -- random forces on the object (shadow_hand.py:700-709); the
     reference's torch.rand / torch.randn draws are then played by the engine's counter-based stream as well."""
     from oracle import tasks_np
     D = model.ndof
     t = object.__new__(sh.ShadowHand)
     t.num_envs, t.device, t.randomize, t.num_shadow_hand_dofs, t.num_actions = n, "cpu", False, D, 20
-    t.up_axis_idx, t.object_type, t.obs_type, t.asymmetric_obs = 2, "block", obs_type, False
+    t.up_axis_idx, t.object_type, t.obs_type, t.asymmetric_obs = 2, object_type, obs_type, False
     t.num_fingertips, t.viewer, t.debug_viz, t.print_success_stat = 5, None, False, False
     t.sim = None
     lo = torch.tensor(model.lower[1:], dtype=torch.float); hi = torch.tensor(model.upper[1:], dtype=torch.float)
@@ -288,8 +288,33 @@ def main_force():
     print("wrote shadow_hand_force.npz; new forces drawn in", int((out["obj_force"] != inp["obj_force"] * np.float32(0.99 ** (0.01667 / 0.08))).any(1).sum()), "of 256 envs")
 
 
+def main_pen():
+    """Case "p": objectType pen -- reset_idx poses the object with randomize_rotation_pen (:626-629) and compute_reward passes
+    ignore_z_rot (:421, :758-759: twice the success tolerance) -> tests/golden/shadow_hand_pen.npz (128 envs)."""
+    from tests.hand_common import hand_setup, DT, SUBSTEPS, G
+    from oracle.oracle import OracleSim
+    tju, sh = load()
+    model, obj, tendons = hand_setup()
+    orc = OracleSim(model, DT, SUBSTEPS, G, obj=obj, tendons=tendons, tendon_k=30.0, tendon_d=0.1)
+    names = list(model.dof_names)
+    act_idx = [names.index(j) for j in model.actuator_joint]
+    ft = [int(b) for b in model.sensor_body]
+    g = torch.Generator().manual_seed(15)
+    inp, out = make_case(sh, g, 128, "full_state", relative=False, mcs=0, mavg=1.0, fall_penalty=0.0, orc=orc, model=model,
+                         act_idx=act_idx, fingertip_handles=ft, object_type="pen")
+    blob = {"seed": np.int64(SEED), "actuated": np.array(act_idx, np.int32), "fingertips": np.array(ft, np.int32)}
+    for k, v in inp.items():
+        blob[f"p_in_{k}"] = v
+    for k, v in out.items():
+        blob[f"p_out_{k}"] = v
+    np.savez_compressed(os.path.join(OUT, "shadow_hand_pen.npz"), **blob)
+    print("wrote shadow_hand_pen.npz; resets", int(inp["reset"].sum()), "successes counted", int((out["successes"] - inp["successes"] * (inp["reset"] == 0)).sum()))
+
+
 if __name__ == "__main__":
-    if "--force" in sys.argv:
+    if "--pen" in sys.argv:
+        main_pen()
+    elif "--force" in sys.argv:
         main_force()
     else:
         main()

@@ -55,7 +55,9 @@ def settled_states(n, steps, seed, precision="f64", threads=8, obj_name=None):
 CASES = {"a": dict(relative=False, mcs=0, mavg=1.0, fall_penalty=0.0), "b": dict(relative=True, mcs=50, mavg=1.0, fall_penalty=-50.0),
          "c": dict(relative=False, mcs=0, mavg=0.3, fall_penalty=0.0),
          # tests/golden/shadow_hand_force.npz (make_golden_hand.py --force): random forces on the object, shadow_hand.py:700-709
-         "f": dict(relative=False, mcs=0, mavg=1.0, fall_penalty=0.0)}
+         "f": dict(relative=False, mcs=0, mavg=1.0, fall_penalty=0.0),
+         # tests/golden/shadow_hand_pen.npz (make_golden_hand.py --pen): objectType pen -- randomize_rotation_pen at reset, ignore_z_rot in the reward
+         "p": dict(relative=False, mcs=0, mavg=1.0, fall_penalty=0.0)}
 
 
 def force_constants(gold):
@@ -92,4 +94,6 @@ def golden_case(gold, case, obs_type="full_state"):
              max_episode_length=600.0, av_factor=0.1)
     if case == "f":
         P.update(force_constants(gold))
+    if case == "p":
+        P.update(object_type="pen", success_tolerance=0.2)      # compute_hand_reward doubles it when ignore_z_rot (:758-759)
     return st, P, g("actions")

@@ -117,11 +117,11 @@ def test_anymal_terrain_restatement_matches_reference_methods():
 
 # ---------------------------------------------------------------------------------------------
 # ShadowHand: numpy restatement against the reference's own methods (tests/golden/shadow_hand.npz)
-@pytest.mark.parametrize("case", ["a", "b", "c", "f"])
+@pytest.mark.parametrize("case", ["a", "b", "c", "f", "p"])
 def test_hand_step_restatement_matches_reference(case):
     from tests.hand_common import golden_case, hand_setup, DT, SUBSTEPS, G as GRAV
     from oracle.oracle import OracleSim
-    gold = np.load(os.path.join(G, "shadow_hand_force.npz" if case == "f" else "shadow_hand.npz"))
+    gold = np.load(os.path.join(G, {"f": "shadow_hand_force.npz", "p": "shadow_hand_pen.npz"}.get(case, "shadow_hand.npz")))
     obs_types = ["full_state", "full", "full_no_vel", "openai"] if case == "a" else ["full_state"]
     m, obj, tendons = hand_setup()
     orc = OracleSim(m, DT, SUBSTEPS, GRAV, obj=obj, tendons=tendons)
